@@ -1,0 +1,256 @@
+/*
+ * mitsubaer_b200.h — C ABI of libmitsubaer_b200.so
+ *
+ * The drop-in boundary for MitsubaER's refractive-radiative-transfer hot path
+ * (SURVEY.md §8b).  Plain pointers and sizes only; no torch / CUDA types in the
+ * signatures (a CUDA stream is passed as `void *`).  Every entry point names the
+ * reference interface it replaces (paths relative to the MitsubaER tree).
+ *
+ * Conventions
+ *   - all functions return MER_OK (0) or a MER_ERR_* code; the message is
+ *     available from mer_last_error() (thread local).  The Mitsuba-side shim
+ *     turns a non-zero status into Log(EError, ...) (src/libcore/logger.cpp:100-147).
+ *   - points / vectors are packed float[n][3]; spectra are float[3] (SPECTRUM_SAMPLES=3).
+ *   - `*_batch` entry points take HOST buffers and do the H2D/D2H copies themselves;
+ *     `*_device` entry points take DEVICE pointers on the handle's GPU and enqueue
+ *     on `stream` without synchronising.
+ *   - handles own all device allocations; they are immutable after creation and may
+ *     be used concurrently from several host threads (like Mitsuba's const plugins).
+ *   - there is NO CPU fallback: every compute entry point fails with
+ *     MER_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef MITSUBAER_B200_H
+#define MITSUBAER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MER_ABI_VERSION 1
+
+enum mer_status {
+    MER_OK = 0,
+    MER_ERR_INVALID = 1,     /* bad argument / descriptor */
+    MER_ERR_CUDA = 2,        /* CUDA runtime failure or no usable device */
+    MER_ERR_UNSUPPORTED = 3, /* feature of the reference that this path does not carry */
+    MER_ERR_OOM = 4
+};
+
+/* ------------------------------------------------------------------ volumes */
+
+/* .vol grid description: src/volume/splinevolume.cpp:204-273 (header fields),
+ * `toWorld` / `min` / `max` properties :87-98.  Data is x-fastest float32,
+ * data[(z*yres + y)*xres + x]; grid points sit ON the bbox. */
+typedef struct mer_volume_desc {
+    int32_t res[3];
+    float bbox_min[3];
+    float bbox_max[3];
+    int32_t has_transform;     /* 0: world == volume space */
+    float world_to_volume[12]; /* row-major 3x4 affine (inverse of `toWorld`) */
+} mer_volume_desc;
+
+/* RIF fetch modes */
+enum mer_rif_mode {
+    MER_RIF_TRICUBIC = 0,        /* the reference's prefiltered cubic B-spline (parity mode) */
+    MER_RIF_TRILINEAR_PACKED = 1 /* float4 {n, dn/dx, dn/dy, dn/dz} per voxel, trilinear (fast mode) */
+};
+
+enum mer_eval_what { MER_EVAL_VALUE = 0, MER_EVAL_GRADIENT = 1, MER_EVAL_VALUE_AND_GRADIENT = 2 };
+
+typedef struct mer_rif mer_rif;   /* <volume type="splinevolume"> : SplineDataSource */
+typedef struct mer_grid mer_grid; /* <volume type="gridvolume">   : GridDataSource (density) */
+
+/* SplineDataSource ctor + loadFromFile + Spline<3>::build (splinevolume.cpp:87-111,
+ * 204-317; basisspline.h:124-138, 865-890).  `data` is a HOST pointer to
+ * res[0]*res[1]*res[2] float32; upload + IIR prefilter run on `device`. */
+int mer_rif_create(int device, const mer_volume_desc *desc, const float *data, int mode, mer_rif **out);
+/* same, `data` already resident on `device` (not modified, may be freed after return) */
+int mer_rif_create_device(int device, const mer_volume_desc *desc, const float *data_dev, int mode,
+                          mer_rif **out);
+/* splinevolume.cpp:204-317 incl. the 48-byte header parse */
+int mer_rif_create_from_file(int device, const char *vol_path, const mer_volume_desc *override_or_null,
+                             int mode, mer_rif **out);
+void mer_rif_destroy(mer_rif *rif);
+/* prefiltered B-spline coefficients, same layout as the input (basisspline.h:865-890 `coeff`) */
+int mer_rif_coefficients(const mer_rif *rif, float *coeff_out_host);
+int mer_rif_desc(const mer_rif *rif, mer_volume_desc *out, int *mode_out);
+/* SplineDataSource::value / gradient / valueAndGradient (splinevolume.cpp:330-360) in the handle's mode */
+int mer_rif_eval_batch(const mer_rif *rif, int what, size_t n, const float *p, float *value_out,
+                       float *grad_out);
+int mer_rif_eval_device(const mer_rif *rif, int what, size_t n, const float *p_dev, float *value_dev,
+                        float *grad_dev, void *stream);
+/* SplineDataSource::insideVolumeLimits (splinevolume.cpp:319-328, limits :280-281) */
+int mer_rif_inside_limits_batch(const mer_rif *rif, size_t n, const float *p, uint8_t *inside_out);
+
+/* GridDataSource ctor + configure (src/volume/gridvolume.cpp:188-199) */
+int mer_grid_create(int device, const mer_volume_desc *desc, const float *data, mer_grid **out);
+int mer_grid_create_device(int device, const mer_volume_desc *desc, const float *data_dev, mer_grid **out);
+int mer_grid_create_from_file(int device, const char *vol_path, const mer_volume_desc *override_or_null,
+                              mer_grid **out);
+void mer_grid_destroy(mer_grid *grid);
+/* GridDataSource::lookupFloat (gridvolume.cpp:337-363) */
+int mer_grid_lookup_batch(const mer_grid *grid, size_t n, const float *p, float *value_out);
+
+/* .vol v3 I/O (mfiles/writeGridToVol.m:1-36, splinevolume.cpp:204-273). */
+int mer_vol_read_header(const char *path, mer_volume_desc *out, int32_t *encoding, int32_t *channels);
+int mer_vol_read_data(const char *path, float *data_out, size_t n_floats);
+int mer_vol_write(const char *path, const mer_volume_desc *desc, const float *data);
+
+/* ------------------------------------------------------------ phase function */
+
+/* HGPhaseFunction::sample (src/phase/hg.cpp:76-98): wi points back along the incoming
+ * ray; xi = sampler->next2D(); returns wo and pdf = eval (hg.cpp:100-105). */
+int mer_hg_sample_batch(int device, float g, size_t n, const float *wi, const float *xi, float *wo_out,
+                        float *pdf_out);
+/* HGPhaseFunction::eval (hg.cpp:107-110) */
+int mer_hg_eval_batch(int device, float g, size_t n, const float *wi, const float *wo, float *value_out);
+
+/* -------------------------------------------------------------------- medium */
+
+enum mer_shape_type {
+    MER_SHAPE_BOX = 0,   /* hackForBox form  (heterogeneousrefractive.cpp:722-726): min<=p<=max */
+    MER_SHAPE_SPHERE = 1 /* hackForSphere    (:714-720): |p-c|^2 < r^2 */
+};
+
+enum mer_strategy { /* heterogeneousrefractive.cpp:194-199 */
+    MER_STRATEGY_BALANCE = 0,
+    MER_STRATEGY_SINGLE = 1,
+    MER_STRATEGY_MANUAL = 2,
+    MER_STRATEGY_MAXIMUM = 3 /* MaxExpDist: MER_ERR_UNSUPPORTED */
+};
+
+/* Properties of <medium type="heterogeneousrefractive"> (heterogeneousrefractive.cpp:201-297)
+ * plus the Medium base class (src/librender/medium.cpp:27-37) and the nested <phase type="hg">. */
+typedef struct mer_medium_desc {
+    float sigma_a[3];
+    float sigma_s[3];
+    float stepsize;               /* `stepsize`, absolute scene units, default 1e-3 */
+    float medium_sampling_weight; /* `mediumSamplingWeight`, -1 => max(max albedo, 0.5) (:239-255) */
+    int32_t strategy;             /* mer_strategy, default balance */
+    int32_t channel;              /* `channel` for strategy single; -1 => smallest sigma_t */
+    float sampling_density;       /* `samplingDensity` for strategy manual */
+    int32_t shape_type;           /* containment predicate (insideShape, :707-739) */
+    float shape[6];               /* box: min xyz, max xyz; sphere: centre xyz, radius */
+    float hg_g;                   /* <phase type="hg"> g */
+    /* optional density grid (new composition): when a grid is attached,
+     * sigma_t(p) = density(p) * density_scale (heterogeneous.cpp:239-242, 613-658),
+     * sigma_s = albedo * sigma_t, sampled by Woodcock tracking ALONG the curved ray. */
+    float density_scale;
+    float albedo[3];
+} mer_medium_desc;
+
+typedef struct mer_medium mer_medium; /* <medium type="heterogeneousrefractive"> */
+
+/* ctor + addChild("rif") + configure (heterogeneousrefractive.cpp:201-297, 366-382, 1177-1193).
+ * `density_or_null` attaches a <volume name="density">.  The medium keeps references to rif / density;
+ * destroy them after the medium. */
+int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer_grid *density_or_null,
+                      mer_medium **out);
+void mer_medium_destroy(mer_medium *medium);
+/* resolved parameters (after the -1 defaults are applied) */
+int mer_medium_resolved(const mer_medium *medium, mer_medium_desc *out, float *sampling_density_out);
+
+/* trace() (heterogeneousrefractive.cpp:671-691): p, v in/out (v = n * dir), dist in;
+ * success (1 = still inside after `dist`), dist_surf, opl (accumulated optical length, starts at 0),
+ * nsteps (er_step calls incl. remainder and step-back) out.  Any output may be NULL. */
+int mer_medium_trace_batch(const mer_medium *medium, size_t n, float *p, float *v, const float *dist,
+                           uint8_t *success_out, float *dist_surf_out, float *opl_out, int32_t *nsteps_out);
+int mer_medium_trace_device(const mer_medium *medium, size_t n, float *p_dev, float *v_dev,
+                            const float *dist_dev, uint8_t *success_dev, float *dist_surf_dev,
+                            float *opl_dev, int32_t *nsteps_dev, void *stream);
+/* traceTillBoundary() (:742-776) */
+int mer_medium_trace_till_boundary_batch(const mer_medium *medium, size_t n, float *p, float *v,
+                                         float *dist_surf_out, float *opl_out, int32_t *nsteps_out);
+
+/* MediumSamplingRecord (include/mitsuba/render/medium.h:33-109) as SoA over a batch */
+typedef struct mer_medium_sampling_records {
+    uint8_t *success;     /* return value of sampleDistance */
+    float *t;             /* [n] */
+    float *p;             /* [n][3] */
+    float *d;             /* [n][3] n-scaled direction at the end of the curved edge */
+    float *optical_length;/* [n] */
+    float *ref_ratio_sq;  /* [n] */
+    float *transmittance; /* [n][3] */
+    float *pdf_success;   /* [n] */
+    float *pdf_failure;   /* [n] */
+    float *sigma_s;       /* [n][3] (valid on success) */
+    int32_t *nsteps;      /* [n] er_step calls */
+} mer_medium_sampling_records;
+
+/* Medium::sampleDistance (include/mitsuba/render/medium.h:130-131;
+ * heterogeneousrefractive.cpp:402-568).  The Sampler is replayed: xi[n][2] holds the two
+ * next1D() draws sampleDistance may consume (distance, balance channel).  Homogeneous
+ * sigma only (the reference's behaviour, R2); any record pointer may be NULL. */
+int mer_medium_sample_distance_batch(const mer_medium *medium, size_t n, const float *ray_o,
+                                     const float *ray_d, const float *ray_mint, const float *xi,
+                                     mer_medium_sampling_records *rec);
+/* Medium::evalTransmittance (heterogeneousrefractive.cpp:393-400) */
+int mer_medium_eval_transmittance_batch(const mer_medium *medium, size_t n, const float *mint,
+                                        const float *maxt, float *transmittance_out);
+
+/* -------------------------------------------------------------- integrator */
+
+enum mer_filter { MER_FILTER_BOX = 0, MER_FILTER_GAUSSIAN = 1 };
+
+/* What the integrator shim extracts from the Scene (sensor, film, rfilter, emitters,
+ * MonteCarloIntegrator properties: src/librender/integrator.cpp:190-225). */
+typedef struct mer_render_desc {
+    int32_t width, height;     /* <film> width/height */
+    int32_t spp_total;         /* sampleCount of the whole render (RNG indexing) */
+    int32_t sample_begin;      /* this call renders samples s = begin, begin+stride, ... < spp_total */
+    int32_t sample_stride;     /* (sample-index sharding across GPUs) */
+    uint64_t seed;
+    float cam_origin[3], cam_target[3], cam_up[3]; /* <lookat> of the perspective sensor */
+    float fov_deg;             /* `fov`, fovAxis = x (src/sensors/perspective.cpp:126-157) */
+    int32_t filter;            /* mer_filter; box radius .5 (rfilters/box.cpp), gaussian stddev .5 */
+    int32_t max_depth;         /* `maxDepth` (-1 = unbounded) */
+    int32_t rr_depth;          /* `rrDepth` (5) */
+    float env_radiance[3];     /* constant environment emitter */
+    int32_t has_quad;          /* optional two-sided quad area emitter */
+    float quad_origin[3], quad_u[3], quad_v[3], quad_radiance[3];
+    int32_t pool_paths;        /* resident path slots (0 => default) */
+    int32_t steps_per_pass;    /* er_steps per path per wavefront pass (0 => default) */
+} mer_render_desc;
+
+typedef struct mer_render_stats {
+    uint64_t samples;        /* camera samples started */
+    uint64_t ray_steps;      /* er_step calls (incl. remainder + step-back) */
+    uint64_t scatter_events; /* real collisions */
+    uint64_t null_collisions;/* Woodcock null collisions */
+    uint64_t boundary_exits;
+    uint64_t nonfinite_dropped; /* samples rejected like ImageBlock::put (imageblock.h:147-152) */
+    uint64_t passes;         /* wavefront passes */
+    uint64_t kernel_launches;
+    float device_ms;         /* CUDA-event time of the render kernels */
+} mer_render_stats;
+
+/* Integrator::render (include/mitsuba/render/integrator.h:61-96) for the eikonal volumetric
+ * path tracer: SamplingIntegrator::renderBlock (src/librender/integrator.cpp:140-190) +
+ * the volpath bounce loop (src/integrators/path/volpath.cpp:84-343) with the curved-ray walk
+ * semantics of libbidir (vertex.cpp:247-279, edge.cpp:26-103) + ImageBlock::put
+ * (include/mitsuba/render/imageblock.h:124-190).
+ * film: width*height*5 float32 [R,G,B,alpha,weight] (Bitmap::ESpectrumAlphaWeight). */
+int mer_render(const mer_medium *medium, const mer_render_desc *desc, float *film_host,
+               mer_render_stats *stats_out);
+/* film_dev is ACCUMULATED into (zero it first); asynchronous except for the pass-count readbacks */
+int mer_render_device(const mer_medium *medium, const mer_render_desc *desc, float *film_dev,
+                      mer_render_stats *stats_out, void *stream);
+/* HDRFilm::develop (src/films/hdrfilm.cpp:527-540): rgb = sum(w*RGB)/sum(w); host buffers */
+int mer_film_develop(int device, int32_t width, int32_t height, const float *film, float *rgb_out);
+
+/* ------------------------------------------------------------------- misc */
+
+const char *mer_last_error(void);
+int mer_abi_version(void);
+/* number of usable sm_100-class devices (0 => every compute call fails) */
+int mer_device_count(void);
+/* total kernels launched by this library in this process (bench.py `gpu_launches`) */
+uint64_t mer_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MITSUBAER_B200_H */

@@ -1,0 +1,327 @@
+"""ctypes front-end of the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+May be imported only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package (mitsubaer_b200/) never imports it.
+
+  * `Oracle(dtype)`  -> oracle/libmer_oracle.so   (restatement of SURVEY.md §8a rows a1-a24,
+                        float or double FLOAT)
+  * `RefSpline(dtype)` -> oracle/_ref/libmer_refspline_{f,d}.so  (the reference's own
+                        include/mitsuba/core/basisspline.h compiled verbatim; rows a1-a4)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+class VolumeDesc(C.Structure):
+    """mirror of mer_volume_desc (include/mitsubaer_b200.h)"""
+    _fields_ = [("res", C.c_int32 * 3), ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
+                ("has_transform", C.c_int32), ("world_to_volume", C.c_float * 12)]
+
+
+class MediumDesc(C.Structure):
+    """mirror of mer_medium_desc"""
+    _fields_ = [("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3), ("stepsize", C.c_float),
+                ("medium_sampling_weight", C.c_float), ("strategy", C.c_int32), ("channel", C.c_int32),
+                ("sampling_density", C.c_float), ("shape_type", C.c_int32), ("shape", C.c_float * 6),
+                ("hg_g", C.c_float), ("density_scale", C.c_float), ("albedo", C.c_float * 3)]
+
+
+class RenderDesc(C.Structure):
+    """mirror of mer_render_desc"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp_total", C.c_int32),
+                ("sample_begin", C.c_int32), ("sample_stride", C.c_int32), ("seed", C.c_uint64),
+                ("cam_origin", C.c_float * 3), ("cam_target", C.c_float * 3), ("cam_up", C.c_float * 3),
+                ("fov_deg", C.c_float), ("filter", C.c_int32), ("max_depth", C.c_int32), ("rr_depth", C.c_int32),
+                ("env_radiance", C.c_float * 3), ("has_quad", C.c_int32), ("quad_origin", C.c_float * 3),
+                ("quad_u", C.c_float * 3), ("quad_v", C.c_float * 3), ("quad_radiance", C.c_float * 3),
+                ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32)]
+
+
+class RenderStats(C.Structure):
+    """mirror of mer_render_stats"""
+    _fields_ = [("samples", C.c_uint64), ("ray_steps", C.c_uint64), ("scatter_events", C.c_uint64),
+                ("null_collisions", C.c_uint64), ("boundary_exits", C.c_uint64),
+                ("nonfinite_dropped", C.c_uint64), ("passes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("device_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def volume_desc(res, bbox_min, bbox_max, world_to_volume=None):
+    d = VolumeDesc()
+    d.res[:] = [int(r) for r in res]
+    d.bbox_min[:] = [float(x) for x in bbox_min]
+    d.bbox_max[:] = [float(x) for x in bbox_max]
+    if world_to_volume is None:
+        d.has_transform = 0
+        d.world_to_volume[:] = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
+    else:
+        d.has_transform = 1
+        d.world_to_volume[:] = [float(x) for x in np.asarray(world_to_volume, dtype=np.float64).reshape(12)]
+    return d
+
+
+def _ptr(a, ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+def build(target="oracle"):
+    """(re)build with oracle/Makefile; `ref` is a no-op when /root/reference is absent"""
+    subprocess.run(["make", "-s", "-C", HERE, target], check=True)
+
+
+class RefSpline:
+    """The reference's Spline<3>, compiled verbatim (oracle/ref_spline.cpp)."""
+
+    def __init__(self, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        suf = "f" if self.dtype == np.float32 else "d"
+        path = os.path.join(REF_DIR, "libmer_refspline_%s.so" % suf)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.ct = C.c_float if suf == "f" else C.c_double
+        self.lib.ref_spline_build.restype = C.c_void_p
+        self.lib.ref_spline_stride.restype = self.ct
+        assert self.lib.ref_spline_sizeof_float() == self.dtype.itemsize
+        self.h = None
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(REF_DIR, "libmer_refspline_f.so"))
+
+    def build(self, data, res, bbox_min, bbox_max):
+        data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+        self.res = tuple(int(r) for r in res)
+        assert data.size == self.res[0] * self.res[1] * self.res[2]
+        N = (C.c_int * 3)(*self.res)
+        bmin = (C.c_float * 3)(*[float(x) for x in bbox_min])
+        bmax = (C.c_float * 3)(*[float(x) for x in bbox_max])
+        self.h = C.c_void_p(self.lib.ref_spline_build(_ptr(data, C.c_float), N, bmin, bmax))
+        return self
+
+    def coefficients(self):
+        out = np.empty(self.res[0] * self.res[1] * self.res[2], dtype=self.dtype)
+        self.lib.ref_spline_coeffs(self.h, _ptr(out, self.ct))
+        return out
+
+    def eval(self, p, what=2):
+        p = np.ascontiguousarray(p, dtype=self.dtype).reshape(-1, 3)
+        n = p.shape[0]
+        f = np.zeros(n, dtype=self.dtype)
+        g = np.zeros((n, 3), dtype=self.dtype)
+        self.lib.ref_spline_eval(self.h, C.c_int(what), C.c_size_t(n), _ptr(p, self.ct), _ptr(f, self.ct),
+                                 _ptr(g, self.ct))
+        return f, g
+
+    def eval_hessian(self, p):
+        p = np.ascontiguousarray(p, dtype=self.dtype).reshape(-1, 3)
+        n = p.shape[0]
+        f = np.zeros(n, dtype=self.dtype)
+        g = np.zeros((n, 3), dtype=self.dtype)
+        H = np.zeros((n, 3, 3), dtype=self.dtype)
+        self.lib.ref_spline_eval_hessian(self.h, C.c_size_t(n), _ptr(p, self.ct), _ptr(f, self.ct),
+                                         _ptr(g, self.ct), _ptr(H, self.ct))
+        return f, g, H
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_spline_free(self.h)
+            self.h = None
+
+
+class Oracle:
+    """The restated path (oracle/mer_oracle.cpp) in float (`Float`) or double (-DFLOATDEBUG)."""
+
+    def __init__(self, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        self.suf = "_f" if self.dtype == np.float32 else "_d"
+        path = os.path.join(HERE, "libmer_oracle.so")
+        if not os.path.exists(path):
+            build("oracle")
+        self.lib = C.CDLL(path)
+        self.ct = C.c_float if self.dtype == np.float32 else C.c_double
+        for name in ("orc_rif_create", "orc_medium_create"):
+            getattr(self.lib, name + self.suf).restype = C.c_void_p
+        self.lib.orc_grid_create.restype = C.c_void_p
+
+    def _fn(self, name):
+        return getattr(self.lib, name + self.suf)
+
+    def num_threads(self):
+        return int(self.lib.orc_num_threads())
+
+    # ---- volumes
+    def rif_create(self, desc, data):
+        data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+        assert data.size == desc.res[0] * desc.res[1] * desc.res[2]
+        return C.c_void_p(self._fn("orc_rif_create")(C.byref(desc), _ptr(data, C.c_float)))
+
+    def rif_destroy(self, h):
+        self._fn("orc_rif_destroy")(h)
+
+    def rif_coefficients(self, h, n):
+        out = np.empty(n, dtype=self.dtype)
+        self._fn("orc_rif_coefficients")(h, _ptr(out, self.ct))
+        return out
+
+    def rif_eval(self, h, p, what=2):
+        p = np.ascontiguousarray(p, dtype=self.dtype).reshape(-1, 3)
+        n = p.shape[0]
+        f = np.zeros(n, dtype=self.dtype)
+        g = np.zeros((n, 3), dtype=self.dtype)
+        self._fn("orc_rif_eval")(h, C.c_int(what), C.c_size_t(n), _ptr(p, self.ct), _ptr(f, self.ct),
+                                 _ptr(g, self.ct))
+        return f, g
+
+    def rif_eval_hessian(self, h, p):
+        p = np.ascontiguousarray(p, dtype=self.dtype).reshape(-1, 3)
+        n = p.shape[0]
+        f = np.zeros(n, dtype=self.dtype)
+        g = np.zeros((n, 3), dtype=self.dtype)
+        H = np.zeros((n, 3, 3), dtype=self.dtype)
+        self._fn("orc_rif_eval_hessian")(h, C.c_size_t(n), _ptr(p, self.ct), _ptr(f, self.ct), _ptr(g, self.ct),
+                                         _ptr(H, self.ct))
+        return f, g, H
+
+    def rif_inside_limits(self, h, p):
+        p = np.ascontiguousarray(p, dtype=self.dtype).reshape(-1, 3)
+        out = np.zeros(p.shape[0], dtype=np.uint8)
+        self._fn("orc_rif_inside_limits")(h, C.c_size_t(p.shape[0]), _ptr(p, self.ct), _ptr(out, C.c_uint8))
+        return out.astype(bool)
+
+    def grid_create(self, desc, data):
+        data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+        return C.c_void_p(self.lib.orc_grid_create(C.byref(desc), _ptr(data, C.c_float)))
+
+    def grid_destroy(self, h):
+        self.lib.orc_grid_destroy(h)
+
+    def grid_lookup(self, h, p):
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(p.shape[0], dtype=np.float32)
+        self.lib.orc_grid_lookup(h, C.c_size_t(p.shape[0]), _ptr(p, C.c_float), _ptr(out, C.c_float))
+        return out
+
+    # ---- phase
+    def hg_sample(self, g, wi, xi):
+        wi = np.ascontiguousarray(wi, dtype=np.float32).reshape(-1, 3)
+        xi = np.ascontiguousarray(xi, dtype=np.float32).reshape(-1, 2)
+        n = wi.shape[0]
+        wo = np.zeros((n, 3), dtype=np.float32)
+        pdf = np.zeros(n, dtype=np.float32)
+        self.lib.orc_hg_sample(C.c_float(g), C.c_size_t(n), _ptr(wi, C.c_float), _ptr(xi, C.c_float),
+                               _ptr(wo, C.c_float), _ptr(pdf, C.c_float))
+        return wo, pdf
+
+    def hg_eval(self, g, wi, wo):
+        wi = np.ascontiguousarray(wi, dtype=np.float32).reshape(-1, 3)
+        wo = np.ascontiguousarray(wo, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(wi.shape[0], dtype=np.float32)
+        self.lib.orc_hg_eval(C.c_float(g), C.c_size_t(wi.shape[0]), _ptr(wi, C.c_float), _ptr(wo, C.c_float),
+                             _ptr(out, C.c_float))
+        return out
+
+    # ---- medium
+    def medium_create(self, desc, rif, density=None):
+        return C.c_void_p(self._fn("orc_medium_create")(C.byref(desc), rif, density))
+
+    def medium_destroy(self, h):
+        self._fn("orc_medium_destroy")(h)
+
+    def medium_resolved(self, h):
+        w, sd = C.c_float(), C.c_float()
+        self._fn("orc_medium_resolved")(h, C.byref(w), C.byref(sd))
+        return w.value, sd.value
+
+    def trace(self, h, p, v, dist):
+        p = np.array(p, dtype=self.dtype).reshape(-1, 3)
+        v = np.array(v, dtype=self.dtype).reshape(-1, 3)
+        dist = np.ascontiguousarray(dist, dtype=self.dtype).reshape(-1)
+        n = p.shape[0]
+        ok = np.zeros(n, dtype=np.uint8)
+        ds = np.zeros(n, dtype=self.dtype)
+        opl = np.zeros(n, dtype=self.dtype)
+        ns = np.zeros(n, dtype=np.int32)
+        self._fn("orc_medium_trace")(h, C.c_size_t(n), _ptr(p, self.ct), _ptr(v, self.ct), _ptr(dist, self.ct),
+                                     _ptr(ok, C.c_uint8), _ptr(ds, self.ct), _ptr(opl, self.ct),
+                                     _ptr(ns, C.c_int32))
+        return dict(p=p, v=v, success=ok.astype(bool), dist_surf=ds, opl=opl, nsteps=ns)
+
+    def trace_till_boundary(self, h, p, v):
+        p = np.array(p, dtype=self.dtype).reshape(-1, 3)
+        v = np.array(v, dtype=self.dtype).reshape(-1, 3)
+        n = p.shape[0]
+        ds = np.zeros(n, dtype=self.dtype)
+        opl = np.zeros(n, dtype=self.dtype)
+        ns = np.zeros(n, dtype=np.int32)
+        self._fn("orc_medium_trace_till_boundary")(h, C.c_size_t(n), _ptr(p, self.ct), _ptr(v, self.ct),
+                                                   _ptr(ds, self.ct), _ptr(opl, self.ct), _ptr(ns, C.c_int32))
+        return dict(p=p, v=v, dist_surf=ds, opl=opl, nsteps=ns)
+
+    def sample_distance(self, h, ro, rd, mint, xi):
+        ro = np.ascontiguousarray(ro, dtype=np.float32).reshape(-1, 3)
+        rd = np.ascontiguousarray(rd, dtype=np.float32).reshape(-1, 3)
+        n = ro.shape[0]
+        mint = np.ascontiguousarray(np.broadcast_to(np.asarray(mint, dtype=np.float32), (n,)))
+        xi = np.ascontiguousarray(xi, dtype=np.float32).reshape(-1, 2)
+        r = dict(success=np.zeros(n, np.uint8), t=np.zeros(n, self.dtype), p=np.zeros((n, 3), self.dtype),
+                 d=np.zeros((n, 3), self.dtype), optical_length=np.zeros(n, self.dtype),
+                 ref_ratio_sq=np.zeros(n, self.dtype), transmittance=np.zeros((n, 3), np.float32),
+                 pdf_success=np.zeros(n, np.float32), pdf_failure=np.zeros(n, np.float32),
+                 sigma_s=np.zeros((n, 3), np.float32), nsteps=np.zeros(n, np.int32))
+        self._fn("orc_medium_sample_distance")(
+            h, C.c_size_t(n), _ptr(ro, C.c_float), _ptr(rd, C.c_float), _ptr(mint, C.c_float), _ptr(xi, C.c_float),
+            _ptr(r["success"], C.c_uint8), _ptr(r["t"], self.ct), _ptr(r["p"], self.ct), _ptr(r["d"], self.ct),
+            _ptr(r["optical_length"], self.ct), _ptr(r["ref_ratio_sq"], self.ct),
+            _ptr(r["transmittance"], C.c_float), _ptr(r["pdf_success"], C.c_float),
+            _ptr(r["pdf_failure"], C.c_float), _ptr(r["sigma_s"], C.c_float), _ptr(r["nsteps"], C.c_int32))
+        r["success"] = r["success"].astype(bool)
+        return r
+
+    def eval_transmittance(self, sigma_t, mint, maxt):
+        mint = np.ascontiguousarray(mint, dtype=np.float32).reshape(-1)
+        maxt = np.ascontiguousarray(maxt, dtype=np.float32).reshape(-1)
+        out = np.zeros((mint.size, 3), dtype=np.float32)
+        st = (C.c_float * 3)(*[float(x) for x in sigma_t])
+        self.lib.orc_eval_transmittance(st, C.c_size_t(mint.size), _ptr(mint, C.c_float), _ptr(maxt, C.c_float),
+                                        _ptr(out, C.c_float))
+        return out
+
+    # ---- integrator
+    def render(self, medium, rdesc, nthreads=0):
+        film = np.zeros((rdesc.height, rdesc.width, 5), dtype=np.float32)
+        stats = RenderStats()
+        self._fn("orc_render")(medium, C.byref(rdesc), _ptr(film, C.c_float), C.byref(stats), C.c_int(nthreads))
+        return film, stats
+
+    def philox(self, seed, sample_id, n):
+        out = np.zeros(n, dtype=np.float32)
+        self.lib.orc_philox(C.c_uint64(seed), C.c_uint64(sample_id), C.c_size_t(n), _ptr(out, C.c_float))
+        return out
+
+    def filter_table(self, ftype):
+        vals = np.zeros(32, dtype=np.float32)
+        r, s = C.c_float(), C.c_float()
+        self.lib.orc_filter_table(C.c_int(ftype), _ptr(vals, C.c_float), C.byref(r), C.byref(s))
+        return vals, r.value, s.value
+
+    def camera_ray(self, rdesc, sample_pos):
+        sp = np.ascontiguousarray(sample_pos, dtype=np.float32).reshape(-1, 2)
+        d = np.zeros((sp.shape[0], 3), dtype=np.float32)
+        self.lib.orc_camera_ray(C.byref(rdesc), C.c_size_t(sp.shape[0]), _ptr(sp, C.c_float), _ptr(d, C.c_float))
+        return d
+
+    def film_develop(self, film):
+        H, W, _ = film.shape
+        film = np.ascontiguousarray(film, dtype=np.float32)
+        rgb = np.zeros((H, W, 3), dtype=np.float32)
+        self.lib.orc_film_develop(C.c_int(W), C.c_int(H), _ptr(film, C.c_float), _ptr(rgb, C.c_float))
+        return rgb
