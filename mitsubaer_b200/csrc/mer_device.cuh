@@ -1,0 +1,341 @@
+/*
+ * mer_device.cuh — device-side primitives of the eikonal hot path (sm_100a).
+ *
+ * Everything here is a from-scratch CUDA formulation of the reference's scalar C++
+ * (citations relative to the MitsubaER tree):
+ *   rif_lookup*      Spline<3>::valueAndGradient / gradient   include/mitsuba/core/basisspline.h:318-364, 438-471
+ *                    + SplineDataSource wrappers              src/volume/splinevolume.cpp:319-360
+ *   grid_lookup      GridDataSource::lookupFloat              src/volume/gridvolume.cpp:337-363
+ *   er_step_fused    HeterogeneousRefractiveMedium::er_step   src/medium/heterogeneousrefractive.cpp:653-661
+ *   inside_shape     insideShape / hackForSphere / hackForBox :707-726
+ *   hg_sample/eval   HGPhaseFunction                          src/phase/hg.cpp:76-110
+ *   Philox4x32-10    stands in for the per-thread Sampler     src/librender/renderjob.cpp:62-66
+ *
+ * Data layout in HBM:
+ *   coeff   float  [z][y][x]   prefiltered B-spline coefficients, the reference's layout
+ *   coeff4  float4 [z][y][x] = (c[x-1], c[x], c[x+1], c[x+2]) (x clamped): the four x-taps of a
+ *           lookup in ONE aligned 16-byte load -> a 4x4x4 stencil is 16 independent LDG.128
+ *   packed  float4 [z][y][x] = (n, dn/dx, dn/dy, dn/dz) sampled at the grid nodes (fast mode)
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mitsubaer_b200.h"
+
+#define MER_EPSILON 1e-4f /* include/mitsuba/core/constants.h:28 */
+
+struct RifDev {
+    int mode;
+    int N[3];
+    float xmin[3], xres[3];
+    float limLo[3], limHi[3];
+    int hasXform;
+    float M[12];
+    const float *coeff;
+    const float4 *coeff4;
+    const float4 *packed;
+};
+
+struct GridDev {
+    int N[3];
+    float G[12]; /* world -> grid, row-major 3x4 (gridvolume.cpp:190-195) */
+    const float *data;
+};
+
+struct MediumDev {
+    RifDev rif;
+    GridDev grid;
+    int hasGrid;
+    float sigmaA[3], sigmaS[3], sigmaT[3];
+    float h;
+    float weight;          /* m_mediumSamplingWeight */
+    int strategy;
+    float samplingDensity; /* m_samplingDensity */
+    int shapeType;
+    float shape[6];
+    float g;
+    float densityScale, invMaxDensity;
+    float albedo[3];
+};
+
+/* ------------------------------------------------------------------ small vector helpers */
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+/* ------------------------------------------------------------------ a1: B-spline kernels
+ * basisspline.h:39-114.  `d` = x - index; the same piecewise polynomials, same branch
+ * conditions.  (The reference evaluates kernel<1>'s centre branch through a double literal;
+ * here it is single precision: <= 1 ulp apart.) */
+__device__ __forceinline__ float bs_k0(float d) {
+    float a = fabsf(d), t = 2.0f - a;
+    float outer = 0.16666666666666666667f * t * t * t;
+    float inner = 0.66666666666666666667f - a * a + 0.5f * a * a * a;
+    float r = a > 1.0f ? outer : inner;
+    return a > 2.0f ? 0.0f : r;
+}
+__device__ __forceinline__ float bs_k1(float d) {
+    float a = fabsf(d), t = 2.0f - a;
+    float s = d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f);
+    float outer = -0.5f * t * t;
+    float inner = (1.5f * a - 2.0f) * a;
+    float r = a > 1.0f ? outer : inner;
+    return a > 2.0f ? 0.0f : s * r;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+__device__ __forceinline__ float3 rif_to_volume(const RifDev &R, float3 p) {
+    if (!R.hasXform) return p;
+    return f3(R.M[0] * p.x + R.M[1] * p.y + R.M[2] * p.z + R.M[3], R.M[4] * p.x + R.M[5] * p.y + R.M[6] * p.z + R.M[7],
+              R.M[8] * p.x + R.M[9] * p.y + R.M[10] * p.z + R.M[11]);
+}
+__device__ __forceinline__ float3 rif_rot_t(const RifDev &R, float3 g) { /* worldToVolume_RotT * g */
+    if (!R.hasXform) return g;
+    return f3(R.M[0] * g.x + R.M[4] * g.y + R.M[8] * g.z, R.M[1] * g.x + R.M[5] * g.y + R.M[9] * g.z,
+              R.M[2] * g.x + R.M[6] * g.y + R.M[10] * g.z);
+}
+
+/* SplineDataSource::insideVolumeLimits, splinevolume.cpp:319-324 (strict inequalities) */
+__device__ __forceinline__ bool rif_inside_limits(const RifDev &R, float3 pw) {
+    float3 p = rif_to_volume(R, pw);
+    return p.x > R.limLo[0] && p.x < R.limHi[0] && p.y > R.limLo[1] && p.y < R.limHi[1] && p.z > R.limLo[2] &&
+           p.z < R.limHi[2];
+}
+
+/* ------------------------------------------------------------------ a4: tricubic value + gradient
+ * One 4x4x4 stencil evaluation giving n and grad n (volume space, already scaled by dxres).
+ * Separable contraction: 16 LDG.128 rows -> x (128 FMA) -> y (48 FMA) -> z (16 FMA).
+ * Tap set = floor(x)-1 .. floor(x)+2 per axis, which is the reference's
+ * ceil(x-2)..floor(x+2) range minus its zero-weight end taps.  Indices are clamped into the
+ * grid (the reference reads out of bounds there). */
+__device__ __forceinline__ void rif_tricubic(const RifDev &R, float3 pv, float &f, float3 &g) {
+    const float x = (pv.x - R.xmin[0]) * R.xres[0], y = (pv.y - R.xmin[1]) * R.xres[1],
+                z = (pv.z - R.xmin[2]) * R.xres[2];
+    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    const int i0 = (int) fx, j0 = (int) fy, k0 = (int) fz;
+    float wx0[4], wx1[4], wy0[4], wy1[4], wz0[4], wz1[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        float dx = x - (fx + (float) (t - 1)), dy = y - (fy + (float) (t - 1)), dz = z - (fz + (float) (t - 1));
+        wx0[t] = bs_k0(dx); wx1[t] = bs_k1(dx);
+        wy0[t] = bs_k0(dy); wy1[t] = bs_k1(dy);
+        wz0[t] = bs_k0(dz); wz1[t] = bs_k1(dz);
+    }
+    const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
+    const int ic = clampi(i0, 0, N0 - 1);
+    size_t rowOff[4], slabOff[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        rowOff[t] = (size_t) clampi(j0 - 1 + t, 0, N1 - 1) * (size_t) N0;
+        slabOff[t] = (size_t) clampi(k0 - 1 + t, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
+    }
+    const float4 *base = R.coeff4 + ic;
+    float4 c[16];
+#pragma unroll
+    for (int dz = 0; dz < 4; dz++)
+#pragma unroll
+        for (int dy = 0; dy < 4; dy++) c[dz * 4 + dy] = __ldg(base + slabOff[dz] + rowOff[dy]);
+
+    float accF = 0.f, accX = 0.f, accY = 0.f, accZ = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 4; dz++) {
+        float b00 = 0.f, b10 = 0.f, b01 = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 4; dy++) {
+            const float4 q = c[dz * 4 + dy];
+            float a0 = q.x * wx0[0] + q.y * wx0[1] + q.z * wx0[2] + q.w * wx0[3];
+            float a1 = q.x * wx1[0] + q.y * wx1[1] + q.z * wx1[2] + q.w * wx1[3];
+            b00 = fmaf(a0, wy0[dy], b00);
+            b10 = fmaf(a1, wy0[dy], b10);
+            b01 = fmaf(a0, wy1[dy], b01);
+        }
+        accF = fmaf(b00, wz0[dz], accF);
+        accX = fmaf(b10, wz0[dz], accX);
+        accY = fmaf(b01, wz0[dz], accY);
+        accZ = fmaf(b00, wz1[dz], accZ);
+    }
+    f = accF;
+    g = f3(accX * R.xres[0], accY * R.xres[1], accZ * R.xres[2]);
+}
+
+/* ------------------------------------------------------------------ fast mode: packed trilinear
+ * 8 aligned float4 {n, grad n} fetches, trilinear weights (gridvolume.cpp:337-363 arithmetic
+ * applied to a 4-channel voxel).  Not the reference's interpolant: see SURVEY.md R1. */
+__device__ __forceinline__ float4 lerp4(float4 a, float4 b, float t) {
+    return make_float4(fmaf(t, b.x - a.x, a.x), fmaf(t, b.y - a.y, a.y), fmaf(t, b.z - a.z, a.z),
+                       fmaf(t, b.w - a.w, a.w));
+}
+__device__ __forceinline__ void rif_trilinear(const RifDev &R, float3 pv, float &f, float3 &g) {
+    const float x = (pv.x - R.xmin[0]) * R.xres[0], y = (pv.y - R.xmin[1]) * R.xres[1],
+                z = (pv.z - R.xmin[2]) * R.xres[2];
+    const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
+    const int i0 = clampi((int) floorf(x), 0, N0 - 2), j0 = clampi((int) floorf(y), 0, N1 - 2),
+              k0 = clampi((int) floorf(z), 0, N2 - 2);
+    const float tx = x - (float) i0, ty = y - (float) j0, tz = z - (float) k0;
+    const float4 *b = R.packed + ((size_t) k0 * N1 + j0) * (size_t) N0 + i0;
+    const size_t sy = N0, sz = (size_t) N0 * N1;
+    float4 c000 = __ldg(b), c001 = __ldg(b + 1), c010 = __ldg(b + sy), c011 = __ldg(b + sy + 1),
+           c100 = __ldg(b + sz), c101 = __ldg(b + sz + 1), c110 = __ldg(b + sz + sy), c111 = __ldg(b + sz + sy + 1);
+    float4 r = lerp4(lerp4(lerp4(c000, c001, tx), lerp4(c010, c011, tx), ty),
+                     lerp4(lerp4(c100, c101, tx), lerp4(c110, c111, tx), ty), tz);
+    f = r.x;
+    g = f3(r.y, r.z, r.w);
+}
+
+/* SplineDataSource::valueAndGradient (splinevolume.cpp:352-358) in the handle's mode, world space */
+template <int MODE> __device__ __forceinline__ void rif_lookup(const RifDev &R, float3 pw, float &n, float3 &G) {
+    float3 pv = rif_to_volume(R, pw);
+    if (MODE == MER_RIF_TRICUBIC)
+        rif_tricubic(R, pv, n, G);
+    else
+        rif_trilinear(R, pv, n, G);
+    G = rif_rot_t(R, G);
+}
+
+/* ------------------------------------------------------------------ a18: density lookup */
+__device__ __forceinline__ float grid_lookup(const GridDev &D, float3 pw) {
+    /* Transform::transformAffine: ((m0*x + m1*y) + m2*z) + m3, every operation rounded */
+    const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(D.G[0], pw.x), __fmul_rn(D.G[1], pw.y)), __fmul_rn(D.G[2], pw.z)), D.G[3]);
+    const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(D.G[4], pw.x), __fmul_rn(D.G[5], pw.y)), __fmul_rn(D.G[6], pw.z)), D.G[7]);
+    const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(D.G[8], pw.x), __fmul_rn(D.G[9], pw.y)), __fmul_rn(D.G[10], pw.z)), D.G[11]);
+    const int x1 = (int) floorf(px), y1 = (int) floorf(py), z1 = (int) floorf(pz);
+    const int x2 = x1 + 1, y2 = y1 + 1, z2 = z1 + 1;
+    if (x1 < 0 || y1 < 0 || z1 < 0 || x2 >= D.N[0] || y2 >= D.N[1] || z2 >= D.N[2]) return 0.0f;
+    const float fx = px - (float) x1, fy = py - (float) y1, fz = pz - (float) z1;
+    const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+    const size_t rx = D.N[0], ry = D.N[1];
+    const float *fd = D.data;
+    const float d000 = __ldg(fd + ((size_t) z1 * ry + y1) * rx + x1), d001 = __ldg(fd + ((size_t) z1 * ry + y1) * rx + x2),
+                d010 = __ldg(fd + ((size_t) z1 * ry + y2) * rx + x1), d011 = __ldg(fd + ((size_t) z1 * ry + y2) * rx + x2),
+                d100 = __ldg(fd + ((size_t) z2 * ry + y1) * rx + x1), d101 = __ldg(fd + ((size_t) z2 * ry + y1) * rx + x2),
+                d110 = __ldg(fd + ((size_t) z2 * ry + y2) * rx + x1), d111 = __ldg(fd + ((size_t) z2 * ry + y2) * rx + x2);
+    /* same association as the reference, products and sums individually rounded */
+    const float a0 = __fadd_rn(__fmul_rn(d000, gx), __fmul_rn(d001, fx)), a1 = __fadd_rn(__fmul_rn(d010, gx), __fmul_rn(d011, fx)),
+                a2 = __fadd_rn(__fmul_rn(d100, gx), __fmul_rn(d101, fx)), a3 = __fadd_rn(__fmul_rn(d110, gx), __fmul_rn(d111, fx));
+    const float b0 = __fadd_rn(__fmul_rn(a0, gy), __fmul_rn(a1, fy)), b1 = __fadd_rn(__fmul_rn(a2, gy), __fmul_rn(a3, fy));
+    return __fadd_rn(__fmul_rn(b0, gz), __fmul_rn(b1, fz));
+}
+
+/* ------------------------------------------------------------------ a11: containment */
+__device__ __forceinline__ bool inside_shape(const MediumDev &M, float3 p) {
+    if (M.shapeType == MER_SHAPE_SPHERE) {
+        float dx = p.x - M.shape[0], dy = p.y - M.shape[1], dz = p.z - M.shape[2];
+        return (dx * dx + dy * dy + dz * dz) < M.shape[3] * M.shape[3];
+    }
+    return p.x >= M.shape[0] && p.x <= M.shape[3] && p.y >= M.shape[1] && p.y <= M.shape[4] && p.z >= M.shape[2] &&
+           p.z <= M.shape[5];
+}
+
+/* ------------------------------------------------------------------ a7: leapfrog step
+ * er_step (:653-661) with the two spline evaluations fused into one: the reference's
+ * `gradient(p_new)` at the end of a step and `valueAndGradient(p)` at the start of the next
+ * are evaluated at the same point, so (n, G) is carried across steps.  On entry (n, G) must be
+ * the field at p; on exit they are the field at the new p.  `v/n` multiplies by 1/n as
+ * TVector3::operator/ does. */
+template <int MODE>
+__device__ __forceinline__ void er_step_fused(const RifDev &R, float3 &p, float3 &v, float &n, float3 &G, float h,
+                                              float &opl) {
+    /* The leapfrog arithmetic is rounded operation by operation exactly like the reference's float
+     * build (no fma contraction): on straight stretches the increment h*v/n is the same every step,
+     * so a contracted multiply-add would turn a half-ulp rounding difference into a systematic
+     * one-ulp-per-step drift against the reference.  Costs 9 extra instructions per step. */
+    const float hs = __fmul_rn(0.5f, h);
+    v = f3(__fadd_rn(v.x, __fmul_rn(hs, G.x)), __fadd_rn(v.y, __fmul_rn(hs, G.y)), __fadd_rn(v.z, __fmul_rn(hs, G.z)));
+    const float recip = __frcp_rn(n);
+    p = f3(__fadd_rn(p.x, __fmul_rn(__fmul_rn(h, v.x), recip)), __fadd_rn(p.y, __fmul_rn(__fmul_rn(h, v.y), recip)),
+           __fadd_rn(p.z, __fmul_rn(__fmul_rn(h, v.z), recip)));
+    opl = __fadd_rn(opl, __fmul_rn(h, n));
+    rif_lookup<MODE>(R, p, n, G);
+    v = f3(__fadd_rn(v.x, __fmul_rn(hs, G.x)), __fadd_rn(v.y, __fmul_rn(hs, G.y)), __fadd_rn(v.z, __fmul_rn(hs, G.z)));
+}
+
+/* trace()'s decomposition of a distance (:673-675): bit-exact single-precision ops so the
+ * step count matches the reference for every input. */
+__device__ __forceinline__ void trace_split(float dist, float h, int &steps, float &rem) {
+    float q = __fdiv_rn(dist, h);
+    /* int conversion of huge / infinite quotients is undefined in C++; clamp */
+    steps = q >= 2.0e9f ? 2000000000 : (int) q;
+    rem = __fsub_rn(dist, __fmul_rn((float) steps, h));
+}
+
+/* ------------------------------------------------------------------ a15-a17: Henyey-Greenstein */
+/* Every operation is individually rounded (no fma contraction), like the reference's x86 build:
+ * cosTheta for |g| -> 1 and sinTheta = sqrt(1 - cos^2) are cancellation-prone, so contraction
+ * would change the sampled direction by ~1e-5. */
+__device__ __forceinline__ float hg_eval_dev(float g, float3 wi, float3 wo) {
+    const float INV_FOURPI = 0.07957747154594766788f;
+    const float gg = __fmul_rn(g, g);
+    const float dotp = __fadd_rn(__fadd_rn(__fmul_rn(wi.x, wo.x), __fmul_rn(wi.y, wo.y)), __fmul_rn(wi.z, wo.z));
+    const float temp = __fadd_rn(__fadd_rn(1.0f, gg), __fmul_rn(__fmul_rn(2.0f, g), dotp));
+    return __fdiv_rn(__fmul_rn(INV_FOURPI, __fsub_rn(1.0f, gg)), __fmul_rn(temp, __fsqrt_rn(temp)));
+}
+__device__ __forceinline__ void coordinate_system(float3 a, float3 &b, float3 &c) { /* util.cpp:606-615 */
+    if (fabsf(a.x) > fabsf(a.y)) {
+        float invLen = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.z, a.z))));
+        c = f3(__fmul_rn(a.z, invLen), 0.0f, __fmul_rn(-a.x, invLen));
+    } else {
+        float invLen = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fmul_rn(a.y, a.y), __fmul_rn(a.z, a.z))));
+        c = f3(0.0f, __fmul_rn(a.z, invLen), __fmul_rn(-a.y, invLen));
+    }
+    b = f3(__fsub_rn(__fmul_rn(c.y, a.z), __fmul_rn(c.z, a.y)), __fsub_rn(__fmul_rn(c.z, a.x), __fmul_rn(c.x, a.z)),
+           __fsub_rn(__fmul_rn(c.x, a.y), __fmul_rn(c.y, a.x)));
+}
+__device__ __forceinline__ float3 hg_sample_dev(float g, float3 wi, float u1, float u2) {
+    float cosTheta;
+    if (fabsf(g) < MER_EPSILON) {
+        cosTheta = __fsub_rn(1.0f, __fmul_rn(2.0f, u1));
+    } else {
+        const float gg = __fmul_rn(g, g);
+        float sqrTerm = __fdiv_rn(__fsub_rn(1.0f, gg), __fadd_rn(__fsub_rn(1.0f, g), __fmul_rn(__fmul_rn(2.0f, g), u1)));
+        cosTheta = __fdiv_rn(__fsub_rn(__fadd_rn(1.0f, gg), __fmul_rn(sqrTerm, sqrTerm)), __fmul_rn(2.0f, g));
+    }
+    float sinTheta = __fsqrt_rn(fmaxf(0.0f, __fsub_rn(1.0f, __fmul_rn(cosTheta, cosTheta))));
+    float phi = (float) (2.0 * 3.14159265358979323846 * (double) u2);
+    float sinPhi, cosPhi;
+    sincosf(phi, &sinPhi, &cosPhi);
+    float3 nrm = f3(-wi.x, -wi.y, -wi.z), s, t;
+    coordinate_system(nrm, s, t);
+    float lx = __fmul_rn(sinTheta, cosPhi), ly = __fmul_rn(sinTheta, sinPhi), lz = cosTheta;
+    /* Frame::toWorld: s * v.x + t * v.y + n * v.z */
+    return f3(__fadd_rn(__fadd_rn(__fmul_rn(s.x, lx), __fmul_rn(t.x, ly)), __fmul_rn(nrm.x, lz)),
+              __fadd_rn(__fadd_rn(__fmul_rn(s.y, lx), __fmul_rn(t.y, ly)), __fmul_rn(nrm.y, lz)),
+              __fadd_rn(__fadd_rn(__fmul_rn(s.z, lx), __fmul_rn(t.z, ly)), __fmul_rn(nrm.z, lz)));
+}
+
+/* fastlog / fastexp: double precision rounded to float on Linux x86-64, math.h:185-199 */
+__device__ __forceinline__ float fastlog_dev(float x) { return (float) log((double) x); }
+__device__ __forceinline__ float fastexp_dev(float x) { return (float) exp((double) x); }
+
+/* ------------------------------------------------------------------ Philox4x32-10
+ * key = seed, counter = (sample id lo, hi, block, 0); float = (u >> 8) * 2^-24.  The k-th
+ * float of a sample's stream is word k%4 of block k/4, so the only per-path RNG state is k. */
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+struct PathRng {
+    uint32_t k0, k1, s0, s1, k; /* key, sample id, draw index */
+    __device__ __forceinline__ void init(uint64_t seed, uint64_t sampleId, uint32_t draw) {
+        k0 = (uint32_t) seed; k1 = (uint32_t) (seed >> 32);
+        s0 = (uint32_t) sampleId; s1 = (uint32_t) (sampleId >> 32);
+        k = draw;
+    }
+    __device__ __forceinline__ float next() {
+        uint4 b = philox4x32_10(s0, s1, k >> 2, 0u, k0, k1);
+        uint32_t w = (k & 3u) == 0 ? b.x : ((k & 3u) == 1 ? b.y : ((k & 3u) == 2 ? b.z : b.w));
+        k++;
+        return (float) (w >> 8) * (1.0f / 16777216.0f);
+    }
+};

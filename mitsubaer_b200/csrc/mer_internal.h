@@ -1,0 +1,87 @@
+/*
+ * mer_internal.h — host-side internals shared by the .cu translation units of
+ * libmitsubaer_b200.so (handle layouts, error plumbing, launch accounting).
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+
+#include "mer_device.cuh"
+#include "mitsubaer_b200.h"
+
+struct mer_rif {
+    int device;
+    int mode;
+    mer_volume_desc desc;
+    RifDev dev;
+    float *d_coeff;
+    float4 *d_coeff4;
+    float4 *d_packed;
+};
+
+struct mer_grid {
+    int device;
+    mer_volume_desc desc;
+    GridDev dev;
+    float *d_data;
+};
+
+struct mer_medium {
+    int device;
+    mer_medium_desc desc; /* resolved */
+    const mer_rif *rif;
+    const mer_grid *grid;
+    MediumDev dev;
+};
+
+namespace mer {
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+extern std::atomic<uint64_t> g_launches;
+
+/* RAII device switch that restores the caller's current device (PyTorch shares the process) */
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_device(int device); /* MER_OK or MER_ERR_CUDA (no usable sm_100-class GPU) */
+
+} /* namespace mer */
+
+#define MER_CUDA(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            char _buf[512];                                                                             \
+            snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                     __FILE__, __LINE__);                                                               \
+            return mer::fail(_e == cudaErrorMemoryAllocation ? MER_ERR_OOM : MER_ERR_CUDA, _buf);       \
+        }                                                                                               \
+    } while (0)
+
+/* every kernel launch goes through this so mer_kernel_launch_count() is exact */
+#define MER_LAUNCH(kernel, grid, block, smem, stream, ...)                                              \
+    do {                                                                                                \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                     \
+        mer::g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+        MER_CUDA(cudaGetLastError());                                                                   \
+    } while (0)
+
+#define MER_REQUIRE(cond, msg)                                                                          \
+    do {                                                                                                \
+        if (!(cond)) return mer::fail(MER_ERR_INVALID, msg);                                            \
+    } while (0)
+
+static inline unsigned mer_blocks(size_t n, unsigned threads) { return (unsigned) ((n + threads - 1) / threads); }

@@ -1,0 +1,467 @@
+/*
+ * mer_medium.cu — Medium / PhaseFunction side of the path: the eikonal ray stepper
+ * (trace, traceTillBoundary), sampleDistance, evalTransmittance and Henyey-Greenstein,
+ * as batch kernels behind the C ABI.
+ *
+ * Reference (paths relative to the MitsubaER tree):
+ *   HeterogeneousRefractiveMedium   src/medium/heterogeneousrefractive.cpp:201-297 (ctor), 393-400, 402-568,
+ *                                   653-691, 707-776
+ *   Medium base                     src/librender/medium.cpp:27-37
+ *   HGPhaseFunction                 src/phase/hg.cpp:76-110
+ */
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "mer_internal.h"
+
+/* ------------------------------------------------------------------ a8: trace() */
+template <int MODE>
+__device__ __forceinline__ bool trace_dev(const MediumDev &M, float3 &p, float3 &v, float &n, float3 &G, float dist,
+                                          float &distSurf, float &opl, int &count) {
+    int steps;
+    float rem;
+    trace_split(dist, M.h, steps, rem);
+    distSurf = 0.0f;
+    const float h = M.h;
+    for (int i = 0; i < steps; i++) {
+        er_step_fused<MODE>(M.rif, p, v, n, G, h, opl);
+        count++;
+        if (!inside_shape(M, p)) {
+            er_step_fused<MODE>(M.rif, p, v, n, G, -h, opl); /* step back, :679 */
+            count++;
+            return false;
+        }
+        distSurf += h;
+    }
+    er_step_fused<MODE>(M.rif, p, v, n, G, rem, opl);
+    count++;
+    if (!inside_shape(M, p)) {
+        er_step_fused<MODE>(M.rif, p, v, n, G, -rem, opl);
+        count++;
+        return false;
+    }
+    distSurf += rem;
+    return true;
+}
+
+/* ------------------------------------------------------------------ a9: traceTillBoundary() */
+template <int MODE>
+__device__ __forceinline__ void trace_till_boundary_dev(const MediumDev &M, float3 &p, float3 &v, float &n, float3 &G,
+                                                        float &distSurf, float &opl, int &count) {
+    distSurf = 0.0f;
+    const float h = M.h;
+    for (int i = 0; i < 100000; i++) { /* maxsteps 1e5, :746 */
+        er_step_fused<MODE>(M.rif, p, v, n, G, h, opl);
+        count++;
+        if (inside_shape(M, p)) {
+            distSurf += h;
+        } else {
+            er_step_fused<MODE>(M.rif, p, v, n, G, -h, opl);
+            count++;
+            distSurf -= h; /* :761 */
+            return;
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_trace(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P, float *__restrict__ V,
+        const float *__restrict__ dist, uint8_t *__restrict__ success, float *__restrict__ distSurfOut,
+        float *__restrict__ oplOut, int32_t *__restrict__ nstepsOut, unsigned long long *__restrict__ stepCounter) {
+    unsigned long long local = 0;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nRays; i += (size_t) gridDim.x * blockDim.x) {
+        float3 p = f3(P[3 * i], P[3 * i + 1], P[3 * i + 2]), v = f3(V[3 * i], V[3 * i + 1], V[3 * i + 2]);
+        float n, ds, opl = 0.0f;
+        float3 G;
+        int count = 0;
+        rif_lookup<MODE>(M.rif, p, n, G);
+        bool ok = trace_dev<MODE>(M, p, v, n, G, dist[i], ds, opl, count);
+        P[3 * i] = p.x; P[3 * i + 1] = p.y; P[3 * i + 2] = p.z;
+        V[3 * i] = v.x; V[3 * i + 1] = v.y; V[3 * i + 2] = v.z;
+        if (success) success[i] = ok ? 1 : 0;
+        if (distSurfOut) distSurfOut[i] = ds;
+        if (oplOut) oplOut[i] = opl;
+        if (nstepsOut) nstepsOut[i] = count;
+        local += (unsigned long long) count;
+    }
+    if (stepCounter) {
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(stepCounter, local);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_trace_till_boundary(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P, float *__restrict__ V,
+                      float *__restrict__ distSurfOut, float *__restrict__ oplOut, int32_t *__restrict__ nstepsOut) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nRays; i += (size_t) gridDim.x * blockDim.x) {
+        float3 p = f3(P[3 * i], P[3 * i + 1], P[3 * i + 2]), v = f3(V[3 * i], V[3 * i + 1], V[3 * i + 2]);
+        float n, ds, opl = 0.0f;
+        float3 G;
+        int count = 0;
+        rif_lookup<MODE>(M.rif, p, n, G);
+        trace_till_boundary_dev<MODE>(M, p, v, n, G, ds, opl, count);
+        P[3 * i] = p.x; P[3 * i + 1] = p.y; P[3 * i + 2] = p.z;
+        V[3 * i] = v.x; V[3 * i + 1] = v.y; V[3 * i + 2] = v.z;
+        if (distSurfOut) distSurfOut[i] = ds;
+        if (oplOut) oplOut[i] = opl;
+        if (nstepsOut) nstepsOut[i] = count;
+    }
+}
+
+/* ------------------------------------------------------------------ a12: sampleDistance() */
+struct SampleDistanceOut {
+    uint8_t *success;
+    float *t, *p, *d, *opl, *refRatioSq, *transmittance, *pdfSuccess, *pdfFailure, *sigmaS;
+    int32_t *nsteps;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float *__restrict__ RO,
+                  const float *__restrict__ RD, const float *__restrict__ mintIn, const float *__restrict__ xi,
+                  SampleDistanceOut out) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nRays; i += (size_t) gridDim.x * blockDim.x) {
+        const float mint = mintIn ? mintIn[i] : 0.0f;
+        float rnd = xi[2 * i], sampledDistance, sd = M.samplingDensity;
+        if (rnd < M.weight) {
+            rnd = __fdiv_rn(rnd, M.weight);
+            if (M.strategy == MER_STRATEGY_BALANCE) sd = M.sigmaT[min((int) (xi[2 * i + 1] * 3.0f), 2)];
+            sampledDistance = __fdiv_rn(-fastlog_dev(1.0f - rnd), sd);
+        } else {
+            sampledDistance = INFINITY;
+        }
+        float3 p = f3(RO[3 * i], RO[3 * i + 1], RO[3 * i + 2]), v = f3(RD[3 * i], RD[3 * i + 1], RD[3 * i + 2]);
+        const float3 o = p;
+        bool success = true;
+        float distSurf = 0.0f, opl = 0.0f, refRatioSq = 0.0f, T[3] = {0.f, 0.f, 0.f}, ps = 1.0f, pf = 1.0f, t = 0.0f;
+        int count = 0;
+        if (!rif_inside_limits(M.rif, p)) { /* :461-466 */
+            success = false;
+        } else {
+            float n;
+            float3 G;
+            rif_lookup<MODE>(M.rif, p, n, G);
+            const float refStart = n;
+            refRatioSq = (float) (1.0 / (double) (refStart * refStart));
+            v = f3(v.x * refStart, v.y * refStart, v.z * refStart);
+            if (isfinite(sampledDistance)) {
+                success = trace_dev<MODE>(M, p, v, n, G, sampledDistance, distSurf, opl, count);
+            } else {
+                trace_till_boundary_dev<MODE>(M, p, v, n, G, distSurf, opl, count);
+                success = false;
+            }
+            refRatioSq *= n * n; /* refEnd = value at the final p, carried by the fused stepper */
+            if (success) {
+                t = sampledDistance + mint;
+                if (p.x == o.x && p.y == o.y && p.z == o.z) success = false; /* no forward progress, :517-520 */
+            } else {
+                sampledDistance = distSurf;
+                t = sampledDistance + mint;
+            }
+            float pdfFailure = 0.0f, pdfSuccess = 0.0f;
+            if (M.strategy == MER_STRATEGY_BALANCE) {
+                for (int c = 0; c < 3; c++) {
+                    float tmp = fastexp_dev(__fmul_rn(-M.sigmaT[c], sampledDistance));
+                    pdfFailure = __fadd_rn(pdfFailure, tmp);
+                    pdfSuccess = __fadd_rn(pdfSuccess, __fmul_rn(M.sigmaT[c], tmp));
+                }
+                pdfFailure = __fdiv_rn(pdfFailure, 3.0f);
+                pdfSuccess = __fdiv_rn(pdfSuccess, 3.0f);
+            } else {
+                pdfFailure = fastexp_dev(__fmul_rn(-sd, sampledDistance));
+                pdfSuccess = __fmul_rn(sd, pdfFailure);
+            }
+            float tmax = 0.0f;
+            for (int c = 0; c < 3; c++) {
+                T[c] = fastexp_dev(__fmul_rn(M.sigmaT[c], -sampledDistance));
+                tmax = fmaxf(tmax, T[c]);
+            }
+            if (tmax < 1e-20f) T[0] = T[1] = T[2] = 0.0f;
+            ps = __fmul_rn(pdfSuccess, M.weight);
+            pf = __fadd_rn(__fmul_rn(M.weight, pdfFailure), 1.0f - M.weight);
+        }
+        if (out.success) out.success[i] = success ? 1 : 0;
+        if (out.t) out.t[i] = t;
+        if (out.p) { out.p[3 * i] = p.x; out.p[3 * i + 1] = p.y; out.p[3 * i + 2] = p.z; }
+        if (out.d) { out.d[3 * i] = v.x; out.d[3 * i + 1] = v.y; out.d[3 * i + 2] = v.z; }
+        if (out.opl) out.opl[i] = opl;
+        if (out.refRatioSq) out.refRatioSq[i] = refRatioSq;
+        if (out.transmittance) { out.transmittance[3 * i] = T[0]; out.transmittance[3 * i + 1] = T[1]; out.transmittance[3 * i + 2] = T[2]; }
+        if (out.pdfSuccess) out.pdfSuccess[i] = ps;
+        if (out.pdfFailure) out.pdfFailure[i] = pf;
+        if (out.sigmaS) { out.sigmaS[3 * i] = M.sigmaS[0]; out.sigmaS[3 * i + 1] = M.sigmaS[1]; out.sigmaS[3 * i + 2] = M.sigmaS[2]; }
+        if (out.nsteps) out.nsteps[i] = count;
+    }
+}
+
+/* ------------------------------------------------------------------ a14-a16 */
+__global__ void k_eval_transmittance(float s0, float s1, float s2, size_t n, const float *__restrict__ mint,
+                                     const float *__restrict__ maxt, float *__restrict__ out) {
+    const float sig[3] = {s0, s1, s2};
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        float negLength = mint[i] - maxt[i];
+        for (int c = 0; c < 3; c++) out[3 * i + c] = sig[c] != 0.0f ? fastexp_dev(__fmul_rn(sig[c], negLength)) : 1.0f;
+    }
+}
+
+__global__ void k_hg_sample(float g, size_t n, const float *__restrict__ wi, const float *__restrict__ xi,
+                            float *__restrict__ wo, float *__restrict__ pdf) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        float3 w = f3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        float3 o = hg_sample_dev(g, w, xi[2 * i], xi[2 * i + 1]);
+        wo[3 * i] = o.x; wo[3 * i + 1] = o.y; wo[3 * i + 2] = o.z;
+        if (pdf) pdf[i] = hg_eval_dev(g, w, o);
+    }
+}
+
+__global__ void k_hg_eval(float g, size_t n, const float *__restrict__ wi, const float *__restrict__ wo,
+                          float *__restrict__ out) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+        out[i] = hg_eval_dev(g, f3(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]), f3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
+}
+
+/* ===================================================================== host side */
+namespace {
+
+/* tiny RAII device buffer for the *_batch (host pointer) entry points */
+struct DevBuf {
+    void *ptr = nullptr;
+    ~DevBuf() { cudaFree(ptr); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&ptr, bytes ? bytes : 1); }
+    template <typename T> T *as() { return (T *) ptr; }
+};
+
+unsigned trace_grid(size_t n) {
+    /* persistent-style sizing: a multiple of the SM count, capped at what is resident */
+    size_t blocks = (n + 127) / 128;
+    size_t cap = 148u * 16u;
+    return (unsigned) (blocks < cap ? blocks : cap);
+}
+
+} /* namespace */
+
+#define UP(buf, host, bytes)                                                      \
+    do {                                                                          \
+        MER_CUDA(buf.alloc(bytes));                                               \
+        if (host) MER_CUDA(cudaMemcpy(buf.ptr, host, bytes, cudaMemcpyHostToDevice)); \
+    } while (0)
+#define DOWN(host, buf, bytes)                                                    \
+    do {                                                                          \
+        if (host) MER_CUDA(cudaMemcpy(host, buf.ptr, bytes, cudaMemcpyDeviceToHost)); \
+    } while (0)
+
+extern "C" {
+
+int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer_grid *density, mer_medium **out) {
+    if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    MER_REQUIRE(desc, "null medium descriptor");
+    MER_REQUIRE(rif, "No RIF specified!"); /* heterogeneousrefractive.cpp:368-369 */
+    MER_REQUIRE(!density || density->device == rif->device, "rif and density live on different devices");
+    MER_REQUIRE(desc->stepsize > 0.0f, "stepsize must be positive");
+    MER_REQUIRE(desc->hg_g > -1.0f && desc->hg_g < 1.0f,
+                "The asymmetry parameter must lie in the interval (-1, 1)!"); /* hg.cpp:50-52 */
+    MER_REQUIRE(desc->shape_type == MER_SHAPE_BOX || desc->shape_type == MER_SHAPE_SPHERE, "unknown shape type");
+    if (desc->strategy == MER_STRATEGY_MAXIMUM)
+        return mer::fail(MER_ERR_UNSUPPORTED, "strategy 'maximum' (MaxExpDist) is not carried by this path");
+    MER_REQUIRE(desc->strategy >= MER_STRATEGY_BALANCE && desc->strategy <= MER_STRATEGY_MANUAL,
+                "Specified an unknown sampling strategy"); /* :296 */
+    if (density) MER_REQUIRE(desc->density_scale > 0.0f, "density_scale must be positive when a density grid is attached");
+
+    mer_medium *m = new mer_medium();
+    memset(m, 0, sizeof(*m));
+    m->device = rif->device;
+    m->rif = rif;
+    m->grid = density;
+    m->desc = *desc;
+    MediumDev &D = m->dev;
+    D.rif = rif->dev;
+    D.hasGrid = density ? 1 : 0;
+    if (density) D.grid = density->dev;
+    for (int i = 0; i < 3; i++) {
+        D.sigmaA[i] = desc->sigma_a[i];
+        D.sigmaS[i] = desc->sigma_s[i];
+        D.sigmaT[i] = desc->sigma_a[i] + desc->sigma_s[i]; /* medium.cpp:36 */
+        D.albedo[i] = desc->albedo[i];
+    }
+    D.h = desc->stepsize;
+    /* mediumSamplingWeight default, :239-255 */
+    float w = desc->medium_sampling_weight;
+    if (w == -1.0f) {
+        for (int i = 0; i < 3; i++) {
+            float albedo = D.sigmaS[i] / D.sigmaT[i];
+            if (albedo > w && D.sigmaT[i] != 0.0f) w = albedo;
+        }
+        if (w > 0.0f) w = std::max(w, 0.5f);
+    }
+    D.weight = w;
+    D.strategy = desc->strategy;
+    D.samplingDensity = 0.0f;
+    if (desc->strategy == MER_STRATEGY_SINGLE) { /* :259-283 */
+        int channel = 0;
+        float smallest = std::numeric_limits<float>::infinity();
+        for (int i = 0; i < 3; i++)
+            if (D.sigmaT[i] < smallest) { smallest = D.sigmaT[i]; channel = i; }
+        if (desc->channel >= 0) {
+            if (desc->channel > 2) { delete m; return mer::fail(MER_ERR_INVALID, "channel out of range"); }
+            channel = desc->channel;
+        }
+        D.samplingDensity = D.sigmaT[channel];
+        m->desc.channel = channel;
+    } else if (desc->strategy == MER_STRATEGY_MANUAL) {
+        D.samplingDensity = desc->sampling_density;
+    }
+    D.shapeType = desc->shape_type;
+    for (int i = 0; i < 6; i++) D.shape[i] = desc->shape[i];
+    D.g = desc->hg_g;
+    D.densityScale = desc->density_scale;
+    D.invMaxDensity = density ? 1.0f / (desc->density_scale * 1.0f) : 0.0f; /* heterogeneous.cpp:239-242 */
+    m->desc.medium_sampling_weight = w;
+    m->desc.sampling_density = D.samplingDensity;
+    *out = m;
+    return MER_OK;
+}
+
+void mer_medium_destroy(mer_medium *m) { delete m; }
+
+int mer_medium_resolved(const mer_medium *m, mer_medium_desc *out, float *sampling_density_out) {
+    MER_REQUIRE(m, "null handle");
+    if (out) *out = m->desc;
+    if (sampling_density_out) *sampling_density_out = m->dev.samplingDensity;
+    return MER_OK;
+}
+
+int mer_medium_trace_device(const mer_medium *m, size_t n, float *p_dev, float *v_dev, const float *dist_dev,
+                            uint8_t *success_dev, float *dist_surf_dev, float *opl_dev, int32_t *nsteps_dev,
+                            void *stream) {
+    MER_REQUIRE(m && (n == 0 || (p_dev && v_dev && dist_dev)), "null argument");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(m->device);
+    if (m->rif->mode == MER_RIF_TRICUBIC)
+        MER_LAUNCH(k_trace<MER_RIF_TRICUBIC>, trace_grid(n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev, v_dev,
+                   dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev, (unsigned long long *) nullptr);
+    else
+        MER_LAUNCH(k_trace<MER_RIF_TRILINEAR_PACKED>, trace_grid(n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev,
+                   v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev, (unsigned long long *) nullptr);
+    return MER_OK;
+}
+
+int mer_medium_trace_batch(const mer_medium *m, size_t n, float *p, float *v, const float *dist, uint8_t *success_out,
+                           float *dist_surf_out, float *opl_out, int32_t *nsteps_out) {
+    MER_REQUIRE(m && (n == 0 || (p && v && dist)), "null argument");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(m->device);
+    DevBuf dp, dv, dd, dok, dds, dopl, dns;
+    UP(dp, p, n * 12); UP(dv, v, n * 12); UP(dd, dist, n * 4);
+    UP(dok, (void *) nullptr, n); UP(dds, (void *) nullptr, n * 4); UP(dopl, (void *) nullptr, n * 4); UP(dns, (void *) nullptr, n * 4);
+    int rc = mer_medium_trace_device(m, n, dp.as<float>(), dv.as<float>(), dd.as<float>(), dok.as<uint8_t>(),
+                                     dds.as<float>(), dopl.as<float>(), dns.as<int32_t>(), nullptr);
+    if (rc) return rc;
+    MER_CUDA(cudaDeviceSynchronize());
+    DOWN(p, dp, n * 12); DOWN(v, dv, n * 12); DOWN(success_out, dok, n); DOWN(dist_surf_out, dds, n * 4);
+    DOWN(opl_out, dopl, n * 4); DOWN(nsteps_out, dns, n * 4);
+    return MER_OK;
+}
+
+int mer_medium_trace_till_boundary_batch(const mer_medium *m, size_t n, float *p, float *v, float *dist_surf_out,
+                                         float *opl_out, int32_t *nsteps_out) {
+    MER_REQUIRE(m && (n == 0 || (p && v)), "null argument");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(m->device);
+    DevBuf dp, dv, dds, dopl, dns;
+    UP(dp, p, n * 12); UP(dv, v, n * 12);
+    UP(dds, (void *) nullptr, n * 4); UP(dopl, (void *) nullptr, n * 4); UP(dns, (void *) nullptr, n * 4);
+    if (m->rif->mode == MER_RIF_TRICUBIC)
+        MER_LAUNCH(k_trace_till_boundary<MER_RIF_TRICUBIC>, trace_grid(n), 128, 0, 0, m->dev, n, dp.as<float>(),
+                   dv.as<float>(), dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
+    else
+        MER_LAUNCH(k_trace_till_boundary<MER_RIF_TRILINEAR_PACKED>, trace_grid(n), 128, 0, 0, m->dev, n, dp.as<float>(),
+                   dv.as<float>(), dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
+    MER_CUDA(cudaDeviceSynchronize());
+    DOWN(p, dp, n * 12); DOWN(v, dv, n * 12); DOWN(dist_surf_out, dds, n * 4); DOWN(opl_out, dopl, n * 4);
+    DOWN(nsteps_out, dns, n * 4);
+    return MER_OK;
+}
+
+int mer_medium_sample_distance_batch(const mer_medium *m, size_t n, const float *ray_o, const float *ray_d,
+                                     const float *ray_mint, const float *xi, mer_medium_sampling_records *rec) {
+    MER_REQUIRE(m && rec && (n == 0 || (ray_o && ray_d && xi)), "null argument");
+    if (m->grid)
+        return mer::fail(MER_ERR_UNSUPPORTED,
+                         "sampleDistance with a density grid is only available inside mer_render (Woodcock on the curve)");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(m->device);
+    DevBuf dro, drd, dmint, dxi, dok, dt, dp, dd, dopl, drr, dT, dps, dpf, dss, dns;
+    UP(dro, ray_o, n * 12); UP(drd, ray_d, n * 12); UP(dxi, xi, n * 8);
+    if (ray_mint) UP(dmint, ray_mint, n * 4);
+    UP(dok, (void *) nullptr, n); UP(dt, (void *) nullptr, n * 4); UP(dp, (void *) nullptr, n * 12);
+    UP(dd, (void *) nullptr, n * 12); UP(dopl, (void *) nullptr, n * 4); UP(drr, (void *) nullptr, n * 4);
+    UP(dT, (void *) nullptr, n * 12); UP(dps, (void *) nullptr, n * 4); UP(dpf, (void *) nullptr, n * 4);
+    UP(dss, (void *) nullptr, n * 12); UP(dns, (void *) nullptr, n * 4);
+    SampleDistanceOut o;
+    o.success = dok.as<uint8_t>(); o.t = dt.as<float>(); o.p = dp.as<float>(); o.d = dd.as<float>();
+    o.opl = dopl.as<float>(); o.refRatioSq = drr.as<float>(); o.transmittance = dT.as<float>();
+    o.pdfSuccess = dps.as<float>(); o.pdfFailure = dpf.as<float>(); o.sigmaS = dss.as<float>();
+    o.nsteps = dns.as<int32_t>();
+    const float *mintDev = ray_mint ? dmint.as<float>() : nullptr;
+    if (m->rif->mode == MER_RIF_TRICUBIC)
+        MER_LAUNCH(k_sample_distance<MER_RIF_TRICUBIC>, trace_grid(n), 128, 0, 0, m->dev, n, dro.as<float>(),
+                   drd.as<float>(), mintDev, dxi.as<float>(), o);
+    else
+        MER_LAUNCH(k_sample_distance<MER_RIF_TRILINEAR_PACKED>, trace_grid(n), 128, 0, 0, m->dev, n, dro.as<float>(),
+                   drd.as<float>(), mintDev, dxi.as<float>(), o);
+    MER_CUDA(cudaDeviceSynchronize());
+    DOWN(rec->success, dok, n); DOWN(rec->t, dt, n * 4); DOWN(rec->p, dp, n * 12); DOWN(rec->d, dd, n * 12);
+    DOWN(rec->optical_length, dopl, n * 4); DOWN(rec->ref_ratio_sq, drr, n * 4); DOWN(rec->transmittance, dT, n * 12);
+    DOWN(rec->pdf_success, dps, n * 4); DOWN(rec->pdf_failure, dpf, n * 4); DOWN(rec->sigma_s, dss, n * 12);
+    DOWN(rec->nsteps, dns, n * 4);
+    return MER_OK;
+}
+
+int mer_medium_eval_transmittance_batch(const mer_medium *m, size_t n, const float *mint, const float *maxt,
+                                        float *transmittance_out) {
+    MER_REQUIRE(m && (n == 0 || (mint && maxt && transmittance_out)), "null argument");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(m->device);
+    DevBuf da, db, dout;
+    UP(da, mint, n * 4); UP(db, maxt, n * 4); UP(dout, (void *) nullptr, n * 12);
+    MER_LAUNCH(k_eval_transmittance, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0,
+               m->dev.sigmaT[0], m->dev.sigmaT[1], m->dev.sigmaT[2], n, da.as<float>(), db.as<float>(), dout.as<float>());
+    DOWN(transmittance_out, dout, n * 12);
+    return MER_OK;
+}
+
+int mer_hg_sample_batch(int device, float g, size_t n, const float *wi, const float *xi, float *wo_out, float *pdf_out) {
+    MER_REQUIRE(n == 0 || (wi && xi && wo_out), "null argument");
+    MER_REQUIRE(g > -1.0f && g < 1.0f, "The asymmetry parameter must lie in the interval (-1, 1)!");
+    int rc = mer::check_device(device);
+    if (rc) return rc;
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(device);
+    DevBuf dwi, dxi, dwo, dpdf;
+    UP(dwi, wi, n * 12); UP(dxi, xi, n * 8); UP(dwo, (void *) nullptr, n * 12); UP(dpdf, (void *) nullptr, n * 4);
+    MER_LAUNCH(k_hg_sample, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, g, n, dwi.as<float>(),
+               dxi.as<float>(), dwo.as<float>(), dpdf.as<float>());
+    DOWN(wo_out, dwo, n * 12); DOWN(pdf_out, dpdf, n * 4);
+    return MER_OK;
+}
+
+int mer_hg_eval_batch(int device, float g, size_t n, const float *wi, const float *wo, float *value_out) {
+    MER_REQUIRE(n == 0 || (wi && wo && value_out), "null argument");
+    MER_REQUIRE(g > -1.0f && g < 1.0f, "The asymmetry parameter must lie in the interval (-1, 1)!");
+    int rc = mer::check_device(device);
+    if (rc) return rc;
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(device);
+    DevBuf dwi, dwo, dout;
+    UP(dwi, wi, n * 12); UP(dwo, wo, n * 12); UP(dout, (void *) nullptr, n * 4);
+    MER_LAUNCH(k_hg_eval, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, g, n, dwi.as<float>(),
+               dwo.as<float>(), dout.as<float>());
+    DOWN(value_out, dout, n * 4);
+    return MER_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,662 @@
+/*
+ * mer_render.cu — the integrator: a wavefront eikonal volumetric path tracer for sm_100a.
+ *
+ * What it replaces (paths relative to the MitsubaER tree):
+ *   SamplingIntegrator::renderBlock      src/librender/integrator.cpp:140-190  (pixel/sample loop)
+ *   PerspectiveCamera::sampleRay         src/sensors/perspective.cpp:126-157, 247-269
+ *   VolumetricPathTracer::Li             src/integrators/path/volpath.cpp:84-343 (control flow, RR :326-336)
+ *   PathVertex/PathEdge::sampleNext      src/libbidir/vertex.cpp:247-279, edge.cpp:26-103 (curved-walk semantics:
+ *                                        wi = normalize(-mRec.d), weight *= refRatioSq, exit along normalize(mRec.d))
+ *   Medium::sampleDistance               src/medium/heterogeneousrefractive.cpp:402-568 (free flight, pdfs)
+ *   Woodcock tracking                    src/medium/heterogeneous.cpp:613-658 (density grid, along the curve: R2)
+ *   ImageBlock::put                      include/mitsuba/render/imageblock.h:124-190
+ *   ReconstructionFilter::configure      src/libcore/rfilter.cpp:37-55, src/rfilters/{gaussian,box}.cpp
+ *   HDRFilm::develop                     src/films/hdrfilm.cpp:527-540
+ *
+ * Structure: the CPU's recursive per-pixel loop becomes a WAVEFRONT over a pool
+ * of path slots.  One launch ("pass") advances every live path by a bounded number of
+ * leapfrog steps with the whole path state in registers; paths that finish are replaced
+ * in-kernel by fresh camera samples (one atomic on a global sample counter) so lanes stay
+ * busy; at the end of the pass the survivors are written out COMPACTED with a warp ballot +
+ * one atomicAdd per warp, and the next pass runs over the compacted queue.  Inside a pass
+ * the warp alternates between a convergent stepping phase (all lanes execute the same
+ * 16xLDG.128 + separable contraction) and an event phase (scatter / exit / regenerate) that
+ * is entered only when enough lanes are waiting, which bounds divergence.
+ */
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mer_internal.h"
+
+namespace {
+
+enum PathKind : int {
+    K_FULL = 0,  /* next step: +h */
+    K_REM = 1,   /* next step: +rem (remainder of trace()) */
+    K_BACKF = 2, /* next step: -h   (step back after leaving the shape on a full step) */
+    K_BACKR = 3, /* next step: -rem */
+    K_ENTRY = 4, /* needs the field at p (camera ray just entered the container) */
+    E_BEGIN = 5, /* start a path edge: sample the free-flight distance */
+    E_REACHED = 6, /* trace() returned true */
+    E_EXIT = 7,  /* trace()/traceTillBoundary() left the shape */
+    E_NEW = 8,   /* needs a new camera sample */
+    K_DEAD = 9
+};
+
+enum { FLAG_TB = 1, FLAG_MOVED = 2 };
+
+enum { ST_SAMPLES = 0, ST_STEPS, ST_SCATTER, ST_NULL, ST_EXIT, ST_NONFINITE, ST_COUNT };
+
+/* persisted path state: 6 x 16 bytes per path, SoA by quad so loads/stores are LDG/STG.128 */
+struct PathPool {
+    float4 *q0; /* p.xyz, v.x */
+    float4 *q1; /* v.yz, thr.rg */
+    float4 *q2; /* thr.b, refStart, segDist, distSurf */
+    float4 *q3; /* rem, sd, (int) stepsLeft, (int) depth */
+    uint4 *q4;  /* kind | flags<<8, rng draw index, sampleId lo, hi */
+    float4 *q5; /* n(p), grad n(p): the field at p carried by the fused stepper */
+};
+
+struct RenderParams {
+    MediumDev M;
+    float camO[3], camLeft[3], camUp[3], camDir[3];
+    float tanHalf, aspect, invW, invH;
+    int W, H;
+    int sppTotal, sampleBegin, sampleStride, sppLocal;
+    unsigned long long seed, totalSamples;
+    int maxDepth, rrDepth;
+    float env[3];
+    int hasQuad;
+    float quadO[3], quadU[3], quadV[3], quadLe[3];
+    float filterRadius, filterScale, filterValues[32];
+    int stepsPerPass, maxWait;
+    float *film;
+    PathPool in, out;
+    unsigned nIn;
+    unsigned *nOut;
+    unsigned long long *sampleCounter;
+    unsigned long long *stats;
+};
+
+struct Lane {
+    float3 p, v;
+    float n;
+    float3 G;
+    float thr[3];
+    float refStart, segDist, distSurf, rem, sd;
+    int stepsLeft, depth, kind, flags;
+    PathRng rng;
+    unsigned long long sampleId;
+};
+
+__device__ __forceinline__ bool intersect_shape(const MediumDev &M, float3 o, float3 d, float &tNear) {
+    if (M.shapeType == MER_SHAPE_SPHERE) {
+        float3 oc = f3(o.x - M.shape[0], o.y - M.shape[1], o.z - M.shape[2]);
+        float b = dot3(oc, d), c = dot3(oc, oc) - M.shape[3] * M.shape[3];
+        float disc = b * b - c;
+        if (disc <= 0.0f) return false;
+        float sq = sqrtf(disc), t0 = -b - sq, t1 = -b + sq;
+        if (t1 <= 0.0f) return false;
+        tNear = fmaxf(t0, 0.0f);
+        return true;
+    }
+    float t0 = 0.0f, t1 = INFINITY;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float inv = 1.0f / dd[i];
+        float ta = (M.shape[i] - oo[i]) * inv, tb = (M.shape[3 + i] - oo[i]) * inv;
+        float lo = ta, hi = tb;
+        if (ta > tb) { lo = tb; hi = ta; }
+        t0 = fmaxf(t0, lo);
+        t1 = fminf(t1, hi);
+    }
+    if (!(t0 < t1)) return false;
+    tNear = t0;
+    return true;
+}
+
+__device__ __forceinline__ bool intersect_quad(const RenderParams &P, float3 o, float3 d, float &t) {
+    if (!P.hasQuad) return false;
+    float3 u = f3(P.quadU[0], P.quadU[1], P.quadU[2]), v = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
+    float3 nrm = f3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+    float denom = dot3(d, nrm);
+    if (denom == 0.0f) return false;
+    float3 w = f3(P.quadO[0] - o.x, P.quadO[1] - o.y, P.quadO[2] - o.z);
+    t = dot3(w, nrm) / denom;
+    if (!(t > 0.0f)) return false;
+    float3 q = f3(o.x + t * d.x - P.quadO[0], o.y + t * d.y - P.quadO[1], o.z + t * d.z - P.quadO[2]);
+    float a = dot3(q, u) / dot3(u, u), b = dot3(q, v) / dot3(v, v);
+    return a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f;
+}
+
+/* ImageBlock::put (imageblock.h:144-190) onto the global film with red.global.add.f32 */
+__device__ __forceinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha,
+                                         unsigned &nonfinite) {
+    const float value[5] = {L[0], L[1], L[2], alpha, 1.0f};
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+        if (!isfinite(value[k])) { nonfinite++; return; }
+    const float px = sx - 0.5f, py = sy - 0.5f, r = P.filterRadius;
+    const int x0 = max((int) ceilf(px - r), 0), y0 = max((int) ceilf(py - r), 0),
+              x1 = min((int) floorf(px + r), P.W - 1), y1 = min((int) floorf(py + r), P.H - 1);
+    for (int y = y0; y <= y1; ++y) {
+        const float wy = P.filterValues[min((int) fabsf(((float) y - py) * P.filterScale), 31)];
+        for (int x = x0; x <= x1; ++x) {
+            const float w = P.filterValues[min((int) fabsf(((float) x - px) * P.filterScale), 31)] * wy;
+            float *dest = P.film + ((size_t) y * P.W + x) * 5;
+#pragma unroll
+            for (int k = 0; k < 5; k++) atomicAdd(dest + k, w * value[k]);
+        }
+    }
+}
+
+/* the sample's film position is draw 0/1 of its Philox stream: recomputed, not stored */
+__device__ __forceinline__ void sample_position(const RenderParams &P, const Lane &L, float &sx, float &sy) {
+    unsigned long long pixel = L.sampleId / (unsigned long long) P.sppTotal;
+    int x = (int) (pixel % (unsigned long long) P.W), y = (int) (pixel / (unsigned long long) P.W);
+    uint4 b = philox4x32_10(L.rng.s0, L.rng.s1, 0u, 0u, L.rng.k0, L.rng.k1);
+    sx = (float) x + (float) (b.x >> 8) * (1.0f / 16777216.0f);
+    sy = (float) y + (float) (b.y >> 8) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, const float rad[3], float alpha,
+                                              unsigned *st) {
+    float sx, sy;
+    sample_position(P, L, sx, sy);
+    film_put(P, sx, sy, rad, alpha, st[ST_NONFINITE]);
+    L.kind = E_NEW;
+}
+
+__device__ __forceinline__ void begin_trace(const RenderParams &P, Lane &L, float dist) {
+    L.segDist = dist;
+    L.distSurf = 0.0f;
+    L.flags &= ~(FLAG_TB | FLAG_MOVED);
+    if (isfinite(dist)) {
+        trace_split(dist, P.M.h, L.stepsLeft, L.rem);
+        L.kind = L.stepsLeft > 0 ? K_FULL : K_REM;
+    } else { /* traceTillBoundary, heterogeneousrefractive.cpp:742-776 */
+        L.flags |= FLAG_TB;
+        L.stepsLeft = 100000;
+        L.rem = 0.0f;
+        L.kind = K_FULL;
+    }
+}
+
+/* exponential free-flight pdfs + transmittance at geometric length d (:533-562) */
+__device__ __forceinline__ void edge_weight(const MediumDev &M, float sd, float d, bool success, float edge[3]) {
+    float pdfFailure = 0.0f, pdfSuccess = 0.0f;
+    if (M.strategy == MER_STRATEGY_BALANCE) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float tmp = fastexp_dev(__fmul_rn(-M.sigmaT[c], d));
+            pdfFailure = __fadd_rn(pdfFailure, tmp);
+            pdfSuccess = __fadd_rn(pdfSuccess, __fmul_rn(M.sigmaT[c], tmp));
+        }
+        pdfFailure = __fdiv_rn(pdfFailure, 3.0f);
+        pdfSuccess = __fdiv_rn(pdfSuccess, 3.0f);
+    } else {
+        pdfFailure = fastexp_dev(__fmul_rn(-sd, d));
+        pdfSuccess = __fmul_rn(sd, pdfFailure);
+    }
+    float T[3], tmax = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        T[c] = fastexp_dev(__fmul_rn(M.sigmaT[c], -d));
+        tmax = fmaxf(tmax, T[c]);
+    }
+    if (tmax < 1e-20f) T[0] = T[1] = T[2] = 0.0f;
+    const float ps = __fmul_rn(pdfSuccess, M.weight), pf = __fadd_rn(__fmul_rn(M.weight, pdfFailure), 1.0f - M.weight);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        edge[c] = success ? __fdiv_rn(__fmul_rn(M.sigmaS[c], T[c]), ps) : __fdiv_rn(T[c], pf);
+}
+
+/* Everything that is not a leapfrog step.  Runs until the lane is steppable again or dead. */
+__device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, unsigned *st) {
+    const MediumDev &M = P.M;
+    const float zero[3] = {0.f, 0.f, 0.f};
+    while (L.kind >= E_BEGIN && L.kind != K_DEAD) {
+        if (L.kind == E_NEW) {
+            /* ---- SamplingIntegrator::renderBlock: next (pixel, sample) */
+            unsigned long long g = atomicAdd(P.sampleCounter, 1ULL);
+            if (g >= P.totalSamples) { L.kind = K_DEAD; break; }
+            st[ST_SAMPLES]++;
+            unsigned long long pixel = g / (unsigned long long) P.sppLocal;
+            int k = (int) (g % (unsigned long long) P.sppLocal);
+            int s = P.sampleBegin + k * P.sampleStride;
+            L.sampleId = pixel * (unsigned long long) P.sppTotal + (unsigned long long) s;
+            L.rng.init(P.seed, L.sampleId, 0u);
+            int x = (int) (pixel % (unsigned long long) P.W), y = (int) (pixel / (unsigned long long) P.W);
+            float sx = (float) x + L.rng.next(), sy = (float) y + L.rng.next();
+            /* PerspectiveCamera::sampleRay, closed form of m_sampleToCamera */
+            float cx = (1.0f - 2.0f * (sx * P.invW)) * P.tanHalf, cy = (1.0f - 2.0f * (sy * P.invH)) * P.tanHalf / P.aspect;
+            float inv = 1.0f / sqrtf(cx * cx + cy * cy + 1.0f);
+            cx *= inv; cy *= inv;
+            float cz = inv;
+            float3 d = f3(P.camLeft[0] * cx + P.camUp[0] * cy + P.camDir[0] * cz,
+                          P.camLeft[1] * cx + P.camUp[1] * cy + P.camDir[1] * cz,
+                          P.camLeft[2] * cx + P.camUp[2] * cy + P.camDir[2] * cz);
+            float3 o = f3(P.camO[0], P.camO[1], P.camO[2]);
+            float tBox, tQuad;
+            bool hitBox = intersect_shape(M, o, d, tBox), hitQuad = intersect_quad(P, o, d, tQuad);
+            if (hitQuad && (!hitBox || tQuad < tBox)) { finish_sample(P, L, P.quadLe, 1.0f, st); continue; }
+            if (!hitBox) { finish_sample(P, L, P.env, 0.0f, st); continue; }
+            L.depth = 1;
+            if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
+            L.depth = 2; /* index-matched container surface, volpath.cpp:287-296 */
+            L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
+            L.v = d;
+            L.thr[0] = L.thr[1] = L.thr[2] = 1.0f;
+            L.flags = 0;
+            L.n = 1.0f;
+            L.G = f3(0.f, 0.f, 0.f);
+            L.kind = K_ENTRY;
+        } else if (L.kind == E_BEGIN) {
+            /* ---- Medium::sampleDistance prologue, heterogeneousrefractive.cpp:402-475; L.v = unit direction */
+            if (!rif_inside_limits(M.rif, L.p)) { finish_sample(P, L, zero, 1.0f, st); continue; }
+            L.refStart = L.n;
+            L.v = f3(L.v.x * L.n, L.v.y * L.n, L.v.z * L.n);
+            float dist;
+            if (M.hasGrid) {
+                dist = __fmul_rn(-fastlog_dev(1.0f - L.rng.next()), M.invMaxDensity);
+            } else {
+                float rnd = L.rng.next();
+                L.sd = M.samplingDensity;
+                if (rnd < M.weight) {
+                    rnd = __fdiv_rn(rnd, M.weight);
+                    if (M.strategy == MER_STRATEGY_BALANCE) L.sd = M.sigmaT[min((int) (L.rng.next() * 3.0f), 2)];
+                    dist = __fdiv_rn(-fastlog_dev(1.0f - rnd), L.sd);
+                } else {
+                    dist = INFINITY;
+                }
+            }
+            begin_trace(P, L, dist);
+        } else {
+            /* ---- end of a path edge */
+            bool scatter = false;
+            float edge[3];
+            if (L.kind == E_REACHED) {
+                if (M.hasGrid) {
+                    /* Woodcock acceptance, heterogeneous.cpp:631-644 */
+                    float densityAtT = __fmul_rn(grid_lookup(M.grid, L.p), M.densityScale);
+                    if (__fmul_rn(densityAtT, M.invMaxDensity) > L.rng.next()) {
+                        scatter = true;
+                        edge[0] = M.albedo[0]; edge[1] = M.albedo[1]; edge[2] = M.albedo[2];
+                    } else {
+                        st[ST_NULL]++;
+                        float dist = __fmul_rn(-fastlog_dev(1.0f - L.rng.next()), M.invMaxDensity);
+                        int moved = L.flags & FLAG_MOVED;
+                        begin_trace(P, L, dist);
+                        L.flags |= moved;
+                        continue;
+                    }
+                } else {
+                    if (!(L.flags & FLAG_MOVED)) { finish_sample(P, L, zero, 1.0f, st); continue; } /* :517-520 */
+                    scatter = true;
+                    edge_weight(M, L.sd, L.segDist, true, edge);
+                }
+            } else { /* E_EXIT */
+                if (M.hasGrid) edge[0] = edge[1] = edge[2] = 1.0f;
+                else edge_weight(M, L.sd, L.distSurf, false, edge);
+            }
+            float rrs = (float) (1.0 / (double) (L.refStart * L.refStart)); /* :469 */
+            rrs *= L.n * L.n;                                                /* :501, refEnd = n(p) */
+            const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
+            if (scatter) {
+                st[ST_SCATTER]++;
+                if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
+#pragma unroll
+                for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
+                float3 wi = f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv);
+                float u1 = L.rng.next(), u2 = L.rng.next();
+                L.v = hg_sample_dev(M.g, wi, u1, u2);
+                if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
+                    float q = fminf(fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2])), 0.95f);
+                    if (L.rng.next() >= q) { finish_sample(P, L, zero, 1.0f, st); continue; }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) L.thr[c] /= q;
+                }
+                L.kind = E_BEGIN; /* field at p is still valid */
+            } else {
+                st[ST_EXIT]++;
+#pragma unroll
+                for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
+                if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
+                L.depth++;
+                float3 d = f3(L.v.x * vinv, L.v.y * vinv, L.v.z * vinv);
+                float tq;
+                const float *Le = intersect_quad(P, L.p, d, tq) ? P.quadLe : P.env;
+                float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
+                finish_sample(P, L, rad, 1.0f, st);
+            }
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_render_pass(const __grid_constant__ RenderParams P) {
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const MediumDev &M = P.M;
+    Lane L;
+    unsigned st[ST_COUNT];
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; i++) st[i] = 0;
+
+    if (tid < P.nIn) {
+        float4 a = P.in.q0[tid], b = P.in.q1[tid], c = P.in.q2[tid], d = P.in.q3[tid];
+        uint4 e = P.in.q4[tid];
+        L.p = f3(a.x, a.y, a.z);
+        L.v = f3(a.w, b.x, b.y);
+        L.thr[0] = b.z; L.thr[1] = b.w; L.thr[2] = c.x;
+        L.refStart = c.y; L.segDist = c.z; L.distSurf = c.w;
+        L.rem = d.x; L.sd = d.y; L.stepsLeft = __float_as_int(d.z); L.depth = __float_as_int(d.w);
+        L.kind = (int) (e.x & 0xffu); L.flags = (int) (e.x >> 8);
+        L.sampleId = ((unsigned long long) e.w << 32) | e.z;
+        L.rng.init(P.seed, L.sampleId, e.y);
+        float4 fg = P.in.q5[tid];
+        L.n = fg.x; L.G = f3(fg.y, fg.z, fg.w);
+    } else {
+        L.p = L.v = L.G = f3(0.f, 0.f, 0.f);
+        L.n = 1.0f;
+        L.thr[0] = L.thr[1] = L.thr[2] = 0.0f;
+        L.refStart = L.segDist = L.distSurf = L.rem = L.sd = 0.0f;
+        L.stepsLeft = L.depth = L.flags = 0;
+        L.sampleId = 0;
+        L.rng.init(P.seed, 0ULL, 0u);
+        L.kind = E_NEW;
+    }
+
+    const float h = M.h;
+    int budget = P.stepsPerPass;
+    float oplUnused = 0.0f;
+    while (true) {
+        /* ---------------- convergent stepping phase */
+        while (budget > 0) {
+            const bool stepping = L.kind <= K_ENTRY;
+            const unsigned ms = __ballot_sync(0xffffffffu, stepping);
+            const unsigned mw = __ballot_sync(0xffffffffu, L.kind >= E_BEGIN && L.kind != K_DEAD);
+            if (ms == 0u || __popc(mw) >= P.maxWait) break;
+            budget--;
+            if (stepping) {
+                /* K_ENTRY is a zero-length step: with hc = 0 the kicks and the drift are exact no-ops and
+                 * only the field fetch remains, so the warp has ONE lookup call site */
+                const int kind = L.kind;
+                const float hc = kind == K_FULL ? h : (kind == K_REM ? L.rem : (kind == K_BACKF ? -h : (kind == K_BACKR ? -L.rem : 0.0f)));
+                const float3 pOld = L.p;
+                er_step_fused<MODE>(M.rif, L.p, L.v, L.n, L.G, hc, oplUnused);
+                const bool inside = inside_shape(M, L.p);
+                const bool moved = L.p.x != pOld.x || L.p.y != pOld.y || L.p.z != pOld.z;
+                if (kind == K_ENTRY) {
+                    L.kind = E_BEGIN;
+                } else {
+                    st[ST_STEPS]++;
+                    if (kind == K_FULL) {
+                        if (inside) {
+                            L.distSurf += h;
+                            if (moved) L.flags |= FLAG_MOVED;
+                            if (--L.stepsLeft == 0) L.kind = (L.flags & FLAG_TB) ? E_EXIT : K_REM;
+                        } else {
+                            L.kind = K_BACKF;
+                        }
+                    } else if (kind == K_REM) {
+                        if (inside) {
+                            L.distSurf += L.rem;
+                            if (moved) L.flags |= FLAG_MOVED;
+                            L.kind = E_REACHED;
+                        } else {
+                            L.kind = K_BACKR;
+                        }
+                    } else {
+                        if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= h; /* :761 */
+                        L.kind = E_EXIT;
+                    }
+                }
+            }
+        }
+        /* ---------------- event phase */
+        if (L.kind >= E_BEGIN && L.kind != K_DEAD) handle_events(P, L, st);
+        const unsigned alive = __ballot_sync(0xffffffffu, L.kind != K_DEAD);
+        if (alive == 0u || budget <= 0) break;
+    }
+
+    /* ---------------- compaction: survivors go to the output queue, one atomic per warp */
+    const bool live = L.kind != K_DEAD;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    unsigned base = 0;
+    if (lane == 0 && m) base = atomicAdd(P.nOut, (unsigned) __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) {
+        const unsigned o = base + __popc(m & ((1u << lane) - 1u));
+        P.out.q0[o] = make_float4(L.p.x, L.p.y, L.p.z, L.v.x);
+        P.out.q1[o] = make_float4(L.v.y, L.v.z, L.thr[0], L.thr[1]);
+        P.out.q2[o] = make_float4(L.thr[2], L.refStart, L.segDist, L.distSurf);
+        P.out.q3[o] = make_float4(L.rem, L.sd, __int_as_float(L.stepsLeft), __int_as_float(L.depth));
+        P.out.q4[o] = make_uint4((unsigned) L.kind | ((unsigned) L.flags << 8), L.rng.k, (unsigned) L.sampleId,
+                                 (unsigned) (L.sampleId >> 32));
+        P.out.q5[o] = make_float4(L.n, L.G.x, L.G.y, L.G.z);
+    }
+
+    /* ---------------- statistics: warp reduce, one atomic per warp and counter */
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; i++) {
+        unsigned v = st[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(P.stats + i, (unsigned long long) v);
+    }
+}
+
+/* HDRFilm::develop: ESpectrumAlphaWeight -> RGB */
+__global__ void k_develop(size_t nPixels, const float *__restrict__ film, float *__restrict__ rgb) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nPixels; i += (size_t) gridDim.x * blockDim.x) {
+        float w = film[5 * i + 4], inv = w != 0.0f ? 1.0f / w : 0.0f;
+        rgb[3 * i] = film[5 * i] * inv;
+        rgb[3 * i + 1] = film[5 * i + 1] * inv;
+        rgb[3 * i + 2] = film[5 * i + 2] * inv;
+    }
+}
+
+/* ReconstructionFilter::configure (rfilter.cpp:37-55) for gaussian (stddev .5) and box (radius .5+1e-5) */
+void configure_filter(int type, RenderParams &P) {
+    const int RES = 31;
+    const float stddev = 0.5f;
+    const float radius = type == MER_FILTER_GAUSSIAN ? 4 * stddev : 0.5f + 1e-5f;
+    float sum = 0;
+    for (int i = 0; i < RES; i++) {
+        float x = (radius * i) / RES, value;
+        if (type == MER_FILTER_GAUSSIAN) {
+            float alpha = -1.0f / (2.0f * stddev * stddev);
+            value = std::max(0.0f, (float) std::exp((double) (alpha * x * x)) -
+                                       (float) std::exp((double) (alpha * radius * radius)));
+        } else {
+            value = std::abs(x) <= radius ? 1.0f : 0.0f;
+        }
+        P.filterValues[i] = value;
+        sum += value;
+    }
+    P.filterValues[RES] = 0.0f;
+    P.filterScale = RES / radius;
+    P.filterRadius = radius;
+    sum *= 2 * radius / RES;
+    float normalization = 1.0f / sum;
+    for (int i = 0; i < RES; i++) P.filterValues[i] *= normalization;
+}
+
+void configure_camera(const mer_render_desc *r, RenderParams &P) {
+    /* Transform::lookAt, src/libcore/transform.cpp:191-214 */
+    float d[3], len = 0;
+    for (int i = 0; i < 3; i++) { P.camO[i] = r->cam_origin[i]; d[i] = r->cam_target[i] - r->cam_origin[i]; len += d[i] * d[i]; }
+    len = std::sqrt(len);
+    for (int i = 0; i < 3; i++) P.camDir[i] = d[i] / len;
+    const float *u = r->cam_up, *dir = P.camDir;
+    float l[3] = {u[1] * dir[2] - u[2] * dir[1], u[2] * dir[0] - u[0] * dir[2], u[0] * dir[1] - u[1] * dir[0]};
+    len = std::sqrt(l[0] * l[0] + l[1] * l[1] + l[2] * l[2]);
+    for (int i = 0; i < 3; i++) P.camLeft[i] = l[i] / len;
+    P.camUp[0] = dir[1] * P.camLeft[2] - dir[2] * P.camLeft[1];
+    P.camUp[1] = dir[2] * P.camLeft[0] - dir[0] * P.camLeft[2];
+    P.camUp[2] = dir[0] * P.camLeft[1] - dir[1] * P.camLeft[0];
+    P.tanHalf = std::tan(0.5f * r->fov_deg * (float) (M_PI / 180.0));
+    P.aspect = (float) r->width / (float) r->height;
+    P.invW = 1.0f / r->width;
+    P.invH = 1.0f / r->height;
+}
+
+struct Scratch { /* per-call device scratch, freed on every exit path */
+    void *pool[12] = {nullptr};
+    unsigned *nOut = nullptr;
+    unsigned long long *counters = nullptr; /* [0] sample counter, [1..] stats */
+    unsigned long long *hostPinned = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~Scratch() {
+        for (void *p : pool) cudaFree(p);
+        cudaFree(nOut);
+        cudaFree(counters);
+        if (hostPinned) cudaFreeHost(hostPinned);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+    }
+};
+
+} /* namespace */
+
+extern "C" {
+
+int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film_dev, mer_render_stats *stats_out,
+                      void *stream_) {
+    MER_REQUIRE(m && r && film_dev, "null argument");
+    MER_REQUIRE(r->width > 0 && r->height > 0 && r->spp_total > 0, "film size and sample count must be positive");
+    MER_REQUIRE(r->sample_stride >= 1 && r->sample_begin >= 0, "bad sample sharding");
+    MER_REQUIRE(r->filter == MER_FILTER_BOX || r->filter == MER_FILTER_GAUSSIAN, "unknown reconstruction filter");
+    mer::DeviceGuard guard(m->device);
+    cudaStream_t stream = (cudaStream_t) stream_;
+
+    RenderParams P;
+    memset(&P, 0, sizeof(P));
+    P.M = m->dev;
+    configure_camera(r, P);
+    configure_filter(r->filter, P);
+    P.W = r->width; P.H = r->height;
+    P.sppTotal = r->spp_total; P.sampleBegin = r->sample_begin; P.sampleStride = r->sample_stride;
+    P.sppLocal = r->sample_begin < r->spp_total ? (r->spp_total - r->sample_begin + r->sample_stride - 1) / r->sample_stride : 0;
+    P.seed = r->seed;
+    P.totalSamples = (unsigned long long) r->width * r->height * (unsigned long long) P.sppLocal;
+    P.maxDepth = r->max_depth; P.rrDepth = r->rr_depth;
+    for (int i = 0; i < 3; i++) {
+        P.env[i] = r->env_radiance[i];
+        P.quadO[i] = r->quad_origin[i]; P.quadU[i] = r->quad_u[i]; P.quadV[i] = r->quad_v[i]; P.quadLe[i] = r->quad_radiance[i];
+    }
+    P.hasQuad = r->has_quad;
+    P.stepsPerPass = r->steps_per_pass > 0 ? r->steps_per_pass : 2048;
+    P.maxWait = 8;
+    P.film = film_dev;
+
+    const unsigned TPB = 128;
+    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 2048u;
+    pool = ((pool + TPB - 1) / TPB) * TPB;
+    if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) (((P.totalSamples + TPB - 1) / TPB) * TPB);
+    if (pool == 0) pool = TPB;
+
+    Scratch S;
+    const size_t qBytes = (size_t) pool * 16;
+    for (int i = 0; i < 12; i++) MER_CUDA(cudaMalloc(&S.pool[i], qBytes));
+    PathPool A = {(float4 *) S.pool[0], (float4 *) S.pool[1], (float4 *) S.pool[2], (float4 *) S.pool[3], (uint4 *) S.pool[4], (float4 *) S.pool[5]};
+    PathPool B = {(float4 *) S.pool[6], (float4 *) S.pool[7], (float4 *) S.pool[8], (float4 *) S.pool[9], (uint4 *) S.pool[10], (float4 *) S.pool[11]};
+    MER_CUDA(cudaMalloc(&S.nOut, sizeof(unsigned)));
+    MER_CUDA(cudaMalloc(&S.counters, (1 + ST_COUNT) * sizeof(unsigned long long)));
+    MER_CUDA(cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long)));
+    MER_CUDA(cudaMemsetAsync(S.counters, 0, (1 + ST_COUNT) * sizeof(unsigned long long), stream));
+    MER_CUDA(cudaEventCreate(&S.ev0));
+    MER_CUDA(cudaEventCreate(&S.ev1));
+    P.nOut = S.nOut;
+    P.sampleCounter = S.counters;
+    P.stats = S.counters + 1;
+
+    unsigned nLive = 0;
+    unsigned long long started = 0, passes = 0, launches = 0;
+    MER_CUDA(cudaEventRecord(S.ev0, stream));
+    while (true) {
+        const bool fresh = started < P.totalSamples;
+        const unsigned threads = fresh ? pool : nLive;
+        if (threads == 0) break;
+        P.in = (passes & 1) ? B : A;
+        P.out = (passes & 1) ? A : B;
+        P.nIn = nLive;
+        MER_CUDA(cudaMemsetAsync(S.nOut, 0, sizeof(unsigned), stream));
+        const unsigned blocks = (threads + TPB - 1) / TPB;
+        if (m->rif->mode == MER_RIF_TRICUBIC)
+            MER_LAUNCH(k_render_pass<MER_RIF_TRICUBIC>, blocks, TPB, 0, stream, P);
+        else
+            MER_LAUNCH(k_render_pass<MER_RIF_TRILINEAR_PACKED>, blocks, TPB, 0, stream, P);
+        launches++;
+        passes++;
+        /* the only host<->device traffic of a pass: 12 bytes telling the host how to size the next one */
+        MER_CUDA(cudaMemcpyAsync(S.hostPinned, S.nOut, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        MER_CUDA(cudaMemcpyAsync(S.hostPinned + 1, S.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        MER_CUDA(cudaStreamSynchronize(stream));
+        nLive = *(unsigned *) S.hostPinned;
+        started = S.hostPinned[1];
+        if (nLive == 0 && started >= P.totalSamples) break;
+    }
+    MER_CUDA(cudaEventRecord(S.ev1, stream));
+    MER_CUDA(cudaEventSynchronize(S.ev1));
+    if (stats_out) {
+        unsigned long long hs[1 + ST_COUNT];
+        MER_CUDA(cudaMemcpy(hs, S.counters, sizeof(hs), cudaMemcpyDeviceToHost));
+        memset(stats_out, 0, sizeof(*stats_out));
+        stats_out->samples = hs[1 + ST_SAMPLES];
+        stats_out->ray_steps = hs[1 + ST_STEPS];
+        stats_out->scatter_events = hs[1 + ST_SCATTER];
+        stats_out->null_collisions = hs[1 + ST_NULL];
+        stats_out->boundary_exits = hs[1 + ST_EXIT];
+        stats_out->nonfinite_dropped = hs[1 + ST_NONFINITE];
+        stats_out->passes = passes;
+        stats_out->kernel_launches = launches;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, S.ev0, S.ev1);
+        stats_out->device_ms = ms;
+    }
+    return MER_OK;
+}
+
+int mer_render(const mer_medium *m, const mer_render_desc *r, float *film_host, mer_render_stats *stats_out) {
+    MER_REQUIRE(m && r && film_host, "null argument");
+    MER_REQUIRE(r->width > 0 && r->height > 0, "film size must be positive");
+    mer::DeviceGuard guard(m->device);
+    float *film = nullptr;
+    const size_t bytes = (size_t) r->width * r->height * 5 * sizeof(float);
+    MER_CUDA(cudaMalloc(&film, bytes));
+    cudaError_t e = cudaMemset(film, 0, bytes);
+    int rc = e == cudaSuccess ? mer_render_device(m, r, film, stats_out, nullptr) : mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));
+    if (rc == MER_OK) {
+        e = cudaMemcpy(film_host, film, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(film);
+    return rc;
+}
+
+int mer_film_develop(int device, int32_t width, int32_t height, const float *film, float *rgb_out) {
+    MER_REQUIRE(film && rgb_out && width > 0 && height > 0, "bad argument");
+    int rc = mer::check_device(device);
+    if (rc) return rc;
+    mer::DeviceGuard guard(device);
+    const size_t n = (size_t) width * height;
+    float *df = nullptr, *dr = nullptr;
+    MER_CUDA(cudaMalloc(&df, n * 5 * sizeof(float)));
+    MER_CUDA(cudaMalloc(&dr, n * 3 * sizeof(float)));
+    cudaError_t e = cudaMemcpy(df, film, n * 5 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_develop<<<(unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256>>>(n, df, dr);
+        mer::g_launches.fetch_add(1);
+        e = cudaMemcpy(rgb_out, dr, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(df);
+    cudaFree(dr);
+    if (e != cudaSuccess) return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));
+    return MER_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,499 @@
+/*
+ * mer_volume.cu — VolumeDataSource side of the path: .vol I/O, the B-spline prefilter on the
+ * GPU, the RIF / density handles and their batch evaluation entry points.
+ *
+ * Reference (paths relative to the MitsubaER tree):
+ *   Spline<3>::initialize / build1d / build3d   include/mitsuba/core/basisspline.h:124-138, 812-840, 865-890
+ *   SplineDataSource                            src/volume/splinevolume.cpp:87-111, 204-360
+ *   GridDataSource                              src/volume/gridvolume.cpp:188-199, 337-363
+ *   .vol v3 format                              src/volume/splinevolume.cpp:39-75, mfiles/writeGridToVol.m
+ */
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "mer_internal.h"
+
+/* ===================================================================== prefilter (a3)
+ * One thread per grid line; three passes (y, x, z — the reference's order).  Line l of a pass
+ * starts at `base(l)` and advances by `stride`.  In the y and z passes adjacent threads own
+ * adjacent x, so every load/store of a warp is one coalesced 128-byte line; in the x pass a
+ * thread walks its own 128-byte lines (L1-resident between consecutive elements).
+ *
+ * Arithmetic follows build1d exactly: the initial causal coefficient is accumulated with the
+ * products formed in double (C pow() semantics) and the running sum rounded to float after every
+ * term; the recursions are single precision WITHOUT fma contraction (__fmul_rn/__fadd_rn), as
+ * the reference's x86 build has none.  z1^e terms with e >= 64 (< 1e-36) are skipped: they
+ * cannot change a float accumulator.
+ */
+enum { PASS_Y = 0, PASS_X = 1, PASS_Z = 2 };
+
+__global__ void __launch_bounds__(128)
+k_prefilter(const float *in, float *out, int N0, int N1, int N2, int pass) {
+    const size_t n0 = N0, n01 = (size_t) N0 * N1;
+    size_t nLines, stride, base;
+    int len;
+    const size_t l = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (pass == PASS_Y) {
+        nLines = n0 * N2; len = N1; stride = n0;
+        base = (l / n0) * n01 + (l % n0);
+    } else if (pass == PASS_X) {
+        nLines = (size_t) N1 * N2; len = N0; stride = 1;
+        base = l * n0;
+    } else {
+        nLines = n01; len = N2; stride = n01;
+        base = l;
+    }
+    if (l >= nLines) return;
+    const float *src = in + base;
+    float *dst = out + base;
+
+    const float z1 = (float) (-2.0 + sqrt(3.0));
+    const double z1d = (double) z1;
+    const int CUT = 64;
+    float cp = 0.0f;
+    double zp = 1.0;
+    for (int i = 0; i < len && i < CUT; i++) {
+        cp = (float) ((double) cp + (double) src[(size_t) i * stride] * zp);
+        zp *= z1d;
+    }
+    for (int i = len - 2; i > 0; i--) {
+        int e = 2 * len - 2 - i;
+        if (e >= CUT) break; /* e grows as i decreases */
+        cp = (float) ((double) cp + (double) src[(size_t) i * stride] * pow(z1d, (double) e));
+    }
+    cp = (float) ((double) cp / (1.0 - pow(z1d, (double) (2 * len - 2))));
+
+    /* causal recursion, storing c+ in place */
+    dst[0] = cp;
+    float cpPrev2 = cp;
+    for (int i = 1; i < len; i++) {
+        cpPrev2 = cp;
+        cp = __fadd_rn(src[(size_t) i * stride], __fmul_rn(z1, cp));
+        dst[(size_t) i * stride] = cp;
+    }
+    /* anti-causal recursion */
+    const float gain = __fdiv_rn(z1, __fsub_rn(__fmul_rn(z1, z1), 1.0f));
+    float cn = __fmul_rn(gain, __fadd_rn(cp, __fmul_rn(z1, cpPrev2)));
+    dst[(size_t) (len - 1) * stride] = __fmul_rn(6.0f, cn);
+    for (int i = len - 2; i >= 0; i--) {
+        cn = __fmul_rn(z1, __fsub_rn(cn, dst[(size_t) i * stride]));
+        dst[(size_t) i * stride] = __fmul_rn(6.0f, cn);
+    }
+}
+
+/* coeff [z][y][x] -> coeff4 [z][y][x] = (c[x-1], c[x], c[x+1], c[x+2]), x clamped */
+__global__ void k_expand_coeff4(const float *__restrict__ coeff, float4 *__restrict__ coeff4, int N0, size_t total) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const int x = (int) (i % (size_t) N0);
+        const float *row = coeff + (i - x);
+        coeff4[i] = make_float4(row[max(x - 1, 0)], row[x], row[min(x + 1, N0 - 1)], row[min(x + 2, N0 - 1)]);
+    }
+}
+
+/* fast mode: sample the spline (value + gradient) at every grid node */
+__global__ void k_build_packed(RifDev R, float4 *__restrict__ packed, size_t total) {
+    const size_t n0 = R.N[0], n01 = (size_t) R.N[0] * R.N[1];
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const int x = (int) (i % n0), y = (int) ((i / n0) % R.N[1]), z = (int) (i / n01);
+        /* node position in volume space: xmin + index / xres */
+        float3 pv = f3(R.xmin[0] + (float) x / R.xres[0], R.xmin[1] + (float) y / R.xres[1],
+                       R.xmin[2] + (float) z / R.xres[2]);
+        float f;
+        float3 g;
+        rif_tricubic(R, pv, f, g);
+        packed[i] = make_float4(f, g.x, g.y, g.z);
+    }
+}
+
+/* SplineDataSource::value / gradient / valueAndGradient over a batch */
+template <int MODE>
+__global__ void k_rif_eval(RifDev R, size_t n, const float *__restrict__ p, float *__restrict__ f,
+                           float *__restrict__ g) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        float val;
+        float3 grad;
+        rif_lookup<MODE>(R, f3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), val, grad);
+        if (f) f[i] = val;
+        if (g) { g[3 * i] = grad.x; g[3 * i + 1] = grad.y; g[3 * i + 2] = grad.z; }
+    }
+}
+
+__global__ void k_rif_inside(RifDev R, size_t n, const float *__restrict__ p, uint8_t *__restrict__ out) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+        out[i] = rif_inside_limits(R, f3(p[3 * i], p[3 * i + 1], p[3 * i + 2])) ? 1 : 0;
+}
+
+__global__ void k_grid_lookup(GridDev D, size_t n, const float *__restrict__ p, float *__restrict__ out) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+        out[i] = grid_lookup(D, f3(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
+}
+
+/* ===================================================================== host side */
+namespace {
+
+int validate_desc(const mer_volume_desc *d, int minRes) {
+    if (!d) return mer::fail(MER_ERR_INVALID, "null volume descriptor");
+    for (int i = 0; i < 3; i++) {
+        if (d->res[i] < minRes) return mer::fail(MER_ERR_INVALID, "volume resolution too small");
+        if (!(d->bbox_max[i] > d->bbox_min[i])) return mer::fail(MER_ERR_INVALID, "invalid volume bounding box");
+    }
+    return MER_OK;
+}
+
+size_t voxels(const mer_volume_desc *d) { return (size_t) d->res[0] * d->res[1] * d->res[2]; }
+
+void fill_rif_dev(mer_rif *r) {
+    RifDev &D = r->dev;
+    const mer_volume_desc &d = r->desc;
+    D.mode = r->mode;
+    for (int i = 0; i < 3; i++) {
+        D.N[i] = d.res[i];
+        D.xmin[i] = d.bbox_min[i];
+        D.xres[i] = (float) (d.res[i] - 1) / (d.bbox_max[i] - d.bbox_min[i]); /* basisspline.h:130 */
+        /* m_interpolatableLimits, splinevolume.cpp:280-281: 2*stride + Epsilon in double, stored single */
+        float stride = (float) (1.0 / (double) D.xres[i]); /* getStride(), basisspline.h:622-624 */
+        float margin = (float) (2.0 * (double) stride + (double) MER_EPSILON);
+        D.limLo[i] = d.bbox_min[i] + margin;
+        D.limHi[i] = d.bbox_max[i] + (-margin);
+    }
+    D.hasXform = d.has_transform != 0;
+    for (int i = 0; i < 12; i++) D.M[i] = D.hasXform ? d.world_to_volume[i] : ((i == 0 || i == 5 || i == 10) ? 1.f : 0.f);
+    D.coeff = r->d_coeff;
+    D.coeff4 = r->d_coeff4;
+    D.packed = r->d_packed;
+}
+
+int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
+    const mer_volume_desc &d = r->desc;
+    const size_t total = voxels(&d);
+    MER_CUDA(cudaMalloc(&r->d_coeff, total * sizeof(float)));
+    const int N0 = d.res[0], N1 = d.res[1], N2 = d.res[2];
+    const unsigned T = 128;
+    MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N2, T), T, 0, s, data_dev, r->d_coeff, N0, N1, N2, (int) PASS_Y);
+    MER_LAUNCH(k_prefilter, mer_blocks((size_t) N1 * N2, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_X);
+    MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N1, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_Z);
+    MER_CUDA(cudaMalloc(&r->d_coeff4, total * sizeof(float4)));
+    const unsigned G = (unsigned) std::min<size_t>(mer_blocks(total, 256), 148u * 16u);
+    MER_LAUNCH(k_expand_coeff4, G, 256, 0, s, r->d_coeff, r->d_coeff4, N0, total);
+    fill_rif_dev(r);
+    if (r->mode == MER_RIF_TRILINEAR_PACKED) {
+        MER_CUDA(cudaMalloc(&r->d_packed, total * sizeof(float4)));
+        fill_rif_dev(r);
+        MER_LAUNCH(k_build_packed, G, 256, 0, s, r->dev, r->d_packed, total);
+        MER_CUDA(cudaStreamSynchronize(s));
+        /* the 4x-expanded cubic coefficients are only needed to build the packed grid */
+        cudaFree(r->d_coeff4);
+        r->d_coeff4 = nullptr;
+        fill_rif_dev(r);
+    }
+    MER_CUDA(cudaStreamSynchronize(s));
+    return MER_OK;
+}
+
+int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *data, int32_t *encoding,
+                  int32_t *channels) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return mer::fail(MER_ERR_INVALID, std::string("cannot open volume file: ") + path);
+    unsigned char hdr[48];
+    if (fread(hdr, 1, 48, f) != 48) { fclose(f); return mer::fail(MER_ERR_INVALID, "volume file too short"); }
+    if (hdr[0] != 'V' || hdr[1] != 'O' || hdr[2] != 'L') {
+        fclose(f);
+        return mer::fail(MER_ERR_INVALID, "Encountered an invalid volume data file (incorrect header identifier)");
+    }
+    if (hdr[3] != 3) {
+        fclose(f);
+        return mer::fail(MER_ERR_INVALID, "Encountered an invalid volume data file (incorrect file version)");
+    }
+    int32_t enc, res[3], ch;
+    float bb[6];
+    memcpy(&enc, hdr + 4, 4);
+    memcpy(res, hdr + 8, 12);
+    memcpy(&ch, hdr + 20, 4);
+    memcpy(bb, hdr + 24, 24);
+    if (encoding) *encoding = enc;
+    if (channels) *channels = ch;
+    if (desc) {
+        memset(desc, 0, sizeof(*desc));
+        for (int i = 0; i < 3; i++) { desc->res[i] = res[i]; desc->bbox_min[i] = bb[i]; desc->bbox_max[i] = bb[3 + i]; }
+        desc->world_to_volume[0] = desc->world_to_volume[5] = desc->world_to_volume[10] = 1.f;
+    }
+    if (data) {
+        if (enc != 1 || ch != 1) {
+            fclose(f);
+            return mer::fail(MER_ERR_UNSUPPORTED, "only single-channel float32 .vol files are supported on this path");
+        }
+        size_t total = (size_t) res[0] * res[1] * res[2];
+        data->resize(total);
+        if (fread(data->data(), sizeof(float), total, f) != total) {
+            fclose(f);
+            return mer::fail(MER_ERR_INVALID, "volume file truncated");
+        }
+    }
+    fclose(f);
+    return MER_OK;
+}
+
+void apply_override(mer_volume_desc *d, const mer_volume_desc *ov) {
+    if (!ov) return;
+    /* `min`/`max` properties replace the file's bbox (splinevolume.cpp:93-98, 260-268); toWorld */
+    if (ov->bbox_max[0] > ov->bbox_min[0]) {
+        for (int i = 0; i < 3; i++) { d->bbox_min[i] = ov->bbox_min[i]; d->bbox_max[i] = ov->bbox_max[i]; }
+    }
+    d->has_transform = ov->has_transform;
+    memcpy(d->world_to_volume, ov->world_to_volume, sizeof(d->world_to_volume));
+}
+
+} /* namespace */
+
+extern "C" {
+
+int mer_rif_create_device(int device, const mer_volume_desc *desc, const float *data_dev, int mode, mer_rif **out) {
+    if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    int rc = validate_desc(desc, 4);
+    if (rc) return rc;
+    MER_REQUIRE(mode == MER_RIF_TRICUBIC || mode == MER_RIF_TRILINEAR_PACKED, "unknown RIF mode");
+    MER_REQUIRE(data_dev != nullptr, "No RIF data specified!");
+    rc = mer::check_device(device);
+    if (rc) return rc;
+    mer::DeviceGuard guard(device);
+    mer_rif *r = new mer_rif();
+    memset(r, 0, sizeof(*r));
+    r->device = device;
+    r->mode = mode;
+    r->desc = *desc;
+    rc = rif_build(r, data_dev, 0);
+    if (rc) { mer_rif_destroy(r); return rc; }
+    *out = r;
+    return MER_OK;
+}
+
+int mer_rif_create(int device, const mer_volume_desc *desc, const float *data, int mode, mer_rif **out) {
+    if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    int rc = validate_desc(desc, 4);
+    if (rc) return rc;
+    MER_REQUIRE(data != nullptr, "No RIF data specified!");
+    rc = mer::check_device(device);
+    if (rc) return rc;
+    mer::DeviceGuard guard(device);
+    float *d_data = nullptr;
+    const size_t bytes = voxels(desc) * sizeof(float);
+    MER_CUDA(cudaMalloc(&d_data, bytes));
+    cudaError_t e = cudaMemcpy(d_data, data, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_data); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
+    rc = mer_rif_create_device(device, desc, d_data, mode, out);
+    cudaFree(d_data);
+    return rc;
+}
+
+int mer_rif_create_from_file(int device, const char *vol_path, const mer_volume_desc *override_or_null, int mode,
+                             mer_rif **out) {
+    mer_volume_desc d;
+    std::vector<float> data;
+    int rc = read_vol_file(vol_path, &d, &data, nullptr, nullptr);
+    if (rc) return rc;
+    apply_override(&d, override_or_null);
+    return mer_rif_create(device, &d, data.data(), mode, out);
+}
+
+void mer_rif_destroy(mer_rif *r) {
+    if (!r) return;
+    mer::DeviceGuard guard(r->device);
+    cudaFree(r->d_coeff);
+    cudaFree(r->d_coeff4);
+    cudaFree(r->d_packed);
+    delete r;
+}
+
+int mer_rif_coefficients(const mer_rif *r, float *coeff_out_host) {
+    MER_REQUIRE(r && coeff_out_host, "null argument");
+    mer::DeviceGuard guard(r->device);
+    MER_CUDA(cudaMemcpy(coeff_out_host, r->d_coeff, voxels(&r->desc) * sizeof(float), cudaMemcpyDeviceToHost));
+    return MER_OK;
+}
+
+int mer_rif_desc(const mer_rif *r, mer_volume_desc *out, int *mode_out) {
+    MER_REQUIRE(r, "null handle");
+    if (out) *out = r->desc;
+    if (mode_out) *mode_out = r->mode;
+    return MER_OK;
+}
+
+int mer_rif_eval_device(const mer_rif *r, int what, size_t n, const float *p_dev, float *value_dev, float *grad_dev,
+                        void *stream) {
+    MER_REQUIRE(r && (n == 0 || p_dev), "null argument");
+    MER_REQUIRE(what >= MER_EVAL_VALUE && what <= MER_EVAL_VALUE_AND_GRADIENT, "bad `what`");
+    if (n == 0) return MER_OK;
+    float *f = what == MER_EVAL_GRADIENT ? nullptr : value_dev;
+    float *g = what == MER_EVAL_VALUE ? nullptr : grad_dev;
+    MER_REQUIRE((what == MER_EVAL_GRADIENT || f) && (what == MER_EVAL_VALUE || g), "missing output buffer");
+    mer::DeviceGuard guard(r->device);
+    const unsigned G = (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u);
+    if (r->mode == MER_RIF_TRICUBIC)
+        MER_LAUNCH(k_rif_eval<MER_RIF_TRICUBIC>, G, 256, 0, (cudaStream_t) stream, r->dev, n, p_dev, f, g);
+    else
+        MER_LAUNCH(k_rif_eval<MER_RIF_TRILINEAR_PACKED>, G, 256, 0, (cudaStream_t) stream, r->dev, n, p_dev, f, g);
+    return MER_OK;
+}
+
+int mer_rif_eval_batch(const mer_rif *r, int what, size_t n, const float *p, float *value_out, float *grad_out) {
+    MER_REQUIRE(r && (n == 0 || p), "null argument");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(r->device);
+    float *dp = nullptr, *df = nullptr, *dg = nullptr;
+    MER_CUDA(cudaMalloc(&dp, n * 3 * sizeof(float)));
+    MER_CUDA(cudaMalloc(&df, n * sizeof(float)));
+    MER_CUDA(cudaMalloc(&dg, n * 3 * sizeof(float)));
+    int rc = MER_OK;
+    cudaError_t e = cudaMemcpy(dp, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = mer_rif_eval_device(r, what, n, dp, df, dg, nullptr);
+        if (rc == MER_OK) e = cudaDeviceSynchronize();
+        if (rc == MER_OK && e == cudaSuccess && what != MER_EVAL_GRADIENT && value_out)
+            e = cudaMemcpy(value_out, df, n * sizeof(float), cudaMemcpyDeviceToHost);
+        if (rc == MER_OK && e == cudaSuccess && what != MER_EVAL_VALUE && grad_out)
+            e = cudaMemcpy(grad_out, dg, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dp); cudaFree(df); cudaFree(dg);
+    if (rc) return rc;
+    if (e != cudaSuccess) return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));
+    return MER_OK;
+}
+
+int mer_rif_inside_limits_batch(const mer_rif *r, size_t n, const float *p, uint8_t *inside_out) {
+    MER_REQUIRE(r && (n == 0 || (p && inside_out)), "null argument");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(r->device);
+    float *dp = nullptr;
+    uint8_t *dout = nullptr;
+    MER_CUDA(cudaMalloc(&dp, n * 3 * sizeof(float)));
+    MER_CUDA(cudaMalloc(&dout, n));
+    MER_CUDA(cudaMemcpy(dp, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    MER_LAUNCH(k_rif_inside, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, r->dev, n, dp, dout);
+    MER_CUDA(cudaMemcpy(inside_out, dout, n, cudaMemcpyDeviceToHost));
+    cudaFree(dp); cudaFree(dout);
+    return MER_OK;
+}
+
+/* ------------------------------------------------------------------ density grid */
+int mer_grid_create_device(int device, const mer_volume_desc *desc, const float *data_dev, mer_grid **out) {
+    if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    int rc = validate_desc(desc, 2);
+    if (rc) return rc;
+    MER_REQUIRE(data_dev != nullptr, "No density specified!");
+    rc = mer::check_device(device);
+    if (rc) return rc;
+    mer::DeviceGuard guard(device);
+    mer_grid *g = new mer_grid();
+    memset(g, 0, sizeof(*g));
+    g->device = device;
+    g->desc = *desc;
+    const size_t bytes = voxels(desc) * sizeof(float);
+    cudaError_t e = cudaMalloc(&g->d_data, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_data, data_dev, bytes, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) { mer_grid_destroy(g); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
+    for (int r = 0; r < 3; r++) {
+        g->dev.N[r] = desc->res[r];
+        /* m_worldToGrid = scale * translate(-min) * worldToVolume, gridvolume.cpp:190-195 */
+        float scale = (float) (desc->res[r] - 1) / (desc->bbox_max[r] - desc->bbox_min[r]);
+        for (int c = 0; c < 4; c++) {
+            float w = desc->has_transform ? desc->world_to_volume[4 * r + c] : (r == c ? 1.0f : 0.0f);
+            if (c == 3) w = w + (-desc->bbox_min[r]);
+            g->dev.G[4 * r + c] = scale * w;
+        }
+    }
+    g->dev.data = g->d_data;
+    *out = g;
+    return MER_OK;
+}
+
+int mer_grid_create(int device, const mer_volume_desc *desc, const float *data, mer_grid **out) {
+    if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    int rc = validate_desc(desc, 2);
+    if (rc) return rc;
+    MER_REQUIRE(data != nullptr, "No density specified!");
+    rc = mer::check_device(device);
+    if (rc) return rc;
+    mer::DeviceGuard guard(device);
+    float *d_data = nullptr;
+    const size_t bytes = voxels(desc) * sizeof(float);
+    MER_CUDA(cudaMalloc(&d_data, bytes));
+    cudaError_t e = cudaMemcpy(d_data, data, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_data); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
+    rc = mer_grid_create_device(device, desc, d_data, out);
+    cudaFree(d_data);
+    return rc;
+}
+
+int mer_grid_create_from_file(int device, const char *vol_path, const mer_volume_desc *override_or_null,
+                              mer_grid **out) {
+    mer_volume_desc d;
+    std::vector<float> data;
+    int rc = read_vol_file(vol_path, &d, &data, nullptr, nullptr);
+    if (rc) return rc;
+    apply_override(&d, override_or_null);
+    return mer_grid_create(device, &d, data.data(), out);
+}
+
+void mer_grid_destroy(mer_grid *g) {
+    if (!g) return;
+    mer::DeviceGuard guard(g->device);
+    cudaFree(g->d_data);
+    delete g;
+}
+
+int mer_grid_lookup_batch(const mer_grid *g, size_t n, const float *p, float *value_out) {
+    MER_REQUIRE(g && (n == 0 || (p && value_out)), "null argument");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(g->device);
+    float *dp = nullptr, *dout = nullptr;
+    MER_CUDA(cudaMalloc(&dp, n * 3 * sizeof(float)));
+    MER_CUDA(cudaMalloc(&dout, n * sizeof(float)));
+    MER_CUDA(cudaMemcpy(dp, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    MER_LAUNCH(k_grid_lookup, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, g->dev, n, dp, dout);
+    MER_CUDA(cudaMemcpy(value_out, dout, n * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(dp); cudaFree(dout);
+    return MER_OK;
+}
+
+/* ------------------------------------------------------------------ .vol I/O (host only) */
+int mer_vol_read_header(const char *path, mer_volume_desc *out, int32_t *encoding, int32_t *channels) {
+    MER_REQUIRE(path, "null path");
+    return read_vol_file(path, out, nullptr, encoding, channels);
+}
+
+int mer_vol_read_data(const char *path, float *data_out, size_t n_floats) {
+    MER_REQUIRE(path && data_out, "null argument");
+    mer_volume_desc d;
+    std::vector<float> data;
+    int rc = read_vol_file(path, &d, &data, nullptr, nullptr);
+    if (rc) return rc;
+    MER_REQUIRE(n_floats == data.size(), "buffer size does not match the volume resolution");
+    memcpy(data_out, data.data(), n_floats * sizeof(float));
+    return MER_OK;
+}
+
+int mer_vol_write(const char *path, const mer_volume_desc *desc, const float *data) {
+    MER_REQUIRE(path && desc && data, "null argument");
+    FILE *f = fopen(path, "wb");
+    if (!f) return mer::fail(MER_ERR_INVALID, std::string("cannot create volume file: ") + path);
+    unsigned char hdr[48];
+    hdr[0] = 'V'; hdr[1] = 'O'; hdr[2] = 'L'; hdr[3] = 3;
+    int32_t enc = 1, ch = 1;
+    memcpy(hdr + 4, &enc, 4);
+    memcpy(hdr + 8, desc->res, 12);
+    memcpy(hdr + 20, &ch, 4);
+    memcpy(hdr + 24, desc->bbox_min, 12);
+    memcpy(hdr + 36, desc->bbox_max, 12);
+    size_t total = voxels(desc);
+    bool ok = fwrite(hdr, 1, 48, f) == 48 && fwrite(data, sizeof(float), total, f) == total;
+    fclose(f);
+    if (!ok) return mer::fail(MER_ERR_INVALID, "short write to volume file");
+    return MER_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,437 @@
+"""Host-side mirror of the Mitsuba plugin interface for the eikonal path.
+
+Same class names, property names, child names and error behaviour as the reference's plugins
+(SURVEY.md Appendix C), implemented as thin owners of C-ABI handles:
+
+  SplineDataSource               <volume type="splinevolume">           src/volume/splinevolume.cpp
+  GridDataSource                 <volume type="gridvolume">             src/volume/gridvolume.cpp
+  HGPhaseFunction                <phase type="hg">                      src/phase/hg.cpp
+  HeterogeneousRefractiveMedium  <medium type="heterogeneousrefractive"> src/medium/heterogeneousrefractive.cpp
+  EikonalVolPathIntegrator       <integrator type="ervolpath">  (new plugin name, SURVEY.md R3:
+                                 volpath control flow + libbidir's curved-walk semantics)
+
+All arithmetic happens in libmitsubaer_b200.so on the GPU; nothing here computes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import check, lib
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _spectrum(v):
+    """Properties::getSpectrum for RGB: a scalar or 3 values"""
+    a = np.asarray(v, dtype=np.float32).reshape(-1)
+    if a.size == 1:
+        a = np.repeat(a, 3)
+    if a.size != 3:
+        raise _abi.MerError(_abi.MER_ERR_INVALID, "spectrum must have 1 or 3 components (SPECTRUM_SAMPLES=3)")
+    return a
+
+
+def make_volume_desc(res, bbox_min, bbox_max, to_world=None):
+    d = _abi.VolumeDesc()
+    d.res[:] = [int(r) for r in res]
+    d.bbox_min[:] = [float(x) for x in bbox_min]
+    d.bbox_max[:] = [float(x) for x in bbox_max]
+    if to_world is None:
+        d.has_transform = 0
+        d.world_to_volume[:] = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]
+    else:
+        m = np.asarray(to_world, dtype=np.float64)
+        if m.shape == (3, 4):
+            m = np.vstack([m, [0, 0, 0, 1]])
+        inv = np.linalg.inv(m.reshape(4, 4))  # m_worldToVolume = m_volumeToWorld.inverse()
+        d.has_transform = 1
+        d.world_to_volume[:] = [float(x) for x in inv[:3, :].reshape(12)]
+    return d
+
+
+class _Volume:
+    handle = None
+
+    def getAABB(self):
+        d = self.desc
+        return np.array(d.bbox_min[:], np.float32), np.array(d.bbox_max[:], np.float32)
+
+    def getResolution(self):
+        return tuple(self.desc.res[:])
+
+    def getStepSize(self):
+        """0.5 * min voxel pitch (splinevolume.cpp:183-185, gridvolume.cpp:196-198)"""
+        lo, hi = self.getAABB()
+        return float(np.min(0.5 * (hi - lo) / (np.array(self.getResolution(), np.float32) - 1)))
+
+    def getMaximumFloatValue(self):
+        return 1.0
+
+
+class SplineDataSource(_Volume):
+    """props: `filename` | (`data`, `res`, `min`, `max`), `toWorld`, `min`/`max` override, `device`,
+    `mode` ('tricubic' parity mode | 'trilinear_packed' fast mode)."""
+
+    def __init__(self, props=None, **kw):
+        props = dict(props or {}, **kw)
+        self.device = int(props.get("device", 0))
+        mode = props.get("mode", "tricubic")
+        self.mode = {"tricubic": _abi.RIF_TRICUBIC, "trilinear_packed": _abi.RIF_TRILINEAR_PACKED}.get(mode, mode)
+        h = C.c_void_p()
+        if "filename" in props:
+            ov = None
+            if "min" in props and "max" in props or "toWorld" in props:
+                lo = props.get("min", (0, 0, 0))
+                hi = props.get("max", (0, 0, 0))  # max<=min => keep the file's bbox
+                ov = make_volume_desc((2, 2, 2), lo, hi, props.get("toWorld"))
+            check(lib.mer_rif_create_from_file(self.device, str(props["filename"]).encode(),
+                                               C.byref(ov) if ov is not None else None, self.mode, C.byref(h)))
+        elif "data_ptr" in props:  # data already resident in HBM (e.g. a torch tensor's data_ptr())
+            desc = make_volume_desc(props["res"], props["min"], props["max"], props.get("toWorld"))
+            check(lib.mer_rif_create_device(self.device, C.byref(desc), C.c_void_p(int(props["data_ptr"])),
+                                            self.mode, C.byref(h)))
+        else:
+            data = _f32(props["data"]).reshape(-1)
+            res = props.get("res") or tuple(reversed(np.shape(props["data"])))
+            desc = make_volume_desc(res, props["min"], props["max"], props.get("toWorld"))
+            if data.size != desc.res[0] * desc.res[1] * desc.res[2]:
+                raise _abi.MerError(_abi.MER_ERR_INVALID, "data size does not match res")
+            check(lib.mer_rif_create(self.device, C.byref(desc), _fp(data), self.mode, C.byref(h)))
+        self.handle = h
+        self.desc = _abi.VolumeDesc()
+        m = C.c_int()
+        check(lib.mer_rif_desc(self.handle, C.byref(self.desc), C.byref(m)))
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib.mer_rif_destroy(self.handle)
+            self.handle = None
+
+    def _eval(self, what, p):
+        p = _f32(p, (-1, 3))
+        n = p.shape[0]
+        f = np.zeros(n, np.float32)
+        g = np.zeros((n, 3), np.float32)
+        check(lib.mer_rif_eval_batch(self.handle, what, n, _fp(p), _fp(f), _fp(g)))
+        return f, g
+
+    def value(self, p):
+        return self._eval(_abi.EVAL_VALUE, p)[0]
+
+    def gradient(self, p):
+        return self._eval(_abi.EVAL_GRADIENT, p)[1]
+
+    def valueAndGradient(self, p):
+        return self._eval(_abi.EVAL_VALUE_AND_GRADIENT, p)
+
+    def insideVolumeLimits(self, p):
+        p = _f32(p, (-1, 3))
+        out = np.zeros(p.shape[0], np.uint8)
+        check(lib.mer_rif_inside_limits_batch(self.handle, p.shape[0], _fp(p), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out.astype(bool)
+
+    def coefficients(self):
+        r = self.getResolution()
+        out = np.zeros(r[0] * r[1] * r[2], np.float32)
+        check(lib.mer_rif_coefficients(self.handle, _fp(out)))
+        return out.reshape(r[2], r[1], r[0])
+
+    def isAcousticRIF(self):
+        return False
+
+
+class GridDataSource(_Volume):
+    """props: `filename` | (`data`, `res`, `min`, `max`), `toWorld`, `device`."""
+
+    def __init__(self, props=None, **kw):
+        props = dict(props or {}, **kw)
+        self.device = int(props.get("device", 0))
+        h = C.c_void_p()
+        if "filename" in props:
+            ov = None
+            if "min" in props and "max" in props or "toWorld" in props:
+                ov = make_volume_desc((2, 2, 2), props.get("min", (0, 0, 0)), props.get("max", (0, 0, 0)),
+                                      props.get("toWorld"))
+            check(lib.mer_grid_create_from_file(self.device, str(props["filename"]).encode(),
+                                                C.byref(ov) if ov is not None else None, C.byref(h)))
+            self.desc = _abi.VolumeDesc()
+            enc, ch = C.c_int32(), C.c_int32()
+            check(lib.mer_vol_read_header(str(props["filename"]).encode(), C.byref(self.desc), C.byref(enc), C.byref(ch)))
+            if ov is not None and ov.bbox_max[0] > ov.bbox_min[0]:
+                self.desc.bbox_min[:] = ov.bbox_min[:]
+                self.desc.bbox_max[:] = ov.bbox_max[:]
+        elif "data_ptr" in props:
+            self.desc = make_volume_desc(props["res"], props["min"], props["max"], props.get("toWorld"))
+            check(lib.mer_grid_create_device(self.device, C.byref(self.desc), C.c_void_p(int(props["data_ptr"])),
+                                             C.byref(h)))
+        else:
+            data = _f32(props["data"]).reshape(-1)
+            res = props.get("res") or tuple(reversed(np.shape(props["data"])))
+            self.desc = make_volume_desc(res, props["min"], props["max"], props.get("toWorld"))
+            if data.size != self.desc.res[0] * self.desc.res[1] * self.desc.res[2]:
+                raise _abi.MerError(_abi.MER_ERR_INVALID, "data size does not match res")
+            check(lib.mer_grid_create(self.device, C.byref(self.desc), _fp(data), C.byref(h)))
+        self.handle = h
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib.mer_grid_destroy(self.handle)
+            self.handle = None
+
+    def lookupFloat(self, p):
+        p = _f32(p, (-1, 3))
+        out = np.zeros(p.shape[0], np.float32)
+        check(lib.mer_grid_lookup_batch(self.handle, p.shape[0], _fp(p), _fp(out)))
+        return out
+
+    def supportsFloatLookups(self):
+        return True
+
+
+class HGPhaseFunction:
+    """props: `g` (default 0.8, must lie in (-1, 1): hg.cpp:46-53)"""
+
+    def __init__(self, props=None, **kw):
+        props = dict(props or {}, **kw)
+        self.g = float(props.get("g", 0.8))
+        self.device = int(props.get("device", 0))
+        if self.g >= 1 or self.g <= -1:
+            raise _abi.MerError(_abi.MER_ERR_INVALID, "The asymmetry parameter must lie in the interval (-1, 1)!")
+
+    def sample(self, wi, xi):
+        """-> (wo, pdf); the returned weight is 1 like hg.cpp:97"""
+        wi = _f32(wi, (-1, 3))
+        xi = _f32(xi, (-1, 2))
+        wo = np.zeros_like(wi)
+        pdf = np.zeros(wi.shape[0], np.float32)
+        check(lib.mer_hg_sample_batch(self.device, self.g, wi.shape[0], _fp(wi), _fp(xi), _fp(wo), _fp(pdf)))
+        return wo, pdf
+
+    def eval(self, wi, wo):
+        wi = _f32(wi, (-1, 3))
+        wo = _f32(wo, (-1, 3))
+        out = np.zeros(wi.shape[0], np.float32)
+        check(lib.mer_hg_eval_batch(self.device, self.g, wi.shape[0], _fp(wi), _fp(wo), _fp(out)))
+        return out
+
+    pdf = eval
+
+    def getMeanCosine(self):
+        return self.g
+
+
+_STRATEGIES = {"balance": _abi.STRATEGY_BALANCE, "single": _abi.STRATEGY_SINGLE, "manual": _abi.STRATEGY_MANUAL,
+               "maximum": _abi.STRATEGY_MAXIMUM}
+
+
+class HeterogeneousRefractiveMedium:
+    """props (heterogeneousrefractive.cpp:205-297, medium.cpp:27-37, materials.h:90-140):
+    `stepsize`, `strategy`, `channel`, `samplingDensity`, `mediumSamplingWeight`,
+    (`sigmaS`,`sigmaA`) | (`sigmaT`,`albedo`), `scale`; children via addChild():
+    "rif" (SplineDataSource), "density" (GridDataSource, optional: new composition R2), a phase function.
+    `shape`: the containment predicate, ('box', min, max) | ('sphere', centre, radius)."""
+
+    def __init__(self, props=None, **kw):
+        props = dict(props or {}, **kw)
+        self.props = props
+        self.rif = None
+        self.density = None
+        self.phase = None
+        self.handle = None
+        strategy = props.get("strategy", "balance")
+        if strategy not in _STRATEGIES:
+            raise _abi.MerError(_abi.MER_ERR_INVALID, "Specified an unknown sampling strategy")
+
+    def addChild(self, name, child):
+        if isinstance(child, HGPhaseFunction):
+            if self.phase is not None:
+                raise _abi.MerError(_abi.MER_ERR_INVALID, "Medium: phase function already set")
+            self.phase = child
+        elif isinstance(child, SplineDataSource) and name == "rif":
+            self.rif = child
+        elif isinstance(child, GridDataSource) and name == "density":
+            self.density = child
+        else:
+            raise _abi.MerError(_abi.MER_ERR_INVALID, 'Medium: Invalid child node! ("%s")' % type(child).__name__)
+        return self
+
+    def configure(self):
+        p = self.props
+        if self.rif is None:
+            raise _abi.MerError(_abi.MER_ERR_INVALID, "No RIF specified!")
+        d = _abi.MediumDesc()
+        scale = float(p.get("scale", 1.0))
+        if "sigmaT" in p and "albedo" in p:
+            st, al = _spectrum(p["sigmaT"]) * scale, _spectrum(p["albedo"])
+            ss, sa = st * al, st * (1 - al)
+        else:
+            ss = _spectrum(p.get("sigmaS", 0.0)) * scale
+            sa = _spectrum(p.get("sigmaA", 0.0)) * scale
+        d.sigma_a[:] = [float(x) for x in sa]
+        d.sigma_s[:] = [float(x) for x in ss]
+        d.stepsize = float(p.get("stepsize", 1e-3))
+        d.medium_sampling_weight = float(p.get("mediumSamplingWeight", -1))
+        d.strategy = _STRATEGIES[p.get("strategy", "balance")]
+        d.channel = int(p.get("channel", -1))
+        d.sampling_density = float(p.get("samplingDensity", 0.0))
+        shape = p.get("shape")
+        if shape is None:  # default: the RIF's interpolatable box shrunk to the data bbox minus 3 voxels
+            lo, hi = self.rif.getAABB()
+            pitch = (hi - lo) / (np.array(self.rif.getResolution(), np.float32) - 1)
+            shape = ("box", lo + 3 * pitch, hi - 3 * pitch)
+        if shape[0] == "box":
+            d.shape_type = _abi.SHAPE_BOX
+            d.shape[:] = [float(x) for x in list(shape[1]) + list(shape[2])]
+        elif shape[0] == "sphere":
+            d.shape_type = _abi.SHAPE_SPHERE
+            d.shape[:] = [float(x) for x in list(shape[1]) + [shape[2], 0.0, 0.0]]
+        else:
+            raise _abi.MerError(_abi.MER_ERR_INVALID, "unknown shape")
+        d.hg_g = self.phase.g if self.phase is not None else 0.0  # Medium::configure: isotropic default
+        d.density_scale = float(p.get("densityScale", p.get("scale", 1.0))) if self.density is not None else 0.0
+        d.albedo[:] = [float(x) for x in _spectrum(p.get("albedo", 0.0))]
+        h = C.c_void_p()
+        check(lib.mer_medium_create(C.byref(d), self.rif.handle, self.density.handle if self.density else None,
+                                    C.byref(h)))
+        self.handle = h
+        self.desc = _abi.MediumDesc()
+        sd = C.c_float()
+        check(lib.mer_medium_resolved(self.handle, C.byref(self.desc), C.byref(sd)))
+        self.samplingDensity = sd.value
+        self.mediumSamplingWeight = self.desc.medium_sampling_weight
+        return self
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib.mer_medium_destroy(self.handle)
+            self.handle = None
+
+    def isheterogeneousrefractive(self):
+        return True
+
+    # ---- hot calls
+    def trace(self, p, v, dist):
+        p = np.array(p, np.float32).reshape(-1, 3)
+        v = np.array(v, np.float32).reshape(-1, 3)
+        n = p.shape[0]
+        dist = np.ascontiguousarray(np.broadcast_to(np.asarray(dist, np.float32), (n,)))
+        ok = np.zeros(n, np.uint8)
+        ds = np.zeros(n, np.float32)
+        opl = np.zeros(n, np.float32)
+        ns = np.zeros(n, np.int32)
+        check(lib.mer_medium_trace_batch(self.handle, n, _fp(p), _fp(v), _fp(dist),
+                                         ok.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(ds), _fp(opl),
+                                         ns.ctypes.data_as(C.POINTER(C.c_int32))))
+        return dict(p=p, v=v, success=ok.astype(bool), dist_surf=ds, opl=opl, nsteps=ns)
+
+    def traceTillBoundary(self, p, v):
+        p = np.array(p, np.float32).reshape(-1, 3)
+        v = np.array(v, np.float32).reshape(-1, 3)
+        n = p.shape[0]
+        ds = np.zeros(n, np.float32)
+        opl = np.zeros(n, np.float32)
+        ns = np.zeros(n, np.int32)
+        check(lib.mer_medium_trace_till_boundary_batch(self.handle, n, _fp(p), _fp(v), _fp(ds), _fp(opl),
+                                                       ns.ctypes.data_as(C.POINTER(C.c_int32))))
+        return dict(p=p, v=v, dist_surf=ds, opl=opl, nsteps=ns)
+
+    def sampleDistance(self, ray_o, ray_d, ray_mint, xi):
+        """Medium::sampleDistance over a batch; xi[n][2] replays sampler->next1D()"""
+        ro = _f32(ray_o, (-1, 3))
+        rd = _f32(ray_d, (-1, 3))
+        n = ro.shape[0]
+        mint = np.ascontiguousarray(np.broadcast_to(np.asarray(ray_mint, np.float32), (n,)))
+        xi = _f32(xi, (-1, 2))
+        r = dict(success=np.zeros(n, np.uint8), t=np.zeros(n, np.float32), p=np.zeros((n, 3), np.float32),
+                 d=np.zeros((n, 3), np.float32), optical_length=np.zeros(n, np.float32),
+                 ref_ratio_sq=np.zeros(n, np.float32), transmittance=np.zeros((n, 3), np.float32),
+                 pdf_success=np.zeros(n, np.float32), pdf_failure=np.zeros(n, np.float32),
+                 sigma_s=np.zeros((n, 3), np.float32), nsteps=np.zeros(n, np.int32))
+        rec = _abi.SamplingRecords()
+        rec.success = r["success"].ctypes.data_as(C.POINTER(C.c_uint8))
+        rec.nsteps = r["nsteps"].ctypes.data_as(C.POINTER(C.c_int32))
+        for k in ("t", "p", "d", "optical_length", "ref_ratio_sq", "transmittance", "pdf_success", "pdf_failure",
+                  "sigma_s"):
+            setattr(rec, k, _fp(r[k]))
+        check(lib.mer_medium_sample_distance_batch(self.handle, n, _fp(ro), _fp(rd), _fp(mint), _fp(xi), C.byref(rec)))
+        r["success"] = r["success"].astype(bool)
+        return r
+
+    def evalTransmittance(self, mint, maxt):
+        mint = _f32(mint).reshape(-1)
+        maxt = _f32(maxt).reshape(-1)
+        out = np.zeros((mint.size, 3), np.float32)
+        check(lib.mer_medium_eval_transmittance_batch(self.handle, mint.size, _fp(mint), _fp(maxt), _fp(out)))
+        return out
+
+
+class EikonalVolPathIntegrator:
+    """<integrator type="ervolpath">: props `maxDepth` (-1), `rrDepth` (5) (MonteCarloIntegrator,
+    src/librender/integrator.cpp:190-225) + scheduling knobs `poolPaths`, `stepsPerPass`."""
+
+    def __init__(self, props=None, **kw):
+        props = dict(props or {}, **kw)
+        self.maxDepth = int(props.get("maxDepth", -1))
+        self.rrDepth = int(props.get("rrDepth", 5))
+        self.poolPaths = int(props.get("poolPaths", 0))
+        self.stepsPerPass = int(props.get("stepsPerPass", 0))
+        if self.maxDepth == 0 or self.maxDepth < -1:
+            raise _abi.MerError(_abi.MER_ERR_INVALID,
+                                "maxDepth must be set to -1 (infinite) or a value greater than zero!")
+
+    def render_desc(self, scene, sample_begin=0, sample_stride=1):
+        """`scene`: dict with sensor/film/emitter parameters (what the C++ shim reads off the Scene)"""
+        r = _abi.RenderDesc()
+        r.width, r.height = int(scene["width"]), int(scene["height"])
+        r.spp_total = int(scene["sampleCount"])
+        r.sample_begin, r.sample_stride = int(sample_begin), int(sample_stride)
+        r.seed = int(scene.get("seed", 20201201))
+        r.cam_origin[:] = [float(x) for x in scene["origin"]]
+        r.cam_target[:] = [float(x) for x in scene["target"]]
+        r.cam_up[:] = [float(x) for x in scene.get("up", (0, 1, 0))]
+        r.fov_deg = float(scene.get("fov", 40.0))
+        r.filter = {"box": _abi.FILTER_BOX, "gaussian": _abi.FILTER_GAUSSIAN}[scene.get("rfilter", "gaussian")]
+        r.max_depth, r.rr_depth = self.maxDepth, self.rrDepth
+        r.env_radiance[:] = [float(x) for x in _spectrum(scene.get("envRadiance", 1.0))]
+        quad = scene.get("quad")
+        r.has_quad = 1 if quad else 0
+        if quad:
+            r.quad_origin[:] = [float(x) for x in quad["origin"]]
+            r.quad_u[:] = [float(x) for x in quad["u"]]
+            r.quad_v[:] = [float(x) for x in quad["v"]]
+            r.quad_radiance[:] = [float(x) for x in _spectrum(quad["radiance"])]
+        r.pool_paths, r.steps_per_pass = self.poolPaths, self.stepsPerPass
+        return r
+
+    def render(self, scene, medium, sample_begin=0, sample_stride=1):
+        """-> (film[H][W][5] = [R,G,B,alpha,weight], stats dict)"""
+        r = self.render_desc(scene, sample_begin, sample_stride)
+        film = np.zeros((r.height, r.width, 5), np.float32)
+        stats = _abi.RenderStats()
+        check(lib.mer_render(medium.handle, C.byref(r), _fp(film), C.byref(stats)))
+        return film, stats.as_dict()
+
+    def render_device(self, scene, medium, film_ptr, stream=None, sample_begin=0, sample_stride=1):
+        """accumulate into a device film buffer (e.g. torch tensor .data_ptr()); -> stats dict"""
+        r = self.render_desc(scene, sample_begin, sample_stride)
+        stats = _abi.RenderStats()
+        check(lib.mer_render_device(medium.handle, C.byref(r), C.c_void_p(int(film_ptr)), C.byref(stats),
+                                    C.c_void_p(int(stream)) if stream else None))
+        return stats.as_dict()
+
+
+def develop(film, device=0):
+    """HDRFilm::develop: [H][W][5] -> RGB [H][W][3]"""
+    film = _f32(film)
+    H, W, _ = film.shape
+    rgb = np.zeros((H, W, 3), np.float32)
+    check(lib.mer_film_develop(device, W, H, _fp(film), _fp(rgb)))
+    return rgb

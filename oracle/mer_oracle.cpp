@@ -153,7 +153,7 @@ template <typename F> struct Spline3 {
     /* One routine for value / gradient / Hessian: the reference's four functions accumulate the
      * same products in the same (x outer, y, z inner) order, so evaluating all of them at once
      * gives bit-identical f and v to value(), gradient() and valueAndGradient(). */
-    void eval(const F *p, F *f, F *g, F *H) const {
+    template <bool HESS> void evalT(const F *p, F *f, F *g, F *H) const {
         F x[3];
         for (int i = 0; i < 3; i++)
             x[i] = (p[i] - xmin[i]) * xres[i]; /* convertToX :655-658 */
@@ -164,14 +164,14 @@ template <typename F> struct Spline3 {
             hi[i] = (int) std::floor(x[i] + 2);
         }
         for (int i1 = lo[0]; i1 <= hi[0]; i1++) {
-            F k0x = bs_k0<F>(x[0] - i1), k1x = bs_k1<F>(x[0] - i1), k2x = bs_k2<F>(x[0] - i1);
+            F k0x = bs_k0<F>(x[0] - i1), k1x = bs_k1<F>(x[0] - i1), k2x = HESS ? bs_k2<F>(x[0] - i1) : (F) 0;
             for (int i2 = lo[1]; i2 <= hi[1]; i2++) {
-                F k0y = bs_k0<F>(x[1] - i2), k1y = bs_k1<F>(x[1] - i2), k2y = bs_k2<F>(x[1] - i2);
+                F k0y = bs_k0<F>(x[1] - i2), k1y = bs_k1<F>(x[1] - i2), k2y = HESS ? bs_k2<F>(x[1] - i2) : (F) 0;
                 for (int i3 = lo[2]; i3 <= hi[2]; i3++) {
-                    F k0z = bs_k0<F>(x[2] - i3), k1z = bs_k1<F>(x[2] - i3), k2z = bs_k2<F>(x[2] - i3);
+                    F k0z = bs_k0<F>(x[2] - i3), k1z = bs_k1<F>(x[2] - i3), k2z = HESS ? bs_k2<F>(x[2] - i3) : (F) 0;
                     F cf = c(i1, i2, i3);
                     fv += cf * k0x * k0y * k0z;
-                    if (H) {
+                    if (HESS) {
                         hxx += cf * k2x * k0y * k0z;
                         hyy += cf * k0x * k2y * k0z;
                         hzz += cf * k0x * k0y * k2z;
@@ -191,13 +191,17 @@ template <typename F> struct Spline3 {
             g[1] = vy * dxres[1];
             g[2] = vz * dxres[2];
         }
-        if (H) {
+        if (HESS) {
             hxx *= dxres2[0]; hyy *= dxres2[1]; hzz *= dxres2[2];
             hxy *= dxres[0] * dxres[1]; hyz *= dxres[1] * dxres[2]; hzx *= dxres[2] * dxres[0];
             H[0] = hxx; H[1] = hxy; H[2] = hzx;
             H[3] = hxy; H[4] = hyy; H[5] = hyz;
             H[6] = hzx; H[7] = hyz; H[8] = hzz;
         }
+    }
+    void eval(const F *p, F *f, F *g, F *H) const {
+        if (H) evalT<true>(p, f, g, H);
+        else evalT<false>(p, f, g, H);
     }
 };
 
@@ -267,31 +271,26 @@ template <typename F> struct SplineVolume {
  * ------------------------------------------------------------------------------------------ */
 struct GridVolume {
     int res[3];
-    float bmin[3], scale[3];
-    bool hasXform;
-    float M[12];
+    float G[12]; /* m_worldToGrid = scale((res-1)/extent) * translate(-min) * worldToVolume, :190-195 */
     std::vector<float> data;
     void create(const mer_volume_desc *d, const float *src) {
         size_t total = 1;
-        for (int i = 0; i < 3; i++) {
-            res[i] = d->res[i];
-            bmin[i] = d->bbox_min[i];
-            scale[i] = (res[i] - 1) / (d->bbox_max[i] - d->bbox_min[i]);
-            total *= (size_t) res[i];
+        for (int r = 0; r < 3; r++) {
+            res[r] = d->res[r];
+            total *= (size_t) res[r];
+            float scale = (res[r] - 1) / (d->bbox_max[r] - d->bbox_min[r]);
+            for (int c = 0; c < 4; c++) {
+                float w = d->has_transform ? d->world_to_volume[4 * r + c] : (r == c ? 1.0f : 0.0f);
+                if (c == 3) w = w + (-d->bbox_min[r]);
+                G[4 * r + c] = scale * w;
+            }
         }
-        hasXform = d->has_transform != 0;
-        for (int i = 0; i < 12; i++)
-            M[i] = hasXform ? d->world_to_volume[i] : 0.f;
         data.assign(src, src + total);
     }
     float lookupFloat(const float *pw) const {
-        float q[3] = {pw[0], pw[1], pw[2]};
-        if (hasXform)
-            for (int r = 0; r < 3; r++)
-                q[r] = M[4 * r] * pw[0] + M[4 * r + 1] * pw[1] + M[4 * r + 2] * pw[2] + M[4 * r + 3];
-        float p[3];
-        for (int i = 0; i < 3; i++)
-            p[i] = (q[i] - bmin[i]) * scale[i];
+        float p[3]; /* Transform::transformAffine: ((m0*x + m1*y) + m2*z) + m3 */
+        for (int r = 0; r < 3; r++)
+            p[r] = G[4 * r] * pw[0] + G[4 * r + 1] * pw[1] + G[4 * r + 2] * pw[2] + G[4 * r + 3];
         const int x1 = (int) std::floor(p[0]), y1 = (int) std::floor(p[1]), z1 = (int) std::floor(p[2]),
                   x2 = x1 + 1, y2 = y1 + 1, z2 = z1 + 1;
         if (x1 < 0 || y1 < 0 || z1 < 0 || x2 >= res[0] || y2 >= res[1] || z2 >= res[2])

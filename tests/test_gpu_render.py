@@ -1,0 +1,140 @@
+"""GPU parity, rows a20-a24: the wavefront integrator vs the CPU oracle renderer.
+
+Both walk the SAME Philox4x32-10 streams (key = seed, counter = (pixel, sample, draw)), so apart from
+FP32 rounding a sample's path is identical; the image gates are those of SURVEY §8d (iv) and in addition
+a much tighter direct comparison that the shared streams make possible."""
+import numpy as np
+import pytest
+
+import mitsubaer_b200 as mer
+from common import (BOX_MAX, BOX_MIN, make_field, medium_props, oracle_medium_desc, oracle_render_desc, scene_dict)
+from oracle.oracle import volume_desc
+
+pytestmark = pytest.mark.gpu
+
+
+def setup(oracle, kind="radial", res=40, props=None, g=0.9, density=False, mode="tricubic"):
+    props = props or medium_props(stepsize=1e-2)
+    data, lo, hi = make_field(kind, res)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi, mode=mode)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=g))
+    orif = oracle.rif_create(volume_desc(rif.getResolution(), lo, hi), data)
+    oden = None
+    keep = [rif]
+    if density:
+        dres = (32, 32, 32)
+        dens = mer.fields.sine_density(dres, BOX_MIN, BOX_MAX)
+        grid = mer.GridDataSource(data=dens, min=BOX_MIN, max=BOX_MAX)
+        med.addChild("density", grid)
+        oden = oracle.grid_create(volume_desc(dres, BOX_MIN, BOX_MAX), dens)
+        keep.append(grid)
+    med.configure()
+    omed = oracle.medium_create(oracle_medium_desc(props, g, has_density=density), orif, oden)
+    return med, omed, keep
+
+
+def image_gates(film_gpu, film_cpu, spp):
+    """§8d (iv): per-pixel k-sigma and relMSE at equal spp.  With shared RNG streams the images are
+    far closer than the statistical bound; both are asserted."""
+    w_g, w_c = film_gpu[..., 4], film_cpu[..., 4]
+    assert np.allclose(w_g, w_c, rtol=1e-5, atol=1e-5)  # filter weights: same sample positions
+    rgb_g = film_gpu[..., :3] / np.maximum(w_g, 1e-9)[..., None]
+    rgb_c = film_cpu[..., :3] / np.maximum(w_c, 1e-9)[..., None]
+    diff = np.abs(rgb_g - rgb_c)
+    # statistical gate: a pixel estimate at `spp` samples has std <= ~mean, so k*sigma/sqrt(N) with k=4
+    sigma = np.maximum(rgb_c, 0.05)
+    frac_ok = np.mean(diff <= 4 * sigma * np.sqrt(2.0 / spp))
+    assert frac_ok >= 0.999, frac_ok
+    relmse = np.mean(diff ** 2) / np.mean(rgb_c ** 2)
+    return float(relmse), float(np.mean(diff <= 1e-3 * np.maximum(rgb_c, 1.0)))
+
+
+@pytest.mark.parametrize("kind,strategy,filt", [("linear", "single", "gaussian"), ("radial", "balance", "box"),
+                                                ("sd", "single", "box")])
+def test_homogeneous_image_matches_oracle(oracle32, kind, strategy, filt):
+    props = medium_props(stepsize=1e-2, strategy=strategy, sigmaS=(3.6, 3.0, 2.4), sigmaA=(0.4, 0.5, 0.6))
+    med, omed, keep = setup(oracle32, kind, 40, props)
+    scene = scene_dict(48, 40, 8, rfilter=filt)
+    integ = mer.EikonalVolPathIntegrator(maxDepth=-1, rrDepth=5, stepsPerPass=256, poolPaths=4096)
+    film, stats = integ.render(scene, med)
+    ofilm, ostats = oracle32.render(omed, oracle_render_desc(scene))
+    assert stats["samples"] == 48 * 40 * 8 == ostats.samples
+    assert stats["nonfinite_dropped"] == 0
+    relmse, frac_tight = image_gates(film, ofilm, 8)
+    # same streams => almost every pixel agrees to 1e-3; event counts agree to a fraction of a percent
+    assert frac_tight > 0.97 and relmse < 1e-3, (relmse, frac_tight)
+    for k, ok in (("ray_steps", ostats.ray_steps), ("scatter_events", ostats.scatter_events),
+                  ("boundary_exits", ostats.boundary_exits)):
+        assert abs(stats[k] - ok) <= 0.005 * ok + 5, (k, stats[k], ok)
+    assert stats["passes"] > 3  # the wavefront really ran in several compacted passes
+
+
+def test_woodcock_density_image_matches_oracle(oracle32):
+    props = medium_props(stepsize=1e-2, albedo=(0.9, 0.8, 0.7), densityScale=8.0)
+    med, omed, keep = setup(oracle32, "radial", 40, props, density=True)
+    scene = scene_dict(40, 40, 8, rfilter="box")
+    film, stats = mer.EikonalVolPathIntegrator(stepsPerPass=300, poolPaths=2048).render(scene, med)
+    ofilm, ostats = oracle32.render(omed, oracle_render_desc(scene))
+    relmse, frac_tight = image_gates(film, ofilm, 8)
+    assert frac_tight > 0.97 and relmse < 1e-3, (relmse, frac_tight)
+    assert stats["null_collisions"] > 0
+    for k, ok in (("ray_steps", ostats.ray_steps), ("scatter_events", ostats.scatter_events),
+                  ("null_collisions", ostats.null_collisions)):
+        assert abs(stats[k] - ok) <= 0.005 * ok + 5, (k, stats[k], ok)
+
+
+def test_max_depth_and_rr(oracle32):
+    props = medium_props(stepsize=2e-2, sigmaS=6.0, sigmaA=0.0)
+    med, omed, keep = setup(oracle32, "radial", 32, props, g=0.0)
+    scene = scene_dict(32, 32, 4, rfilter="box", quad=False)
+    for md, rr in ((3, 5), (8, 2), (-1, 1)):
+        film, stats = mer.EikonalVolPathIntegrator(maxDepth=md, rrDepth=rr, stepsPerPass=128, poolPaths=1024).render(scene, med)
+        ofilm, ostats = oracle32.render(omed, oracle_render_desc(scene, max_depth=md, rr_depth=rr))
+        relmse, frac_tight = image_gates(film, ofilm, 4)
+        assert frac_tight > 0.95, (md, rr, frac_tight)
+        assert abs(stats["scatter_events"] - ostats.scatter_events) <= 0.01 * ostats.scatter_events + 5
+
+
+def test_energy_conservation_white_furnace():
+    """no absorption, unit environment, constant index => every pixel is exactly 1: with the default
+    mediumSamplingWeight (= albedo = 1, heterogeneousrefractive.cpp:239-255) the weight sigma_s T / pdf of
+    every edge is exactly 1, as are refRatioSq and the RR factor"""
+    res = 24
+    lo, hi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    data = np.full((res, res, res), 1.33, np.float32)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(medium_props(stepsize=2e-2, sigmaS=4.0, sigmaA=0.0))
+    med.addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.5)).configure()
+    scene = scene_dict(32, 32, 4, rfilter="box", quad=False)
+    film, stats = mer.EikonalVolPathIntegrator(rrDepth=1000, stepsPerPass=200, poolPaths=2048).render(scene, med)
+    rgb = mer.develop(film)
+    assert np.allclose(rgb, 1.0, atol=2e-4), (rgb.min(), rgb.max())
+    assert np.allclose(film[..., 4], film[0, 0, 4])
+
+
+def test_sample_sharding_adds_up(oracle32):
+    """§8e: sample s -> GPU s mod G; partial films add to the single-GPU film (FP32 summation order only)"""
+    med, omed, keep = setup(oracle32, "radial", 32, medium_props(stepsize=2e-2))
+    scene = scene_dict(32, 24, 8, rfilter="gaussian")
+    integ = mer.EikonalVolPathIntegrator(stepsPerPass=128, poolPaths=1024)
+    full, st = integ.render(scene, med)
+    parts = [integ.render(scene, med, sample_begin=r, sample_stride=3) for r in range(3)]
+    total = sum(p[0] for p in parts)
+    assert sum(p[1]["samples"] for p in parts) == st["samples"]
+    assert sum(p[1]["ray_steps"] for p in parts) == st["ray_steps"]  # identical paths, just regrouped
+    assert np.allclose(total, full, rtol=1e-5, atol=1e-5)
+    # pool/pass sizes are scheduling knobs only
+    other, st2 = mer.EikonalVolPathIntegrator(stepsPerPass=37, poolPaths=128).render(scene, med)
+    assert st2["ray_steps"] == st["ray_steps"] and np.allclose(other, full, rtol=1e-5, atol=1e-5)
+
+
+def test_packed_mode_renders_close_to_tricubic(oracle32):
+    props = medium_props(stepsize=1e-2)
+    med_c, _, k1 = setup(oracle32, "radial", 64, props, mode="tricubic")
+    med_p, _, k2 = setup(oracle32, "radial", 64, props, mode="trilinear_packed")
+    scene = scene_dict(32, 32, 64, rfilter="box")
+    integ = mer.EikonalVolPathIntegrator(stepsPerPass=256, poolPaths=8192)
+    a = mer.develop(integ.render(scene, med_c)[0])
+    b = mer.develop(integ.render(scene, med_p)[0])
+    # different interpolant (R1): images agree statistically, not bitwise
+    assert abs(a.mean() - b.mean()) / a.mean() < 0.02
