@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <mutex>
 #include <string>
 
 #include "mer_device.cuh"
@@ -29,12 +30,36 @@ struct mer_grid {
     float *d_data;
 };
 
+/* per-handle render scratch (path pool, counters, pinned read-back word), allocated on first use and
+ * reused by later mer_render* calls: cudaMalloc / cudaMallocHost / cudaFree cost 0.1-1 s per call */
+struct RenderScratch {
+    std::mutex lock; /* mer_render* calls on one handle are serialised */
+    size_t poolBytes = 0;
+    void *pool[12] = {nullptr};
+    unsigned *nOut = nullptr;
+    unsigned long long *counters = nullptr;
+    unsigned long long *hostPinned = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void release() {
+        for (void *&p : pool) { cudaFree(p); p = nullptr; }
+        cudaFree(nOut); nOut = nullptr;
+        cudaFree(counters); counters = nullptr;
+        if (hostPinned) cudaFreeHost(hostPinned);
+        hostPinned = nullptr;
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        ev0 = ev1 = nullptr;
+        poolBytes = 0;
+    }
+};
+
 struct mer_medium {
     int device;
     mer_medium_desc desc; /* resolved */
     const mer_rif *rif;
     const mer_grid *grid;
     MediumDev dev;
+    RenderScratch *scratch;
 };
 
 namespace mer {

@@ -17,7 +17,7 @@
 
 /* ------------------------------------------------------------------ a8: trace() */
 template <int MODE>
-__device__ __forceinline__ bool trace_dev(const MediumDev &M, float3 &p, float3 &v, float &n, float3 &G, float dist,
+__device__ __forceinline__ bool trace_dev(const MediumDev &M, StencilCache<MODE> &S, float3 &p, float3 &v, float &n, float3 &G, float dist,
                                           float &distSurf, float &opl, int &count) {
     int steps;
     float rem;
@@ -25,19 +25,19 @@ __device__ __forceinline__ bool trace_dev(const MediumDev &M, float3 &p, float3 
     distSurf = 0.0f;
     const float h = M.h;
     for (int i = 0; i < steps; i++) {
-        er_step_fused<MODE>(M.rif, p, v, n, G, h, opl);
+        er_step_fused<MODE>(M.rif, S, p, v, n, G, h, opl);
         count++;
         if (!inside_shape(M, p)) {
-            er_step_fused<MODE>(M.rif, p, v, n, G, -h, opl); /* step back, :679 */
+            er_step_fused<MODE>(M.rif, S, p, v, n, G, -h, opl); /* step back, :679 */
             count++;
             return false;
         }
         distSurf += h;
     }
-    er_step_fused<MODE>(M.rif, p, v, n, G, rem, opl);
+    er_step_fused<MODE>(M.rif, S, p, v, n, G, rem, opl);
     count++;
     if (!inside_shape(M, p)) {
-        er_step_fused<MODE>(M.rif, p, v, n, G, -rem, opl);
+        er_step_fused<MODE>(M.rif, S, p, v, n, G, -rem, opl);
         count++;
         return false;
     }
@@ -47,17 +47,17 @@ __device__ __forceinline__ bool trace_dev(const MediumDev &M, float3 &p, float3 
 
 /* ------------------------------------------------------------------ a9: traceTillBoundary() */
 template <int MODE>
-__device__ __forceinline__ void trace_till_boundary_dev(const MediumDev &M, float3 &p, float3 &v, float &n, float3 &G,
+__device__ __forceinline__ void trace_till_boundary_dev(const MediumDev &M, StencilCache<MODE> &S, float3 &p, float3 &v, float &n, float3 &G,
                                                         float &distSurf, float &opl, int &count) {
     distSurf = 0.0f;
     const float h = M.h;
     for (int i = 0; i < 100000; i++) { /* maxsteps 1e5, :746 */
-        er_step_fused<MODE>(M.rif, p, v, n, G, h, opl);
+        er_step_fused<MODE>(M.rif, S, p, v, n, G, h, opl);
         count++;
         if (inside_shape(M, p)) {
             distSurf += h;
         } else {
-            er_step_fused<MODE>(M.rif, p, v, n, G, -h, opl);
+            er_step_fused<MODE>(M.rif, S, p, v, n, G, -h, opl);
             count++;
             distSurf -= h; /* :761 */
             return;
@@ -76,8 +76,10 @@ k_trace(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P
         float n, ds, opl = 0.0f;
         float3 G;
         int count = 0;
-        rif_lookup<MODE>(M.rif, p, n, G);
-        bool ok = trace_dev<MODE>(M, p, v, n, G, dist[i], ds, opl, count);
+        StencilCache<MODE> S;
+        S.invalidate();
+        rif_lookup_cached<MODE>(M.rif, p, S, n, G);
+        bool ok = trace_dev<MODE>(M, S, p, v, n, G, dist[i], ds, opl, count);
         P[3 * i] = p.x; P[3 * i + 1] = p.y; P[3 * i + 2] = p.z;
         V[3 * i] = v.x; V[3 * i + 1] = v.y; V[3 * i + 2] = v.z;
         if (success) success[i] = ok ? 1 : 0;
@@ -101,8 +103,10 @@ k_trace_till_boundary(const __grid_constant__ MediumDev M, size_t nRays, float *
         float n, ds, opl = 0.0f;
         float3 G;
         int count = 0;
-        rif_lookup<MODE>(M.rif, p, n, G);
-        trace_till_boundary_dev<MODE>(M, p, v, n, G, ds, opl, count);
+        StencilCache<MODE> S;
+        S.invalidate();
+        rif_lookup_cached<MODE>(M.rif, p, S, n, G);
+        trace_till_boundary_dev<MODE>(M, S, p, v, n, G, ds, opl, count);
         P[3 * i] = p.x; P[3 * i + 1] = p.y; P[3 * i + 2] = p.z;
         V[3 * i] = v.x; V[3 * i + 1] = v.y; V[3 * i + 2] = v.z;
         if (distSurfOut) distSurfOut[i] = ds;
@@ -143,14 +147,16 @@ k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float
         } else {
             float n;
             float3 G;
-            rif_lookup<MODE>(M.rif, p, n, G);
+            StencilCache<MODE> S;
+            S.invalidate();
+            rif_lookup_cached<MODE>(M.rif, p, S, n, G);
             const float refStart = n;
             refRatioSq = (float) (1.0 / (double) (refStart * refStart));
             v = f3(v.x * refStart, v.y * refStart, v.z * refStart);
             if (isfinite(sampledDistance)) {
-                success = trace_dev<MODE>(M, p, v, n, G, sampledDistance, distSurf, opl, count);
+                success = trace_dev<MODE>(M, S, p, v, n, G, sampledDistance, distSurf, opl, count);
             } else {
-                trace_till_boundary_dev<MODE>(M, p, v, n, G, distSurf, opl, count);
+                trace_till_boundary_dev<MODE>(M, S, p, v, n, G, distSurf, opl, count);
                 success = false;
             }
             refRatioSq *= n * n; /* refEnd = value at the final p, carried by the fused stepper */
@@ -321,11 +327,20 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
     D.invMaxDensity = density ? 1.0f / (desc->density_scale * 1.0f) : 0.0f; /* heterogeneous.cpp:239-242 */
     m->desc.medium_sampling_weight = w;
     m->desc.sampling_density = D.samplingDensity;
+    m->scratch = new RenderScratch();
     *out = m;
     return MER_OK;
 }
 
-void mer_medium_destroy(mer_medium *m) { delete m; }
+void mer_medium_destroy(mer_medium *m) {
+    if (!m) return;
+    if (m->scratch) {
+        mer::DeviceGuard guard(m->device);
+        m->scratch->release();
+        delete m->scratch;
+    }
+    delete m;
+}
 
 int mer_medium_resolved(const mer_medium *m, mer_medium_desc *out, float *sampling_density_out) {
     MER_REQUIRE(m, "null handle");

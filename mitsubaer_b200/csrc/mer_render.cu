@@ -54,7 +54,7 @@ struct PathPool {
     float4 *q1; /* v.yz, thr.rg */
     float4 *q2; /* thr.b, refStart, segDist, distSurf */
     float4 *q3; /* rem, sd, (int) stepsLeft, (int) depth */
-    uint4 *q4;  /* kind | flags<<8, rng draw index, sampleId lo, hi */
+    uint4 *q4;  /* kind | flags<<8, rng draw index, pixel, sample index */
     float4 *q5; /* n(p), grad n(p): the field at p carried by the fused stepper */
 };
 
@@ -87,7 +87,7 @@ struct Lane {
     float refStart, segDist, distSurf, rem, sd;
     int stepsLeft, depth, kind, flags;
     PathRng rng;
-    unsigned long long sampleId;
+    unsigned pixel, sample; /* sample id = pixel * sppTotal + sample */
 };
 
 __device__ __forceinline__ bool intersect_shape(const MediumDev &M, float3 o, float3 d, float &tNear) {
@@ -154,8 +154,8 @@ __device__ __forceinline__ void film_put(const RenderParams &P, float sx, float 
 
 /* the sample's film position is draw 0/1 of its Philox stream: recomputed, not stored */
 __device__ __forceinline__ void sample_position(const RenderParams &P, const Lane &L, float &sx, float &sy) {
-    unsigned long long pixel = L.sampleId / (unsigned long long) P.sppTotal;
-    int x = (int) (pixel % (unsigned long long) P.W), y = (int) (pixel / (unsigned long long) P.W);
+    const unsigned yy = L.pixel / (unsigned) P.W;
+    int x = (int) (L.pixel - yy * (unsigned) P.W), y = (int) yy;
     uint4 b = philox4x32_10(L.rng.s0, L.rng.s1, 0u, 0u, L.rng.k0, L.rng.k1);
     sx = (float) x + (float) (b.x >> 8) * (1.0f / 16777216.0f);
     sy = (float) y + (float) (b.y >> 8) * (1.0f / 16777216.0f);
@@ -217,18 +217,26 @@ __device__ __forceinline__ void edge_weight(const MediumDev &M, float sd, float 
 __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, unsigned *st) {
     const MediumDev &M = P.M;
     const float zero[3] = {0.f, 0.f, 0.f};
+    L.rng.cachedBlock = 0xffffffffu; /* the cached Philox block lives only inside one event phase (registers) */
     while (L.kind >= E_BEGIN && L.kind != K_DEAD) {
         if (L.kind == E_NEW) {
             /* ---- SamplingIntegrator::renderBlock: next (pixel, sample) */
             unsigned long long g = atomicAdd(P.sampleCounter, 1ULL);
             if (g >= P.totalSamples) { L.kind = K_DEAD; break; }
             st[ST_SAMPLES]++;
-            unsigned long long pixel = g / (unsigned long long) P.sppLocal;
-            int k = (int) (g % (unsigned long long) P.sppLocal);
-            int s = P.sampleBegin + k * P.sampleStride;
-            L.sampleId = pixel * (unsigned long long) P.sppTotal + (unsigned long long) s;
-            L.rng.init(P.seed, L.sampleId, 0u);
-            int x = (int) (pixel % (unsigned long long) P.W), y = (int) (pixel / (unsigned long long) P.W);
+            unsigned pixel, k;
+            if (P.totalSamples <= 0xffffffffULL) { /* warp-uniform: 32-bit division in the common case */
+                pixel = (unsigned) g / (unsigned) P.sppLocal;
+                k = (unsigned) g - pixel * (unsigned) P.sppLocal;
+            } else {
+                pixel = (unsigned) (g / (unsigned long long) P.sppLocal);
+                k = (unsigned) (g - (unsigned long long) pixel * (unsigned long long) P.sppLocal);
+            }
+            L.pixel = pixel;
+            L.sample = (unsigned) P.sampleBegin + k * (unsigned) P.sampleStride;
+            L.rng.init(P.seed, (unsigned long long) pixel * (unsigned long long) P.sppTotal + L.sample, 0u);
+            const unsigned py = pixel / (unsigned) P.W;
+            int x = (int) (pixel - py * (unsigned) P.W), y = (int) py;
             float sx = (float) x + L.rng.next(), sy = (float) y + L.rng.next();
             /* PerspectiveCamera::sampleRay, closed form of m_sampleToCamera */
             float cx = (1.0f - 2.0f * (sx * P.invW)) * P.tanHalf, cy = (1.0f - 2.0f * (sy * P.invH)) * P.tanHalf / P.aspect;
@@ -355,8 +363,8 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.refStart = c.y; L.segDist = c.z; L.distSurf = c.w;
         L.rem = d.x; L.sd = d.y; L.stepsLeft = __float_as_int(d.z); L.depth = __float_as_int(d.w);
         L.kind = (int) (e.x & 0xffu); L.flags = (int) (e.x >> 8);
-        L.sampleId = ((unsigned long long) e.w << 32) | e.z;
-        L.rng.init(P.seed, L.sampleId, e.y);
+        L.pixel = e.z; L.sample = e.w;
+        L.rng.init(P.seed, (unsigned long long) e.z * (unsigned long long) P.sppTotal + e.w, e.y);
         float4 fg = P.in.q5[tid];
         L.n = fg.x; L.G = f3(fg.y, fg.z, fg.w);
     } else {
@@ -365,21 +373,32 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.thr[0] = L.thr[1] = L.thr[2] = 0.0f;
         L.refStart = L.segDist = L.distSurf = L.rem = L.sd = 0.0f;
         L.stepsLeft = L.depth = L.flags = 0;
-        L.sampleId = 0;
+        L.pixel = L.sample = 0;
         L.rng.init(P.seed, 0ULL, 0u);
         L.kind = E_NEW;
     }
 
+    StencilCache<MODE> S; /* registers only: refilled by the first step of the pass */
+    S.invalidate();
     const float h = M.h;
     int budget = P.stepsPerPass;
     float oplUnused = 0.0f;
+    /* ONE flat loop, three votes per iteration, and a two-way (warp-uniform) choice between a convergent
+     * step and the event phase.  (A nested step-loop/event-loop formulation left the halves of a warp
+     * that diverged in the event phase running the 600-instruction step body one after the other for
+     * the rest of the pass: ncu r01a/r01b, 19 of 32 lanes active.) */
     while (true) {
-        /* ---------------- convergent stepping phase */
-        while (budget > 0) {
-            const bool stepping = L.kind <= K_ENTRY;
-            const unsigned ms = __ballot_sync(0xffffffffu, stepping);
-            const unsigned mw = __ballot_sync(0xffffffffu, L.kind >= E_BEGIN && L.kind != K_DEAD);
-            if (ms == 0u || __popc(mw) >= P.maxWait) break;
+        /* Explicit reconvergence.  The event phase leaves the warp split into groups (its BSYNC is a plain one
+         * with YIELDs), and from then on every group would run the step body on its own, meeting the others
+         * only inside the collective votes (ncu r01c: 16 of 32 lanes active).  NVVM folds __syncwarp() into the
+         * following vote, so the barrier is spelled in PTX. */
+        asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+        const bool stepping = L.kind <= K_ENTRY;
+        const bool waiting = L.kind >= E_BEGIN && L.kind != K_DEAD;
+        const unsigned ms = __ballot_sync(0xffffffffu, stepping);
+        const unsigned mw = __ballot_sync(0xffffffffu, waiting);
+        if (ms != 0u && budget > 0 && __popc(mw) < P.maxWait) {
+            /* ---------------- convergent stepping phase */
             budget--;
             if (stepping) {
                 /* K_ENTRY is a zero-length step: with hc = 0 the kicks and the drift are exact no-ops and
@@ -387,40 +406,32 @@ k_render_pass(const __grid_constant__ RenderParams P) {
                 const int kind = L.kind;
                 const float hc = kind == K_FULL ? h : (kind == K_REM ? L.rem : (kind == K_BACKF ? -h : (kind == K_BACKR ? -L.rem : 0.0f)));
                 const float3 pOld = L.p;
-                er_step_fused<MODE>(M.rif, L.p, L.v, L.n, L.G, hc, oplUnused);
+                er_step_fused<MODE>(M.rif, S, L.p, L.v, L.n, L.G, hc, oplUnused);
                 const bool inside = inside_shape(M, L.p);
                 const bool moved = L.p.x != pOld.x || L.p.y != pOld.y || L.p.z != pOld.z;
-                if (kind == K_ENTRY) {
-                    L.kind = E_BEGIN;
+                int next;
+                if (kind == K_FULL) {
+                    next = inside ? ((L.stepsLeft == 1) ? ((L.flags & FLAG_TB) ? E_EXIT : K_REM) : K_FULL) : K_BACKF;
+                    if (inside) { L.distSurf += h; L.stepsLeft--; }
+                } else if (kind == K_REM) {
+                    next = inside ? E_REACHED : K_BACKR;
+                    if (inside) L.distSurf += L.rem;
+                } else if (kind == K_ENTRY) {
+                    next = E_BEGIN;
                 } else {
-                    st[ST_STEPS]++;
-                    if (kind == K_FULL) {
-                        if (inside) {
-                            L.distSurf += h;
-                            if (moved) L.flags |= FLAG_MOVED;
-                            if (--L.stepsLeft == 0) L.kind = (L.flags & FLAG_TB) ? E_EXIT : K_REM;
-                        } else {
-                            L.kind = K_BACKF;
-                        }
-                    } else if (kind == K_REM) {
-                        if (inside) {
-                            L.distSurf += L.rem;
-                            if (moved) L.flags |= FLAG_MOVED;
-                            L.kind = E_REACHED;
-                        } else {
-                            L.kind = K_BACKR;
-                        }
-                    } else {
-                        if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= h; /* :761 */
-                        L.kind = E_EXIT;
-                    }
+                    if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= h; /* :761 */
+                    next = E_EXIT;
                 }
+                if (kind <= K_REM && inside && moved) L.flags |= FLAG_MOVED;
+                if (kind != K_ENTRY) st[ST_STEPS]++;
+                L.kind = next;
             }
+        } else if (mw != 0u) {
+            /* ---------------- event phase: scatter / exit / regenerate for every waiting lane at once */
+            if (waiting) handle_events(P, L, st);
+        } else {
+            break; /* budget exhausted (or nobody alive) and nothing waiting */
         }
-        /* ---------------- event phase */
-        if (L.kind >= E_BEGIN && L.kind != K_DEAD) handle_events(P, L, st);
-        const unsigned alive = __ballot_sync(0xffffffffu, L.kind != K_DEAD);
-        if (alive == 0u || budget <= 0) break;
     }
 
     /* ---------------- compaction: survivors go to the output queue, one atomic per warp */
@@ -435,8 +446,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         P.out.q1[o] = make_float4(L.v.y, L.v.z, L.thr[0], L.thr[1]);
         P.out.q2[o] = make_float4(L.thr[2], L.refStart, L.segDist, L.distSurf);
         P.out.q3[o] = make_float4(L.rem, L.sd, __int_as_float(L.stepsLeft), __int_as_float(L.depth));
-        P.out.q4[o] = make_uint4((unsigned) L.kind | ((unsigned) L.flags << 8), L.rng.k, (unsigned) L.sampleId,
-                                 (unsigned) (L.sampleId >> 32));
+        P.out.q4[o] = make_uint4((unsigned) L.kind | ((unsigned) L.flags << 8), L.rng.k, L.pixel, L.sample);
         P.out.q5[o] = make_float4(L.n, L.G.x, L.G.y, L.G.z);
     }
 
@@ -504,22 +514,6 @@ void configure_camera(const mer_render_desc *r, RenderParams &P) {
     P.invH = 1.0f / r->height;
 }
 
-struct Scratch { /* per-call device scratch, freed on every exit path */
-    void *pool[12] = {nullptr};
-    unsigned *nOut = nullptr;
-    unsigned long long *counters = nullptr; /* [0] sample counter, [1..] stats */
-    unsigned long long *hostPinned = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    ~Scratch() {
-        for (void *p : pool) cudaFree(p);
-        cudaFree(nOut);
-        cudaFree(counters);
-        if (hostPinned) cudaFreeHost(hostPinned);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-    }
-};
-
 } /* namespace */
 
 extern "C" {
@@ -554,22 +548,27 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.film = film_dev;
 
     const unsigned TPB = 128;
-    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 2048u;
+    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 4096u;
     pool = ((pool + TPB - 1) / TPB) * TPB;
     if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) (((P.totalSamples + TPB - 1) / TPB) * TPB);
     if (pool == 0) pool = TPB;
 
-    Scratch S;
+    RenderScratch &S = *m->scratch;
+    std::lock_guard<std::mutex> hold(S.lock);
     const size_t qBytes = (size_t) pool * 16;
-    for (int i = 0; i < 12; i++) MER_CUDA(cudaMalloc(&S.pool[i], qBytes));
+    if (S.poolBytes < qBytes) {
+        S.release();
+        for (int i = 0; i < 12; i++) MER_CUDA(cudaMalloc(&S.pool[i], qBytes));
+        S.poolBytes = qBytes;
+        MER_CUDA(cudaMalloc(&S.nOut, sizeof(unsigned)));
+        MER_CUDA(cudaMalloc(&S.counters, (1 + ST_COUNT) * sizeof(unsigned long long)));
+        MER_CUDA(cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long)));
+        MER_CUDA(cudaEventCreate(&S.ev0));
+        MER_CUDA(cudaEventCreate(&S.ev1));
+    }
     PathPool A = {(float4 *) S.pool[0], (float4 *) S.pool[1], (float4 *) S.pool[2], (float4 *) S.pool[3], (uint4 *) S.pool[4], (float4 *) S.pool[5]};
     PathPool B = {(float4 *) S.pool[6], (float4 *) S.pool[7], (float4 *) S.pool[8], (float4 *) S.pool[9], (uint4 *) S.pool[10], (float4 *) S.pool[11]};
-    MER_CUDA(cudaMalloc(&S.nOut, sizeof(unsigned)));
-    MER_CUDA(cudaMalloc(&S.counters, (1 + ST_COUNT) * sizeof(unsigned long long)));
-    MER_CUDA(cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long)));
     MER_CUDA(cudaMemsetAsync(S.counters, 0, (1 + ST_COUNT) * sizeof(unsigned long long), stream));
-    MER_CUDA(cudaEventCreate(&S.ev0));
-    MER_CUDA(cudaEventCreate(&S.ev1));
     P.nOut = S.nOut;
     P.sampleCounter = S.counters;
     P.stats = S.counters + 1;

@@ -1,0 +1,191 @@
+"""CPU tests (no GPU): the oracle against the golden vectors generated from the reference's own
+basisspline.h, against the verbatim build in oracle/_ref when present, and its own invariants."""
+import os
+
+import numpy as np
+import pytest
+
+from common import (BOX_MAX, BOX_MIN, make_field, medium_props, oracle_medium_desc, oracle_render_desc,
+                    random_directions, random_points_in_box, scene_dict)
+from oracle.oracle import Oracle, RefSpline, volume_desc
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("tag,dtype", [("f32", np.float32), ("f64", np.float64)])
+def test_oracle_spline_bit_exact_vs_reference_golden(tag, dtype):
+    g = np.load(os.path.join(GOLDEN, "spline_ref_%s.npz" % tag))
+    orc = Oracle(dtype)
+    h = orc.rif_create(volume_desc(g["res"], g["bbox_min"], g["bbox_max"]), g["data"])
+    assert np.array_equal(orc.rif_coefficients(h, g["data"].size), g["coeff"])
+    f, grad, H = orc.rif_eval_hessian(h, g["points"])
+    assert np.array_equal(f, g["value"]) and np.array_equal(grad, g["gradient"]) and np.array_equal(H, g["hessian"])
+    for what in (0, 1, 2):
+        f2, g2 = orc.rif_eval(h, g["points"], what)
+        if what != 1:
+            assert np.array_equal(f2, g["value"])
+        if what != 0:
+            assert np.array_equal(g2, g["gradient"])
+    orc.rif_destroy(h)
+
+
+@pytest.mark.skipif(not RefSpline.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_oracle_spline_bit_exact_vs_verbatim_reference(dtype):
+    rng = np.random.default_rng(5)
+    res = (17, 12, 21)
+    data = (1 + rng.random((res[2], res[1], res[0]))).astype(np.float32)
+    lo, hi = np.array([0, -1, 2], np.float32), np.array([3, 1, 2.5], np.float32)
+    ref = RefSpline(dtype).build(data, res, lo, hi)
+    orc = Oracle(dtype)
+    h = orc.rif_create(volume_desc(res, lo, hi), data)
+    assert np.array_equal(ref.coefficients(), orc.rif_coefficients(h, data.size))
+    pitch = (hi - lo) / (np.array(res) - 1)
+    p = (lo + 2.1 * pitch + rng.random((3000, 3)) * (hi - lo - 4.2 * pitch)).astype(dtype)
+    fr, gr, Hr = ref.eval_hessian(p)
+    fo, go, Ho = orc.rif_eval_hessian(h, p)
+    assert np.array_equal(fr, fo) and np.array_equal(gr, go) and np.array_equal(Hr, Ho)
+    orc.rif_destroy(h)
+
+
+def test_spline_interpolates_data_at_nodes(oracle64):
+    """the prefilter makes the cubic B-spline INTERPOLATE the samples (that is what build3d is for)"""
+    res = (16, 14, 12)
+    data, lo, hi = make_field("random", res, seed=2)
+    h = oracle64.rif_create(volume_desc(res, lo, hi), data)
+    idx = np.stack(np.meshgrid(np.arange(2, 14), np.arange(2, 12), np.arange(2, 10), indexing="ij"), -1).reshape(-1, 3)
+    p = lo.astype(np.float64) + idx * ((hi - lo).astype(np.float64) / (np.array(res) - 1))
+    f, _ = oracle64.rif_eval(h, p, 0)
+    assert np.max(np.abs(f - data[idx[:, 2], idx[:, 1], idx[:, 0]])) < 1e-6  # float32 bbox -> node positions
+    oracle64.rif_destroy(h)
+
+
+def test_leapfrog_invariants(oracle64):
+    """known answers of heterogeneousrefractive.cpp:653-661: constant gradient => v_x, v_z constant and
+    v_y linear in arc length; radial field => (p x v) conserved by the discrete scheme"""
+    h, steps, n = 2e-3, 300, 500
+    p0 = (random_points_in_box(n, 1, margin=0.3) * 0.5).astype(np.float64)
+    d0 = random_directions(n, 2).astype(np.float64)
+    props = medium_props(stepsize=h)
+    for kind in ("linear", "radial"):
+        data, lo, hi = make_field(kind, 40)
+        orif = oracle64.rif_create(volume_desc((40,) * 3, lo, hi), data)
+        omed = oracle64.medium_create(oracle_medium_desc(props), orif)
+        n0, g0 = oracle64.rif_eval(orif, p0, 2)
+        v0 = d0 * n0[:, None]
+        out = oracle64.trace(omed, p0, v0, np.full(n, h * steps))
+        ok = out["success"]
+        assert ok.sum() > n // 2
+        if kind == "linear":
+            a = np.median(g0[:, 1])
+            assert np.max(np.abs(out["v"][ok][:, [0, 2]] - v0[ok][:, [0, 2]])) < 1e-5
+            assert np.max(np.abs(out["v"][ok][:, 1] - (v0[ok][:, 1] + a * out["dist_surf"][ok]))) < 1e-5
+        else:
+            # exact for a radial n; the 40^3 spline of it is radial only to interpolation error
+            assert np.max(np.abs(np.cross(out["p"][ok], out["v"][ok]) - np.cross(p0[ok], v0[ok]))) < 5e-5
+        # int(dist/h) full steps + ONE remainder step, even when the remainder is ~0 (quirk 3)
+        assert np.all(out["nsteps"][ok] == int(np.float64(h * steps) / np.float64(np.float32(h))) + 1)  # stepsize is a Float property
+        oracle64.medium_destroy(omed)
+        oracle64.rif_destroy(orif)
+
+
+def test_trace_quirks(oracle32):
+    """appendix A quirks 3-5: truncated step count + remainder step, step back with -h, distSurf one h short"""
+    data, lo, hi = make_field("radial", 32)
+    props = medium_props(stepsize=1e-2)
+    orif = oracle32.rif_create(volume_desc((32,) * 3, lo, hi), data)
+    omed = oracle32.medium_create(oracle_medium_desc(props), orif)
+    p0 = np.array([[0.0, 0.0, 0.0]], np.float32)
+    v0 = np.array([[0.0, 0.0, 1.0]], np.float32) * oracle32.rif_eval(orif, p0, 0)[0][:, None]
+    inside = oracle32.trace(omed, p0, v0, np.array([0.255], np.float32))
+    assert inside["success"][0] and inside["nsteps"][0] == 26 and abs(inside["dist_surf"][0] - 0.255) < 1e-6
+    out = oracle32.trace(omed, p0, v0, np.array([5.0], np.float32))
+    assert not out["success"][0]
+    k = out["nsteps"][0]  # steps until outside (k-1 forward incl. the exiting one) + 1 back
+    assert abs(out["dist_surf"][0] - (k - 2) * 1e-2) < 1e-4 and out["p"][0, 2] <= 1.0
+    tb = oracle32.trace_till_boundary(omed, p0, v0)
+    assert tb["nsteps"][0] == k and abs(tb["dist_surf"][0] - (k - 3) * 1e-2) < 1e-4  # one h short (:761)
+    assert np.allclose(tb["p"], out["p"], atol=1e-6)
+
+
+def test_sample_distance_semantics(oracle32):
+    data, lo, hi = make_field("linear", 24)
+    props = medium_props(stepsize=1e-2, strategy="balance", sigmaS=(2.0, 3.0, 4.0), sigmaA=(0.5, 0.25, 0.1))
+    orif = oracle32.rif_create(volume_desc((24,) * 3, lo, hi), data)
+    omed = oracle32.medium_create(oracle_medium_desc(props), orif)
+    w, sd = oracle32.medium_resolved(omed)
+    assert w == pytest.approx(max(2 / 2.5, 3 / 3.25, 4 / 4.1))  # max albedo (>= 0.5), :239-255
+    n = 4000
+    o = random_points_in_box(n, 3, margin=0.1)
+    d = random_directions(n, 4)
+    xi = np.random.default_rng(5).random((n, 2)).astype(np.float32)
+    r = oracle32.sample_distance(omed, o, d, 0.0, xi)
+    # xi >= w  => no medium interaction is sampled: traceTillBoundary, failure (:447-450, :495-498)
+    assert not r["success"][xi[:, 0] >= w].any()
+    s = r["success"]
+    ch = np.minimum((xi[:, 1] * 3).astype(int), 2)
+    sig_t = np.array([2.5, 3.25, 4.1], np.float32)
+    expect_t = -np.log(1 - (xi[:, 0] / np.float32(w)).astype(np.float64)) / sig_t[ch]
+    assert np.allclose(r["t"][s], expect_t[s], rtol=1e-5)
+    # balance pdfs (:540-548) and transmittance (:557) at the geometric distance
+    T = np.exp(-sig_t[None, :] * r["t"][:, None])
+    assert np.allclose(r["transmittance"], T, rtol=1e-5)
+    assert np.allclose(r["pdf_success"], w * (sig_t * T).mean(axis=1), rtol=1e-5)
+    assert np.allclose(r["pdf_failure"], w * T.mean(axis=1) + (1 - w), rtol=1e-5)
+    # v = n * d: |mRec.d| ~ n at the end point (quirk 2); refRatioSq = (n_end/n_start)^2 (quirk 7)
+    n_end = oracle32.rif_eval(orif, r["p"], 0)[0]
+    n_start = oracle32.rif_eval(orif, o, 0)[0]
+    assert np.allclose(np.linalg.norm(r["d"], axis=1), n_end, rtol=2e-3)
+    assert np.allclose(r["ref_ratio_sq"], (n_end / n_start) ** 2, rtol=1e-5)
+    # start outside insideVolumeLimits (quirk 8)
+    far = oracle32.sample_distance(omed, np.array([[5.0, 0, 0]]), np.array([[1.0, 0, 0]]), 0.0, np.array([[0.1, 0.1]]))
+    assert not far["success"][0] and np.all(far["transmittance"] == 0) and far["pdf_failure"][0] == 1
+
+
+def test_hg_normalisation_and_mean_cosine(oracle32):
+    for g in (0.9, -0.3, 0.0):
+        n = 200000
+        wi = np.repeat(np.array([[0.0, 0.0, 1.0]], np.float32), n, 0)
+        xi = np.random.default_rng(6).random((n, 2)).astype(np.float32)
+        wo, pdf = oracle32.hg_sample(g, wi, xi)
+        # wi points back along the incoming ray: mean cosine of the scattering angle is -<wi, wo>
+        assert abs(np.mean(-(wi * wo).sum(axis=1)) - g) < 5e-3
+        assert np.allclose(pdf, oracle32.hg_eval(g, wi, wo))
+        mu = np.linspace(-1, 1, 20001)
+        dirs = np.stack([np.sqrt(1 - mu ** 2), 0 * mu, mu], 1).astype(np.float32)
+        val = oracle32.hg_eval(g, np.repeat(wi[:1], mu.size, 0), dirs)
+        assert abs(np.trapezoid(val, mu) * 2 * np.pi - 1) < 1e-3
+
+
+def test_filter_tables_and_film_put(oracle32):
+    vals, r, s = oracle32.filter_table(1)
+    assert r == 2.0 and s == pytest.approx(31 / 2.0) and vals[31] == 0
+    assert abs(vals[:31].sum() * 2 * r / 31 - 1) < 1e-6  # rfilter.cpp:51-54 normalisation
+    vals, r, s = oracle32.filter_table(0)
+    assert r == pytest.approx(0.5 + 1e-5) and np.allclose(vals[:31], vals[0])
+
+
+def test_philox_known_answer(oracle32):
+    """Random123 known-answer test for philox4x32-10: counter = key = 0"""
+    def as_u24(words):
+        return np.array([(w >> 8) / 16777216.0 for w in words], np.float32)
+    assert np.array_equal(oracle32.philox(0, 0, 4), as_u24([0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]))
+    a, b = oracle32.philox(20201201, 77, 64), oracle32.philox(20201201, 78, 64)
+    assert not np.array_equal(a, b) and np.all((a >= 0) & (a < 1))
+
+
+def test_render_white_furnace_and_sharding(oracle32):
+    res = 16
+    from mitsubaer_b200 import fields
+    lo, hi = fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    data = np.full((res,) * 3, 1.33, np.float32)
+    props = medium_props(stepsize=5e-2, sigmaS=4.0, sigmaA=0.0)
+    orif = oracle32.rif_create(volume_desc((res,) * 3, lo, hi), data)
+    omed = oracle32.medium_create(oracle_medium_desc(props, 0.5), orif)
+    scene = scene_dict(16, 12, 4, rfilter="box", quad=False)
+    film, st = oracle32.render(omed, oracle_render_desc(scene, rr_depth=1000))
+    rgb = oracle32.film_develop(film)
+    assert st.samples == 16 * 12 * 4 and np.allclose(rgb, 1.0, atol=1e-4)
+    parts = [oracle32.render(omed, oracle_render_desc(scene, rr_depth=1000, sample_begin=r, sample_stride=3)) for r in range(3)]
+    assert sum(p[1].samples for p in parts) == st.samples and sum(p[1].ray_steps for p in parts) == st.ray_steps
+    assert np.allclose(sum(p[0] for p in parts), film, rtol=1e-5, atol=1e-6)
