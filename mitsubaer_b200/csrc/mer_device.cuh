@@ -86,6 +86,23 @@ __device__ __forceinline__ float bs_k1(float d) {
     return a > 2.0f ? 0.0f : s * r;
 }
 
+/* The four taps of a lookup sit at known distances: t0 in [1,2), t1 in [0,1), t2 in (-1,0], t3 in (-2,-1],
+ * so each needs only ONE branch of the reference's piecewise kernel (same polynomial, same operation order
+ * as bs_k0/bs_k1; at the shared end points both branches agree).  Halves the weight arithmetic. */
+__device__ __forceinline__ void bs_weights(float x, float fx, float w0[4], float w1[4]) {
+    const float d0 = x - (fx - 1.0f), d1 = x - fx, d2 = x - (fx + 1.0f), d3 = x - (fx + 2.0f);
+    const float a0 = d0, a1 = d1, a2 = -d2, a3 = -d3; /* |d| */
+    const float t0 = 2.0f - a0, t3 = 2.0f - a3;
+    w0[0] = 0.16666666666666666667f * t0 * t0 * t0;
+    w1[0] = -0.5f * t0 * t0;
+    w0[1] = 0.66666666666666666667f - a1 * a1 + 0.5f * a1 * a1 * a1;
+    w1[1] = (1.5f * a1 - 2.0f) * a1;
+    w0[2] = 0.66666666666666666667f - a2 * a2 + 0.5f * a2 * a2 * a2;
+    w1[2] = -((1.5f * a2 - 2.0f) * a2);
+    w0[3] = 0.16666666666666666667f * t3 * t3 * t3;
+    w1[3] = 0.5f * t3 * t3;
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 __device__ __forceinline__ float3 rif_to_volume(const RifDev &R, float3 p) {
@@ -118,13 +135,9 @@ __device__ __forceinline__ void rif_tricubic(const RifDev &R, float3 pv, float &
     const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
     const int i0 = (int) fx, j0 = (int) fy, k0 = (int) fz;
     float wx0[4], wx1[4], wy0[4], wy1[4], wz0[4], wz1[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        float dx = x - (fx + (float) (t - 1)), dy = y - (fy + (float) (t - 1)), dz = z - (fz + (float) (t - 1));
-        wx0[t] = bs_k0(dx); wx1[t] = bs_k1(dx);
-        wy0[t] = bs_k0(dy); wy1[t] = bs_k1(dy);
-        wz0[t] = bs_k0(dz); wz1[t] = bs_k1(dz);
-    }
+    bs_weights(x, fx, wx0, wx1);
+    bs_weights(y, fy, wy0, wy1);
+    bs_weights(z, fz, wz0, wz1);
     const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
     const int ic = clampi(i0, 0, N0 - 1);
     size_t rowOff[4], slabOff[4];
@@ -225,13 +238,9 @@ __device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, 
         S.i = i0; S.j = j0; S.k = k0;
     }
     float wx0[4], wx1[4], wy0[4], wy1[4], wz0[4], wz1[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        float dx = x - (fx + (float) (t - 1)), dy = y - (fy + (float) (t - 1)), dz = z - (fz + (float) (t - 1));
-        wx0[t] = bs_k0(dx); wx1[t] = bs_k1(dx);
-        wy0[t] = bs_k0(dy); wy1[t] = bs_k1(dy);
-        wz0[t] = bs_k0(dz); wz1[t] = bs_k1(dz);
-    }
+    bs_weights(x, fx, wx0, wx1);
+    bs_weights(y, fy, wy0, wy1);
+    bs_weights(z, fz, wz0, wz1);
     float accF = 0.f, accX = 0.f, accY = 0.f, accZ = 0.f;
 #pragma unroll
     for (int dz = 0; dz < 4; dz++) {
@@ -389,7 +398,7 @@ __device__ __forceinline__ void coordinate_system(float3 a, float3 &b, float3 &c
     b = f3(__fsub_rn(__fmul_rn(c.y, a.z), __fmul_rn(c.z, a.y)), __fsub_rn(__fmul_rn(c.z, a.x), __fmul_rn(c.x, a.z)),
            __fsub_rn(__fmul_rn(c.x, a.y), __fmul_rn(c.y, a.x)));
 }
-__device__ __forceinline__ float3 hg_sample_dev(float g, float3 wi, float u1, float u2) {
+static __device__ __noinline__ float3 hg_sample_dev(float g, float3 wi, float u1, float u2) {
     float cosTheta;
     if (fabsf(g) < MER_EPSILON) {
         cosTheta = __fsub_rn(1.0f, __fmul_rn(2.0f, u1));
@@ -412,13 +421,13 @@ __device__ __forceinline__ float3 hg_sample_dev(float g, float3 wi, float u1, fl
 }
 
 /* fastlog / fastexp: double precision rounded to float on Linux x86-64, math.h:185-199 */
-__device__ __forceinline__ float fastlog_dev(float x) { return (float) log((double) x); }
-__device__ __forceinline__ float fastexp_dev(float x) { return (float) exp((double) x); }
+static __device__ __noinline__ float fastlog_dev(float x) { return (float) log((double) x); }
+static __device__ __noinline__ float fastexp_dev(float x) { return (float) exp((double) x); }
 
 /* ------------------------------------------------------------------ Philox4x32-10
  * key = seed, counter = (sample id lo, hi, block, 0); float = (u >> 8) * 2^-24.  The k-th
  * float of a sample's stream is word k%4 of block k/4, so the only per-path RNG state is k. */
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+static __device__ __noinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {

@@ -24,10 +24,15 @@
  * is entered only when enough lanes are waiting, which bounds divergence.
  */
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "mer_internal.h"
+
+#ifndef MER_RENDER_MIN_BLOCKS
+#define MER_RENDER_MIN_BLOCKS 3 /* 170 registers/thread: the 64-register stencil cache fits without spills */
+#endif
 
 namespace {
 
@@ -132,7 +137,7 @@ __device__ __forceinline__ bool intersect_quad(const RenderParams &P, float3 o, 
 }
 
 /* ImageBlock::put (imageblock.h:144-190) onto the global film with red.global.add.f32 */
-__device__ __forceinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha,
+__device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha,
                                          unsigned &nonfinite) {
     const float value[5] = {L[0], L[1], L[2], alpha, 1.0f};
 #pragma unroll
@@ -185,7 +190,7 @@ __device__ __forceinline__ void begin_trace(const RenderParams &P, Lane &L, floa
 }
 
 /* exponential free-flight pdfs + transmittance at geometric length d (:533-562) */
-__device__ __forceinline__ void edge_weight(const MediumDev &M, float sd, float d, bool success, float edge[3]) {
+__device__ __noinline__ void edge_weight(const MediumDev &M, float sd, float d, bool success, float edge[3]) {
     float pdfFailure = 0.0f, pdfSuccess = 0.0f;
     if (M.strategy == MER_STRATEGY_BALANCE) {
 #pragma unroll
@@ -344,7 +349,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MER_RENDER_MIN_BLOCKS)
 k_render_pass(const __grid_constant__ RenderParams P) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -544,7 +549,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     }
     P.hasQuad = r->has_quad;
     P.stepsPerPass = r->steps_per_pass > 0 ? r->steps_per_pass : 2048;
-    P.maxWait = 8;
+    P.maxWait = 10;
+    if (const char *e = getenv("MER_MAX_WAIT")) P.maxWait = atoi(e); /* tuning knob */
     P.film = film_dev;
 
     const unsigned TPB = 128;

@@ -13,7 +13,7 @@ grid = mer.GridDataSource(data=den_np, min=bench.BOX_MIN, max=bench.BOX_MAX)
 med = mer.HeterogeneousRefractiveMedium(bench.medium_props(w)).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9)).addChild("density", grid).configure()
 scene = bench.scene_dict(w, spp)
 film = torch.zeros(w["height"], w["width"], 5, device=dev)
-for spass, pool in ((2048, 0), (4096, 0), (1024, 0), (2048, 148*4096), (2048, 148*1024), (8192, 0)):
+for spass, pool in ((2048, 0),):
     integ = mer.EikonalVolPathIntegrator(maxDepth=64, rrDepth=5, stepsPerPass=spass, poolPaths=pool)
     for rep in range(2):
         film.zero_(); torch.cuda.synchronize(); t0 = time.time()

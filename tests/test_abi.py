@@ -125,3 +125,17 @@ def test_field_generators():
     lo, hi = f.padded_bbox((-1, -1, -1), (1, 1, 1), (64, 64, 64))
     pitch = (hi - lo) / 63
     assert np.allclose(lo + 3 * pitch, -1, atol=1e-6) and np.allclose(hi - 3 * pitch, 1, atol=1e-6)
+
+
+def test_plain_c_client_builds_and_fails_loudly_without_gpu(tmp_path):
+    """integration/example_host.c: the boundary is usable from C99 with nothing but the header"""
+    exe = tmp_path / "example_host"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "integration", "example_host.c"), "-L", os.path.dirname(_abi.LIB_PATH),
+                    "-lmitsubaer_b200", "-lm", "-Wl,-rpath," + os.path.dirname(_abi.LIB_PATH), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    if mer.device_count() == 0:
+        assert "no CPU fallback" in out.stdout
+    else:
+        assert "eikonal steps" in out.stdout
