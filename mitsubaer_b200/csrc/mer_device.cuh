@@ -204,16 +204,39 @@ __device__ __forceinline__ void rif_trilinear(const RifDev &R, float3 pv, float 
  * coefficient block.  The block is kept in registers (16 float4) and re-fetched only when the cell
  * index changes: the L2->L1 traffic of a step drops from 512 B to 512 B x P(cell change) (ncu r01b:
  * the uncached kernel was bound by the L1/L2 pipe at a 10 % L1 hit rate, not by issue). */
-template <int MODE> struct StencilCache;
-template <> struct StencilCache<MER_RIF_TRICUBIC> {
-    int i, j, k;
-    float4 c[16];
-    __device__ __forceinline__ void invalidate() { i = j = k = -0x7fffffff; }
+/* Where the cached block lives.  Registers (MER_STENCIL_SMEM=0): no extra instructions, 168 regs -> 12
+ * warps/SM.  Shared memory (MER_STENCIL_SMEM=1): [row][thread] float4, conflict-free LDS.128, ~100 regs ->
+ * 20 warps/SM at the price of 16 LDS per step. */
+#ifndef MER_STENCIL_SMEM
+#define MER_STENCIL_SMEM 0
+#endif
+#define MER_STENCIL_BLOCK 128 /* threads per CTA of every kernel that uses a stencil cache */
+
+template <int ROWS> struct StencilStore {
+#if MER_STENCIL_SMEM
+    float4 *base; /* &smem[threadIdx.x]; row r at base[r * MER_STENCIL_BLOCK] */
+    __device__ __forceinline__ float4 get(int r) const { return base[r * MER_STENCIL_BLOCK]; }
+    __device__ __forceinline__ void set(int r, float4 v) { base[r * MER_STENCIL_BLOCK] = v; }
+    __device__ __forceinline__ void bind() {
+        __shared__ float4 stencilSmem[ROWS * MER_STENCIL_BLOCK];
+        base = stencilSmem + threadIdx.x;
+    }
+#else
+    float4 c[ROWS];
+    __device__ __forceinline__ float4 get(int r) const { return c[r]; }
+    __device__ __forceinline__ void set(int r, float4 v) { c[r] = v; }
+    __device__ __forceinline__ void bind() {}
+#endif
 };
-template <> struct StencilCache<MER_RIF_TRILINEAR_PACKED> {
+
+template <int MODE> struct StencilCache;
+template <> struct StencilCache<MER_RIF_TRICUBIC> : StencilStore<16> {
     int i, j, k;
-    float4 c[8];
-    __device__ __forceinline__ void invalidate() { i = j = k = -0x7fffffff; }
+    __device__ __forceinline__ void invalidate() { bind(); i = j = k = -0x7fffffff; }
+};
+template <> struct StencilCache<MER_RIF_TRILINEAR_PACKED> : StencilStore<8> {
+    int i, j, k;
+    __device__ __forceinline__ void invalidate() { bind(); i = j = k = -0x7fffffff; }
 };
 
 __device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, StencilCache<MER_RIF_TRICUBIC> &S,
@@ -234,7 +257,7 @@ __device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, 
 #pragma unroll
         for (int dz = 0; dz < 4; dz++)
 #pragma unroll
-            for (int dy = 0; dy < 4; dy++) S.c[dz * 4 + dy] = __ldg(base + slabOff[dz] + rowOff[dy]);
+            for (int dy = 0; dy < 4; dy++) S.set(dz * 4 + dy, __ldg(base + slabOff[dz] + rowOff[dy]));
         S.i = i0; S.j = j0; S.k = k0;
     }
     float wx0[4], wx1[4], wy0[4], wy1[4], wz0[4], wz1[4];
@@ -247,7 +270,7 @@ __device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, 
         float b00 = 0.f, b10 = 0.f, b01 = 0.f;
 #pragma unroll
         for (int dy = 0; dy < 4; dy++) {
-            const float4 q = S.c[dz * 4 + dy];
+            const float4 q = S.get(dz * 4 + dy);
             float a0 = q.x * wx0[0] + q.y * wx0[1] + q.z * wx0[2] + q.w * wx0[3];
             float a1 = q.x * wx1[0] + q.y * wx1[1] + q.z * wx1[2] + q.w * wx1[3];
             b00 = fmaf(a0, wy0[dy], b00);
@@ -273,13 +296,13 @@ __device__ __forceinline__ void rif_trilinear_cached(const RifDev &R, float3 pv,
     if (i0 != S.i || j0 != S.j || k0 != S.k) {
         const float4 *b = R.packed + ((size_t) k0 * N1 + j0) * (size_t) N0 + i0;
         const size_t sy = N0, sz = (size_t) N0 * N1;
-        S.c[0] = __ldg(b); S.c[1] = __ldg(b + 1); S.c[2] = __ldg(b + sy); S.c[3] = __ldg(b + sy + 1);
-        S.c[4] = __ldg(b + sz); S.c[5] = __ldg(b + sz + 1); S.c[6] = __ldg(b + sz + sy); S.c[7] = __ldg(b + sz + sy + 1);
+        S.set(0, __ldg(b)); S.set(1, __ldg(b + 1)); S.set(2, __ldg(b + sy)); S.set(3, __ldg(b + sy + 1));
+        S.set(4, __ldg(b + sz)); S.set(5, __ldg(b + sz + 1)); S.set(6, __ldg(b + sz + sy)); S.set(7, __ldg(b + sz + sy + 1));
         S.i = i0; S.j = j0; S.k = k0;
     }
     const float tx = x - (float) i0, ty = y - (float) j0, tz = z - (float) k0;
-    float4 r = lerp4(lerp4(lerp4(S.c[0], S.c[1], tx), lerp4(S.c[2], S.c[3], tx), ty),
-                     lerp4(lerp4(S.c[4], S.c[5], tx), lerp4(S.c[6], S.c[7], tx), ty), tz);
+    float4 r = lerp4(lerp4(lerp4(S.get(0), S.get(1), tx), lerp4(S.get(2), S.get(3), tx), ty),
+                     lerp4(lerp4(S.get(4), S.get(5), tx), lerp4(S.get(6), S.get(7), tx), ty), tz);
     f = r.x;
     g = f3(r.y, r.z, r.w);
 }

@@ -10,6 +10,7 @@
  *   HGPhaseFunction                 src/phase/hg.cpp:76-110
  */
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -65,53 +66,80 @@ __device__ __forceinline__ void trace_till_boundary_dev(const MediumDev &M, Sten
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(128)
+/* Batch stepper behind mer_medium_trace_* (and the C4 step-size sweep).  Rays of a batch need very
+ * different step counts (they leave the shape at random times), so a thread-per-ray loop leaves most
+ * lanes idle waiting for the warp's longest ray (ncu r01e: 13.6 of 32 lanes active).  Instead every lane
+ * is a small state machine over the SAME flat loop: it takes the next ray of its stride as soon as its
+ * current one ends, and the warp executes one convergent step body (one lookup call site) per iteration.
+ * Per-ray results are identical to trace() / traceTillBoundary() (:671-691, :742-776). */
+enum TraceKind : int { T_FULL = 0, T_REM = 1, T_BACKF = 2, T_BACKR = 3, T_ENTRY = 4, T_IDLE = 5 };
+
+template <int MODE, bool TILL_BOUNDARY>
+__global__ void __launch_bounds__(128, 3)
 k_trace(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P, float *__restrict__ V,
         const float *__restrict__ dist, uint8_t *__restrict__ success, float *__restrict__ distSurfOut,
-        float *__restrict__ oplOut, int32_t *__restrict__ nstepsOut, unsigned long long *__restrict__ stepCounter) {
-    unsigned long long local = 0;
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nRays; i += (size_t) gridDim.x * blockDim.x) {
-        float3 p = f3(P[3 * i], P[3 * i + 1], P[3 * i + 2]), v = f3(V[3 * i], V[3 * i + 1], V[3 * i + 2]);
-        float n, ds, opl = 0.0f;
-        float3 G;
-        int count = 0;
-        StencilCache<MODE> S;
-        S.invalidate();
-        rif_lookup_cached<MODE>(M.rif, p, S, n, G);
-        bool ok = trace_dev<MODE>(M, S, p, v, n, G, dist[i], ds, opl, count);
-        P[3 * i] = p.x; P[3 * i + 1] = p.y; P[3 * i + 2] = p.z;
-        V[3 * i] = v.x; V[3 * i + 1] = v.y; V[3 * i + 2] = v.z;
-        if (success) success[i] = ok ? 1 : 0;
-        if (distSurfOut) distSurfOut[i] = ds;
-        if (oplOut) oplOut[i] = opl;
-        if (nstepsOut) nstepsOut[i] = count;
-        local += (unsigned long long) count;
-    }
-    if (stepCounter) {
-        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-        if ((threadIdx.x & 31) == 0 && local) atomicAdd(stepCounter, local);
-    }
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(128)
-k_trace_till_boundary(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P, float *__restrict__ V,
-                      float *__restrict__ distSurfOut, float *__restrict__ oplOut, int32_t *__restrict__ nstepsOut) {
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nRays; i += (size_t) gridDim.x * blockDim.x) {
-        float3 p = f3(P[3 * i], P[3 * i + 1], P[3 * i + 2]), v = f3(V[3 * i], V[3 * i + 1], V[3 * i + 2]);
-        float n, ds, opl = 0.0f;
-        float3 G;
-        int count = 0;
-        StencilCache<MODE> S;
-        S.invalidate();
-        rif_lookup_cached<MODE>(M.rif, p, S, n, G);
-        trace_till_boundary_dev<MODE>(M, S, p, v, n, G, ds, opl, count);
-        P[3 * i] = p.x; P[3 * i + 1] = p.y; P[3 * i + 2] = p.z;
-        V[3 * i] = v.x; V[3 * i + 1] = v.y; V[3 * i + 2] = v.z;
-        if (distSurfOut) distSurfOut[i] = ds;
-        if (oplOut) oplOut[i] = opl;
-        if (nstepsOut) nstepsOut[i] = count;
+        float *__restrict__ oplOut, int32_t *__restrict__ nstepsOut) {
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    size_t next = (size_t) blockIdx.x * blockDim.x + threadIdx.x, cur = 0;
+    StencilCache<MODE> S;
+    S.invalidate();
+    float3 p = f3(0.f, 0.f, 0.f), v = p, G = p;
+    float n = 1.0f, ds = 0.0f, opl = 0.0f, rem = 0.0f;
+    int kind = T_IDLE, stepsLeft = 0, count = 0;
+    const float h = M.h;
+    while (true) {
+        asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); /* see k_render_pass */
+        if (kind == T_IDLE && next < nRays) {
+            cur = next;
+            next += stride;
+            p = f3(P[3 * cur], P[3 * cur + 1], P[3 * cur + 2]);
+            v = f3(V[3 * cur], V[3 * cur + 1], V[3 * cur + 2]);
+            n = 1.0f; G = f3(0.f, 0.f, 0.f);
+            ds = 0.0f; opl = 0.0f; count = 0;
+            if (TILL_BOUNDARY) { stepsLeft = 100000; rem = 0.0f; }
+            else trace_split(dist[cur], h, stepsLeft, rem);
+            kind = T_ENTRY; /* zero-length step: fetches the field at the start point */
+        }
+        if (__ballot_sync(0xffffffffu, kind != T_IDLE) == 0u) break;
+        if (kind != T_IDLE) {
+            const int k = kind;
+            const float hc = k == T_FULL ? h : (k == T_REM ? rem : (k == T_BACKF ? -h : (k == T_BACKR ? -rem : 0.0f)));
+            er_step_fused<MODE>(M.rif, S, p, v, n, G, hc, opl);
+            const bool inside = inside_shape(M, p);
+            bool done = false, ok = false;
+            if (k == T_ENTRY) {
+                opl = 0.0f;
+                kind = (TILL_BOUNDARY || stepsLeft > 0) ? T_FULL : T_REM;
+            } else {
+                count++;
+                if (k == T_FULL) {
+                    if (inside) {
+                        ds += h;
+                        if (--stepsLeft == 0) {
+                            if (TILL_BOUNDARY) done = true; /* 1e5 steps exhausted, :746 */
+                            else kind = T_REM;
+                        }
+                    } else {
+                        kind = T_BACKF;
+                    }
+                } else if (k == T_REM) {
+                    if (inside) { ds += rem; done = true; ok = true; }
+                    else kind = T_BACKR;
+                } else {
+                    if (TILL_BOUNDARY && k == T_BACKF) ds -= h; /* :761 */
+                    done = true;
+                }
+            }
+            if (done) {
+                P[3 * cur] = p.x; P[3 * cur + 1] = p.y; P[3 * cur + 2] = p.z;
+                V[3 * cur] = v.x; V[3 * cur + 1] = v.y; V[3 * cur + 2] = v.z;
+                if (success) success[cur] = ok ? 1 : 0;
+                if (distSurfOut) distSurfOut[cur] = ds;
+                if (oplOut) oplOut[cur] = opl;
+                if (nstepsOut) nstepsOut[cur] = count;
+                kind = T_IDLE;
+            }
+        }
     }
 }
 
@@ -240,10 +268,17 @@ struct DevBuf {
     template <typename T> T *as() { return (T *) ptr; }
 };
 
-unsigned trace_grid(size_t n) {
-    /* persistent-style sizing: a multiple of the SM count, capped at what is resident */
+/* persistent-style sizing: every CTA the kernel can keep resident (occupancy query: 3 per SM for the
+ * 168-register tricubic stepper, 6 for the packed one), times two so that the tail of one wave overlaps
+ * the start of the next */
+template <typename K> unsigned trace_grid(K kernel, size_t n) {
+    int perSm = 3, sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, 128, 0) != cudaSuccess || perSm < 1) perSm = 3;
+    size_t cap = (size_t) sms * (size_t) perSm * 2u;
+    if (const char *e = getenv("MER_TRACE_CTAS_PER_SM")) cap = (size_t) sms * (size_t) atoi(e); /* tuning knob */
     size_t blocks = (n + 127) / 128;
-    size_t cap = 148u * 16u;
     return (unsigned) (blocks < cap ? blocks : cap);
 }
 
@@ -356,11 +391,11 @@ int mer_medium_trace_device(const mer_medium *m, size_t n, float *p_dev, float *
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(m->device);
     if (m->rif->mode == MER_RIF_TRICUBIC)
-        MER_LAUNCH(k_trace<MER_RIF_TRICUBIC>, trace_grid(n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev, v_dev,
-                   dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev, (unsigned long long *) nullptr);
+        MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, false>), trace_grid(k_trace<MER_RIF_TRICUBIC, false>, n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev, v_dev,
+                   dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev);
     else
-        MER_LAUNCH(k_trace<MER_RIF_TRILINEAR_PACKED>, trace_grid(n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev,
-                   v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev, (unsigned long long *) nullptr);
+        MER_LAUNCH((k_trace<MER_RIF_TRILINEAR_PACKED, false>), trace_grid(k_trace<MER_RIF_TRILINEAR_PACKED, false>, n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev,
+                   v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev);
     return MER_OK;
 }
 
@@ -390,11 +425,11 @@ int mer_medium_trace_till_boundary_batch(const mer_medium *m, size_t n, float *p
     UP(dp, p, n * 12); UP(dv, v, n * 12);
     UP(dds, (void *) nullptr, n * 4); UP(dopl, (void *) nullptr, n * 4); UP(dns, (void *) nullptr, n * 4);
     if (m->rif->mode == MER_RIF_TRICUBIC)
-        MER_LAUNCH(k_trace_till_boundary<MER_RIF_TRICUBIC>, trace_grid(n), 128, 0, 0, m->dev, n, dp.as<float>(),
-                   dv.as<float>(), dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
+        MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, true>), trace_grid(k_trace<MER_RIF_TRICUBIC, true>, n), 128, 0, 0, m->dev, n, dp.as<float>(), dv.as<float>(),
+                   (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
     else
-        MER_LAUNCH(k_trace_till_boundary<MER_RIF_TRILINEAR_PACKED>, trace_grid(n), 128, 0, 0, m->dev, n, dp.as<float>(),
-                   dv.as<float>(), dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
+        MER_LAUNCH((k_trace<MER_RIF_TRILINEAR_PACKED, true>), trace_grid(k_trace<MER_RIF_TRILINEAR_PACKED, true>, n), 128, 0, 0, m->dev, n, dp.as<float>(), dv.as<float>(),
+                   (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
     MER_CUDA(cudaDeviceSynchronize());
     DOWN(p, dp, n * 12); DOWN(v, dv, n * 12); DOWN(dist_surf_out, dds, n * 4); DOWN(opl_out, dopl, n * 4);
     DOWN(nsteps_out, dns, n * 4);
@@ -423,10 +458,10 @@ int mer_medium_sample_distance_batch(const mer_medium *m, size_t n, const float 
     o.nsteps = dns.as<int32_t>();
     const float *mintDev = ray_mint ? dmint.as<float>() : nullptr;
     if (m->rif->mode == MER_RIF_TRICUBIC)
-        MER_LAUNCH(k_sample_distance<MER_RIF_TRICUBIC>, trace_grid(n), 128, 0, 0, m->dev, n, dro.as<float>(),
+        MER_LAUNCH(k_sample_distance<MER_RIF_TRICUBIC>, trace_grid(k_sample_distance<MER_RIF_TRICUBIC>, n), 128, 0, 0, m->dev, n, dro.as<float>(),
                    drd.as<float>(), mintDev, dxi.as<float>(), o);
     else
-        MER_LAUNCH(k_sample_distance<MER_RIF_TRILINEAR_PACKED>, trace_grid(n), 128, 0, 0, m->dev, n, dro.as<float>(),
+        MER_LAUNCH(k_sample_distance<MER_RIF_TRILINEAR_PACKED>, trace_grid(k_sample_distance<MER_RIF_TRILINEAR_PACKED>, n), 128, 0, 0, m->dev, n, dro.as<float>(),
                    drd.as<float>(), mintDev, dxi.as<float>(), o);
     MER_CUDA(cudaDeviceSynchronize());
     DOWN(rec->success, dok, n); DOWN(rec->t, dt, n * 4); DOWN(rec->p, dp, n * 12); DOWN(rec->d, dd, n * 12);
