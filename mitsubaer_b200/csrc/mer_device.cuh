@@ -307,6 +307,49 @@ __device__ __forceinline__ void rif_trilinear_cached(const RifDev &R, float3 pv,
     g = f3(r.y, r.z, r.w);
 }
 
+/* Software prefetch of the NEXT cell's stencil rows.  A warp stalls for a full L2/HBM round trip whenever
+ * one of its lanes changes cell (at h = pitch/4 that is almost every warp-step).  The position one step ahead
+ * is predictable to O(h^2) by linear extrapolation, so when it falls into a different cell the 16 rows of that
+ * cell are pulled towards L1 one step early; the real (dependent) fetch of the next step then hits on chip. */
+#ifndef MER_PREFETCH
+#define MER_PREFETCH 0 /* measured: CCTL.E.PF1 + the extra index math cost more than the latency they hide (-15 %) */
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
+__device__ __forceinline__ void rif_prefetch_tricubic(const RifDev &R, float3 pvNext, int ci, int cj, int ck) {
+    const int i0 = (int) floorf((pvNext.x - R.xmin[0]) * R.xres[0]), j0 = (int) floorf((pvNext.y - R.xmin[1]) * R.xres[1]),
+              k0 = (int) floorf((pvNext.z - R.xmin[2]) * R.xres[2]);
+    if (i0 != ci || j0 != cj || k0 != ck) {
+        const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
+        const float4 *base = R.coeff4 + clampi(i0, 0, N0 - 1);
+#pragma unroll
+        for (int dz = 0; dz < 4; dz++) {
+            const size_t slab = (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
+#pragma unroll
+            for (int dy = 0; dy < 4; dy++) prefetch_l1(base + slab + (size_t) clampi(j0 - 1 + dy, 0, N1 - 1) * (size_t) N0);
+        }
+    }
+}
+__device__ __forceinline__ void rif_prefetch_trilinear(const RifDev &R, float3 pvNext, int ci, int cj, int ck) {
+    const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
+    const int i0 = clampi((int) floorf((pvNext.x - R.xmin[0]) * R.xres[0]), 0, N0 - 2),
+              j0 = clampi((int) floorf((pvNext.y - R.xmin[1]) * R.xres[1]), 0, N1 - 2),
+              k0 = clampi((int) floorf((pvNext.z - R.xmin[2]) * R.xres[2]), 0, N2 - 2);
+    if (i0 != ci || j0 != cj || k0 != ck) {
+        const float4 *b = R.packed + ((size_t) k0 * N1 + j0) * (size_t) N0 + i0;
+        const size_t sy = N0, sz = (size_t) N0 * N1;
+        prefetch_l1(b); prefetch_l1(b + sy); prefetch_l1(b + sz); prefetch_l1(b + sz + sy); /* x and x+1 share a sector pair */
+        prefetch_l1(b + 1); prefetch_l1(b + sy + 1); prefetch_l1(b + sz + 1); prefetch_l1(b + sz + sy + 1);
+    }
+}
+template <int MODE> __device__ __forceinline__ void rif_prefetch(const RifDev &R, float3 pwNext, const StencilCache<MODE> &S) {
+#if MER_PREFETCH
+    const float3 pv = rif_to_volume(R, pwNext);
+    if (MODE == MER_RIF_TRICUBIC) rif_prefetch_tricubic(R, pv, S.i, S.j, S.k);
+    else rif_prefetch_trilinear(R, pv, S.i, S.j, S.k);
+#endif
+}
+
 template <int MODE>
 __device__ __forceinline__ void rif_lookup_cached(const RifDev &R, float3 pw, StencilCache<MODE> &S, float &n, float3 &G);
 template <>
@@ -383,10 +426,12 @@ __device__ __forceinline__ void er_step_fused(const RifDev &R, StencilCache<MODE
     const float hs = __fmul_rn(0.5f, h);
     v = f3(__fadd_rn(v.x, __fmul_rn(hs, G.x)), __fadd_rn(v.y, __fmul_rn(hs, G.y)), __fadd_rn(v.z, __fmul_rn(hs, G.z)));
     const float recip = __frcp_rn(n);
+    const float3 pOld = p;
     p = f3(__fadd_rn(p.x, __fmul_rn(__fmul_rn(h, v.x), recip)), __fadd_rn(p.y, __fmul_rn(__fmul_rn(h, v.y), recip)),
            __fadd_rn(p.z, __fmul_rn(__fmul_rn(h, v.z), recip)));
     opl = __fadd_rn(opl, __fmul_rn(h, n));
     rif_lookup_cached<MODE>(R, p, S, n, G);
+    rif_prefetch<MODE>(R, f3(p.x + (p.x - pOld.x), p.y + (p.y - pOld.y), p.z + (p.z - pOld.z)), S);
     v = f3(__fadd_rn(v.x, __fmul_rn(hs, G.x)), __fadd_rn(v.y, __fmul_rn(hs, G.y)), __fadd_rn(v.z, __fmul_rn(hs, G.z)));
 }
 
