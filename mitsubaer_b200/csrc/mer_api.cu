@@ -35,6 +35,11 @@ int check_device(int device) {
     return MER_OK;
 }
 
+RenderScratch &device_scratch(int device) {
+    static RenderScratch scratch[64];
+    return scratch[(device >= 0 && device < 64) ? device : 0];
+}
+
 } /* namespace mer */
 
 extern "C" {

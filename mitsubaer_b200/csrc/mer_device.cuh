@@ -239,12 +239,7 @@ template <> struct StencilCache<MER_RIF_TRILINEAR_PACKED> : StencilStore<8> {
     __device__ __forceinline__ void invalidate() { bind(); i = j = k = -0x7fffffff; }
 };
 
-__device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, StencilCache<MER_RIF_TRICUBIC> &S,
-                                                    float &f, float3 &g) {
-    const float x = (pv.x - R.xmin[0]) * R.xres[0], y = (pv.y - R.xmin[1]) * R.xres[1],
-                z = (pv.z - R.xmin[2]) * R.xres[2];
-    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
-    const int i0 = (int) fx, j0 = (int) fy, k0 = (int) fz;
+__device__ __forceinline__ void stencil_ensure(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
     if (i0 != S.i || j0 != S.j || k0 != S.k) {
         const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
         const float4 *base = R.coeff4 + clampi(i0, 0, N0 - 1);
@@ -260,6 +255,14 @@ __device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, 
             for (int dy = 0; dy < 4; dy++) S.set(dz * 4 + dy, __ldg(base + slabOff[dz] + rowOff[dy]));
         S.i = i0; S.j = j0; S.k = k0;
     }
+}
+
+__device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, StencilCache<MER_RIF_TRICUBIC> &S,
+                                                    float &f, float3 &g) {
+    const float x = (pv.x - R.xmin[0]) * R.xres[0], y = (pv.y - R.xmin[1]) * R.xres[1],
+                z = (pv.z - R.xmin[2]) * R.xres[2];
+    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    stencil_ensure(R, S, (int) fx, (int) fy, (int) fz);
     float wx0[4], wx1[4], wy0[4], wy1[4], wz0[4], wz1[4];
     bs_weights(x, fx, wx0, wx1);
     bs_weights(y, fy, wy0, wy1);
@@ -286,6 +289,17 @@ __device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, 
     g = f3(accX * R.xres[0], accY * R.xres[1], accZ * R.xres[2]);
 }
 
+__device__ __forceinline__ void stencil_ensure(const RifDev &R, StencilCache<MER_RIF_TRILINEAR_PACKED> &S, int i0, int j0, int k0) {
+    if (i0 != S.i || j0 != S.j || k0 != S.k) {
+        const int N0 = R.N[0], N1 = R.N[1];
+        const float4 *b = R.packed + ((size_t) k0 * N1 + j0) * (size_t) N0 + i0;
+        const size_t sy = N0, sz = (size_t) N0 * N1;
+        S.set(0, __ldg(b)); S.set(1, __ldg(b + 1)); S.set(2, __ldg(b + sy)); S.set(3, __ldg(b + sy + 1));
+        S.set(4, __ldg(b + sz)); S.set(5, __ldg(b + sz + 1)); S.set(6, __ldg(b + sz + sy)); S.set(7, __ldg(b + sz + sy + 1));
+        S.i = i0; S.j = j0; S.k = k0;
+    }
+}
+
 __device__ __forceinline__ void rif_trilinear_cached(const RifDev &R, float3 pv, StencilCache<MER_RIF_TRILINEAR_PACKED> &S,
                                                      float &f, float3 &g) {
     const float x = (pv.x - R.xmin[0]) * R.xres[0], y = (pv.y - R.xmin[1]) * R.xres[1],
@@ -293,18 +307,35 @@ __device__ __forceinline__ void rif_trilinear_cached(const RifDev &R, float3 pv,
     const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
     const int i0 = clampi((int) floorf(x), 0, N0 - 2), j0 = clampi((int) floorf(y), 0, N1 - 2),
               k0 = clampi((int) floorf(z), 0, N2 - 2);
-    if (i0 != S.i || j0 != S.j || k0 != S.k) {
-        const float4 *b = R.packed + ((size_t) k0 * N1 + j0) * (size_t) N0 + i0;
-        const size_t sy = N0, sz = (size_t) N0 * N1;
-        S.set(0, __ldg(b)); S.set(1, __ldg(b + 1)); S.set(2, __ldg(b + sy)); S.set(3, __ldg(b + sy + 1));
-        S.set(4, __ldg(b + sz)); S.set(5, __ldg(b + sz + 1)); S.set(6, __ldg(b + sz + sy)); S.set(7, __ldg(b + sz + sy + 1));
-        S.i = i0; S.j = j0; S.k = k0;
-    }
+    stencil_ensure(R, S, i0, j0, k0);
     const float tx = x - (float) i0, ty = y - (float) j0, tz = z - (float) k0;
     float4 r = lerp4(lerp4(lerp4(S.get(0), S.get(1), tx), lerp4(S.get(2), S.get(3), tx), ty),
                      lerp4(lerp4(S.get(4), S.get(5), tx), lerp4(S.get(6), S.get(7), tx), ty), tz);
     f = r.x;
     g = f3(r.y, r.z, r.w);
+}
+
+/* Speculative early refetch.  The dependency chain of a step is contraction_k -> p_{k+1} -> loads_{k+1} ->
+ * contraction_{k+1}, so a cell change costs a full L2/HBM round trip with nothing to overlap (ncu r01:
+ * long_scoreboard = 33 % of stall samples).  p_{k+1} is predictable to O(h^2 |grad n|) by linear
+ * extrapolation as soon as contraction_k has consumed the cached block, so the block of the PREDICTED next
+ * cell is fetched into the cache registers right there — a whole kick / containment test / loop turn /
+ * drift / weight evaluation before it is needed.  The cache is keyed by the cell index, so a wrong
+ * prediction only costs the ordinary refetch. */
+#ifndef MER_SPECULATE
+#define MER_SPECULATE 1
+#endif
+template <int MODE> __device__ __forceinline__ void rif_speculate(const RifDev &R, float3 pwNext, StencilCache<MODE> &S) {
+#if MER_SPECULATE
+    const float3 pv = rif_to_volume(R, pwNext);
+    const float x = (pv.x - R.xmin[0]) * R.xres[0], y = (pv.y - R.xmin[1]) * R.xres[1], z = (pv.z - R.xmin[2]) * R.xres[2];
+    if (MODE == MER_RIF_TRICUBIC) {
+        stencil_ensure(R, S, (int) floorf(x), (int) floorf(y), (int) floorf(z));
+    } else {
+        stencil_ensure(R, S, clampi((int) floorf(x), 0, R.N[0] - 2), clampi((int) floorf(y), 0, R.N[1] - 2),
+                       clampi((int) floorf(z), 0, R.N[2] - 2));
+    }
+#endif
 }
 
 /* Software prefetch of the NEXT cell's stencil rows.  A warp stalls for a full L2/HBM round trip whenever
@@ -416,7 +447,7 @@ __device__ __forceinline__ bool inside_shape(const MediumDev &M, float3 p) {
  * are evaluated at the same point, so (n, G) is carried across steps.  On entry (n, G) must be
  * the field at p; on exit they are the field at the new p.  `v/n` multiplies by 1/n as
  * TVector3::operator/ does. */
-template <int MODE>
+template <int MODE, bool SPECULATE = true>
 __device__ __forceinline__ void er_step_fused(const RifDev &R, StencilCache<MODE> &S, float3 &p, float3 &v, float &n,
                                               float3 &G, float h, float &opl) {
     /* The leapfrog arithmetic is rounded operation by operation exactly like the reference's float
@@ -431,7 +462,7 @@ __device__ __forceinline__ void er_step_fused(const RifDev &R, StencilCache<MODE
            __fadd_rn(p.z, __fmul_rn(__fmul_rn(h, v.z), recip)));
     opl = __fadd_rn(opl, __fmul_rn(h, n));
     rif_lookup_cached<MODE>(R, p, S, n, G);
-    rif_prefetch<MODE>(R, f3(p.x + (p.x - pOld.x), p.y + (p.y - pOld.y), p.z + (p.z - pOld.z)), S);
+    if (SPECULATE) rif_speculate<MODE>(R, f3(p.x + (p.x - pOld.x), p.y + (p.y - pOld.y), p.z + (p.z - pOld.z)), S);
     v = f3(__fadd_rn(v.x, __fmul_rn(hs, G.x)), __fadd_rn(v.y, __fmul_rn(hs, G.y)), __fadd_rn(v.z, __fmul_rn(hs, G.z)));
 }
 

@@ -30,10 +30,11 @@ struct mer_grid {
     float *d_data;
 };
 
-/* per-handle render scratch (path pool, counters, pinned read-back word), allocated on first use and
- * reused by later mer_render* calls: cudaMalloc / cudaMallocHost / cudaFree cost 0.1-1 s per call */
+/* per-DEVICE render scratch (path pool, counters, pinned read-back word), allocated on first use and reused by
+ * every later mer_render* call on that device (cudaMalloc / cudaMallocHost / cudaFree cost 0.1-1 s per call);
+ * lives until the process exits */
 struct RenderScratch {
-    std::mutex lock; /* mer_render* calls on one handle are serialised */
+    std::mutex lock; /* mer_render* calls on one device are serialised */
     size_t poolBytes = 0;
     void *pool[12] = {nullptr};
     unsigned *nOut = nullptr;
@@ -59,7 +60,6 @@ struct mer_medium {
     const mer_rif *rif;
     const mer_grid *grid;
     MediumDev dev;
-    RenderScratch *scratch;
 };
 
 namespace mer {
@@ -82,6 +82,7 @@ struct DeviceGuard {
 };
 
 int check_device(int device); /* MER_OK or MER_ERR_CUDA (no usable sm_100-class GPU) */
+RenderScratch &device_scratch(int device);
 
 } /* namespace mer */
 

@@ -559,7 +559,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) (((P.totalSamples + TPB - 1) / TPB) * TPB);
     if (pool == 0) pool = TPB;
 
-    RenderScratch &S = *m->scratch;
+    RenderScratch &S = mer::device_scratch(m->device);
     std::lock_guard<std::mutex> hold(S.lock);
     const size_t qBytes = (size_t) pool * 16;
     if (S.poolBytes < qBytes) {
