@@ -1,0 +1,116 @@
+"""The compiled C++ host side (host/): Mitsuba scene XML -> plugin objects -> C ABI.
+CPU tests use --dry-run (everything but device handles); the GPU test renders the scene with the CLI and
+compares the film with the Python mirror driving the same C ABI."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import mitsubaer_b200 as mer
+from common import BOX_MAX, BOX_MIN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "host", "mer_render")
+SCENE = os.path.join(ROOT, "scenes", "eikonal_box.xml")
+
+
+@pytest.fixture(scope="module")
+def volumes(tmp_path_factory):
+    d = tmp_path_factory.mktemp("vols")
+    res = (40, 40, 40)
+    lo, hi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, res)
+    mer.fields.write_vol(d / "rif.vol", mer.fields.radial_rif(res, lo, hi), lo, hi)
+    mer.fields.write_vol(d / "den.vol", mer.fields.sine_density((24, 24, 24), BOX_MIN, BOX_MAX), BOX_MIN, BOX_MAX)
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "host")], check=True)
+    return d, lo, hi
+
+
+def run(args, **kw):
+    return subprocess.run([EXE] + args, capture_output=True, text=True, timeout=600, **kw)
+
+
+def test_scene_xml_resolves_like_mitsuba(volumes):
+    d, lo, hi = volumes
+    out = run([SCENE, "-D", "rif=%s" % (d / "rif.vol"), "-Dspp=7", "-D", "g=0.5", "--dry-run"])
+    assert out.returncode == 0, out.stderr
+    s = json.loads(out.stdout)
+    assert s["integrator"] == "ervolpath" and (s["width"], s["height"], s["spp"]) == (128, 128, 7)  # <default> + -D
+    assert s["max_depth"] == 64 and s["rr_depth"] == 5 and s["filter"] == 1 and s["fov"] == 40
+    assert s["cam_origin"] == [0, 0, -4] and s["cam_target"] == [0, 0, -3] and s["cam_up"] == [0, 1, 0]  # <lookat>
+    assert s["env"] == [1, 1, 1] and s["has_quad"] == 1 and s["quad_radiance"] == [8, 6, 4]
+    # rectangle [-1,1]^2 -> scale .5 -> rotate 90 deg about x -> translate y 1.5 (elements apply in document order)
+    assert np.allclose(s["quad_origin"], [-0.5, 1.5, -0.5]) and np.allclose(s["quad_u"], [1, 0, 0]) and np.allclose(s["quad_v"], [0, 0, 1], atol=1e-12)
+    m = s["medium"]
+    assert np.allclose(m["sigma_s"], 3.6) and np.allclose(m["sigma_a"], 0.4) and m["strategy"] == 1 and m["hg_g"] == 0.5
+    assert m["stepsize"] == pytest.approx(0.002) and m["weight"] == -1 and m["shape_type"] == 0 and m["shape"] == [-1, -1, -1, 1, 1, 1]
+    assert m["rif_res"] == [40, 40, 40] and np.allclose(m["rif_bbox"], list(lo) + list(hi))
+
+
+def test_scene_xml_error_behaviour(volumes, tmp_path):
+    d, lo, hi = volumes
+    rif = "rif=%s" % (d / "rif.vol")
+    out = run([SCENE, "--dry-run"])
+    assert out.returncode == 1 and "undefined parameter" in out.stderr  # scenehandler.cpp:210-219
+    text = open(SCENE).read()
+
+    def variant(name, old, new):
+        assert old in text
+        p = tmp_path / name
+        p.write_text(text.replace(old, new))
+        return run([str(p), "-D", rif, "--dry-run"])
+
+    out = variant("a.xml", '<volume name="rif" type="splinevolume">', '<volume name="sdf" type="splinevolume">')
+    assert out.returncode == 1 and "No RIF specified!" in out.stderr
+    out = variant("b.xml", '<string name="strategy" value="single"/>', '<string name="strategy" value="bogus"/>')
+    assert out.returncode == 1 and "unknown sampling strategy" in out.stderr
+    out = variant("c.xml", '<float name="g" value="$g"/>', '<float name="g" value="1.5"/>')
+    assert out.returncode == 1 and "interval (-1, 1)" in out.stderr
+    out = variant("d.xml", '<integrator type="ervolpath">', '<integrator type="bdpt">')
+    assert out.returncode == 1 and "bdpt" in out.stderr
+    out = variant("e.xml", '<float name="stepsize" value="$stepsize"/>', '<float name="stepsize" value="$stepsize"/><float name="stepsiz" value="1"/>')
+    assert out.returncode == 1 and "unused property" in out.stderr
+    out = variant("f.xml", '<integer name="maxDepth" value="64"/>', '<integer name="maxDepth" value="0"/>')
+    assert out.returncode == 1 and "maxDepth" in out.stderr
+    out = variant("g.xml", "</scene>", "")
+    assert out.returncode == 1 and "XML parse error" in out.stderr
+    out = run([SCENE, "-D", "rif=/nonexistent.vol", "--dry-run"])
+    assert out.returncode == 1 and "cannot open volume file" in out.stderr
+
+
+def test_density_child_and_sphere_container(volumes, tmp_path):
+    d, lo, hi = volumes
+    text = open(SCENE).read()
+    text = text.replace('<volume name="rif" type="splinevolume">', '<volume name="density" type="gridvolume"><string name="filename" value="%s"/></volume>\n'
+                        '<float name="scale" value="8"/><spectrum name="albedo" value="0.9, 0.8, 0.7"/>\n<volume name="rif" type="splinevolume">' % (d / "den.vol"))
+    text = text.replace('<shape type="cube">', '<shape type="sphere"><point name="center" x="0.1" y="0" z="0"/><float name="radius" value="0.7"/>')
+    p = tmp_path / "s.xml"
+    p.write_text(text)
+    out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "--dry-run"])
+    assert out.returncode == 0, out.stderr
+    m = json.loads(out.stdout)["medium"]
+    assert m["has_density"] == 1 and m["density_scale"] == 8 and np.allclose(m["albedo"], [0.9, 0.8, 0.7])
+    assert m["shape_type"] == 1 and np.allclose(m["shape"][:4], [0.1, 0, 0, 0.7])
+    assert np.allclose(m["sigma_s"], 3.6 * 8)  # `scale` multiplies sigmaS / sigmaA (medium/materials.h)
+
+
+@pytest.mark.gpu
+def test_cli_render_matches_python_mirror(volumes, tmp_path):
+    d, lo, hi = volumes
+    film_path, pfm = tmp_path / "film.bin", tmp_path / "out.pfm"
+    out = run([SCENE, "-D", "rif=%s" % (d / "rif.vol"), "-D", "spp=8", "-D", "width=64", "-D", "height=48", "-D", "stepsize=0.01",
+               "-o", str(pfm), "--film", str(film_path)])
+    assert out.returncode == 0, out.stderr
+    stats = json.loads(out.stdout)
+    film = np.fromfile(film_path, np.float32).reshape(48, 64, 5)
+    rif = mer.SplineDataSource(filename=str(d / "rif.vol"))
+    med = mer.HeterogeneousRefractiveMedium(sigmaS=3.6, sigmaA=0.4, stepsize=0.01, strategy="single", shape=("box", BOX_MIN, BOX_MAX))
+    med.addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9)).configure()
+    scene = dict(width=64, height=48, sampleCount=8, seed=20201201, origin=(0, 0, -4), target=(0, 0, -3), up=(0, 1, 0), fov=40.0,
+                 rfilter="gaussian", envRadiance=1.0, quad=dict(origin=(-0.5, 1.5, -0.5), u=(1, 0, 0), v=(0, 0, 1), radiance=(8, 6, 4)))
+    ref, st = mer.EikonalVolPathIntegrator(maxDepth=64, rrDepth=5).render(scene, med)
+    assert stats["samples"] == st["samples"] == 64 * 48 * 8 and stats["ray_steps"] == st["ray_steps"]
+    assert np.allclose(film, ref, rtol=1e-5, atol=1e-5)  # same paths; only the order of the float atomics differs
+    hdr = open(pfm, "rb").read(16)
+    assert hdr.startswith(b"PF\n64 48\n-1.0\n")
