@@ -376,8 +376,8 @@ def run_gpu(args, w, wname):
         "data": "synthetic",
         "config": {"workload": wname + ": " + w["desc"], "rif_mode": args.mode, "spp_per_gpu": spp, "spp_total": spp_total,
                    "stepsize": props["stepsize"], "seed": SEED, "film": "%dx%d box filter" % (w["width"], w["height"]),
-                   "l2": "inputs larger than L2 (coeff4 %d MiB + density)" % (int(np.prod(w["rif_res"])) * 16 >> 20)
-                   if int(np.prod(w["rif_res"])) * 16 > 126e6 else "grids fit L2; film + path pool rewritten between steps",
+                   "l2": "inputs larger than L2 (coeff8 %d MiB + density)" % (int(np.prod(w["rif_res"])) * 32 >> 20)
+                   if int(np.prod(w["rif_res"])) * 32 > 126e6 else "grids fit L2; film + path pool rewritten between steps",
                    "parallelism": "sample-index sharding, NCCL film reduce" if world > 1 else "single GPU",
                    "setup_s_upload_prefilter": setup_s},
         "ray_steps_per_sec": ray_steps / (ms * 1e-3),

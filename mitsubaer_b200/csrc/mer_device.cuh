@@ -13,8 +13,10 @@
  *
  * Data layout in HBM:
  *   coeff   float  [z][y][x]   prefiltered B-spline coefficients, the reference's layout
- *   coeff4  float4 [z][y][x] = (c[x-1], c[x], c[x+1], c[x+2]) (x clamped): the four x-taps of a
- *           lookup in ONE aligned 16-byte load -> a 4x4x4 stencil is 16 independent LDG.128
+ *   coeff8  2 x float4 [z][y][x] = (c[x-1..x+2] of row y, c[x-1..x+2] of row y+1) (clamped): the x-taps of
+ *           TWO stencil rows in one aligned 32-byte sector -> a 4x4x4 stencil is 8 independent
+ *           LDG.E.256 that use every byte of the 8 sectors they touch (the scalar layout needs 64
+ *           loads from 16-32 sectors; a one-row float4 layout 16 loads from 16 half-used sectors)
  *   packed  float4 [z][y][x] = (n, dn/dx, dn/dy, dn/dz) sampled at the grid nodes (fast mode)
  */
 #pragma once
@@ -33,7 +35,7 @@ struct RifDev {
     int hasXform;
     float M[12];
     const float *coeff;
-    const float4 *coeff4;
+    const float4 *coeff8; /* two float4 per voxel */
     const float4 *packed;
 };
 
@@ -105,6 +107,13 @@ __device__ __forceinline__ void bs_weights(float x, float fx, float w0[4], float
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+/* one 32-byte sector per lane: LDG.E.256 (sm_100+), read-only path */
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 __device__ __forceinline__ float3 rif_to_volume(const RifDev &R, float3 p) {
     if (!R.hasXform) return p;
     return f3(R.M[0] * p.x + R.M[1] * p.y + R.M[2] * p.z + R.M[3], R.M[4] * p.x + R.M[5] * p.y + R.M[6] * p.z + R.M[7],
@@ -139,19 +148,15 @@ __device__ __forceinline__ void rif_tricubic(const RifDev &R, float3 pv, float &
     bs_weights(y, fy, wy0, wy1);
     bs_weights(z, fz, wz0, wz1);
     const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
-    const int ic = clampi(i0, 0, N0 - 1);
-    size_t rowOff[4], slabOff[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        rowOff[t] = (size_t) clampi(j0 - 1 + t, 0, N1 - 1) * (size_t) N0;
-        slabOff[t] = (size_t) clampi(k0 - 1 + t, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
-    }
-    const float4 *base = R.coeff4 + ic;
+    const float4 *base = R.coeff8 + 2 * (size_t) clampi(i0, 0, N0 - 1);
+    const size_t rowA = 2 * (size_t) clampi(j0 - 1, 0, N1 - 1) * (size_t) N0, rowB = 2 * (size_t) clampi(j0 + 1, 0, N1 - 1) * (size_t) N0;
     float4 c[16];
 #pragma unroll
-    for (int dz = 0; dz < 4; dz++)
-#pragma unroll
-        for (int dy = 0; dy < 4; dy++) c[dz * 4 + dy] = __ldg(base + slabOff[dz] + rowOff[dy]);
+    for (int dz = 0; dz < 4; dz++) {
+        const size_t slab = 2 * (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
+        ldg256(base + slab + rowA, c[dz * 4 + 0], c[dz * 4 + 1]);
+        ldg256(base + slab + rowB, c[dz * 4 + 2], c[dz * 4 + 3]);
+    }
 
     float accF = 0.f, accX = 0.f, accY = 0.f, accZ = 0.f;
 #pragma unroll
@@ -242,17 +247,17 @@ template <> struct StencilCache<MER_RIF_TRILINEAR_PACKED> : StencilStore<8> {
 __device__ __forceinline__ void stencil_ensure(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
     if (i0 != S.i || j0 != S.j || k0 != S.k) {
         const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
-        const float4 *base = R.coeff4 + clampi(i0, 0, N0 - 1);
-        size_t rowOff[4], slabOff[4];
+        const float4 *base = R.coeff8 + 2 * (size_t) clampi(i0, 0, N0 - 1);
+        const size_t rowA = 2 * (size_t) clampi(j0 - 1, 0, N1 - 1) * (size_t) N0, rowB = 2 * (size_t) clampi(j0 + 1, 0, N1 - 1) * (size_t) N0;
 #pragma unroll
-        for (int t = 0; t < 4; t++) {
-            rowOff[t] = (size_t) clampi(j0 - 1 + t, 0, N1 - 1) * (size_t) N0;
-            slabOff[t] = (size_t) clampi(k0 - 1 + t, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
+        for (int dz = 0; dz < 4; dz++) {
+            const size_t slab = 2 * (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
+            float4 a, b;
+            ldg256(base + slab + rowA, a, b);
+            S.set(dz * 4 + 0, a); S.set(dz * 4 + 1, b);
+            ldg256(base + slab + rowB, a, b);
+            S.set(dz * 4 + 2, a); S.set(dz * 4 + 3, b);
         }
-#pragma unroll
-        for (int dz = 0; dz < 4; dz++)
-#pragma unroll
-            for (int dy = 0; dy < 4; dy++) S.set(dz * 4 + dy, __ldg(base + slabOff[dz] + rowOff[dy]));
         S.i = i0; S.j = j0; S.k = k0;
     }
 }
@@ -352,12 +357,12 @@ __device__ __forceinline__ void rif_prefetch_tricubic(const RifDev &R, float3 pv
               k0 = (int) floorf((pvNext.z - R.xmin[2]) * R.xres[2]);
     if (i0 != ci || j0 != cj || k0 != ck) {
         const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
-        const float4 *base = R.coeff4 + clampi(i0, 0, N0 - 1);
+        const float4 *base = R.coeff8 + 2 * (size_t) clampi(i0, 0, N0 - 1);
 #pragma unroll
         for (int dz = 0; dz < 4; dz++) {
-            const size_t slab = (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
-#pragma unroll
-            for (int dy = 0; dy < 4; dy++) prefetch_l1(base + slab + (size_t) clampi(j0 - 1 + dy, 0, N1 - 1) * (size_t) N0);
+            const size_t slab = 2 * (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
+            prefetch_l1(base + slab + 2 * (size_t) clampi(j0 - 1, 0, N1 - 1) * (size_t) N0);
+            prefetch_l1(base + slab + 2 * (size_t) clampi(j0 + 1, 0, N1 - 1) * (size_t) N0);
         }
     }
 }

@@ -19,7 +19,7 @@ struct mer_rif {
     mer_volume_desc desc;
     RifDev dev;
     float *d_coeff;
-    float4 *d_coeff4;
+    float4 *d_coeff8;
     float4 *d_packed;
 };
 

@@ -82,12 +82,15 @@ k_prefilter(const float *in, float *out, int N0, int N1, int N2, int pass) {
     }
 }
 
-/* coeff [z][y][x] -> coeff4 [z][y][x] = (c[x-1], c[x], c[x+1], c[x+2]), x clamped */
-__global__ void k_expand_coeff4(const float *__restrict__ coeff, float4 *__restrict__ coeff4, int N0, size_t total) {
+/* coeff [z][y][x] -> coeff8 [z][y][x] = { (c[x-1], c[x], c[x+1], c[x+2]) of row y, the same of row y+1 }, clamped */
+__global__ void k_expand_coeff8(const float *__restrict__ coeff, float4 *__restrict__ coeff8, int N0, int N1, size_t total) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
-        const int x = (int) (i % (size_t) N0);
+        const int x = (int) (i % (size_t) N0), y = (int) ((i / (size_t) N0) % (size_t) N1);
         const float *row = coeff + (i - x);
-        coeff4[i] = make_float4(row[max(x - 1, 0)], row[x], row[min(x + 1, N0 - 1)], row[min(x + 2, N0 - 1)]);
+        const float *rowUp = y + 1 < N1 ? row + N0 : row;
+        const int xm = max(x - 1, 0), x1 = min(x + 1, N0 - 1), x2 = min(x + 2, N0 - 1);
+        coeff8[2 * i] = make_float4(row[xm], row[x], row[x1], row[x2]);
+        coeff8[2 * i + 1] = make_float4(rowUp[xm], rowUp[x], rowUp[x1], rowUp[x2]);
     }
 }
 
@@ -160,7 +163,7 @@ void fill_rif_dev(mer_rif *r) {
     D.hasXform = d.has_transform != 0;
     for (int i = 0; i < 12; i++) D.M[i] = D.hasXform ? d.world_to_volume[i] : ((i == 0 || i == 5 || i == 10) ? 1.f : 0.f);
     D.coeff = r->d_coeff;
-    D.coeff4 = r->d_coeff4;
+    D.coeff8 = r->d_coeff8;
     D.packed = r->d_packed;
 }
 
@@ -173,18 +176,18 @@ int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N2, T), T, 0, s, data_dev, r->d_coeff, N0, N1, N2, (int) PASS_Y);
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N1 * N2, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_X);
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N1, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_Z);
-    MER_CUDA(cudaMalloc(&r->d_coeff4, total * sizeof(float4)));
+    MER_CUDA(cudaMalloc(&r->d_coeff8, 2 * total * sizeof(float4)));
     const unsigned G = (unsigned) std::min<size_t>(mer_blocks(total, 256), 148u * 16u);
-    MER_LAUNCH(k_expand_coeff4, G, 256, 0, s, r->d_coeff, r->d_coeff4, N0, total);
+    MER_LAUNCH(k_expand_coeff8, G, 256, 0, s, r->d_coeff, r->d_coeff8, N0, N1, total);
     fill_rif_dev(r);
     if (r->mode == MER_RIF_TRILINEAR_PACKED) {
         MER_CUDA(cudaMalloc(&r->d_packed, total * sizeof(float4)));
         fill_rif_dev(r);
         MER_LAUNCH(k_build_packed, G, 256, 0, s, r->dev, r->d_packed, total);
         MER_CUDA(cudaStreamSynchronize(s));
-        /* the 4x-expanded cubic coefficients are only needed to build the packed grid */
-        cudaFree(r->d_coeff4);
-        r->d_coeff4 = nullptr;
+        /* the 8x-expanded cubic coefficients are only needed to build the packed grid */
+        cudaFree(r->d_coeff8);
+        r->d_coeff8 = nullptr;
         fill_rif_dev(r);
     }
     MER_CUDA(cudaStreamSynchronize(s));
@@ -302,7 +305,7 @@ void mer_rif_destroy(mer_rif *r) {
     if (!r) return;
     mer::DeviceGuard guard(r->device);
     cudaFree(r->d_coeff);
-    cudaFree(r->d_coeff4);
+    cudaFree(r->d_coeff8);
     cudaFree(r->d_packed);
     delete r;
 }
