@@ -549,7 +549,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     }
     P.hasQuad = r->has_quad;
     P.stepsPerPass = r->steps_per_pass > 0 ? r->steps_per_pass : 2048;
-    P.maxWait = 10;
+    P.maxWait = 12;
     if (const char *e = getenv("MER_MAX_WAIT")) P.maxWait = atoi(e); /* tuning knob */
     P.film = film_dev;
 

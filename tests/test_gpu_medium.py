@@ -88,6 +88,56 @@ def test_trace_parity(oracle32, oracle64, kind, h):
     assert got["nsteps"].max() <= 1003
 
 
+def test_long_trajectory_drift_report(oracle32, oracle64):
+    """drift against the FLOAT=double reference up to 1e5 steps (h = 2.5e-6 * extent).  Single precision cannot hold 1e-5 over 1e5 steps against double (position round-off
+    alone random-walks to ~1e-5); the assertion is that the GPU drifts no more than the reference's own float
+    build does, and that it stays within 1e-5 of THAT build on the rays it computes stably."""
+    h = 5e-6
+    props = medium_props(stepsize=h)
+    rif, med, orif, omed = build("radial", 48, oracle32, props)
+    orif64 = oracle64.rif_create(volume_desc(rif.getResolution(), *rif.getAABB()), make_field("radial", 48)[0])
+    omed64 = oracle64.medium_create(oracle_medium_desc(props), orif64)
+    n = 384
+    p0 = random_points_in_box(n, 101, margin=0.55)
+    v0 = random_directions(n, 102) * rif.value(p0)[:, None]
+    dist = np.linspace(0.1, 0.5, n).astype(np.float32)  # 2e4 .. 1e5 steps, all rays stay inside the box
+    got, ref, ref64 = med.trace(p0, v0, dist), oracle32.trace(omed, p0, v0, dist), oracle64.trace(omed64, p0, v0, dist)
+    # (the double build may split dist into one step more or less; the remainder step makes up for it)
+    same = got["success"] & ref["success"] & ref64["success"] & (got["nsteps"] == ref["nsteps"])
+    assert same.mean() > 0.97 and got["nsteps"].max() > 90000
+    e_gpu64 = np.abs(got["p"] - ref64["p"]).max(axis=1)[same]
+    e_cpu64 = np.abs(ref["p"] - ref64["p"]).max(axis=1)[same]
+    e_gpu32 = np.abs(got["p"] - ref["p"]).max(axis=1)[same]
+    print("1e5-step drift |p|: gpu-vs-double median %.2e max %.2e | reference float-vs-double median %.2e max %.2e | "
+          "gpu-vs-float median %.2e p95 %.2e" % (np.median(e_gpu64), e_gpu64.max(), np.median(e_cpu64), e_cpu64.max(),
+                                                  np.median(e_gpu32), np.percentile(e_gpu32, 95)))
+    assert np.median(e_gpu64) <= 1.5 * np.median(e_cpu64) + 1e-7
+    assert e_gpu64.max() <= 2.0 * e_cpu64.max() + 1e-6
+    assert np.median(e_gpu32) <= 1e-5
+
+
+def test_non_cubic_grid_and_transform_trace(oracle32):
+    """C1-shaped anisotropic grid (226 x 226 x 51 scaled down) under a rotated / translated toWorld"""
+    res = (57, 45, 23)
+    data, lo, hi = make_field("smooth", res)
+    th = 0.3
+    to_world = np.array([[np.cos(th), 0, np.sin(th), 0.05], [0, 1, 0, -0.02], [-np.sin(th), 0, np.cos(th), 0.03], [0, 0, 0, 1]])
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi, toWorld=to_world)
+    props = medium_props(stepsize=5e-3, shape=("sphere", (0.05, -0.02, 0.03), 0.6))
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).configure()
+    orif = oracle32.rif_create(volume_desc(res, lo, hi, np.linalg.inv(to_world)[:3, :]), data)
+    omed = oracle32.medium_create(oracle_medium_desc(props), orif)
+    n = 6000
+    p0 = (random_points_in_box(n, 111) * 0.3 + np.array([0.05, -0.02, 0.03], np.float32)).astype(np.float32)
+    v0 = random_directions(n, 112) * rif.value(p0)[:, None]
+    dist = (np.random.default_rng(113).random(n) * 1.0).astype(np.float32)
+    got, ref = med.trace(p0, v0, dist), oracle32.trace(omed, p0, v0, dist)
+    same = (got["success"] == ref["success"]) & (got["nsteps"] == ref["nsteps"])
+    assert same.mean() > 0.998
+    e = np.abs(got["p"] - ref["p"]).max(axis=1)[same]
+    assert np.mean(e <= 1e-5) > 0.998 and e.max() <= 1e-4 and np.abs(got["v"] - ref["v"]).max(axis=1)[same].max() <= 2e-4
+
+
 def test_trace_till_boundary_parity(oracle32):
     props = medium_props(stepsize=5e-3)
     rif, med, orif, omed = build("radial", 40, oracle32, props)
