@@ -94,6 +94,17 @@ void mer_grid_destroy(mer_grid *grid);
 /* GridDataSource::lookupFloat (gridvolume.cpp:337-363) */
 int mer_grid_lookup_batch(const mer_grid *grid, size_t n, const float *p, float *value_out);
 
+/* HeterogeneousMedium on STRAIGHT rays, Woodcock tracking (src/medium/heterogeneous.cpp:239-242 majorant =
+ * scale * 1, :613-658 sampleDistance, :546-587 evalTransmittance with 2 samples; AABB clipping
+ * include/mitsuba/core/aabb.h:308-338).  The Sampler of ray i is the Philox4x32-10 stream (seed, i).
+ * This is the arithmetic the curved-ray composition inside mer_render is built from. */
+int mer_grid_sample_distance_batch(const mer_grid *grid, float scale, size_t n, const float *ray_o, const float *ray_d,
+                                   const float *ray_mint, const float *ray_maxt, uint64_t seed, uint8_t *success_out,
+                                   float *t_out, float *density_at_t_out);
+int mer_grid_eval_transmittance_batch(const mer_grid *grid, float scale, size_t n, const float *ray_o,
+                                      const float *ray_d, const float *ray_mint, const float *ray_maxt, uint64_t seed,
+                                      float *transmittance_out);
+
 /* .vol v3 I/O (mfiles/writeGridToVol.m:1-36, splinevolume.cpp:204-273). */
 int mer_vol_read_header(const char *path, mer_volume_desc *out, int32_t *encoding, int32_t *channels);
 int mer_vol_read_data(const char *path, float *data_out, size_t n_floats);
@@ -150,6 +161,12 @@ typedef struct mer_medium mer_medium; /* <medium type="heterogeneousrefractive">
 int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer_grid *density_or_null,
                       mer_medium **out);
 void mer_medium_destroy(mer_medium *medium);
+/* addChild("sdf") + `aggressivetracing` (heterogeneousrefractive.cpp:230, 1177-1193): with aggressive != 0,
+ * mer_medium_sample_distance_batch sphere-traces the signed-distance spline before the tested trace
+ * (:476-493, aggressive_trace :697-704).  The sdf volume must have the RIF's AABB (:372-377).  mer_render
+ * keeps using tested tracing only (containment there is the analytic box / sphere predicate, R5) and
+ * returns MER_ERR_UNSUPPORTED for an aggressive medium. */
+int mer_medium_set_sdf(mer_medium *medium, const mer_rif *sdf, int aggressive);
 /* resolved parameters (after the -1 defaults are applied) */
 int mer_medium_resolved(const mer_medium *medium, mer_medium_desc *out, float *sampling_density_out);
 

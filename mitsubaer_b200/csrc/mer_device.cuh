@@ -42,11 +42,15 @@ struct RifDev {
 struct GridDev {
     int N[3];
     float G[12]; /* world -> grid, row-major 3x4 (gridvolume.cpp:190-195) */
+    float aabbLo[3], aabbHi[3]; /* world AABB of the data box (gridvolume.cpp:199-201) */
     const float *data;
 };
 
 struct MediumDev {
     RifDev rif;
+    RifDev sdf; /* <volume name="sdf"> (aggressive tracing only) */
+    int hasSdf, aggressive;
+    float maxSdfError;
     GridDev grid;
     int hasGrid;
     float sigmaA[3], sigmaS[3], sigmaT[3];

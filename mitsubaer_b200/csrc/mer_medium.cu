@@ -66,6 +66,21 @@ __device__ __forceinline__ void trace_till_boundary_dev(const MediumDev &M, Sten
     }
 }
 
+/* ------------------------------------------------------------------ a10: aggressive_trace() (:697-704) */
+template <int MODE>
+__device__ __forceinline__ void aggressive_trace_dev(const MediumDev &M, StencilCache<MODE> &S, float3 &p, float3 &v, float &n,
+                                                     float3 &G, float dist, float &opl, int &count) {
+    int steps;
+    float rem;
+    trace_split(dist, M.h, steps, rem);
+    for (int i = 0; i < steps; i++) {
+        er_step_fused<MODE, false>(M.rif, S, p, v, n, G, M.h, opl);
+        count++;
+    }
+    er_step_fused<MODE, false>(M.rif, S, p, v, n, G, rem, opl);
+    count++;
+}
+
 /* Batch stepper behind mer_medium_trace_* (and the C4 step-size sweep).  Rays of a batch need very
  * different step counts (they leave the shape at random times), so a thread-per-ray loop leaves most
  * lanes idle waiting for the warp's longest ray (ncu r01e: 13.6 of 32 lanes active).  Instead every lane
@@ -172,7 +187,7 @@ k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float
         bool success = true;
         float distSurf = 0.0f, opl = 0.0f, refRatioSq = 0.0f, T[3] = {0.f, 0.f, 0.f}, ps = 1.0f, pf = 1.0f, t = 0.0f;
         int count = 0;
-        if (!rif_inside_limits(M.rif, p)) { /* :461-466 */
+        if (!rif_inside_limits(M.hasSdf ? M.sdf : M.rif, p)) { /* :461-466 */
             success = false;
         } else {
             float n;
@@ -184,7 +199,24 @@ k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float
             refRatioSq = (float) (1.0 / (double) (refStart * refStart));
             v = f3(v.x * refStart, v.y * refStart, v.z * refStart);
             if (isfinite(sampledDistance)) {
-                success = trace_dev<MODE>(M, S, p, v, n, G, sampledDistance, distSurf, opl, count);
+                if (!M.aggressive) {
+                    success = trace_dev<MODE>(M, S, p, v, n, G, sampledDistance, distSurf, opl, count);
+                } else { /* :476-493 */
+                    float distLeft = sampledDistance, distTraced = 0.0f;
+                    while (distLeft > MER_EPSILON) {
+                        float sdfv;
+                        float3 gUnused;
+                        rif_tricubic(M.sdf, rif_to_volume(M.sdf, p), sdfv, gUnused); /* m_SDF->value(p) */
+                        sdfv = __fsub_rn(-sdfv, M.maxSdfError);
+                        if (sdfv < MER_EPSILON) break;
+                        const float traceDist = fminf(sdfv, distLeft);
+                        aggressive_trace_dev<MODE>(M, S, p, v, n, G, traceDist, opl, count);
+                        distLeft = __fsub_rn(distLeft, traceDist);
+                        distTraced = __fadd_rn(distTraced, traceDist);
+                    }
+                    success = trace_dev<MODE>(M, S, p, v, n, G, distLeft, distSurf, opl, count);
+                    distSurf = __fadd_rn(distSurf, distTraced);
+                }
             } else {
                 trace_till_boundary_dev<MODE>(M, S, p, v, n, G, distSurf, opl, count);
                 success = false;
@@ -371,6 +403,27 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
 void mer_medium_destroy(mer_medium *m) {
     if (!m) return;
     delete m;
+}
+
+int mer_medium_set_sdf(mer_medium *m, const mer_rif *sdf, int aggressive) {
+    MER_REQUIRE(m, "null handle");
+    if (!sdf) {
+        MER_REQUIRE(!aggressive, "No SDF specified!"); /* heterogeneousrefractive.cpp:371-372 */
+        m->dev.hasSdf = m->dev.aggressive = 0;
+        return MER_OK;
+    }
+    MER_REQUIRE(sdf->device == m->device, "rif and sdf live on different devices");
+    MER_REQUIRE(sdf->mode == MER_RIF_TRICUBIC, "the sdf volume must be a tricubic splinevolume");
+    for (int i = 0; i < 3; i++) /* :374-377 */
+        MER_REQUIRE(sdf->desc.bbox_min[i] == m->rif->desc.bbox_min[i] && sdf->desc.bbox_max[i] == m->rif->desc.bbox_max[i],
+                    "The bounding boxes of rif and winding number do not match");
+    m->dev.sdf = sdf->dev;
+    m->dev.hasSdf = 1;
+    m->dev.aggressive = aggressive ? 1 : 0;
+    /* maxSDFError, splinevolume.cpp:282: sqrt(sum stride^2), stride = FLOAT(1/xres) */
+    float s0 = (float) (1.0 / (double) sdf->dev.xres[0]), s1 = (float) (1.0 / (double) sdf->dev.xres[1]), s2 = (float) (1.0 / (double) sdf->dev.xres[2]);
+    m->dev.maxSdfError = std::sqrt(s0 * s0 + s1 * s1 + s2 * s2);
+    return MER_OK;
 }
 
 int mer_medium_resolved(const mer_medium *m, mer_medium_desc *out, float *sampling_density_out) {

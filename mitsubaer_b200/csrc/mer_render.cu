@@ -529,6 +529,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     MER_REQUIRE(r->width > 0 && r->height > 0 && r->spp_total > 0, "film size and sample count must be positive");
     MER_REQUIRE(r->sample_stride >= 1 && r->sample_begin >= 0, "bad sample sharding");
     MER_REQUIRE(r->filter == MER_FILTER_BOX || r->filter == MER_FILTER_GAUSSIAN, "unknown reconstruction filter");
+    if (m->dev.aggressive)
+        return mer::fail(MER_ERR_UNSUPPORTED, "aggressivetracing is only available in mer_medium_sample_distance_batch");
     mer::DeviceGuard guard(m->device);
     cudaStream_t stream = (cudaStream_t) stream_;
 

@@ -132,6 +132,76 @@ __global__ void k_grid_lookup(GridDev D, size_t n, const float *__restrict__ p, 
         out[i] = grid_lookup(D, f3(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
 }
 
+/* ------------------------------------------------------------------ a19: straight-ray Woodcock tracking
+ * heterogeneous.cpp:613-658 / :546-587; every operation individually rounded like the reference's float code. */
+__device__ __forceinline__ bool aabb_ray_intersect(const GridDev &D, float3 o, float3 d, float &nearT, float &farT) {
+    nearT = -INFINITY;
+    farT = INFINITY;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (dd[i] == 0.0f) {
+            if (oo[i] < D.aabbLo[i] || oo[i] > D.aabbHi[i]) return false;
+        } else {
+            const float rcp = __fdiv_rn(1.0f, dd[i]);
+            float t1 = __fmul_rn(__fsub_rn(D.aabbLo[i], oo[i]), rcp), t2 = __fmul_rn(__fsub_rn(D.aabbHi[i], oo[i]), rcp);
+            if (t1 > t2) { float t = t1; t1 = t2; t2 = t; }
+            nearT = fmaxf(t1, nearT);
+            farT = fminf(t2, farT);
+            if (!(nearT <= farT)) return false;
+        }
+    }
+    return true;
+}
+__device__ __forceinline__ float3 ray_at(float3 o, float3 d, float t) { /* Ray::operator(): o + t * d */
+    return f3(__fadd_rn(o.x, __fmul_rn(t, d.x)), __fadd_rn(o.y, __fmul_rn(t, d.y)), __fadd_rn(o.z, __fmul_rn(t, d.z)));
+}
+
+__global__ void k_grid_woodcock(GridDev D, float scale, size_t n, const float *__restrict__ RO, const float *__restrict__ RD,
+                                const float *__restrict__ rmint, const float *__restrict__ rmaxt, unsigned long long seed,
+                                int evalTransmittance, uint8_t *__restrict__ success, float *__restrict__ tOut,
+                                float *__restrict__ densOut, float *__restrict__ trOut) {
+    const float invMax = 1.0f / (scale * 1.0f); /* heterogeneous.cpp:239-242 */
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        const float3 o = f3(RO[3 * i], RO[3 * i + 1], RO[3 * i + 2]), d = f3(RD[3 * i], RD[3 * i + 1], RD[3 * i + 2]);
+        PathRng rng;
+        rng.init(seed, (unsigned long long) i, 0u);
+        float mint, maxt;
+        const bool hit = aabb_ray_intersect(D, o, d, mint, maxt);
+        mint = fmaxf(mint, rmint[i]);
+        maxt = fminf(maxt, rmaxt[i]);
+        if (!evalTransmittance) {
+            bool ok = false;
+            float t = mint, dens = 0.0f, tHit = 0.0f;
+            while (hit) {
+                t = __fsub_rn(t, __fmul_rn(fastlog_dev(1.0f - rng.next()), invMax));
+                if (t >= maxt) break;
+                dens = __fmul_rn(grid_lookup(D, ray_at(o, d, t)), scale);
+                if (__fmul_rn(dens, invMax) > rng.next()) { ok = true; tHit = t; break; }
+            }
+            success[i] = ok ? 1 : 0;
+            tOut[i] = tHit;
+            densOut[i] = hit ? dens : 0.0f;
+        } else {
+            float result = 0.0f;
+            if (!hit) {
+                result = 2.0f;
+            } else {
+                for (int s = 0; s < 2; s++) {
+                    float t = mint;
+                    while (true) {
+                        t = __fsub_rn(t, __fmul_rn(fastlog_dev(1.0f - rng.next()), invMax));
+                        if (t >= maxt) { result += 1.0f; break; }
+                        const float dens = __fmul_rn(grid_lookup(D, ray_at(o, d, t)), scale);
+                        if (__fmul_rn(dens, invMax) > rng.next()) break;
+                    }
+                }
+            }
+            trOut[i] = result / 2.0f;
+        }
+    }
+}
+
 /* ===================================================================== host side */
 namespace {
 
@@ -409,6 +479,29 @@ int mer_grid_create_device(int device, const mer_volume_desc *desc, const float 
         }
     }
     g->dev.data = g->d_data;
+    /* m_aabb: the data box's 8 corners through volumeToWorld (gridvolume.cpp:199-201) */
+    if (!desc->has_transform) {
+        for (int i = 0; i < 3; i++) { g->dev.aabbLo[i] = desc->bbox_min[i]; g->dev.aabbHi[i] = desc->bbox_max[i]; }
+    } else {
+        const float *w = desc->world_to_volume;
+        /* inverse of the affine 3x4: R^-1 by cofactors, t' = -R^-1 t */
+        double R[9] = {w[0], w[1], w[2], w[4], w[5], w[6], w[8], w[9], w[10]}, t[3] = {w[3], w[7], w[11]};
+        double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+        if (det == 0) { mer_grid_destroy(g); return mer::fail(MER_ERR_INVALID, "toWorld is singular"); }
+        double I[9] = {(R[4] * R[8] - R[5] * R[7]) / det, (R[2] * R[7] - R[1] * R[8]) / det, (R[1] * R[5] - R[2] * R[4]) / det,
+                       (R[5] * R[6] - R[3] * R[8]) / det, (R[0] * R[8] - R[2] * R[6]) / det, (R[2] * R[3] - R[0] * R[5]) / det,
+                       (R[3] * R[7] - R[4] * R[6]) / det, (R[1] * R[6] - R[0] * R[7]) / det, (R[0] * R[4] - R[1] * R[3]) / det};
+        for (int i = 0; i < 3; i++) { g->dev.aabbLo[i] = INFINITY; g->dev.aabbHi[i] = -INFINITY; }
+        for (int c = 0; c < 8; c++) {
+            double q[3] = {(c & 1 ? desc->bbox_max[0] : desc->bbox_min[0]) - t[0], (c & 2 ? desc->bbox_max[1] : desc->bbox_min[1]) - t[1],
+                           (c & 4 ? desc->bbox_max[2] : desc->bbox_min[2]) - t[2]};
+            for (int i = 0; i < 3; i++) {
+                float pw = (float) (I[3 * i] * q[0] + I[3 * i + 1] * q[1] + I[3 * i + 2] * q[2]);
+                g->dev.aabbLo[i] = std::min(g->dev.aabbLo[i], pw);
+                g->dev.aabbHi[i] = std::max(g->dev.aabbHi[i], pw);
+            }
+        }
+    }
     *out = g;
     return MER_OK;
 }
@@ -461,6 +554,39 @@ int mer_grid_lookup_batch(const mer_grid *g, size_t n, const float *p, float *va
     MER_CUDA(cudaMemcpy(value_out, dout, n * sizeof(float), cudaMemcpyDeviceToHost));
     cudaFree(dp); cudaFree(dout);
     return MER_OK;
+}
+
+static int grid_woodcock(const mer_grid *g, float scale, size_t n, const float *ro, const float *rd, const float *mint,
+                         const float *maxt, uint64_t seed, int evalT, uint8_t *ok, float *t, float *dens, float *tr) {
+    MER_REQUIRE(g && (n == 0 || (ro && rd && mint && maxt)), "null argument");
+    MER_REQUIRE(scale > 0.0f, "scale must be positive");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(g->device);
+    float *dro = nullptr, *drd = nullptr, *dmi = nullptr, *dma = nullptr, *dt = nullptr, *dd = nullptr, *dtr = nullptr;
+    uint8_t *dok = nullptr;
+    MER_CUDA(cudaMalloc(&dro, n * 12)); MER_CUDA(cudaMalloc(&drd, n * 12)); MER_CUDA(cudaMalloc(&dmi, n * 4)); MER_CUDA(cudaMalloc(&dma, n * 4));
+    MER_CUDA(cudaMalloc(&dt, n * 4)); MER_CUDA(cudaMalloc(&dd, n * 4)); MER_CUDA(cudaMalloc(&dtr, n * 4)); MER_CUDA(cudaMalloc(&dok, n));
+    MER_CUDA(cudaMemcpy(dro, ro, n * 12, cudaMemcpyHostToDevice)); MER_CUDA(cudaMemcpy(drd, rd, n * 12, cudaMemcpyHostToDevice));
+    MER_CUDA(cudaMemcpy(dmi, mint, n * 4, cudaMemcpyHostToDevice)); MER_CUDA(cudaMemcpy(dma, maxt, n * 4, cudaMemcpyHostToDevice));
+    MER_LAUNCH(k_grid_woodcock, (unsigned) std::min<size_t>(mer_blocks(n, 128), 148u * 16u), 128, 0, 0, g->dev, scale, n, dro, drd, dmi, dma,
+               (unsigned long long) seed, evalT, dok, dt, dd, dtr);
+    if (ok) MER_CUDA(cudaMemcpy(ok, dok, n, cudaMemcpyDeviceToHost));
+    if (t) MER_CUDA(cudaMemcpy(t, dt, n * 4, cudaMemcpyDeviceToHost));
+    if (dens) MER_CUDA(cudaMemcpy(dens, dd, n * 4, cudaMemcpyDeviceToHost));
+    if (tr) MER_CUDA(cudaMemcpy(tr, dtr, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dro); cudaFree(drd); cudaFree(dmi); cudaFree(dma); cudaFree(dt); cudaFree(dd); cudaFree(dtr); cudaFree(dok);
+    return MER_OK;
+}
+
+int mer_grid_sample_distance_batch(const mer_grid *g, float scale, size_t n, const float *ray_o, const float *ray_d,
+                                   const float *ray_mint, const float *ray_maxt, uint64_t seed, uint8_t *success_out, float *t_out,
+                                   float *density_at_t_out) {
+    return grid_woodcock(g, scale, n, ray_o, ray_d, ray_mint, ray_maxt, seed, 0, success_out, t_out, density_at_t_out, nullptr);
+}
+
+int mer_grid_eval_transmittance_batch(const mer_grid *g, float scale, size_t n, const float *ray_o, const float *ray_d,
+                                      const float *ray_mint, const float *ray_maxt, uint64_t seed, float *transmittance_out) {
+    return grid_woodcock(g, scale, n, ray_o, ray_d, ray_mint, ray_maxt, seed, 1, nullptr, nullptr, nullptr, transmittance_out);
 }
 
 /* ------------------------------------------------------------------ .vol I/O (host only) */

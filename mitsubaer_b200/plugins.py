@@ -195,6 +195,28 @@ class GridDataSource(_Volume):
     def supportsFloatLookups(self):
         return True
 
+    # ---- HeterogeneousMedium (straight rays, Woodcock tracking) on this density grid: heterogeneous.cpp:546-658
+    def _rays(self, ray_o, ray_d, mint, maxt):
+        ro, rd = _f32(ray_o, (-1, 3)), _f32(ray_d, (-1, 3))
+        n = ro.shape[0]
+        mint = np.ascontiguousarray(np.broadcast_to(np.asarray(mint, np.float32), (n,)))
+        maxt = np.ascontiguousarray(np.broadcast_to(np.asarray(maxt, np.float32), (n,)))
+        return ro, rd, mint, maxt, n
+
+    def sampleDistance(self, ray_o, ray_d, mint, maxt, scale, seed):
+        """-> (success, t, densityAtT); the Sampler of ray i is the Philox stream (seed, i)"""
+        ro, rd, mint, maxt, n = self._rays(ray_o, ray_d, mint, maxt)
+        ok, t, dens = np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        check(lib.mer_grid_sample_distance_batch(self.handle, float(scale), n, _fp(ro), _fp(rd), _fp(mint), _fp(maxt), int(seed),
+                                                 ok.ctypes.data_as(C.POINTER(C.c_uint8)), _fp(t), _fp(dens)))
+        return ok.astype(bool), t, dens
+
+    def evalTransmittance(self, ray_o, ray_d, mint, maxt, scale, seed):
+        ro, rd, mint, maxt, n = self._rays(ray_o, ray_d, mint, maxt)
+        out = np.zeros(n, np.float32)
+        check(lib.mer_grid_eval_transmittance_batch(self.handle, float(scale), n, _fp(ro), _fp(rd), _fp(mint), _fp(maxt), int(seed), _fp(out)))
+        return out
+
 
 class HGPhaseFunction:
     """props: `g` (default 0.8, must lie in (-1, 1): hg.cpp:46-53)"""
@@ -243,6 +265,7 @@ class HeterogeneousRefractiveMedium:
         props = dict(props or {}, **kw)
         self.props = props
         self.rif = None
+        self.sdf = None
         self.density = None
         self.phase = None
         self.handle = None
@@ -259,6 +282,8 @@ class HeterogeneousRefractiveMedium:
             self.rif = child
         elif isinstance(child, GridDataSource) and name == "density":
             self.density = child
+        elif isinstance(child, SplineDataSource) and name == "sdf":
+            self.sdf = child
         else:
             raise _abi.MerError(_abi.MER_ERR_INVALID, 'Medium: Invalid child node! ("%s")' % type(child).__name__)
         return self
@@ -302,6 +327,9 @@ class HeterogeneousRefractiveMedium:
         check(lib.mer_medium_create(C.byref(d), self.rif.handle, self.density.handle if self.density else None,
                                     C.byref(h)))
         self.handle = h
+        aggressive = bool(p.get("aggressivetracing", False))
+        if self.sdf is not None or aggressive:
+            check(lib.mer_medium_set_sdf(self.handle, self.sdf.handle if self.sdf is not None else None, 1 if aggressive else 0))
         self.desc = _abi.MediumDesc()
         sd = C.c_float()
         check(lib.mer_medium_resolved(self.handle, C.byref(self.desc), C.byref(sd)))

@@ -357,6 +357,8 @@ inline void hg_sample(float g, const float wi[3], float u1, float u2, float wo[3
  * ------------------------------------------------------------------------------------------ */
 template <typename F> struct Medium {
     const SplineVolume<F> *rif;
+    const SplineVolume<F> *sdf = nullptr; /* <volume name="sdf">, used by aggressive tracing (a10) */
+    bool aggressive = false;              /* `aggressivetracing` */
     const GridVolume *density; /* optional (new composition, R2) */
     mer_medium_desc d;
     float sigmaT[3];
@@ -445,6 +447,21 @@ template <typename F> struct Medium {
         return true;
     }
 
+    /* aggressive_trace, :697-704: no containment tests */
+    void aggressive_trace(F *p, F *v, F sampledDistance, F &opl, long &count) const {
+        F distance = sampledDistance;
+        int steps = (int) (distance / h);
+        distance = distance - steps * h;
+        for (int i = 0; i < steps; i++) er_step(p, v, h, opl, count);
+        er_step(p, v, distance, opl, count);
+    }
+
+    /* maxSDFError, src/volume/splinevolume.cpp:282 */
+    float maxSDFError() const {
+        F a = (F) (1.0 / sdf->spline.xres[0]), b = (F) (1.0 / sdf->spline.xres[1]), c = (F) (1.0 / sdf->spline.xres[2]);
+        return (float) std::sqrt(a * a + b * b + c * c);
+    }
+
     /* traceTillBoundary, :742-776 */
     void traceTillBoundary(F *p, F *v, F &distSurf, F &opl, long &count) const {
         distSurf = 0;
@@ -486,7 +503,7 @@ template <typename F> struct Medium {
         bool success = true;
         F distSurf = 0, opl = 0;
         F tp[3] = {(F) ro[0], (F) ro[1], (F) ro[2]}, tv[3] = {(F) rd[0], (F) rd[1], (F) rd[2]};
-        if (!rif->insideVolumeLimits(tp)) { /* :461-466 */
+        if (!(sdf ? sdf : rif)->insideVolumeLimits(tp)) { /* :461-466 (the reference asks m_SDF, whose AABB equals the RIF's) */
             for (int i = 0; i < 3; i++) rec.transmittance[i] = 0;
             rec.pdfSuccess = rec.pdfFailure = 1.0f;
             rec.success = false;
@@ -498,7 +515,22 @@ template <typename F> struct Medium {
         F refRatioSq = (F) (1.0 / (refStart * refStart));
         for (int i = 0; i < 3; i++) tv[i] *= refStart;
         if (std::isfinite(sampledDistance)) {
-            success = trace(tp, tv, sampledDistance, distSurf, opl, rec.nsteps);
+            if (!aggressive) {
+                success = trace(tp, tv, sampledDistance, distSurf, opl, rec.nsteps);
+            } else { /* :476-493: sphere-trace the signed-distance field, then finish with a tested trace */
+                float dist_left = (float) sampledDistance, dist_traced = 0; /* `Float` in the reference */
+                while (dist_left > kEpsilon) {
+                    float sdfv = (float) -sdf->value(tp);
+                    sdfv -= maxSDFError();
+                    if (sdfv < kEpsilon) break;
+                    float traceDist = std::min(sdfv, dist_left);
+                    aggressive_trace(tp, tv, (F) traceDist, opl, rec.nsteps);
+                    dist_left -= traceDist;
+                    dist_traced += traceDist;
+                }
+                success = trace(tp, tv, (F) dist_left, distSurf, opl, rec.nsteps);
+                distSurf += dist_traced;
+            }
         } else {
             traceTillBoundary(tp, tv, distSurf, opl, rec.nsteps);
             success = false;
@@ -578,6 +610,70 @@ struct PhiloxStream {
         uint32_t u = out[4 - have];
         have--;
         return (float) (u >> 8) * (1.0f / 16777216.0f);
+    }
+};
+
+/* ------------------------------------------------------------------------------------------
+ * a19  HeterogeneousMedium, straight rays, Woodcock tracking — src/medium/heterogeneous.cpp:239-242
+ * (majorant), :546-587 (evalTransmittance, 2 samples), :613-658 (sampleDistance); AABB::rayIntersect
+ * include/mitsuba/core/aabb.h:308-338.  The Sampler is a Philox stream per ray.
+ * ------------------------------------------------------------------------------------------ */
+inline bool aabbRayIntersect(const float lo[3], const float hi[3], const float o[3], const float d[3], float &nearT, float &farT) {
+    nearT = -std::numeric_limits<float>::infinity();
+    farT = std::numeric_limits<float>::infinity();
+    for (int i = 0; i < 3; i++) {
+        if (d[i] == 0) {
+            if (o[i] < lo[i] || o[i] > hi[i]) return false;
+        } else {
+            float rcp = 1.0f / d[i];
+            float t1 = (lo[i] - o[i]) * rcp, t2 = (hi[i] - o[i]) * rcp;
+            if (t1 > t2) std::swap(t1, t2);
+            nearT = std::max(t1, nearT);
+            farT = std::min(t2, farT);
+            if (!(nearT <= farT)) return false;
+        }
+    }
+    return true;
+}
+
+struct StraightWoodcock {
+    const GridVolume *grid;
+    float lo[3], hi[3], scale, invMaxDensity;
+    bool sampleDistance(const float o[3], const float d[3], float rmint, float rmaxt, PhiloxStream &rng, float &tOut, float &densityAtT) const {
+        float mint, maxt;
+        densityAtT = 0;
+        tOut = 0;
+        if (!aabbRayIntersect(lo, hi, o, d, mint, maxt)) return false;
+        mint = std::max(mint, rmint);
+        maxt = std::min(maxt, rmaxt);
+        float t = mint;
+        while (true) {
+            t -= (float) std::log((double) (1 - rng.next())) * invMaxDensity;
+            if (t >= maxt) break;
+            float p[3] = {o[0] + t * d[0], o[1] + t * d[1], o[2] + t * d[2]};
+            densityAtT = grid->lookupFloat(p) * scale;
+            if (densityAtT * invMaxDensity > rng.next()) { tOut = t; return true; }
+        }
+        return false;
+    }
+    float evalTransmittance(const float o[3], const float d[3], float rmint, float rmaxt, PhiloxStream &rng) const {
+        float mint, maxt;
+        if (!aabbRayIntersect(lo, hi, o, d, mint, maxt)) return 1.0f;
+        mint = std::max(mint, rmint);
+        maxt = std::min(maxt, rmaxt);
+        const int nSamples = 2;
+        float result = 0;
+        for (int i = 0; i < nSamples; ++i) {
+            float t = mint;
+            while (true) {
+                t -= (float) std::log((double) (1 - rng.next())) * invMaxDensity;
+                if (t >= maxt) { result += 1; break; }
+                float p[3] = {o[0] + t * d[0], o[1] + t * d[1], o[2] + t * d[2]};
+                float density = grid->lookupFloat(p) * scale;
+                if (density * invMaxDensity > rng.next()) break;
+            }
+        }
+        return result / nSamples;
     }
 };
 
@@ -948,6 +1044,10 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
         return m;                                                                                                 \
     }                                                                                                             \
     extern "C" void orc_medium_destroy##SUF(void *h) { delete (Medium<F> *) h; }                                  \
+    extern "C" void orc_medium_set_sdf##SUF(void *h, void *sdf, int aggressive) {                                 \
+        ((Medium<F> *) h)->sdf = (const SplineVolume<F> *) sdf;                                                    \
+        ((Medium<F> *) h)->aggressive = aggressive != 0;                                                          \
+    }                                  \
     extern "C" void orc_medium_resolved##SUF(void *h, float *weight, float *samplingDensity) {                    \
         *weight = ((Medium<F> *) h)->weight;                                                                      \
         *samplingDensity = ((Medium<F> *) h)->samplingDensity;                                                    \
@@ -1018,6 +1118,33 @@ extern "C" void orc_grid_destroy(void *h) { delete (GridVolume *) h; }
 extern "C" void orc_grid_lookup(void *h, size_t n, const float *p, float *out) {
     const GridVolume *g = (const GridVolume *) h;
     for (size_t i = 0; i < n; i++) out[i] = g->lookupFloat(p + 3 * i);
+}
+static StraightWoodcock makeWoodcock(void *grid, const mer_volume_desc *d, float scale) {
+    StraightWoodcock w;
+    w.grid = (const GridVolume *) grid;
+    for (int i = 0; i < 3; i++) { w.lo[i] = d->bbox_min[i]; w.hi[i] = d->bbox_max[i]; }
+    w.scale = scale;
+    w.invMaxDensity = 1.0f / (scale * 1.0f);
+    return w;
+}
+extern "C" void orc_grid_sample_distance(void *grid, const mer_volume_desc *d, float scale, size_t n, const float *ro,
+                                         const float *rd, const float *mint, const float *maxt, uint64_t seed,
+                                         uint8_t *success, float *t, float *densityAtT) {
+    StraightWoodcock w = makeWoodcock(grid, d, scale);
+    for (size_t i = 0; i < n; i++) {
+        PhiloxStream rng;
+        rng.init(seed, i);
+        success[i] = w.sampleDistance(ro + 3 * i, rd + 3 * i, mint[i], maxt[i], rng, t[i], densityAtT[i]) ? 1 : 0;
+    }
+}
+extern "C" void orc_grid_eval_transmittance(void *grid, const mer_volume_desc *d, float scale, size_t n, const float *ro,
+                                            const float *rd, const float *mint, const float *maxt, uint64_t seed, float *out) {
+    StraightWoodcock w = makeWoodcock(grid, d, scale);
+    for (size_t i = 0; i < n; i++) {
+        PhiloxStream rng;
+        rng.init(seed, i);
+        out[i] = w.evalTransmittance(ro + 3 * i, rd + 3 * i, mint[i], maxt[i], rng);
+    }
 }
 extern "C" void orc_hg_sample(float g, size_t n, const float *wi, const float *xi, float *wo, float *pdf) {
     for (size_t i = 0; i < n; i++) {

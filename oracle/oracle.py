@@ -236,6 +236,33 @@ class Oracle:
     def medium_destroy(self, h):
         self._fn("orc_medium_destroy")(h)
 
+    def medium_set_sdf(self, h, sdf, aggressive=True):
+        self._fn("orc_medium_set_sdf")(h, sdf, C.c_int(1 if aggressive else 0))
+
+    def grid_sample_distance(self, grid, desc, scale, ro, rd, mint, maxt, seed):
+        ro = np.ascontiguousarray(ro, dtype=np.float32).reshape(-1, 3)
+        rd = np.ascontiguousarray(rd, dtype=np.float32).reshape(-1, 3)
+        n = ro.shape[0]
+        mint = np.ascontiguousarray(np.broadcast_to(np.asarray(mint, np.float32), (n,)))
+        maxt = np.ascontiguousarray(np.broadcast_to(np.asarray(maxt, np.float32), (n,)))
+        ok, t, dens = np.zeros(n, np.uint8), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self.lib.orc_grid_sample_distance(grid, C.byref(desc), C.c_float(scale), C.c_size_t(n), _ptr(ro, C.c_float),
+                                          _ptr(rd, C.c_float), _ptr(mint, C.c_float), _ptr(maxt, C.c_float), C.c_uint64(seed),
+                                          _ptr(ok, C.c_uint8), _ptr(t, C.c_float), _ptr(dens, C.c_float))
+        return ok.astype(bool), t, dens
+
+    def grid_eval_transmittance(self, grid, desc, scale, ro, rd, mint, maxt, seed):
+        ro = np.ascontiguousarray(ro, dtype=np.float32).reshape(-1, 3)
+        rd = np.ascontiguousarray(rd, dtype=np.float32).reshape(-1, 3)
+        n = ro.shape[0]
+        mint = np.ascontiguousarray(np.broadcast_to(np.asarray(mint, np.float32), (n,)))
+        maxt = np.ascontiguousarray(np.broadcast_to(np.asarray(maxt, np.float32), (n,)))
+        out = np.zeros(n, np.float32)
+        self.lib.orc_grid_eval_transmittance(grid, C.byref(desc), C.c_float(scale), C.c_size_t(n), _ptr(ro, C.c_float),
+                                             _ptr(rd, C.c_float), _ptr(mint, C.c_float), _ptr(maxt, C.c_float),
+                                             C.c_uint64(seed), _ptr(out, C.c_float))
+        return out
+
     def medium_resolved(self, h):
         w, sd = C.c_float(), C.c_float()
         self._fn("orc_medium_resolved")(h, C.byref(w), C.byref(sd))

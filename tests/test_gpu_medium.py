@@ -320,3 +320,72 @@ def test_error_behaviour():
     out = med.trace(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0))
     assert out["p"].shape == (0, 3)
     assert rif.value(np.zeros((0, 3))).shape == (0,)
+
+
+def test_aggressive_tracing_sdf(oracle32):
+    """row a10: aggressive_trace (:697-704) + the signed-distance sphere-tracing loop of sampleDistance (:476-493)"""
+    res = 48
+    data, lo, hi = make_field("radial", res)
+    sdf_data = mer.fields.sphere_sdf((res,) * 3, lo, hi, radius=0.8).astype(np.float32)
+    props = medium_props(stepsize=4e-3, strategy="single", shape=("sphere", (0.0, 0.0, 0.0), 0.8), aggressivetracing=True)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    sdf = mer.SplineDataSource(data=sdf_data, min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("sdf", sdf).addChild("", mer.HGPhaseFunction(g=0.9)).configure()
+    plain = mer.HeterogeneousRefractiveMedium(medium_props(stepsize=4e-3, strategy="single", shape=("sphere", (0.0, 0.0, 0.0), 0.8)))
+    plain.addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9)).configure()
+    d = volume_desc((res,) * 3, lo, hi)
+    orif, osdf = oracle32.rif_create(d, data), oracle32.rif_create(d, sdf_data)
+    omed = oracle32.medium_create(oracle_medium_desc(props, 0.9), orif)
+    oracle32.medium_set_sdf(omed, osdf, True)
+    n = 12000
+    o = (random_points_in_box(n, 121) * 0.45).astype(np.float32)
+    dd = random_directions(n, 122)
+    xi = np.random.default_rng(123).random((n, 2)).astype(np.float32)
+    got = med.sampleDistance(o, dd, 0.0, xi)
+    ref = oracle32.sample_distance(omed, o, dd, 0.0, xi)
+    same = (got["success"] == ref["success"]) & (got["nsteps"] == ref["nsteps"])
+    assert same.mean() > 0.995 and got["success"].sum() > n // 5 and (~got["success"]).sum() > n // 10
+    for key, scale in (("t", 2.0), ("p", 1.0), ("d", 2.0), ("optical_length", 4.0), ("ref_ratio_sq", 2.0), ("pdf_success", 5.0)):
+        e = np.abs(np.asarray(got[key], np.float64) - ref[key]).reshape(n, -1).max(axis=1)[same] / scale
+        assert np.mean(e <= 1e-5) > 0.998 and e.max() <= 1e-4, key
+    # aggressive segments add remainder steps (one per sphere-tracing hop) but land in the same place as the tested trace
+    base = plain.sampleDistance(o, dd, 0.0, xi)
+    both = got["success"] & base["success"]
+    assert both.sum() > n // 5 and np.all(got["nsteps"][both] >= base["nsteps"][both])
+    assert np.abs(got["p"][both] - base["p"][both]).max() < 5e-4 and np.allclose(got["t"][both], base["t"][both], rtol=1e-6)
+    # the integrator refuses an aggressive medium (containment there is analytic, R5)
+    with pytest.raises(mer.MerError, match="aggressivetracing"):
+        mer.EikonalVolPathIntegrator().render(dict(width=8, height=8, sampleCount=1, origin=(0, 0, -4), target=(0, 0, 0)), med)
+    with pytest.raises(mer.MerError, match="No SDF specified"):
+        mer.HeterogeneousRefractiveMedium(medium_props(aggressivetracing=True)).addChild("rif", rif).configure()
+
+
+@pytest.mark.parametrize("scale", [4.0, 20.0])
+def test_straight_ray_woodcock(oracle32, scale):
+    """row a19: HeterogeneousMedium::sampleDistance / evalTransmittance (Woodcock), straight rays, Philox replay"""
+    res = (24, 20, 28)
+    dens = mer.fields.sine_density(res, BOX_MIN, BOX_MAX)
+    grid = mer.GridDataSource(data=dens, min=BOX_MIN, max=BOX_MAX)
+    d = volume_desc(res, BOX_MIN, BOX_MAX)
+    ogrid = oracle32.grid_create(d, dens)
+    n = 20000
+    o = (random_points_in_box(n, 131) * 1.6).astype(np.float32)  # some origins outside the box
+    dd = random_directions(n, 132)
+    dd[:50, 0] = 0.0  # rays parallel to a slab
+    mint = np.zeros(n, np.float32)
+    maxt = (np.random.default_rng(133).random(n) * 3 + 0.1).astype(np.float32)
+    ok, t, den = grid.sampleDistance(o, dd, mint, maxt, scale, seed=77)
+    rok, rt, rden = oracle32.grid_sample_distance(ogrid, d, scale, o, dd, mint, maxt, 77)
+    assert np.array_equal(ok, rok) and ok.sum() > n // 10 and (~ok).sum() > n // 10
+    assert np.array_equal(t[ok], rt[ok]) and np.array_equal(den[ok], rden[ok])  # same streams, same roundings: bit-exact
+    T = grid.evalTransmittance(o, dd, mint, maxt, scale, seed=78)
+    rT = oracle32.grid_eval_transmittance(ogrid, d, scale, o, dd, mint, maxt, 78)
+    assert np.array_equal(T, rT) and set(np.unique(T)) <= {0.0, 0.5, 1.0}
+    # unbiasedness: the 2-sample estimate averages to exp(-integral of density) along a fixed ray
+    oo = np.repeat(np.array([[-0.9, 0.13, 0.21]], np.float32), 40000, 0)
+    dv = np.repeat(np.array([[1.0, 0.0, 0.0]], np.float32), 40000, 0)
+    est = grid.evalTransmittance(oo, dv, 0.0, 1.8, scale, seed=79).mean()
+    ts = np.linspace(0, 1.8, 4001)
+    pts = (oo[:1] + ts[:, None] * dv[:1]).astype(np.float32)
+    tau = np.trapezoid(grid.lookupFloat(pts).astype(np.float64) * scale, ts)
+    assert abs(est - np.exp(-tau)) < 4 * np.sqrt(0.25 / 40000) + 2e-3
