@@ -208,6 +208,56 @@ int mer_medium_sample_distance_batch(const mer_medium *medium, size_t n, const f
 int mer_medium_eval_transmittance_batch(const mer_medium *medium, size_t n, const float *mint,
                                         const float *maxt, float *transmittance_out);
 
+/* ------------------------------------------------ curved direct connections
+ * Function-level building blocks of HeterogeneousRefractiveMedium::eval / makeDirectConnections
+ * (heterogeneousrefractive.cpp:571-640, 1087-1163).  The solver itself is Ceres BFGS in the reference
+ * (not reproducible bit-wise: parity unpinned there); what is deterministic is exposed and parity-tested: */
+
+/* SplineDataSource::valueGradientAndHessian (splinevolume.cpp:371-377, basisspline.h:539-606);
+ * hess_out is row-major [n][9] */
+int mer_rif_eval_hessian_batch(const mer_rif *rif, size_t n, const float *p, float *value_out, float *grad_out,
+                               float *hess_out);
+/* nsteps[i] calls of er_derivativestep (:798-814) from dp/dv0 = 0, dv/dv0 = I; p, v in/out; Jacobians [n][9] out */
+int mer_medium_derivative_trace_batch(const mer_medium *medium, size_t n, float *p, float *v, const int32_t *nsteps,
+                                      float *dpdv0_out, float *dvdv0_out);
+/* computefdfBDPT (:816-939): residual p(t*) - p2 at the closest approach of the ray launched from p1 with
+ * velocity v0, and its Jacobian (stored transposed like :936-938).  status: 0 inside, 1 left the object
+ * (Snell at the sdf boundary + straight extension; needs mer_medium_set_sdf), 2 degenerate. */
+int mer_medium_connection_residual_batch(const mer_medium *medium, int boundary_precision, size_t n, const float *p1,
+                                         const float *p2, const float *v0, int is_sensor_sample, float *error_out,
+                                         float *derror_out, int32_t *status_out, int32_t *nsteps_out);
+
+/* `tol2`, `rrweight`, `boundaryprecision`, `ceresmaxiterations` (heterogeneousrefractive.cpp:208-219) */
+typedef struct mer_connection_params {
+    float tol2;                 /* 1e-6: accept when 0.5 |r|^2 < tol2; reject when |p(t*) - p2|^2 > tol2 after the re-trace */
+    float rrweight;             /* 1e-2: Russian roulette on solver failures */
+    int32_t boundary_precision; /* 3: ceil(precision / log10 2) step halvings */
+    int32_t max_iterations;     /* 20 */
+} mer_connection_params;
+
+/* what HeterogeneousRefractiveMedium::eval fills into the MediumSamplingRecord for a connection (:571-640) */
+typedef struct mer_connection_records {
+    uint8_t *success;      /* [n] */
+    float *dir_to_p2;      /* [n][3] launch velocity at p1 (n-scaled) */
+    float *rev_dir_to_p1;  /* [n][3] mRec.drev: unit arrival direction at p2, reversed */
+    float *optical_length; /* [n] midpoint-rule optical length (:941-1030) */
+    float *distance;       /* [n] curved geometric length */
+    float *weight;         /* [n] 1 / rrweight^k */
+    float *transmittance;  /* [n][3] exp(-sigma_t * distance) * weight */
+    float *pdf_success;    /* [n] */
+    float *pdf_failure;    /* [n] */
+    int32_t *evaluations;  /* [n] residual evaluations (each one a Jacobian-carrying trace) */
+} mer_connection_records;
+
+/* HeterogeneousRefractiveMedium::eval / makeDirectConnections (:571-640, 1087-1163): for every pair find the launch
+ * direction at p1 whose eikonal ray passes through p2 (seed directions: uniform on the hemisphere about `seed_dir`,
+ * Sampler of pair i = Philox stream (seed, i)), then measure the path (computePathLengthsTillClosestP2 :941-1030) and
+ * fill pdfs / transmittance.  The minimiser is Levenberg-Marquardt on computefdfBDPT's residual and Jacobian; the
+ * reference uses Ceres 1.14 BFGS (not available, not bit-reproducible: parity unpinned at the solver). */
+int mer_medium_connect_batch(const mer_medium *medium, const mer_connection_params *params, size_t n, const float *p1,
+                             const float *p2, const float *seed_dir, int is_sensor_sample, uint64_t seed,
+                             mer_connection_records *rec);
+
 /* -------------------------------------------------------------- integrator */
 
 enum mer_filter { MER_FILTER_BOX = 0, MER_FILTER_GAUSSIAN = 1 };

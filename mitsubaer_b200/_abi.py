@@ -47,6 +47,17 @@ class SamplingRecords(C.Structure):
                 ("sigma_s", C.POINTER(C.c_float)), ("nsteps", C.POINTER(C.c_int32))]
 
 
+class ConnectionParams(C.Structure):
+    _fields_ = [("tol2", C.c_float), ("rrweight", C.c_float), ("boundary_precision", C.c_int32), ("max_iterations", C.c_int32)]
+
+
+class ConnectionRecords(C.Structure):
+    _fields_ = [("success", C.POINTER(C.c_uint8)), ("dir_to_p2", C.POINTER(C.c_float)), ("rev_dir_to_p1", C.POINTER(C.c_float)),
+                ("optical_length", C.POINTER(C.c_float)), ("distance", C.POINTER(C.c_float)), ("weight", C.POINTER(C.c_float)),
+                ("transmittance", C.POINTER(C.c_float)), ("pdf_success", C.POINTER(C.c_float)), ("pdf_failure", C.POINTER(C.c_float)),
+                ("evaluations", C.POINTER(C.c_int32))]
+
+
 class RenderDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp_total", C.c_int32),
                 ("sample_begin", C.c_int32), ("sample_stride", C.c_int32), ("seed", C.c_uint64),
@@ -104,6 +115,11 @@ SIGNATURES = {
     "mer_medium_trace_till_boundary_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp, _fp, _i32p]),
     "mer_medium_sample_distance_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp, _fp, C.POINTER(SamplingRecords)]),
     "mer_medium_eval_transmittance_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp]),
+    "mer_rif_eval_hessian_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp, _fp]),
+    "mer_medium_derivative_trace_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _i32p, _fp, _fp]),
+    "mer_medium_connection_residual_batch": (C.c_int, [_vp, C.c_int, C.c_size_t, _fp, _fp, _fp, C.c_int, _fp, _fp, _i32p, _i32p]),
+    "mer_medium_connect_batch": (C.c_int, [_vp, C.POINTER(ConnectionParams), C.c_size_t, _fp, _fp, _fp, C.c_int, C.c_uint64,
+                                           C.POINTER(ConnectionRecords)]),
     "mer_render": (C.c_int, [_vp, C.POINTER(RenderDesc), _fp, C.POINTER(RenderStats)]),
     "mer_render_device": (C.c_int, [_vp, C.POINTER(RenderDesc), _vp, C.POINTER(RenderStats), _vp]),
     "mer_film_develop": (C.c_int, [C.c_int, C.c_int32, C.c_int32, _fp, _fp]),

@@ -132,6 +132,13 @@ class SplineDataSource(_Volume):
     def valueAndGradient(self, p):
         return self._eval(_abi.EVAL_VALUE_AND_GRADIENT, p)
 
+    def valueGradientAndHessian(self, p):
+        p = _f32(p, (-1, 3))
+        n = p.shape[0]
+        f, g, H = np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 3, 3), np.float32)
+        check(lib.mer_rif_eval_hessian_batch(self.handle, n, _fp(p), _fp(f), _fp(g), _fp(H)))
+        return f, g, H
+
     def insideVolumeLimits(self, p):
         p = _f32(p, (-1, 3))
         out = np.zeros(p.shape[0], np.uint8)
@@ -390,6 +397,48 @@ class HeterogeneousRefractiveMedium:
                   "sigma_s"):
             setattr(rec, k, _fp(r[k]))
         check(lib.mer_medium_sample_distance_batch(self.handle, n, _fp(ro), _fp(rd), _fp(mint), _fp(xi), C.byref(rec)))
+        r["success"] = r["success"].astype(bool)
+        return r
+
+    # ---- curved direct connections, function level
+    def derivativeTrace(self, p, v, nsteps):
+        """nsteps x er_derivativestep -> p, v, dp/dv0, dv/dv0"""
+        p = np.array(p, np.float32).reshape(-1, 3)
+        v = np.array(v, np.float32).reshape(-1, 3)
+        n = p.shape[0]
+        ns = np.ascontiguousarray(np.broadcast_to(np.asarray(nsteps, np.int32), (n,)))
+        A, B = np.zeros((n, 3, 3), np.float32), np.zeros((n, 3, 3), np.float32)
+        check(lib.mer_medium_derivative_trace_batch(self.handle, n, _fp(p), _fp(v), ns.ctypes.data_as(C.POINTER(C.c_int32)), _fp(A), _fp(B)))
+        return dict(p=p, v=v, dpdv0=A, dvdv0=B)
+
+    def connectionResidual(self, p1, p2, v0, is_sensor_sample=False):
+        """computefdfBDPT -> error, derror (transposed Jacobian), status, nsteps"""
+        p1, p2, v0 = _f32(p1, (-1, 3)), _f32(p2, (-1, 3)), _f32(v0, (-1, 3))
+        n = p1.shape[0]
+        err, J = np.zeros((n, 3), np.float32), np.zeros((n, 3, 3), np.float32)
+        st, ns = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        check(lib.mer_medium_connection_residual_batch(self.handle, int(self.props.get("boundaryprecision", 3)), n, _fp(p1), _fp(p2), _fp(v0),
+                                                       1 if is_sensor_sample else 0, _fp(err), _fp(J),
+                                                       st.ctypes.data_as(C.POINTER(C.c_int32)), ns.ctypes.data_as(C.POINTER(C.c_int32))))
+        return dict(error=err, derror=J, status=st, nsteps=ns)
+
+    def eval(self, vsp, vtp, seed_dir, is_sensor_sample=False, seed=1):
+        """HeterogeneousRefractiveMedium::eval over a batch of (p1 = vsp, p2 = vtp) pairs"""
+        p1, p2, sd = _f32(vsp, (-1, 3)), _f32(vtp, (-1, 3)), _f32(seed_dir, (-1, 3))
+        n = p1.shape[0]
+        cp = _abi.ConnectionParams(float(self.props.get("tol2", 1e-6)), float(self.props.get("rrweight", 1e-2)),
+                                   int(self.props.get("boundaryprecision", 3)), int(self.props.get("ceresmaxiterations", 20)))
+        r = dict(success=np.zeros(n, np.uint8), dir_to_p2=np.zeros((n, 3), np.float32), rev_dir_to_p1=np.zeros((n, 3), np.float32),
+                 optical_length=np.zeros(n, np.float32), distance=np.zeros(n, np.float32), weight=np.zeros(n, np.float32),
+                 transmittance=np.zeros((n, 3), np.float32), pdf_success=np.zeros(n, np.float32), pdf_failure=np.zeros(n, np.float32),
+                 evaluations=np.zeros(n, np.int32))
+        rec = _abi.ConnectionRecords()
+        rec.success = r["success"].ctypes.data_as(C.POINTER(C.c_uint8))
+        rec.evaluations = r["evaluations"].ctypes.data_as(C.POINTER(C.c_int32))
+        for k in ("dir_to_p2", "rev_dir_to_p1", "optical_length", "distance", "weight", "transmittance", "pdf_success", "pdf_failure"):
+            setattr(rec, k, _fp(r[k]))
+        check(lib.mer_medium_connect_batch(self.handle, C.byref(cp), n, _fp(p1), _fp(p2), _fp(sd), 1 if is_sensor_sample else 0, int(seed),
+                                           C.byref(rec)))
         r["success"] = r["success"].astype(bool)
         return r
 

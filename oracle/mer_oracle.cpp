@@ -263,6 +263,18 @@ template <typename F> struct SplineVolume {
         spline.eval(p, f, g, nullptr);
         rotT(g);
     }
+    /* valueGradientAndHessian, :371-377: H_world = RotT * H * Rot */
+    inline void valueGradientAndHessian(const F *pw, F *f, F *g, F *H) const {
+        F p[3];
+        toVolume(pw, p);
+        spline.eval(p, f, g, H);
+        rotT(g);
+        if (!hasXform) return;
+        F R[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]}, T[9], O[9];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { F a = 0; for (int k = 0; k < 3; k++) a += R[3 * k + i] * H[3 * k + j]; T[3 * i + j] = a; }
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { F a = 0; for (int k = 0; k < 3; k++) a += T[3 * i + k] * R[3 * k + j]; O[3 * i + j] = a; }
+        for (int i = 0; i < 9; i++) H[i] = O[i];
+    }
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -478,6 +490,173 @@ template <typename F> struct Medium {
         }
     }
 
+    /* ---------------------------------------------------------------- a25: curved direct connections
+     * 3x3 matrices are row-major F[9]; outer(a,b) = Matrix3x3F(a,b) (include/mitsuba/core/matrix.h:584-588);
+     * preMult(M, x) = M^T x (matrix.h:765-769). */
+    static void mmul(const F *A, const F *B, F *C) {
+        F T[9];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { F a = 0; for (int k = 0; k < 3; k++) a += A[3 * i + k] * B[3 * k + j]; T[3 * i + j] = a; }
+        for (int i = 0; i < 9; i++) C[i] = T[i];
+    }
+    static void outer(const F *a, const F *b, F *C) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C[3 * i + j] = a[i] * b[j]; }
+    static void preMult(const F *Mx, const F *x, F *y) { for (int j = 0; j < 3; j++) y[j] = x[0] * Mx[j] + x[1] * Mx[3 + j] + x[2] * Mx[6 + j]; }
+    static F dot(const F *a, const F *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+    /* er_derivativestep, :798-814: leapfrog on (p, v, A = dp/dv0, B = dv/dv0) */
+    void er_derivativestep(F *p, F *v, F *A, F *B, F stepsize, long &count) const {
+        const F half = (F) 0.5;
+        F n, G[3], H[9], T[9];
+        rif->valueGradientAndHessian(p, &n, G, H);
+        for (int i = 0; i < 3; i++) v[i] += half * stepsize * G[i];
+        mmul(H, A, T);
+        for (int i = 0; i < 9; i++) B[i] += half * stepsize * T[i];
+        F recip = (F) 1 / n;
+        for (int i = 0; i < 3; i++) p[i] += (stepsize * v[i]) * recip;
+        rif->valueGradientAndHessian(p, &n, G, H);
+        F invn = 1 / n;
+        F VG[9], T2[9];
+        outer(v, G, VG);
+        mmul(VG, A, T2);
+        for (int i = 0; i < 9; i++) A[i] += stepsize * (-invn * invn * T2[i] + invn * B[i]);
+        for (int i = 0; i < 3; i++) v[i] += half * stepsize * G[i];
+        mmul(H, A, T);
+        for (int i = 0; i < 9; i++) B[i] += half * stepsize * T[i];
+        count++;
+    }
+
+    /* boundaryVelocity, :1036-1051 (Snell towards exterior index ne; reflection when total) */
+    static void boundaryVelocity(F *v, const F *N, F ni, F ne) {
+        F dotp = dot(v, N), r = ne / ni;
+        r = r * r - 1;
+        F n2 = dot(v, v), sq = r * n2 + dotp * dotp;
+        if (sq < kEpsilon) { for (int i = 0; i < 3; i++) v[i] = 2 * dotp * N[i] - v[i]; return; }
+        sq = std::sqrt(sq);
+        int sg = (F(0) < dotp) - (dotp < F(0));
+        for (int i = 0; i < 3; i++) v[i] = v[i] - dotp * N[i] + sg * sq * N[i];
+    }
+    /* boundaryVelocityDerivative, :1057-1074 */
+    static void boundaryVelocityDerivative(F *v, F *B, const F *dtb, const F *dnb, const F *N, F ni, F ne) {
+        F dotp = dot(v, N), r = ne / ni;
+        r = r * r - 1;
+        F n2 = dot(v, v), sq = r * n2 + dotp * dotp;
+        F NN[9], DT[9], S[9], L[9];
+        outer(N, N, NN);
+        outer(dnb, dtb, DT);
+        for (int i = 0; i < 9; i++) S[i] = B[i] + DT[i];
+        if (sq < kEpsilon) {
+            for (int i = 0; i < 3; i++) v[i] = 2 * dotp * N[i] - v[i];
+            for (int i = 0; i < 9; i++) L[i] = (F) 2.0 * NN[i] - ((i % 4 == 0) ? (F) 1 : (F) 0);
+            mmul(L, S, B);
+            return;
+        }
+        sq = std::sqrt(sq);
+        int sg = (F(0) < dotp) - (dotp < F(0));
+        F w[3], NW[9];
+        for (int i = 0; i < 3; i++) w[i] = (r * v[i] + dotp * N[i]) / sq;
+        outer(N, w, NW);
+        for (int i = 0; i < 9; i++) L[i] = ((i % 4 == 0) ? (F) 1 : (F) 0) - NN[i] + sg * NW[i];
+        mmul(L, S, B);
+        for (int i = 0; i < 3; i++) v[i] = v[i] - dotp * N[i] + sg * sq * N[i];
+    }
+
+    int boundaryprecision = 3; /* `boundaryprecision` */
+    F tol2 = (F) 1e-6;         /* `tol2` */
+
+    /* computefdfBDPT, :816-939: residual p(t*) - p2 and its Jacobian w.r.t. the launch velocity.
+     * returns 0 = closest approach inside, 1 = left the object (needs sdf), 2 = degenerate (error = p1 - p2, J = 0) */
+    int computefdf(const F *v_i, const F *p1, const F *p2, bool isSensorSample, F *err, F *derr, long &count) const {
+        F A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, B[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int i = 0; i < 9; i++) derr[i] = 0;
+        if (!(sdf ? sdf : rif)->insideVolumeLimits(p1)) { for (int i = 0; i < 3; i++) err[i] = p1[i] - p2[i]; return 2; }
+        F h0 = h;
+        const int maxSteps = 100000;
+        long nBisect = (long) std::ceil(boundaryprecision / std::log10(2.0));
+        bool leftObject = false;
+        F p[3] = {p1[0], p1[1], p1[2]}, v[3] = {v_i[0], v_i[1], v_i[2]}, oldp[3], oldv[3], oldA[9], oldB[9], d[3];
+        for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+        bool signOld = std::signbit(dot(d, v)), signNew;
+        F r = rif->value(p), n1 = std::sqrt(dot(v_i, v_i)), n2 = n1 * n1, n3 = n2 * n1;
+        { /* chain rule through the renormalisation of the launch velocity, :838-843 */
+            F VV[9], P[9];
+            outer(v, v, VV);
+            for (int i = 0; i < 9; i++) P[i] = (r / n3) * (n2 * ((i % 4 == 0) ? (F) 1 : (F) 0) - VV[i]);
+            mmul(P, B, B);
+            F recip = (F) 1 / n1;
+            for (int i = 0; i < 3; i++) v[i] = (v[i] * recip) * r;
+        }
+        auto save = [&]() { for (int i = 0; i < 3; i++) { oldp[i] = p[i]; oldv[i] = v[i]; } for (int i = 0; i < 9; i++) { oldA[i] = A[i]; oldB[i] = B[i]; } };
+        auto load = [&]() { for (int i = 0; i < 3; i++) { p[i] = oldp[i]; v[i] = oldv[i]; } for (int i = 0; i < 9; i++) { A[i] = oldA[i]; B[i] = oldB[i]; } };
+        for (int it = 0; it < maxSteps; it++) {
+            save();
+            er_derivativestep(p, v, A, B, h0, count);
+            for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+            signNew = std::signbit(dot(d, v));
+            if (signNew != signOld) {
+                while (nBisect > 0) {
+                    nBisect--;
+                    load();
+                    h0 = h0 / 2;
+                    er_derivativestep(p, v, A, B, h0, count);
+                    for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+                    signNew = std::signbit(dot(d, v));
+                    if (signNew == signOld) save();
+                }
+                break;
+            } else if (!insideShape(p)) {
+                while (nBisect > 0) {
+                    nBisect--;
+                    load();
+                    h0 = h0 / 2;
+                    er_derivativestep(p, v, A, B, h0, count);
+                    if (insideShape(p)) save();
+                }
+                F dp1[3] = {p[0] - p1[0], p[1] - p1[1], p[2] - p1[2]};
+                if (dot(dp1, dp1) < kEpsilon || !sdf) { for (int i = 0; i < 3; i++) err[i] = p1[i] - p2[i]; for (int i = 0; i < 9; i++) derr[i] = 0; return sdf ? 2 : 1; }
+                F nb, dnb[3], dpdtb[3], N[3], dtb[3];
+                rif->valueAndGradient(p, &nb, dnb);
+                F rn = (F) 1 / nb;
+                for (int i = 0; i < 3; i++) dpdtb[i] = v[i] * rn;
+                sdf->gradient(p, N);
+                F nl = (F) 1 / std::sqrt(dot(N, N));
+                for (int i = 0; i < 3; i++) N[i] *= nl;
+                preMult(A, N, dtb);
+                F den = dot(N, dpdtb);
+                for (int i = 0; i < 3; i++) dtb[i] = -dtb[i] / den;
+                boundaryVelocityDerivative(v, B, dtb, dnb, N, nb, (F) 1.0);
+                for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+                F extra_t = -dot(v, d) / dot(v, v);
+                leftObject = true;
+                if (isSensorSample && extra_t < 0) { for (int i = 0; i < 3; i++) err[i] = p1[i] - p2[i]; return 2; }
+                F dv[3] = {dpdtb[0] - v[0], dpdtb[1] - v[1], dpdtb[2] - v[2]}, O[9];
+                outer(dv, dtb, O);
+                for (int i = 0; i < 9; i++) A[i] += O[i] + extra_t * B[i];
+                for (int i = 0; i < 3; i++) p[i] += extra_t * v[i];
+                break;
+            }
+        }
+        F dts[3], dpdt[3], a[3], b[3];
+        for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+        preMult(A, v, a);
+        preMult(B, d, b);
+        if (!leftObject) {
+            F dvdt[3];
+            rif->valueAndGradient(p, &r, dvdt);
+            F rr = (F) 1 / r;
+            for (int i = 0; i < 3; i++) dpdt[i] = v[i] * rr;
+            F den = dot(v, dpdt) + dot(d, dvdt);
+            for (int i = 0; i < 3; i++) dts[i] = -(a[i] + b[i]) / den;
+        } else {
+            for (int i = 0; i < 3; i++) dpdt[i] = v[i];
+            F den = dot(v, dpdt);
+            for (int i = 0; i < 3; i++) dts[i] = -(a[i] + b[i]) / den;
+        }
+        F O[9];
+        outer(dpdt, dts, O);
+        for (int i = 0; i < 3; i++) err[i] = d[i];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) derr[3 * i + j] = A[3 * j + i] + O[3 * j + i]; /* transposed, :936-938 */
+        return leftObject ? 1 : 0;
+    }
+
     struct Record {
         bool success;
         F t, p[3], dvec[3], opticalLength, refRatioSq;
@@ -676,6 +855,186 @@ struct StraightWoodcock {
         return result / nSamples;
     }
 };
+
+/* ------------------------------------------------------------------------------------------
+ * a25  makeDirectConnections (:1087-1163) + computePathLengthsTillClosestP2 (:941-1030) + eval (:571-640).
+ * The reference minimises 0.5 |r(v0)|^2 with Ceres 1.14 (LINE_SEARCH / BFGS, <= 20 iterations); Ceres is
+ * not available and not bit-reproducible, so the minimiser here is a Levenberg-Marquardt iteration on the
+ * SAME residual and Jacobian (computefdf above), written identically in the CUDA path.  PARITY UNPINNED at
+ * the solver: results are validated by the residual they reach, not against Ceres.
+ * ------------------------------------------------------------------------------------------ */
+template <typename F> struct ConnectionResult {
+    bool success;
+    F dirToP2[3], revDirToP1[3], opticalDist, dist, weight;
+    float transmittance[3], pdfSuccess, pdfFailure;
+    int evaluations;
+};
+
+template <typename F> bool solve3(const F *Mx, const F *b, F *x) { /* symmetric 3x3 by Cramer */
+    F det = Mx[0] * (Mx[4] * Mx[8] - Mx[5] * Mx[7]) - Mx[1] * (Mx[3] * Mx[8] - Mx[5] * Mx[6]) + Mx[2] * (Mx[3] * Mx[7] - Mx[4] * Mx[6]);
+    if (!(std::abs(det) > 0)) return false;
+    F inv = (F) 1 / det;
+    x[0] = inv * (b[0] * (Mx[4] * Mx[8] - Mx[5] * Mx[7]) - Mx[1] * (b[1] * Mx[8] - Mx[5] * b[2]) + Mx[2] * (b[1] * Mx[7] - Mx[4] * b[2]));
+    x[1] = inv * (Mx[0] * (b[1] * Mx[8] - Mx[5] * b[2]) - b[0] * (Mx[3] * Mx[8] - Mx[5] * Mx[6]) + Mx[2] * (Mx[3] * b[2] - b[1] * Mx[6]));
+    x[2] = inv * (Mx[0] * (Mx[4] * b[2] - b[1] * Mx[7]) - Mx[1] * (Mx[3] * b[2] - b[1] * Mx[6]) + b[0] * (Mx[3] * Mx[7] - Mx[4] * Mx[6]));
+    return true;
+}
+
+/* computePathLengthsTillClosestP2, :941-1030 */
+template <typename F>
+bool computePathLengths(const Medium<F> &M, const F *p1, const F *p2, const F *dirToP2, F *revDir, bool isSensorSample, F &opl, F &dist) {
+    dist = 0;
+    opl = 0;
+    F h0 = M.h;
+    long nBisect = (long) std::ceil(M.boundaryprecision / std::log10(2.0)), count = 0;
+    F p[3] = {p1[0], p1[1], p1[2]}, v[3] = {dirToP2[0], dirToP2[1], dirToP2[2]}, oldp[3], oldv[3], d[3], mid[3], dummy = 0;
+    for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+    bool signOld = std::signbit(Medium<F>::dot(d, v)), signNew;
+    auto midpointN = [&]() { for (int i = 0; i < 3; i++) mid[i] = (F) 0.5 * (p[i] + oldp[i]); return M.rif->value(mid); };
+    for (int it = 0; it < 100000; it++) {
+        for (int i = 0; i < 3; i++) { oldp[i] = p[i]; oldv[i] = v[i]; }
+        M.er_step(p, v, h0, dummy, count);
+        for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+        signNew = std::signbit(Medium<F>::dot(d, v));
+        if (!M.insideShape(p)) {
+            if (!isSensorSample || !M.sdf) return false;
+            while (nBisect > 0) {
+                nBisect--;
+                for (int i = 0; i < 3; i++) { p[i] = oldp[i]; v[i] = oldv[i]; }
+                h0 = h0 / 2;
+                M.er_step(p, v, h0, dummy, count);
+                if (M.insideShape(p)) {
+                    dist += h0;
+                    opl += h0 * midpointN();
+                    for (int i = 0; i < 3; i++) { oldp[i] = p[i]; oldv[i] = v[i]; }
+                }
+            }
+            F N[3];
+            M.sdf->gradient(p, N);
+            F nl = (F) 1 / std::sqrt(Medium<F>::dot(N, N));
+            for (int i = 0; i < 3; i++) N[i] *= nl;
+            Medium<F>::boundaryVelocity(v, N, M.rif->value(p), (F) 1.0);
+            for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+            F extra_t = -Medium<F>::dot(v, d) / Medium<F>::dot(v, v);
+            if (extra_t < 0) return false;
+            for (int i = 0; i < 3; i++) p[i] += extra_t * v[i];
+            opl += extra_t;
+            break;
+        }
+        if (signNew != signOld) {
+            while (nBisect > 0) {
+                nBisect--;
+                for (int i = 0; i < 3; i++) { p[i] = oldp[i]; v[i] = oldv[i]; }
+                h0 = h0 / 2;
+                M.er_step(p, v, h0, dummy, count);
+                for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+                signNew = std::signbit(Medium<F>::dot(d, v));
+                if (signNew == signOld) {
+                    dist += h0;
+                    opl += h0 * midpointN();
+                    for (int i = 0; i < 3; i++) { oldp[i] = p[i]; oldv[i] = v[i]; }
+                }
+            }
+            break;
+        } else {
+            dist += h0;
+            opl += h0 * midpointN();
+        }
+    }
+    for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
+    if (Medium<F>::dot(d, d) > M.tol2) return false;
+    F vl = (F) 1 / std::sqrt(Medium<F>::dot(v, v));
+    for (int i = 0; i < 3; i++) revDir[i] = -(v[i] * vl);
+    return true;
+}
+
+template <typename F>
+void connect(const Medium<F> &M, const F *p1, const F *p2, const F *dseed, bool isSensorSample, float rrweight, int maxIterations,
+             PhiloxStream &rng, ConnectionResult<F> &R) {
+    R.success = false;
+    R.weight = 1;
+    R.opticalDist = R.dist = 0;
+    R.evaluations = 0;
+    for (int i = 0; i < 3; i++) { R.dirToP2[i] = R.revDirToP1[i] = 0; R.transmittance[i] = 0; }
+    R.pdfSuccess = R.pdfFailure = 1.0f; /* failed case of eval(), :618-624 */
+    if (!(M.sdf ? M.sdf : M.rif)->insideVolumeLimits(p1)) return;
+    const F RIFp = M.rif->value(p1);
+    F x[3];
+    bool converged = false;
+    while (true) {
+        /* uniformSample, :1078-1084 + warp::squareToUniformHemisphere (src/libcore/warp.cpp:33-41) */
+        float din[3] = {(float) dseed[0], (float) dseed[1], (float) dseed[2]}, ax[3], ay[3];
+        coordinateSystem(din, ax, ay);
+        float u1 = rng.next(), u2 = rng.next();
+        float z = u1, tmp = std::sqrt(std::max(0.0f, 1.0f - z * z)), phi = (float) (2.0f * M_PI * u2);
+        float lx = cosf(phi) * tmp, ly = sinf(phi) * tmp;
+        for (int i = 0; i < 3; i++) x[i] = (F) (lx * ax[i] + ly * ay[i] + z * din[i]) * RIFp;
+        /* Levenberg-Marquardt on r(x) = p(t*) - p2, J = d r / d x (= derror^T) */
+        F r[3], Jt[9], cost, lambda = 0;
+        long cnt = 0;
+        M.computefdf(x, p1, p2, isSensorSample, r, Jt, cnt);
+        R.evaluations++;
+        cost = (F) 0.5 * Medium<F>::dot(r, r);
+        int accepted = 0;
+        for (int ev = 0; ev < 2 * maxIterations && accepted < maxIterations && !(cost < M.tol2); ev++) {
+            /* normal equations: (J^T J + lambda I) dx = -J^T r with J^T = Jt (row j of Jt = d r / d x_j) */
+            F JTJ[9], g[3], dx[3];
+            for (int a = 0; a < 3; a++) {
+                g[a] = -(Jt[3 * a] * r[0] + Jt[3 * a + 1] * r[1] + Jt[3 * a + 2] * r[2]);
+                for (int b = 0; b < 3; b++) JTJ[3 * a + b] = Jt[3 * a] * Jt[3 * b] + Jt[3 * a + 1] * Jt[3 * b + 1] + Jt[3 * a + 2] * Jt[3 * b + 2];
+            }
+            if (lambda == 0) lambda = (F) 1e-3 * std::max(std::max(JTJ[0], JTJ[4]), std::max(JTJ[8], (F) 1e-12));
+            JTJ[0] += lambda; JTJ[4] += lambda; JTJ[8] += lambda;
+            if (!solve3<F>(JTJ, g, dx)) break;
+            F xn[3] = {x[0] + dx[0], x[1] + dx[1], x[2] + dx[2]}, rn[3], Jn[9];
+            M.computefdf(xn, p1, p2, isSensorSample, rn, Jn, cnt);
+            R.evaluations++;
+            F costn = (F) 0.5 * Medium<F>::dot(rn, rn);
+            if (costn < cost) {
+                for (int i = 0; i < 3; i++) { x[i] = xn[i]; r[i] = rn[i]; }
+                for (int i = 0; i < 9; i++) Jt[i] = Jn[i];
+                cost = costn;
+                lambda = std::max(lambda / 3, (F) 1e-15);
+                accepted++;
+            } else {
+                lambda *= 4;
+                if (lambda > (F) 1e12) break;
+            }
+        }
+        if (cost < M.tol2) { converged = true; break; } /* :1121-1138 always ends with multiplicity weight 1 */
+        if (rng.next() < rrweight) R.weight = R.weight * (1 / (F) rrweight); /* :1146-1155 */
+        else break;
+    }
+    F xl = (F) 1 / std::sqrt(Medium<F>::dot(x, x));
+    for (int i = 0; i < 3; i++) R.dirToP2[i] = (x[i] * xl) * RIFp;
+    if (!converged) return;
+    if (!computePathLengths<F>(M, p1, p2, R.dirToP2, R.revDirToP1, isSensorSample, R.opticalDist, R.dist)) return;
+    R.success = true;
+    /* eval(), :585-617 */
+    const float distance = (float) R.dist;
+    float pdfSuccess = 0, pdfFailure = 0;
+    if (M.d.strategy == MER_STRATEGY_BALANCE) {
+        for (int i = 0; i < 3; i++) {
+            float t = (float) std::exp((double) (-M.sigmaT[i] * distance));
+            pdfSuccess += M.sigmaT[i] * t;
+            pdfFailure += t;
+        }
+        pdfSuccess /= 3;
+        pdfFailure /= 3;
+    } else {
+        float t = (float) std::exp((double) (-M.samplingDensity * distance));
+        pdfSuccess = M.samplingDensity * t;
+        pdfFailure = t;
+    }
+    float tmax = 0;
+    for (int i = 0; i < 3; i++) {
+        R.transmittance[i] = (float) std::exp((double) (M.sigmaT[i] * (-distance))) * (float) R.weight;
+        tmax = std::max(tmax, R.transmittance[i]);
+    }
+    R.pdfSuccess = pdfSuccess * M.weight;
+    R.pdfFailure = pdfFailure * M.weight + (1 - M.weight);
+    if (tmax < 1e-20f) for (int i = 0; i < 3; i++) R.transmittance[i] = 0;
+}
 
 /* ------------------------------------------------------------------------------------------
  * a23-a24  reconstruction filter + ImageBlock::put — src/libcore/rfilter.cpp:37-55,
@@ -1052,6 +1411,30 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
         *weight = ((Medium<F> *) h)->weight;                                                                      \
         *samplingDensity = ((Medium<F> *) h)->samplingDensity;                                                    \
     }                                                                                                             \
+    extern "C" void orc_rif_eval_hessian_world##SUF(void *h, size_t n, const F *p, F *f, F *g, F *H) {             \
+        const SplineVolume<F> *s = (const SplineVolume<F> *) h;                                                   \
+        for (size_t i = 0; i < n; i++) s->valueGradientAndHessian(p + 3 * i, f + i, g + 3 * i, H + 9 * i);        \
+    }                                                                                                             \
+    extern "C" void orc_medium_derivative_trace##SUF(void *h, size_t n, F *p, F *v, const int32_t *nsteps, F *A,   \
+                                                     F *B) {                                                      \
+        const Medium<F> *m = (const Medium<F> *) h;                                                               \
+        for (size_t i = 0; i < n; i++) {                                                                          \
+            F *a = A + 9 * i, *b = B + 9 * i;                                                                     \
+            for (int k = 0; k < 9; k++) { a[k] = 0; b[k] = (k % 4 == 0) ? 1 : 0; }                                \
+            long c = 0;                                                                                           \
+            for (int k = 0; k < nsteps[i]; k++) m->er_derivativestep(p + 3 * i, v + 3 * i, a, b, m->h, c);        \
+        }                                                                                                         \
+    }                                                                                                             \
+    extern "C" void orc_medium_connection_residual##SUF(void *h, size_t n, const F *p1, const F *p2, const F *v0,  \
+                                                        int isSensor, F *err, F *derr, int32_t *status,           \
+                                                        int32_t *nsteps) {                                        \
+        const Medium<F> *m = (const Medium<F> *) h;                                                               \
+        _Pragma("omp parallel for schedule(dynamic, 16)") for (long i = 0; i < (long) n; i++) {                   \
+            long c = 0;                                                                                           \
+            status[i] = m->computefdf(v0 + 3 * i, p1 + 3 * i, p2 + 3 * i, isSensor != 0, err + 3 * i, derr + 9 * i, c); \
+            if (nsteps) nsteps[i] = (int32_t) c;                                                                  \
+        }                                                                                                         \
+    }                                                                                                             \
     extern "C" void orc_medium_trace##SUF(void *h, size_t n, F *p, F *v, const F *dist, uint8_t *success,         \
                                           F *distSurf, F *opl, int32_t *nsteps) {                                 \
         const Medium<F> *m = (const Medium<F> *) h;                                                               \
@@ -1108,6 +1491,28 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
 
 ORC_API(float, _f)
 ORC_API(double, _d)
+
+#define ORC_CONNECT(F, SUF)                                                                                       \
+    extern "C" void orc_medium_connect##SUF(void *h, size_t n, const F *p1, const F *p2, const F *dseed, int isSensor,  \
+                                            float tol2, float rrweight, int precision, int maxIterations, uint64_t seed, \
+                                            uint8_t *success, F *dirToP2, F *revDir, F *opl, F *dist, F *weight,   \
+                                            float *transmittance, float *pdfSuccess, float *pdfFailure, int32_t *evals) { \
+        Medium<F> *m = (Medium<F> *) h;                                                                           \
+        m->tol2 = (F) tol2;                                                                                       \
+        m->boundaryprecision = precision;                                                                         \
+        _Pragma("omp parallel for schedule(dynamic, 8)") for (long i = 0; i < (long) n; i++) {                    \
+            PhiloxStream rng;                                                                                     \
+            rng.init(seed, (uint64_t) i);                                                                         \
+            ConnectionResult<F> R;                                                                                \
+            connect<F>(*m, p1 + 3 * i, p2 + 3 * i, dseed + 3 * i, isSensor != 0, rrweight, maxIterations, rng, R); \
+            success[i] = R.success;                                                                               \
+            opl[i] = R.opticalDist; dist[i] = R.dist; weight[i] = R.weight;                                       \
+            pdfSuccess[i] = R.pdfSuccess; pdfFailure[i] = R.pdfFailure; evals[i] = R.evaluations;                  \
+            for (int k = 0; k < 3; k++) { dirToP2[3 * i + k] = R.dirToP2[k]; revDir[3 * i + k] = R.revDirToP1[k]; transmittance[3 * i + k] = R.transmittance[k]; } \
+        }                                                                                                         \
+    }
+ORC_CONNECT(float, _f)
+ORC_CONNECT(double, _d)
 
 extern "C" void *orc_grid_create(const mer_volume_desc *d, const float *data) {
     GridVolume *g = new GridVolume();

@@ -236,6 +236,53 @@ class Oracle:
     def medium_destroy(self, h):
         self._fn("orc_medium_destroy")(h)
 
+    def rif_eval_hessian_world(self, h, p):
+        p = np.ascontiguousarray(p, dtype=self.dtype).reshape(-1, 3)
+        n = p.shape[0]
+        f, g, H = np.zeros(n, self.dtype), np.zeros((n, 3), self.dtype), np.zeros((n, 3, 3), self.dtype)
+        self._fn("orc_rif_eval_hessian_world")(h, C.c_size_t(n), _ptr(p, self.ct), _ptr(f, self.ct), _ptr(g, self.ct), _ptr(H, self.ct))
+        return f, g, H
+
+    def derivative_trace(self, h, p, v, nsteps):
+        p = np.array(p, dtype=self.dtype).reshape(-1, 3)
+        v = np.array(v, dtype=self.dtype).reshape(-1, 3)
+        n = p.shape[0]
+        ns = np.ascontiguousarray(np.broadcast_to(np.asarray(nsteps, np.int32), (n,)))
+        A, B = np.zeros((n, 3, 3), self.dtype), np.zeros((n, 3, 3), self.dtype)
+        self._fn("orc_medium_derivative_trace")(h, C.c_size_t(n), _ptr(p, self.ct), _ptr(v, self.ct), _ptr(ns, C.c_int32),
+                                                _ptr(A, self.ct), _ptr(B, self.ct))
+        return dict(p=p, v=v, dpdv0=A, dvdv0=B)
+
+    def connection_residual(self, h, p1, p2, v0, is_sensor=False):
+        p1 = np.ascontiguousarray(p1, dtype=self.dtype).reshape(-1, 3)
+        p2 = np.ascontiguousarray(p2, dtype=self.dtype).reshape(-1, 3)
+        v0 = np.ascontiguousarray(v0, dtype=self.dtype).reshape(-1, 3)
+        n = p1.shape[0]
+        err, J = np.zeros((n, 3), self.dtype), np.zeros((n, 3, 3), self.dtype)
+        st, ns = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._fn("orc_medium_connection_residual")(h, C.c_size_t(n), _ptr(p1, self.ct), _ptr(p2, self.ct), _ptr(v0, self.ct),
+                                                   C.c_int(1 if is_sensor else 0), _ptr(err, self.ct), _ptr(J, self.ct),
+                                                   _ptr(st, C.c_int32), _ptr(ns, C.c_int32))
+        return dict(error=err, derror=J, status=st, nsteps=ns)
+
+    def connect(self, h, p1, p2, dseed, is_sensor=False, tol2=1e-6, rrweight=1e-2, precision=3, max_iterations=20, seed=1):
+        p1 = np.ascontiguousarray(p1, dtype=self.dtype).reshape(-1, 3)
+        p2 = np.ascontiguousarray(p2, dtype=self.dtype).reshape(-1, 3)
+        ds = np.ascontiguousarray(dseed, dtype=self.dtype).reshape(-1, 3)
+        n = p1.shape[0]
+        r = dict(success=np.zeros(n, np.uint8), dir_to_p2=np.zeros((n, 3), self.dtype), rev_dir=np.zeros((n, 3), self.dtype),
+                 optical_dist=np.zeros(n, self.dtype), dist=np.zeros(n, self.dtype), weight=np.zeros(n, self.dtype),
+                 transmittance=np.zeros((n, 3), np.float32), pdf_success=np.zeros(n, np.float32), pdf_failure=np.zeros(n, np.float32),
+                 evaluations=np.zeros(n, np.int32))
+        self._fn("orc_medium_connect")(h, C.c_size_t(n), _ptr(p1, self.ct), _ptr(p2, self.ct), _ptr(ds, self.ct), C.c_int(1 if is_sensor else 0),
+                                       C.c_float(tol2), C.c_float(rrweight), C.c_int(precision), C.c_int(max_iterations), C.c_uint64(seed),
+                                       _ptr(r["success"], C.c_uint8), _ptr(r["dir_to_p2"], self.ct), _ptr(r["rev_dir"], self.ct),
+                                       _ptr(r["optical_dist"], self.ct), _ptr(r["dist"], self.ct), _ptr(r["weight"], self.ct),
+                                       _ptr(r["transmittance"], C.c_float), _ptr(r["pdf_success"], C.c_float), _ptr(r["pdf_failure"], C.c_float),
+                                       _ptr(r["evaluations"], C.c_int32))
+        r["success"] = r["success"].astype(bool)
+        return r
+
     def medium_set_sdf(self, h, sdf, aggressive=True):
         self._fn("orc_medium_set_sdf")(h, sdf, C.c_int(1 if aggressive else 0))
 

@@ -42,7 +42,9 @@ def test_struct_layouts_match_the_header(tmp_path):
               "mer_render_desc": ["width", "spp_total", "sample_stride", "seed", "cam_origin", "fov_deg", "filter",
                                   "max_depth", "env_radiance", "has_quad", "quad_radiance", "pool_paths", "steps_per_pass"],
               "mer_render_stats": ["samples", "ray_steps", "passes", "kernel_launches", "device_ms"],
-              "mer_medium_sampling_records": ["success", "t", "nsteps"]}
+              "mer_medium_sampling_records": ["success", "t", "nsteps"],
+              "mer_connection_params": ["tol2", "rrweight", "boundary_precision", "max_iterations"],
+              "mer_connection_records": ["success", "dir_to_p2", "distance", "transmittance", "evaluations"]}
     body = ['#include <stdio.h>', '#include <stddef.h>', '#include "mitsubaer_b200.h"', "int main(void){"]
     for s, fs in fields.items():
         body.append('printf("%s %%zu\\n", sizeof(%s));' % (s, s))
@@ -54,7 +56,8 @@ def test_struct_layouts_match_the_header(tmp_path):
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)], check=True)
     got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
     mirrors = {"mer_volume_desc": _abi.VolumeDesc, "mer_medium_desc": _abi.MediumDesc, "mer_render_desc": _abi.RenderDesc,
-               "mer_render_stats": _abi.RenderStats, "mer_medium_sampling_records": _abi.SamplingRecords}
+               "mer_render_stats": _abi.RenderStats, "mer_medium_sampling_records": _abi.SamplingRecords,
+               "mer_connection_params": _abi.ConnectionParams, "mer_connection_records": _abi.ConnectionRecords}
     from oracle import oracle as orc
     oracle_mirrors = {"mer_volume_desc": orc.VolumeDesc, "mer_medium_desc": orc.MediumDesc,
                       "mer_render_desc": orc.RenderDesc, "mer_render_stats": orc.RenderStats}

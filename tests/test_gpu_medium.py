@@ -389,3 +389,138 @@ def test_straight_ray_woodcock(oracle32, scale):
     pts = (oo[:1] + ts[:, None] * dv[:1]).astype(np.float32)
     tau = np.trapezoid(grid.lookupFloat(pts).astype(np.float64) * scale, ts)
     assert abs(est - np.exp(-tau)) < 4 * np.sqrt(0.25 / 40000) + 2e-3
+
+
+def test_hessian_matches_reference_golden_and_oracle(oracle32, oracle64):
+    """valueGradientAndHessian (basisspline.h:539-606): golden vectors from the reference header + oracle"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spline_ref_f32.npz"))
+    rif = mer.SplineDataSource(data=g["data"], min=g["bbox_min"], max=g["bbox_max"])
+    f, grad, H = rif.valueGradientAndHessian(g["points"])
+    dx = (g["res"] - 1) / (g["bbox_max"] - g["bbox_min"])
+    cmax = float(np.abs(g["data"]).max())
+    assert np.abs(f - g["value"]).max() <= 1e-5 * cmax
+    assert np.abs(grad - g["gradient"]).max() <= 1e-5 * cmax * dx.max()
+    # second derivatives: second differences of n over a voxel -> operand scale max|n| * dxres^2
+    assert np.abs(H - g["hessian"]).max() <= 1e-5 * cmax * dx.max() ** 2
+    assert np.allclose(H, np.transpose(H, (0, 2, 1)))
+    # and at least as close to the FLOAT=double reference as the reference's float build
+    g64 = np.load(os.path.join(os.path.dirname(__file__), "golden", "spline_ref_f64.npz"))
+    assert np.abs(H - g64["hessian"]).max() <= 1.25 * np.abs(g["hessian"] - g64["hessian"]).max() + 1e-6
+    # rotated volume: H_world = R^T H R (splinevolume.cpp:371-377)
+    data, lo, hi = make_field("smooth", (20, 22, 24))
+    th = 0.4
+    to_world = np.array([[np.cos(th), -np.sin(th), 0, 0.1], [np.sin(th), np.cos(th), 0, -0.2], [0, 0, 1, 0.05], [0, 0, 0, 1]])
+    rot = mer.SplineDataSource(data=data, min=lo, max=hi, toWorld=to_world)
+    h = oracle32.rif_create(volume_desc((20, 22, 24), lo, hi, np.linalg.inv(to_world)[:3, :]), data)
+    p = random_points_in_box(5000, 141, margin=0.35)
+    _, _, Hg = rot.valueGradientAndHessian(p)
+    _, _, Ho = oracle32.rif_eval_hessian_world(h, p)
+    assert np.abs(Hg - Ho).max() <= 1e-5 * 1.6 * (23 / (hi[2] - lo[2])) ** 2
+
+
+def test_derivative_step_and_connection_residual(oracle32, oracle64):
+    """er_derivativestep (:798-814) and computefdfBDPT (:816-939) against the restatement, float and double"""
+    props = medium_props(stepsize=5e-3, shape=("sphere", (0.0, 0.0, 0.0), 0.8))
+    data, lo, hi = make_field("smooth", 40)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    sdf_data = mer.fields.sphere_sdf((40,) * 3, lo, hi, radius=0.8).astype(np.float32)
+    sdf = mer.SplineDataSource(data=sdf_data, min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("sdf", sdf).configure()
+    d = volume_desc((40,) * 3, lo, hi)
+    outs = {}
+    n = 4000
+    p0 = (random_points_in_box(n, 151) * 0.35).astype(np.float32)
+    d0 = random_directions(n, 152)
+    v0 = d0 * rif.value(p0)[:, None]
+    nsteps = np.random.default_rng(153).integers(1, 120, n).astype(np.int32)
+    got = med.derivativeTrace(p0, v0, nsteps)
+    p2 = (p0 + d0 * (0.15 + 0.5 * np.random.default_rng(154).random((n, 1))) + 0.03 * random_directions(n, 155)).astype(np.float32)
+    res = med.connectionResidual(p0, p2, v0 * 1.7)  # |v0| != n: exercises the renormalisation chain rule
+    for name, orc in (("f32", oracle32), ("f64", oracle64)):
+        orif, osdf = orc.rif_create(d, data), orc.rif_create(d, sdf_data)
+        omed = orc.medium_create(oracle_medium_desc(props), orif)
+        orc.medium_set_sdf(omed, osdf, False)
+        ref = orc.derivative_trace(omed, p0, v0, nsteps)
+        tol = 1e-5 if name == "f32" else 2e-5
+        assert np.abs(got["p"] - ref["p"]).max() <= tol and np.abs(got["v"] - ref["v"]).max() <= 2 * tol
+        assert np.abs(got["dpdv0"] - ref["dpdv0"]).max() <= 2e-5 and np.abs(got["dvdv0"] - ref["dvdv0"]).max() <= 5e-5
+        rr = orc.connection_residual(omed, p0, p2, v0 * 1.7)
+        same = (res["status"] == rr["status"]) & (res["nsteps"] == rr["nsteps"])
+        assert same.mean() > 0.99, same.mean()
+        assert set(np.unique(res["status"])) >= {0, 1}  # both the interior and the boundary-exit branch are exercised
+        assert np.abs(res["error"] - rr["error"])[same].max() <= 5e-5
+        assert np.abs(res["derror"] - rr["derror"])[same].max() <= 2e-3 * max(1.0, np.abs(rr["derror"]).max())
+    # the Jacobian is the derivative of the residual: finite differences through the GPU entry point itself
+    sel = np.where(res["status"] == 0)[0][:200]
+    eps = 2e-3
+    J = np.zeros((sel.size, 3, 3))
+    for j in range(3):
+        dv = np.zeros(3, np.float32)
+        dv[j] = eps
+        J[:, :, j] = (med.connectionResidual(p0[sel], p2[sel], v0[sel] * 1.7 + dv)["error"].astype(np.float64) -
+                      med.connectionResidual(p0[sel], p2[sel], v0[sel] * 1.7 - dv)["error"]) / (2 * eps)
+    Ja = np.transpose(res["derror"][sel], (0, 2, 1))  # stored transposed (:936-938)
+    assert np.median(np.abs(J - Ja).max(axis=(1, 2))) < 0.02 * np.median(np.abs(Ja).max(axis=(1, 2))) + 2e-3
+
+
+def test_curved_direct_connections(oracle32, oracle64):
+    """makeDirectConnections / eval (:571-640, 1087-1163) with the Levenberg-Marquardt minimiser.
+    Parity is UNPINNED at the solver (the reference calls Ceres): validated by (1) ground truth — p2 is the end
+    point of a known eikonal ray, so the solver must recover that ray's launch direction, length and optical
+    length; (2) the residual actually reached; (3) agreement with the same algorithm restated on the CPU."""
+    props = medium_props(stepsize=5e-3, strategy="single", sigmaS=2.0, sigmaA=0.5, shape=("sphere", (0.0, 0.0, 0.0), 0.85))
+    data, lo, hi = make_field("smooth", 40)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).configure()
+    n = 3000
+    p1 = (random_points_in_box(n, 161) * 0.25).astype(np.float32)
+    d0 = random_directions(n, 162)
+    v0 = d0 * rif.value(p1)[:, None]
+    L = (0.15 + 0.25 * np.random.default_rng(163).random(n)).astype(np.float32)
+    truth = med.trace(p1, v0, L)
+    assert truth["success"].all()
+    p2 = truth["p"]
+    seeds = random_directions(n, 164) * 0.35 + d0
+    seeds = (seeds / np.linalg.norm(seeds, axis=1, keepdims=True)).astype(np.float32)
+    got = med.eval(p1, p2, seeds, seed=5)
+    ok = got["success"]
+    assert ok.mean() > 0.8, ok.mean()
+    dirn = got["dir_to_p2"] / np.linalg.norm(got["dir_to_p2"], axis=1, keepdims=True)
+    assert np.abs(np.linalg.norm(got["dir_to_p2"], axis=1) - rif.value(p1))[ok].max() < 1e-5  # |v| = n(p1)
+    # tol2 = 1e-6 => the ray passes within 1e-3 of p2: direction to ~1e-3 / L, lengths to ~1e-3
+    assert np.abs(dirn - d0)[ok].max() < 8e-3 and np.median(np.abs(dirn - d0)[ok]) < 5e-4
+    assert np.abs(got["distance"] - L)[ok].max() < 2e-3 and np.abs(got["optical_length"] - truth["opl"])[ok].max() < 4e-3
+    back = med.trace(p1[ok], got["dir_to_p2"][ok], got["distance"][ok])  # the residual actually reached
+    assert (np.linalg.norm(back["p"] - p2[ok], axis=1) < 1.5e-3).all()
+    assert np.abs(back["v"] / np.linalg.norm(back["v"], axis=1, keepdims=True) + got["rev_dir_to_p1"][ok]).max() < 5e-3
+    # eval()'s record: single strategy, sigma_t = 2.5
+    w = med.mediumSamplingWeight
+    T = np.exp(-2.5 * got["distance"][ok])
+    assert np.allclose(got["transmittance"][ok], T[:, None] * got["weight"][ok][:, None], rtol=1e-5)
+    assert np.allclose(got["pdf_success"][ok], w * 2.5 * T, rtol=1e-5) and np.allclose(got["pdf_failure"][ok], w * T + (1 - w), rtol=1e-5)
+    assert np.all(got["transmittance"][~ok] == 0) and np.all(got["pdf_success"][~ok] == 1)
+    assert set(np.round(np.log(got["weight"]) / np.log(100.0)).astype(int)) <= {0, 1, 2, 3}  # 1 / rrweight^k
+    # the same algorithm on the CPU: same successes and same measured paths
+    d = volume_desc((40,) * 3, lo, hi)
+    omed = oracle32.medium_create(oracle_medium_desc(props), oracle32.rif_create(d, data))
+    ref = oracle32.connect(omed, p1, p2, seeds, seed=5)
+    both = ok & ref["success"]
+    assert (ok == ref["success"]).mean() > 0.97 and both.mean() > 0.75
+    assert np.abs(got["distance"] - ref["dist"])[both].max() < 2e-3 and np.median(np.abs(got["distance"] - ref["dist"])[both]) < 2e-5
+    assert np.median(np.abs(got["dir_to_p2"] - ref["dir_to_p2"])[both]) < 1e-4
+    # constant index: the connection is the straight segment
+    res = 24
+    clo, chi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    flat = mer.SplineDataSource(data=np.full((res,) * 3, 1.4, np.float32), min=clo, max=chi)
+    fm = mer.HeterogeneousRefractiveMedium(medium_props(stepsize=1e-2)).addChild("rif", flat).configure()
+    q1, q2 = random_points_in_box(500, 165) * 0.5, random_points_in_box(500, 166) * 0.5
+    seg = q2 - q1
+    out = fm.eval(q1, q2, seg / np.linalg.norm(seg, axis=1, keepdims=True), seed=6)
+    s = out["success"]
+    assert s.mean() > 0.9
+    assert np.abs(out["distance"][s] - np.linalg.norm(seg, axis=1)[s]).max() < 2e-3
+    assert np.abs(out["optical_length"][s] - 1.4 * np.linalg.norm(seg, axis=1)[s]).max() < 3e-3
+    # passing within sqrt(2 tol2) of p2 bounds the direction error by ~1.4e-3 / |p2 - p1|
+    dir_err = np.abs(out["dir_to_p2"][s] / 1.4 - (seg / np.linalg.norm(seg, axis=1, keepdims=True))[s]).max(axis=1)
+    assert (dir_err * np.linalg.norm(seg, axis=1)[s]).max() < 2.5e-3
