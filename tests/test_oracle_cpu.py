@@ -189,3 +189,54 @@ def test_render_white_furnace_and_sharding(oracle32):
     parts = [oracle32.render(omed, oracle_render_desc(scene, rr_depth=1000, sample_begin=r, sample_stride=3)) for r in range(3)]
     assert sum(p[1].samples for p in parts) == st.samples and sum(p[1].ray_steps for p in parts) == st.ray_steps
     assert np.allclose(sum(p[0] for p in parts), film, rtol=1e-5, atol=1e-6)
+
+
+def test_hessian_and_derivative_step_consistency(oracle64):
+    """a25 building blocks of the oracle: the spline Hessian is the derivative of its gradient, and the Jacobians
+    carried by er_derivativestep (:798-814) are the derivatives of the end state w.r.t. the launch velocity"""
+    data, lo, hi = make_field("smooth", 36)
+    orif = oracle64.rif_create(volume_desc((36,) * 3, lo, hi), data)
+    p = random_points_in_box(200, 1, margin=0.4).astype(np.float64)
+    f, g, H = oracle64.rif_eval_hessian(orif, p)
+    eps = 1e-5
+    for j in range(3):
+        dp = np.zeros(3)
+        dp[j] = eps
+        gp, gm = oracle64.rif_eval(orif, p + dp, 1)[1], oracle64.rif_eval(orif, p - dp, 1)[1]
+        assert np.abs((gp - gm) / (2 * eps) - H[:, :, j]).max() < 1e-4
+    med = oracle64.medium_create(oracle_medium_desc(medium_props(stepsize=5e-3)), orif)
+    d0 = random_directions(200, 2).astype(np.float64)
+    v0 = d0 * oracle64.rif_eval(orif, p, 0)[0][:, None]
+    r = oracle64.derivative_trace(med, p, v0, 50)
+    plain = oracle64.trace(med, p, v0, np.full(200, 50 * np.float64(np.float32(5e-3))))
+    assert np.abs(r["p"] - plain["p"]).max() < 1e-9  # same trajectory as er_step (the last step of trace() is a ~0 remainder)
+    for j in range(3):
+        dv = np.zeros(3)
+        dv[j] = 1e-6
+        rp, rm = oracle64.derivative_trace(med, p, v0 + dv, 50), oracle64.derivative_trace(med, p, v0 - dv, 50)
+        # transported Jacobians agree with differences of the discrete map to O(h)
+        assert np.abs((rp["p"] - rm["p"]) / 2e-6 - r["dpdv0"][:, :, j]).max() < 2e-3
+        assert np.abs((rp["v"] - rm["v"]) / 2e-6 - r["dvdv0"][:, :, j]).max() < 2e-3
+
+
+def test_curved_connection_recovers_known_ray(oracle64):
+    """makeDirectConnections with the LM minimiser: p2 is the end point of a known eikonal ray"""
+    data, lo, hi = make_field("smooth", 36)
+    orif = oracle64.rif_create(volume_desc((36,) * 3, lo, hi), data)
+    med = oracle64.medium_create(oracle_medium_desc(medium_props(stepsize=5e-3, strategy="single")), orif)
+    n = 150
+    p1 = (random_points_in_box(n, 3) * 0.3).astype(np.float64)
+    d0 = random_directions(n, 4).astype(np.float64)
+    v0 = d0 * oracle64.rif_eval(orif, p1, 0)[0][:, None]
+    truth = oracle64.trace(med, p1, v0, np.full(n, 0.4))
+    assert truth["success"].all()
+    seeds = random_directions(n, 5) * 0.3 + d0
+    seeds /= np.linalg.norm(seeds, axis=1, keepdims=True)
+    r = oracle64.connect(med, p1, truth["p"], seeds, seed=9)
+    ok = r["success"]
+    assert ok.mean() > 0.8
+    dirn = r["dir_to_p2"] / np.linalg.norm(r["dir_to_p2"], axis=1, keepdims=True)
+    assert np.abs(dirn - d0)[ok].max() < 6e-3 and np.abs(r["dist"] - 0.4)[ok].max() < 2e-3
+    assert np.abs(r["optical_dist"] - truth["opl"])[ok].max() < 4e-3
+    res = oracle64.connection_residual(med, p1[ok], truth["p"][ok], r["dir_to_p2"][ok])
+    assert (0.5 * (res["error"] ** 2).sum(axis=1) < 1e-6).all() and (res["status"] == 0).all()
