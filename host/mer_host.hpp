@@ -218,13 +218,27 @@ struct HGPhaseFunction : Object { /* <phase type="hg"> */
     }
 };
 
+struct SurfaceBsdf : Object { /* <bsdf> on the container: "null" (index-matched) or "hdielectric" (src/bsdfs/hdielectric.cpp) */
+    const char *className() const override { return "SurfaceBsdf"; }
+    void addChild(const std::string &, ObjectRef) override {}
+    void configure() override { /* specularReflectance / specularTransmittance other than 1 are not carried */
+        for (const char *n : {"specularReflectance", "specularTransmittance"})
+            if (props.has(n)) { Spectrum3 v = props.getSpectrum(n, 1.0f); if (v.c[0] != 1 || v.c[1] != 1 || v.c[2] != 1) logError(std::string("hdielectric: ") + n + " must be 1 on this path"); }
+    }
+};
+
 struct Shape : Object { /* the medium's container: <shape type="cube"|"sphere"> */
     int shapeType = MER_SHAPE_BOX;
+    int boundary = MER_BOUNDARY_INDEX_MATCHED;
     float params[6] = {-1, -1, -1, 1, 1, 1};
     ObjectRef interior;
     const char *className() const override { return "Shape"; }
     void addChild(const std::string &name, ObjectRef child) override {
         if (name == "interior") interior = child;
+        else if (auto b = std::dynamic_pointer_cast<SurfaceBsdf>(child)) {
+            if (b->props.pluginName == "hdielectric") boundary = MER_BOUNDARY_HDIELECTRIC;
+            else if (b->props.pluginName != "null") logError("Shape: the container's bsdf must be \"null\" or \"hdielectric\" on this path (got \"" + b->props.pluginName + "\")");
+        }
         else if (name == "exterior" || std::string(child->className()) == "Ignored") { /* bsdf, exterior medium: not on this path */ }
         else logError("Shape: Invalid child node! (\"" + name + "\")");
     }
@@ -298,6 +312,7 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
     void attach(const Shape &shape) {
         desc.shape_type = shape.shapeType;
         for (int i = 0; i < 6; i++) desc.shape[i] = shape.params[i];
+        desc.boundary = shape.boundary;
         desc.hg_g = phase ? phase->g : 0.0f; /* Medium::configure: isotropic default */
         if (dryRun()) return;
         merCheck(mer_medium_create(&desc, rif->handle, density ? density->handle : nullptr, &handle));

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 1
+#define MER_ABI_VERSION 2
 
 enum mer_status {
     MER_OK = 0,
@@ -151,7 +151,15 @@ typedef struct mer_medium_desc {
      * sigma_s = albedo * sigma_t, sampled by Woodcock tracking ALONG the curved ray. */
     float density_scale;
     float albedo[3];
+    /* BSDF of the container surface (the medium's shape):
+     *   MER_BOUNDARY_INDEX_MATCHED  null surface, rays pass straight through (volpath.cpp:287-296)
+     *   MER_BOUNDARY_HDIELECTRIC    <bsdf type="hdielectric">: smooth dielectric whose eta is the RIF at the hit
+     *                               point, exterior index 1 (src/bsdfs/hdielectric.cpp:115-125, 244-300;
+     *                               fresnelDielectricExt src/libcore/util.cpp:665-695) */
+    int32_t boundary;
 } mer_medium_desc;
+
+enum mer_boundary { MER_BOUNDARY_INDEX_MATCHED = 0, MER_BOUNDARY_HDIELECTRIC = 1 };
 
 typedef struct mer_medium mer_medium; /* <medium type="heterogeneousrefractive"> */
 

@@ -17,6 +17,7 @@ EVAL_VALUE, EVAL_GRADIENT, EVAL_VALUE_AND_GRADIENT = 0, 1, 2
 SHAPE_BOX, SHAPE_SPHERE = 0, 1
 STRATEGY_BALANCE, STRATEGY_SINGLE, STRATEGY_MANUAL, STRATEGY_MAXIMUM = 0, 1, 2, 3
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
+BOUNDARY_INDEX_MATCHED, BOUNDARY_HDIELECTRIC = 0, 1
 
 
 class MerError(RuntimeError):
@@ -36,7 +37,7 @@ class MediumDesc(C.Structure):
     _fields_ = [("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3), ("stepsize", C.c_float),
                 ("medium_sampling_weight", C.c_float), ("strategy", C.c_int32), ("channel", C.c_int32),
                 ("sampling_density", C.c_float), ("shape_type", C.c_int32), ("shape", C.c_float * 6),
-                ("hg_g", C.c_float), ("density_scale", C.c_float), ("albedo", C.c_float * 3)]
+                ("hg_g", C.c_float), ("density_scale", C.c_float), ("albedo", C.c_float * 3), ("boundary", C.c_int32)]
 
 
 class SamplingRecords(C.Structure):

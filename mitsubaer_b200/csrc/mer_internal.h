@@ -36,7 +36,7 @@ struct mer_grid {
 struct RenderScratch {
     std::mutex lock; /* mer_render* calls on one device are serialised */
     size_t poolBytes = 0;
-    void *pool[12] = {nullptr};
+    void *pool[14] = {nullptr};
     unsigned *nOut = nullptr;
     unsigned long long *counters = nullptr;
     unsigned long long *hostPinned = nullptr;

@@ -340,6 +340,7 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
     MER_REQUIRE(desc->hg_g > -1.0f && desc->hg_g < 1.0f,
                 "The asymmetry parameter must lie in the interval (-1, 1)!"); /* hg.cpp:50-52 */
     MER_REQUIRE(desc->shape_type == MER_SHAPE_BOX || desc->shape_type == MER_SHAPE_SPHERE, "unknown shape type");
+    MER_REQUIRE(desc->boundary == MER_BOUNDARY_INDEX_MATCHED || desc->boundary == MER_BOUNDARY_HDIELECTRIC, "unknown boundary type");
     if (desc->strategy == MER_STRATEGY_MAXIMUM)
         return mer::fail(MER_ERR_UNSUPPORTED, "strategy 'maximum' (MaxExpDist) is not carried by this path");
     MER_REQUIRE(desc->strategy >= MER_STRATEGY_BALANCE && desc->strategy <= MER_STRATEGY_MANUAL,

@@ -12,6 +12,8 @@
  *   ImageBlock::put                      include/mitsuba/render/imageblock.h:124-190
  *   ReconstructionFilter::configure      src/libcore/rfilter.cpp:37-55, src/rfilters/{gaussian,box}.cpp
  *   HDRFilm::develop                     src/films/hdrfilm.cpp:527-540
+ *   HSmoothDielectric::sample            src/bsdfs/hdielectric.cpp:115-125, 244-300 (container surface whose eta is the
+ *                                        RIF at the hit point; fresnelDielectricExt src/libcore/util.cpp:665-695)
  *
  * Structure: the CPU's recursive per-pixel loop becomes a WAVEFRONT over a pool
  * of path slots.  One launch ("pass") advances every live path by a bounded number of
@@ -46,10 +48,11 @@ enum PathKind : int {
     E_REACHED = 6, /* trace() returned true */
     E_EXIT = 7,  /* trace()/traceTillBoundary() left the shape */
     E_NEW = 8,   /* needs a new camera sample */
-    K_DEAD = 9
+    E_SURFACE = 9, /* at the container surface with the field known: dielectric interaction (hdielectric boundary) */
+    K_DEAD = 10
 };
 
-enum { FLAG_TB = 1, FLAG_MOVED = 2 };
+enum { FLAG_TB = 1, FLAG_MOVED = 2, FLAG_OUTWARD = 4 /* reached the surface from inside */ };
 
 enum { ST_SAMPLES = 0, ST_STEPS, ST_SCATTER, ST_NULL, ST_EXIT, ST_NONFINITE, ST_COUNT };
 
@@ -61,6 +64,7 @@ struct PathPool {
     float4 *q3; /* rem, sd, (int) stepsLeft, (int) depth */
     uint4 *q4;  /* kind | flags<<8, rng draw index, pixel, sample index */
     float4 *q5; /* n(p), grad n(p): the field at p carried by the fused stepper */
+    float4 *q6; /* product of the surface BSDFs' relative indices (RR), unused x3; hdielectric boundary only */
 };
 
 struct RenderParams {
@@ -89,7 +93,7 @@ struct Lane {
     float n;
     float3 G;
     float thr[3];
-    float refStart, segDist, distSurf, rem, sd;
+    float refStart, segDist, distSurf, rem, sd, etaPath;
     int stepsLeft, depth, kind, flags;
     PathRng rng;
     unsigned pixel, sample; /* sample id = pixel * sppTotal + sample */
@@ -134,6 +138,82 @@ __device__ __forceinline__ bool intersect_quad(const RenderParams &P, float3 o, 
     float3 q = f3(o.x + t * d.x - P.quadO[0], o.y + t * d.y - P.quadO[1], o.z + t * d.z - P.quadO[2]);
     float a = dot3(q, u) / dot3(u, u), b = dot3(q, v) / dot3(v, v);
     return a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f;
+}
+
+/* fresnelDielectricExt, src/libcore/util.cpp:665-695 */
+__device__ __forceinline__ float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
+    if (eta == 1.0f) { cosThetaT_ = -cosThetaI_; return 0.0f; }
+    const float scale = (cosThetaI_ > 0.0f) ? __fdiv_rn(1.0f, eta) : eta;
+    const float cosThetaTSqr = __fsub_rn(1.0f, __fmul_rn(__fsub_rn(1.0f, __fmul_rn(cosThetaI_, cosThetaI_)), __fmul_rn(scale, scale)));
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    const float cosThetaI = fabsf(cosThetaI_), cosThetaT = __fsqrt_rn(cosThetaTSqr);
+    const float ect = __fmul_rn(eta, cosThetaT), eci = __fmul_rn(eta, cosThetaI);
+    const float Rs = __fdiv_rn(__fsub_rn(cosThetaI, ect), __fadd_rn(cosThetaI, ect));
+    const float Rp = __fdiv_rn(__fsub_rn(eci, cosThetaT), __fadd_rn(eci, cosThetaT));
+    cosThetaT_ = (cosThetaI_ > 0.0f) ? -cosThetaT : cosThetaT;
+    return __fmul_rn(0.5f, __fadd_rn(__fmul_rn(Rs, Rs), __fmul_rn(Rp, Rp)));
+}
+
+/* outward unit normal of the container at a surface point */
+__device__ __forceinline__ float3 shape_normal(const MediumDev &M, float3 p) {
+    if (M.shapeType == MER_SHAPE_SPHERE) {
+        float3 d = f3(p.x - M.shape[0], p.y - M.shape[1], p.z - M.shape[2]);
+        float l = 1.0f / sqrtf(dot3(d, d));
+        return f3(d.x * l, d.y * l, d.z * l);
+    }
+    const float pp[3] = {p.x, p.y, p.z};
+    int axis = 0;
+    float best = INFINITY, sign = 1.0f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float a = fabsf(pp[i] - M.shape[i]), b = fabsf(pp[i] - M.shape[3 + i]);
+        if (a < best) { best = a; axis = i; sign = -1.0f; }
+        if (b < best) { best = b; axis = i; sign = 1.0f; }
+    }
+    return f3(axis == 0 ? sign : 0.0f, axis == 1 ? sign : 0.0f, axis == 2 ? sign : 0.0f);
+}
+
+/* distance along a straight ray from a point inside the container to its surface (edge.cpp:45-67 re-finds the
+ * surface point of a curved segment with a straight ray from the last interior point) */
+__device__ __forceinline__ float exit_distance(const MediumDev &M, float3 o, float3 d) {
+    if (M.shapeType == MER_SHAPE_SPHERE) {
+        float3 oc = f3(o.x - M.shape[0], o.y - M.shape[1], o.z - M.shape[2]);
+        float b = dot3(oc, d), c = dot3(oc, oc) - M.shape[3] * M.shape[3];
+        float disc = b * b - c;
+        return disc > 0.0f ? fmaxf(-b + sqrtf(disc), 0.0f) : 0.0f;
+    }
+    float t1 = INFINITY;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (dd[i] == 0.0f) continue;
+        float inv = 1.0f / dd[i];
+        float ta = (M.shape[i] - oo[i]) * inv, tb = (M.shape[3 + i] - oo[i]) * inv;
+        t1 = fminf(t1, fmaxf(ta, tb));
+    }
+    return fmaxf(t1, 0.0f);
+}
+
+/* HSmoothDielectric::sample (hdielectric.cpp:244-300) in ERadiance mode with both components: d is the unit
+ * direction of travel, N the outward normal, eta the RIF at the hit point.  Returns true for transmission. */
+__device__ __forceinline__ bool hdielectric_sample(float3 d, float3 N, float eta, float u, float3 &dOut, float &weight,
+                                                   float &etaScale) {
+    const float wiN = -dot3(d, N); /* Frame::cosTheta(wi), wi = -d */
+    float cosThetaT;
+    const float F = fresnel_dielectric_ext(wiN, cosThetaT, eta);
+    if (u <= F) {
+        dOut = f3(d.x + 2.0f * wiN * N.x, d.y + 2.0f * wiN * N.y, d.z + 2.0f * wiN * N.z);
+        weight = 1.0f;
+        etaScale = 1.0f;
+        return false;
+    }
+    const float invEta = __fdiv_rn(1.0f, eta), scale = -(cosThetaT < 0.0f ? invEta : eta);
+    dOut = f3(scale * (-d.x - wiN * N.x) + cosThetaT * N.x, scale * (-d.y - wiN * N.y) + cosThetaT * N.y,
+              scale * (-d.z - wiN * N.z) + cosThetaT * N.z);
+    const float factor = cosThetaT < 0.0f ? invEta : eta; /* radiance scaling, :262-268 */
+    weight = __fmul_rn(factor, factor);
+    etaScale = cosThetaT < 0.0f ? eta : invEta;
+    return true;
 }
 
 /* ImageBlock::put (imageblock.h:144-190) onto the global film with red.global.add.f32 */
@@ -218,7 +298,9 @@ __device__ __noinline__ void edge_weight(const MediumDev &M, float sd, float d, 
         edge[c] = success ? __fdiv_rn(__fmul_rn(M.sigmaS[c], T[c]), ps) : __fdiv_rn(T[c], pf);
 }
 
-/* Everything that is not a leapfrog step.  Runs until the lane is steppable again or dead. */
+/* Everything that is not a leapfrog step.  Runs until the lane is steppable again or dead.
+ * DIELECTRIC selects the container surface: false = index-matched null surface, true = hdielectric. */
+template <bool DIELECTRIC>
 __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, unsigned *st) {
     const MediumDev &M = P.M;
     const float zero[3] = {0.f, 0.f, 0.f};
@@ -258,7 +340,8 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             if (!hitBox) { finish_sample(P, L, P.env, 0.0f, st); continue; }
             L.depth = 1;
             if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
-            L.depth = 2; /* index-matched container surface, volpath.cpp:287-296 */
+            if (!DIELECTRIC) L.depth = 2; /* index-matched container surface, volpath.cpp:287-296 */
+            L.etaPath = 1.0f;
             L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
             L.v = d;
             L.thr[0] = L.thr[1] = L.thr[2] = 1.0f;
@@ -286,6 +369,34 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 }
             }
             begin_trace(P, L, dist);
+        } else if (DIELECTRIC && L.kind == E_SURFACE) {
+            /* ---- container surface with a dielectric BSDF; L.v = unit direction of travel, L.n = RIF at the hit point */
+            const float3 N = shape_normal(M, L.p);
+            const float u = L.rng.next();
+            L.rng.next(); /* the BSDF sample is a Point2 */
+            float3 dOut;
+            float w, es;
+            const bool transmitted = hdielectric_sample(L.v, N, L.n, u, dOut, w, es);
+#pragma unroll
+            for (int c = 0; c < 3; c++) L.thr[c] *= w;
+            L.etaPath *= es;
+            L.v = dOut;
+            const bool inside = (L.flags & FLAG_OUTWARD) ? !transmitted : transmitted;
+            L.flags &= ~FLAG_OUTWARD;
+            if (!inside) { /* rayIntersectAndLookForEmitter with a delta BSDF: MIS weight 1, volpath.cpp:300-320 */
+                float tq;
+                const float *Le = intersect_quad(P, L.p, dOut, tq) ? P.quadLe : P.env;
+                float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
+                finish_sample(P, L, rad, 1.0f, st);
+                continue;
+            }
+            if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
+                float q = fminf(fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2])) * L.etaPath * L.etaPath, 0.95f);
+                if (L.rng.next() >= q) { finish_sample(P, L, zero, 1.0f, st); continue; }
+#pragma unroll
+                for (int c = 0; c < 3; c++) L.thr[c] /= q;
+            }
+            L.kind = E_BEGIN;
         } else {
             /* ---- end of a path edge */
             bool scatter = false;
@@ -326,7 +437,9 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 float u1 = L.rng.next(), u2 = L.rng.next();
                 L.v = hg_sample_dev(M.g, wi, u1, u2);
                 if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
-                    float q = fminf(fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2])), 0.95f);
+                    float q = fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2]));
+                    if (DIELECTRIC) q *= L.etaPath * L.etaPath;
+                    q = fminf(q, 0.95f);
                     if (L.rng.next() >= q) { finish_sample(P, L, zero, 1.0f, st); continue; }
 #pragma unroll
                     for (int c = 0; c < 3; c++) L.thr[c] /= q;
@@ -337,8 +450,16 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
 #pragma unroll
                 for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
                 if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
-                L.depth++;
                 float3 d = f3(L.v.x * vinv, L.v.y * vinv, L.v.z * vinv);
+                if (DIELECTRIC) { /* move to the surface point and fetch the field there, then E_SURFACE */
+                    const float te = exit_distance(M, L.p, d);
+                    L.p = f3(L.p.x + te * d.x, L.p.y + te * d.y, L.p.z + te * d.z);
+                    L.v = d;
+                    L.flags |= FLAG_OUTWARD;
+                    L.kind = K_ENTRY;
+                    continue;
+                }
+                L.depth++;
                 float tq;
                 const float *Le = intersect_quad(P, L.p, d, tq) ? P.quadLe : P.env;
                 float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
@@ -348,7 +469,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
     }
 }
 
-template <int MODE>
+template <int MODE, bool DIELECTRIC>
 __global__ void __launch_bounds__(128, MER_RENDER_MIN_BLOCKS)
 k_render_pass(const __grid_constant__ RenderParams P) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -372,11 +493,13 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.rng.init(P.seed, (unsigned long long) e.z * (unsigned long long) P.sppTotal + e.w, e.y);
         float4 fg = P.in.q5[tid];
         L.n = fg.x; L.G = f3(fg.y, fg.z, fg.w);
+        L.etaPath = DIELECTRIC ? P.in.q6[tid].x : 1.0f;
     } else {
         L.p = L.v = L.G = f3(0.f, 0.f, 0.f);
         L.n = 1.0f;
         L.thr[0] = L.thr[1] = L.thr[2] = 0.0f;
         L.refStart = L.segDist = L.distSurf = L.rem = L.sd = 0.0f;
+        L.etaPath = 1.0f;
         L.stepsLeft = L.depth = L.flags = 0;
         L.pixel = L.sample = 0;
         L.rng.init(P.seed, 0ULL, 0u);
@@ -422,7 +545,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
                     next = inside ? E_REACHED : K_BACKR;
                     if (inside) L.distSurf += L.rem;
                 } else if (kind == K_ENTRY) {
-                    next = E_BEGIN;
+                    next = DIELECTRIC ? E_SURFACE : E_BEGIN;
                 } else {
                     if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= h; /* :761 */
                     next = E_EXIT;
@@ -433,7 +556,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
             }
         } else if (mw != 0u) {
             /* ---------------- event phase: scatter / exit / regenerate for every waiting lane at once */
-            if (waiting) handle_events(P, L, st);
+            if (waiting) handle_events<DIELECTRIC>(P, L, st);
         } else {
             break; /* budget exhausted (or nobody alive) and nothing waiting */
         }
@@ -453,6 +576,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         P.out.q3[o] = make_float4(L.rem, L.sd, __int_as_float(L.stepsLeft), __int_as_float(L.depth));
         P.out.q4[o] = make_uint4((unsigned) L.kind | ((unsigned) L.flags << 8), L.rng.k, L.pixel, L.sample);
         P.out.q5[o] = make_float4(L.n, L.G.x, L.G.y, L.G.z);
+        if (DIELECTRIC) P.out.q6[o] = make_float4(L.etaPath, 0.f, 0.f, 0.f);
     }
 
     /* ---------------- statistics: warp reduce, one atomic per warp and counter */
@@ -566,7 +690,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     const size_t qBytes = (size_t) pool * 16;
     if (S.poolBytes < qBytes) {
         S.release();
-        for (int i = 0; i < 12; i++) MER_CUDA(cudaMalloc(&S.pool[i], qBytes));
+        for (int i = 0; i < 14; i++) MER_CUDA(cudaMalloc(&S.pool[i], qBytes));
         S.poolBytes = qBytes;
         MER_CUDA(cudaMalloc(&S.nOut, sizeof(unsigned)));
         MER_CUDA(cudaMalloc(&S.counters, (1 + ST_COUNT) * sizeof(unsigned long long)));
@@ -574,8 +698,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         MER_CUDA(cudaEventCreate(&S.ev0));
         MER_CUDA(cudaEventCreate(&S.ev1));
     }
-    PathPool A = {(float4 *) S.pool[0], (float4 *) S.pool[1], (float4 *) S.pool[2], (float4 *) S.pool[3], (uint4 *) S.pool[4], (float4 *) S.pool[5]};
-    PathPool B = {(float4 *) S.pool[6], (float4 *) S.pool[7], (float4 *) S.pool[8], (float4 *) S.pool[9], (uint4 *) S.pool[10], (float4 *) S.pool[11]};
+    PathPool A = {(float4 *) S.pool[0], (float4 *) S.pool[1], (float4 *) S.pool[2], (float4 *) S.pool[3], (uint4 *) S.pool[4], (float4 *) S.pool[5], (float4 *) S.pool[12]};
+    PathPool B = {(float4 *) S.pool[6], (float4 *) S.pool[7], (float4 *) S.pool[8], (float4 *) S.pool[9], (uint4 *) S.pool[10], (float4 *) S.pool[11], (float4 *) S.pool[13]};
     MER_CUDA(cudaMemsetAsync(S.counters, 0, (1 + ST_COUNT) * sizeof(unsigned long long), stream));
     P.nOut = S.nOut;
     P.sampleCounter = S.counters;
@@ -593,10 +717,14 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         P.nIn = nLive;
         MER_CUDA(cudaMemsetAsync(S.nOut, 0, sizeof(unsigned), stream));
         const unsigned blocks = (threads + TPB - 1) / TPB;
-        if (m->rif->mode == MER_RIF_TRICUBIC)
-            MER_LAUNCH(k_render_pass<MER_RIF_TRICUBIC>, blocks, TPB, 0, stream, P);
-        else
-            MER_LAUNCH(k_render_pass<MER_RIF_TRILINEAR_PACKED>, blocks, TPB, 0, stream, P);
+        const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC;
+        if (m->rif->mode == MER_RIF_TRICUBIC) {
+            if (dielectric) MER_LAUNCH((k_render_pass<MER_RIF_TRICUBIC, true>), blocks, TPB, 0, stream, P);
+            else MER_LAUNCH((k_render_pass<MER_RIF_TRICUBIC, false>), blocks, TPB, 0, stream, P);
+        } else {
+            if (dielectric) MER_LAUNCH((k_render_pass<MER_RIF_TRILINEAR_PACKED, true>), blocks, TPB, 0, stream, P);
+            else MER_LAUNCH((k_render_pass<MER_RIF_TRILINEAR_PACKED, false>), blocks, TPB, 0, stream, P);
+        }
         launches++;
         passes++;
         /* the only host<->device traffic of a pass: 12 bytes telling the host how to size the next one */

@@ -330,6 +330,10 @@ class HeterogeneousRefractiveMedium:
         d.hg_g = self.phase.g if self.phase is not None else 0.0  # Medium::configure: isotropic default
         d.density_scale = float(p.get("densityScale", p.get("scale", 1.0))) if self.density is not None else 0.0
         d.albedo[:] = [float(x) for x in _spectrum(p.get("albedo", 0.0))]
+        bsdf = str(p.get("bsdf", "null"))  # the container shape's <bsdf>: "null" | "hdielectric"
+        if bsdf not in ("null", "hdielectric"):
+            raise _abi.MerError(_abi.MER_ERR_INVALID, 'the container\'s bsdf must be "null" or "hdielectric"')
+        d.boundary = _abi.BOUNDARY_HDIELECTRIC if bsdf == "hdielectric" else _abi.BOUNDARY_INDEX_MATCHED
         h = C.c_void_p()
         check(lib.mer_medium_create(C.byref(d), self.rif.handle, self.density.handle if self.density else None,
                                     C.byref(h)))

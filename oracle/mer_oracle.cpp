@@ -1177,6 +1177,77 @@ inline bool intersectQuad(const mer_render_desc &r, const float o[3], const floa
  * grid the free flight is Woodcock tracking (src/medium/heterogeneous.cpp:613-658) along the
  * curved ray (new composition, R2).
  * ------------------------------------------------------------------------------------------ */
+/* fresnelDielectricExt, src/libcore/util.cpp:665-695 */
+inline float fresnelDielectricExt(float cosThetaI_, float &cosThetaT_, float eta) {
+    if (eta == 1) { cosThetaT_ = -cosThetaI_; return 0.0f; }
+    float scale = (cosThetaI_ > 0) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    float cosThetaI = std::abs(cosThetaI_), cosThetaT = std::sqrt(cosThetaTSqr);
+    float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+
+/* outward unit normal of the container at a surface point */
+inline void shapeNormal(const mer_medium_desc &m, const float p[3], float N[3]) {
+    if (m.shape_type == MER_SHAPE_SPHERE) {
+        float d[3] = {p[0] - m.shape[0], p[1] - m.shape[1], p[2] - m.shape[2]};
+        float l = 1.0f / std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int i = 0; i < 3; i++) N[i] = d[i] * l;
+        return;
+    }
+    int axis = 0;
+    float best = std::numeric_limits<float>::infinity(), sign = 1;
+    for (int i = 0; i < 3; i++) {
+        float a = std::abs(p[i] - m.shape[i]), b = std::abs(p[i] - m.shape[3 + i]);
+        if (a < best) { best = a; axis = i; sign = -1; }
+        if (b < best) { best = b; axis = i; sign = 1; }
+    }
+    N[0] = N[1] = N[2] = 0;
+    N[axis] = sign;
+}
+
+/* distance along a straight ray from a point inside the container to its surface */
+inline float exitDistance(const mer_medium_desc &m, const float o[3], const float d[3]) {
+    if (m.shape_type == MER_SHAPE_SPHERE) {
+        float oc[3] = {o[0] - m.shape[0], o[1] - m.shape[1], o[2] - m.shape[2]};
+        float b = oc[0] * d[0] + oc[1] * d[1] + oc[2] * d[2], c = oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2] - m.shape[3] * m.shape[3];
+        float disc = b * b - c;
+        return disc > 0 ? std::max(-b + std::sqrt(disc), 0.0f) : 0.0f;
+    }
+    float t1 = std::numeric_limits<float>::infinity();
+    for (int i = 0; i < 3; i++) {
+        if (d[i] == 0) continue;
+        float inv = 1.0f / d[i];
+        float ta = (m.shape[i] - o[i]) * inv, tb = (m.shape[3 + i] - o[i]) * inv;
+        t1 = std::min(t1, std::max(ta, tb));
+    }
+    return std::max(t1, 0.0f);
+}
+
+/* HSmoothDielectric::sample (src/bsdfs/hdielectric.cpp:244-300), ERadiance mode, both components enabled.
+ * d: unit direction of travel, N: outward normal, eta = RIF at the hit point.  Returns true for transmission. */
+inline bool hdielectricSample(const float d[3], const float N[3], float eta, float u, float dOut[3], float &weight, float &etaScale) {
+    float wiN = -(d[0] * N[0] + d[1] * N[1] + d[2] * N[2]); /* Frame::cosTheta(wi), wi = -d */
+    float cosThetaT, F = fresnelDielectricExt(wiN, cosThetaT, eta);
+    if (u <= F) { /* reflect(wi) = (-wi.x, -wi.y, wi.z) */
+        for (int i = 0; i < 3; i++) dOut[i] = d[i] + 2 * wiN * N[i];
+        weight = 1.0f;
+        etaScale = 1.0f;
+        return false;
+    }
+    float invEta = 1 / eta, scale = -(cosThetaT < 0 ? invEta : eta);
+    for (int i = 0; i < 3; i++) { /* (scale * wi.x, scale * wi.y, cosThetaT) in the local frame with z = N */
+        float wiT = -d[i] - wiN * N[i];
+        dOut[i] = scale * wiT + cosThetaT * N[i];
+    }
+    float factor = cosThetaT < 0 ? invEta : eta; /* radiance scaling, :262-268 */
+    weight = factor * factor;
+    etaScale = cosThetaT < 0 ? eta : invEta;
+    return true;
+}
+
 struct Stats {
     uint64_t samples = 0, raySteps = 0, scatter = 0, nullColl = 0, exits = 0, nonfinite = 0;
 };
@@ -1186,8 +1257,9 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         float L[3], float &alpha, Stats &st) {
     L[0] = L[1] = L[2] = 0;
     alpha = 0;
-    float thr[3] = {1, 1, 1};
+    float thr[3] = {1, 1, 1}, etaPath = 1.0f;
     int depth = 1;
+    const bool dielectric = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
     float tBox, tQuad;
     bool hitBox = intersectShape(M.d, o, dcam, tBox);
     bool hitQuad = intersectQuad(R, o, dcam, tQuad);
@@ -1201,11 +1273,48 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         return;
     }
     alpha = 1;
-    /* index-matched container surface: null BSDF, depth++ without RR (volpath.cpp:287-296) */
-    if (R.max_depth != -1 && depth >= R.max_depth) return;
-    depth++;
+    if (R.max_depth != -1 && depth >= R.max_depth) return; /* volpath.cpp:200-201 */
     F p[3], dir[3];
     for (int i = 0; i < 3; i++) { p[i] = (F) (o[i] + tBox * dcam[i]); dir[i] = (F) dcam[i]; }
+
+    /* straight escape from point q in direction e: emitters are gathered by hitting them */
+    auto escape = [&](const float q[3], const float e[3]) {
+        float tq;
+        const float *Le = intersectQuad(R, q, e, tq) ? R.quad_radiance : R.env_radiance;
+        for (int i = 0; i < 3; i++) L[i] += thr[i] * Le[i];
+    };
+    /* Russian roulette of volpath.cpp:326-336 (eta = product of the BSDFs' relative indices) */
+    auto roulette = [&]() {
+        if (depth++ >= R.rr_depth) {
+            float q = std::min(std::max(thr[0], std::max(thr[1], thr[2])) * etaPath * etaPath, 0.95f);
+            if (rng.next() >= q) return false;
+            for (int i = 0; i < 3; i++) thr[i] /= q;
+        }
+        return true;
+    };
+    /* container surface at p (travelling along dir): returns true when the path continues INSIDE the medium */
+    auto surface = [&](bool fromOutside) {
+        float pf[3] = {(float) p[0], (float) p[1], (float) p[2]}, df[3] = {(float) dir[0], (float) dir[1], (float) dir[2]};
+        if (!dielectric) { /* null BSDF: depth++ and `continue` without RR (volpath.cpp:287-296) */
+            depth++;
+            if (!fromOutside) escape(pf, df);
+            return fromOutside;
+        }
+        float N[3], dOut[3], w, es;
+        shapeNormal(M.d, pf, N);
+        float eta = (float) M.rif->value(p); /* hdielectric.cpp:115-118: m_shape->getInteriorMedium()->getRIF(p) */
+        float u = rng.next();
+        rng.next(); /* the BSDF sample is a Point2 (rRec.nextSample2D()) */
+        bool transmitted = hdielectricSample(df, N, eta, u, dOut, w, es);
+        for (int i = 0; i < 3; i++) thr[i] *= w;
+        etaPath *= es;
+        for (int i = 0; i < 3; i++) dir[i] = (F) dOut[i];
+        bool inside = fromOutside ? transmitted : !transmitted;
+        if (!inside) { escape(pf, dOut); return false; } /* rayIntersectAndLookForEmitter with a delta BSDF: weight 1 */
+        return roulette();
+    };
+
+    if (!surface(true)) return;
 
     while (true) {
         /* ---- one path edge: Medium::sampleDistance semantics ---- */
@@ -1290,23 +1399,19 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             float u1 = rng.next(), u2 = rng.next();
             hg_sample(M.d.hg_g, wi, u1, u2, wo);
             for (int i = 0; i < 3; i++) dir[i] = (F) wo[i];
-            /* Russian roulette, volpath.cpp:326-336 (eta == 1 for the index-matched container) */
-            if (depth++ >= R.rr_depth) {
-                float q = std::min(std::max(thr[0], std::max(thr[1], thr[2])), 0.95f);
-                if (rng.next() >= q) return;
-                for (int i = 0; i < 3; i++) thr[i] /= q;
-            }
+            if (!roulette()) return;
         } else {
             st.exits++;
             for (int i = 0; i < 3; i++) thr[i] *= edge[i] * refRatioSq;
             if (R.max_depth != -1 && depth >= R.max_depth) return; /* volpath.cpp:200-201 */
-            depth++;
-            float po[3] = {(float) p[0], (float) p[1], (float) p[2]};
-            float dd[3] = {(float) (v[0] * vinv), (float) (v[1] * vinv), (float) (v[2] * vinv)};
-            float tq;
-            const float *Le = intersectQuad(R, po, dd, tq) ? R.quad_radiance : R.env_radiance;
-            for (int i = 0; i < 3; i++) L[i] += thr[i] * Le[i];
-            return;
+            for (int i = 0; i < 3; i++) dir[i] = v[i] * vinv;
+            if (dielectric) {
+                /* edge.cpp:45-67: the surface point is re-found by a straight ray from the last interior point */
+                float pf32[3] = {(float) p[0], (float) p[1], (float) p[2]}, df[3] = {(float) dir[0], (float) dir[1], (float) dir[2]};
+                float te = exitDistance(M.d, pf32, df);
+                for (int i = 0; i < 3; i++) p[i] = (F) (pf32[i] + te * df[i]);
+            }
+            if (!surface(false)) return;
         }
     }
 }

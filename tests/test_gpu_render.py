@@ -138,3 +138,62 @@ def test_packed_mode_renders_close_to_tricubic(oracle32):
     b = mer.develop(integ.render(scene, med_p)[0])
     # different interpolant (R1): images agree statistically, not bitwise
     assert abs(a.mean() - b.mean()) / a.mean() < 0.02
+
+
+# ---------------------------------------------------------------------------------------------------------
+# next-row 3: index-mismatched container, <bsdf type="hdielectric"> (src/bsdfs/hdielectric.cpp)
+
+@pytest.mark.parametrize("kind,shape", [("radial", ("box", BOX_MIN, BOX_MAX)), ("sd", ("sphere", (0.0, 0.0, 0.0), 0.95))])
+def test_hdielectric_boundary_image_matches_oracle(oracle32, kind, shape):
+    props = medium_props(stepsize=1e-2, sigmaS=(1.8, 1.5, 1.2), sigmaA=(0.2, 0.25, 0.3), bsdf="hdielectric", shape=shape)
+    med, omed, keep = setup(oracle32, kind, 40, props, g=0.6)
+    scene = scene_dict(48, 40, 8, rfilter="box")
+    integ = mer.EikonalVolPathIntegrator(maxDepth=-1, rrDepth=5, stepsPerPass=256, poolPaths=4096)
+    film, stats = integ.render(scene, med)
+    ofilm, ostats = oracle32.render(omed, oracle_render_desc(scene))
+    assert stats["samples"] == ostats.samples and stats["nonfinite_dropped"] == 0
+    relmse, frac_tight = image_gates(film, ofilm, 8)
+    assert frac_tight > 0.95 and relmse < 2e-3, (relmse, frac_tight)
+    for k, ok in (("ray_steps", ostats.ray_steps), ("scatter_events", ostats.scatter_events),
+                  ("boundary_exits", ostats.boundary_exits)):
+        assert abs(stats[k] - ok) <= 0.01 * ok + 5, (k, stats[k], ok)
+    # the boundary matters: internal reflection sends paths back in, so there are more surface events than samples
+    matched = mer.HeterogeneousRefractiveMedium(dict(props, bsdf="null")).addChild("rif", keep[0]).addChild("", mer.HGPhaseFunction(g=0.6))
+    matched.configure()
+    _, st0 = integ.render(scene, matched)
+    assert stats["boundary_exits"] > 1.02 * st0["boundary_exits"]
+
+
+def test_hdielectric_white_furnace():
+    """constant index 1.5 behind a Fresnel boundary, no absorption, unit environment: reflection has weight 1 and the
+    1/eta^2 of entering cancels the eta^2 of leaving, so every pixel is exactly 1 whatever the path does"""
+    res = 24
+    lo, hi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    rif = mer.SplineDataSource(data=np.full((res,) * 3, 1.5, np.float32), min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(medium_props(stepsize=2e-2, sigmaS=2.0, sigmaA=0.0, bsdf="hdielectric"))
+    med.addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.3)).configure()
+    scene = scene_dict(32, 32, 8, rfilter="box", quad=False)
+    film, stats = mer.EikonalVolPathIntegrator(rrDepth=1000, stepsPerPass=200, poolPaths=2048).render(scene, med)
+    rgb = mer.develop(film)
+    assert np.allclose(rgb, 1.0, atol=3e-4), (rgb.min(), rgb.max())
+
+
+def test_hdielectric_fresnel_reflectance():
+    """a non-scattering slab of constant index seen head-on against a black environment with a bright quad BEHIND THE
+    CAMERA: the only light a pixel can receive is the mirror reflection off the front face plus the (multiply
+    reflected) light re-emerging towards the camera side, all of which see the quad; a camera ray that transmits through
+    both faces sees black.  Expected pixel value = R_total = 2R/(1+R) for normal incidence, R = ((n-1)/(n+1))^2."""
+    n = 1.5
+    res = 16
+    lo, hi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    rif = mer.SplineDataSource(data=np.full((res,) * 3, n, np.float32), min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(medium_props(stepsize=5e-2, sigmaS=0.0, sigmaA=0.0, mediumSamplingWeight=0.0,
+                                                         bsdf="hdielectric"))
+    med.addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.0)).configure()
+    scene = scene_dict(8, 8, 4096, rfilter="box", quad=False)
+    scene.update(fov=2.0, envRadiance=0.0, quad=dict(origin=(-50.0, -50.0, -6.0), u=(100.0, 0.0, 0.0), v=(0.0, 100.0, 0.0), radiance=(1.0, 1.0, 1.0)))
+    film, stats = mer.EikonalVolPathIntegrator(rrDepth=1000, stepsPerPass=64, poolPaths=4096).render(scene, med)
+    rgb = mer.develop(film)
+    R = ((n - 1) / (n + 1)) ** 2
+    expect = 2 * R / (1 + R)
+    assert abs(rgb.mean() - expect) < 4 * np.sqrt(expect * (1 - expect) / (64 * 4096)) + 1e-3, (rgb.mean(), expect)

@@ -44,6 +44,11 @@ def test_scene_xml_resolves_like_mitsuba(volumes):
     assert np.allclose(s["quad_origin"], [-0.5, 1.5, -0.5]) and np.allclose(s["quad_u"], [1, 0, 0]) and np.allclose(s["quad_v"], [0, 0, 1], atol=1e-12)
     m = s["medium"]
     assert np.allclose(m["sigma_s"], 3.6) and np.allclose(m["sigma_a"], 0.4) and m["strategy"] == 1 and m["hg_g"] == 0.5
+    assert m["boundary"] == 0  # <bsdf type="null"/> on the container
+    out = run([SCENE, "-D", "rif=%s" % (d / "rif.vol"), "-D", "bsdf=hdielectric", "--dry-run"])
+    assert out.returncode == 0 and json.loads(out.stdout)["medium"]["boundary"] == 1, out.stderr
+    out = run([SCENE, "-D", "rif=%s" % (d / "rif.vol"), "-D", "bsdf=dielectric", "--dry-run"])
+    assert out.returncode == 1 and "hdielectric" in out.stderr  # a fixed-IOR boundary is not on this path
     assert m["stepsize"] == pytest.approx(0.002) and m["weight"] == -1 and m["shape_type"] == 0 and m["shape"] == [-1, -1, -1, 1, 1, 1]
     assert m["rif_res"] == [40, 40, 40] and np.allclose(m["rif_bbox"], list(lo) + list(hi))
 

@@ -240,3 +240,27 @@ def test_curved_connection_recovers_known_ray(oracle64):
     assert np.abs(r["optical_dist"] - truth["opl"])[ok].max() < 4e-3
     res = oracle64.connection_residual(med, p1[ok], truth["p"][ok], r["dir_to_p2"][ok])
     assert (0.5 * (res["error"] ** 2).sum(axis=1) < 1e-6).all() and (res["status"] == 0).all()
+
+
+def test_oracle_hdielectric_boundary(oracle32):
+    """next-row 3: the oracle's Fresnel container (hdielectric.cpp:244-300).  (i) white furnace: eta^2 factors cancel;
+    (ii) a clear slab of index n reflects 2R/(1+R) of a source on the camera side (incoherent multiple reflection)."""
+    from common import BOX_MAX, BOX_MIN, medium_props, oracle_medium_desc, oracle_render_desc, scene_dict
+    from mitsubaer_b200 import fields
+    res, n = 16, 1.5
+    lo, hi = fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    orif = oracle32.rif_create(volume_desc((res,) * 3, lo, hi), np.full((res,) * 3, n, np.float32))
+    med = oracle32.medium_create(oracle_medium_desc(medium_props(stepsize=5e-2, sigmaS=2.0, sigmaA=0.0, bsdf="hdielectric"), 0.3), orif)
+    film, st = oracle32.render(med, oracle_render_desc(scene_dict(16, 16, 16, rfilter="box", quad=False), rr_depth=1000))
+    assert np.allclose(oracle32.film_develop(film), 1.0, atol=3e-4)
+    assert st.boundary_exits > st.samples * 0.5  # internal reflections are counted as surface events
+
+    clear = oracle32.medium_create(oracle_medium_desc(medium_props(stepsize=5e-2, sigmaS=0.0, sigmaA=0.0, mediumSamplingWeight=0.0,
+                                                                   bsdf="hdielectric"), 0.0), orif)
+    scene = scene_dict(4, 4, 2048, rfilter="box", quad=False)
+    scene.update(fov=2.0, envRadiance=0.0, quad=dict(origin=(-50.0, -50.0, -6.0), u=(100.0, 0.0, 0.0), v=(0.0, 100.0, 0.0), radiance=(1.0, 1.0, 1.0)))
+    film, st = oracle32.render(clear, oracle_render_desc(scene, rr_depth=1000))
+    R = ((n - 1) / (n + 1)) ** 2
+    expect = 2 * R / (1 + R)
+    got = oracle32.film_develop(film).mean()
+    assert abs(got - expect) < 4 * np.sqrt(expect * (1 - expect) / (16 * 2048)) + 1e-3, (got, expect)
