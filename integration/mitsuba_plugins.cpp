@@ -100,6 +100,9 @@ public:
         AABB box = m_shape->getAABB();
         d.shape_type = MER_SHAPE_BOX;
         for (int i = 0; i < 3; ++i) { d.shape[i] = box.min[i]; d.shape[3 + i] = box.max[i]; }
+        /* the container's surface: hdielectric (eta from this medium's RIF) or anything index-matched */
+        d.boundary = (m_shape->getBSDF() && m_shape->getBSDF()->getClass()->getName() == "HSmoothDielectric")
+                         ? MER_BOUNDARY_HDIELECTRIC : MER_BOUNDARY_INDEX_MATCHED;
         d.hg_g = m_phaseFunction->getMeanCosine();
         d.density_scale = m_props.getFloat("scale", 1.0f);
         Spectrum albedo = m_props.getSpectrum("albedo", Spectrum(0.0f));
