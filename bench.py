@@ -363,6 +363,17 @@ def run_gpu(args, w, wname):
                 "note": "algorithmic bytes exceed HBM peak when the stencil is served from L1/L2 (grid "
                         "re-use between consecutive steps of a ray); frac > 1 is cache reuse, not skipped work"}
 
+    # secondary ceilings measured with tools/microbench.cu on this pool (FP32 issue rate at ~1.0 kFLOP per
+    # tricubic step, 130 FLOP packed; L2 read bandwidth for tables that fit the L2)
+    mpath = os.path.join(ROOT, "profiles", "r01_microbench.json")
+    if os.path.exists(mpath):
+        mb = json.load(open(mpath))
+        flop_per_step = 1000.0 if args.mode == "tricubic" else 160.0
+        tf = ray_steps / world * flop_per_step / (k_ms * 1e-3) / 1e12
+        roofline["fp32"] = {"achieved_tflops": tf, "peak_tflops": mb["fp32_fma_tflops"], "frac": tf / mb["fp32_fma_tflops"],
+                            "flop_per_ray_step": flop_per_step, "peak_source": "profiles/r01_microbench.json (FFMA microbenchmark)"}
+        roofline["l2_read_gbs_measured"] = mb["l2_read_gbs"]
+
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample, rank 0 / N=1 only
     cpu = None
     if world == 1 and not args.no_cpu:

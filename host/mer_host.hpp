@@ -272,6 +272,7 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
     std::shared_ptr<GridDataSource> density;
     std::shared_ptr<HGPhaseFunction> phase;
     mer_medium_desc desc;
+    mer_connection_params connection;
     mer_medium *handle = nullptr;
     const char *className() const override { return "HeterogeneousRefractiveMedium"; }
     void addChild(const std::string &name, ObjectRef child) override {
@@ -303,9 +304,14 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         desc.sampling_density = (float) props.getFloat("samplingDensity", 0.0);
         desc.density_scale = (float) scale;
         props.getBoolean("monochromatic", false);
-        /* accepted for XML compatibility; they belong to the curved-NEE row or to inactive code paths */
-        for (const char *n : {"tol2", "rrweight", "ceresfunctiontolerance", "ceresgradienttolerance", "ceresparametertolerance"}) props.getFloat(n, 0);
-        for (const char *n : {"boundaryprecision", "ceresmaxiterations"}) props.getInteger(n, 0);
+        /* solver parameters of the direct connections (heterogeneousrefractive.cpp:208-219), used when the integrator asks for them */
+        connection.tol2 = (float) props.getFloat("tol2", 1e-6);
+        connection.rrweight = (float) props.getFloat("rrweight", 1e-2);
+        connection.boundary_precision = (int) props.getInteger("boundaryprecision", 3);
+        connection.max_iterations = (int) props.getInteger("ceresmaxiterations", 20);
+        connection.start_mode = MER_START_DEFAULT;
+        /* accepted for XML compatibility: Ceres-specific tolerances have no counterpart in the Levenberg-Marquardt solver */
+        for (const char *n : {"ceresfunctiontolerance", "ceresgradienttolerance", "ceresparametertolerance"}) props.getFloat(n, 0);
         for (const char *n : {"cerescheckgradients", "makesensordirectconnections", "aggressivetracing"}) props.getBoolean(n, false);
         if (!rif) logError("No RIF specified!");
     }

@@ -283,6 +283,9 @@ Scene loadScene(const std::string &xmlPath, const std::map<std::string, std::str
     if (R.max_depth == 0 || R.max_depth < -1) logError("maxDepth must be set to -1 (infinite) or a value greater than zero!");
     R.pool_paths = (int) integrator->props.getInteger("poolPaths", 0);
     R.steps_per_pass = (int) integrator->props.getInteger("stepsPerPass", 0);
+    R.direct_connections = integrator->props.getBoolean("directConnections", false) ? 1 : 0;
+    const std::string connectionStart = integrator->props.getString("connectionStart", "straight");
+    if (connectionStart != "straight" && connectionStart != "random") logError("connectionStart must be \"straight\" or \"random\"");
 
     if (sensor->props.pluginName != "perspective") logError("sensor \"" + sensor->props.pluginName + "\": only `perspective` is on this path");
     Transform toWorld = sensor->props.getTransform("toWorld", Transform());
@@ -332,6 +335,9 @@ Scene loadScene(const std::string &xmlPath, const std::map<std::string, std::str
         }
     }
     if (!S.medium) logError("the scene contains no shape with an interior heterogeneousrefractive medium");
+    R.connection = S.medium->connection;
+    R.connection.start_mode = connectionStart == "random" ? MER_START_RANDOM : MER_START_STRAIGHT;
+    if (R.direct_connections && !R.has_quad) logError("directConnections needs an area emitter (rectangle)");
     S.keepAlive = L.all;
     return S;
 }

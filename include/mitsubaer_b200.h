@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 2
+#define MER_ABI_VERSION 3
 
 enum mer_status {
     MER_OK = 0,
@@ -230,7 +230,8 @@ int mer_medium_derivative_trace_batch(const mer_medium *medium, size_t n, float 
                                       float *dpdv0_out, float *dvdv0_out);
 /* computefdfBDPT (:816-939): residual p(t*) - p2 at the closest approach of the ray launched from p1 with
  * velocity v0, and its Jacobian (stored transposed like :936-938).  status: 0 inside, 1 left the object
- * (Snell at the sdf boundary + straight extension; needs mer_medium_set_sdf), 2 degenerate. */
+ * (boundary normal from the sdf child, else the analytic box / sphere normal; Snell to exterior index 1 when the medium's
+ * boundary is MER_BOUNDARY_HDIELECTRIC as in the reference, unrefracted when index-matched; straight extension), 2 degenerate, 3 left the object by total internal reflection. */
 int mer_medium_connection_residual_batch(const mer_medium *medium, int boundary_precision, size_t n, const float *p1,
                                          const float *p2, const float *v0, int is_sensor_sample, float *error_out,
                                          float *derror_out, int32_t *status_out, int32_t *nsteps_out);
@@ -241,7 +242,14 @@ typedef struct mer_connection_params {
     float rrweight;             /* 1e-2: Russian roulette on solver failures */
     int32_t boundary_precision; /* 3: ceil(precision / log10 2) step halvings */
     int32_t max_iterations;     /* 20 */
+    /* first guess of the launch direction: MER_START_RANDOM = every attempt starts uniformly in the hemisphere about the
+     * seed direction (the reference, :1078-1105); MER_START_STRAIGHT = the first attempt starts from the seed direction
+     * itself and only retries are random.  MER_START_DEFAULT: random for mer_medium_connect_batch (= eval()), straight for
+     * the integrator's direct connections. */
+    int32_t start_mode;
 } mer_connection_params;
+
+enum mer_start_mode { MER_START_DEFAULT = 0, MER_START_RANDOM = 1, MER_START_STRAIGHT = 2 };
 
 /* what HeterogeneousRefractiveMedium::eval fills into the MediumSamplingRecord for a connection (:571-640) */
 typedef struct mer_connection_records {
@@ -288,6 +296,12 @@ typedef struct mer_render_desc {
     float quad_origin[3], quad_u[3], quad_v[3], quad_radiance[3];
     int32_t pool_paths;        /* resident path slots (0 => default) */
     int32_t steps_per_pass;    /* er_steps per path per wavefront pass (0 => default) */
+    /* next-event estimation along the curved path: 0 = the quad emitter is found only by hitting it;
+     * 1 = every scattering vertex in the medium is connected to a uniformly sampled point of the quad by solving the
+     * shooting problem of makeDirectConnections (heterogeneousrefractive.cpp:1087-1163), and paths that reach the quad
+     * after a scattering event no longer count it.  Requires a quad, the tricubic RIF mode and no density grid. */
+    int32_t direct_connections;
+    mer_connection_params connection; /* solver parameters for direct_connections = 1 (zeros => tol2 1e-6, rrweight 1e-2, 3, 20) */
 } mer_render_desc;
 
 typedef struct mer_render_stats {
@@ -298,6 +312,9 @@ typedef struct mer_render_stats {
     uint64_t boundary_exits;
     uint64_t nonfinite_dropped; /* samples rejected like ImageBlock::put (imageblock.h:147-152) */
     uint64_t passes;         /* wavefront passes */
+    uint64_t connections;          /* direct connections attempted (direct_connections = 1) */
+    uint64_t connections_failed;   /* of those: no solution found / no transmitted path */
+    uint64_t connection_steps;     /* Hessian-carrying leapfrog steps spent in the solver */
     uint64_t kernel_launches;
     float device_ms;         /* CUDA-event time of the render kernels */
 } mer_render_stats;

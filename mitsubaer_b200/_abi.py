@@ -49,7 +49,8 @@ class SamplingRecords(C.Structure):
 
 
 class ConnectionParams(C.Structure):
-    _fields_ = [("tol2", C.c_float), ("rrweight", C.c_float), ("boundary_precision", C.c_int32), ("max_iterations", C.c_int32)]
+    _fields_ = [("tol2", C.c_float), ("rrweight", C.c_float), ("boundary_precision", C.c_int32), ("max_iterations", C.c_int32),
+                ("start_mode", C.c_int32)]
 
 
 class ConnectionRecords(C.Structure):
@@ -66,13 +67,15 @@ class RenderDesc(C.Structure):
                 ("fov_deg", C.c_float), ("filter", C.c_int32), ("max_depth", C.c_int32), ("rr_depth", C.c_int32),
                 ("env_radiance", C.c_float * 3), ("has_quad", C.c_int32), ("quad_origin", C.c_float * 3),
                 ("quad_u", C.c_float * 3), ("quad_v", C.c_float * 3), ("quad_radiance", C.c_float * 3),
-                ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32)]
+                ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32), ("direct_connections", C.c_int32),
+                ("connection", ConnectionParams)]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("ray_steps", C.c_uint64), ("scatter_events", C.c_uint64),
                 ("null_collisions", C.c_uint64), ("boundary_exits", C.c_uint64),
-                ("nonfinite_dropped", C.c_uint64), ("passes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("nonfinite_dropped", C.c_uint64), ("passes", C.c_uint64), ("connections", C.c_uint64),
+                ("connections_failed", C.c_uint64), ("connection_steps", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_float)]
 
     def as_dict(self):

@@ -59,6 +59,8 @@ struct MediumDev {
     int strategy;
     float samplingDensity; /* m_samplingDensity */
     int shapeType;
+    int boundary; /* MER_BOUNDARY_*: what the container surface does to a ray */
+    float minExit2; /* computefdfBDPT calls a connection degenerate when it leaves the shape within sqrt(minExit2) of p1 (:891: Epsilon) */
     float shape[6];
     float g;
     float densityScale, invMaxDensity;
@@ -568,3 +570,58 @@ struct PathRng {
         return (float) (w >> 8) * (1.0f / 16777216.0f);
     }
 };
+
+/* ------------------------------------------------------------------ container surface */
+/* fresnelDielectricExt, src/libcore/util.cpp:665-695 */
+static __device__ __forceinline__ float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
+    if (eta == 1.0f) { cosThetaT_ = -cosThetaI_; return 0.0f; }
+    const float scale = (cosThetaI_ > 0.0f) ? __fdiv_rn(1.0f, eta) : eta;
+    const float cosThetaTSqr = __fsub_rn(1.0f, __fmul_rn(__fsub_rn(1.0f, __fmul_rn(cosThetaI_, cosThetaI_)), __fmul_rn(scale, scale)));
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    const float cosThetaI = fabsf(cosThetaI_), cosThetaT = __fsqrt_rn(cosThetaTSqr);
+    const float ect = __fmul_rn(eta, cosThetaT), eci = __fmul_rn(eta, cosThetaI);
+    const float Rs = __fdiv_rn(__fsub_rn(cosThetaI, ect), __fadd_rn(cosThetaI, ect));
+    const float Rp = __fdiv_rn(__fsub_rn(eci, cosThetaT), __fadd_rn(eci, cosThetaT));
+    cosThetaT_ = (cosThetaI_ > 0.0f) ? -cosThetaT : cosThetaT;
+    return __fmul_rn(0.5f, __fadd_rn(__fmul_rn(Rs, Rs), __fmul_rn(Rp, Rp)));
+}
+
+/* outward unit normal of the container at a surface point */
+static __device__ __forceinline__ float3 shape_normal(const MediumDev &M, float3 p) {
+    if (M.shapeType == MER_SHAPE_SPHERE) {
+        float3 d = f3(p.x - M.shape[0], p.y - M.shape[1], p.z - M.shape[2]);
+        float l = 1.0f / sqrtf(dot3(d, d));
+        return f3(d.x * l, d.y * l, d.z * l);
+    }
+    const float pp[3] = {p.x, p.y, p.z};
+    int axis = 0;
+    float best = INFINITY, sign = 1.0f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float a = fabsf(pp[i] - M.shape[i]), b = fabsf(pp[i] - M.shape[3 + i]);
+        if (a < best) { best = a; axis = i; sign = -1.0f; }
+        if (b < best) { best = b; axis = i; sign = 1.0f; }
+    }
+    return f3(axis == 0 ? sign : 0.0f, axis == 1 ? sign : 0.0f, axis == 2 ? sign : 0.0f);
+}
+
+/* distance along a straight ray from a point inside the container to its surface (edge.cpp:45-67 re-finds the
+ * surface point of a curved segment with a straight ray from the last interior point) */
+static __device__ __forceinline__ float exit_distance(const MediumDev &M, float3 o, float3 d) {
+    if (M.shapeType == MER_SHAPE_SPHERE) {
+        float3 oc = f3(o.x - M.shape[0], o.y - M.shape[1], o.z - M.shape[2]);
+        float b = dot3(oc, d), c = dot3(oc, oc) - M.shape[3] * M.shape[3];
+        float disc = b * b - c;
+        return disc > 0.0f ? fmaxf(-b + sqrtf(disc), 0.0f) : 0.0f;
+    }
+    float t1 = INFINITY;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (dd[i] == 0.0f) continue;
+        float inv = 1.0f / dd[i];
+        float ta = (M.shape[i] - oo[i]) * inv, tb = (M.shape[3 + i] - oo[i]) * inv;
+        t1 = fminf(t1, fmaxf(ta, tb));
+    }
+    return fmaxf(t1, 0.0f);
+}

@@ -37,12 +37,18 @@ struct RenderScratch {
     std::mutex lock; /* mer_render* calls on one device are serialised */
     size_t poolBytes = 0;
     void *pool[14] = {nullptr};
+    void *neeQ[3] = {nullptr, nullptr, nullptr}; /* direct-connection request queue */
+    unsigned *neeCount = nullptr;
+    unsigned neeCap = 0;
     unsigned *nOut = nullptr;
     unsigned long long *counters = nullptr;
     unsigned long long *hostPinned = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void release() {
         for (void *&p : pool) { cudaFree(p); p = nullptr; }
+        for (void *&p : neeQ) { cudaFree(p); p = nullptr; }
+        cudaFree(neeCount); neeCount = nullptr;
+        neeCap = 0;
         cudaFree(nOut); nOut = nullptr;
         cudaFree(counters); counters = nullptr;
         if (hostPinned) cudaFreeHost(hostPinned);

@@ -393,6 +393,8 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
     D.shapeType = desc->shape_type;
     for (int i = 0; i < 6; i++) D.shape[i] = desc->shape[i];
     D.g = desc->hg_g;
+    D.boundary = desc->boundary;
+    D.minExit2 = MER_EPSILON;
     D.densityScale = desc->density_scale;
     D.invMaxDensity = density ? 1.0f / (desc->density_scale * 1.0f) : 0.0f; /* heterogeneous.cpp:239-242 */
     m->desc.medium_sampling_weight = w;

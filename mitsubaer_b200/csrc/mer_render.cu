@@ -24,6 +24,11 @@
  * the warp alternates between a convergent stepping phase (all lanes execute the same
  * 16xLDG.128 + separable contraction) and an event phase (scatter / exit / regenerate) that
  * is entered only when enough lanes are waiting, which bounds divergence.
+ *
+ * Next-event estimation along curved paths (desc.direct_connections): a scattering vertex appends a
+ * 48-byte request to a device queue; between passes k_nee gives every request a thread that samples a point of the quad
+ * emitter, solves the shooting problem of makeDirectConnections (mer_connect.cuh) and splats the contribution.  The
+ * solver costs 1e3-1e5 Hessian-carrying steps per request, which is why it is its own kernel and not an event.
  */
 #include <cmath>
 #include <cstdlib>
@@ -31,6 +36,7 @@
 #include <vector>
 
 #include "mer_internal.h"
+#include "mer_connect.cuh"
 
 #ifndef MER_RENDER_MIN_BLOCKS
 #define MER_RENDER_MIN_BLOCKS 3 /* 170 registers/thread: the 64-register stencil cache fits without spills */
@@ -49,12 +55,20 @@ enum PathKind : int {
     E_EXIT = 7,  /* trace()/traceTillBoundary() left the shape */
     E_NEW = 8,   /* needs a new camera sample */
     E_SURFACE = 9, /* at the container surface with the field known: dielectric interaction (hdielectric boundary) */
-    K_DEAD = 10
+    E_SCATTER = 10, /* real collision accepted, throughput updated: direct connection request, phase sampling, roulette */
+    K_DEAD = 11
 };
 
-enum { FLAG_TB = 1, FLAG_MOVED = 2, FLAG_OUTWARD = 4 /* reached the surface from inside */ };
+enum {
+    FLAG_TB = 1, FLAG_MOVED = 2,
+    FLAG_OUTWARD = 4, /* reached the surface from inside */
+    FLAG_COVERED = 8, /* the quad's light along the current edge chain is estimated by a direct connection */
+    FLAG_PARKED = 16  /* the request queue is full: wait for the next pass */
+};
 
-enum { ST_SAMPLES = 0, ST_STEPS, ST_SCATTER, ST_NULL, ST_EXIT, ST_NONFINITE, ST_COUNT };
+enum { ST_SAMPLES = 0, ST_STEPS, ST_SCATTER, ST_NULL, ST_EXIT, ST_NONFINITE, ST_CONN, ST_CONNFAIL, ST_CONNSTEPS, ST_COUNT };
+
+#define MER_NEE_SALT 0x5851F42D4C957F2DULL /* direct connections draw from their own Philox key */
 
 /* persisted path state: 6 x 16 bytes per path, SoA by quad so loads/stores are LDG/STG.128 */
 struct PathPool {
@@ -86,6 +100,13 @@ struct RenderParams {
     unsigned *nOut;
     unsigned long long *sampleCounter;
     unsigned long long *stats;
+    /* direct connections */
+    int nee, neePrecision, neeMaxIterations, neeStraightFirst;
+    float neeTol2, neeRRWeight;
+    unsigned neeCap;
+    unsigned *neeCount;
+    float4 *neeQ0, *neeQ1; /* (p1.xyz, wi.x), (wi.yz, thr.rg) */
+    uint4 *neeQ2;          /* thr.b, depth, pixel, sample */
 };
 
 struct Lane {
@@ -140,60 +161,6 @@ __device__ __forceinline__ bool intersect_quad(const RenderParams &P, float3 o, 
     return a >= 0.0f && a <= 1.0f && b >= 0.0f && b <= 1.0f;
 }
 
-/* fresnelDielectricExt, src/libcore/util.cpp:665-695 */
-__device__ __forceinline__ float fresnel_dielectric_ext(float cosThetaI_, float &cosThetaT_, float eta) {
-    if (eta == 1.0f) { cosThetaT_ = -cosThetaI_; return 0.0f; }
-    const float scale = (cosThetaI_ > 0.0f) ? __fdiv_rn(1.0f, eta) : eta;
-    const float cosThetaTSqr = __fsub_rn(1.0f, __fmul_rn(__fsub_rn(1.0f, __fmul_rn(cosThetaI_, cosThetaI_)), __fmul_rn(scale, scale)));
-    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
-    const float cosThetaI = fabsf(cosThetaI_), cosThetaT = __fsqrt_rn(cosThetaTSqr);
-    const float ect = __fmul_rn(eta, cosThetaT), eci = __fmul_rn(eta, cosThetaI);
-    const float Rs = __fdiv_rn(__fsub_rn(cosThetaI, ect), __fadd_rn(cosThetaI, ect));
-    const float Rp = __fdiv_rn(__fsub_rn(eci, cosThetaT), __fadd_rn(eci, cosThetaT));
-    cosThetaT_ = (cosThetaI_ > 0.0f) ? -cosThetaT : cosThetaT;
-    return __fmul_rn(0.5f, __fadd_rn(__fmul_rn(Rs, Rs), __fmul_rn(Rp, Rp)));
-}
-
-/* outward unit normal of the container at a surface point */
-__device__ __forceinline__ float3 shape_normal(const MediumDev &M, float3 p) {
-    if (M.shapeType == MER_SHAPE_SPHERE) {
-        float3 d = f3(p.x - M.shape[0], p.y - M.shape[1], p.z - M.shape[2]);
-        float l = 1.0f / sqrtf(dot3(d, d));
-        return f3(d.x * l, d.y * l, d.z * l);
-    }
-    const float pp[3] = {p.x, p.y, p.z};
-    int axis = 0;
-    float best = INFINITY, sign = 1.0f;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        float a = fabsf(pp[i] - M.shape[i]), b = fabsf(pp[i] - M.shape[3 + i]);
-        if (a < best) { best = a; axis = i; sign = -1.0f; }
-        if (b < best) { best = b; axis = i; sign = 1.0f; }
-    }
-    return f3(axis == 0 ? sign : 0.0f, axis == 1 ? sign : 0.0f, axis == 2 ? sign : 0.0f);
-}
-
-/* distance along a straight ray from a point inside the container to its surface (edge.cpp:45-67 re-finds the
- * surface point of a curved segment with a straight ray from the last interior point) */
-__device__ __forceinline__ float exit_distance(const MediumDev &M, float3 o, float3 d) {
-    if (M.shapeType == MER_SHAPE_SPHERE) {
-        float3 oc = f3(o.x - M.shape[0], o.y - M.shape[1], o.z - M.shape[2]);
-        float b = dot3(oc, d), c = dot3(oc, oc) - M.shape[3] * M.shape[3];
-        float disc = b * b - c;
-        return disc > 0.0f ? fmaxf(-b + sqrtf(disc), 0.0f) : 0.0f;
-    }
-    float t1 = INFINITY;
-    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        if (dd[i] == 0.0f) continue;
-        float inv = 1.0f / dd[i];
-        float ta = (M.shape[i] - oo[i]) * inv, tb = (M.shape[3 + i] - oo[i]) * inv;
-        t1 = fminf(t1, fmaxf(ta, tb));
-    }
-    return fmaxf(t1, 0.0f);
-}
-
 /* HSmoothDielectric::sample (hdielectric.cpp:244-300) in ERadiance mode with both components: d is the unit
  * direction of travel, N the outward normal, eta the RIF at the hit point.  Returns true for transmission. */
 __device__ __forceinline__ bool hdielectric_sample(float3 d, float3 N, float eta, float u, float3 &dOut, float &weight,
@@ -217,9 +184,9 @@ __device__ __forceinline__ bool hdielectric_sample(float3 d, float3 N, float eta
 }
 
 /* ImageBlock::put (imageblock.h:144-190) onto the global film with red.global.add.f32 */
-__device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha,
+__device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha, float wgt,
                                          unsigned &nonfinite) {
-    const float value[5] = {L[0], L[1], L[2], alpha, 1.0f};
+    const float value[5] = {L[0], L[1], L[2], alpha, wgt};
 #pragma unroll
     for (int k = 0; k < 5; k++)
         if (!isfinite(value[k])) { nonfinite++; return; }
@@ -238,10 +205,11 @@ __device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy,
 }
 
 /* the sample's film position is draw 0/1 of its Philox stream: recomputed, not stored */
-__device__ __forceinline__ void sample_position(const RenderParams &P, const Lane &L, float &sx, float &sy) {
-    const unsigned yy = L.pixel / (unsigned) P.W;
-    int x = (int) (L.pixel - yy * (unsigned) P.W), y = (int) yy;
-    uint4 b = philox4x32_10(L.rng.s0, L.rng.s1, 0u, 0u, L.rng.k0, L.rng.k1);
+__device__ __forceinline__ void sample_position(const RenderParams &P, unsigned pixel, unsigned sample, float &sx, float &sy) {
+    const unsigned yy = pixel / (unsigned) P.W;
+    int x = (int) (pixel - yy * (unsigned) P.W), y = (int) yy;
+    const unsigned long long id = (unsigned long long) pixel * (unsigned long long) P.sppTotal + sample;
+    uint4 b = philox4x32_10((uint32_t) id, (uint32_t) (id >> 32), 0u, 0u, (uint32_t) P.seed, (uint32_t) (P.seed >> 32));
     sx = (float) x + (float) (b.x >> 8) * (1.0f / 16777216.0f);
     sy = (float) y + (float) (b.y >> 8) * (1.0f / 16777216.0f);
 }
@@ -249,8 +217,8 @@ __device__ __forceinline__ void sample_position(const RenderParams &P, const Lan
 __device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, const float rad[3], float alpha,
                                               unsigned *st) {
     float sx, sy;
-    sample_position(P, L, sx, sy);
-    film_put(P, sx, sy, rad, alpha, st[ST_NONFINITE]);
+    sample_position(P, L.pixel, L.sample, sx, sy);
+    film_put(P, sx, sy, rad, alpha, 1.0f, st[ST_NONFINITE]);
     L.kind = E_NEW;
 }
 
@@ -305,7 +273,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
     const MediumDev &M = P.M;
     const float zero[3] = {0.f, 0.f, 0.f};
     L.rng.cachedBlock = 0xffffffffu; /* the cached Philox block lives only inside one event phase (registers) */
-    while (L.kind >= E_BEGIN && L.kind != K_DEAD) {
+    while (L.kind >= E_BEGIN && L.kind != K_DEAD && !(L.flags & FLAG_PARKED)) {
         if (L.kind == E_NEW) {
             /* ---- SamplingIntegrator::renderBlock: next (pixel, sample) */
             unsigned long long g = atomicAdd(P.sampleCounter, 1ULL);
@@ -385,11 +353,13 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             L.flags &= ~FLAG_OUTWARD;
             if (!inside) { /* rayIntersectAndLookForEmitter with a delta BSDF: MIS weight 1, volpath.cpp:300-320 */
                 float tq;
-                const float *Le = intersect_quad(P, L.p, dOut, tq) ? P.quadLe : P.env;
+                const bool hitsQuad = intersect_quad(P, L.p, dOut, tq);
+                const float *Le = hitsQuad ? ((L.flags & FLAG_COVERED) ? zero : P.quadLe) : P.env;
                 float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
                 finish_sample(P, L, rad, 1.0f, st);
                 continue;
             }
+            L.flags &= ~FLAG_COVERED; /* an internal reflection starts a chain no direct connection accounts for */
             if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
                 float q = fminf(fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2])) * L.etaPath * L.etaPath, 0.95f);
                 if (L.rng.next() >= q) { finish_sample(P, L, zero, 1.0f, st); continue; }
@@ -397,6 +367,31 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 for (int c = 0; c < 3; c++) L.thr[c] /= q;
             }
             L.kind = E_BEGIN;
+        } else if (L.kind == E_SCATTER) {
+            /* ---- scattering vertex: L.v = arrival velocity, throughput already carries the edge */
+            const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
+            const float3 wi = f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv);
+            if (P.nee) {
+                if (P.maxDepth == -1 || L.depth + 1 < P.maxDepth) {
+                    const unsigned slot = atomicAdd(P.neeCount, 1u);
+                    if (slot >= P.neeCap) { L.flags |= FLAG_PARKED; break; } /* the host clamps the count; retried next pass */
+                    P.neeQ0[slot] = make_float4(L.p.x, L.p.y, L.p.z, wi.x);
+                    P.neeQ1[slot] = make_float4(wi.y, wi.z, L.thr[0], L.thr[1]);
+                    P.neeQ2[slot] = make_uint4(__float_as_uint(L.thr[2]), (unsigned) L.depth, L.pixel, L.sample);
+                }
+                L.flags |= FLAG_COVERED;
+            }
+            float u1 = L.rng.next(), u2 = L.rng.next();
+            L.v = hg_sample_dev(M.g, wi, u1, u2);
+            if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
+                float q = fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2]));
+                if (DIELECTRIC) q *= L.etaPath * L.etaPath;
+                q = fminf(q, 0.95f);
+                if (L.rng.next() >= q) { finish_sample(P, L, zero, 1.0f, st); continue; }
+#pragma unroll
+                for (int c = 0; c < 3; c++) L.thr[c] /= q;
+            }
+            L.kind = E_BEGIN; /* field at p is still valid */
         } else {
             /* ---- end of a path edge */
             bool scatter = false;
@@ -433,18 +428,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
 #pragma unroll
                 for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
-                float3 wi = f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv);
-                float u1 = L.rng.next(), u2 = L.rng.next();
-                L.v = hg_sample_dev(M.g, wi, u1, u2);
-                if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
-                    float q = fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2]));
-                    if (DIELECTRIC) q *= L.etaPath * L.etaPath;
-                    q = fminf(q, 0.95f);
-                    if (L.rng.next() >= q) { finish_sample(P, L, zero, 1.0f, st); continue; }
-#pragma unroll
-                    for (int c = 0; c < 3; c++) L.thr[c] /= q;
-                }
-                L.kind = E_BEGIN; /* field at p is still valid */
+                L.kind = E_SCATTER;
             } else {
                 st[ST_EXIT]++;
 #pragma unroll
@@ -461,7 +445,8 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 }
                 L.depth++;
                 float tq;
-                const float *Le = intersect_quad(P, L.p, d, tq) ? P.quadLe : P.env;
+                const bool hitsQuad = intersect_quad(P, L.p, d, tq);
+                const float *Le = hitsQuad ? ((L.flags & FLAG_COVERED) ? zero : P.quadLe) : P.env;
                 float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
                 finish_sample(P, L, rad, 1.0f, st);
             }
@@ -488,7 +473,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.thr[0] = b.z; L.thr[1] = b.w; L.thr[2] = c.x;
         L.refStart = c.y; L.segDist = c.z; L.distSurf = c.w;
         L.rem = d.x; L.sd = d.y; L.stepsLeft = __float_as_int(d.z); L.depth = __float_as_int(d.w);
-        L.kind = (int) (e.x & 0xffu); L.flags = (int) (e.x >> 8);
+        L.kind = (int) (e.x & 0xffu); L.flags = (int) (e.x >> 8) & ~FLAG_PARKED;
         L.pixel = e.z; L.sample = e.w;
         L.rng.init(P.seed, (unsigned long long) e.z * (unsigned long long) P.sppTotal + e.w, e.y);
         float4 fg = P.in.q5[tid];
@@ -522,7 +507,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
          * following vote, so the barrier is spelled in PTX. */
         asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
         const bool stepping = L.kind <= K_ENTRY;
-        const bool waiting = L.kind >= E_BEGIN && L.kind != K_DEAD;
+        const bool waiting = L.kind >= E_BEGIN && L.kind != K_DEAD && !(L.flags & FLAG_PARKED);
         const unsigned ms = __ballot_sync(0xffffffffu, stepping);
         const unsigned mw = __ballot_sync(0xffffffffu, waiting);
         if (ms != 0u && budget > 0 && __popc(mw) < P.maxWait) {
@@ -586,6 +571,81 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(P.stats + i, (unsigned long long) v);
     }
+}
+
+/* Next-event estimation of the quad emitter from the queued scattering vertices, one thread per vertex.
+ * Around the reference's shooting problem (makeDirectConnections, mer_connect.cuh) the estimator is
+ *     thr * phase(wi, w) * exp(-sigma_t dist) * (n_b / n_1)^2 [* (1 - Fresnel) n_b^2 for hdielectric]
+ *         * Le * |cos theta_y| * Area / |d r_perp / d omega|
+ * i.e. the random walk's own exit-edge weights with the change of variables launch direction -> sampled point written
+ * with the solver's Jacobian in place of 1 / distance^2.  The splat adds radiance only (filter weight 0): the sample's
+ * weight is added once, by the walk. */
+__global__ void __launch_bounds__(128)
+k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const MediumDev &M = P.M;
+    unsigned st[3] = {0u, 0u, 0u}, nonfinite = 0u; /* connections, failed, steps */
+    if (i < nReq) {
+        const float4 a = P.neeQ0[i], b = P.neeQ1[i];
+        const uint4 c = P.neeQ2[i];
+        const float3 p1 = f3(a.x, a.y, a.z), wi = f3(a.w, b.x, b.y);
+        const float thr[3] = {b.z, b.w, __uint_as_float(c.x)};
+        const unsigned depth = c.y, pixel = c.z, sample = c.w;
+        PathRng nrng;
+        nrng.init(P.seed ^ MER_NEE_SALT, (unsigned long long) pixel * (unsigned long long) P.sppTotal + sample, depth * 256u);
+        const float u = nrng.next(), w = nrng.next();
+        const float3 qu = f3(P.quadU[0], P.quadU[1], P.quadU[2]), qv = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
+        float3 Nq = f3(qu.y * qv.z - qu.z * qv.y, qu.z * qv.x - qu.x * qv.z, qu.x * qv.y - qu.y * qv.x);
+        const float area = sqrtf(dot3(Nq, Nq));
+        const float3 y = f3(P.quadO[0] + u * qu.x + w * qv.x, P.quadO[1] + u * qu.y + w * qv.y, P.quadO[2] + u * qu.z + w * qv.z);
+        float3 ds = f3(y.x - p1.x, y.y - p1.y, y.z - p1.z);
+        const float dl = 1.0f / sqrtf(dot3(ds, ds));
+        ds = f3(ds.x * dl, ds.y * dl, ds.z * dl);
+        const bool refract = M.boundary == MER_BOUNDARY_HDIELECTRIC;
+        merc::ConnectResult C;
+        merc::connect_solve(M, P.neePrecision, P.neeTol2, P.neeRRWeight, P.neeMaxIterations, p1, y, ds, true, refract, P.neeStraightFirst != 0,
+                            nrng, C);
+        st[0] = 1u;
+        int steps = C.steps;
+        bool ok = C.success && C.exit.exited && !C.exit.tir;
+        if (ok) {
+            float3 r;
+            merc::M3 J;
+            merc::compute_fdf(M, P.neePrecision, C.dir, p1, y, true, refract, r, J, steps);
+            const float spread = merc::connection_spread(J, C.n1);
+            ok = spread > 0.0f;
+            if (ok) {
+                const float cosY = fabsf(dot3(C.rev, Nq)) / area;
+                const float inv1 = 1.0f / C.n1;
+                const float phase = hg_eval_dev(M.g, wi, f3(C.dir.x * inv1, C.dir.y * inv1, C.dir.z * inv1));
+                float scale = (float) (1.0 / (double) (C.n1 * C.n1)) * C.exit.nb * C.exit.nb;
+                if (refract) {
+                    float cosT;
+                    const float Fr = fresnel_dielectric_ext(-C.exit.cosI, cosT, C.exit.nb);
+                    scale *= (1.0f - Fr) * (C.exit.nb * C.exit.nb);
+                }
+                const float geom = cosY * area / spread;
+                float rad[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    rad[k] = thr[k] * phase * fastexp_dev(M.sigmaT[k] * -C.dist) * C.weight * scale * P.quadLe[k] * geom;
+                float sx, sy;
+                sample_position(P, pixel, sample, sx, sy);
+                film_put(P, sx, sy, rad, 0.0f, 0.0f, nonfinite);
+            }
+        }
+        if (!ok) st[1] = 1u;
+        st[2] = (unsigned) steps;
+    }
+    const int slots[3] = {ST_CONN, ST_CONNFAIL, ST_CONNSTEPS};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        unsigned long long v = st[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(P.stats + slots[k], v);
+    }
+    if (nonfinite) atomicAdd(P.stats + ST_NONFINITE, (unsigned long long) nonfinite);
 }
 
 /* HDRFilm::develop: ESpectrumAlphaWeight -> RGB */
@@ -655,6 +715,13 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     MER_REQUIRE(r->filter == MER_FILTER_BOX || r->filter == MER_FILTER_GAUSSIAN, "unknown reconstruction filter");
     if (m->dev.aggressive)
         return mer::fail(MER_ERR_UNSUPPORTED, "aggressivetracing is only available in mer_medium_sample_distance_batch");
+    if (r->direct_connections) {
+        MER_REQUIRE(r->has_quad, "direct_connections needs the quad emitter");
+        if (m->rif->mode != MER_RIF_TRICUBIC)
+            return mer::fail(MER_ERR_UNSUPPORTED, "direct_connections needs the tricubic RIF mode (the solver differentiates the spline twice)");
+        if (m->dev.hasGrid)
+            return mer::fail(MER_ERR_UNSUPPORTED, "direct_connections with a density grid (transmittance along the curve) is not built");
+    }
     mer::DeviceGuard guard(m->device);
     cudaStream_t stream = (cudaStream_t) stream_;
 
@@ -678,6 +745,15 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.maxWait = 12;
     if (const char *e = getenv("MER_MAX_WAIT")) P.maxWait = atoi(e); /* tuning knob */
     P.film = film_dev;
+    P.nee = r->direct_connections ? 1 : 0;
+    /* the reference drops connections that leave the shape within sqrt(Epsilon) = 0.01 of p1; for next-event estimation that
+     * would discard the brightest vertices (those next to the surface facing the light), so only exact degeneracy is dropped */
+    P.M.minExit2 = 1e-10f;
+    P.neeTol2 = r->connection.tol2 > 0.0f ? r->connection.tol2 : 1e-6f;
+    P.neeRRWeight = r->connection.rrweight > 0.0f ? r->connection.rrweight : 1e-2f;
+    P.neePrecision = r->connection.boundary_precision > 0 ? r->connection.boundary_precision : 3;
+    P.neeMaxIterations = r->connection.max_iterations > 0 ? r->connection.max_iterations : 20;
+    P.neeStraightFirst = r->connection.start_mode != MER_START_RANDOM;
 
     const unsigned TPB = 128;
     unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 4096u;
@@ -697,6 +773,20 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         MER_CUDA(cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long)));
         MER_CUDA(cudaEventCreate(&S.ev0));
         MER_CUDA(cudaEventCreate(&S.ev1));
+    }
+    if (P.nee) {
+        const unsigned cap = std::min(pool * 2u, 1u << 21);
+        if (S.neeCap < cap) {
+            for (int i = 0; i < 3; i++) { cudaFree(S.neeQ[i]); S.neeQ[i] = nullptr; }
+            S.neeCap = 0;
+            for (int i = 0; i < 3; i++) MER_CUDA(cudaMalloc(&S.neeQ[i], (size_t) cap * 16));
+            if (!S.neeCount) MER_CUDA(cudaMalloc(&S.neeCount, sizeof(unsigned)));
+            S.neeCap = cap;
+        }
+        P.neeCap = cap;
+        P.neeCount = S.neeCount;
+        P.neeQ0 = (float4 *) S.neeQ[0]; P.neeQ1 = (float4 *) S.neeQ[1]; P.neeQ2 = (uint4 *) S.neeQ[2];
+        MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
     }
     PathPool A = {(float4 *) S.pool[0], (float4 *) S.pool[1], (float4 *) S.pool[2], (float4 *) S.pool[3], (uint4 *) S.pool[4], (float4 *) S.pool[5], (float4 *) S.pool[12]};
     PathPool B = {(float4 *) S.pool[6], (float4 *) S.pool[7], (float4 *) S.pool[8], (float4 *) S.pool[9], (uint4 *) S.pool[10], (float4 *) S.pool[11], (float4 *) S.pool[13]};
@@ -730,9 +820,18 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         /* the only host<->device traffic of a pass: 12 bytes telling the host how to size the next one */
         MER_CUDA(cudaMemcpyAsync(S.hostPinned, S.nOut, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
         MER_CUDA(cudaMemcpyAsync(S.hostPinned + 1, S.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        if (P.nee) MER_CUDA(cudaMemcpyAsync(S.hostPinned + 2, S.neeCount, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
         MER_CUDA(cudaStreamSynchronize(stream));
         nLive = *(unsigned *) S.hostPinned;
         started = S.hostPinned[1];
+        if (P.nee) {
+            const unsigned nReq = std::min(*(unsigned *) (S.hostPinned + 2), P.neeCap);
+            if (nReq) {
+                MER_LAUNCH(k_nee, (nReq + TPB - 1) / TPB, TPB, 0, stream, P, nReq);
+                launches++;
+                MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
+            }
+        }
         if (nLive == 0 && started >= P.totalSamples) break;
     }
     MER_CUDA(cudaEventRecord(S.ev1, stream));
@@ -747,6 +846,9 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         stats_out->null_collisions = hs[1 + ST_NULL];
         stats_out->boundary_exits = hs[1 + ST_EXIT];
         stats_out->nonfinite_dropped = hs[1 + ST_NONFINITE];
+        stats_out->connections = hs[1 + ST_CONN];
+        stats_out->connections_failed = hs[1 + ST_CONNFAIL];
+        stats_out->connection_steps = hs[1 + ST_CONNSTEPS];
         stats_out->passes = passes;
         stats_out->kernel_launches = launches;
         float ms = 0;

@@ -426,12 +426,13 @@ class HeterogeneousRefractiveMedium:
                                                        st.ctypes.data_as(C.POINTER(C.c_int32)), ns.ctypes.data_as(C.POINTER(C.c_int32))))
         return dict(error=err, derror=J, status=st, nsteps=ns)
 
-    def eval(self, vsp, vtp, seed_dir, is_sensor_sample=False, seed=1):
-        """HeterogeneousRefractiveMedium::eval over a batch of (p1 = vsp, p2 = vtp) pairs"""
+    def eval(self, vsp, vtp, seed_dir, is_sensor_sample=False, seed=1, start_mode=0):
+        """HeterogeneousRefractiveMedium::eval over a batch of (p1 = vsp, p2 = vtp) pairs
+        (start_mode: 0/1 random first guess as in the reference, 2 = first guess along seed_dir)"""
         p1, p2, sd = _f32(vsp, (-1, 3)), _f32(vtp, (-1, 3)), _f32(seed_dir, (-1, 3))
         n = p1.shape[0]
         cp = _abi.ConnectionParams(float(self.props.get("tol2", 1e-6)), float(self.props.get("rrweight", 1e-2)),
-                                   int(self.props.get("boundaryprecision", 3)), int(self.props.get("ceresmaxiterations", 20)))
+                                   int(self.props.get("boundaryprecision", 3)), int(self.props.get("ceresmaxiterations", 20)), int(start_mode))
         r = dict(success=np.zeros(n, np.uint8), dir_to_p2=np.zeros((n, 3), np.float32), rev_dir_to_p1=np.zeros((n, 3), np.float32),
                  optical_length=np.zeros(n, np.float32), distance=np.zeros(n, np.float32), weight=np.zeros(n, np.float32),
                  transmittance=np.zeros((n, 3), np.float32), pdf_success=np.zeros(n, np.float32), pdf_failure=np.zeros(n, np.float32),
@@ -456,7 +457,10 @@ class HeterogeneousRefractiveMedium:
 
 class EikonalVolPathIntegrator:
     """<integrator type="ervolpath">: props `maxDepth` (-1), `rrDepth` (5) (MonteCarloIntegrator,
-    src/librender/integrator.cpp:190-225) + scheduling knobs `poolPaths`, `stepsPerPass`."""
+    src/librender/integrator.cpp:190-225) + scheduling knobs `poolPaths`, `stepsPerPass`.
+    `directConnections` (false): next-event estimation of the quad emitter from every scattering vertex along the curved
+    connection (makeDirectConnections, heterogeneousrefractive.cpp:1087-1163); the solver reads the medium's `tol2`,
+    `rrweight`, `boundaryprecision`, `ceresmaxiterations` and the integrator's `connectionStart` ("straight" | "random")."""
 
     def __init__(self, props=None, **kw):
         props = dict(props or {}, **kw)
@@ -464,11 +468,15 @@ class EikonalVolPathIntegrator:
         self.rrDepth = int(props.get("rrDepth", 5))
         self.poolPaths = int(props.get("poolPaths", 0))
         self.stepsPerPass = int(props.get("stepsPerPass", 0))
+        self.directConnections = bool(props.get("directConnections", False))
+        self.connectionStart = str(props.get("connectionStart", "straight"))
+        if self.connectionStart not in ("straight", "random"):
+            raise _abi.MerError(_abi.MER_ERR_INVALID, 'connectionStart must be "straight" or "random"')
         if self.maxDepth == 0 or self.maxDepth < -1:
             raise _abi.MerError(_abi.MER_ERR_INVALID,
                                 "maxDepth must be set to -1 (infinite) or a value greater than zero!")
 
-    def render_desc(self, scene, sample_begin=0, sample_stride=1):
+    def render_desc(self, scene, sample_begin=0, sample_stride=1, medium=None):
         """`scene`: dict with sensor/film/emitter parameters (what the C++ shim reads off the Scene)"""
         r = _abi.RenderDesc()
         r.width, r.height = int(scene["width"]), int(scene["height"])
@@ -490,11 +498,18 @@ class EikonalVolPathIntegrator:
             r.quad_v[:] = [float(x) for x in quad["v"]]
             r.quad_radiance[:] = [float(x) for x in _spectrum(quad["radiance"])]
         r.pool_paths, r.steps_per_pass = self.poolPaths, self.stepsPerPass
+        r.direct_connections = 1 if self.directConnections else 0
+        mp = getattr(medium, "props", None) or {}
+        r.connection.tol2 = float(mp.get("tol2", 1e-6))
+        r.connection.rrweight = float(mp.get("rrweight", 1e-2))
+        r.connection.boundary_precision = int(mp.get("boundaryprecision", 3))
+        r.connection.max_iterations = int(mp.get("ceresmaxiterations", 20))
+        r.connection.start_mode = 1 if self.connectionStart == "random" else 2
         return r
 
     def render(self, scene, medium, sample_begin=0, sample_stride=1):
         """-> (film[H][W][5] = [R,G,B,alpha,weight], stats dict)"""
-        r = self.render_desc(scene, sample_begin, sample_stride)
+        r = self.render_desc(scene, sample_begin, sample_stride, medium)
         film = np.zeros((r.height, r.width, 5), np.float32)
         stats = _abi.RenderStats()
         check(lib.mer_render(medium.handle, C.byref(r), _fp(film), C.byref(stats)))
@@ -502,7 +517,7 @@ class EikonalVolPathIntegrator:
 
     def render_device(self, scene, medium, film_ptr, stream=None, sample_begin=0, sample_stride=1):
         """accumulate into a device film buffer (e.g. torch tensor .data_ptr()); -> stats dict"""
-        r = self.render_desc(scene, sample_begin, sample_stride)
+        r = self.render_desc(scene, sample_begin, sample_stride, medium)
         stats = _abi.RenderStats()
         check(lib.mer_render_device(medium.handle, C.byref(r), C.c_void_p(int(film_ptr)), C.byref(stats),
                                     C.c_void_p(int(stream)) if stream else None))

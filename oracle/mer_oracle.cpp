@@ -367,6 +367,55 @@ inline void hg_sample(float g, const float wi[3], float u1, float u2, float wo[3
 /* ------------------------------------------------------------------------------------------
  * a7-a14  HeterogeneousRefractiveMedium — src/medium/heterogeneousrefractive.cpp
  * ------------------------------------------------------------------------------------------ */
+/* fresnelDielectricExt, src/libcore/util.cpp:665-695 */
+inline float fresnelDielectricExt(float cosThetaI_, float &cosThetaT_, float eta) {
+    if (eta == 1) { cosThetaT_ = -cosThetaI_; return 0.0f; }
+    float scale = (cosThetaI_ > 0) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    float cosThetaI = std::abs(cosThetaI_), cosThetaT = std::sqrt(cosThetaTSqr);
+    float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+
+/* outward unit normal of the container at a surface point */
+inline void shapeNormal(const mer_medium_desc &m, const float p[3], float N[3]) {
+    if (m.shape_type == MER_SHAPE_SPHERE) {
+        float d[3] = {p[0] - m.shape[0], p[1] - m.shape[1], p[2] - m.shape[2]};
+        float l = 1.0f / std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int i = 0; i < 3; i++) N[i] = d[i] * l;
+        return;
+    }
+    int axis = 0;
+    float best = std::numeric_limits<float>::infinity(), sign = 1;
+    for (int i = 0; i < 3; i++) {
+        float a = std::abs(p[i] - m.shape[i]), b = std::abs(p[i] - m.shape[3 + i]);
+        if (a < best) { best = a; axis = i; sign = -1; }
+        if (b < best) { best = b; axis = i; sign = 1; }
+    }
+    N[0] = N[1] = N[2] = 0;
+    N[axis] = sign;
+}
+
+/* distance along a straight ray from a point inside the container to its surface */
+inline float exitDistance(const mer_medium_desc &m, const float o[3], const float d[3]) {
+    if (m.shape_type == MER_SHAPE_SPHERE) {
+        float oc[3] = {o[0] - m.shape[0], o[1] - m.shape[1], o[2] - m.shape[2]};
+        float b = oc[0] * d[0] + oc[1] * d[1] + oc[2] * d[2], c = oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2] - m.shape[3] * m.shape[3];
+        float disc = b * b - c;
+        return disc > 0 ? std::max(-b + std::sqrt(disc), 0.0f) : 0.0f;
+    }
+    float t1 = std::numeric_limits<float>::infinity();
+    for (int i = 0; i < 3; i++) {
+        if (d[i] == 0) continue;
+        float inv = 1.0f / d[i];
+        float ta = (m.shape[i] - o[i]) * inv, tb = (m.shape[3 + i] - o[i]) * inv;
+        t1 = std::min(t1, std::max(ta, tb));
+    }
+    return std::max(t1, 0.0f);
+}
+
 template <typename F> struct Medium {
     const SplineVolume<F> *rif;
     const SplineVolume<F> *sdf = nullptr; /* <volume name="sdf">, used by aggressive tracing (a10) */
@@ -560,18 +609,34 @@ template <typename F> struct Medium {
     }
 
     int boundaryprecision = 3; /* `boundaryprecision` */
+    F minExit2 = kEpsilon;     /* :891: a connection that leaves the shape within sqrt(Epsilon) of p1 is degenerate */
     F tol2 = (F) 1e-6;         /* `tol2` */
 
     /* computefdfBDPT, :816-939: residual p(t*) - p2 and its Jacobian w.r.t. the launch velocity.
-     * returns 0 = closest approach inside, 1 = left the object (needs sdf), 2 = degenerate (error = p1 - p2, J = 0) */
-    int computefdf(const F *v_i, const F *p1, const F *p2, bool isSensorSample, F *err, F *derr, long &count) const {
+     * returns 0 = closest approach inside, 1 = left the object, 2 = degenerate (error = p1 - p2, J = 0),
+     * 3 = left the object by total internal reflection */
+    /* outward unit normal at the container surface: sdf gradient (:892-893) or, without an sdf child, the analytic one */
+    void containerNormal(const F *p, F *N) const {
+        if (sdf) {
+            sdf->gradient(p, N);
+            F nl = (F) 1 / std::sqrt(dot(N, N));
+            for (int i = 0; i < 3; i++) N[i] *= nl;
+            return;
+        }
+        float pf[3] = {(float) p[0], (float) p[1], (float) p[2]}, Nf[3];
+        shapeNormal(d, pf, Nf);
+        for (int i = 0; i < 3; i++) N[i] = (F) Nf[i];
+    }
+
+    /* `refract` = reference behaviour (Snell to exterior index 1); false = index-matched container, velocity unchanged */
+    int computefdf(const F *v_i, const F *p1, const F *p2, bool isSensorSample, F *err, F *derr, long &count, bool refract = true) const {
         F A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, B[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         for (int i = 0; i < 9; i++) derr[i] = 0;
         if (!(sdf ? sdf : rif)->insideVolumeLimits(p1)) { for (int i = 0; i < 3; i++) err[i] = p1[i] - p2[i]; return 2; }
         F h0 = h;
         const int maxSteps = 100000;
         long nBisect = (long) std::ceil(boundaryprecision / std::log10(2.0));
-        bool leftObject = false;
+        bool leftObject = false, tir = false;
         F p[3] = {p1[0], p1[1], p1[2]}, v[3] = {v_i[0], v_i[1], v_i[2]}, oldp[3], oldv[3], oldA[9], oldB[9], d[3];
         for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
         bool signOld = std::signbit(dot(d, v)), signNew;
@@ -611,18 +676,25 @@ template <typename F> struct Medium {
                     if (insideShape(p)) save();
                 }
                 F dp1[3] = {p[0] - p1[0], p[1] - p1[1], p[2] - p1[2]};
-                if (dot(dp1, dp1) < kEpsilon || !sdf) { for (int i = 0; i < 3; i++) err[i] = p1[i] - p2[i]; for (int i = 0; i < 9; i++) derr[i] = 0; return sdf ? 2 : 1; }
+                if (dot(dp1, dp1) < minExit2) { for (int i = 0; i < 3; i++) err[i] = p1[i] - p2[i]; for (int i = 0; i < 9; i++) derr[i] = 0; return 2; }
                 F nb, dnb[3], dpdtb[3], N[3], dtb[3];
                 rif->valueAndGradient(p, &nb, dnb);
                 F rn = (F) 1 / nb;
                 for (int i = 0; i < 3; i++) dpdtb[i] = v[i] * rn;
-                sdf->gradient(p, N);
-                F nl = (F) 1 / std::sqrt(dot(N, N));
-                for (int i = 0; i < 3; i++) N[i] *= nl;
+                containerNormal(p, N);
                 preMult(A, N, dtb);
                 F den = dot(N, dpdtb);
                 for (int i = 0; i < 3; i++) dtb[i] = -dtb[i] / den;
-                boundaryVelocityDerivative(v, B, dtb, dnb, N, nb, (F) 1.0);
+                if (refract) {
+                    F dotp = dot(v, N), rr = (F) 1 / nb;
+                    rr = rr * rr - 1;
+                    tir = rr * dot(v, v) + dotp * dotp < kEpsilon;
+                    boundaryVelocityDerivative(v, B, dtb, dnb, N, nb, (F) 1.0);
+                } else {
+                    F S[9];
+                    outer(dnb, dtb, S);
+                    for (int i = 0; i < 9; i++) B[i] += S[i];
+                }
                 for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
                 F extra_t = -dot(v, d) / dot(v, v);
                 leftObject = true;
@@ -654,7 +726,7 @@ template <typename F> struct Medium {
         outer(dpdt, dts, O);
         for (int i = 0; i < 3; i++) err[i] = d[i];
         for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) derr[3 * i + j] = A[3 * j + i] + O[3 * j + i]; /* transposed, :936-938 */
-        return leftObject ? 1 : 0;
+        return leftObject ? (tir ? 3 : 1) : 0; /* 3: total internal reflection at the boundary (the reference reflects and goes on, :1041-1044) */
     }
 
     struct Record {
@@ -863,7 +935,11 @@ struct StraightWoodcock {
  * SAME residual and Jacobian (computefdf above), written identically in the CUDA path.  PARITY UNPINNED at
  * the solver: results are validated by the residual they reach, not against Ceres.
  * ------------------------------------------------------------------------------------------ */
+struct ExitInfo { bool exited = false, tir = false; float nb = 1, cosI = 1; };
+
 template <typename F> struct ConnectionResult {
+    ExitInfo exit;
+    F n1;
     bool success;
     F dirToP2[3], revDirToP1[3], opticalDist, dist, weight;
     float transmittance[3], pdfSuccess, pdfFailure;
@@ -882,7 +958,9 @@ template <typename F> bool solve3(const F *Mx, const F *b, F *x) { /* symmetric 
 
 /* computePathLengthsTillClosestP2, :941-1030 */
 template <typename F>
-bool computePathLengths(const Medium<F> &M, const F *p1, const F *p2, const F *dirToP2, F *revDir, bool isSensorSample, F &opl, F &dist) {
+bool computePathLengths(const Medium<F> &M, const F *p1, const F *p2, const F *dirToP2, F *revDir, bool isSensorSample, F &opl, F &dist,
+                        bool refract, ExitInfo &ex) {
+    ex = ExitInfo();
     dist = 0;
     opl = 0;
     F h0 = M.h;
@@ -897,7 +975,7 @@ bool computePathLengths(const Medium<F> &M, const F *p1, const F *p2, const F *d
         for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
         signNew = std::signbit(Medium<F>::dot(d, v));
         if (!M.insideShape(p)) {
-            if (!isSensorSample || !M.sdf) return false;
+            if (!isSensorSample) return false;
             while (nBisect > 0) {
                 nBisect--;
                 for (int i = 0; i < 3; i++) { p[i] = oldp[i]; v[i] = oldv[i]; }
@@ -910,10 +988,17 @@ bool computePathLengths(const Medium<F> &M, const F *p1, const F *p2, const F *d
                 }
             }
             F N[3];
-            M.sdf->gradient(p, N);
-            F nl = (F) 1 / std::sqrt(Medium<F>::dot(N, N));
-            for (int i = 0; i < 3; i++) N[i] *= nl;
-            Medium<F>::boundaryVelocity(v, N, M.rif->value(p), (F) 1.0);
+            M.containerNormal(p, N);
+            const F nb = M.rif->value(p);
+            ex.exited = true;
+            ex.nb = (float) nb;
+            ex.cosI = (float) (Medium<F>::dot(v, N) / std::sqrt(Medium<F>::dot(v, v)));
+            if (refract) {
+                F dotp = Medium<F>::dot(v, N), rr = (F) 1 / nb;
+                rr = rr * rr - 1;
+                ex.tir = rr * Medium<F>::dot(v, v) + dotp * dotp < kEpsilon;
+                Medium<F>::boundaryVelocity(v, N, nb, (F) 1.0);
+            }
             for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
             F extra_t = -Medium<F>::dot(v, d) / Medium<F>::dot(v, v);
             if (extra_t < 0) return false;
@@ -950,8 +1035,10 @@ bool computePathLengths(const Medium<F> &M, const F *p1, const F *p2, const F *d
 
 template <typename F>
 void connect(const Medium<F> &M, const F *p1, const F *p2, const F *dseed, bool isSensorSample, float rrweight, int maxIterations,
-             PhiloxStream &rng, ConnectionResult<F> &R) {
+             PhiloxStream &rng, ConnectionResult<F> &R, bool refract = true, long *steps = nullptr, bool straightFirst = false) {
     R.success = false;
+    R.exit = ExitInfo();
+    R.n1 = 1;
     R.weight = 1;
     R.opticalDist = R.dist = 0;
     R.evaluations = 0;
@@ -959,24 +1046,49 @@ void connect(const Medium<F> &M, const F *p1, const F *p2, const F *dseed, bool 
     R.pdfSuccess = R.pdfFailure = 1.0f; /* failed case of eval(), :618-624 */
     if (!(M.sdf ? M.sdf : M.rif)->insideVolumeLimits(p1)) return;
     const F RIFp = M.rif->value(p1);
+    R.n1 = RIFp;
     F x[3];
     bool converged = false;
     while (true) {
         /* uniformSample, :1078-1084 + warp::squareToUniformHemisphere (src/libcore/warp.cpp:33-41) */
         float din[3] = {(float) dseed[0], (float) dseed[1], (float) dseed[2]}, ax[3], ay[3];
         coordinateSystem(din, ax, ay);
-        float u1 = rng.next(), u2 = rng.next();
-        float z = u1, tmp = std::sqrt(std::max(0.0f, 1.0f - z * z)), phi = (float) (2.0f * M_PI * u2);
-        float lx = cosf(phi) * tmp, ly = sinf(phi) * tmp;
-        for (int i = 0; i < 3; i++) x[i] = (F) (lx * ax[i] + ly * ay[i] + z * din[i]) * RIFp;
+        if (straightFirst) { /* MER_START_STRAIGHT: the first guess is the seed direction itself ... */
+            straightFirst = false;
+            float g[3] = {din[0], din[1], din[2]};
+            if (refract && !M.sdf) {
+                /* ... bent by Snell's law at the point where the straight line leaves an analytic container, as if the
+                 * exterior direction were the seed direction: sin(theta_i) = sin(theta_seed) / n, never totally reflected */
+                float pf[3] = {(float) p1[0], (float) p1[1], (float) p1[2]}, pe[3], N[3];
+                float te = exitDistance(M.d, pf, din);
+                for (int i = 0; i < 3; i++) pe[i] = pf[i] + te * din[i];
+                shapeNormal(M.d, pe, N);
+                float c = din[0] * N[0] + din[1] * N[1] + din[2] * N[2];
+                if (c > 0) {
+                    float inv = 1.0f / (float) RIFp, gt[3], t2 = 0;
+                    for (int i = 0; i < 3; i++) { gt[i] = (din[i] - c * N[i]) * inv; t2 += gt[i] * gt[i]; }
+                    float gn = std::sqrt(std::max(0.0f, 1.0f - t2));
+                    for (int i = 0; i < 3; i++) g[i] = gt[i] + gn * N[i];
+                }
+            }
+            for (int i = 0; i < 3; i++) x[i] = (F) g[i] * RIFp;
+        } else {
+            float u1 = rng.next(), u2 = rng.next();
+            float z = u1, tmp = std::sqrt(std::max(0.0f, 1.0f - z * z)), phi = (float) (2.0f * M_PI * u2);
+            float lx = cosf(phi) * tmp, ly = sinf(phi) * tmp;
+            for (int i = 0; i < 3; i++) x[i] = (F) (lx * ax[i] + ly * ay[i] + z * din[i]) * RIFp;
+        }
         /* Levenberg-Marquardt on r(x) = p(t*) - p2, J = d r / d x (= derror^T) */
         F r[3], Jt[9], cost, lambda = 0;
         long cnt = 0;
-        M.computefdf(x, p1, p2, isSensorSample, r, Jt, cnt);
+        /* evaluations that end degenerate or totally reflected carry no usable residual: infinite cost */
+        const F kInf = std::numeric_limits<F>::infinity();
+        int status = M.computefdf(x, p1, p2, isSensorSample, r, Jt, cnt, refract);
         R.evaluations++;
-        cost = (F) 0.5 * Medium<F>::dot(r, r);
+        cost = status >= 2 ? kInf : (F) 0.5 * Medium<F>::dot(r, r);
         int accepted = 0;
-        for (int ev = 0; ev < 2 * maxIterations && accepted < maxIterations && !(cost < M.tol2); ev++) {
+        /* iterate to |r|^2 < tol2 / 4 so that the re-trace's |p - p2|^2 <= tol2 test (:1023-1027) is met with margin */
+        for (int ev = 0; ev < 2 * maxIterations && accepted < maxIterations && !(cost < (F) 0.125 * M.tol2) && cost < kInf; ev++) {
             /* normal equations: (J^T J + lambda I) dx = -J^T r with J^T = Jt (row j of Jt = d r / d x_j) */
             F JTJ[9], g[3], dx[3];
             for (int a = 0; a < 3; a++) {
@@ -987,9 +1099,9 @@ void connect(const Medium<F> &M, const F *p1, const F *p2, const F *dseed, bool 
             JTJ[0] += lambda; JTJ[4] += lambda; JTJ[8] += lambda;
             if (!solve3<F>(JTJ, g, dx)) break;
             F xn[3] = {x[0] + dx[0], x[1] + dx[1], x[2] + dx[2]}, rn[3], Jn[9];
-            M.computefdf(xn, p1, p2, isSensorSample, rn, Jn, cnt);
+            status = M.computefdf(xn, p1, p2, isSensorSample, rn, Jn, cnt, refract);
             R.evaluations++;
-            F costn = (F) 0.5 * Medium<F>::dot(rn, rn);
+            F costn = status >= 2 ? kInf : (F) 0.5 * Medium<F>::dot(rn, rn);
             if (costn < cost) {
                 for (int i = 0; i < 3; i++) { x[i] = xn[i]; r[i] = rn[i]; }
                 for (int i = 0; i < 9; i++) Jt[i] = Jn[i];
@@ -1001,6 +1113,7 @@ void connect(const Medium<F> &M, const F *p1, const F *p2, const F *dseed, bool 
                 if (lambda > (F) 1e12) break;
             }
         }
+        if (steps) *steps += cnt;
         if (cost < M.tol2) { converged = true; break; } /* :1121-1138 always ends with multiplicity weight 1 */
         if (rng.next() < rrweight) R.weight = R.weight * (1 / (F) rrweight); /* :1146-1155 */
         else break;
@@ -1008,7 +1121,7 @@ void connect(const Medium<F> &M, const F *p1, const F *p2, const F *dseed, bool 
     F xl = (F) 1 / std::sqrt(Medium<F>::dot(x, x));
     for (int i = 0; i < 3; i++) R.dirToP2[i] = (x[i] * xl) * RIFp;
     if (!converged) return;
-    if (!computePathLengths<F>(M, p1, p2, R.dirToP2, R.revDirToP1, isSensorSample, R.opticalDist, R.dist)) return;
+    if (!computePathLengths<F>(M, p1, p2, R.dirToP2, R.revDirToP1, isSensorSample, R.opticalDist, R.dist, refract, R.exit)) return;
     R.success = true;
     /* eval(), :585-617 */
     const float distance = (float) R.dist;
@@ -1177,55 +1290,6 @@ inline bool intersectQuad(const mer_render_desc &r, const float o[3], const floa
  * grid the free flight is Woodcock tracking (src/medium/heterogeneous.cpp:613-658) along the
  * curved ray (new composition, R2).
  * ------------------------------------------------------------------------------------------ */
-/* fresnelDielectricExt, src/libcore/util.cpp:665-695 */
-inline float fresnelDielectricExt(float cosThetaI_, float &cosThetaT_, float eta) {
-    if (eta == 1) { cosThetaT_ = -cosThetaI_; return 0.0f; }
-    float scale = (cosThetaI_ > 0) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
-    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
-    float cosThetaI = std::abs(cosThetaI_), cosThetaT = std::sqrt(cosThetaTSqr);
-    float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
-    float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
-    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
-    return 0.5f * (Rs * Rs + Rp * Rp);
-}
-
-/* outward unit normal of the container at a surface point */
-inline void shapeNormal(const mer_medium_desc &m, const float p[3], float N[3]) {
-    if (m.shape_type == MER_SHAPE_SPHERE) {
-        float d[3] = {p[0] - m.shape[0], p[1] - m.shape[1], p[2] - m.shape[2]};
-        float l = 1.0f / std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        for (int i = 0; i < 3; i++) N[i] = d[i] * l;
-        return;
-    }
-    int axis = 0;
-    float best = std::numeric_limits<float>::infinity(), sign = 1;
-    for (int i = 0; i < 3; i++) {
-        float a = std::abs(p[i] - m.shape[i]), b = std::abs(p[i] - m.shape[3 + i]);
-        if (a < best) { best = a; axis = i; sign = -1; }
-        if (b < best) { best = b; axis = i; sign = 1; }
-    }
-    N[0] = N[1] = N[2] = 0;
-    N[axis] = sign;
-}
-
-/* distance along a straight ray from a point inside the container to its surface */
-inline float exitDistance(const mer_medium_desc &m, const float o[3], const float d[3]) {
-    if (m.shape_type == MER_SHAPE_SPHERE) {
-        float oc[3] = {o[0] - m.shape[0], o[1] - m.shape[1], o[2] - m.shape[2]};
-        float b = oc[0] * d[0] + oc[1] * d[1] + oc[2] * d[2], c = oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2] - m.shape[3] * m.shape[3];
-        float disc = b * b - c;
-        return disc > 0 ? std::max(-b + std::sqrt(disc), 0.0f) : 0.0f;
-    }
-    float t1 = std::numeric_limits<float>::infinity();
-    for (int i = 0; i < 3; i++) {
-        if (d[i] == 0) continue;
-        float inv = 1.0f / d[i];
-        float ta = (m.shape[i] - o[i]) * inv, tb = (m.shape[3 + i] - o[i]) * inv;
-        t1 = std::min(t1, std::max(ta, tb));
-    }
-    return std::max(t1, 0.0f);
-}
-
 /* HSmoothDielectric::sample (src/bsdfs/hdielectric.cpp:244-300), ERadiance mode, both components enabled.
  * d: unit direction of travel, N: outward normal, eta = RIF at the hit point.  Returns true for transmission. */
 inline bool hdielectricSample(const float d[3], const float N[3], float eta, float u, float dOut[3], float &weight, float &etaScale) {
@@ -1250,16 +1314,82 @@ inline bool hdielectricSample(const float d[3], const float N[3], float eta, flo
 
 struct Stats {
     uint64_t samples = 0, raySteps = 0, scatter = 0, nullColl = 0, exits = 0, nonfinite = 0;
+    uint64_t connections = 0, connFailed = 0, connSteps = 0;
 };
+
+const uint64_t kNeeSalt = 0x5851F42D4C957F2DULL; /* next-event estimation draws come from their own Philox key */
+
+/* Next-event estimation of the quad emitter from a scattering vertex p1 of the medium.  The curved
+ * connection is the reference's shooting problem (makeDirectConnections); the estimator around it is
+ *     thr * phase(wi, w) * exp(-sigma_t * dist) * (n_b / n_1)^2 [* (1 - Fresnel) * n_b^2 for hdielectric]
+ *         * Le * |cos theta_y| * Area / |d r_perp / d omega|
+ * i.e. the random walk's own exit-edge weights (refRatioSq, BSDF factor) with the change of variables from the
+ * launch direction at p1 to the sampled point y written with the solver's Jacobian instead of 1/distance^2. */
+template <typename F>
+void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, const float wi[3], const float thr[3], int depth,
+                 uint64_t sampleId, float L[3], Stats &st) {
+    PhiloxStream nrng;
+    nrng.init(R.seed ^ kNeeSalt, sampleId);
+    nrng.ctr[2] = (uint32_t) depth * 64u; /* 256 draws per vertex */
+    const float u = nrng.next(), w = nrng.next();
+    const float *qu = R.quad_u, *qv = R.quad_v;
+    float Nq[3] = {qu[1] * qv[2] - qu[2] * qv[1], qu[2] * qv[0] - qu[0] * qv[2], qu[0] * qv[1] - qu[1] * qv[0]};
+    const float area = std::sqrt(Nq[0] * Nq[0] + Nq[1] * Nq[1] + Nq[2] * Nq[2]);
+    F y[3], dseed[3];
+    float dl = 0;
+    for (int i = 0; i < 3; i++) {
+        float yi = R.quad_origin[i] + u * qu[i] + w * qv[i];
+        y[i] = (F) yi;
+        dseed[i] = (F) (yi - (float) p1[i]);
+        dl += (float) dseed[i] * (float) dseed[i];
+    }
+    dl = 1.0f / std::sqrt(dl);
+    for (int i = 0; i < 3; i++) dseed[i] = (F) ((float) dseed[i] * dl);
+    const bool refract = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
+    const float rrweight = R.connection.rrweight > 0 ? R.connection.rrweight : 1e-2f;
+    const int maxIt = R.connection.max_iterations > 0 ? R.connection.max_iterations : 20;
+    ConnectionResult<F> C;
+    long steps = 0;
+    connect<F>(M, p1, y, dseed, true, rrweight, maxIt, nrng, C, refract, &steps, R.connection.start_mode != MER_START_RANDOM);
+    st.connections++;
+    if (!C.success || !C.exit.exited || C.exit.tir) { st.connSteps += steps; st.connFailed++; return; }
+    F r[3], Jt[9];
+    M.computefdf(C.dirToP2, p1, y, true, r, Jt, steps, refract);
+    st.connSteps += steps;
+    const F *m = Jt;
+    const F cof[9] = {m[4] * m[8] - m[5] * m[7], m[5] * m[6] - m[3] * m[8], m[3] * m[7] - m[4] * m[6],
+                      m[2] * m[7] - m[1] * m[8], m[0] * m[8] - m[2] * m[6], m[1] * m[6] - m[0] * m[7],
+                      m[1] * m[5] - m[2] * m[4], m[2] * m[3] - m[0] * m[5], m[0] * m[4] - m[1] * m[3]};
+    F ss = 0;
+    for (int i = 0; i < 9; i++) ss += cof[i] * cof[i];
+    const float n1 = (float) C.n1, spread = n1 * n1 * (float) std::sqrt(ss);
+    if (!(spread > 0)) { st.connFailed++; return; }
+    float cosY = 0, wo[3];
+    for (int i = 0; i < 3; i++) { cosY += (float) C.revDirToP1[i] * (Nq[i] / area); wo[i] = (float) C.dirToP2[i] / n1; }
+    cosY = std::abs(cosY);
+    const float phase = hg_eval(M.d.hg_g, wi, wo);
+    float scale = (float) ((F) (1.0 / (C.n1 * C.n1)) * (F) C.exit.nb * (F) C.exit.nb);
+    if (refract) {
+        float cosT, Fr = fresnelDielectricExt(-C.exit.cosI, cosT, C.exit.nb);
+        scale *= (1.0f - Fr) * (C.exit.nb * C.exit.nb);
+    }
+    const float geom = cosY * area / spread;
+    for (int c = 0; c < 3; c++) {
+        float T = (float) std::exp((double) (M.sigmaT[c] * (float) (-C.dist)));
+        L[c] += thr[c] * phase * T * (float) C.weight * scale * R.quad_radiance[c] * geom;
+    }
+}
 
 template <typename F>
 void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const float dcam[3], PhiloxStream &rng,
-        float L[3], float &alpha, Stats &st) {
+        float L[3], float &alpha, Stats &st, uint64_t sampleId = 0) {
     L[0] = L[1] = L[2] = 0;
     alpha = 0;
     float thr[3] = {1, 1, 1}, etaPath = 1.0f;
     int depth = 1;
     const bool dielectric = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
+    const bool nee = R.direct_connections != 0 && R.has_quad && !M.density;
+    bool covered = false; /* the quad's light along the current edge chain was already estimated by a direct connection */
     float tBox, tQuad;
     bool hitBox = intersectShape(M.d, o, dcam, tBox);
     bool hitQuad = intersectQuad(R, o, dcam, tQuad);
@@ -1280,7 +1410,9 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
     /* straight escape from point q in direction e: emitters are gathered by hitting them */
     auto escape = [&](const float q[3], const float e[3]) {
         float tq;
-        const float *Le = intersectQuad(R, q, e, tq) ? R.quad_radiance : R.env_radiance;
+        const bool hitsQuad = intersectQuad(R, q, e, tq);
+        if (hitsQuad && covered) return;
+        const float *Le = hitsQuad ? R.quad_radiance : R.env_radiance;
         for (int i = 0; i < 3; i++) L[i] += thr[i] * Le[i];
     };
     /* Russian roulette of volpath.cpp:326-336 (eta = product of the BSDFs' relative indices) */
@@ -1310,6 +1442,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         etaPath *= es;
         for (int i = 0; i < 3; i++) dir[i] = (F) dOut[i];
         bool inside = fromOutside ? transmitted : !transmitted;
+        if (inside) covered = false; /* an internal reflection starts a chain no direct connection accounts for */
         if (!inside) { escape(pf, dOut); return false; } /* rayIntersectAndLookForEmitter with a delta BSDF: weight 1 */
         return roulette();
     };
@@ -1396,6 +1529,10 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             for (int i = 0; i < 3; i++) thr[i] *= edge[i] * refRatioSq;
             /* phase sampling: wi = normalize(-mRec.d) */
             float wi[3] = {(float) (-v[0] * vinv), (float) (-v[1] * vinv), (float) (-v[2] * vinv)}, wo[3];
+            if (nee) {
+                covered = true;
+                if (R.max_depth == -1 || depth + 1 < R.max_depth) directLight<F>(M, R, p, wi, thr, depth, sampleId, L, st);
+            }
             float u1 = rng.next(), u2 = rng.next();
             hg_sample(M.d.hg_g, wi, u1, u2, wo);
             for (int i = 0; i < 3; i++) dir[i] = (F) wo[i];
@@ -1421,6 +1558,10 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
 template <typename F>
 void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_render_stats *out, int nthreads) {
     const int W = R.width, H = R.height, B = 32;
+    Medium<F> Mr = M; /* solver parameters of the direct connections live on the medium */
+    if (R.connection.tol2 > 0) Mr.tol2 = (F) R.connection.tol2;
+    if (R.connection.boundary_precision > 0) Mr.boundaryprecision = R.connection.boundary_precision;
+    Mr.minExit2 = (F) 1e-10; /* next-event estimation keeps the vertices next to the surface */
     Filter flt;
     flt.configure(R.filter);
     Camera cam;
@@ -1445,7 +1586,7 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
                         float sx = x + rng.next(), sy = y + rng.next();
                         float d[3], L[3], alpha;
                         cam.sampleRay(sx, sy, d);
-                        Li<F>(M, R, cam.o, d, rng, L, alpha, st);
+                        Li<F>(Mr, R, cam.o, d, rng, L, alpha, st, ((uint64_t) y * W + x) * (uint64_t) R.spp_total + (uint64_t) s);
                         st.samples++;
                         float value[5] = {L[0], L[1], L[2], alpha, 1.0f};
                         if (!film_put(local.data(), W, H, flt, sx, sy, value)) st.nonfinite++;
@@ -1456,6 +1597,7 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
             for (size_t i = 0; i < local.size(); i++) film[i] += local[i];
             total.samples += st.samples; total.raySteps += st.raySteps; total.scatter += st.scatter;
             total.nullColl += st.nullColl; total.exits += st.exits; total.nonfinite += st.nonfinite;
+            total.connections += st.connections; total.connFailed += st.connFailed; total.connSteps += st.connSteps;
         }
     }
     if (out) {
@@ -1463,6 +1605,7 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
         out->samples = total.samples; out->ray_steps = total.raySteps; out->scatter_events = total.scatter;
         out->null_collisions = total.nullColl; out->boundary_exits = total.exits;
         out->nonfinite_dropped = total.nonfinite;
+        out->connections = total.connections; out->connections_failed = total.connFailed; out->connection_steps = total.connSteps;
     }
 }
 
@@ -1536,7 +1679,7 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
         const Medium<F> *m = (const Medium<F> *) h;                                                               \
         _Pragma("omp parallel for schedule(dynamic, 16)") for (long i = 0; i < (long) n; i++) {                   \
             long c = 0;                                                                                           \
-            status[i] = m->computefdf(v0 + 3 * i, p1 + 3 * i, p2 + 3 * i, isSensor != 0, err + 3 * i, derr + 9 * i, c); \
+            status[i] = m->computefdf(v0 + 3 * i, p1 + 3 * i, p2 + 3 * i, isSensor != 0, err + 3 * i, derr + 9 * i, c, m->d.boundary == MER_BOUNDARY_HDIELECTRIC); \
             if (nsteps) nsteps[i] = (int32_t) c;                                                                  \
         }                                                                                                         \
     }                                                                                                             \
@@ -1601,7 +1744,7 @@ ORC_API(double, _d)
     extern "C" void orc_medium_connect##SUF(void *h, size_t n, const F *p1, const F *p2, const F *dseed, int isSensor,  \
                                             float tol2, float rrweight, int precision, int maxIterations, uint64_t seed, \
                                             uint8_t *success, F *dirToP2, F *revDir, F *opl, F *dist, F *weight,   \
-                                            float *transmittance, float *pdfSuccess, float *pdfFailure, int32_t *evals) { \
+                                            float *transmittance, float *pdfSuccess, float *pdfFailure, int32_t *evals, int startMode) { \
         Medium<F> *m = (Medium<F> *) h;                                                                           \
         m->tol2 = (F) tol2;                                                                                       \
         m->boundaryprecision = precision;                                                                         \
@@ -1609,7 +1752,7 @@ ORC_API(double, _d)
             PhiloxStream rng;                                                                                     \
             rng.init(seed, (uint64_t) i);                                                                         \
             ConnectionResult<F> R;                                                                                \
-            connect<F>(*m, p1 + 3 * i, p2 + 3 * i, dseed + 3 * i, isSensor != 0, rrweight, maxIterations, rng, R); \
+            connect<F>(*m, p1 + 3 * i, p2 + 3 * i, dseed + 3 * i, isSensor != 0, rrweight, maxIterations, rng, R, m->d.boundary == MER_BOUNDARY_HDIELECTRIC, nullptr, startMode == MER_START_STRAIGHT); \
             success[i] = R.success;                                                                               \
             opl[i] = R.opticalDist; dist[i] = R.dist; weight[i] = R.weight;                                       \
             pdfSuccess[i] = R.pdfSuccess; pdfFailure[i] = R.pdfFailure; evals[i] = R.evaluations;                  \

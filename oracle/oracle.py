@@ -32,6 +32,12 @@ class MediumDesc(C.Structure):
                 ("hg_g", C.c_float), ("density_scale", C.c_float), ("albedo", C.c_float * 3), ("boundary", C.c_int32)]
 
 
+class ConnectionParams(C.Structure):
+    """mirror of mer_connection_params"""
+    _fields_ = [("tol2", C.c_float), ("rrweight", C.c_float), ("boundary_precision", C.c_int32), ("max_iterations", C.c_int32),
+                ("start_mode", C.c_int32)]
+
+
 class RenderDesc(C.Structure):
     """mirror of mer_render_desc"""
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp_total", C.c_int32),
@@ -40,14 +46,16 @@ class RenderDesc(C.Structure):
                 ("fov_deg", C.c_float), ("filter", C.c_int32), ("max_depth", C.c_int32), ("rr_depth", C.c_int32),
                 ("env_radiance", C.c_float * 3), ("has_quad", C.c_int32), ("quad_origin", C.c_float * 3),
                 ("quad_u", C.c_float * 3), ("quad_v", C.c_float * 3), ("quad_radiance", C.c_float * 3),
-                ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32)]
+                ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32), ("direct_connections", C.c_int32),
+                ("connection", ConnectionParams)]
 
 
 class RenderStats(C.Structure):
     """mirror of mer_render_stats"""
     _fields_ = [("samples", C.c_uint64), ("ray_steps", C.c_uint64), ("scatter_events", C.c_uint64),
                 ("null_collisions", C.c_uint64), ("boundary_exits", C.c_uint64),
-                ("nonfinite_dropped", C.c_uint64), ("passes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("nonfinite_dropped", C.c_uint64), ("passes", C.c_uint64), ("connections", C.c_uint64),
+                ("connections_failed", C.c_uint64), ("connection_steps", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_float)]
 
     def as_dict(self):
@@ -265,7 +273,7 @@ class Oracle:
                                                    _ptr(st, C.c_int32), _ptr(ns, C.c_int32))
         return dict(error=err, derror=J, status=st, nsteps=ns)
 
-    def connect(self, h, p1, p2, dseed, is_sensor=False, tol2=1e-6, rrweight=1e-2, precision=3, max_iterations=20, seed=1):
+    def connect(self, h, p1, p2, dseed, is_sensor=False, tol2=1e-6, rrweight=1e-2, precision=3, max_iterations=20, seed=1, start_mode=0):
         p1 = np.ascontiguousarray(p1, dtype=self.dtype).reshape(-1, 3)
         p2 = np.ascontiguousarray(p2, dtype=self.dtype).reshape(-1, 3)
         ds = np.ascontiguousarray(dseed, dtype=self.dtype).reshape(-1, 3)
@@ -279,7 +287,7 @@ class Oracle:
                                        _ptr(r["success"], C.c_uint8), _ptr(r["dir_to_p2"], self.ct), _ptr(r["rev_dir"], self.ct),
                                        _ptr(r["optical_dist"], self.ct), _ptr(r["dist"], self.ct), _ptr(r["weight"], self.ct),
                                        _ptr(r["transmittance"], C.c_float), _ptr(r["pdf_success"], C.c_float), _ptr(r["pdf_failure"], C.c_float),
-                                       _ptr(r["evaluations"], C.c_int32))
+                                       _ptr(r["evaluations"], C.c_int32), C.c_int(start_mode))
         r["success"] = r["success"].astype(bool)
         return r
 

@@ -93,7 +93,8 @@ def scene_dict(width=64, height=64, spp=16, rfilter="gaussian", quad=True, seed=
     return s
 
 
-def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_stride=1):
+def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_stride=1, direct_connections=False, props=None,
+                       start="straight"):
     from oracle.oracle import RenderDesc
     r = RenderDesc()
     r.width, r.height, r.spp_total = scene["width"], scene["height"], scene["sampleCount"]
@@ -114,4 +115,11 @@ def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_s
         r.quad_u[:] = q["u"]
         r.quad_v[:] = q["v"]
         r.quad_radiance[:] = q["radiance"]
+    r.direct_connections = 1 if direct_connections else 0
+    props = props or {}
+    r.connection.tol2 = float(props.get("tol2", 1e-6))
+    r.connection.rrweight = float(props.get("rrweight", 1e-2))
+    r.connection.boundary_precision = int(props.get("boundaryprecision", 3))
+    r.connection.max_iterations = int(props.get("ceresmaxiterations", 20))
+    r.connection.start_mode = 1 if start == "random" else 2
     return r

@@ -40,10 +40,11 @@ def test_struct_layouts_match_the_header(tmp_path):
               "mer_medium_desc": ["sigma_a", "sigma_s", "stepsize", "medium_sampling_weight", "strategy", "channel",
                                   "sampling_density", "shape_type", "shape", "hg_g", "density_scale", "albedo", "boundary"],
               "mer_render_desc": ["width", "spp_total", "sample_stride", "seed", "cam_origin", "fov_deg", "filter",
-                                  "max_depth", "env_radiance", "has_quad", "quad_radiance", "pool_paths", "steps_per_pass"],
-              "mer_render_stats": ["samples", "ray_steps", "passes", "kernel_launches", "device_ms"],
+                                  "max_depth", "env_radiance", "has_quad", "quad_radiance", "pool_paths", "steps_per_pass",
+                                  "direct_connections", "connection"],
+              "mer_render_stats": ["samples", "ray_steps", "passes", "connections", "connection_steps", "kernel_launches", "device_ms"],
               "mer_medium_sampling_records": ["success", "t", "nsteps"],
-              "mer_connection_params": ["tol2", "rrweight", "boundary_precision", "max_iterations"],
+              "mer_connection_params": ["tol2", "rrweight", "boundary_precision", "max_iterations", "start_mode"],
               "mer_connection_records": ["success", "dir_to_p2", "distance", "transmittance", "evaluations"]}
     body = ['#include <stdio.h>', '#include <stddef.h>', '#include "mitsubaer_b200.h"', "int main(void){"]
     for s, fs in fields.items():
@@ -71,7 +72,7 @@ def test_struct_layouts_match_the_header(tmp_path):
 
 
 def test_version_and_error_plumbing():
-    assert _abi.lib.mer_abi_version() == 2
+    assert _abi.lib.mer_abi_version() == 3
     assert isinstance(mer.kernel_launch_count(), int)
     with pytest.raises(mer.MerError, match=r"interval \(-1, 1\)"):
         mer.HGPhaseFunction(g=-1.5)

@@ -421,7 +421,7 @@ def test_hessian_matches_reference_golden_and_oracle(oracle32, oracle64):
 
 def test_derivative_step_and_connection_residual(oracle32, oracle64):
     """er_derivativestep (:798-814) and computefdfBDPT (:816-939) against the restatement, float and double"""
-    props = medium_props(stepsize=5e-3, shape=("sphere", (0.0, 0.0, 0.0), 0.8))
+    props = medium_props(stepsize=5e-3, shape=("sphere", (0.0, 0.0, 0.0), 0.8), bsdf="hdielectric")  # Snell at the boundary, as the reference
     data, lo, hi = make_field("smooth", 40)
     rif = mer.SplineDataSource(data=data, min=lo, max=hi)
     sdf_data = mer.fields.sphere_sdf((40,) * 3, lo, hi, radius=0.8).astype(np.float32)
@@ -469,7 +469,7 @@ def test_curved_direct_connections(oracle32, oracle64):
     Parity is UNPINNED at the solver (the reference calls Ceres): validated by (1) ground truth — p2 is the end
     point of a known eikonal ray, so the solver must recover that ray's launch direction, length and optical
     length; (2) the residual actually reached; (3) agreement with the same algorithm restated on the CPU."""
-    props = medium_props(stepsize=5e-3, strategy="single", sigmaS=2.0, sigmaA=0.5, shape=("sphere", (0.0, 0.0, 0.0), 0.85))
+    props = medium_props(stepsize=5e-3, strategy="single", sigmaS=2.0, sigmaA=0.5, shape=("sphere", (0.0, 0.0, 0.0), 0.85), bsdf="hdielectric")
     data, lo, hi = make_field("smooth", 40)
     rif = mer.SplineDataSource(data=data, min=lo, max=hi)
     med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).configure()

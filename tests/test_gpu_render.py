@@ -197,3 +197,88 @@ def test_hdielectric_fresnel_reflectance():
     R = ((n - 1) / (n + 1)) ** 2
     expect = 2 * R / (1 + R)
     assert abs(rgb.mean() - expect) < 4 * np.sqrt(expect * (1 - expect) / (64 * 4096)) + 1e-3, (rgb.mean(), expect)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# next-row 1: next-event estimation along curved connections inside the bounce loop
+
+def _nee_medium(kind, h, bsdf, res=32, g=0.5, sigmaS=1.5, sigmaA=0.5, shape=("box", BOX_MIN, BOX_MAX)):
+    if kind == "const":
+        lo, hi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+        data = np.full((res,) * 3, 1.5, np.float32)
+    else:
+        data, lo, hi = make_field(kind, res)
+    props = medium_props(stepsize=h, sigmaS=sigmaS, sigmaA=sigmaA, bsdf=bsdf, shape=shape)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=g)).configure()
+    return med, rif, props, data, lo, hi
+
+
+@pytest.mark.parametrize("kind,bsdf", [("linear", "null"), ("radial", "hdielectric")])
+def test_direct_connections_match_oracle(oracle32, kind, bsdf):
+    """the wavefront (request queue + k_nee) against the oracle's inline restatement of the same estimator: the walk and
+    the solver draw from the same Philox streams, so connections, failures and pixels agree one by one"""
+    med, rif, props, data, lo, hi = _nee_medium(kind, 1e-2, bsdf)
+    omed = oracle32.medium_create(oracle_medium_desc(props, 0.5), oracle32.rif_create(volume_desc((32,) * 3, lo, hi), data))
+    scene = scene_dict(32, 32, 8, rfilter="box")
+    scene["envRadiance"] = 0.25
+    film, st = mer.EikonalVolPathIntegrator(rrDepth=5, directConnections=True, poolPaths=512, stepsPerPass=64).render(scene, med)
+    ofilm, ost = oracle32.render(omed, oracle_render_desc(scene, direct_connections=True, props=props))
+    assert st["connections"] > 5000 and abs(st["connections"] - ost.connections) <= 0.005 * ost.connections
+    assert abs(st["connections_failed"] - ost.connections_failed) <= 0.02 * ost.connections + 3
+    assert abs(st["connection_steps"] - ost.connection_steps) <= 0.01 * ost.connection_steps
+    assert st["nonfinite_dropped"] == 0 and st["kernel_launches"] > st["passes"]  # k_nee ran between the passes
+    a, b = mer.develop(film), oracle32.film_develop(ofilm)
+    assert np.mean(np.abs(a - b) <= 2e-3 * np.maximum(b, 1.0)) > 0.97
+    assert abs(a.mean() - b.mean()) <= 2e-3 * b.mean()
+
+
+@pytest.mark.parametrize("kind,bsdf,shape", [("const", "null", ("box", BOX_MIN, BOX_MAX)), ("linear", "null", ("box", BOX_MIN, BOX_MAX)),
+                                             ("sd", "hdielectric", ("box", BOX_MIN, BOX_MAX)),
+                                             ("radial", "null", ("sphere", (0.0, 0.0, 0.0), 0.9))])
+def test_direct_connections_agree_with_random_walk(kind, bsdf, shape):
+    """the physics check SURVEY 8f-1 asks for: with and without direct connections the image has the same expectation.
+    The quad's light is estimated either by hitting it (walk) or by solving the curved connection from every scattering
+    vertex (and then no longer counted on hits).  The walk's exit edges are ~0.75 h short (heterogeneousrefractive.cpp
+    :742-776 quirk), which makes it brighter by about 0.75 sigma_t h; that shift is allowed for."""
+    h, sigma_t = 2.5e-3, 2.0
+    med = _nee_medium(kind, h, bsdf, shape=shape)[0]
+    mean = {}
+    for nee in (False, True):
+        vals = []
+        for seed in range(1, 9):
+            scene = scene_dict(128, 128, 16, rfilter="box", seed=seed)
+            scene["envRadiance"] = 0.0
+            film, st = mer.EikonalVolPathIntegrator(rrDepth=5, directConnections=nee).render(scene, med)
+            vals.append(float(mer.develop(film)[..., 0].mean()))
+        mean[nee] = (np.mean(vals), np.std(vals, ddof=1) / np.sqrt(len(vals)))
+    assert st["connections"] > 1e5 and st["connections_failed"] < (0.02 if bsdf == "null" else 0.2) * st["connections"]
+    ratio = mean[True][0] / mean[False][0] - 1 + 0.75 * sigma_t * h
+    sigma = np.hypot(mean[True][1], mean[False][1]) / mean[False][0]
+    assert abs(ratio) < 4 * sigma + 4e-3, (kind, bsdf, ratio, sigma, mean)
+    assert mean[True][1] < mean[False][1]  # and it is the lower-variance estimator
+
+
+def test_direct_connections_queue_and_validation(oracle32):
+    med, rif, props, data, lo, hi = _nee_medium("linear", 1e-2, "null")
+    scene = scene_dict(32, 32, 8, rfilter="box")
+    big, st_big = mer.EikonalVolPathIntegrator(directConnections=True).render(scene, med)
+    # 128 path slots => a 256-entry request queue that overflows in every pass: vertices wait for the next pass
+    small, st_small = mer.EikonalVolPathIntegrator(directConnections=True, poolPaths=128, stepsPerPass=512).render(scene, med)
+    assert st_small["connections"] == st_big["connections"] and st_small["ray_steps"] == st_big["ray_steps"]
+    assert st_small["passes"] > st_big["passes"]
+    assert np.allclose(small, big, rtol=1e-4, atol=1e-4)
+    # the random first guess of the reference is available and statistically equivalent, only more expensive
+    rnd, st_rnd = mer.EikonalVolPathIntegrator(directConnections=True, connectionStart="random").render(scene, med)
+    assert st_rnd["connection_steps"] > 1.5 * st_big["connection_steps"]
+    assert abs(mer.develop(rnd).mean() / mer.develop(big).mean() - 1) < 0.1
+    with pytest.raises(mer.MerError, match="quad"):
+        mer.EikonalVolPathIntegrator(directConnections=True).render(scene_dict(16, 16, 1, quad=False), med)
+    packed = mer.SplineDataSource(data=data, min=lo, max=hi, mode="trilinear_packed")
+    pm = mer.HeterogeneousRefractiveMedium(props).addChild("rif", packed).configure()
+    with pytest.raises(mer.MerError, match="tricubic"):
+        mer.EikonalVolPathIntegrator(directConnections=True).render(scene, pm)
+    grid = mer.GridDataSource(data=mer.fields.sine_density((16,) * 3, BOX_MIN, BOX_MAX), min=BOX_MIN, max=BOX_MAX)
+    dm = mer.HeterogeneousRefractiveMedium(medium_props(stepsize=1e-2, albedo=0.9, densityScale=4.0)).addChild("rif", rif).addChild("density", grid).configure()
+    with pytest.raises(mer.MerError, match="density"):
+        mer.EikonalVolPathIntegrator(directConnections=True).render(scene, dm)

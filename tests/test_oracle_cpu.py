@@ -264,3 +264,24 @@ def test_oracle_hdielectric_boundary(oracle32):
     expect = 2 * R / (1 + R)
     got = oracle32.film_develop(film).mean()
     assert abs(got - expect) < 4 * np.sqrt(expect * (1 - expect) / (16 * 2048)) + 1e-3, (got, expect)
+
+
+def test_oracle_direct_connections_agree_with_random_walk(oracle32):
+    """next-row 1: the oracle's next-event estimation has the expectation of its random walk (coarse CPU-sized check;
+    the tight statistical version runs on the GPU) and its connections converge from the straight first guess"""
+    from common import BOX_MAX, BOX_MIN, medium_props, oracle_medium_desc, oracle_render_desc, scene_dict
+    from mitsubaer_b200 import fields
+    res = 16
+    lo, hi = fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    orif = oracle32.rif_create(volume_desc((res,) * 3, lo, hi), fields.linear_rif((res,) * 3, lo, hi))
+    props = medium_props(stepsize=1e-2, sigmaS=1.5, sigmaA=0.5)
+    med = oracle32.medium_create(oracle_medium_desc(props, 0.5), orif)
+    scene = scene_dict(64, 64, 12, rfilter="box", quad=True)
+    scene["envRadiance"] = 0.0
+    means = {}
+    for nee in (False, True):
+        film, st = oracle32.render(med, oracle_render_desc(scene, direct_connections=nee, props=props))
+        means[nee] = oracle32.film_develop(film)[..., 0].mean()
+    assert st.connections > 30000 and st.connections_failed < 0.01 * st.connections
+    assert st.connection_steps / st.connections < 4 * (2.5 / 1e-2)  # ~2-3 residual evaluations of ~200 steps each
+    assert abs(means[True] / means[False] - 1 + 0.75 * 2.0 * 1e-2) < 0.05, means  # walk noise ~1.5 % at 49k samples
