@@ -255,7 +255,8 @@ def run_gpu(args, w, wname):
     setup_s = time.time() - t0
     if den_t is not None:
         del den_t  # the handle keeps its own copy
-    integ = mer.EikonalVolPathIntegrator(maxDepth=w["max_depth"], rrDepth=5, poolPaths=args.pool, stepsPerPass=args.steps_per_pass)
+    integ = mer.EikonalVolPathIntegrator(maxDepth=w["max_depth"], rrDepth=5, poolPaths=args.pool, stepsPerPass=args.steps_per_pass,
+                                         directConnections=args.direct_connections)
     scene = scene_dict(w, spp_total)
     film = torch.zeros(w["height"], w["width"], 5, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -395,6 +396,12 @@ def run_gpu(args, w, wname):
         "ray_steps_per_sample": ray_steps / max(samples, 1),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
     }
+    if args.direct_connections:  # rank-0 figures of the solver kernel (k_nee)
+        conn = float(sum(s["connections"] for s in stats))
+        out["direct_connections"] = {"connections_per_sec": conn * world / (ms * 1e-3),
+                                     "failed_fraction": float(sum(s["connections_failed"] for s in stats)) / max(conn, 1.0),
+                                     "hessian_steps_per_sec": float(sum(s["connection_steps"] for s in stats)) * world / (ms * 1e-3),
+                                     "hessian_steps_per_connection": float(sum(s["connection_steps"] for s in stats)) / max(conn, 1.0)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -412,6 +419,8 @@ def main():
     ap.add_argument("--pool", type=int, default=0)
     ap.add_argument("--steps-per-pass", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--direct-connections", action="store_true",
+                    help="next-event estimation along curved connections (SURVEY 8f-1; homogeneous workloads: C1, C3)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -387,6 +387,8 @@ struct ConnectResult {
     float opl, dist, weight, n1;
     int evals, steps; /* residual evaluations, Hessian-carrying leapfrog steps */
     ExitInfo exit;
+    M3 J;        /* residual Jacobian at the accepted launch velocity x (as computefdf returns it) ... */
+    float xnorm; /* ... and |x|: computefdf renormalises x to n(p1), so J scales like n(p1) / |x| */
 };
 
 static __device__ void connect_solve(const MediumDev &M, int precision, float tol2, float rrweight, int maxIterations, float3 p1, float3 p2,
@@ -472,11 +474,13 @@ static __device__ void connect_solve(const MediumDev &M, int precision, float to
             }
         }
         R.steps += cnt;
+        R.J = Jt;
         if (cost < tol2) { converged = true; break; }
         if (rng.next() < rrweight) R.weight = R.weight * (1.0f / rrweight);
         else break;
     }
-    const float xl = 1.0f / sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    R.xnorm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const float xl = 1.0f / R.xnorm;
     R.dir = f3((x[0] * xl) * RIFp, (x[1] * xl) * RIFp, (x[2] * xl) * RIFp);
     if (converged && compute_path_lengths(M, precision, tol2, p1, p2, R.dir, R.rev, isSensor, refract, R.opl, R.dist, R.exit)) R.success = true;
 }
@@ -485,15 +489,16 @@ static __device__ void connect_solve(const MediumDev &M, int precision, float to
  * solid angle of launch direction at p1 (t^2 for a straight ray of length t).  The Jacobian of computefdf w.r.t. the
  * launch velocity has rank 2 (the radial direction is projected out, the image is perpendicular to the arrival
  * direction); the product of its two singular values is the Frobenius norm of its cofactor matrix, and a unit change of
- * direction is a change n(p1) of velocity. */
-static __device__ float connection_spread(const M3 &J, float n1) {
+ * direction is a change n(p1) of velocity; J taken at a launch velocity of length |x| is n(p1) / |x| times the one at
+ * length n(p1), hence the factor |x|^2. */
+static __device__ float connection_spread(const M3 &J, float xnorm) {
     const float *m = J.m;
     const float c[9] = {m[4] * m[8] - m[5] * m[7], m[5] * m[6] - m[3] * m[8], m[3] * m[7] - m[4] * m[6],
                         m[2] * m[7] - m[1] * m[8], m[0] * m[8] - m[2] * m[6], m[1] * m[6] - m[0] * m[7],
                         m[1] * m[5] - m[2] * m[4], m[2] * m[3] - m[0] * m[5], m[0] * m[4] - m[1] * m[3]};
     float s = 0.0f;
     for (int i = 0; i < 9; i++) s += c[i] * c[i];
-    return n1 * n1 * sqrtf(s);
+    return xnorm * xnorm * sqrtf(s);
 }
 
 } /* namespace merc */

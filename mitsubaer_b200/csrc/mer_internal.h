@@ -38,7 +38,8 @@ struct RenderScratch {
     size_t poolBytes = 0;
     void *pool[14] = {nullptr};
     void *neeQ[3] = {nullptr, nullptr, nullptr}; /* direct-connection request queue */
-    unsigned *neeCount = nullptr;
+    unsigned *neeCount = nullptr, *neePerm = nullptr, *neeHist = nullptr;
+    unsigned char *neeKey = nullptr;
     unsigned neeCap = 0;
     unsigned *nOut = nullptr;
     unsigned long long *counters = nullptr;
@@ -48,6 +49,9 @@ struct RenderScratch {
         for (void *&p : pool) { cudaFree(p); p = nullptr; }
         for (void *&p : neeQ) { cudaFree(p); p = nullptr; }
         cudaFree(neeCount); neeCount = nullptr;
+        cudaFree(neePerm); neePerm = nullptr;
+        cudaFree(neeHist); neeHist = nullptr;
+        cudaFree(neeKey); neeKey = nullptr;
         neeCap = 0;
         cudaFree(nOut); nOut = nullptr;
         cudaFree(counters); counters = nullptr;

@@ -107,7 +107,12 @@ struct RenderParams {
     unsigned *neeCount;
     float4 *neeQ0, *neeQ1; /* (p1.xyz, wi.x), (wi.yz, thr.rg) */
     uint4 *neeQ2;          /* thr.b, depth, pixel, sample */
+    unsigned *neePerm;     /* requests ordered by expected length (null: queue order) */
+    unsigned char *neeKey;
+    unsigned *neeHist;     /* NEE_BINS counters, then offsets */
 };
+
+#define NEE_BINS 64
 
 struct Lane {
     float3 p, v;
@@ -573,6 +578,47 @@ k_render_pass(const __grid_constant__ RenderParams P) {
     }
 }
 
+/* A warp of k_nee costs what its longest connection costs, and the cost is roughly the number of steps from the vertex to
+ * the container surface.  So the requests are counting-sorted by that distance (towards the centre of the quad, 64 bins,
+ * longest first) before the solver runs: three trivial kernels in front of one that costs 1e3-1e5 steps per thread. */
+__global__ void k_nee_keys(const __grid_constant__ RenderParams P, unsigned nReq) {
+    __shared__ unsigned hist[NEE_BINS];
+    if (threadIdx.x < NEE_BINS) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nReq) {
+        const float4 a = P.neeQ0[i];
+        const float3 p1 = f3(a.x, a.y, a.z);
+        float3 d = f3(P.quadO[0] + 0.5f * (P.quadU[0] + P.quadV[0]) - p1.x, P.quadO[1] + 0.5f * (P.quadU[1] + P.quadV[1]) - p1.y,
+                      P.quadO[2] + 0.5f * (P.quadU[2] + P.quadV[2]) - p1.z);
+        const float dl = 1.0f / sqrtf(dot3(d, d));
+        d = f3(d.x * dl, d.y * dl, d.z * dl);
+        const float te = exit_distance(P.M, p1, d);
+        float extent;
+        if (P.M.shapeType == MER_SHAPE_SPHERE) extent = 2.0f * P.M.shape[3];
+        else extent = sqrtf((P.M.shape[3] - P.M.shape[0]) * (P.M.shape[3] - P.M.shape[0]) + (P.M.shape[4] - P.M.shape[1]) * (P.M.shape[4] - P.M.shape[1]) +
+                            (P.M.shape[5] - P.M.shape[2]) * (P.M.shape[5] - P.M.shape[2]));
+        const int bin = min(max((int) (te / extent * (float) NEE_BINS), 0), NEE_BINS - 1);
+        const unsigned key = (unsigned) (NEE_BINS - 1 - bin); /* longest first */
+        P.neeKey[i] = (unsigned char) key;
+        atomicAdd(&hist[key], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < NEE_BINS && hist[threadIdx.x]) atomicAdd(P.neeHist + threadIdx.x, hist[threadIdx.x]);
+}
+
+__global__ void k_nee_offsets(unsigned *hist) { /* exclusive prefix sum of NEE_BINS counters, one thread: 64 adds */
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned run = 0;
+        for (int b = 0; b < NEE_BINS; b++) { const unsigned c = hist[b]; hist[b] = run; run += c; }
+    }
+}
+
+__global__ void k_nee_scatter(const __grid_constant__ RenderParams P, unsigned nReq) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nReq) P.neePerm[atomicAdd(P.neeHist + P.neeKey[i], 1u)] = i;
+}
+
 /* Next-event estimation of the quad emitter from the queued scattering vertices, one thread per vertex.
  * Around the reference's shooting problem (makeDirectConnections, mer_connect.cuh) the estimator is
  *     thr * phase(wi, w) * exp(-sigma_t dist) * (n_b / n_1)^2 [* (1 - Fresnel) n_b^2 for hdielectric]
@@ -580,13 +626,15 @@ k_render_pass(const __grid_constant__ RenderParams P) {
  * i.e. the random walk's own exit-edge weights with the change of variables launch direction -> sampled point written
  * with the solver's Jacobian in place of 1 / distance^2.  The splat adds radiance only (filter weight 0): the sample's
  * weight is added once, by the walk. */
-__global__ void __launch_bounds__(128)
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS)
 k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const MediumDev &M = P.M;
     unsigned st[3] = {0u, 0u, 0u}, nonfinite = 0u; /* connections, failed, steps */
-    if (i < nReq) {
+    if (tid < nReq) {
+        const unsigned i = P.neePerm ? P.neePerm[tid] : tid;
         const float4 a = P.neeQ0[i], b = P.neeQ1[i];
         const uint4 c = P.neeQ2[i];
         const float3 p1 = f3(a.x, a.y, a.z), wi = f3(a.w, b.x, b.y);
@@ -607,13 +655,10 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         merc::connect_solve(M, P.neePrecision, P.neeTol2, P.neeRRWeight, P.neeMaxIterations, p1, y, ds, true, refract, P.neeStraightFirst != 0,
                             nrng, C);
         st[0] = 1u;
-        int steps = C.steps;
+        const int steps = C.steps;
         bool ok = C.success && C.exit.exited && !C.exit.tir;
         if (ok) {
-            float3 r;
-            merc::M3 J;
-            merc::compute_fdf(M, P.neePrecision, C.dir, p1, y, true, refract, r, J, steps);
-            const float spread = merc::connection_spread(J, C.n1);
+            const float spread = merc::connection_spread(C.J, C.xnorm); /* the Jacobian of the solver's last accepted evaluation */
             ok = spread > 0.0f;
             if (ok) {
                 const float cosY = fabsf(dot3(C.rev, Nq)) / area;
@@ -780,12 +825,21 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
             for (int i = 0; i < 3; i++) { cudaFree(S.neeQ[i]); S.neeQ[i] = nullptr; }
             S.neeCap = 0;
             for (int i = 0; i < 3; i++) MER_CUDA(cudaMalloc(&S.neeQ[i], (size_t) cap * 16));
+            cudaFree(S.neePerm); cudaFree(S.neeKey);
+            S.neePerm = nullptr; S.neeKey = nullptr;
+            MER_CUDA(cudaMalloc(&S.neePerm, (size_t) cap * sizeof(unsigned)));
+            MER_CUDA(cudaMalloc(&S.neeKey, (size_t) cap));
+            if (!S.neeHist) MER_CUDA(cudaMalloc(&S.neeHist, NEE_BINS * sizeof(unsigned)));
             if (!S.neeCount) MER_CUDA(cudaMalloc(&S.neeCount, sizeof(unsigned)));
             S.neeCap = cap;
         }
         P.neeCap = cap;
         P.neeCount = S.neeCount;
         P.neeQ0 = (float4 *) S.neeQ[0]; P.neeQ1 = (float4 *) S.neeQ[1]; P.neeQ2 = (uint4 *) S.neeQ[2];
+        P.neeKey = S.neeKey;
+        P.neeHist = S.neeHist;
+        P.neePerm = m->dev.hasSdf ? nullptr : S.neePerm; /* the length estimate needs an analytic container */
+        if (const char *e = getenv("MER_NEE_SORT")) if (atoi(e) == 0) P.neePerm = nullptr; /* tuning knob */
         MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
     }
     PathPool A = {(float4 *) S.pool[0], (float4 *) S.pool[1], (float4 *) S.pool[2], (float4 *) S.pool[3], (uint4 *) S.pool[4], (float4 *) S.pool[5], (float4 *) S.pool[12]};
@@ -797,6 +851,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
 
     unsigned nLive = 0;
     unsigned long long started = 0, passes = 0, launches = 0;
+    int neeMinBlocks = 2;
+    if (const char *e = getenv("MER_NEE_MIN_BLOCKS")) neeMinBlocks = atoi(e); /* tuning knob */
     MER_CUDA(cudaEventRecord(S.ev0, stream));
     while (true) {
         const bool fresh = started < P.totalSamples;
@@ -827,7 +883,15 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         if (P.nee) {
             const unsigned nReq = std::min(*(unsigned *) (S.hostPinned + 2), P.neeCap);
             if (nReq) {
-                MER_LAUNCH(k_nee, (nReq + TPB - 1) / TPB, TPB, 0, stream, P, nReq);
+                if (P.neePerm && nReq > 32u) {
+                    MER_CUDA(cudaMemsetAsync(S.neeHist, 0, NEE_BINS * sizeof(unsigned), stream));
+                    MER_LAUNCH(k_nee_keys, (nReq + 255u) / 256u, 256, 0, stream, P, nReq);
+                    MER_LAUNCH(k_nee_offsets, 1, 32, 0, stream, S.neeHist);
+                    MER_LAUNCH(k_nee_scatter, (nReq + 255u) / 256u, 256, 0, stream, P, nReq);
+                    launches += 3;
+                }
+                if (neeMinBlocks >= 3) MER_LAUNCH(k_nee<3>, (nReq + TPB - 1) / TPB, TPB, 0, stream, P, nReq);
+                else MER_LAUNCH(k_nee<2>, (nReq + TPB - 1) / TPB, TPB, 0, stream, P, nReq);
                 launches++;
                 MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
             }

@@ -939,7 +939,7 @@ struct ExitInfo { bool exited = false, tir = false; float nb = 1, cosI = 1; };
 
 template <typename F> struct ConnectionResult {
     ExitInfo exit;
-    F n1;
+    F n1, J[9], xnorm; /* residual Jacobian at the accepted launch velocity x and |x| (computefdf renormalises x to n(p1)) */
     bool success;
     F dirToP2[3], revDirToP1[3], opticalDist, dist, weight;
     float transmittance[3], pdfSuccess, pdfFailure;
@@ -1114,11 +1114,13 @@ void connect(const Medium<F> &M, const F *p1, const F *p2, const F *dseed, bool 
             }
         }
         if (steps) *steps += cnt;
+        for (int i = 0; i < 9; i++) R.J[i] = Jt[i];
         if (cost < M.tol2) { converged = true; break; } /* :1121-1138 always ends with multiplicity weight 1 */
         if (rng.next() < rrweight) R.weight = R.weight * (1 / (F) rrweight); /* :1146-1155 */
         else break;
     }
-    F xl = (F) 1 / std::sqrt(Medium<F>::dot(x, x));
+    R.xnorm = std::sqrt(Medium<F>::dot(x, x));
+    F xl = (F) 1 / R.xnorm;
     for (int i = 0; i < 3; i++) R.dirToP2[i] = (x[i] * xl) * RIFp;
     if (!converged) return;
     if (!computePathLengths<F>(M, p1, p2, R.dirToP2, R.revDirToP1, isSensorSample, R.opticalDist, R.dist, refract, R.exit)) return;
@@ -1353,16 +1355,14 @@ void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, cons
     connect<F>(M, p1, y, dseed, true, rrweight, maxIt, nrng, C, refract, &steps, R.connection.start_mode != MER_START_RANDOM);
     st.connections++;
     if (!C.success || !C.exit.exited || C.exit.tir) { st.connSteps += steps; st.connFailed++; return; }
-    F r[3], Jt[9];
-    M.computefdf(C.dirToP2, p1, y, true, r, Jt, steps, refract);
     st.connSteps += steps;
-    const F *m = Jt;
+    const F *m = C.J; /* the Jacobian of the solver's last accepted evaluation */
     const F cof[9] = {m[4] * m[8] - m[5] * m[7], m[5] * m[6] - m[3] * m[8], m[3] * m[7] - m[4] * m[6],
                       m[2] * m[7] - m[1] * m[8], m[0] * m[8] - m[2] * m[6], m[1] * m[6] - m[0] * m[7],
                       m[1] * m[5] - m[2] * m[4], m[2] * m[3] - m[0] * m[5], m[0] * m[4] - m[1] * m[3]};
     F ss = 0;
     for (int i = 0; i < 9; i++) ss += cof[i] * cof[i];
-    const float n1 = (float) C.n1, spread = n1 * n1 * (float) std::sqrt(ss);
+    const float n1 = (float) C.n1, spread = (float) (C.xnorm * C.xnorm) * (float) std::sqrt(ss);
     if (!(spread > 0)) { st.connFailed++; return; }
     float cosY = 0, wo[3];
     for (int i = 0; i < 3; i++) { cosY += (float) C.revDirToP1[i] * (Nq[i] / area); wo[i] = (float) C.dirToP2[i] / n1; }
