@@ -145,7 +145,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(w, budget_s=15.0):
+def cpu_arm(w, budget_s=15.0, direct_connections=False):
     """the oracle port (reference algorithm on the host cores) on a bounded sample of the workload:
     same grids, same camera, a centred 1/4-resolution film and as many spp as fit the time budget"""
     from oracle.oracle import Oracle, volume_desc
@@ -160,13 +160,14 @@ def cpu_arm(w, budget_s=15.0):
     sw, sh = max(w["width"] // 4, 16), max(w["height"] // 4, 16)
     small = dict(w, width=sw, height=sh)
     scene = scene_dict(small, 1)
+    nee = dict(direct_connections=direct_connections, props=medium_props(w))
     t0 = time.time()
-    _, st = orc.render(omed, oracle_render_desc(scene, max_depth=w["max_depth"], rr_depth=5))
+    _, st = orc.render(omed, oracle_render_desc(scene, max_depth=w["max_depth"], rr_depth=5, **nee))
     cal = time.time() - t0
     spp = int(max(1, min(64, budget_s / max(cal, 1e-3))))
     scene = scene_dict(small, spp)
     t0 = time.time()
-    _, st = orc.render(omed, oracle_render_desc(scene, max_depth=w["max_depth"], rr_depth=5))
+    _, st = orc.render(omed, oracle_render_desc(scene, max_depth=w["max_depth"], rr_depth=5, **nee))
     dt = time.time() - t0
     return dict(samples_per_s=st.samples / dt, steps_per_s=st.ray_steps / dt, cores=orc.num_threads(),
                 sample="%dx%d film (same camera) at %d spp = %d samples, %.1f s; prefilter %.1f s"
@@ -181,7 +182,7 @@ def run_reference(args, w, wname):
     rates, steps_rates, info = [], [], None
     budget = max(3.0, min(15.0, 120.0 / max(K + W, 1)))
     for i in range(W + K):
-        r = cpu_arm(w, budget_s=budget)
+        r = cpu_arm(w, budget_s=budget, direct_connections=args.direct_connections)
         if i >= W:
             rates.append(r["samples_per_s"])
             steps_rates.append(r["steps_per_s"])
@@ -378,7 +379,7 @@ def run_gpu(args, w, wname):
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample, rank 0 / N=1 only
     cpu = None
     if world == 1 and not args.no_cpu:
-        c = cpu_arm(w, budget_s=15.0)
+        c = cpu_arm(w, budget_s=15.0, direct_connections=args.direct_connections)
         cpu = {"value": c["samples_per_s"], "unit": "samples/s", "cores": c["cores"], "kind": "port", "sample": c["sample"],
                "ray_steps_per_sec": c["steps_per_s"]}
 
