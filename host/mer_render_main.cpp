@@ -18,9 +18,9 @@ static void printDesc(const Scene &S) {
     const mer_render_desc &r = S.render;
     const mer_medium_desc &m = S.medium->desc;
     std::printf("{\"integrator\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"seed\": %llu, \"fov\": %g, \"filter\": %d,\n"
-                " \"max_depth\": %d, \"rr_depth\": %d, \"direct_connections\": %d, \"cam_origin\": [%g, %g, %g], \"cam_target\": [%g, %g, %g], \"cam_up\": [%g, %g, %g],\n"
+                " \"max_depth\": %d, \"rr_depth\": %d, \"direct_connections\": %d, \"frames\": %d, \"min_bound\": %g, \"bin_width\": %g, \"cam_origin\": [%g, %g, %g], \"cam_target\": [%g, %g, %g], \"cam_up\": [%g, %g, %g],\n"
                 " \"env\": [%g, %g, %g], \"has_quad\": %d, \"quad_origin\": [%g, %g, %g], \"quad_u\": [%g, %g, %g], \"quad_v\": [%g, %g, %g], \"quad_radiance\": [%g, %g, %g],\n",
-                S.integratorType.c_str(), r.width, r.height, r.spp_total, (unsigned long long) r.seed, r.fov_deg, r.filter, r.max_depth, r.rr_depth, r.direct_connections,
+                S.integratorType.c_str(), r.width, r.height, r.spp_total, (unsigned long long) r.seed, r.fov_deg, r.filter, r.max_depth, r.rr_depth, r.direct_connections, r.frames, r.min_bound, r.bin_width,
                 r.cam_origin[0], r.cam_origin[1], r.cam_origin[2], r.cam_target[0], r.cam_target[1], r.cam_target[2], r.cam_up[0], r.cam_up[1], r.cam_up[2],
                 r.env_radiance[0], r.env_radiance[1], r.env_radiance[2], r.has_quad, r.quad_origin[0], r.quad_origin[1], r.quad_origin[2],
                 r.quad_u[0], r.quad_u[1], r.quad_u[2], r.quad_v[0], r.quad_v[1], r.quad_v[2], r.quad_radiance[0], r.quad_radiance[1], r.quad_radiance[2]);
@@ -55,11 +55,24 @@ int main(int argc, char **argv) {
         Scene S = loadScene(scenePath, params);
         if (dryRun()) { printDesc(S); return 0; }
         const mer_render_desc &r = S.render;
-        std::vector<float> film((size_t) r.width * r.height * 5), rgb((size_t) r.width * r.height * 3);
+        const int frames = r.frames > 1 ? r.frames : 1;
+        const size_t npx = (size_t) r.width * r.height;
+        std::vector<float> film(npx * (3 * (size_t) frames + 2)), rgb(npx * 3 * (size_t) frames);
         mer_render_stats st;
         merCheck(mer_render(S.medium->handle, &r, film.data(), &st));
-        merCheck(mer_film_develop(0, r.width, r.height, film.data(), rgb.data()));
-        writePFM(out, r.width, r.height, rgb.data());
+        merCheck(mer_film_develop_frames(0, r.width, r.height, frames, film.data(), rgb.data()));
+        if (frames == 1) {
+            writePFM(out, r.width, r.height, rgb.data());
+        } else { /* one PFM per frame next to `out` (the reference writes a multi-channel EXR): out_0000.pfm ... */
+            std::vector<float> one(npx * 3);
+            const std::string stem = out.size() > 4 && out.substr(out.size() - 4) == ".pfm" ? out.substr(0, out.size() - 4) : out;
+            for (int f = 0; f < frames; f++) {
+                for (size_t i = 0; i < npx; i++) for (int k = 0; k < 3; k++) one[3 * i + k] = rgb[(i * frames + f) * 3 + k];
+                char name[32];
+                std::snprintf(name, sizeof(name), "_%04d.pfm", f);
+                writePFM(stem + name, r.width, r.height, one.data());
+            }
+        }
         if (!filmOut.empty()) {
             FILE *f = std::fopen(filmOut.c_str(), "wb");
             if (!f) logError("cannot create \"" + filmOut + "\"");

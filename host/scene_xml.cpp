@@ -302,6 +302,20 @@ Scene loadScene(const std::string &xmlPath, const std::map<std::string, std::str
     R.sample_stride = 1;
     R.width = (int) (film ? film->props.getInteger("width", 768) : 768); /* film.cpp defaults */
     R.height = (int) (film ? film->props.getInteger("height", 576) : 576);
+    if (film) { /* transient film, src/librender/film.cpp:56-78 */
+        std::string dec = film->props.getString("decomposition", "none");
+        for (auto &c : dec) c = (char) std::tolower((unsigned char) c);
+        if (dec != "none" && dec != "transient") logError("The \"decomposition\" parameter must be equal to either \"none\" or \"transient\" on this path");
+        const double lo = film->props.getFloat("minBound", 0.0), hi = film->props.getFloat("maxBound", 0.0), bw = film->props.getFloat("binWidth", 1.0);
+        if (film->props.getString("modulation", "none") != "none") logError("continuous-wave modulation (pathlengthsampler.cpp) is not carried by this path");
+        if (dec == "transient") {
+            if (!(bw > 0) || !(hi > lo)) logError("transient film: binWidth must be positive and maxBound > minBound");
+            R.frames = (int) std::ceil((hi - lo) / bw);
+            R.min_bound = (float) lo;
+            R.bin_width = (float) bw;
+            R.calibrated_transient = film->props.getBoolean("calibratedTransient", false) ? 1 : 0;
+        }
+    }
     std::shared_ptr<Generic> rf = film ? film->child("rfilter") : nullptr;
     std::string rfType = rf ? rf->props.pluginName : "gaussian"; /* hdrfilm default filter */
     if (rfType == "gaussian") R.filter = MER_FILTER_GAUSSIAN;

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 3
+#define MER_ABI_VERSION 4
 
 enum mer_status {
     MER_OK = 0,
@@ -302,6 +302,15 @@ typedef struct mer_render_desc {
      * after a scattering event no longer count it.  Requires a quad, the tricubic RIF mode and no density grid. */
     int32_t direct_connections;
     mer_connection_params connection; /* solver parameters for direct_connections = 1 (zeros => tol2 1e-6, rrweight 1e-2, 3, 20) */
+    /* transient film: <film> properties decomposition="transient", minBound, maxBound, binWidth (src/librender/film.cpp
+     * :56-78).  frames = ceil((maxBound - minBound) / binWidth) > 1 resolves every contribution by the optical path
+     * length of its path (sum of the edges' opticalLength, exterior segments at index 1; bdpt_proc.cpp:147-176) into bin
+     * floor((length - min_bound) / bin_width) and drops it when the bin is outside [0, frames) (:446-449).  The film then
+     * has 3 * frames + 2 channels per pixel: RGB of every frame, then alpha and weight (bdpt_wr.cpp:52-56).
+     * frames <= 1: steady state, 5 channels.  calibrated_transient skips the camera -> first surface segment (:163-171). */
+    int32_t frames;
+    float min_bound, bin_width;
+    int32_t calibrated_transient;
 } mer_render_desc;
 
 typedef struct mer_render_stats {
@@ -332,6 +341,8 @@ int mer_render_device(const mer_medium *medium, const mer_render_desc *desc, flo
                       mer_render_stats *stats_out, void *stream);
 /* HDRFilm::develop (src/films/hdrfilm.cpp:527-540): rgb = sum(w*RGB)/sum(w); host buffers */
 int mer_film_develop(int device, int32_t width, int32_t height, const float *film, float *rgb_out);
+/* the same for a transient film of `frames` frames: film [H][W][3*frames+2] -> rgb_out [H][W][frames][3] */
+int mer_film_develop_frames(int device, int32_t width, int32_t height, int32_t frames, const float *film, float *rgb_out);
 
 /* ------------------------------------------------------------------- misc */
 

@@ -68,7 +68,8 @@ class RenderDesc(C.Structure):
                 ("env_radiance", C.c_float * 3), ("has_quad", C.c_int32), ("quad_origin", C.c_float * 3),
                 ("quad_u", C.c_float * 3), ("quad_v", C.c_float * 3), ("quad_radiance", C.c_float * 3),
                 ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32), ("direct_connections", C.c_int32),
-                ("connection", ConnectionParams)]
+                ("connection", ConnectionParams), ("frames", C.c_int32), ("min_bound", C.c_float), ("bin_width", C.c_float),
+                ("calibrated_transient", C.c_int32)]
 
 
 class RenderStats(C.Structure):
@@ -127,6 +128,7 @@ SIGNATURES = {
     "mer_render": (C.c_int, [_vp, C.POINTER(RenderDesc), _fp, C.POINTER(RenderStats)]),
     "mer_render_device": (C.c_int, [_vp, C.POINTER(RenderDesc), _vp, C.POINTER(RenderStats), _vp]),
     "mer_film_develop": (C.c_int, [C.c_int, C.c_int32, C.c_int32, _fp, _fp]),
+    "mer_film_develop_frames": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _fp, _fp]),
     "mer_last_error": (C.c_char_p, []),
     "mer_abi_version": (C.c_int, []),
     "mer_device_count": (C.c_int, []),

@@ -40,6 +40,7 @@ struct RenderScratch {
     void *neeQ[3] = {nullptr, nullptr, nullptr}; /* direct-connection request queue */
     unsigned *neeCount = nullptr, *neePerm = nullptr, *neeHist = nullptr;
     unsigned char *neeKey = nullptr;
+    float *neeOpl = nullptr;
     unsigned neeCap = 0;
     unsigned *nOut = nullptr;
     unsigned long long *counters = nullptr;
@@ -52,6 +53,7 @@ struct RenderScratch {
         cudaFree(neePerm); neePerm = nullptr;
         cudaFree(neeHist); neeHist = nullptr;
         cudaFree(neeKey); neeKey = nullptr;
+        cudaFree(neeOpl); neeOpl = nullptr;
         neeCap = 0;
         cudaFree(nOut); nOut = nullptr;
         cudaFree(counters); counters = nullptr;

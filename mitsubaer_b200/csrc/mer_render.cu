@@ -78,7 +78,7 @@ struct PathPool {
     float4 *q3; /* rem, sd, (int) stepsLeft, (int) depth */
     uint4 *q4;  /* kind | flags<<8, rng draw index, pixel, sample index */
     float4 *q5; /* n(p), grad n(p): the field at p carried by the fused stepper */
-    float4 *q6; /* product of the surface BSDFs' relative indices (RR), unused x3; hdielectric boundary only */
+    float4 *q6; /* product of the surface BSDFs' relative indices (RR), optical path length, unused x2; hdielectric / transient only */
 };
 
 struct RenderParams {
@@ -93,6 +93,8 @@ struct RenderParams {
     int hasQuad;
     float quadO[3], quadU[3], quadV[3], quadLe[3];
     float filterRadius, filterScale, filterValues[32];
+    int frames, channels, calibrated; /* transient film: 3 * frames + 2 channels per pixel (bdpt_wr.cpp:52-56) */
+    float minBound, binWidth;
     int stepsPerPass, maxWait;
     float *film;
     PathPool in, out;
@@ -107,6 +109,7 @@ struct RenderParams {
     unsigned *neeCount;
     float4 *neeQ0, *neeQ1; /* (p1.xyz, wi.x), (wi.yz, thr.rg) */
     uint4 *neeQ2;          /* thr.b, depth, pixel, sample */
+    float *neeQ3;          /* optical path length at the vertex (transient film) */
     unsigned *neePerm;     /* requests ordered by expected length (null: queue order) */
     unsigned char *neeKey;
     unsigned *neeHist;     /* NEE_BINS counters, then offsets */
@@ -119,7 +122,7 @@ struct Lane {
     float n;
     float3 G;
     float thr[3];
-    float refStart, segDist, distSurf, rem, sd, etaPath;
+    float refStart, segDist, distSurf, rem, sd, etaPath, opl;
     int stepsLeft, depth, kind, flags;
     PathRng rng;
     unsigned pixel, sample; /* sample id = pixel * sppTotal + sample */
@@ -189,7 +192,14 @@ __device__ __forceinline__ bool hdielectric_sample(float3 d, float3 N, float eta
 }
 
 /* ImageBlock::put (imageblock.h:144-190) onto the global film with red.global.add.f32 */
-__device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha, float wgt,
+/* frame of the transient film a path of optical length `len` falls into (bdpt_proc.cpp:446-449), -1: none */
+__device__ __forceinline__ int path_frame(const RenderParams &P, float len) {
+    if (P.frames <= 1) return 0;
+    const float b = floorf((len - P.minBound) / P.binWidth);
+    return (b >= 0.0f && b < (float) P.frames) ? (int) b : -1;
+}
+
+__device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha, float wgt, int frame,
                                          unsigned &nonfinite) {
     const float value[5] = {L[0], L[1], L[2], alpha, wgt};
 #pragma unroll
@@ -202,9 +212,13 @@ __device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy,
         const float wy = P.filterValues[min((int) fabsf(((float) y - py) * P.filterScale), 31)];
         for (int x = x0; x <= x1; ++x) {
             const float w = P.filterValues[min((int) fabsf(((float) x - px) * P.filterScale), 31)] * wy;
-            float *dest = P.film + ((size_t) y * P.W + x) * 5;
+            float *dest = P.film + ((size_t) y * P.W + x) * (size_t) P.channels;
+            if (frame >= 0) {
 #pragma unroll
-            for (int k = 0; k < 5; k++) atomicAdd(dest + k, w * value[k]);
+                for (int k = 0; k < 3; k++) atomicAdd(dest + 3 * frame + k, w * value[k]);
+            }
+            atomicAdd(dest + P.channels - 2, w * value[3]);
+            atomicAdd(dest + P.channels - 1, w * value[4]);
         }
     }
 }
@@ -220,10 +234,10 @@ __device__ __forceinline__ void sample_position(const RenderParams &P, unsigned 
 }
 
 __device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, const float rad[3], float alpha,
-                                              unsigned *st) {
+                                              unsigned *st, float pathLength = INFINITY) {
     float sx, sy;
     sample_position(P, L.pixel, L.sample, sx, sy);
-    film_put(P, sx, sy, rad, alpha, 1.0f, st[ST_NONFINITE]);
+    film_put(P, sx, sy, rad, alpha, 1.0f, path_frame(P, pathLength), st[ST_NONFINITE]);
     L.kind = E_NEW;
 }
 
@@ -273,7 +287,7 @@ __device__ __noinline__ void edge_weight(const MediumDev &M, float sd, float d, 
 
 /* Everything that is not a leapfrog step.  Runs until the lane is steppable again or dead.
  * DIELECTRIC selects the container surface: false = index-matched null surface, true = hdielectric. */
-template <bool DIELECTRIC>
+template <bool DIELECTRIC, bool TRANSIENT>
 __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, unsigned *st) {
     const MediumDev &M = P.M;
     const float zero[3] = {0.f, 0.f, 0.f};
@@ -309,12 +323,13 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             float3 o = f3(P.camO[0], P.camO[1], P.camO[2]);
             float tBox, tQuad;
             bool hitBox = intersect_shape(M, o, d, tBox), hitQuad = intersect_quad(P, o, d, tQuad);
-            if (hitQuad && (!hitBox || tQuad < tBox)) { finish_sample(P, L, P.quadLe, 1.0f, st); continue; }
+            if (hitQuad && (!hitBox || tQuad < tBox)) { finish_sample(P, L, P.quadLe, 1.0f, st, P.calibrated ? 0.0f : tQuad); continue; }
             if (!hitBox) { finish_sample(P, L, P.env, 0.0f, st); continue; }
             L.depth = 1;
             if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
             if (!DIELECTRIC) L.depth = 2; /* index-matched container surface, volpath.cpp:287-296 */
             L.etaPath = 1.0f;
+            L.opl = P.calibrated ? 0.0f : tBox; /* bdpt_proc.cpp:163-171 */
             L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
             L.v = d;
             L.thr[0] = L.thr[1] = L.thr[2] = 1.0f;
@@ -361,7 +376,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 const bool hitsQuad = intersect_quad(P, L.p, dOut, tq);
                 const float *Le = hitsQuad ? ((L.flags & FLAG_COVERED) ? zero : P.quadLe) : P.env;
                 float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
-                finish_sample(P, L, rad, 1.0f, st);
+                finish_sample(P, L, rad, 1.0f, st, hitsQuad ? L.opl + tq : INFINITY);
                 continue;
             }
             L.flags &= ~FLAG_COVERED; /* an internal reflection starts a chain no direct connection accounts for */
@@ -383,6 +398,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                     P.neeQ0[slot] = make_float4(L.p.x, L.p.y, L.p.z, wi.x);
                     P.neeQ1[slot] = make_float4(wi.y, wi.z, L.thr[0], L.thr[1]);
                     P.neeQ2[slot] = make_uint4(__float_as_uint(L.thr[2]), (unsigned) L.depth, L.pixel, L.sample);
+                    if (TRANSIENT) P.neeQ3[slot] = L.opl;
                 }
                 L.flags |= FLAG_COVERED;
             }
@@ -453,13 +469,13 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 const bool hitsQuad = intersect_quad(P, L.p, d, tq);
                 const float *Le = hitsQuad ? ((L.flags & FLAG_COVERED) ? zero : P.quadLe) : P.env;
                 float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
-                finish_sample(P, L, rad, 1.0f, st);
+                finish_sample(P, L, rad, 1.0f, st, hitsQuad ? L.opl + tq : INFINITY);
             }
         }
     }
 }
 
-template <int MODE, bool DIELECTRIC>
+template <int MODE, bool DIELECTRIC, bool TRANSIENT>
 __global__ void __launch_bounds__(128, MER_RENDER_MIN_BLOCKS)
 k_render_pass(const __grid_constant__ RenderParams P) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -483,13 +499,16 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.rng.init(P.seed, (unsigned long long) e.z * (unsigned long long) P.sppTotal + e.w, e.y);
         float4 fg = P.in.q5[tid];
         L.n = fg.x; L.G = f3(fg.y, fg.z, fg.w);
-        L.etaPath = DIELECTRIC ? P.in.q6[tid].x : 1.0f;
+        L.etaPath = 1.0f;
+        L.opl = 0.0f;
+        if (DIELECTRIC || TRANSIENT) { const float4 ex = P.in.q6[tid]; L.etaPath = ex.x; L.opl = ex.y; }
     } else {
         L.p = L.v = L.G = f3(0.f, 0.f, 0.f);
         L.n = 1.0f;
         L.thr[0] = L.thr[1] = L.thr[2] = 0.0f;
         L.refStart = L.segDist = L.distSurf = L.rem = L.sd = 0.0f;
         L.etaPath = 1.0f;
+        L.opl = 0.0f;
         L.stepsLeft = L.depth = L.flags = 0;
         L.pixel = L.sample = 0;
         L.rng.init(P.seed, 0ULL, 0u);
@@ -524,7 +543,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
                 const int kind = L.kind;
                 const float hc = kind == K_FULL ? h : (kind == K_REM ? L.rem : (kind == K_BACKF ? -h : (kind == K_BACKR ? -L.rem : 0.0f)));
                 const float3 pOld = L.p;
-                er_step_fused<MODE>(M.rif, S, L.p, L.v, L.n, L.G, hc, oplUnused);
+                er_step_fused<MODE>(M.rif, S, L.p, L.v, L.n, L.G, hc, TRANSIENT ? L.opl : oplUnused);
                 const bool inside = inside_shape(M, L.p);
                 const bool moved = L.p.x != pOld.x || L.p.y != pOld.y || L.p.z != pOld.z;
                 int next;
@@ -546,7 +565,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
             }
         } else if (mw != 0u) {
             /* ---------------- event phase: scatter / exit / regenerate for every waiting lane at once */
-            if (waiting) handle_events<DIELECTRIC>(P, L, st);
+            if (waiting) handle_events<DIELECTRIC, TRANSIENT>(P, L, st);
         } else {
             break; /* budget exhausted (or nobody alive) and nothing waiting */
         }
@@ -566,7 +585,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         P.out.q3[o] = make_float4(L.rem, L.sd, __int_as_float(L.stepsLeft), __int_as_float(L.depth));
         P.out.q4[o] = make_uint4((unsigned) L.kind | ((unsigned) L.flags << 8), L.rng.k, L.pixel, L.sample);
         P.out.q5[o] = make_float4(L.n, L.G.x, L.G.y, L.G.z);
-        if (DIELECTRIC) P.out.q6[o] = make_float4(L.etaPath, 0.f, 0.f, 0.f);
+        if (DIELECTRIC || TRANSIENT) P.out.q6[o] = make_float4(L.etaPath, L.opl, 0.f, 0.f);
     }
 
     /* ---------------- statistics: warp reduce, one atomic per warp and counter */
@@ -640,6 +659,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         const float3 p1 = f3(a.x, a.y, a.z), wi = f3(a.w, b.x, b.y);
         const float thr[3] = {b.z, b.w, __uint_as_float(c.x)};
         const unsigned depth = c.y, pixel = c.z, sample = c.w;
+        const float oplVertex = P.frames > 1 ? P.neeQ3[i] : 0.0f;
         PathRng nrng;
         nrng.init(P.seed ^ MER_NEE_SALT, (unsigned long long) pixel * (unsigned long long) P.sppTotal + sample, depth * 256u);
         const float u = nrng.next(), w = nrng.next();
@@ -677,7 +697,9 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                     rad[k] = thr[k] * phase * fastexp_dev(M.sigmaT[k] * -C.dist) * C.weight * scale * P.quadLe[k] * geom;
                 float sx, sy;
                 sample_position(P, pixel, sample, sx, sy);
-                film_put(P, sx, sy, rad, 0.0f, 0.0f, nonfinite);
+                /* the connection's optical length: curved part (midpoint rule, :941-1030) + exterior segment */
+                const int frame = path_frame(P, oplVertex + C.opl);
+                if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, nonfinite);
             }
         }
         if (!ok) st[1] = 1u;
@@ -694,12 +716,12 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
 }
 
 /* HDRFilm::develop: ESpectrumAlphaWeight -> RGB */
-__global__ void k_develop(size_t nPixels, const float *__restrict__ film, float *__restrict__ rgb) {
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nPixels; i += (size_t) gridDim.x * blockDim.x) {
-        float w = film[5 * i + 4], inv = w != 0.0f ? 1.0f / w : 0.0f;
-        rgb[3 * i] = film[5 * i] * inv;
-        rgb[3 * i + 1] = film[5 * i + 1] * inv;
-        rgb[3 * i + 2] = film[5 * i + 2] * inv;
+__global__ void k_develop(size_t nPixels, int frames, const float *__restrict__ film, float *__restrict__ rgb) {
+    const size_t C = 3 * (size_t) frames + 2, V = 3 * (size_t) frames;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nPixels * V; i += (size_t) gridDim.x * blockDim.x) {
+        const size_t px = i / V, k = i - px * V;
+        const float w = film[C * px + C - 1], inv = w != 0.0f ? 1.0f / w : 0.0f;
+        rgb[i] = film[C * px + k] * inv;
     }
 }
 
@@ -790,6 +812,12 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.maxWait = 12;
     if (const char *e = getenv("MER_MAX_WAIT")) P.maxWait = atoi(e); /* tuning knob */
     P.film = film_dev;
+    P.frames = r->frames > 1 ? r->frames : 1;
+    P.channels = 3 * P.frames + 2;
+    P.minBound = r->min_bound;
+    P.binWidth = r->bin_width;
+    P.calibrated = r->calibrated_transient ? 1 : 0;
+    if (P.frames > 1) MER_REQUIRE(r->bin_width > 0.0f, "transient film: bin_width must be positive");
     P.nee = r->direct_connections ? 1 : 0;
     /* the reference drops connections that leave the shape within sqrt(Epsilon) = 0.01 of p1; for next-event estimation that
      * would discard the brightest vertices (those next to the surface facing the light), so only exact degeneracy is dropped */
@@ -830,12 +858,16 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
             MER_CUDA(cudaMalloc(&S.neePerm, (size_t) cap * sizeof(unsigned)));
             MER_CUDA(cudaMalloc(&S.neeKey, (size_t) cap));
             if (!S.neeHist) MER_CUDA(cudaMalloc(&S.neeHist, NEE_BINS * sizeof(unsigned)));
+            cudaFree(S.neeOpl);
+            S.neeOpl = nullptr;
+            MER_CUDA(cudaMalloc(&S.neeOpl, (size_t) cap * sizeof(float)));
             if (!S.neeCount) MER_CUDA(cudaMalloc(&S.neeCount, sizeof(unsigned)));
             S.neeCap = cap;
         }
         P.neeCap = cap;
         P.neeCount = S.neeCount;
         P.neeQ0 = (float4 *) S.neeQ[0]; P.neeQ1 = (float4 *) S.neeQ[1]; P.neeQ2 = (uint4 *) S.neeQ[2];
+        P.neeQ3 = S.neeOpl;
         P.neeKey = S.neeKey;
         P.neeHist = S.neeHist;
         P.neePerm = m->dev.hasSdf ? nullptr : S.neePerm; /* the length estimate needs an analytic container */
@@ -863,14 +895,16 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         P.nIn = nLive;
         MER_CUDA(cudaMemsetAsync(S.nOut, 0, sizeof(unsigned), stream));
         const unsigned blocks = (threads + TPB - 1) / TPB;
-        const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC;
+        const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, transient = P.frames > 1;
+#define MER_PASS(MODE_, D_, T_) MER_LAUNCH((k_render_pass<MODE_, D_, T_>), blocks, TPB, 0, stream, P)
         if (m->rif->mode == MER_RIF_TRICUBIC) {
-            if (dielectric) MER_LAUNCH((k_render_pass<MER_RIF_TRICUBIC, true>), blocks, TPB, 0, stream, P);
-            else MER_LAUNCH((k_render_pass<MER_RIF_TRICUBIC, false>), blocks, TPB, 0, stream, P);
+            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true); else MER_PASS(MER_RIF_TRICUBIC, true, false); }
+            else { if (transient) MER_PASS(MER_RIF_TRICUBIC, false, true); else MER_PASS(MER_RIF_TRICUBIC, false, false); }
         } else {
-            if (dielectric) MER_LAUNCH((k_render_pass<MER_RIF_TRILINEAR_PACKED, true>), blocks, TPB, 0, stream, P);
-            else MER_LAUNCH((k_render_pass<MER_RIF_TRILINEAR_PACKED, false>), blocks, TPB, 0, stream, P);
+            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRILINEAR_PACKED, true, true); else MER_PASS(MER_RIF_TRILINEAR_PACKED, true, false); }
+            else { if (transient) MER_PASS(MER_RIF_TRILINEAR_PACKED, false, true); else MER_PASS(MER_RIF_TRILINEAR_PACKED, false, false); }
         }
+#undef MER_PASS
         launches++;
         passes++;
         /* the only host<->device traffic of a pass: 12 bytes telling the host how to size the next one */
@@ -883,15 +917,17 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         if (P.nee) {
             const unsigned nReq = std::min(*(unsigned *) (S.hostPinned + 2), P.neeCap);
             if (nReq) {
-                if (P.neePerm && nReq > 32u) {
+                RenderParams Pn = P; /* this launch's view: sorted only when the sort ran */
+                if (!(P.neePerm && nReq > 32u)) Pn.neePerm = nullptr;
+                if (Pn.neePerm) {
                     MER_CUDA(cudaMemsetAsync(S.neeHist, 0, NEE_BINS * sizeof(unsigned), stream));
                     MER_LAUNCH(k_nee_keys, (nReq + 255u) / 256u, 256, 0, stream, P, nReq);
                     MER_LAUNCH(k_nee_offsets, 1, 32, 0, stream, S.neeHist);
                     MER_LAUNCH(k_nee_scatter, (nReq + 255u) / 256u, 256, 0, stream, P, nReq);
                     launches += 3;
                 }
-                if (neeMinBlocks >= 3) MER_LAUNCH(k_nee<3>, (nReq + TPB - 1) / TPB, TPB, 0, stream, P, nReq);
-                else MER_LAUNCH(k_nee<2>, (nReq + TPB - 1) / TPB, TPB, 0, stream, P, nReq);
+                if (neeMinBlocks >= 3) MER_LAUNCH(k_nee<3>, (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
+                else MER_LAUNCH(k_nee<2>, (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
                 launches++;
                 MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
             }
@@ -927,7 +963,7 @@ int mer_render(const mer_medium *m, const mer_render_desc *r, float *film_host, 
     MER_REQUIRE(r->width > 0 && r->height > 0, "film size must be positive");
     mer::DeviceGuard guard(m->device);
     float *film = nullptr;
-    const size_t bytes = (size_t) r->width * r->height * 5 * sizeof(float);
+    const size_t bytes = (size_t) r->width * r->height * (3 * (size_t) (r->frames > 1 ? r->frames : 1) + 2) * sizeof(float);
     MER_CUDA(cudaMalloc(&film, bytes));
     cudaError_t e = cudaMemset(film, 0, bytes);
     int rc = e == cudaSuccess ? mer_render_device(m, r, film, stats_out, nullptr) : mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));
@@ -939,25 +975,29 @@ int mer_render(const mer_medium *m, const mer_render_desc *r, float *film_host, 
     return rc;
 }
 
-int mer_film_develop(int device, int32_t width, int32_t height, const float *film, float *rgb_out) {
-    MER_REQUIRE(film && rgb_out && width > 0 && height > 0, "bad argument");
+int mer_film_develop_frames(int device, int32_t width, int32_t height, int32_t frames, const float *film, float *rgb_out) {
+    MER_REQUIRE(film && rgb_out && width > 0 && height > 0 && frames > 0, "bad argument");
     int rc = mer::check_device(device);
     if (rc) return rc;
     mer::DeviceGuard guard(device);
-    const size_t n = (size_t) width * height;
+    const size_t n = (size_t) width * height, C = 3 * (size_t) frames + 2, V = 3 * (size_t) frames;
     float *df = nullptr, *dr = nullptr;
-    MER_CUDA(cudaMalloc(&df, n * 5 * sizeof(float)));
-    MER_CUDA(cudaMalloc(&dr, n * 3 * sizeof(float)));
-    cudaError_t e = cudaMemcpy(df, film, n * 5 * sizeof(float), cudaMemcpyHostToDevice);
+    MER_CUDA(cudaMalloc(&df, n * C * sizeof(float)));
+    MER_CUDA(cudaMalloc(&dr, n * V * sizeof(float)));
+    cudaError_t e = cudaMemcpy(df, film, n * C * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        k_develop<<<(unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256>>>(n, df, dr);
+        k_develop<<<(unsigned) std::min<size_t>(mer_blocks(n * V, 256), 148u * 8u), 256>>>(n, frames, df, dr);
         mer::g_launches.fetch_add(1);
-        e = cudaMemcpy(rgb_out, dr, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(rgb_out, dr, n * V * sizeof(float), cudaMemcpyDeviceToHost);
     }
     cudaFree(df);
     cudaFree(dr);
     if (e != cudaSuccess) return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));
     return MER_OK;
+}
+
+int mer_film_develop(int device, int32_t width, int32_t height, const float *film, float *rgb_out) {
+    return mer_film_develop_frames(device, width, height, 1, film, rgb_out);
 }
 
 } /* extern "C" */

@@ -505,12 +505,20 @@ class EikonalVolPathIntegrator:
         r.connection.boundary_precision = int(mp.get("boundaryprecision", 3))
         r.connection.max_iterations = int(mp.get("ceresmaxiterations", 20))
         r.connection.start_mode = 1 if self.connectionStart == "random" else 2
+        tr = scene.get("transient")  # <film>: decomposition="transient", minBound, maxBound, binWidth, calibratedTransient
+        if tr:
+            width = float(tr.get("binWidth", 1.0))
+            if not width > 0:
+                raise _abi.MerError(_abi.MER_ERR_INVALID, "transient film: binWidth must be positive")
+            r.frames = int(np.ceil((float(tr["maxBound"]) - float(tr["minBound"])) / width))  # film.cpp:73
+            r.min_bound, r.bin_width = float(tr["minBound"]), width
+            r.calibrated_transient = 1 if tr.get("calibrated", tr.get("calibratedTransient", False)) else 0
         return r
 
     def render(self, scene, medium, sample_begin=0, sample_stride=1):
-        """-> (film[H][W][5] = [R,G,B,alpha,weight], stats dict)"""
+        """-> (film[H][W][5] = [R,G,B,alpha,weight], stats dict); with scene["transient"]: film[H][W][3*frames+2]"""
         r = self.render_desc(scene, sample_begin, sample_stride, medium)
-        film = np.zeros((r.height, r.width, 5), np.float32)
+        film = np.zeros((r.height, r.width, 3 * max(int(r.frames), 1) + 2), np.float32)
         stats = _abi.RenderStats()
         check(lib.mer_render(medium.handle, C.byref(r), _fp(film), C.byref(stats)))
         return film, stats.as_dict()
@@ -525,9 +533,10 @@ class EikonalVolPathIntegrator:
 
 
 def develop(film, device=0):
-    """HDRFilm::develop: [H][W][5] -> RGB [H][W][3]"""
+    """HDRFilm::develop: [H][W][5] -> RGB [H][W][3]; transient film [H][W][3*frames+2] -> [H][W][frames][3]"""
     film = _f32(film)
-    H, W, _ = film.shape
-    rgb = np.zeros((H, W, 3), np.float32)
-    check(lib.mer_film_develop(device, W, H, _fp(film), _fp(rgb)))
-    return rgb
+    H, W, ch = film.shape
+    frames = (ch - 2) // 3
+    rgb = np.zeros((H, W, frames, 3), np.float32)
+    check(lib.mer_film_develop_frames(device, W, H, frames, _fp(film), _fp(rgb)))
+    return rgb[:, :, 0, :] if frames == 1 else rgb

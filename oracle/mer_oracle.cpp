@@ -1187,8 +1187,8 @@ struct Filter {
 };
 
 /* returns false (and leaves the film untouched) for a non-finite sample, imageblock.h:147-152 */
-inline bool film_put(float *film, int W, int H, const Filter &flt, float sx, float sy, const float value[5]) {
-    for (int i = 0; i < 5; i++)
+inline bool film_put(float *film, int W, int H, const Filter &flt, float sx, float sy, const float *value, int channels = 5) {
+    for (int i = 0; i < channels; i++)
         if (!std::isfinite(value[i])) return false;
     const float px = sx - 0.5f, py = sy - 0.5f, r = flt.radius;
     const int x0 = std::max((int) std::ceil(px - r), 0), y0 = std::max((int) std::ceil(py - r), 0),
@@ -1199,8 +1199,8 @@ inline bool film_put(float *film, int W, int H, const Filter &flt, float sx, flo
     for (int y = y0, yr = 0; y <= y1; ++y, ++yr)
         for (int x = x0, xr = 0; x <= x1; ++x, ++xr) {
             const float w = wx[xr] * wy[yr];
-            float *dest = film + ((size_t) y * W + x) * 5;
-            for (int k = 0; k < 5; k++) dest[k] += w * value[k];
+            float *dest = film + ((size_t) y * W + x) * channels;
+            for (int k = 0; k < channels; k++) dest[k] += w * value[k];
         }
     return true;
 }
@@ -1319,6 +1319,20 @@ struct Stats {
     uint64_t connections = 0, connFailed = 0, connSteps = 0;
 };
 
+/* Where a path's contributions go: one RGB triple (steady state) or the frame of the transient film selected by the
+ * optical path length, bdpt_proc.cpp:446-449: binIndex = floor((pathLength - minBound) / binWidth), kept if in [0, frames) */
+struct Radiance {
+    float *L;
+    int frames;
+    float minBound, binWidth;
+    void add(float pathLength, const float rgb[3]) const {
+        if (frames <= 1) { for (int i = 0; i < 3; i++) L[i] += rgb[i]; return; }
+        const float b = std::floor((pathLength - minBound) / binWidth);
+        if (!(b >= 0.0f && b < (float) frames)) return;
+        for (int i = 0; i < 3; i++) L[3 * (int) b + i] += rgb[i];
+    }
+};
+
 const uint64_t kNeeSalt = 0x5851F42D4C957F2DULL; /* next-event estimation draws come from their own Philox key */
 
 /* Next-event estimation of the quad emitter from a scattering vertex p1 of the medium.  The curved
@@ -1329,7 +1343,7 @@ const uint64_t kNeeSalt = 0x5851F42D4C957F2DULL; /* next-event estimation draws 
  * launch direction at p1 to the sampled point y written with the solver's Jacobian instead of 1/distance^2. */
 template <typename F>
 void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, const float wi[3], const float thr[3], int depth,
-                 uint64_t sampleId, float L[3], Stats &st) {
+                 uint64_t sampleId, const Radiance &L, float pathLength, Stats &st) {
     PhiloxStream nrng;
     nrng.init(R.seed ^ kNeeSalt, sampleId);
     nrng.ctr[2] = (uint32_t) depth * 64u; /* 256 draws per vertex */
@@ -1374,17 +1388,21 @@ void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, cons
         scale *= (1.0f - Fr) * (C.exit.nb * C.exit.nb);
     }
     const float geom = cosY * area / spread;
+    float rad[3];
     for (int c = 0; c < 3; c++) {
         float T = (float) std::exp((double) (M.sigmaT[c] * (float) (-C.dist)));
-        L[c] += thr[c] * phase * T * (float) C.weight * scale * R.quad_radiance[c] * geom;
+        rad[c] = thr[c] * phase * T * (float) C.weight * scale * R.quad_radiance[c] * geom;
     }
+    L.add(pathLength + (float) C.opticalDist, rad); /* the connection's optical length: curved part + exterior segment */
 }
 
 template <typename F>
 void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const float dcam[3], PhiloxStream &rng,
-        float L[3], float &alpha, Stats &st, uint64_t sampleId = 0) {
-    L[0] = L[1] = L[2] = 0;
+        float *Lout, float &alpha, Stats &st, uint64_t sampleId = 0) {
+    const Radiance L = {Lout, R.frames > 1 ? R.frames : 1, R.min_bound, R.bin_width};
+    for (int i = 0; i < 3 * L.frames; i++) Lout[i] = 0;
     alpha = 0;
+    F opl = 0; /* optical path length from the camera (or from the first surface: calibrated_transient) */
     float thr[3] = {1, 1, 1}, etaPath = 1.0f;
     int depth = 1;
     const bool dielectric = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
@@ -1394,14 +1412,15 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
     bool hitBox = intersectShape(M.d, o, dcam, tBox);
     bool hitQuad = intersectQuad(R, o, dcam, tQuad);
     if (hitQuad && (!hitBox || tQuad < tBox)) {
-        for (int i = 0; i < 3; i++) L[i] = R.quad_radiance[i];
+        L.add(R.calibrated_transient ? 0.0f : tQuad, R.quad_radiance);
         alpha = 1;
         return;
     }
     if (!hitBox) {
-        for (int i = 0; i < 3; i++) L[i] = R.env_radiance[i];
+        L.add(std::numeric_limits<float>::infinity(), R.env_radiance);
         return;
     }
+    if (!R.calibrated_transient) opl = (F) tBox;
     alpha = 1;
     if (R.max_depth != -1 && depth >= R.max_depth) return; /* volpath.cpp:200-201 */
     F p[3], dir[3];
@@ -1413,7 +1432,8 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         const bool hitsQuad = intersectQuad(R, q, e, tq);
         if (hitsQuad && covered) return;
         const float *Le = hitsQuad ? R.quad_radiance : R.env_radiance;
-        for (int i = 0; i < 3; i++) L[i] += thr[i] * Le[i];
+        const float rad[3] = {thr[0] * Le[0], thr[1] * Le[1], thr[2] * Le[2]};
+        L.add(hitsQuad ? (float) opl + tq : std::numeric_limits<float>::infinity(), rad);
     };
     /* Russian roulette of volpath.cpp:326-336 (eta = product of the BSDFs' relative indices) */
     auto roulette = [&]() {
@@ -1454,7 +1474,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         if (!M.rif->insideVolumeLimits(p)) return; /* transmittance = 0, :461-466 */
         F refStart = M.rif->value(p);
         F v[3] = {dir[0] * refStart, dir[1] * refStart, dir[2] * refStart};
-        F distSurf = 0, opl = 0;
+        F distSurf = 0;
         long nsteps = 0;
         bool success;
         float edge[3]; /* T / pdf (and sigma_s on success) */
@@ -1531,7 +1551,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             float wi[3] = {(float) (-v[0] * vinv), (float) (-v[1] * vinv), (float) (-v[2] * vinv)}, wo[3];
             if (nee) {
                 covered = true;
-                if (R.max_depth == -1 || depth + 1 < R.max_depth) directLight<F>(M, R, p, wi, thr, depth, sampleId, L, st);
+                if (R.max_depth == -1 || depth + 1 < R.max_depth) directLight<F>(M, R, p, wi, thr, depth, sampleId, L, (float) opl, st);
             }
             float u1 = rng.next(), u2 = rng.next();
             hg_sample(M.d.hg_g, wi, u1, u2, wo);
@@ -1567,13 +1587,14 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
     Camera cam;
     cam.configure(&R);
     const int bx = (W + B - 1) / B, by = (H + B - 1) / B;
+    const int channels = 3 * (R.frames > 1 ? R.frames : 1) + 2; /* bdpt_wr.cpp:52-56 */
     Stats total;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
 #pragma omp parallel
     {
-        std::vector<float> local((size_t) W * H * 5, 0.f);
+        std::vector<float> local((size_t) W * H * channels, 0.f), value(channels);
         Stats st;
 #pragma omp for schedule(dynamic, 1) nowait
         for (int b = 0; b < bx * by; b++) {
@@ -1584,12 +1605,13 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
                         PhiloxStream rng;
                         rng.init(R.seed, ((uint64_t) y * W + x) * (uint64_t) R.spp_total + (uint64_t) s);
                         float sx = x + rng.next(), sy = y + rng.next();
-                        float d[3], L[3], alpha;
+                        float d[3], alpha;
                         cam.sampleRay(sx, sy, d);
-                        Li<F>(Mr, R, cam.o, d, rng, L, alpha, st, ((uint64_t) y * W + x) * (uint64_t) R.spp_total + (uint64_t) s);
+                        Li<F>(Mr, R, cam.o, d, rng, value.data(), alpha, st, ((uint64_t) y * W + x) * (uint64_t) R.spp_total + (uint64_t) s);
                         st.samples++;
-                        float value[5] = {L[0], L[1], L[2], alpha, 1.0f};
-                        if (!film_put(local.data(), W, H, flt, sx, sy, value)) st.nonfinite++;
+                        value[channels - 2] = alpha;
+                        value[channels - 1] = 1.0f;
+                        if (!film_put(local.data(), W, H, flt, sx, sy, value.data(), channels)) st.nonfinite++;
                     }
         }
 #pragma omp critical
@@ -1835,12 +1857,14 @@ extern "C" void orc_camera_ray(const mer_render_desc *r, size_t n, const float *
     for (size_t i = 0; i < n; i++) c.sampleRay(samplePos[2 * i], samplePos[2 * i + 1], d + 3 * i);
 }
 /* HDRFilm::develop, src/films/hdrfilm.cpp:527-540 (ESpectrumAlphaWeight -> RGB) */
-extern "C" void orc_film_develop(int W, int H, const float *film, float *rgb) {
+extern "C" void orc_film_develop_frames(int W, int H, int frames, const float *film, float *rgb) {
+    const int C = 3 * frames + 2;
     for (size_t i = 0; i < (size_t) W * H; i++) {
-        float w = film[5 * i + 4], inv = w != 0 ? 1.0f / w : 0.0f;
-        for (int k = 0; k < 3; k++) rgb[3 * i + k] = film[5 * i + k] * inv;
+        float w = film[C * i + C - 1], inv = w != 0 ? 1.0f / w : 0.0f;
+        for (int k = 0; k < 3 * frames; k++) rgb[3 * frames * i + k] = film[C * i + k] * inv;
     }
 }
+extern "C" void orc_film_develop(int W, int H, const float *film, float *rgb) { orc_film_develop_frames(W, H, 1, film, rgb); }
 extern "C" int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -47,7 +47,8 @@ class RenderDesc(C.Structure):
                 ("env_radiance", C.c_float * 3), ("has_quad", C.c_int32), ("quad_origin", C.c_float * 3),
                 ("quad_u", C.c_float * 3), ("quad_v", C.c_float * 3), ("quad_radiance", C.c_float * 3),
                 ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32), ("direct_connections", C.c_int32),
-                ("connection", ConnectionParams)]
+                ("connection", ConnectionParams), ("frames", C.c_int32), ("min_bound", C.c_float), ("bin_width", C.c_float),
+                ("calibrated_transient", C.c_int32)]
 
 
 class RenderStats(C.Structure):
@@ -379,7 +380,7 @@ class Oracle:
 
     # ---- integrator
     def render(self, medium, rdesc, nthreads=0):
-        film = np.zeros((rdesc.height, rdesc.width, 5), dtype=np.float32)
+        film = np.zeros((rdesc.height, rdesc.width, 3 * max(int(rdesc.frames), 1) + 2), dtype=np.float32)
         stats = RenderStats()
         self._fn("orc_render")(medium, C.byref(rdesc), _ptr(film, C.c_float), C.byref(stats), C.c_int(nthreads))
         return film, stats
@@ -402,8 +403,10 @@ class Oracle:
         return d
 
     def film_develop(self, film):
-        H, W, _ = film.shape
+        """[H][W][3*frames+2] -> [H][W][3] (steady state) or [H][W][frames][3]"""
+        H, W, ch = film.shape
+        frames = (ch - 2) // 3
         film = np.ascontiguousarray(film, dtype=np.float32)
-        rgb = np.zeros((H, W, 3), dtype=np.float32)
-        self.lib.orc_film_develop(C.c_int(W), C.c_int(H), _ptr(film, C.c_float), _ptr(rgb, C.c_float))
-        return rgb
+        rgb = np.zeros((H, W, frames, 3), dtype=np.float32)
+        self.lib.orc_film_develop_frames(C.c_int(W), C.c_int(H), C.c_int(frames), _ptr(film, C.c_float), _ptr(rgb, C.c_float))
+        return rgb[:, :, 0, :] if frames == 1 else rgb

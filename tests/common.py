@@ -122,4 +122,9 @@ def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_s
     r.connection.boundary_precision = int(props.get("boundaryprecision", 3))
     r.connection.max_iterations = int(props.get("ceresmaxiterations", 20))
     r.connection.start_mode = 1 if start == "random" else 2
+    tr = scene.get("transient")  # dict(minBound, maxBound, binWidth[, calibrated]) as on <film>
+    if tr:
+        r.frames = int(np.ceil((tr["maxBound"] - tr["minBound"]) / tr["binWidth"]))
+        r.min_bound, r.bin_width = float(tr["minBound"]), float(tr["binWidth"])
+        r.calibrated_transient = 1 if tr.get("calibrated", False) else 0
     return r

@@ -285,3 +285,40 @@ def test_oracle_direct_connections_agree_with_random_walk(oracle32):
     assert st.connections > 30000 and st.connections_failed < 0.01 * st.connections
     assert st.connection_steps / st.connections < 4 * (2.5 / 1e-2)  # ~2-3 residual evaluations of ~200 steps each
     assert abs(means[True] / means[False] - 1 + 0.75 * 2.0 * 1e-2) < 0.05, means  # walk noise ~1.5 % at 49k samples
+
+
+def test_oracle_transient_film(oracle32):
+    """next-row 2 (film half): path-length resolved film of the fork (film.cpp:56-78, bdpt_proc.cpp:147-176, 446-449)"""
+    from common import BOX_MAX, BOX_MIN, medium_props, oracle_medium_desc, oracle_render_desc, scene_dict
+    from mitsubaer_b200 import fields
+    res = 16
+    lo, hi = fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    orif = oracle32.rif_create(volume_desc((res,) * 3, lo, hi), np.full((res,) * 3, 1.5, np.float32))
+    # (i) a clear slab of index 1.5 in front of a bright wall: camera -> box 3, inside 2 * 1.5, box -> wall 2: length 8
+    clear = oracle32.medium_create(oracle_medium_desc(medium_props(stepsize=1e-2, sigmaS=0.0, sigmaA=0.0, mediumSamplingWeight=0.0), 0.0), orif)
+    scene = scene_dict(8, 8, 8, rfilter="box", quad=False)
+    scene.update(fov=2.0, envRadiance=0.0, quad=dict(origin=(-50.0, -50.0, 3.0), u=(100.0, 0.0, 0.0), v=(0.0, 100.0, 0.0), radiance=(1.0, 1.0, 1.0)),
+                 transient=dict(minBound=7.0, maxBound=9.0, binWidth=0.125))
+    film, st = oracle32.render(clear, oracle_render_desc(scene))
+    assert film.shape == (8, 8, 3 * 16 + 2)
+    frames = oracle32.film_develop(film)[..., 0].mean(axis=(0, 1))
+    # the walk stops up to 2 h short of the far face (exit quirk), i.e. lengths in (8 - 0.03, 8 + 1e-3]
+    assert abs(frames[7] + frames[8] - 1.0) < 1e-5 and frames[:7].sum() == 0 and frames[9:].sum() == 0
+    scene["transient"]["calibrated"] = True  # the camera segment (3) is not counted
+    scene["transient"].update(minBound=4.0, maxBound=6.0)
+    frames = oracle32.film_develop(oracle32.render(clear, oracle_render_desc(scene))[0])[..., 0].mean(axis=(0, 1))
+    assert abs(frames[7] + frames[8] - 1.0) < 1e-5
+    # (ii) scattering medium + direct connections: the frames add up to the steady-state image of the same samples
+    lin = oracle32.rif_create(volume_desc((res,) * 3, lo, hi), fields.linear_rif((res,) * 3, lo, hi))
+    props = medium_props(stepsize=2e-2, sigmaS=1.5, sigmaA=0.5)
+    med = oracle32.medium_create(oracle_medium_desc(props, 0.5), lin)
+    for nee in (False, True):
+        scene = scene_dict(16, 16, 8, rfilter="gaussian")
+        scene["envRadiance"] = 0.0
+        steady, _ = oracle32.render(med, oracle_render_desc(scene, direct_connections=nee, props=props))
+        scene["transient"] = dict(minBound=0.0, maxBound=64.0, binWidth=0.5)
+        trans, _ = oracle32.render(med, oracle_render_desc(scene, direct_connections=nee, props=props))
+        rgb = trans[..., :-2].reshape(16, 16, -1, 3)
+        assert np.allclose(rgb.sum(axis=2), steady[..., :3], rtol=1e-5, atol=1e-6)
+        assert np.array_equal(trans[..., -2:], steady[..., 3:])
+        assert (rgb.sum(axis=(0, 1, 3)) > 0).sum() >= 5  # light arrives spread over several frames
