@@ -299,7 +299,8 @@ typedef struct mer_render_desc {
     /* next-event estimation along the curved path: 0 = the quad emitter is found only by hitting it;
      * 1 = every scattering vertex in the medium is connected to a uniformly sampled point of the quad by solving the
      * shooting problem of makeDirectConnections (heterogeneousrefractive.cpp:1087-1163), and paths that reach the quad
-     * after a scattering event no longer count it.  Requires a quad, the tricubic RIF mode and no density grid. */
+     * after a scattering event no longer count it.  Requires a quad and the tricubic RIF mode; through a density grid the
+     * connection's transmittance is exp(-optical depth), midpoint rule on the re-trace's steps. */
     int32_t direct_connections;
     mer_connection_params connection; /* solver parameters for direct_connections = 1 (zeros => tol2 1e-6, rrweight 1e-2, 3, 20) */
     /* transient film: <film> properties decomposition="transient", minBound, maxBound, binWidth (src/librender/film.cpp

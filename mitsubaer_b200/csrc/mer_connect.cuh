@@ -275,6 +275,7 @@ static __device__ int compute_fdf(const MediumDev &M, int precision, float3 vi, 
  * midpoint-rule optical length, same closest-approach / boundary halvings. */
 struct ExitInfo { /* how a connection left the container (next-event estimation needs the boundary terms) */
     bool exited, tir;
+    float tau;  /* optical depth of the density grid along the connection (midpoint rule on the re-trace's steps) */
     float nb;   /* RIF at the exit point */
     float cosI; /* cosine between the interior direction and the outward normal */
 };
@@ -286,6 +287,7 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
     ex.exited = ex.tir = false;
     ex.nb = 1.0f;
     ex.cosI = 1.0f;
+    ex.tau = 0.0f;
     float h = M.h, n, oldn, dummy = 0.0f;
     int nBisect = (int) ceil((double) precision / log10(2.0));
     float3 p = p1, v = dirToP2, oldp, oldv, G, oldG;
@@ -310,6 +312,7 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
                     rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
                     dist += h;
                     opl += h * nm;
+                    if (M.hasGrid) ex.tau += h * (grid_lookup(M.grid, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z))) * M.densityScale);
                     oldp = p; oldv = v; oldn = n; oldG = G;
                 }
             }
@@ -350,6 +353,7 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
                     rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
                     dist += h;
                     opl += h * nm;
+                    if (M.hasGrid) ex.tau += h * (grid_lookup(M.grid, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z))) * M.densityScale);
                     oldp = p; oldv = v; oldn = n; oldG = G;
                 }
             }
@@ -360,6 +364,7 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
             rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
             dist += h;
             opl += h * nm;
+            if (M.hasGrid) ex.tau += h * (grid_lookup(M.grid, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z))) * M.densityScale);
         }
     }
     const float3 d = p - p2;
@@ -401,6 +406,7 @@ static __device__ void connect_solve(const MediumDev &M, int precision, float to
     R.evals = R.steps = 0;
     R.exit.exited = R.exit.tir = false;
     R.exit.nb = R.exit.cosI = 1.0f;
+    R.exit.tau = 0.0f;
     if (!rif_inside_limits(M.hasSdf ? M.sdf : M.rif, p1)) return;
     float RIFp;
     float3 g0;

@@ -693,8 +693,10 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                 const float geom = cosY * area / spread;
                 float rad[3];
 #pragma unroll
-                for (int k = 0; k < 3; k++)
-                    rad[k] = thr[k] * phase * fastexp_dev(M.sigmaT[k] * -C.dist) * C.weight * scale * P.quadLe[k] * geom;
+                for (int k = 0; k < 3; k++) { /* homogeneous: exp(-sigma_t dist); density grid: exp(-optical depth along the curve) */
+                    const float T = fastexp_dev(M.hasGrid ? -C.exit.tau : M.sigmaT[k] * -C.dist);
+                    rad[k] = thr[k] * phase * T * C.weight * scale * P.quadLe[k] * geom;
+                }
                 float sx, sy;
                 sample_position(P, pixel, sample, sx, sy);
                 /* the connection's optical length: curved part (midpoint rule, :941-1030) + exterior segment */
@@ -786,8 +788,6 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         MER_REQUIRE(r->has_quad, "direct_connections needs the quad emitter");
         if (m->rif->mode != MER_RIF_TRICUBIC)
             return mer::fail(MER_ERR_UNSUPPORTED, "direct_connections needs the tricubic RIF mode (the solver differentiates the spline twice)");
-        if (m->dev.hasGrid)
-            return mer::fail(MER_ERR_UNSUPPORTED, "direct_connections with a density grid (transmittance along the curve) is not built");
     }
     mer::DeviceGuard guard(m->device);
     cudaStream_t stream = (cudaStream_t) stream_;

@@ -935,7 +935,7 @@ struct StraightWoodcock {
  * SAME residual and Jacobian (computefdf above), written identically in the CUDA path.  PARITY UNPINNED at
  * the solver: results are validated by the residual they reach, not against Ceres.
  * ------------------------------------------------------------------------------------------ */
-struct ExitInfo { bool exited = false, tir = false; float nb = 1, cosI = 1; };
+struct ExitInfo { bool exited = false, tir = false; float nb = 1, cosI = 1, tau = 0; /* tau: optical depth of the density grid */ };
 
 template <typename F> struct ConnectionResult {
     ExitInfo exit;
@@ -968,7 +968,14 @@ bool computePathLengths(const Medium<F> &M, const F *p1, const F *p2, const F *d
     F p[3] = {p1[0], p1[1], p1[2]}, v[3] = {dirToP2[0], dirToP2[1], dirToP2[2]}, oldp[3], oldv[3], d[3], mid[3], dummy = 0;
     for (int i = 0; i < 3; i++) d[i] = p[i] - p2[i];
     bool signOld = std::signbit(Medium<F>::dot(d, v)), signNew;
-    auto midpointN = [&]() { for (int i = 0; i < 3; i++) mid[i] = (F) 0.5 * (p[i] + oldp[i]); return M.rif->value(mid); };
+    auto midpointN = [&]() {
+        for (int i = 0; i < 3; i++) mid[i] = (F) 0.5 * (p[i] + oldp[i]);
+        if (M.density) { /* optical depth along the curve, same midpoints as the optical length */
+            float mf[3] = {(float) mid[0], (float) mid[1], (float) mid[2]};
+            ex.tau += (float) h0 * (M.density->lookupFloat(mf) * M.d.density_scale);
+        }
+        return M.rif->value(mid);
+    };
     for (int it = 0; it < 100000; it++) {
         for (int i = 0; i < 3; i++) { oldp[i] = p[i]; oldv[i] = v[i]; }
         M.er_step(p, v, h0, dummy, count);
@@ -1390,7 +1397,7 @@ void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, cons
     const float geom = cosY * area / spread;
     float rad[3];
     for (int c = 0; c < 3; c++) {
-        float T = (float) std::exp((double) (M.sigmaT[c] * (float) (-C.dist)));
+        float T = (float) std::exp((double) (M.density ? -C.exit.tau : M.sigmaT[c] * (float) (-C.dist)));
         rad[c] = thr[c] * phase * T * (float) C.weight * scale * R.quad_radiance[c] * geom;
     }
     L.add(pathLength + (float) C.opticalDist, rad); /* the connection's optical length: curved part + exterior segment */
@@ -1406,7 +1413,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
     float thr[3] = {1, 1, 1}, etaPath = 1.0f;
     int depth = 1;
     const bool dielectric = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
-    const bool nee = R.direct_connections != 0 && R.has_quad && !M.density;
+    const bool nee = R.direct_connections != 0 && R.has_quad;
     bool covered = false; /* the quad's light along the current edge chain was already estimated by a direct connection */
     float tBox, tQuad;
     bool hitBox = intersectShape(M.d, o, dcam, tBox);

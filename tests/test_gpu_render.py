@@ -280,10 +280,38 @@ def test_direct_connections_queue_and_validation(oracle32):
     pm = mer.HeterogeneousRefractiveMedium(props).addChild("rif", packed).configure()
     with pytest.raises(mer.MerError, match="tricubic"):
         mer.EikonalVolPathIntegrator(directConnections=True).render(scene, pm)
-    grid = mer.GridDataSource(data=mer.fields.sine_density((16,) * 3, BOX_MIN, BOX_MAX), min=BOX_MIN, max=BOX_MAX)
-    dm = mer.HeterogeneousRefractiveMedium(medium_props(stepsize=1e-2, albedo=0.9, densityScale=4.0)).addChild("rif", rif).addChild("density", grid).configure()
-    with pytest.raises(mer.MerError, match="density"):
-        mer.EikonalVolPathIntegrator(directConnections=True).render(scene, dm)
+
+
+def test_direct_connections_through_density_grid(oracle32):
+    """Woodcock medium (density grid) + direct connections: the connection's transmittance is exp(-optical depth) along the
+    curve.  Parity with the oracle on shared streams, and the same expectation as the walk without connections."""
+    data, lo, hi = make_field("linear", 32)
+    dres = (24,) * 3
+    dens = mer.fields.sine_density(dres, BOX_MIN, BOX_MAX)
+    props = medium_props(stepsize=5e-3, albedo=0.8, densityScale=3.0)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    grid = mer.GridDataSource(data=dens, min=BOX_MIN, max=BOX_MAX)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("density", grid).addChild("", mer.HGPhaseFunction(g=0.5)).configure()
+    omed = oracle32.medium_create(oracle_medium_desc(props, 0.5, has_density=True), oracle32.rif_create(volume_desc((32,) * 3, lo, hi), data),
+                                  oracle32.grid_create(volume_desc(dres, BOX_MIN, BOX_MAX), dens))
+    scene = scene_dict(32, 32, 4, rfilter="box")
+    scene["envRadiance"] = 0.0
+    film, st = mer.EikonalVolPathIntegrator(directConnections=True, poolPaths=2048, stepsPerPass=256).render(scene, med)
+    ofilm, ost = oracle32.render(omed, oracle_render_desc(scene, direct_connections=True, props=props))
+    assert st["connections"] > 2000 and abs(st["connections"] - ost.connections) <= 0.01 * ost.connections and st["null_collisions"] > 0
+    a, b = mer.develop(film), oracle32.film_develop(ofilm)
+    assert np.mean(np.abs(a - b) <= 2e-3 * np.maximum(b, 1.0)) > 0.97 and abs(a.mean() - b.mean()) <= 3e-3 * b.mean()
+    mean = {}
+    for nee in (False, True):
+        vals = []
+        for seed in range(1, 9):
+            sc = scene_dict(128, 128, 16, rfilter="box", seed=seed)
+            sc["envRadiance"] = 0.0
+            vals.append(float(mer.develop(mer.EikonalVolPathIntegrator(directConnections=nee).render(sc, med)[0])[..., 0].mean()))
+        mean[nee] = (np.mean(vals), np.std(vals, ddof=1) / np.sqrt(len(vals)))
+    ratio = mean[True][0] / mean[False][0] - 1
+    sigma = np.hypot(mean[True][1], mean[False][1]) / mean[False][0]
+    assert abs(ratio) < 4 * sigma + 4e-3, (ratio, sigma, mean)
 
 
 # ---------------------------------------------------------------------------------------------------------
