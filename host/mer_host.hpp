@@ -303,6 +303,9 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         desc.channel = (int) props.getInteger("channel", -1);
         desc.sampling_density = (float) props.getFloat("samplingDensity", 0.0);
         desc.density_scale = (float) scale;
+        const std::string scaling = props.getString("radianceScaling", "reference");
+        if (scaling != "reference" && scaling != "physical") logError("radianceScaling must be \"reference\" or \"physical\"");
+        desc.radiance_scaling = scaling == "physical" ? MER_SCALING_PHYSICAL : MER_SCALING_REFERENCE;
         props.getBoolean("monochromatic", false);
         /* solver parameters of the direct connections (heterogeneousrefractive.cpp:208-219), used when the integrator asks for them */
         connection.tol2 = (float) props.getFloat("tol2", 1e-6);

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 4
+#define MER_ABI_VERSION 5
 
 enum mer_status {
     MER_OK = 0,
@@ -157,7 +157,15 @@ typedef struct mer_medium_desc {
      *                               point, exterior index 1 (src/bsdfs/hdielectric.cpp:115-125, 244-300;
      *                               fresnelDielectricExt src/libcore/util.cpp:665-695) */
     int32_t boundary;
+    /* what a camera-side path edge multiplies into the throughput for the change of index along it:
+     *   MER_SCALING_REFERENCE  refRatioSq = (n_end / n_start)^2, as heterogeneousrefractive.cpp:469,501 + edge.cpp:96-98
+     *   MER_SCALING_PHYSICAL   (n_start / n_end)^2, what the invariance of L / n^2 along a ray asks for: with it a lossless
+     *                          medium in an hdielectric container under a uniform environment renders as exactly that
+     *                          environment */
+    int32_t radiance_scaling;
 } mer_medium_desc;
+
+enum mer_radiance_scaling { MER_SCALING_REFERENCE = 0, MER_SCALING_PHYSICAL = 1 };
 
 enum mer_boundary { MER_BOUNDARY_INDEX_MATCHED = 0, MER_BOUNDARY_HDIELECTRIC = 1 };
 

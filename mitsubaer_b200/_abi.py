@@ -37,7 +37,8 @@ class MediumDesc(C.Structure):
     _fields_ = [("sigma_a", C.c_float * 3), ("sigma_s", C.c_float * 3), ("stepsize", C.c_float),
                 ("medium_sampling_weight", C.c_float), ("strategy", C.c_int32), ("channel", C.c_int32),
                 ("sampling_density", C.c_float), ("shape_type", C.c_int32), ("shape", C.c_float * 6),
-                ("hg_g", C.c_float), ("density_scale", C.c_float), ("albedo", C.c_float * 3), ("boundary", C.c_int32)]
+                ("hg_g", C.c_float), ("density_scale", C.c_float), ("albedo", C.c_float * 3), ("boundary", C.c_int32),
+                ("radiance_scaling", C.c_int32)]
 
 
 class SamplingRecords(C.Structure):

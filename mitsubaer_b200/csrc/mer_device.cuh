@@ -60,6 +60,7 @@ struct MediumDev {
     float samplingDensity; /* m_samplingDensity */
     int shapeType;
     int boundary; /* MER_BOUNDARY_*: what the container surface does to a ray */
+    int physicalScaling; /* MER_SCALING_PHYSICAL: edges carry (n_start / n_end)^2 instead of the reference's refRatioSq */
     float minExit2; /* computefdfBDPT calls a connection degenerate when it leaves the shape within sqrt(minExit2) of p1 (:891: Epsilon) */
     float shape[6];
     float g;

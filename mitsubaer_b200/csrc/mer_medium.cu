@@ -341,6 +341,7 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
                 "The asymmetry parameter must lie in the interval (-1, 1)!"); /* hg.cpp:50-52 */
     MER_REQUIRE(desc->shape_type == MER_SHAPE_BOX || desc->shape_type == MER_SHAPE_SPHERE, "unknown shape type");
     MER_REQUIRE(desc->boundary == MER_BOUNDARY_INDEX_MATCHED || desc->boundary == MER_BOUNDARY_HDIELECTRIC, "unknown boundary type");
+    MER_REQUIRE(desc->radiance_scaling == MER_SCALING_REFERENCE || desc->radiance_scaling == MER_SCALING_PHYSICAL, "unknown radiance scaling");
     if (desc->strategy == MER_STRATEGY_MAXIMUM)
         return mer::fail(MER_ERR_UNSUPPORTED, "strategy 'maximum' (MaxExpDist) is not carried by this path");
     MER_REQUIRE(desc->strategy >= MER_STRATEGY_BALANCE && desc->strategy <= MER_STRATEGY_MANUAL,
@@ -394,6 +395,7 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
     for (int i = 0; i < 6; i++) D.shape[i] = desc->shape[i];
     D.g = desc->hg_g;
     D.boundary = desc->boundary;
+    D.physicalScaling = desc->radiance_scaling == MER_SCALING_PHYSICAL ? 1 : 0;
     D.minExit2 = MER_EPSILON;
     D.densityScale = desc->density_scale;
     D.invMaxDensity = density ? 1.0f / (desc->density_scale * 1.0f) : 0.0f; /* heterogeneous.cpp:239-242 */

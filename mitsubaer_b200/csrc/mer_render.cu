@@ -443,6 +443,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             }
             float rrs = (float) (1.0 / (double) (L.refStart * L.refStart)); /* :469 */
             rrs *= L.n * L.n;                                                /* :501, refEnd = n(p) */
+            if (M.physicalScaling) rrs = 1.0f / rrs;
             const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
             if (scatter) {
                 st[ST_SCATTER]++;
@@ -685,6 +686,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                 const float inv1 = 1.0f / C.n1;
                 const float phase = hg_eval_dev(M.g, wi, f3(C.dir.x * inv1, C.dir.y * inv1, C.dir.z * inv1));
                 float scale = (float) (1.0 / (double) (C.n1 * C.n1)) * C.exit.nb * C.exit.nb;
+                if (M.physicalScaling) scale = 1.0f / scale;
                 if (refract) {
                     float cosT;
                     const float Fr = fresnel_dielectric_ext(-C.exit.cosI, cosT, C.exit.nb);

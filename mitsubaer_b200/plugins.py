@@ -334,6 +334,10 @@ class HeterogeneousRefractiveMedium:
         if bsdf not in ("null", "hdielectric"):
             raise _abi.MerError(_abi.MER_ERR_INVALID, 'the container\'s bsdf must be "null" or "hdielectric"')
         d.boundary = _abi.BOUNDARY_HDIELECTRIC if bsdf == "hdielectric" else _abi.BOUNDARY_INDEX_MATCHED
+        scaling = str(p.get("radianceScaling", "reference"))  # "reference": refRatioSq as the fork; "physical": its reciprocal
+        if scaling not in ("reference", "physical"):
+            raise _abi.MerError(_abi.MER_ERR_INVALID, 'radianceScaling must be "reference" or "physical"')
+        d.radiance_scaling = 1 if scaling == "physical" else 0
         h = C.c_void_p()
         check(lib.mer_medium_create(C.byref(d), self.rif.handle, self.density.handle if self.density else None,
                                     C.byref(h)))

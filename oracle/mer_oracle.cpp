@@ -1390,6 +1390,7 @@ void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, cons
     cosY = std::abs(cosY);
     const float phase = hg_eval(M.d.hg_g, wi, wo);
     float scale = (float) ((F) (1.0 / (C.n1 * C.n1)) * (F) C.exit.nb * (F) C.exit.nb);
+    if (M.d.radiance_scaling == MER_SCALING_PHYSICAL) scale = 1.0f / scale;
     if (refract) {
         float cosT, Fr = fresnelDielectricExt(-C.exit.cosI, cosT, C.exit.nb);
         scale *= (1.0f - Fr) * (C.exit.nb * C.exit.nb);
@@ -1548,6 +1549,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         F rrs = (F) (1.0 / (refStart * refStart)); /* heterogeneousrefractive.cpp:469, :501 */
         rrs *= refEnd * refEnd;
         float refRatioSq = (float) rrs;
+        if (M.d.radiance_scaling == MER_SCALING_PHYSICAL) refRatioSq = 1.0f / refRatioSq;
         F vlen = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), vinv = (F) 1 / vlen;
 
         if (success) {

@@ -82,6 +82,7 @@ def oracle_medium_desc(props, g=0.9, has_density=False):
     d.density_scale = float(props.get("densityScale", props.get("scale", 1.0))) if has_density else 0.0
     d.albedo[:] = [float(x) for x in spec(props.get("albedo", 0.0))]
     d.boundary = 1 if props.get("bsdf", "null") == "hdielectric" else 0
+    d.radiance_scaling = 1 if props.get("radianceScaling", "reference") == "physical" else 0
     return d
 
 

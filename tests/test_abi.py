@@ -38,7 +38,7 @@ def test_struct_layouts_match_the_header(tmp_path):
     probe = tmp_path / "probe.c"
     fields = {"mer_volume_desc": ["res", "bbox_min", "bbox_max", "has_transform", "world_to_volume"],
               "mer_medium_desc": ["sigma_a", "sigma_s", "stepsize", "medium_sampling_weight", "strategy", "channel",
-                                  "sampling_density", "shape_type", "shape", "hg_g", "density_scale", "albedo", "boundary"],
+                                  "sampling_density", "shape_type", "shape", "hg_g", "density_scale", "albedo", "boundary", "radiance_scaling"],
               "mer_render_desc": ["width", "spp_total", "sample_stride", "seed", "cam_origin", "fov_deg", "filter",
                                   "max_depth", "env_radiance", "has_quad", "quad_radiance", "pool_paths", "steps_per_pass",
                                   "direct_connections", "connection", "frames", "min_bound", "bin_width", "calibrated_transient"],
@@ -72,7 +72,7 @@ def test_struct_layouts_match_the_header(tmp_path):
 
 
 def test_version_and_error_plumbing():
-    assert _abi.lib.mer_abi_version() == 4
+    assert _abi.lib.mer_abi_version() == 5
     assert isinstance(mer.kernel_launch_count(), int)
     with pytest.raises(mer.MerError, match=r"interval \(-1, 1\)"):
         mer.HGPhaseFunction(g=-1.5)

@@ -364,3 +364,23 @@ def test_transient_film_slab_time_of_flight():
     del scene["transient"]
     film, _ = mer.EikonalVolPathIntegrator().render(scene, med)
     assert film.shape == (8, 8, 5) and np.allclose(mer.develop(film), 1.0, atol=1e-4)
+
+
+def test_radiance_scaling_conventions(oracle32):
+    """the fork's refRatioSq (default, parity) against its reciprocal (`radianceScaling="physical"`): only the latter makes a
+    lossless GRIN medium behind a Fresnel boundary a white furnace; both match the oracle"""
+    data, lo, hi = make_field("linear", 32)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    orif = oracle32.rif_create(volume_desc((32,) * 3, lo, hi), data)
+    scene = scene_dict(32, 32, 16, rfilter="box", quad=False)
+    for scaling in ("physical", "reference"):
+        props = medium_props(stepsize=1e-2, sigmaS=2.0, sigmaA=0.0, bsdf="hdielectric", radianceScaling=scaling)
+        med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.3)).configure()
+        rgb = mer.develop(mer.EikonalVolPathIntegrator(rrDepth=1000).render(scene, med)[0])
+        omed = oracle32.medium_create(oracle_medium_desc(props, 0.3), orif)
+        ref = oracle32.film_develop(oracle32.render(omed, oracle_render_desc(scene, rr_depth=1000))[0])
+        assert np.mean(np.abs(rgb - ref) <= 2e-3 * np.maximum(ref, 1.0)) > 0.97
+        if scaling == "physical":
+            assert np.abs(rgb - 1.0).max() < 3e-3
+        else:
+            assert np.abs(rgb - 1.0).max() > 0.1

@@ -322,3 +322,20 @@ def test_oracle_transient_film(oracle32):
         assert np.allclose(rgb.sum(axis=2), steady[..., :3], rtol=1e-5, atol=1e-6)
         assert np.array_equal(trans[..., -2:], steady[..., 3:])
         assert (rgb.sum(axis=(0, 1, 3)) > 0).sum() >= 5  # light arrives spread over several frames
+
+
+def test_oracle_radiance_scaling_conventions(oracle32):
+    """DESIGN.md 6c observation: a lossless GRIN medium in an hdielectric container under a uniform environment is a white
+    furnace.  With the reciprocal of the fork's refRatioSq ("physical") every path's factors telescope to 1 (up to the
+    O(h) gap between the last interior point and the surface); with the fork's own factor they give (n_exit/n_entry)^4."""
+    from common import make_field, medium_props, oracle_medium_desc, oracle_render_desc, scene_dict
+    data, lo, hi = make_field("linear", 32)
+    orif = oracle32.rif_create(volume_desc((32,) * 3, lo, hi), data)
+    out = {}
+    for scaling in ("physical", "reference"):
+        props = medium_props(stepsize=1e-2, sigmaS=2.0, sigmaA=0.0, bsdf="hdielectric", radianceScaling=scaling)
+        med = oracle32.medium_create(oracle_medium_desc(props, 0.3), orif)
+        film, _ = oracle32.render(med, oracle_render_desc(scene_dict(24, 24, 16, rfilter="box", quad=False), rr_depth=1000))
+        out[scaling] = oracle32.film_develop(film)
+    assert np.abs(out["physical"] - 1.0).max() < 3e-3
+    assert np.abs(out["reference"] - 1.0).max() > 0.1
