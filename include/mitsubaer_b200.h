@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 5
+#define MER_ABI_VERSION 6
 
 enum mer_status {
     MER_OK = 0,
@@ -320,7 +320,18 @@ typedef struct mer_render_desc {
     int32_t frames;
     float min_bound, bin_width;
     int32_t calibrated_transient;
+    /* light tracing: 0 = camera path tracer.  1 = width*height*spp_total paths start at the emitter, walk
+     * the medium with importance-mode weights (no refRatioSq, BSDF factor 1: edge.cpp:88-98, hdielectric.cpp:262-268) and
+     * every scattering vertex is connected to the pinhole through the curved connection of makeDirectConnections with
+     * isSensorSample = true (the t = 1 strategy, bdpt_proc.cpp:340-363); the arrival direction picks the pixel
+     * (vertex.cpp:1339-1343), the perspective sensor's importance 1 / (A cos^3) weighs it.  Light that reaches the camera
+     * without scattering in the medium is not sampled by this strategy.  The environment emitter is ignored. */
+    int32_t light_tracing;
+    int32_t emitter_type;   /* MER_EMITTER_QUAD: the quad above, cosine-weighted, both sides; MER_EMITTER_COLLIMATED */
+    float beam_origin[3], beam_direction[3], beam_power[3]; /* <emitter type="collimated">: src/emitters/collimated.cpp:59-110 */
 } mer_render_desc;
+
+enum mer_emitter_type { MER_EMITTER_QUAD = 0, MER_EMITTER_COLLIMATED = 1 };
 
 typedef struct mer_render_stats {
     uint64_t samples;        /* camera samples started */

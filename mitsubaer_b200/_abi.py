@@ -18,6 +18,7 @@ SHAPE_BOX, SHAPE_SPHERE = 0, 1
 STRATEGY_BALANCE, STRATEGY_SINGLE, STRATEGY_MANUAL, STRATEGY_MAXIMUM = 0, 1, 2, 3
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
 BOUNDARY_INDEX_MATCHED, BOUNDARY_HDIELECTRIC = 0, 1
+EMITTER_QUAD, EMITTER_COLLIMATED = 0, 1
 
 
 class MerError(RuntimeError):
@@ -70,7 +71,8 @@ class RenderDesc(C.Structure):
                 ("quad_u", C.c_float * 3), ("quad_v", C.c_float * 3), ("quad_radiance", C.c_float * 3),
                 ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32), ("direct_connections", C.c_int32),
                 ("connection", ConnectionParams), ("frames", C.c_int32), ("min_bound", C.c_float), ("bin_width", C.c_float),
-                ("calibrated_transient", C.c_int32)]
+                ("calibrated_transient", C.c_int32), ("light_tracing", C.c_int32), ("emitter_type", C.c_int32),
+                ("beam_origin", C.c_float * 3), ("beam_direction", C.c_float * 3), ("beam_power", C.c_float * 3)]
 
 
 class RenderStats(C.Structure):

@@ -337,7 +337,7 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
             const float extra_t = -dot3(v, p - p2) / dot3(v, v);
             if (extra_t < 0.0f) return false;
             p = f3(p.x + extra_t * v.x, p.y + extra_t * v.y, p.z + extra_t * v.z);
-            opl += extra_t;
+            opl += extra_t * sqrtf(dot3(v, v)); /* exterior index 1; |v| = 1 after Snell (:989), n_b when the boundary is index-matched */
             break;
         }
         if (signNew != signOld) {

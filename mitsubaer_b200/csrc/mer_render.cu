@@ -110,6 +110,10 @@ struct RenderParams {
     float4 *neeQ0, *neeQ1; /* (p1.xyz, wi.x), (wi.yz, thr.rg) */
     uint4 *neeQ2;          /* thr.b, depth, pixel, sample */
     float *neeQ3;          /* optical path length at the vertex (transient film) */
+    /* light tracing */
+    int lightMode, emitterType;
+    float beamO[3], beamD[3], beamPower[3];
+    float lightScale;      /* 1 / (number of light paths * pixel area on the image plane at unit distance) */
     unsigned *neePerm;     /* requests ordered by expected length (null: queue order) */
     unsigned char *neeKey;
     unsigned *neeHist;     /* NEE_BINS counters, then offsets */
@@ -171,7 +175,7 @@ __device__ __forceinline__ bool intersect_quad(const RenderParams &P, float3 o, 
 
 /* HSmoothDielectric::sample (hdielectric.cpp:244-300) in ERadiance mode with both components: d is the unit
  * direction of travel, N the outward normal, eta the RIF at the hit point.  Returns true for transmission. */
-__device__ __forceinline__ bool hdielectric_sample(float3 d, float3 N, float eta, float u, float3 &dOut, float &weight,
+__device__ __forceinline__ bool hdielectric_sample(float3 d, float3 N, float eta, float u, bool radianceMode, float3 &dOut, float &weight,
                                                    float &etaScale) {
     const float wiN = -dot3(d, N); /* Frame::cosTheta(wi), wi = -d */
     float cosThetaT;
@@ -185,7 +189,7 @@ __device__ __forceinline__ bool hdielectric_sample(float3 d, float3 N, float eta
     const float invEta = __fdiv_rn(1.0f, eta), scale = -(cosThetaT < 0.0f ? invEta : eta);
     dOut = f3(scale * (-d.x - wiN * N.x) + cosThetaT * N.x, scale * (-d.y - wiN * N.y) + cosThetaT * N.y,
               scale * (-d.z - wiN * N.z) + cosThetaT * N.z);
-    const float factor = cosThetaT < 0.0f ? invEta : eta; /* radiance scaling, :262-268 */
+    const float factor = radianceMode ? (cosThetaT < 0.0f ? invEta : eta) : 1.0f; /* radiance scaling only in ERadiance mode, :262-268 */
     weight = __fmul_rn(factor, factor);
     etaScale = cosThetaT < 0.0f ? eta : invEta;
     return true;
@@ -235,6 +239,7 @@ __device__ __forceinline__ void sample_position(const RenderParams &P, unsigned 
 
 __device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, const float rad[3], float alpha,
                                               unsigned *st, float pathLength = INFINITY) {
+    if (P.lightMode) { L.kind = E_NEW; return; } /* a light path that leaves or dies deposits nothing: only its connections do */
     float sx, sy;
     sample_position(P, L.pixel, L.sample, sx, sy);
     film_put(P, sx, sy, rad, alpha, 1.0f, path_frame(P, pathLength), st[ST_NONFINITE]);
@@ -309,6 +314,45 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             L.pixel = pixel;
             L.sample = (unsigned) P.sampleBegin + k * (unsigned) P.sampleStride;
             L.rng.init(P.seed, (unsigned long long) pixel * (unsigned long long) P.sppTotal + L.sample, 0u);
+            if (P.lightMode) {
+                /* ---- emitter-side walk: sample the emitter (its stream is keyed like a camera sample's) */
+                float3 o, d;
+                if (P.emitterType == MER_EMITTER_COLLIMATED) { /* collimated.cpp:59-110: delta position and direction, weight = power */
+                    o = f3(P.beamO[0], P.beamO[1], P.beamO[2]);
+                    d = f3(P.beamD[0], P.beamD[1], P.beamD[2]);
+                    L.thr[0] = P.beamPower[0]; L.thr[1] = P.beamPower[1]; L.thr[2] = P.beamPower[2];
+                } else { /* two-sided diffuse quad: uniform position, cosine-weighted direction => weight Le * pi * Area * 2 */
+                    const float u1 = L.rng.next(), u2 = L.rng.next(), u3 = L.rng.next(), u4 = L.rng.next(), u5 = L.rng.next();
+                    const float3 qu = f3(P.quadU[0], P.quadU[1], P.quadU[2]), qv = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
+                    float3 Nq = f3(qu.y * qv.z - qu.z * qv.y, qu.z * qv.x - qu.x * qv.z, qu.x * qv.y - qu.y * qv.x);
+                    const float area = sqrtf(dot3(Nq, Nq)), side = u3 < 0.5f ? 1.0f : -1.0f;
+                    Nq = f3(Nq.x / area * side, Nq.y / area * side, Nq.z / area * side);
+                    float3 sa, ta;
+                    coordinate_system(Nq, sa, ta);
+                    const float rr = sqrtf(u4), lz = sqrtf(fmaxf(0.0f, 1.0f - u4));
+                    float sp, cp;
+                    sincosf(6.283185307179586f * u5, &sp, &cp);
+                    const float lx = rr * cp, ly = rr * sp;
+                    o = f3(P.quadO[0] + u1 * qu.x + u2 * qv.x, P.quadO[1] + u1 * qu.y + u2 * qv.y, P.quadO[2] + u1 * qu.z + u2 * qv.z);
+                    d = f3(sa.x * lx + ta.x * ly + Nq.x * lz, sa.y * lx + ta.y * ly + Nq.y * lz, sa.z * lx + ta.z * ly + Nq.z * lz);
+                    const float wgt = 6.283185307179586f * area;
+                    L.thr[0] = P.quadLe[0] * wgt; L.thr[1] = P.quadLe[1] * wgt; L.thr[2] = P.quadLe[2] * wgt;
+                }
+                float tBox;
+                if (!intersect_shape(M, o, d, tBox)) continue; /* misses the medium: next path */
+                L.depth = 1;
+                if (P.maxDepth != -1 && L.depth >= P.maxDepth) continue;
+                if (!DIELECTRIC) L.depth = 2;
+                L.etaPath = 1.0f;
+                L.opl = tBox; /* emitterPathlength counts every edge from the emitter, bdpt_proc.cpp:160-165 */
+                L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
+                L.v = d;
+                L.flags = 0;
+                L.n = 1.0f;
+                L.G = f3(0.f, 0.f, 0.f);
+                L.kind = K_ENTRY;
+                continue;
+            }
             const unsigned py = pixel / (unsigned) P.W;
             int x = (int) (pixel - py * (unsigned) P.W), y = (int) py;
             float sx = (float) x + L.rng.next(), sy = (float) y + L.rng.next();
@@ -364,7 +408,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             L.rng.next(); /* the BSDF sample is a Point2 */
             float3 dOut;
             float w, es;
-            const bool transmitted = hdielectric_sample(L.v, N, L.n, u, dOut, w, es);
+            const bool transmitted = hdielectric_sample(L.v, N, L.n, u, !P.lightMode, dOut, w, es);
 #pragma unroll
             for (int c = 0; c < 3; c++) L.thr[c] *= w;
             L.etaPath *= es;
@@ -444,6 +488,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             float rrs = (float) (1.0 / (double) (L.refStart * L.refStart)); /* :469 */
             rrs *= L.n * L.n;                                                /* :501, refEnd = n(p) */
             if (M.physicalScaling) rrs = 1.0f / rrs;
+            if (P.lightMode) rrs = 1.0f; /* weight[EImportance] carries no refRatioSq, edge.cpp:96-98 */
             const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
             if (scatter) {
                 st[ST_SCATTER]++;
@@ -600,7 +645,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
 
 /* A warp of k_nee costs what its longest connection costs, and the cost is roughly the number of steps from the vertex to
  * the container surface.  So the requests are counting-sorted by that distance (towards the centre of the quad, 64 bins,
- * longest first) before the solver runs: three trivial kernels in front of one that costs 1e3-1e5 steps per thread. */
+ * or the pinhole; longest first) before the solver runs: three trivial kernels in front of one that costs 1e3-1e5 steps per thread. */
 __global__ void k_nee_keys(const __grid_constant__ RenderParams P, unsigned nReq) {
     __shared__ unsigned hist[NEE_BINS];
     if (threadIdx.x < NEE_BINS) hist[threadIdx.x] = 0u;
@@ -609,8 +654,9 @@ __global__ void k_nee_keys(const __grid_constant__ RenderParams P, unsigned nReq
     if (i < nReq) {
         const float4 a = P.neeQ0[i];
         const float3 p1 = f3(a.x, a.y, a.z);
-        float3 d = f3(P.quadO[0] + 0.5f * (P.quadU[0] + P.quadV[0]) - p1.x, P.quadO[1] + 0.5f * (P.quadU[1] + P.quadV[1]) - p1.y,
-                      P.quadO[2] + 0.5f * (P.quadU[2] + P.quadV[2]) - p1.z);
+        float3 d = P.lightMode ? f3(P.camO[0] - p1.x, P.camO[1] - p1.y, P.camO[2] - p1.z)
+                               : f3(P.quadO[0] + 0.5f * (P.quadU[0] + P.quadV[0]) - p1.x, P.quadO[1] + 0.5f * (P.quadU[1] + P.quadV[1]) - p1.y,
+                                    P.quadO[2] + 0.5f * (P.quadU[2] + P.quadV[2]) - p1.z);
         const float dl = 1.0f / sqrtf(dot3(d, d));
         d = f3(d.x * dl, d.y * dl, d.z * dl);
         const float te = exit_distance(P.M, p1, d);
@@ -663,11 +709,17 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         const float oplVertex = P.frames > 1 ? P.neeQ3[i] : 0.0f;
         PathRng nrng;
         nrng.init(P.seed ^ MER_NEE_SALT, (unsigned long long) pixel * (unsigned long long) P.sppTotal + sample, depth * 256u);
-        const float u = nrng.next(), w = nrng.next();
-        const float3 qu = f3(P.quadU[0], P.quadU[1], P.quadU[2]), qv = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
-        float3 Nq = f3(qu.y * qv.z - qu.z * qv.y, qu.z * qv.x - qu.x * qv.z, qu.x * qv.y - qu.y * qv.x);
-        const float area = sqrtf(dot3(Nq, Nq));
-        const float3 y = f3(P.quadO[0] + u * qu.x + w * qv.x, P.quadO[1] + u * qu.y + w * qv.y, P.quadO[2] + u * qu.z + w * qv.z);
+        float3 y, Nq = f3(0.f, 0.f, 1.f);
+        float area = 1.0f;
+        if (P.lightMode) { /* t = 1: the target is the pinhole */
+            y = f3(P.camO[0], P.camO[1], P.camO[2]);
+        } else {
+            const float u = nrng.next(), w = nrng.next();
+            const float3 qu = f3(P.quadU[0], P.quadU[1], P.quadU[2]), qv = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
+            Nq = f3(qu.y * qv.z - qu.z * qv.y, qu.z * qv.x - qu.x * qv.z, qu.x * qv.y - qu.y * qv.x);
+            area = sqrtf(dot3(Nq, Nq));
+            y = f3(P.quadO[0] + u * qu.x + w * qv.x, P.quadO[1] + u * qu.y + w * qv.y, P.quadO[2] + u * qu.z + w * qv.z);
+        }
         float3 ds = f3(y.x - p1.x, y.y - p1.y, y.z - p1.z);
         const float dl = 1.0f / sqrtf(dot3(ds, ds));
         ds = f3(ds.x * dl, ds.y * dl, ds.z * dl);
@@ -681,7 +733,39 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         if (ok) {
             const float spread = merc::connection_spread(C.J, C.xnorm); /* the Jacobian of the solver's last accepted evaluation */
             ok = spread > 0.0f;
-            if (ok) {
+            if (ok && P.lightMode) {
+                /* C.rev is the direction in which the camera sees the vertex: pixel by the inverse of sampleRay's mapping,
+                 * importance of the perspective sensor 1 / (A cos^3 theta) (src/sensors/perspective.cpp importance()),
+                 * irradiance on the plane perpendicular to the arriving ray = intensity / spread (flux is conserved: no n^2) */
+                const float3 cl = f3(P.camLeft[0], P.camLeft[1], P.camLeft[2]), cu = f3(P.camUp[0], P.camUp[1], P.camUp[2]),
+                             cd = f3(P.camDir[0], P.camDir[1], P.camDir[2]);
+                const float zc = dot3(C.rev, cd);
+                ok = zc > 0.0f;
+                if (ok) {
+                    const float cx = dot3(C.rev, cl) / zc, cy = dot3(C.rev, cu) / zc;
+                    const float sx = 0.5f * (float) P.W * (1.0f - cx / P.tanHalf), sy = 0.5f * (float) P.H * (1.0f - cy * P.aspect / P.tanHalf);
+                    ok = sx >= 0.0f && sx < (float) P.W && sy >= 0.0f && sy < (float) P.H;
+                    if (ok) {
+                        const float inv1 = 1.0f / C.n1;
+                        const float phase = hg_eval_dev(M.g, wi, f3(C.dir.x * inv1, C.dir.y * inv1, C.dir.z * inv1));
+                        float bf = 1.0f;
+                        if (refract) {
+                            float cosT;
+                            bf = 1.0f - fresnel_dielectric_ext(-C.exit.cosI, cosT, C.exit.nb);
+                        }
+                        const float g = P.lightScale / (spread * zc * zc * zc);
+                        float rad[3];
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const float T = fastexp_dev(M.hasGrid ? -C.exit.tau : M.sigmaT[k] * -C.dist);
+                            rad[k] = thr[k] * phase * T * C.weight * bf * g;
+                        }
+                        /* bdpt_proc.cpp:352-357: the sensor connection's length is left out of a calibrated transient */
+                        const int frame = path_frame(P, oplVertex + (P.calibrated ? 0.0f : C.opl));
+                        if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, nonfinite);
+                    }
+                }
+            } else if (ok) {
                 const float cosY = fabsf(dot3(C.rev, Nq)) / area;
                 const float inv1 = 1.0f / C.n1;
                 const float phase = hg_eval_dev(M.g, wi, f3(C.dir.x * inv1, C.dir.y * inv1, C.dir.z * inv1));
@@ -717,6 +801,15 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         if (lane == 0 && v) atomicAdd(P.stats + slots[k], v);
     }
     if (nonfinite) atomicAdd(P.stats + ST_NONFINITE, (unsigned long long) nonfinite);
+}
+
+/* a light-traced film has no camera samples: every pixel gets this GPU's share of a unit weight (and alpha), so that
+ * develop() returns the sum of the splats, which are already normalised by the number of light paths */
+__global__ void k_film_unit_weight(size_t nPixels, int channels, float share, float *__restrict__ film) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nPixels; i += (size_t) gridDim.x * blockDim.x) {
+        film[i * channels + channels - 2] += share;
+        film[i * channels + channels - 1] += share;
+    }
 }
 
 /* HDRFilm::develop: ESpectrumAlphaWeight -> RGB */
@@ -786,7 +879,13 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     MER_REQUIRE(r->filter == MER_FILTER_BOX || r->filter == MER_FILTER_GAUSSIAN, "unknown reconstruction filter");
     if (m->dev.aggressive)
         return mer::fail(MER_ERR_UNSUPPORTED, "aggressivetracing is only available in mer_medium_sample_distance_batch");
-    if (r->direct_connections) {
+    if (r->light_tracing) {
+        MER_REQUIRE(r->emitter_type == MER_EMITTER_QUAD || r->emitter_type == MER_EMITTER_COLLIMATED, "unknown emitter type");
+        MER_REQUIRE(r->emitter_type != MER_EMITTER_QUAD || r->has_quad, "light tracing from the quad emitter needs the quad");
+        if (m->rif->mode != MER_RIF_TRICUBIC)
+            return mer::fail(MER_ERR_UNSUPPORTED, "light tracing needs the tricubic RIF mode (the sensor connection differentiates the spline twice)");
+    }
+    if (r->direct_connections && !r->light_tracing) {
         MER_REQUIRE(r->has_quad, "direct_connections needs the quad emitter");
         if (m->rif->mode != MER_RIF_TRICUBIC)
             return mer::fail(MER_ERR_UNSUPPORTED, "direct_connections needs the tricubic RIF mode (the solver differentiates the spline twice)");
@@ -820,7 +919,19 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.binWidth = r->bin_width;
     P.calibrated = r->calibrated_transient ? 1 : 0;
     if (P.frames > 1) MER_REQUIRE(r->bin_width > 0.0f, "transient film: bin_width must be positive");
-    P.nee = r->direct_connections ? 1 : 0;
+    P.nee = (r->direct_connections || r->light_tracing) ? 1 : 0;
+    P.lightMode = r->light_tracing ? 1 : 0;
+    P.emitterType = r->emitter_type;
+    {
+        float dl = 0.0f;
+        for (int i = 0; i < 3; i++) { P.beamO[i] = r->beam_origin[i]; P.beamPower[i] = r->beam_power[i]; dl += r->beam_direction[i] * r->beam_direction[i]; }
+        dl = dl > 0.0f ? 1.0f / std::sqrt(dl) : 0.0f;
+        for (int i = 0; i < 3; i++) P.beamD[i] = r->beam_direction[i] * dl;
+        if (P.lightMode && P.emitterType == MER_EMITTER_COLLIMATED) MER_REQUIRE(dl > 0.0f, "collimated emitter: zero direction");
+        const double aImg = (2.0 * P.tanHalf) * (2.0 * P.tanHalf / P.aspect); /* image plane at unit distance */
+        const double nPaths = (double) r->width * r->height * (double) r->spp_total;
+        P.lightScale = (float) (1.0 / (nPaths * aImg / ((double) r->width * r->height)));
+    }
     /* the reference drops connections that leave the shape within sqrt(Epsilon) = 0.01 of p1; for next-event estimation that
      * would discard the brightest vertices (those next to the surface facing the light), so only exact degeneracy is dropped */
     P.M.minExit2 = 1e-10f;
@@ -935,6 +1046,12 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
             }
         }
         if (nLive == 0 && started >= P.totalSamples) break;
+    }
+    if (P.lightMode) {
+        const size_t npx = (size_t) r->width * r->height;
+        MER_LAUNCH(k_film_unit_weight, (unsigned) std::min<size_t>(mer_blocks(npx, 256), 148u * 8u), 256, 0, stream, npx, P.channels,
+                   (float) P.sppLocal / (float) r->spp_total, film_dev);
+        launches++;
     }
     MER_CUDA(cudaEventRecord(S.ev1, stream));
     MER_CUDA(cudaEventSynchronize(S.ev1));

@@ -473,6 +473,7 @@ class EikonalVolPathIntegrator:
         self.poolPaths = int(props.get("poolPaths", 0))
         self.stepsPerPass = int(props.get("stepsPerPass", 0))
         self.directConnections = bool(props.get("directConnections", False))
+        self.lightTracing = bool(props.get("lightTracing", False))  # emitter-side walk + t = 1 sensor connections
         self.connectionStart = str(props.get("connectionStart", "straight"))
         if self.connectionStart not in ("straight", "random"):
             raise _abi.MerError(_abi.MER_ERR_INVALID, 'connectionStart must be "straight" or "random"')
@@ -509,6 +510,15 @@ class EikonalVolPathIntegrator:
         r.connection.boundary_precision = int(mp.get("boundaryprecision", 3))
         r.connection.max_iterations = int(mp.get("ceresmaxiterations", 20))
         r.connection.start_mode = 1 if self.connectionStart == "random" else 2
+        r.light_tracing = 1 if self.lightTracing else 0
+        em = scene.get("emitter")  # light tracing: dict(type="collimated", origin, direction, power) or the quad (default)
+        if em and em.get("type", "quad") == "collimated":
+            r.emitter_type = _abi.EMITTER_COLLIMATED
+            r.beam_origin[:] = [float(x) for x in em.get("origin", (0, 0, 0))]
+            r.beam_direction[:] = [float(x) for x in em.get("direction", (0, 0, 1))]
+            r.beam_power[:] = [float(x) for x in _spectrum(em.get("power", 1.0))]
+        elif em and em.get("type", "quad") != "quad":
+            raise _abi.MerError(_abi.MER_ERR_INVALID, 'emitter type must be "quad" or "collimated"')
         tr = scene.get("transient")  # <film>: decomposition="transient", minBound, maxBound, binWidth, calibratedTransient
         if tr:
             width = float(tr.get("binWidth", 1.0))

@@ -1010,7 +1010,7 @@ bool computePathLengths(const Medium<F> &M, const F *p1, const F *p2, const F *d
             F extra_t = -Medium<F>::dot(v, d) / Medium<F>::dot(v, v);
             if (extra_t < 0) return false;
             for (int i = 0; i < 3; i++) p[i] += extra_t * v[i];
-            opl += extra_t;
+            opl += extra_t * std::sqrt(Medium<F>::dot(v, v)); /* exterior index 1; |v| = 1 after Snell (:989), n_b when index-matched */
             break;
         }
         if (signNew != signOld) {
@@ -1301,7 +1301,8 @@ inline bool intersectQuad(const mer_render_desc &r, const float o[3], const floa
  * ------------------------------------------------------------------------------------------ */
 /* HSmoothDielectric::sample (src/bsdfs/hdielectric.cpp:244-300), ERadiance mode, both components enabled.
  * d: unit direction of travel, N: outward normal, eta = RIF at the hit point.  Returns true for transmission. */
-inline bool hdielectricSample(const float d[3], const float N[3], float eta, float u, float dOut[3], float &weight, float &etaScale) {
+inline bool hdielectricSample(const float d[3], const float N[3], float eta, float u, float dOut[3], float &weight, float &etaScale,
+                              bool radianceMode = true) {
     float wiN = -(d[0] * N[0] + d[1] * N[1] + d[2] * N[2]); /* Frame::cosTheta(wi), wi = -d */
     float cosThetaT, F = fresnelDielectricExt(wiN, cosThetaT, eta);
     if (u <= F) { /* reflect(wi) = (-wi.x, -wi.y, wi.z) */
@@ -1315,7 +1316,7 @@ inline bool hdielectricSample(const float d[3], const float N[3], float eta, flo
         float wiT = -d[i] - wiN * N[i];
         dOut[i] = scale * wiT + cosThetaT * N[i];
     }
-    float factor = cosThetaT < 0 ? invEta : eta; /* radiance scaling, :262-268 */
+    float factor = radianceMode ? (cosThetaT < 0 ? invEta : eta) : 1.0f; /* radiance scaling only in ERadiance mode, :262-268 */
     weight = factor * factor;
     etaScale = cosThetaT < 0 ? eta : invEta;
     return true;
@@ -1404,21 +1405,98 @@ void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, cons
     L.add(pathLength + (float) C.opticalDist, rad); /* the connection's optical length: curved part + exterior segment */
 }
 
+/* light tracing: where the t = 1 connections of an emitter-side walk are splatted */
+struct LightCtx {
+    float *film;
+    int W, H, channels;
+    const Filter *flt;
+    const Camera *cam;
+    float lightScale; /* 1 / (number of light paths * pixel area on the image plane at unit distance) */
+    float thr0[3];    /* emitted weight of this path */
+};
+
+/* t = 1 strategy (bdpt_proc.cpp:340-363): connect a scattering vertex of a light path to the pinhole along the curved
+ * connection (isSensorSample = true); the arrival direction picks the pixel (vertex.cpp:1339-1343), the perspective
+ * sensor's importance 1 / (A cos^3) weighs it; the irradiance on the plane perpendicular to the arriving ray is
+ * intensity / spread (flux is conserved along the connection: no n^2 factors in importance mode). */
+template <typename F>
+void sensorConnection(const Medium<F> &M, const mer_render_desc &R, const LightCtx &LC, const F *p1, const float wi[3], const float thr[3],
+                      int depth, uint64_t sampleId, float pathLength, Stats &st) {
+    PhiloxStream nrng;
+    nrng.init(R.seed ^ kNeeSalt, sampleId);
+    nrng.ctr[2] = (uint32_t) depth * 64u;
+    const Camera &cam = *LC.cam;
+    F y[3], dseed[3];
+    float dl = 0;
+    for (int i = 0; i < 3; i++) { y[i] = (F) cam.o[i]; dseed[i] = (F) (cam.o[i] - (float) p1[i]); dl += (float) dseed[i] * (float) dseed[i]; }
+    dl = 1.0f / std::sqrt(dl);
+    for (int i = 0; i < 3; i++) dseed[i] = (F) ((float) dseed[i] * dl);
+    const bool refract = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
+    const float rrweight = R.connection.rrweight > 0 ? R.connection.rrweight : 1e-2f;
+    const int maxIt = R.connection.max_iterations > 0 ? R.connection.max_iterations : 20;
+    ConnectionResult<F> C;
+    long steps = 0;
+    connect<F>(M, p1, y, dseed, true, rrweight, maxIt, nrng, C, refract, &steps, R.connection.start_mode != MER_START_RANDOM);
+    st.connections++;
+    st.connSteps += steps;
+    if (!C.success || !C.exit.exited || C.exit.tir) { st.connFailed++; return; }
+    const F *m = C.J;
+    const F cof[9] = {m[4] * m[8] - m[5] * m[7], m[5] * m[6] - m[3] * m[8], m[3] * m[7] - m[4] * m[6],
+                      m[2] * m[7] - m[1] * m[8], m[0] * m[8] - m[2] * m[6], m[1] * m[6] - m[0] * m[7],
+                      m[1] * m[5] - m[2] * m[4], m[2] * m[3] - m[0] * m[5], m[0] * m[4] - m[1] * m[3]};
+    F ss = 0;
+    for (int i = 0; i < 9; i++) ss += cof[i] * cof[i];
+    const float n1 = (float) C.n1, spread = (float) (C.xnorm * C.xnorm) * (float) std::sqrt(ss);
+    if (!(spread > 0)) { st.connFailed++; return; }
+    float rev[3] = {(float) C.revDirToP1[0], (float) C.revDirToP1[1], (float) C.revDirToP1[2]};
+    const float zc = rev[0] * cam.dir[0] + rev[1] * cam.dir[1] + rev[2] * cam.dir[2];
+    if (!(zc > 0)) { st.connFailed++; return; }
+    const float cx = (rev[0] * cam.left[0] + rev[1] * cam.left[1] + rev[2] * cam.left[2]) / zc,
+                cy = (rev[0] * cam.up[0] + rev[1] * cam.up[1] + rev[2] * cam.up[2]) / zc;
+    const float sx = 0.5f * (float) LC.W * (1.0f - cx / cam.tanHalf), sy = 0.5f * (float) LC.H * (1.0f - cy * cam.aspect / cam.tanHalf);
+    if (!(sx >= 0 && sx < (float) LC.W && sy >= 0 && sy < (float) LC.H)) { st.connFailed++; return; }
+    float wo[3];
+    for (int i = 0; i < 3; i++) wo[i] = (float) C.dirToP2[i] / n1;
+    const float phase = hg_eval(M.d.hg_g, wi, wo);
+    float bf = 1.0f;
+    if (refract) {
+        float cosT;
+        bf = 1.0f - fresnelDielectricExt(-C.exit.cosI, cosT, C.exit.nb);
+    }
+    const float g = LC.lightScale / (spread * zc * zc * zc);
+    const int frames = R.frames > 1 ? R.frames : 1;
+    std::vector<float> value(LC.channels, 0.0f);
+    const Radiance acc = {value.data(), frames, R.min_bound, R.bin_width};
+    float rad[3];
+    for (int c = 0; c < 3; c++) {
+        float T = (float) std::exp((double) (M.density ? -C.exit.tau : M.sigmaT[c] * (float) (-C.dist)));
+        rad[c] = thr[c] * phase * T * (float) C.weight * bf * g;
+    }
+    /* bdpt_proc.cpp:352-357: the sensor connection's length is left out of a calibrated transient */
+    acc.add(pathLength + (R.calibrated_transient ? 0.0f : (float) C.opticalDist), rad);
+    if (!film_put(LC.film, LC.W, LC.H, *LC.flt, sx, sy, value.data(), LC.channels)) st.nonfinite++;
+}
+
 template <typename F>
 void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const float dcam[3], PhiloxStream &rng,
-        float *Lout, float &alpha, Stats &st, uint64_t sampleId = 0) {
+        float *Lout, float &alpha, Stats &st, uint64_t sampleId = 0, const LightCtx *LC = nullptr) {
+    /* LC != nullptr: the same walk started at the emitter (o, dcam = emitted ray) with importance-mode weights; nothing is
+     * returned, the scattering vertices splat their sensor connections */
+    const bool light = LC != nullptr;
     const Radiance L = {Lout, R.frames > 1 ? R.frames : 1, R.min_bound, R.bin_width};
-    for (int i = 0; i < 3 * L.frames; i++) Lout[i] = 0;
+    if (!light) for (int i = 0; i < 3 * L.frames; i++) Lout[i] = 0;
     alpha = 0;
     F opl = 0; /* optical path length from the camera (or from the first surface: calibrated_transient) */
     float thr[3] = {1, 1, 1}, etaPath = 1.0f;
+    if (light) for (int i = 0; i < 3; i++) thr[i] = LC->thr0[i];
     int depth = 1;
     const bool dielectric = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
     const bool nee = R.direct_connections != 0 && R.has_quad;
     bool covered = false; /* the quad's light along the current edge chain was already estimated by a direct connection */
     float tBox, tQuad;
     bool hitBox = intersectShape(M.d, o, dcam, tBox);
-    bool hitQuad = intersectQuad(R, o, dcam, tQuad);
+    bool hitQuad = !light && intersectQuad(R, o, dcam, tQuad);
+    if (light && !hitBox) return;
     if (hitQuad && (!hitBox || tQuad < tBox)) {
         L.add(R.calibrated_transient ? 0.0f : tQuad, R.quad_radiance);
         alpha = 1;
@@ -1428,7 +1506,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         L.add(std::numeric_limits<float>::infinity(), R.env_radiance);
         return;
     }
-    if (!R.calibrated_transient) opl = (F) tBox;
+    if (light || !R.calibrated_transient) opl = (F) tBox; /* emitterPathlength counts every edge, bdpt_proc.cpp:160-165 */
     alpha = 1;
     if (R.max_depth != -1 && depth >= R.max_depth) return; /* volpath.cpp:200-201 */
     F p[3], dir[3];
@@ -1436,6 +1514,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
 
     /* straight escape from point q in direction e: emitters are gathered by hitting them */
     auto escape = [&](const float q[3], const float e[3]) {
+        if (light) return; /* a light path that leaves deposits nothing */
         float tq;
         const bool hitsQuad = intersectQuad(R, q, e, tq);
         if (hitsQuad && covered) return;
@@ -1465,7 +1544,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         float eta = (float) M.rif->value(p); /* hdielectric.cpp:115-118: m_shape->getInteriorMedium()->getRIF(p) */
         float u = rng.next();
         rng.next(); /* the BSDF sample is a Point2 (rRec.nextSample2D()) */
-        bool transmitted = hdielectricSample(df, N, eta, u, dOut, w, es);
+        bool transmitted = hdielectricSample(df, N, eta, u, dOut, w, es, !light);
         for (int i = 0; i < 3; i++) thr[i] *= w;
         etaPath *= es;
         for (int i = 0; i < 3; i++) dir[i] = (F) dOut[i];
@@ -1550,6 +1629,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         rrs *= refEnd * refEnd;
         float refRatioSq = (float) rrs;
         if (M.d.radiance_scaling == MER_SCALING_PHYSICAL) refRatioSq = 1.0f / refRatioSq;
+        if (light) refRatioSq = 1.0f; /* weight[EImportance] carries no refRatioSq, edge.cpp:96-98 */
         F vlen = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), vinv = (F) 1 / vlen;
 
         if (success) {
@@ -1558,7 +1638,9 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             for (int i = 0; i < 3; i++) thr[i] *= edge[i] * refRatioSq;
             /* phase sampling: wi = normalize(-mRec.d) */
             float wi[3] = {(float) (-v[0] * vinv), (float) (-v[1] * vinv), (float) (-v[2] * vinv)}, wo[3];
-            if (nee) {
+            if (light) {
+                if (R.max_depth == -1 || depth + 1 < R.max_depth) sensorConnection<F>(M, R, *LC, p, wi, thr, depth, sampleId, (float) opl, st);
+            } else if (nee) {
                 covered = true;
                 if (R.max_depth == -1 || depth + 1 < R.max_depth) directLight<F>(M, R, p, wi, thr, depth, sampleId, L, (float) opl, st);
             }
@@ -1597,6 +1679,7 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
     cam.configure(&R);
     const int bx = (W + B - 1) / B, by = (H + B - 1) / B;
     const int channels = 3 * (R.frames > 1 ? R.frames : 1) + 2; /* bdpt_wr.cpp:52-56 */
+    const float lightScale = (float) (1.0 / ((double) W * H * (double) R.spp_total * ((2.0 * cam.tanHalf) * (2.0 * cam.tanHalf / cam.aspect)) / ((double) W * H)));
     Stats total;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -1613,6 +1696,34 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
                     for (int s = R.sample_begin; s < R.spp_total; s += std::max(R.sample_stride, 1)) {
                         PhiloxStream rng;
                         rng.init(R.seed, ((uint64_t) y * W + x) * (uint64_t) R.spp_total + (uint64_t) s);
+                        if (R.light_tracing) { /* one emitter-side walk per (pixel, sample) id; the id only keys the stream */
+                            LightCtx LC = {local.data(), W, H, channels, &flt, &cam, lightScale, {0, 0, 0}};
+                            float eo[3], ed[3], alpha;
+                            if (R.emitter_type == MER_EMITTER_COLLIMATED) { /* collimated.cpp:59-110 */
+                                float dl = 0;
+                                for (int i = 0; i < 3; i++) dl += R.beam_direction[i] * R.beam_direction[i];
+                                dl = 1.0f / std::sqrt(dl);
+                                for (int i = 0; i < 3; i++) { eo[i] = R.beam_origin[i]; ed[i] = R.beam_direction[i] * dl; LC.thr0[i] = R.beam_power[i]; }
+                            } else { /* two-sided diffuse quad: uniform position, cosine-weighted direction */
+                                const float u1 = rng.next(), u2 = rng.next(), u3 = rng.next(), u4 = rng.next(), u5 = rng.next();
+                                const float *qu = R.quad_u, *qv = R.quad_v;
+                                float Nq[3] = {qu[1] * qv[2] - qu[2] * qv[1], qu[2] * qv[0] - qu[0] * qv[2], qu[0] * qv[1] - qu[1] * qv[0]};
+                                const float area = std::sqrt(Nq[0] * Nq[0] + Nq[1] * Nq[1] + Nq[2] * Nq[2]), side = u3 < 0.5f ? 1.0f : -1.0f;
+                                for (int i = 0; i < 3; i++) Nq[i] = Nq[i] / area * side;
+                                float sa[3], ta[3];
+                                coordinateSystem(Nq, sa, ta);
+                                const float rr = std::sqrt(u4), lz = std::sqrt(std::max(0.0f, 1.0f - u4)), ph = 6.283185307179586f * u5;
+                                const float lx = rr * cosf(ph), ly = rr * sinf(ph), wgt = 6.283185307179586f * area;
+                                for (int i = 0; i < 3; i++) {
+                                    eo[i] = R.quad_origin[i] + u1 * qu[i] + u2 * qv[i];
+                                    ed[i] = sa[i] * lx + ta[i] * ly + Nq[i] * lz;
+                                    LC.thr0[i] = R.quad_radiance[i] * wgt;
+                                }
+                            }
+                            Li<F>(Mr, R, eo, ed, rng, nullptr, alpha, st, ((uint64_t) y * W + x) * (uint64_t) R.spp_total + (uint64_t) s, &LC);
+                            st.samples++;
+                            continue;
+                        }
                         float sx = x + rng.next(), sy = y + rng.next();
                         float d[3], alpha;
                         cam.sampleRay(sx, sy, d);
@@ -1630,6 +1741,12 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
             total.nullColl += st.nullColl; total.exits += st.exits; total.nonfinite += st.nonfinite;
             total.connections += st.connections; total.connFailed += st.connFailed; total.connSteps += st.connSteps;
         }
+    }
+    if (R.light_tracing) { /* no camera samples: every pixel gets this shard's share of a unit weight */
+        const int stride = std::max(R.sample_stride, 1);
+        const int sppLocal = R.sample_begin < R.spp_total ? (R.spp_total - R.sample_begin + stride - 1) / stride : 0;
+        const float share = (float) sppLocal / (float) R.spp_total;
+        for (size_t i = 0; i < (size_t) W * H; i++) { film[i * channels + channels - 2] += share; film[i * channels + channels - 1] += share; }
     }
     if (out) {
         memset(out, 0, sizeof(*out));

@@ -95,7 +95,7 @@ def scene_dict(width=64, height=64, spp=16, rfilter="gaussian", quad=True, seed=
 
 
 def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_stride=1, direct_connections=False, props=None,
-                       start="straight"):
+                       start="straight", light_tracing=False):
     from oracle.oracle import RenderDesc
     r = RenderDesc()
     r.width, r.height, r.spp_total = scene["width"], scene["height"], scene["sampleCount"]
@@ -117,12 +117,20 @@ def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_s
         r.quad_v[:] = q["v"]
         r.quad_radiance[:] = q["radiance"]
     r.direct_connections = 1 if direct_connections else 0
+    r.light_tracing = 1 if light_tracing else 0
     props = props or {}
     r.connection.tol2 = float(props.get("tol2", 1e-6))
     r.connection.rrweight = float(props.get("rrweight", 1e-2))
     r.connection.boundary_precision = int(props.get("boundaryprecision", 3))
     r.connection.max_iterations = int(props.get("ceresmaxiterations", 20))
     r.connection.start_mode = 1 if start == "random" else 2
+    em = scene.get("emitter")
+    if em and em.get("type", "quad") == "collimated":
+        r.emitter_type = 1
+        r.beam_origin[:] = em.get("origin", (0, 0, 0))
+        r.beam_direction[:] = em.get("direction", (0, 0, 1))
+        pw = np.asarray(em.get("power", 1.0), np.float32).reshape(-1)
+        r.beam_power[:] = [float(x) for x in (np.repeat(pw, 3) if pw.size == 1 else pw)]
     tr = scene.get("transient")  # dict(minBound, maxBound, binWidth[, calibrated]) as on <film>
     if tr:
         r.frames = int(np.ceil((tr["maxBound"] - tr["minBound"]) / tr["binWidth"]))

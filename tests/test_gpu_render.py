@@ -384,3 +384,97 @@ def test_radiance_scaling_conventions(oracle32):
             assert np.abs(rgb - 1.0).max() < 3e-3
         else:
             assert np.abs(rgb - 1.0).max() > 0.1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# next-row 2, walk half: light tracing = emitter-side walk + t = 1 sensor connections
+
+def _hidden_quad_scene(w, h, spp, seed=20201201, **kw):
+    """fov 30 deg: the quad above the box is outside the camera's view, so every bit of light scatters in the medium first
+    (light tracing towards a pinhole cannot sample an emitter that is seen directly)"""
+    scene = scene_dict(w, h, spp, rfilter="box", seed=seed)
+    scene.update(fov=30.0, envRadiance=0.0, **kw)
+    return scene
+
+
+@pytest.mark.parametrize("kind,bsdf,emitter", [("linear", "hdielectric", "quad"), ("const", "null", "collimated")])
+def test_light_tracing_matches_oracle(oracle32, kind, bsdf, emitter):
+    med, rif, props, data, lo, hi = _nee_medium(kind, 1e-2, bsdf)
+    omed = oracle32.medium_create(oracle_medium_desc(props, 0.5), oracle32.rif_create(volume_desc((32,) * 3, lo, hi), data))
+    scene = _hidden_quad_scene(32, 32, 8, transient=dict(minBound=2.0, maxBound=18.0, binWidth=0.5))
+    if emitter == "collimated":
+        scene["emitter"] = dict(type="collimated", origin=(0.2, 0.1, -3.0), direction=(0.0, 0.0, 1.0), power=(30.0, 20.0, 10.0))
+    # every path of a collimated beam starts on the same ray and lands on the same few pixels, so the handful of walks that
+    # FP32 rounding sends different ways (0.06 % of them) would dominate a multiple-scattering comparison: single scattering there
+    md = 4 if emitter == "collimated" else -1
+    film, st = mer.EikonalVolPathIntegrator(maxDepth=md, rrDepth=5, lightTracing=True, poolPaths=1024, stepsPerPass=128).render(scene, med)
+    ofilm, ost = oracle32.render(omed, oracle_render_desc(scene, max_depth=md, light_tracing=True, props=props))
+    assert film.shape == ofilm.shape == (32, 32, 3 * 32 + 2)
+    assert st["samples"] == ost.samples == 32 * 32 * 8 and st["connections"] > 3000
+    assert abs(st["connections"] - ost.connections) <= 0.01 * ost.connections
+    assert np.allclose(film[..., -1], 1.0) and np.allclose(ofilm[..., -1], 1.0)  # unit weight: develop() returns the splats' sum
+    a, b = film[..., :-2].reshape(32, 32, 32, 3), ofilm[..., :-2].reshape(32, 32, 32, 3)
+    assert abs(a.sum() / b.sum() - 1) < 5e-3
+    # time profile and image (summed over frames) of the same light paths
+    assert np.allclose(a.sum(axis=(0, 1, 3)), b.sum(axis=(0, 1, 3)), rtol=0.03, atol=3e-3 * b.sum(axis=(0, 1, 3)).max())
+    ia, ib = a.sum(axis=(2, 3)), b.sum(axis=(2, 3))
+    assert np.mean(np.abs(ia - ib) <= 0.02 * ib + 1e-3 * ib.max()) > 0.95
+
+
+@pytest.mark.parametrize("kind,bsdf,scaling", [("const", "null", "reference"), ("linear", "hdielectric", "physical")])
+def test_light_tracing_agrees_with_camera_tracer(kind, bsdf, scaling):
+    """the two estimators of the same image: camera walk (+ direct connections to the quad) and emitter walk (+ sensor
+    connections).  Importance transport carries no index factors, so it is the physically scaled camera estimator
+    (radianceScaling="physical") that it has to agree with once the index varies."""
+    if kind == "const":
+        lo, hi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, (32,) * 3)
+        data = np.full((32,) * 3, 1.5, np.float32)
+    else:
+        data, lo, hi = make_field(kind, 32)
+    props = medium_props(stepsize=5e-3, sigmaS=1.5, sigmaA=0.5, bsdf=bsdf, radianceScaling=scaling)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.5)).configure()
+    imgs = {}
+    for name, kw in (("camera", dict(directConnections=True)), ("light", dict(lightTracing=True))):
+        runs = []
+        for seed in range(1, 5):
+            film, st = mer.EikonalVolPathIntegrator(rrDepth=5, **kw).render(_hidden_quad_scene(64, 64, 64, seed=seed), med)
+            runs.append(mer.develop(film)[..., 0])
+        imgs[name] = np.array(runs)
+    # blocks of 8x8 pixels, 4 independent runs each: means and their standard errors
+    blk = {k: v.reshape(4, 8, 8, 8, 8).mean(axis=(2, 4)) for k, v in imgs.items()}
+    mc, ml = blk["camera"].mean(axis=0), blk["light"].mean(axis=0)
+    se = np.sqrt(blk["camera"].var(axis=0, ddof=1) / 4 + blk["light"].var(axis=0, ddof=1) / 4)
+    assert abs(ml.mean() / mc.mean() - 1) < 0.015, (ml.mean(), mc.mean())
+    bright = mc > 0.05 * mc.max()
+    assert np.all(np.abs(ml - mc)[bright] <= 5 * se[bright] + 0.03 * mc[bright])
+    assert np.corrcoef(mc.ravel(), ml.ravel())[0, 1] > 0.995
+
+
+def test_light_tracing_collimated_beam_time_of_flight():
+    """the fork's showcase configuration (collimated beam into a scattering refractive medium, transient film), with a
+    closed-form bound: a beam along +z from z = -3 into a slab of index 1.5 behind z = -1, camera at z = -4.  Light that
+    scatters at depth s has travelled 2 + 1.5 s and returns over at least 1.5 s + 3: nothing arrives before 5, and
+    `calibratedTransient` (sensor connection left out) starts at 2."""
+    res = 16
+    lo, hi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    rif = mer.SplineDataSource(data=np.full((res,) * 3, 1.5, np.float32), min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(medium_props(stepsize=1e-2, sigmaS=1.0, sigmaA=0.2))
+    med.addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.0)).configure()
+    scene = scene_dict(32, 32, 16, rfilter="box", quad=False)
+    scene.update(envRadiance=0.0, emitter=dict(type="collimated", origin=(0.0, 0.0, -3.0), direction=(0.0, 0.0, 1.0), power=100.0),
+                 transient=dict(minBound=0.0, maxBound=32.0, binWidth=0.25))
+    integ = mer.EikonalVolPathIntegrator(lightTracing=True)
+    film, st = integ.render(scene, med)
+    prof = film[..., :-2].reshape(32, 32, 128, 3).sum(axis=(0, 1, 3))
+    first = int(np.nonzero(prof > 0)[0][0])
+    assert first == 20 and prof[20:24].sum() > 0.2 * prof.sum()  # 5 / 0.25; single scattering near the front face dominates
+    scene["transient"]["calibrated"] = True
+    cal = integ.render(scene, med)[0][..., :-2].reshape(32, 32, 128, 3).sum(axis=(0, 1, 3))
+    assert int(np.nonzero(cal > 0)[0][0]) == 8  # 2 / 0.25
+    del scene["transient"]
+    steady = integ.render(scene, med)[0]
+    assert steady.shape == (32, 32, 5) and abs(prof.sum() / steady[..., :3].sum() - 1) < 1e-3
+    # the beam is seen as a streak through the centre of the image
+    img = steady[..., 0]
+    assert img[12:20, 12:20].sum() > 0.5 * img.sum()

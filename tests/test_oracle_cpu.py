@@ -339,3 +339,24 @@ def test_oracle_radiance_scaling_conventions(oracle32):
         out[scaling] = oracle32.film_develop(film)
     assert np.abs(out["physical"] - 1.0).max() < 3e-3
     assert np.abs(out["reference"] - 1.0).max() > 0.1
+
+
+def test_oracle_light_tracing_agrees_with_camera_tracer(oracle32):
+    """next-row 2, walk half: the oracle's emitter-side walk with sensor connections estimates the image its camera walk
+    does (constant index, quad outside the field of view so that all light scatters first; coarse CPU-sized check)"""
+    from common import BOX_MAX, BOX_MIN, medium_props, oracle_medium_desc, oracle_render_desc, scene_dict
+    from mitsubaer_b200 import fields
+    res = 16
+    lo, hi = fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    orif = oracle32.rif_create(volume_desc((res,) * 3, lo, hi), np.full((res,) * 3, 1.5, np.float32))
+    props = medium_props(stepsize=1e-2, sigmaS=1.5, sigmaA=0.5)
+    med = oracle32.medium_create(oracle_medium_desc(props, 0.5), orif)
+    scene = scene_dict(64, 64, 6, rfilter="box")
+    scene.update(fov=30.0, envRadiance=0.0)
+    cam, st_c = oracle32.render(med, oracle_render_desc(scene, direct_connections=True, props=props))
+    lit, st_l = oracle32.render(med, oracle_render_desc(scene, light_tracing=True, props=props))
+    a, b = oracle32.film_develop(cam)[..., 0], oracle32.film_develop(lit)[..., 0]
+    assert np.allclose(lit[..., -1], 1.0) and st_l.connections > 5000
+    assert abs(b.mean() / a.mean() - 1) < 0.05, (a.mean(), b.mean())
+    ab, bb = a.reshape(8, 8, 8, 8).mean(axis=(1, 3)), b.reshape(8, 8, 8, 8).mean(axis=(1, 3))
+    assert np.corrcoef(ab.ravel(), bb.ravel())[0, 1] > 0.98
