@@ -284,6 +284,7 @@ Scene loadScene(const std::string &xmlPath, const std::map<std::string, std::str
     R.pool_paths = (int) integrator->props.getInteger("poolPaths", 0);
     R.steps_per_pass = (int) integrator->props.getInteger("stepsPerPass", 0);
     R.direct_connections = integrator->props.getBoolean("directConnections", false) ? 1 : 0;
+    R.light_tracing = integrator->props.getBoolean("lightTracing", false) ? 1 : 0; /* emitter-side walk + t = 1 sensor connections */
     const std::string connectionStart = integrator->props.getString("connectionStart", "straight");
     if (connectionStart != "straight" && connectionStart != "random") logError("connectionStart must be \"straight\" or \"random\"");
 
@@ -322,10 +323,20 @@ Scene loadScene(const std::string &xmlPath, const std::map<std::string, std::str
     else if (rfType == "box") R.filter = MER_FILTER_BOX;
     else logError("rfilter \"" + rfType + "\": gaussian and box are carried by this path");
 
+    bool haveBeam = false;
     for (auto &kv : sceneObj->children) {
         if (auto g = std::dynamic_pointer_cast<Generic>(kv.second)) {
-            if (g->tag == "emitter") {
-                if (g->props.pluginName != "constant") logError("emitter \"" + g->props.pluginName + "\": constant environment and rectangle area emitters are carried by this path");
+            if (g->tag == "emitter" && g->props.pluginName == "collimated") { /* src/emitters/collimated.cpp:59-110 */
+                Transform t = g->props.getTransform("toWorld", Transform());
+                Vec3 o = t.point({0, 0, 0}), d = t.vector({0, 0, 1});
+                Spectrum3 pw = g->props.getSpectrum("power", 1.0f);
+                R.emitter_type = MER_EMITTER_COLLIMATED;
+                R.beam_origin[0] = (float) o.x; R.beam_origin[1] = (float) o.y; R.beam_origin[2] = (float) o.z;
+                R.beam_direction[0] = (float) d.x; R.beam_direction[1] = (float) d.y; R.beam_direction[2] = (float) d.z;
+                for (int i = 0; i < 3; i++) R.beam_power[i] = pw.c[i];
+                haveBeam = true;
+            } else if (g->tag == "emitter") {
+                if (g->props.pluginName != "constant") logError("emitter \"" + g->props.pluginName + "\": constant environment, collimated beam and rectangle area emitters are carried by this path");
                 Spectrum3 L = g->props.getSpectrum("radiance", 1.0f);
                 for (int i = 0; i < 3; i++) R.env_radiance[i] = L.c[i];
             } else if (g->tag == "shape") { /* rectangle with an area emitter */
@@ -351,7 +362,9 @@ Scene loadScene(const std::string &xmlPath, const std::map<std::string, std::str
     if (!S.medium) logError("the scene contains no shape with an interior heterogeneousrefractive medium");
     R.connection = S.medium->connection;
     R.connection.start_mode = connectionStart == "random" ? MER_START_RANDOM : MER_START_STRAIGHT;
-    if (R.direct_connections && !R.has_quad) logError("directConnections needs an area emitter (rectangle)");
+    if (R.direct_connections && !R.light_tracing && !R.has_quad) logError("directConnections needs an area emitter (rectangle)");
+    if (haveBeam && !R.light_tracing) logError("a collimated beam has no extent: only the lightTracing mode of ervolpath can render it");
+    if (R.light_tracing && !haveBeam && !R.has_quad) logError("lightTracing needs a collimated beam or a rectangle area emitter");
     S.keepAlive = L.all;
     return S;
 }

@@ -119,3 +119,37 @@ def test_cli_render_matches_python_mirror(volumes, tmp_path):
     assert np.allclose(film, ref, rtol=1e-5, atol=1e-5)  # same paths; only the order of the float atomics differs
     hdr = open(pfm, "rb").read(16)
     assert hdr.startswith(b"PF\n64 48\n-1.0\n")
+
+
+BEAM = os.path.join(ROOT, "scenes", "eikonal_beam_transient.xml")
+
+
+def test_beam_scene_resolves(volumes):
+    """scenes/eikonal_beam_transient.xml: collimated emitter (toWorld lookat -> origin, direction), lightTracing, transient film"""
+    d, lo, hi = volumes
+    out = run([BEAM, "-D", "rif=%s" % (d / "rif.vol"), "-D", "tRes=0.5", "--dry-run"])
+    assert out.returncode == 0, out.stderr
+    s = json.loads(out.stdout)
+    assert s["light_tracing"] == 1 and s["emitter_type"] == 1 and s["has_quad"] == 0 and s["env"] == [0, 0, 0]
+    assert s["frames"] == 16 and s["min_bound"] == 4 and s["bin_width"] == 0.5  # ceil((12 - 4) / 0.5), film.cpp:73
+    assert s["medium"]["boundary"] == 1
+    text = open(BEAM).read()
+    p = d / "beam_camera.xml"
+    p.write_text(text.replace('<boolean name="lightTracing" value="true"/>', ""))
+    out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "--dry-run"])
+    assert out.returncode == 1 and "lightTracing" in out.stderr  # a delta beam cannot be found by a camera walk
+
+
+@pytest.mark.gpu
+def test_cli_renders_beam_transient(volumes, tmp_path):
+    d, lo, hi = volumes
+    pfm, film_path = tmp_path / "beam.pfm", tmp_path / "beam.bin"
+    out = run([BEAM, "-D", "rif=%s" % (d / "rif.vol"), "-D", "spp=4", "-D", "width=48", "-D", "height=48", "-D", "stepsize=0.01", "-D", "tRes=0.5",
+               "-o", str(pfm), "--film", str(film_path)])
+    assert out.returncode == 0, out.stderr
+    film = np.fromfile(film_path, np.float32).reshape(48, 48, 3 * 16 + 2)
+    assert np.allclose(film[..., -1], 1.0) and film[..., :-2].sum() > 0
+    assert os.path.exists(tmp_path / "beam_0000.pfm") and os.path.exists(tmp_path / "beam_0015.pfm")
+    prof = film[..., :-2].reshape(48, 48, 16, 3).sum(axis=(0, 1, 3))
+    # beam enters at x = -1 after 2 units; the earliest return to the camera (z = -4) is a few units later: early frames are empty
+    assert prof[0] == 0 and (prof > 0).sum() >= 4
