@@ -25,7 +25,7 @@ def local_spp(spp_total, rank, world):
 
 def render_sharded(render_local, film, dst=0, all_ranks=False):
     """`render_local(sample_begin, sample_stride)` accumulates this rank's partial film into the
-    tensor `film` (H x W x 5, zeroed by the caller) and returns its stats dict; the partial films
+    tensor `film` (H x W x 5, or H x W x (3*frames+2) for a transient film; zeroed by the caller) and returns its stats dict; the partial films
     are then summed onto rank `dst` (or onto every rank).  Counters are summed with a second,
     tiny all-reduce by `reduce_stats`."""
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -41,7 +41,8 @@ def render_sharded(render_local, film, dst=0, all_ranks=False):
 
 
 def reduce_stats(stats, device=None, keys=("samples", "ray_steps", "scatter_events", "null_collisions",
-                                           "boundary_exits", "nonfinite_dropped")):
+                                           "boundary_exits", "nonfinite_dropped", "connections", "connections_failed",
+                                           "connection_steps")):
     import torch
     world = dist.get_world_size() if dist.is_initialized() else 1
     if world == 1:

@@ -478,3 +478,19 @@ def test_light_tracing_collimated_beam_time_of_flight():
     # the beam is seen as a streak through the centre of the image
     img = steady[..., 0]
     assert img[12:20, 12:20].sum() > 0.5 * img.sum()
+
+
+def test_sample_sharding_adds_up_in_every_mode():
+    """§8e for the widened path: sample s -> GPU s mod G also shards direct connections, light paths and transient frames;
+    the partial films (each with its share of the light-traced unit weight) add up to the single-GPU film"""
+    med = _nee_medium("linear", 1e-2, "hdielectric")[0]
+    for kw, scene in ((dict(directConnections=True), _hidden_quad_scene(24, 24, 6, transient=dict(minBound=4.0, maxBound=20.0, binWidth=1.0))),
+                      (dict(lightTracing=True), _hidden_quad_scene(24, 24, 6, transient=dict(minBound=2.0, maxBound=18.0, binWidth=1.0))),
+                      (dict(lightTracing=True), _hidden_quad_scene(24, 24, 7))):
+        integ = mer.EikonalVolPathIntegrator(rrDepth=5, poolPaths=512, stepsPerPass=128, **kw)
+        full, st = integ.render(scene, med)
+        parts = [integ.render(scene, med, sample_begin=r, sample_stride=3) for r in range(3)]
+        total = sum(p[0] for p in parts)
+        for k in ("samples", "ray_steps", "connections", "connections_failed"):
+            assert sum(p[1][k] for p in parts) == st[k], k
+        assert np.allclose(total, full, rtol=1e-5, atol=1e-5 * np.abs(full).max())
