@@ -261,14 +261,19 @@ struct Shape : Object { /* the medium's container: <shape type="cube"|"sphere"> 
             shapeType = MER_SHAPE_SPHERE;
             params[0] = (float) cw.x; params[1] = (float) cw.y; params[2] = (float) cw.z;
             params[3] = (float) std::sqrt(sx.x * sx.x + sx.y * sx.y + sx.z * sx.z); params[4] = params[5] = 0;
+        } else if (props.pluginName == "obj" || props.pluginName == "ply" || props.pluginName == "serialized") {
+            shapeType = MER_SHAPE_SDF; /* the mesh itself is not read: the medium's sdf child volume describes it */
+            props.getString("filename", "");
+            for (const char *n : {"faceNormals", "flipNormals", "flipTexCoords", "collapse"}) props.getBoolean(n, false);
+            props.getFloat("maxSmoothAngle", 0.0);
         } else {
-            logError("shape type \"" + props.pluginName + "\" cannot contain a heterogeneousrefractive medium on this path (cube, sphere)");
+            logError("shape type \"" + props.pluginName + "\" cannot contain a heterogeneousrefractive medium on this path (cube, sphere, or a mesh with an sdf volume)");
         }
     }
 };
 
 struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousrefractive"> */
-    std::shared_ptr<SplineDataSource> rif;
+    std::shared_ptr<SplineDataSource> rif, sdf;
     std::shared_ptr<GridDataSource> density;
     std::shared_ptr<HGPhaseFunction> phase;
     mer_medium_desc desc;
@@ -279,7 +284,7 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         if (auto p = std::dynamic_pointer_cast<HGPhaseFunction>(child)) { if (phase) logError("Medium: phase function already set"); phase = p; }
         else if (name == "rif" && std::dynamic_pointer_cast<SplineDataSource>(child)) rif = std::dynamic_pointer_cast<SplineDataSource>(child);
         else if (name == "density" && std::dynamic_pointer_cast<GridDataSource>(child)) density = std::dynamic_pointer_cast<GridDataSource>(child);
-        else if (name == "sdf") { /* accepted and unused: containment comes from the shape on this path (R5) */ }
+        else if (name == "sdf" && std::dynamic_pointer_cast<SplineDataSource>(child)) sdf = std::dynamic_pointer_cast<SplineDataSource>(child); /* :376-380 */
         else logError("Medium: Invalid child node! (\"" + std::string(child->className()) + "\")");
     }
     void configure() override { /* properties are resolved here, the handle is created by attach() once the shape is known */
@@ -321,10 +326,15 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
     void attach(const Shape &shape) {
         desc.shape_type = shape.shapeType;
         for (int i = 0; i < 6; i++) desc.shape[i] = shape.params[i];
+        if (shape.shapeType == MER_SHAPE_SDF) { /* a mesh container: containment by the sdf child, bounded by that volume's box */
+            if (!sdf) logError("shape type \"" + shape.props.pluginName + "\": a mesh can contain the medium only through an <volume name=\"sdf\"> child (signed-distance grid)");
+            for (int i = 0; i < 3; i++) { desc.shape[i] = sdf->desc.bbox_min[i]; desc.shape[3 + i] = sdf->desc.bbox_max[i]; }
+        }
         desc.boundary = shape.boundary;
         desc.hg_g = phase ? phase->g : 0.0f; /* Medium::configure: isotropic default */
         if (dryRun()) return;
         merCheck(mer_medium_create(&desc, rif->handle, density ? density->handle : nullptr, &handle));
+        if (sdf) merCheck(mer_medium_set_sdf(handle, sdf->handle, 0));
     }
     ~HeterogeneousRefractiveMedium() override { mer_medium_destroy(handle); }
 };

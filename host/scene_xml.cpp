@@ -207,7 +207,7 @@ struct Loader {
         else if (n.tag == "volume" && type == "gridvolume") o = std::make_shared<GridDataSource>();
         else if (n.tag == "phase" && type == "hg") o = std::make_shared<HGPhaseFunction>();
         else if (n.tag == "medium" && type == "heterogeneousrefractive") o = std::make_shared<HeterogeneousRefractiveMedium>();
-        else if (n.tag == "shape" && (type == "cube" || type == "sphere")) o = std::make_shared<Shape>();
+        else if (n.tag == "shape" && (type == "cube" || type == "sphere" || type == "obj" || type == "ply" || type == "serialized")) o = std::make_shared<Shape>();
         else if (n.tag == "bsdf" && (type == "hdielectric" || type == "null" || type == "dielectric")) o = std::make_shared<SurfaceBsdf>();
         else if (n.tag == "bsdf" || n.tag == "texture") o = std::make_shared<Ignored>();
         else if (n.tag == "integrator" || n.tag == "sensor" || n.tag == "sampler" || n.tag == "film" || n.tag == "rfilter" ||

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 6
+#define MER_ABI_VERSION 7
 
 enum mer_status {
     MER_OK = 0,
@@ -123,7 +123,12 @@ int mer_hg_eval_batch(int device, float g, size_t n, const float *wi, const floa
 
 enum mer_shape_type {
     MER_SHAPE_BOX = 0,   /* hackForBox form  (heterogeneousrefractive.cpp:722-726): min<=p<=max */
-    MER_SHAPE_SPHERE = 1 /* hackForSphere    (:714-720): |p-c|^2 < r^2 */
+    MER_SHAPE_SPHERE = 1, /* hackForSphere    (:714-720): |p-c|^2 < r^2 */
+    /* any closed shape given by the signed-distance grid of mer_medium_set_sdf (the `sdf` child volume, :376-380, made by
+     * mfiles/createRIFFromSD.m): inside <=> sdf(p) < 0.  shape[0..5] is an axis-aligned box that bounds the shape (rays are
+     * sphere-traced from where they enter it).  Stands in for the reference's mesh containment test, which needs libigl's
+     * fast winding number (not vendored). */
+    MER_SHAPE_SDF = 2
 };
 
 enum mer_strategy { /* heterogeneousrefractive.cpp:194-199 */

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmitsubaer_b200.so")
 MER_OK, MER_ERR_INVALID, MER_ERR_CUDA, MER_ERR_UNSUPPORTED, MER_ERR_OOM = 0, 1, 2, 3, 4
 RIF_TRICUBIC, RIF_TRILINEAR_PACKED = 0, 1
 EVAL_VALUE, EVAL_GRADIENT, EVAL_VALUE_AND_GRADIENT = 0, 1, 2
-SHAPE_BOX, SHAPE_SPHERE = 0, 1
+SHAPE_BOX, SHAPE_SPHERE, SHAPE_SDF = 0, 1, 2
 STRATEGY_BALANCE, STRATEGY_SINGLE, STRATEGY_MANUAL, STRATEGY_MAXIMUM = 0, 1, 2, 3
 FILTER_BOX, FILTER_GAUSSIAN = 0, 1
 BOUNDARY_INDEX_MATCHED, BOUNDARY_HDIELECTRIC = 0, 1

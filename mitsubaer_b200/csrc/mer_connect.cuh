@@ -213,14 +213,14 @@ static __device__ int compute_fdf(const MediumDev &M, int precision, float3 vi, 
                 if (signNew == signOld) { oldp = p; oldv = v; oldA = A; oldB = B; oldF = F; }
             }
             break;
-        } else if (!inside_shape(M, p)) {
+        } else if (!inside_shape_any(M, p)) {
             while (nBisect > 0) {
                 nBisect--;
                 p = oldp; v = oldv; A = oldA; B = oldB; F = oldF;
                 h = h / 2;
                 er_derivativestep_fused(M.rif, p, v, A, B, F, h);
                 count++;
-                if (inside_shape(M, p)) { oldp = p; oldv = v; oldA = A; oldB = B; oldF = F; }
+                if (inside_shape_any(M, p)) { oldp = p; oldv = v; oldA = A; oldB = B; oldF = F; }
             }
             const float3 dp1 = p - p1;
             if (dot3(dp1, dp1) < M.minExit2) return 2;
@@ -299,14 +299,14 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
         oldp = p; oldv = v; oldn = n; oldG = G;
         er_step_fused<MER_RIF_TRICUBIC, false>(M.rif, S, p, v, n, G, h, dummy);
         signNew = signbit(dot3(p - p2, v));
-        if (!inside_shape(M, p)) {
+        if (!inside_shape_any(M, p)) {
             if (!isSensorSample) return false;
             while (nBisect > 0) {
                 nBisect--;
                 p = oldp; v = oldv; n = oldn; G = oldG;
                 h = h / 2;
                 er_step_fused<MER_RIF_TRICUBIC, false>(M.rif, S, p, v, n, G, h, dummy);
-                if (inside_shape(M, p)) {
+                if (inside_shape_any(M, p)) {
                     float nm;
                     float3 gm;
                     rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);

@@ -444,6 +444,40 @@ __device__ __forceinline__ float grid_lookup(const GridDev &D, float3 pw) {
 }
 
 /* ------------------------------------------------------------------ a11: containment */
+/* value of the signed-distance spline; outlined: it is off the hot path (see inside_shape_lazy) */
+/* (a compact loop over the scalar coefficient array: cicc 12.9 crashes on an outlined function around rif_tricubic's
+ * unrolled 256-bit loads, and 64 scalar loads are fine for a lookup that is taken near the surface only) */
+template <int UNUSED>
+__device__ __noinline__ float sdf_value_outlined(const RifDev &S, float3 p) {
+    const float3 pv = rif_to_volume(S, p);
+    const float x = (pv.x - S.xmin[0]) * S.xres[0], y = (pv.y - S.xmin[1]) * S.xres[1], z = (pv.z - S.xmin[2]) * S.xres[2];
+    const float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    const int i0 = (int) fx, j0 = (int) fy, k0 = (int) fz;
+    float wx0[4], wx1[4], wy0[4], wy1[4], wz0[4], wz1[4];
+    bs_weights(x, fx, wx0, wx1);
+    bs_weights(y, fy, wy0, wy1);
+    bs_weights(z, fz, wz0, wz1);
+    const int N0 = S.N[0], N1 = S.N[1], N2 = S.N[2];
+    float acc = 0.0f;
+#pragma unroll 1
+    for (int dz = 0; dz < 4; dz++) {
+        const size_t slab = (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N1;
+        float b = 0.0f;
+#pragma unroll 1
+        for (int dy = 0; dy < 4; dy++) {
+            const float *row = S.coeff + (slab + (size_t) clampi(j0 - 1 + dy, 0, N1 - 1)) * (size_t) N0;
+            const float a = row[clampi(i0 - 1, 0, N0 - 1)] * wx0[0] + row[clampi(i0, 0, N0 - 1)] * wx0[1] +
+                            row[clampi(i0 + 1, 0, N0 - 1)] * wx0[2] + row[clampi(i0 + 2, 0, N0 - 1)] * wx0[3];
+            b = fmaf(a, wy0[dy], b);
+        }
+        acc = fmaf(b, wz0[dz], acc);
+    }
+    return acc;
+}
+__device__ __forceinline__ float sdf_value(const RifDev &S, float3 p) { return sdf_value_outlined<0>(S, p); }
+
+/* the analytic containers only: this is what the steppers' hot loops call (MER_SHAPE_SDF goes through inside_shape_any /
+ * inside_shape_lazy, selected at compile time where the loop is hot) */
 __device__ __forceinline__ bool inside_shape(const MediumDev &M, float3 p) {
     if (M.shapeType == MER_SHAPE_SPHERE) {
         float dx = p.x - M.shape[0], dy = p.y - M.shape[1], dz = p.z - M.shape[2];
@@ -451,6 +485,20 @@ __device__ __forceinline__ bool inside_shape(const MediumDev &M, float3 p) {
     }
     return p.x >= M.shape[0] && p.x <= M.shape[3] && p.y >= M.shape[1] && p.y <= M.shape[4] && p.z >= M.shape[2] &&
            p.z <= M.shape[5];
+}
+
+/* The stepper's containment test for MER_SHAPE_SDF without a 64-tap lookup per step: |sdf| bounds the distance to the
+ * surface from below (up to the interpolation error maxSdfError, as aggressive_trace assumes, :476-493), so after a
+ * lookup that found the surface `safe` away the next lookups can wait until the ray has moved that far. */
+__device__ __forceinline__ bool inside_shape_any(const MediumDev &M, float3 p) {
+    if (M.shapeType == MER_SHAPE_SDF) return sdf_value(M.sdf, p) < 0.0f;
+    return inside_shape(M, p);
+}
+__device__ __forceinline__ bool inside_shape_lazy(const MediumDev &M, float3 p, float moved, float &safe) {
+    if (safe > moved) { safe -= moved; return true; }
+    const float v = sdf_value(M.sdf, p);
+    safe = -v - M.maxSdfError;
+    return v < 0.0f;
 }
 
 /* ------------------------------------------------------------------ a7: leapfrog step
@@ -608,6 +656,20 @@ static __device__ __forceinline__ float3 shape_normal(const MediumDev &M, float3
 
 /* distance along a straight ray from a point inside the container to its surface (edge.cpp:45-67 re-finds the
  * surface point of a curved segment with a straight ray from the last interior point) */
+#define MER_SDF_TRACE_STEPS 512
+#define MER_SDF_TRACE_EPS 1e-4f
+
+/* MER_SHAPE_SDF: sphere tracing from inside, advance by -sdf until the sign changes */
+static __device__ __forceinline__ float exit_distance_sdf(const MediumDev &M, float3 o, float3 d) {
+    float t = 0.0f;
+    for (int i = 0; i < MER_SDF_TRACE_STEPS; i++) {
+        const float v = sdf_value(M.sdf, f3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z));
+        if (v >= 0.0f) break;
+        t += fmaxf(-v, MER_SDF_TRACE_EPS);
+    }
+    return t;
+}
+
 static __device__ __forceinline__ float exit_distance(const MediumDev &M, float3 o, float3 d) {
     if (M.shapeType == MER_SHAPE_SPHERE) {
         float3 oc = f3(o.x - M.shape[0], o.y - M.shape[1], o.z - M.shape[2]);

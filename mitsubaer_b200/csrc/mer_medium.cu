@@ -339,7 +339,7 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
     MER_REQUIRE(desc->stepsize > 0.0f, "stepsize must be positive");
     MER_REQUIRE(desc->hg_g > -1.0f && desc->hg_g < 1.0f,
                 "The asymmetry parameter must lie in the interval (-1, 1)!"); /* hg.cpp:50-52 */
-    MER_REQUIRE(desc->shape_type == MER_SHAPE_BOX || desc->shape_type == MER_SHAPE_SPHERE, "unknown shape type");
+    MER_REQUIRE(desc->shape_type == MER_SHAPE_BOX || desc->shape_type == MER_SHAPE_SPHERE || desc->shape_type == MER_SHAPE_SDF, "unknown shape type");
     MER_REQUIRE(desc->boundary == MER_BOUNDARY_INDEX_MATCHED || desc->boundary == MER_BOUNDARY_HDIELECTRIC, "unknown boundary type");
     MER_REQUIRE(desc->radiance_scaling == MER_SCALING_REFERENCE || desc->radiance_scaling == MER_SCALING_PHYSICAL, "unknown radiance scaling");
     if (desc->strategy == MER_STRATEGY_MAXIMUM)
@@ -441,6 +441,8 @@ int mer_medium_resolved(const mer_medium *m, mer_medium_desc *out, float *sampli
 int mer_medium_trace_device(const mer_medium *m, size_t n, float *p_dev, float *v_dev, const float *dist_dev,
                             uint8_t *success_dev, float *dist_surf_dev, float *opl_dev, int32_t *nsteps_dev,
                             void *stream) {
+    if (m && m->dev.shapeType == MER_SHAPE_SDF)
+        return mer::fail(MER_ERR_UNSUPPORTED, "the batch steppers hold box and sphere containers; shape type SDF is carried by mer_render and the connection entry points");
     MER_REQUIRE(m && (n == 0 || (p_dev && v_dev && dist_dev)), "null argument");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(m->device);
@@ -472,6 +474,8 @@ int mer_medium_trace_batch(const mer_medium *m, size_t n, float *p, float *v, co
 
 int mer_medium_trace_till_boundary_batch(const mer_medium *m, size_t n, float *p, float *v, float *dist_surf_out,
                                          float *opl_out, int32_t *nsteps_out) {
+    if (m && m->dev.shapeType == MER_SHAPE_SDF)
+        return mer::fail(MER_ERR_UNSUPPORTED, "the batch steppers hold box and sphere containers; shape type SDF is carried by mer_render and the connection entry points");
     MER_REQUIRE(m && (n == 0 || (p && v)), "null argument");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(m->device);
@@ -492,6 +496,8 @@ int mer_medium_trace_till_boundary_batch(const mer_medium *m, size_t n, float *p
 
 int mer_medium_sample_distance_batch(const mer_medium *m, size_t n, const float *ray_o, const float *ray_d,
                                      const float *ray_mint, const float *xi, mer_medium_sampling_records *rec) {
+    if (m && m->dev.shapeType == MER_SHAPE_SDF)
+        return mer::fail(MER_ERR_UNSUPPORTED, "the batch steppers hold box and sphere containers; shape type SDF is carried by mer_render and the connection entry points");
     MER_REQUIRE(m && rec && (n == 0 || (ray_o && ray_d && xi)), "null argument");
     if (m->grid)
         return mer::fail(MER_ERR_UNSUPPORTED,

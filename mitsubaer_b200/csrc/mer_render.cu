@@ -127,12 +127,43 @@ struct Lane {
     float3 G;
     float thr[3];
     float refStart, segDist, distSurf, rem, sd, etaPath, opl;
+    float safe; /* MER_SHAPE_SDF: distance the ray may still move before the containment test needs a lookup (not persisted) */
     int stepsLeft, depth, kind, flags;
     PathRng rng;
     unsigned pixel, sample; /* sample id = pixel * sppTotal + sample */
 };
 
+__device__ __forceinline__ bool intersect_box(const float *box, float3 o, float3 d, float &tNear, float &tFar) {
+    float t0 = 0.0f, t1 = INFINITY;
+    const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float inv = 1.0f / dd[i];
+        float ta = (box[i] - oo[i]) * inv, tb = (box[3 + i] - oo[i]) * inv;
+        float lo = ta, hi = tb;
+        if (ta > tb) { lo = tb; hi = ta; }
+        t0 = fmaxf(t0, lo);
+        t1 = fminf(t1, hi);
+    }
+    tNear = t0;
+    tFar = t1;
+    return t0 < t1;
+}
+
+template <bool SDFSHAPE>
 __device__ __forceinline__ bool intersect_shape(const MediumDev &M, float3 o, float3 d, float &tNear) {
+    if (SDFSHAPE) {
+        /* sphere tracing from where the ray enters the bounding box until the signed distance turns negative: the entry
+         * point is inside the shape by at most MER_SDF_TRACE_EPS */
+        float t, tFar;
+        if (!intersect_box(M.shape, o, d, t, tFar)) return false;
+        for (int i = 0; i < MER_SDF_TRACE_STEPS && t <= tFar; i++) {
+            const float v = sdf_value(M.sdf, f3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z));
+            if (v < 0.0f) { tNear = t; return true; }
+            t += fmaxf(v, MER_SDF_TRACE_EPS);
+        }
+        return false;
+    }
     if (M.shapeType == MER_SHAPE_SPHERE) {
         float3 oc = f3(o.x - M.shape[0], o.y - M.shape[1], o.z - M.shape[2]);
         float b = dot3(oc, d), c = dot3(oc, oc) - M.shape[3] * M.shape[3];
@@ -292,7 +323,7 @@ __device__ __noinline__ void edge_weight(const MediumDev &M, float sd, float d, 
 
 /* Everything that is not a leapfrog step.  Runs until the lane is steppable again or dead.
  * DIELECTRIC selects the container surface: false = index-matched null surface, true = hdielectric. */
-template <bool DIELECTRIC, bool TRANSIENT>
+template <bool DIELECTRIC, bool TRANSIENT, bool SDFSHAPE>
 __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, unsigned *st) {
     const MediumDev &M = P.M;
     const float zero[3] = {0.f, 0.f, 0.f};
@@ -339,7 +370,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                     L.thr[0] = P.quadLe[0] * wgt; L.thr[1] = P.quadLe[1] * wgt; L.thr[2] = P.quadLe[2] * wgt;
                 }
                 float tBox;
-                if (!intersect_shape(M, o, d, tBox)) continue; /* misses the medium: next path */
+                if (!intersect_shape<SDFSHAPE>(M, o, d, tBox)) continue; /* misses the medium: next path */
                 L.depth = 1;
                 if (P.maxDepth != -1 && L.depth >= P.maxDepth) continue;
                 if (!DIELECTRIC) L.depth = 2;
@@ -348,6 +379,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
                 L.v = d;
                 L.flags = 0;
+                L.safe = 0.0f;
                 L.n = 1.0f;
                 L.G = f3(0.f, 0.f, 0.f);
                 L.kind = K_ENTRY;
@@ -366,7 +398,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                           P.camLeft[2] * cx + P.camUp[2] * cy + P.camDir[2] * cz);
             float3 o = f3(P.camO[0], P.camO[1], P.camO[2]);
             float tBox, tQuad;
-            bool hitBox = intersect_shape(M, o, d, tBox), hitQuad = intersect_quad(P, o, d, tQuad);
+            bool hitBox = intersect_shape<SDFSHAPE>(M, o, d, tBox), hitQuad = intersect_quad(P, o, d, tQuad);
             if (hitQuad && (!hitBox || tQuad < tBox)) { finish_sample(P, L, P.quadLe, 1.0f, st, P.calibrated ? 0.0f : tQuad); continue; }
             if (!hitBox) { finish_sample(P, L, P.env, 0.0f, st); continue; }
             L.depth = 1;
@@ -378,6 +410,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             L.v = d;
             L.thr[0] = L.thr[1] = L.thr[2] = 1.0f;
             L.flags = 0;
+            L.safe = 0.0f;
             L.n = 1.0f;
             L.G = f3(0.f, 0.f, 0.f);
             L.kind = K_ENTRY;
@@ -403,7 +436,8 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             begin_trace(P, L, dist);
         } else if (DIELECTRIC && L.kind == E_SURFACE) {
             /* ---- container surface with a dielectric BSDF; L.v = unit direction of travel, L.n = RIF at the hit point */
-            const float3 N = shape_normal(M, L.p);
+            /* MER_SHAPE_SDF: normalised gradient of the signed distance; box / sphere: analytic */
+            const float3 N = SDFSHAPE ? merc::container_normal(M, L.p) : shape_normal(M, L.p);
             const float u = L.rng.next();
             L.rng.next(); /* the BSDF sample is a Point2 */
             float3 dOut;
@@ -503,8 +537,9 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
                 float3 d = f3(L.v.x * vinv, L.v.y * vinv, L.v.z * vinv);
                 if (DIELECTRIC) { /* move to the surface point and fetch the field there, then E_SURFACE */
-                    const float te = exit_distance(M, L.p, d);
+                    const float te = SDFSHAPE ? exit_distance_sdf(M, L.p, d) : exit_distance(M, L.p, d);
                     L.p = f3(L.p.x + te * d.x, L.p.y + te * d.y, L.p.z + te * d.z);
+                    L.safe = 0.0f;
                     L.v = d;
                     L.flags |= FLAG_OUTWARD;
                     L.kind = K_ENTRY;
@@ -521,7 +556,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
     }
 }
 
-template <int MODE, bool DIELECTRIC, bool TRANSIENT>
+template <int MODE, bool DIELECTRIC, bool TRANSIENT, bool SDFSHAPE>
 __global__ void __launch_bounds__(128, MER_RENDER_MIN_BLOCKS)
 k_render_pass(const __grid_constant__ RenderParams P) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -547,6 +582,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.n = fg.x; L.G = f3(fg.y, fg.z, fg.w);
         L.etaPath = 1.0f;
         L.opl = 0.0f;
+        L.safe = 0.0f;
         if (DIELECTRIC || TRANSIENT) { const float4 ex = P.in.q6[tid]; L.etaPath = ex.x; L.opl = ex.y; }
     } else {
         L.p = L.v = L.G = f3(0.f, 0.f, 0.f);
@@ -555,6 +591,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.refStart = L.segDist = L.distSurf = L.rem = L.sd = 0.0f;
         L.etaPath = 1.0f;
         L.opl = 0.0f;
+        L.safe = 0.0f;
         L.stepsLeft = L.depth = L.flags = 0;
         L.pixel = L.sample = 0;
         L.rng.init(P.seed, 0ULL, 0u);
@@ -590,7 +627,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
                 const float hc = kind == K_FULL ? h : (kind == K_REM ? L.rem : (kind == K_BACKF ? -h : (kind == K_BACKR ? -L.rem : 0.0f)));
                 const float3 pOld = L.p;
                 er_step_fused<MODE>(M.rif, S, L.p, L.v, L.n, L.G, hc, TRANSIENT ? L.opl : oplUnused);
-                const bool inside = inside_shape(M, L.p);
+                const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
                 const bool moved = L.p.x != pOld.x || L.p.y != pOld.y || L.p.z != pOld.z;
                 int next;
                 if (kind == K_FULL) {
@@ -611,7 +648,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
             }
         } else if (mw != 0u) {
             /* ---------------- event phase: scatter / exit / regenerate for every waiting lane at once */
-            if (waiting) handle_events<DIELECTRIC, TRANSIENT>(P, L, st);
+            if (waiting) handle_events<DIELECTRIC, TRANSIENT, SDFSHAPE>(P, L, st);
         } else {
             break; /* budget exhausted (or nobody alive) and nothing waiting */
         }
@@ -879,6 +916,10 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     MER_REQUIRE(r->filter == MER_FILTER_BOX || r->filter == MER_FILTER_GAUSSIAN, "unknown reconstruction filter");
     if (m->dev.aggressive)
         return mer::fail(MER_ERR_UNSUPPORTED, "aggressivetracing is only available in mer_medium_sample_distance_batch");
+    if (m->dev.shapeType == MER_SHAPE_SDF) {
+        MER_REQUIRE(m->dev.hasSdf, "shape type SDF needs the sdf volume (mer_medium_set_sdf)");
+        if (m->rif->mode != MER_RIF_TRICUBIC) return mer::fail(MER_ERR_UNSUPPORTED, "shape type SDF is built for the tricubic RIF mode");
+    }
     if (r->light_tracing) {
         MER_REQUIRE(r->emitter_type == MER_EMITTER_QUAD || r->emitter_type == MER_EMITTER_COLLIMATED, "unknown emitter type");
         MER_REQUIRE(r->emitter_type != MER_EMITTER_QUAD || r->has_quad, "light tracing from the quad emitter needs the quad");
@@ -1009,13 +1050,16 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         MER_CUDA(cudaMemsetAsync(S.nOut, 0, sizeof(unsigned), stream));
         const unsigned blocks = (threads + TPB - 1) / TPB;
         const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, transient = P.frames > 1;
-#define MER_PASS(MODE_, D_, T_) MER_LAUNCH((k_render_pass<MODE_, D_, T_>), blocks, TPB, 0, stream, P)
-        if (m->rif->mode == MER_RIF_TRICUBIC) {
-            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true); else MER_PASS(MER_RIF_TRICUBIC, true, false); }
-            else { if (transient) MER_PASS(MER_RIF_TRICUBIC, false, true); else MER_PASS(MER_RIF_TRICUBIC, false, false); }
+#define MER_PASS(MODE_, D_, T_, S_) MER_LAUNCH((k_render_pass<MODE_, D_, T_, S_>), blocks, TPB, 0, stream, P)
+        if (m->dev.shapeType == MER_SHAPE_SDF) { /* tricubic only (checked above) */
+            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true, true); else MER_PASS(MER_RIF_TRICUBIC, true, false, true); }
+            else { if (transient) MER_PASS(MER_RIF_TRICUBIC, false, true, true); else MER_PASS(MER_RIF_TRICUBIC, false, false, true); }
+        } else if (m->rif->mode == MER_RIF_TRICUBIC) {
+            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true, false); else MER_PASS(MER_RIF_TRICUBIC, true, false, false); }
+            else { if (transient) MER_PASS(MER_RIF_TRICUBIC, false, true, false); else MER_PASS(MER_RIF_TRICUBIC, false, false, false); }
         } else {
-            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRILINEAR_PACKED, true, true); else MER_PASS(MER_RIF_TRILINEAR_PACKED, true, false); }
-            else { if (transient) MER_PASS(MER_RIF_TRILINEAR_PACKED, false, true); else MER_PASS(MER_RIF_TRILINEAR_PACKED, false, false); }
+            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRILINEAR_PACKED, true, true, false); else MER_PASS(MER_RIF_TRILINEAR_PACKED, true, false, false); }
+            else { if (transient) MER_PASS(MER_RIF_TRILINEAR_PACKED, false, true, false); else MER_PASS(MER_RIF_TRILINEAR_PACKED, false, false, false); }
         }
 #undef MER_PASS
         launches++;

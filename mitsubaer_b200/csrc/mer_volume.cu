@@ -307,6 +307,55 @@ int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *d
     return MER_OK;
 }
 
+/* Streams the payload of a single-channel float32 .vol file into a fresh device array: 64 MiB slabs through two pinned
+ * staging buffers, the disk read of one overlapping the H2D copy of the other.  Peak host memory is 128 MiB whatever the
+ * grid (a 1024^3 RIF is 4 GiB on disk); the reference reads the file through a memory map and prefilters on the CPU
+ * (splinevolume.cpp:204-317), here the prefilter runs on the device array. */
+int stream_vol_to_device(int device, const char *path, mer_volume_desc *desc, float **data_dev_out) {
+    *data_dev_out = nullptr;
+    int32_t enc = 0, ch = 0;
+    int rc = read_vol_file(path, desc, nullptr, &enc, &ch);
+    if (rc) return rc;
+    if (enc != 1 || ch != 1) return mer::fail(MER_ERR_UNSUPPORTED, "only single-channel float32 .vol files are supported on this path");
+    rc = mer::check_device(device);
+    if (rc) return rc;
+    mer::DeviceGuard guard(device);
+    const size_t total = (size_t) desc->res[0] * desc->res[1] * desc->res[2];
+    FILE *f = fopen(path, "rb");
+    if (!f) return mer::fail(MER_ERR_INVALID, std::string("cannot open volume file: ") + path);
+    fseek(f, 48, SEEK_SET);
+    const size_t slab = std::min<size_t>(total, (size_t) 16 << 20); /* floats per slab */
+    float *dev = nullptr, *stage[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    cudaError_t e = cudaMalloc(&dev, total * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreate(&st);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaMallocHost(&stage[i], slab * sizeof(float));
+        if (e == cudaSuccess) e = cudaEventCreate(&done[i]);
+    }
+    bool truncated = false;
+    for (size_t off = 0, k = 0; e == cudaSuccess && off < total; off += slab, k++) {
+        const int b = (int) (k & 1);
+        const size_t n = std::min(slab, total - off);
+        if (k >= 2) e = cudaEventSynchronize(done[b]); /* the copy that last used this buffer */
+        if (e != cudaSuccess) break;
+        if (fread(stage[b], sizeof(float), n, f) != n) { truncated = true; break; }
+        e = cudaMemcpyAsync(dev + off, stage[b], n * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(done[b], st);
+    }
+    if (st) cudaStreamSynchronize(st);
+    fclose(f);
+    for (int i = 0; i < 2; i++) { if (stage[i]) cudaFreeHost(stage[i]); if (done[i]) cudaEventDestroy(done[i]); }
+    if (st) cudaStreamDestroy(st);
+    if (truncated || e != cudaSuccess) {
+        cudaFree(dev);
+        return truncated ? mer::fail(MER_ERR_INVALID, "volume file truncated") : mer::fail(e == cudaErrorMemoryAllocation ? MER_ERR_OOM : MER_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *data_dev_out = dev;
+    return MER_OK;
+}
+
 void apply_override(mer_volume_desc *d, const mer_volume_desc *ov) {
     if (!ov) return;
     /* `min`/`max` properties replace the file's bbox (splinevolume.cpp:93-98, 260-268); toWorld */
@@ -363,12 +412,18 @@ int mer_rif_create(int device, const mer_volume_desc *desc, const float *data, i
 
 int mer_rif_create_from_file(int device, const char *vol_path, const mer_volume_desc *override_or_null, int mode,
                              mer_rif **out) {
+    if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    MER_REQUIRE(vol_path, "null path");
     mer_volume_desc d;
-    std::vector<float> data;
-    int rc = read_vol_file(vol_path, &d, &data, nullptr, nullptr);
+    float *raw = nullptr;
+    int rc = stream_vol_to_device(device, vol_path, &d, &raw);
     if (rc) return rc;
     apply_override(&d, override_or_null);
-    return mer_rif_create(device, &d, data.data(), mode, out);
+    rc = mer_rif_create_device(device, &d, raw, mode, out);
+    mer::DeviceGuard guard(device);
+    cudaFree(raw);
+    return rc;
 }
 
 void mer_rif_destroy(mer_rif *r) {
@@ -527,12 +582,18 @@ int mer_grid_create(int device, const mer_volume_desc *desc, const float *data, 
 
 int mer_grid_create_from_file(int device, const char *vol_path, const mer_volume_desc *override_or_null,
                               mer_grid **out) {
+    if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    MER_REQUIRE(vol_path, "null path");
     mer_volume_desc d;
-    std::vector<float> data;
-    int rc = read_vol_file(vol_path, &d, &data, nullptr, nullptr);
+    float *raw = nullptr;
+    int rc = stream_vol_to_device(device, vol_path, &d, &raw);
     if (rc) return rc;
     apply_override(&d, override_or_null);
-    return mer_grid_create(device, &d, data.data(), out);
+    rc = mer_grid_create_device(device, &d, raw, out);
+    mer::DeviceGuard guard(device);
+    cudaFree(raw);
+    return rc;
 }
 
 void mer_grid_destroy(mer_grid *g) {

@@ -325,6 +325,11 @@ class HeterogeneousRefractiveMedium:
         elif shape[0] == "sphere":
             d.shape_type = _abi.SHAPE_SPHERE
             d.shape[:] = [float(x) for x in list(shape[1]) + [shape[2], 0.0, 0.0]]
+        elif shape[0] == "sdf":  # any closed shape: the `sdf` child volume, bounded by the given box
+            d.shape_type = _abi.SHAPE_SDF
+            d.shape[:] = [float(x) for x in list(shape[1]) + list(shape[2])]
+            if self.sdf is None:
+                raise _abi.MerError(_abi.MER_ERR_INVALID, 'shape ("sdf", min, max) needs an "sdf" child volume')
         else:
             raise _abi.MerError(_abi.MER_ERR_INVALID, "unknown shape")
         d.hg_g = self.phase.g if self.phase is not None else 0.0  # Medium::configure: isotropic default

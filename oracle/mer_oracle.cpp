@@ -460,6 +460,7 @@ template <typename F> struct Medium {
 
     /* insideShape, :707-726 (sphere: strict <; box: closed) */
     inline bool insideShape(const F *p) const {
+        if (d.shape_type == MER_SHAPE_SDF) return sdf->value(p) < 0; /* any closed shape by its signed-distance grid */
         if (d.shape_type == MER_SHAPE_SPHERE) {
             F dx = p[0] - (F) d.shape[0], dy = p[1] - (F) d.shape[1], dz = p[2] - (F) d.shape[2];
             F r = (F) d.shape[3];
@@ -615,6 +616,11 @@ template <typename F> struct Medium {
     /* computefdfBDPT, :816-939: residual p(t*) - p2 and its Jacobian w.r.t. the launch velocity.
      * returns 0 = closest approach inside, 1 = left the object, 2 = degenerate (error = p1 - p2, J = 0),
      * 3 = left the object by total internal reflection */
+    /* MER_SHAPE_SDF: sphere tracing from where the ray enters the bounding box (shape[0..5]) until the signed distance turns
+     * negative; the other shapes analytically.  Defined after intersectShape below. */
+    bool enterShape(const float *o, const float *dd, float &tNear) const;
+    float exitDist(const float *o, const float *dd) const;
+
     /* outward unit normal at the container surface: sdf gradient (:892-893) or, without an sdf child, the analytic one */
     void containerNormal(const F *p, F *N) const {
         if (sdf) {
@@ -1273,6 +1279,40 @@ inline bool intersectShape(const mer_medium_desc &m, const float o[3], const flo
     return true;
 }
 
+const int kSdfTraceSteps = 512;
+const float kSdfTraceEps = 1e-4f;
+
+template <typename F> bool Medium<F>::enterShape(const float *o, const float *dd, float &tNear) const {
+    if (d.shape_type != MER_SHAPE_SDF) return intersectShape(d, o, dd, tNear);
+    mer_medium_desc box = d;
+    box.shape_type = MER_SHAPE_BOX;
+    float t, tFar = std::numeric_limits<float>::infinity();
+    if (!intersectShape(box, o, dd, t)) return false;
+    for (int i = 0; i < 3; i++) { /* far end of the bounding box */
+        float inv = 1.0f / dd[i], ta = (d.shape[i] - o[i]) * inv, tb = (d.shape[3 + i] - o[i]) * inv;
+        tFar = std::min(tFar, std::max(ta, tb));
+    }
+    for (int i = 0; i < kSdfTraceSteps && t <= tFar; i++) {
+        F q[3] = {(F) (o[0] + t * dd[0]), (F) (o[1] + t * dd[1]), (F) (o[2] + t * dd[2])};
+        float v = (float) sdf->value(q);
+        if (v < 0) { tNear = t; return true; }
+        t += std::max(v, kSdfTraceEps);
+    }
+    return false;
+}
+
+template <typename F> float Medium<F>::exitDist(const float *o, const float *dd) const {
+    if (d.shape_type != MER_SHAPE_SDF) return exitDistance(d, o, dd);
+    float t = 0;
+    for (int i = 0; i < kSdfTraceSteps; i++) {
+        F q[3] = {(F) (o[0] + t * dd[0]), (F) (o[1] + t * dd[1]), (F) (o[2] + t * dd[2])};
+        float v = (float) sdf->value(q);
+        if (v >= 0) break;
+        t += std::max(-v, kSdfTraceEps);
+    }
+    return t;
+}
+
 inline bool intersectQuad(const mer_render_desc &r, const float o[3], const float d[3], float &t) {
     if (!r.has_quad) return false;
     const float *u = r.quad_u, *v = r.quad_v;
@@ -1494,7 +1534,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
     const bool nee = R.direct_connections != 0 && R.has_quad;
     bool covered = false; /* the quad's light along the current edge chain was already estimated by a direct connection */
     float tBox, tQuad;
-    bool hitBox = intersectShape(M.d, o, dcam, tBox);
+    bool hitBox = M.enterShape(o, dcam, tBox);
     bool hitQuad = !light && intersectQuad(R, o, dcam, tQuad);
     if (light && !hitBox) return;
     if (hitQuad && (!hitBox || tQuad < tBox)) {
@@ -1540,7 +1580,13 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             return fromOutside;
         }
         float N[3], dOut[3], w, es;
-        shapeNormal(M.d, pf, N);
+        if (M.d.shape_type == MER_SHAPE_SDF) { /* normalised gradient of the signed distance; box / sphere: analytic */
+            F Nf[3];
+            M.containerNormal(p, Nf);
+            for (int i = 0; i < 3; i++) N[i] = (float) Nf[i];
+        } else {
+            shapeNormal(M.d, pf, N);
+        }
         float eta = (float) M.rif->value(p); /* hdielectric.cpp:115-118: m_shape->getInteriorMedium()->getRIF(p) */
         float u = rng.next();
         rng.next(); /* the BSDF sample is a Point2 (rRec.nextSample2D()) */
@@ -1656,7 +1702,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             if (dielectric) {
                 /* edge.cpp:45-67: the surface point is re-found by a straight ray from the last interior point */
                 float pf32[3] = {(float) p[0], (float) p[1], (float) p[2]}, df[3] = {(float) dir[0], (float) dir[1], (float) dir[2]};
-                float te = exitDistance(M.d, pf32, df);
+                float te = M.exitDist(pf32, df);
                 for (int i = 0; i < 3; i++) p[i] = (F) (pf32[i] + te * df[i]);
             }
             if (!surface(false)) return;

@@ -75,6 +75,9 @@ def oracle_medium_desc(props, g=0.9, has_density=False):
     if shape[0] == "box":
         d.shape_type = 0
         d.shape[:] = [float(x) for x in list(shape[1]) + list(shape[2])]
+    elif shape[0] == "sdf":
+        d.shape_type = 2
+        d.shape[:] = [float(x) for x in list(shape[1]) + list(shape[2])]
     else:
         d.shape_type = 1
         d.shape[:] = [float(x) for x in list(shape[1]) + [shape[2], 0.0, 0.0]]

@@ -494,3 +494,43 @@ def test_sample_sharding_adds_up_in_every_mode():
         for k in ("samples", "ray_steps", "connections", "connections_failed"):
             assert sum(p[1][k] for p in parts) == st[k], k
         assert np.allclose(total, full, rtol=1e-5, atol=1e-5 * np.abs(full).max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# next-row 4: containment by a signed-distance grid
+
+@pytest.mark.parametrize("bsdf,nee", [("null", False), ("hdielectric", True)])
+def test_sdf_container_matches_oracle_and_the_analytic_sphere(oracle32, bsdf, nee):
+    """shape ("sdf", bbox): inside <=> sdf(p) < 0, entry by sphere tracing, normals from the gradient, and a stepper that
+    skips the containment lookup while the last one guarantees room.  With the signed distance of a sphere on a grid the
+    result must be the analytic sphere's (up to the 1e-4 the entry point sits inside the surface), and the oracle's."""
+    res = 48
+    data, lo, hi = make_field("sd", res)
+    sdf_data = mer.fields.sphere_sdf((res,) * 3, lo, hi, radius=0.8).astype(np.float32)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    sdf = mer.SplineDataSource(data=sdf_data, min=lo, max=hi)
+    scene = scene_dict(40, 40, 8, rfilter="box")
+    integ = mer.EikonalVolPathIntegrator(rrDepth=5, directConnections=nee, poolPaths=2048, stepsPerPass=128)
+    out = {}
+    for name, shape in (("sdf", ("sdf", BOX_MIN, BOX_MAX)), ("sphere", ("sphere", (0.0, 0.0, 0.0), 0.8))):
+        props = medium_props(stepsize=5e-3, sigmaS=2.0, sigmaA=0.5, bsdf=bsdf, shape=shape)
+        med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.5))
+        if name == "sdf":
+            med.addChild("sdf", sdf)
+        med.configure()
+        film, st = integ.render(scene, med)
+        out[name] = (mer.develop(film), st, props)
+    a, b = out["sdf"][0], out["sphere"][0]
+    for k in ("ray_steps", "scatter_events", "boundary_exits"):
+        assert abs(out["sdf"][1][k] - out["sphere"][1][k]) <= 0.01 * out["sphere"][1][k], k
+    assert abs(a.mean() / b.mean() - 1) < 0.01 and np.mean(np.abs(a - b) <= 0.02 * np.maximum(b, 1.0)) > 0.9
+    # oracle with the same shape type
+    d = volume_desc((res,) * 3, lo, hi)
+    omed = oracle32.medium_create(oracle_medium_desc(out["sdf"][2], 0.5), oracle32.rif_create(d, data))
+    oracle32.medium_set_sdf(omed, oracle32.rif_create(d, sdf_data), False)
+    ofilm, ost = oracle32.render(omed, oracle_render_desc(scene, direct_connections=nee, props=out["sdf"][2]))
+    ref = oracle32.film_develop(ofilm)
+    assert abs(out["sdf"][1]["ray_steps"] - ost.ray_steps) <= 0.005 * ost.ray_steps
+    assert np.mean(np.abs(a - ref) <= 2e-3 * np.maximum(ref, 1.0)) > 0.95 and abs(a.mean() / ref.mean() - 1) < 3e-3
+    with pytest.raises(mer.MerError, match="sdf"):
+        mer.HeterogeneousRefractiveMedium(medium_props(shape=("sdf", BOX_MIN, BOX_MAX))).addChild("rif", rif).configure()

@@ -171,3 +171,24 @@ def test_vol_roundtrip_and_file_loading(tmp_path, oracle32):
     bad.write_bytes(b"VOX\x03" + raw[4:])
     with pytest.raises(mer.MerError, match="incorrect header identifier"):
         mer.SplineDataSource(filename=str(bad))
+
+
+def test_streamed_loading_of_a_multi_slab_file(tmp_path):
+    """.vol files are streamed to the device in 64 MiB slabs through two pinned buffers (a 1024^3 RIF is 4 GiB
+    on disk); a 288^3 file spans two slabs, a truncated one is refused, density grids go the same way"""
+    res = (288, 288, 288)
+    lo, hi = mer.fields.padded_bbox(BOX_MIN, BOX_MAX, res)
+    data = mer.fields.radial_rif(res, lo, hi)
+    path = tmp_path / "big.vol"
+    mer.fields.write_vol(path, data, lo, hi)
+    assert os.path.getsize(path) > 64 << 20
+    a = mer.SplineDataSource(filename=str(path))
+    b = mer.SplineDataSource(data=data, min=lo, max=hi)
+    assert a.getResolution() == res and np.array_equal(a.coefficients(), b.coefficients())
+    g = mer.GridDataSource(filename=str(path))
+    pts = np.random.default_rng(3).uniform(-0.9, 0.9, (1000, 3)).astype(np.float32)
+    assert np.array_equal(g.lookupFloat(pts), mer.GridDataSource(data=data, min=lo, max=hi).lookupFloat(pts))
+    cut = tmp_path / "cut.vol"
+    cut.write_bytes(open(path, "rb").read()[: 48 + (70 << 20)])
+    with pytest.raises(mer.MerError, match="truncated"):
+        mer.SplineDataSource(filename=str(cut))

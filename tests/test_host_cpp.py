@@ -153,3 +153,21 @@ def test_cli_renders_beam_transient(volumes, tmp_path):
     prof = film[..., :-2].reshape(48, 48, 16, 3).sum(axis=(0, 1, 3))
     # beam enters at x = -1 after 2 units; the earliest return to the camera (z = -4) is a few units later: early frames are empty
     assert prof[0] == 0 and (prof > 0).sum() >= 4
+
+
+def test_mesh_container_through_sdf_volume(volumes, tmp_path):
+    """<shape type="obj"> cannot be read here, but with an <volume name="sdf"> child on the medium the signed-distance grid is
+    the container; without it the scene is refused like any shape this path cannot hold"""
+    d, lo, hi = volumes
+    mer.fields.write_vol(d / "sdf.vol", mer.fields.sphere_sdf((40, 40, 40), lo, hi, radius=0.8).astype(np.float32), lo, hi)
+    text = open(SCENE).read().replace('<shape type="cube">', '<shape type="obj"><string name="filename" value="bunny.obj"/>')
+    p = tmp_path / "mesh.xml"
+    p.write_text(text)
+    out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "--dry-run"])
+    assert out.returncode == 1 and "sdf" in out.stderr
+    p.write_text(text.replace('<volume name="rif" type="splinevolume">',
+                              '<volume name="sdf" type="splinevolume"><string name="filename" value="%s"/></volume>\n<volume name="rif" type="splinevolume">' % (d / "sdf.vol")))
+    out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "--dry-run"])
+    assert out.returncode == 0, out.stderr
+    m = json.loads(out.stdout)["medium"]
+    assert m["shape_type"] == 2 and np.allclose(m["shape"], list(lo) + list(hi))
