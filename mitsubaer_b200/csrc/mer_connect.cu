@@ -59,8 +59,10 @@ k_connection_residual(const __grid_constant__ MediumDev M, int precision, size_t
         float3 e;
         M3 J;
         int count = 0;
-        int st = compute_fdf(M, precision, f3(V0[3 * i], V0[3 * i + 1], V0[3 * i + 2]), f3(P1[3 * i], P1[3 * i + 1], P1[3 * i + 2]),
-                             f3(P2[3 * i], P2[3 * i + 1], P2[3 * i + 2]), isSensor != 0, M.boundary == MER_BOUNDARY_HDIELECTRIC, e, J, count);
+        const float3 v0 = f3(V0[3 * i], V0[3 * i + 1], V0[3 * i + 2]), p1 = f3(P1[3 * i], P1[3 * i + 1], P1[3 * i + 2]), p2 = f3(P2[3 * i], P2[3 * i + 1], P2[3 * i + 2]);
+        const bool refract = M.boundary == MER_BOUNDARY_HDIELECTRIC;
+        const int st = M.shapeType == MER_SHAPE_SDF ? compute_fdf<true>(M, precision, v0, p1, p2, isSensor != 0, refract, e, J, count)
+                                                    : compute_fdf<false>(M, precision, v0, p1, p2, isSensor != 0, refract, e, J, count);
         err[3 * i] = e.x; err[3 * i + 1] = e.y; err[3 * i + 2] = e.z;
         for (int k = 0; k < 9; k++) derr[9 * i + k] = J.m[k];
         if (status) status[i] = st;
@@ -86,7 +88,10 @@ k_connect(const __grid_constant__ MediumDev M, int precision, float tol2, float 
         PathRng rng;
         rng.init(seed, (unsigned long long) i, 0u);
         ConnectResult R;
-        connect_solve(M, precision, tol2, rrweight, maxIterations, p1, p2, din, isSensor != 0, M.boundary == MER_BOUNDARY_HDIELECTRIC, straightFirst != 0, rng, R);
+        if (M.shapeType == MER_SHAPE_SDF)
+            connect_solve<true>(M, precision, tol2, rrweight, maxIterations, p1, p2, din, isSensor != 0, M.boundary == MER_BOUNDARY_HDIELECTRIC, straightFirst != 0, rng, R);
+        else
+            connect_solve<false>(M, precision, tol2, rrweight, maxIterations, p1, p2, din, isSensor != 0, M.boundary == MER_BOUNDARY_HDIELECTRIC, straightFirst != 0, rng, R);
         const bool success = R.success;
         const float weight = R.weight, opl = R.opl, dist = R.dist;
         const float3 dir = R.dir, rev = R.rev;

@@ -174,6 +174,7 @@ static __device__ float3 container_normal(const MediumDev &M, float3 p) {
 /* computefdfBDPT, :816-939.  status: 0 closest approach inside the shape, 1 left the object (boundary + straight
  * extension), 2 degenerate (error = p1 - p2, Jacobian 0), 3 left the object by total internal reflection.  `refract` = the reference's behaviour (Snell to exterior
  * index 1, i.e. an hdielectric container); false = index-matched container: the velocity crosses unchanged. */
+template <bool SDFSHAPE>
 static __device__ int compute_fdf(const MediumDev &M, int precision, float3 vi, float3 p1, float3 p2, bool isSensorSample,
                            bool refract, float3 &err, M3 &derr, int &count) {
     M3 A = m3_zero(), B = m3_identity();
@@ -213,14 +214,14 @@ static __device__ int compute_fdf(const MediumDev &M, int precision, float3 vi, 
                 if (signNew == signOld) { oldp = p; oldv = v; oldA = A; oldB = B; oldF = F; }
             }
             break;
-        } else if (!inside_shape_any(M, p)) {
+        } else if (!(SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p))) {
             while (nBisect > 0) {
                 nBisect--;
                 p = oldp; v = oldv; A = oldA; B = oldB; F = oldF;
                 h = h / 2;
                 er_derivativestep_fused(M.rif, p, v, A, B, F, h);
                 count++;
-                if (inside_shape_any(M, p)) { oldp = p; oldv = v; oldA = A; oldB = B; oldF = F; }
+                if ((SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p))) { oldp = p; oldv = v; oldA = A; oldB = B; oldF = F; }
             }
             const float3 dp1 = p - p1;
             if (dot3(dp1, dp1) < M.minExit2) return 2;
@@ -280,6 +281,7 @@ struct ExitInfo { /* how a connection left the container (next-event estimation 
     float cosI; /* cosine between the interior direction and the outward normal */
 };
 
+template <bool SDFSHAPE>
 static __device__ bool compute_path_lengths(const MediumDev &M, int precision, float tol2, float3 p1, float3 p2, float3 dirToP2, float3 &revDir,
                                      bool isSensorSample, bool refract, float &opl, float &dist, ExitInfo &ex) {
     dist = 0.0f;
@@ -299,14 +301,14 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
         oldp = p; oldv = v; oldn = n; oldG = G;
         er_step_fused<MER_RIF_TRICUBIC, false>(M.rif, S, p, v, n, G, h, dummy);
         signNew = signbit(dot3(p - p2, v));
-        if (!inside_shape_any(M, p)) {
+        if (!(SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p))) {
             if (!isSensorSample) return false;
             while (nBisect > 0) {
                 nBisect--;
                 p = oldp; v = oldv; n = oldn; G = oldG;
                 h = h / 2;
                 er_step_fused<MER_RIF_TRICUBIC, false>(M.rif, S, p, v, n, G, h, dummy);
-                if (inside_shape_any(M, p)) {
+                if ((SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p))) {
                     float nm;
                     float3 gm;
                     rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
@@ -396,6 +398,7 @@ struct ConnectResult {
     float xnorm; /* ... and |x|: computefdf renormalises x to n(p1), so J scales like n(p1) / |x| */
 };
 
+template <bool SDFSHAPE>
 static __device__ void connect_solve(const MediumDev &M, int precision, float tol2, float rrweight, int maxIterations, float3 p1, float3 p2,
                                      float3 din, bool isSensor, bool refract, bool straightFirst, PathRng &rng, ConnectResult &R) {
     R.success = false;
@@ -449,7 +452,7 @@ static __device__ void connect_solve(const MediumDev &M, int precision, float to
         M3 Jt;
         int cnt = 0;
         /* evaluations that end degenerate or totally reflected carry no usable residual: infinite cost */
-        int status = compute_fdf(M, precision, f3(x[0], x[1], x[2]), p1, p2, isSensor, refract, r, Jt, cnt);
+        int status = compute_fdf<SDFSHAPE>(M, precision, f3(x[0], x[1], x[2]), p1, p2, isSensor, refract, r, Jt, cnt);
         R.evals++;
         float cost = status >= 2 ? INFINITY : 0.5f * dot3(r, r), lambda = 0.0f;
         int accepted = 0;
@@ -466,7 +469,7 @@ static __device__ void connect_solve(const MediumDev &M, int precision, float to
             if (!solve3(JTJ, g, dx)) break;
             float3 rn;
             M3 Jn;
-            status = compute_fdf(M, precision, f3(x[0] + dx[0], x[1] + dx[1], x[2] + dx[2]), p1, p2, isSensor, refract, rn, Jn, cnt);
+            status = compute_fdf<SDFSHAPE>(M, precision, f3(x[0] + dx[0], x[1] + dx[1], x[2] + dx[2]), p1, p2, isSensor, refract, rn, Jn, cnt);
             R.evals++;
             const float costn = status >= 2 ? INFINITY : 0.5f * dot3(rn, rn);
             if (costn < cost) {
@@ -488,7 +491,7 @@ static __device__ void connect_solve(const MediumDev &M, int precision, float to
     R.xnorm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
     const float xl = 1.0f / R.xnorm;
     R.dir = f3((x[0] * xl) * RIFp, (x[1] * xl) * RIFp, (x[2] * xl) * RIFp);
-    if (converged && compute_path_lengths(M, precision, tol2, p1, p2, R.dir, R.rev, isSensor, refract, R.opl, R.dist, R.exit)) R.success = true;
+    if (converged && compute_path_lengths<SDFSHAPE>(M, precision, tol2, p1, p2, R.dir, R.rev, isSensor, refract, R.opl, R.dist, R.exit)) R.success = true;
 }
 
 /* |d r_perp / d omega| of a solved connection: the area, in the plane perpendicular to the arriving ray, swept per unit

@@ -268,12 +268,14 @@ __device__ __forceinline__ void sample_position(const RenderParams &P, unsigned 
     sy = (float) y + (float) (b.y >> 8) * (1.0f / 16777216.0f);
 }
 
+/* EXTRAS = any of: transient film, direct connections, light tracing.  The plain camera walk is compiled without them. */
+template <bool EXTRAS>
 __device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, const float rad[3], float alpha,
                                               unsigned *st, float pathLength = INFINITY) {
-    if (P.lightMode) { L.kind = E_NEW; return; } /* a light path that leaves or dies deposits nothing: only its connections do */
+    if (EXTRAS && P.lightMode) { L.kind = E_NEW; return; } /* a light path that leaves or dies deposits nothing: only its connections do */
     float sx, sy;
     sample_position(P, L.pixel, L.sample, sx, sy);
-    film_put(P, sx, sy, rad, alpha, 1.0f, path_frame(P, pathLength), st[ST_NONFINITE]);
+    film_put(P, sx, sy, rad, alpha, 1.0f, EXTRAS ? path_frame(P, pathLength) : 0, st[ST_NONFINITE]);
     L.kind = E_NEW;
 }
 
@@ -321,9 +323,26 @@ __device__ __noinline__ void edge_weight(const MediumDev &M, float sd, float d, 
         edge[c] = success ? __fdiv_rn(__fmul_rn(M.sigmaS[c], T[c]), ps) : __fdiv_rn(T[c], pf);
 }
 
+/* phase sampling (wi = normalize(-mRec.d)) and the Russian roulette of volpath.cpp:326-336 at a scattering vertex */
+template <bool DIELECTRIC, bool EXTRAS>
+__device__ __forceinline__ void scatter_and_roulette(const RenderParams &P, Lane &L, float3 wi, unsigned *st) {
+    const float zero[3] = {0.f, 0.f, 0.f};
+    float u1 = L.rng.next(), u2 = L.rng.next();
+    L.v = hg_sample_dev(P.M.g, wi, u1, u2);
+    if (L.depth++ >= P.rrDepth) {
+        float q = fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2]));
+        if (DIELECTRIC) q *= L.etaPath * L.etaPath;
+        q = fminf(q, 0.95f);
+        if (L.rng.next() >= q) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); return; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) L.thr[c] /= q;
+    }
+    L.kind = E_BEGIN; /* field at p is still valid */
+}
+
 /* Everything that is not a leapfrog step.  Runs until the lane is steppable again or dead.
  * DIELECTRIC selects the container surface: false = index-matched null surface, true = hdielectric. */
-template <bool DIELECTRIC, bool TRANSIENT, bool SDFSHAPE>
+template <bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE>
 __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, unsigned *st) {
     const MediumDev &M = P.M;
     const float zero[3] = {0.f, 0.f, 0.f};
@@ -345,7 +364,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             L.pixel = pixel;
             L.sample = (unsigned) P.sampleBegin + k * (unsigned) P.sampleStride;
             L.rng.init(P.seed, (unsigned long long) pixel * (unsigned long long) P.sppTotal + L.sample, 0u);
-            if (P.lightMode) {
+            if (EXTRAS && P.lightMode) {
                 /* ---- emitter-side walk: sample the emitter (its stream is keyed like a camera sample's) */
                 float3 o, d;
                 if (P.emitterType == MER_EMITTER_COLLIMATED) { /* collimated.cpp:59-110: delta position and direction, weight = power */
@@ -399,13 +418,13 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             float3 o = f3(P.camO[0], P.camO[1], P.camO[2]);
             float tBox, tQuad;
             bool hitBox = intersect_shape<SDFSHAPE>(M, o, d, tBox), hitQuad = intersect_quad(P, o, d, tQuad);
-            if (hitQuad && (!hitBox || tQuad < tBox)) { finish_sample(P, L, P.quadLe, 1.0f, st, P.calibrated ? 0.0f : tQuad); continue; }
-            if (!hitBox) { finish_sample(P, L, P.env, 0.0f, st); continue; }
+            if (hitQuad && (!hitBox || tQuad < tBox)) { finish_sample<EXTRAS>(P, L, P.quadLe, 1.0f, st, (EXTRAS && P.calibrated) ? 0.0f : tQuad); continue; }
+            if (!hitBox) { finish_sample<EXTRAS>(P, L, P.env, 0.0f, st); continue; }
             L.depth = 1;
-            if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
+            if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
             if (!DIELECTRIC) L.depth = 2; /* index-matched container surface, volpath.cpp:287-296 */
             L.etaPath = 1.0f;
-            L.opl = P.calibrated ? 0.0f : tBox; /* bdpt_proc.cpp:163-171 */
+            L.opl = (EXTRAS && P.calibrated) ? 0.0f : tBox; /* bdpt_proc.cpp:163-171 */
             L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
             L.v = d;
             L.thr[0] = L.thr[1] = L.thr[2] = 1.0f;
@@ -416,7 +435,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             L.kind = K_ENTRY;
         } else if (L.kind == E_BEGIN) {
             /* ---- Medium::sampleDistance prologue, heterogeneousrefractive.cpp:402-475; L.v = unit direction */
-            if (!rif_inside_limits(M.rif, L.p)) { finish_sample(P, L, zero, 1.0f, st); continue; }
+            if (!rif_inside_limits(M.rif, L.p)) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
             L.refStart = L.n;
             L.v = f3(L.v.x * L.n, L.v.y * L.n, L.v.z * L.n);
             float dist;
@@ -442,7 +461,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             L.rng.next(); /* the BSDF sample is a Point2 */
             float3 dOut;
             float w, es;
-            const bool transmitted = hdielectric_sample(L.v, N, L.n, u, !P.lightMode, dOut, w, es);
+            const bool transmitted = hdielectric_sample(L.v, N, L.n, u, !(EXTRAS && P.lightMode), dOut, w, es);
 #pragma unroll
             for (int c = 0; c < 3; c++) L.thr[c] *= w;
             L.etaPath *= es;
@@ -452,15 +471,15 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             if (!inside) { /* rayIntersectAndLookForEmitter with a delta BSDF: MIS weight 1, volpath.cpp:300-320 */
                 float tq;
                 const bool hitsQuad = intersect_quad(P, L.p, dOut, tq);
-                const float *Le = hitsQuad ? ((L.flags & FLAG_COVERED) ? zero : P.quadLe) : P.env;
+                const float *Le = hitsQuad ? ((EXTRAS && (L.flags & FLAG_COVERED)) ? zero : P.quadLe) : P.env;
                 float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
-                finish_sample(P, L, rad, 1.0f, st, hitsQuad ? L.opl + tq : INFINITY);
+                finish_sample<EXTRAS>(P, L, rad, 1.0f, st, hitsQuad ? L.opl + tq : INFINITY);
                 continue;
             }
             L.flags &= ~FLAG_COVERED; /* an internal reflection starts a chain no direct connection accounts for */
             if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
                 float q = fminf(fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2])) * L.etaPath * L.etaPath, 0.95f);
-                if (L.rng.next() >= q) { finish_sample(P, L, zero, 1.0f, st); continue; }
+                if (L.rng.next() >= q) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
 #pragma unroll
                 for (int c = 0; c < 3; c++) L.thr[c] /= q;
             }
@@ -469,28 +488,18 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             /* ---- scattering vertex: L.v = arrival velocity, throughput already carries the edge */
             const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
             const float3 wi = f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv);
-            if (P.nee) {
+            if (EXTRAS && P.nee) {
                 if (P.maxDepth == -1 || L.depth + 1 < P.maxDepth) {
                     const unsigned slot = atomicAdd(P.neeCount, 1u);
                     if (slot >= P.neeCap) { L.flags |= FLAG_PARKED; break; } /* the host clamps the count; retried next pass */
                     P.neeQ0[slot] = make_float4(L.p.x, L.p.y, L.p.z, wi.x);
                     P.neeQ1[slot] = make_float4(wi.y, wi.z, L.thr[0], L.thr[1]);
                     P.neeQ2[slot] = make_uint4(__float_as_uint(L.thr[2]), (unsigned) L.depth, L.pixel, L.sample);
-                    if (TRANSIENT) P.neeQ3[slot] = L.opl;
+                    if (EXTRAS) P.neeQ3[slot] = L.opl;
                 }
                 L.flags |= FLAG_COVERED;
             }
-            float u1 = L.rng.next(), u2 = L.rng.next();
-            L.v = hg_sample_dev(M.g, wi, u1, u2);
-            if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
-                float q = fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2]));
-                if (DIELECTRIC) q *= L.etaPath * L.etaPath;
-                q = fminf(q, 0.95f);
-                if (L.rng.next() >= q) { finish_sample(P, L, zero, 1.0f, st); continue; }
-#pragma unroll
-                for (int c = 0; c < 3; c++) L.thr[c] /= q;
-            }
-            L.kind = E_BEGIN; /* field at p is still valid */
+            scatter_and_roulette<DIELECTRIC, EXTRAS>(P, L, wi, st);
         } else {
             /* ---- end of a path edge */
             bool scatter = false;
@@ -511,7 +520,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                         continue;
                     }
                 } else {
-                    if (!(L.flags & FLAG_MOVED)) { finish_sample(P, L, zero, 1.0f, st); continue; } /* :517-520 */
+                    if (!(L.flags & FLAG_MOVED)) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; } /* :517-520 */
                     scatter = true;
                     edge_weight(M, L.sd, L.segDist, true, edge);
                 }
@@ -522,19 +531,20 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             float rrs = (float) (1.0 / (double) (L.refStart * L.refStart)); /* :469 */
             rrs *= L.n * L.n;                                                /* :501, refEnd = n(p) */
             if (M.physicalScaling) rrs = 1.0f / rrs;
-            if (P.lightMode) rrs = 1.0f; /* weight[EImportance] carries no refRatioSq, edge.cpp:96-98 */
+            if (EXTRAS && P.lightMode) rrs = 1.0f; /* weight[EImportance] carries no refRatioSq, edge.cpp:96-98 */
             const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
             if (scatter) {
                 st[ST_SCATTER]++;
-                if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
+                if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
 #pragma unroll
                 for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
-                L.kind = E_SCATTER;
+                if (EXTRAS) L.kind = E_SCATTER; /* the vertex may have to wait for a slot of the request queue */
+                else scatter_and_roulette<DIELECTRIC, false>(P, L, f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv), st);
             } else {
                 st[ST_EXIT]++;
 #pragma unroll
                 for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
-                if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample(P, L, zero, 1.0f, st); continue; }
+                if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
                 float3 d = f3(L.v.x * vinv, L.v.y * vinv, L.v.z * vinv);
                 if (DIELECTRIC) { /* move to the surface point and fetch the field there, then E_SURFACE */
                     const float te = SDFSHAPE ? exit_distance_sdf(M, L.p, d) : exit_distance(M, L.p, d);
@@ -548,15 +558,15 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 L.depth++;
                 float tq;
                 const bool hitsQuad = intersect_quad(P, L.p, d, tq);
-                const float *Le = hitsQuad ? ((L.flags & FLAG_COVERED) ? zero : P.quadLe) : P.env;
+                const float *Le = hitsQuad ? ((EXTRAS && (L.flags & FLAG_COVERED)) ? zero : P.quadLe) : P.env;
                 float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
-                finish_sample(P, L, rad, 1.0f, st, hitsQuad ? L.opl + tq : INFINITY);
+                finish_sample<EXTRAS>(P, L, rad, 1.0f, st, hitsQuad ? L.opl + tq : INFINITY);
             }
         }
     }
 }
 
-template <int MODE, bool DIELECTRIC, bool TRANSIENT, bool SDFSHAPE>
+template <int MODE, bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE>
 __global__ void __launch_bounds__(128, MER_RENDER_MIN_BLOCKS)
 k_render_pass(const __grid_constant__ RenderParams P) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -583,7 +593,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.etaPath = 1.0f;
         L.opl = 0.0f;
         L.safe = 0.0f;
-        if (DIELECTRIC || TRANSIENT) { const float4 ex = P.in.q6[tid]; L.etaPath = ex.x; L.opl = ex.y; }
+        if (DIELECTRIC || EXTRAS) { const float4 ex = P.in.q6[tid]; L.etaPath = ex.x; L.opl = ex.y; }
     } else {
         L.p = L.v = L.G = f3(0.f, 0.f, 0.f);
         L.n = 1.0f;
@@ -626,7 +636,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
                 const int kind = L.kind;
                 const float hc = kind == K_FULL ? h : (kind == K_REM ? L.rem : (kind == K_BACKF ? -h : (kind == K_BACKR ? -L.rem : 0.0f)));
                 const float3 pOld = L.p;
-                er_step_fused<MODE>(M.rif, S, L.p, L.v, L.n, L.G, hc, TRANSIENT ? L.opl : oplUnused);
+                er_step_fused<MODE>(M.rif, S, L.p, L.v, L.n, L.G, hc, EXTRAS ? L.opl : oplUnused);
                 const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
                 const bool moved = L.p.x != pOld.x || L.p.y != pOld.y || L.p.z != pOld.z;
                 int next;
@@ -648,7 +658,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
             }
         } else if (mw != 0u) {
             /* ---------------- event phase: scatter / exit / regenerate for every waiting lane at once */
-            if (waiting) handle_events<DIELECTRIC, TRANSIENT, SDFSHAPE>(P, L, st);
+            if (waiting) handle_events<DIELECTRIC, EXTRAS, SDFSHAPE>(P, L, st);
         } else {
             break; /* budget exhausted (or nobody alive) and nothing waiting */
         }
@@ -668,7 +678,7 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         P.out.q3[o] = make_float4(L.rem, L.sd, __int_as_float(L.stepsLeft), __int_as_float(L.depth));
         P.out.q4[o] = make_uint4((unsigned) L.kind | ((unsigned) L.flags << 8), L.rng.k, L.pixel, L.sample);
         P.out.q5[o] = make_float4(L.n, L.G.x, L.G.y, L.G.z);
-        if (DIELECTRIC || TRANSIENT) P.out.q6[o] = make_float4(L.etaPath, L.opl, 0.f, 0.f);
+        if (DIELECTRIC || EXTRAS) P.out.q6[o] = make_float4(L.etaPath, L.opl, 0.f, 0.f);
     }
 
     /* ---------------- statistics: warp reduce, one atomic per warp and counter */
@@ -729,7 +739,7 @@ __global__ void k_nee_scatter(const __grid_constant__ RenderParams P, unsigned n
  * i.e. the random walk's own exit-edge weights with the change of variables launch direction -> sampled point written
  * with the solver's Jacobian in place of 1 / distance^2.  The splat adds radiance only (filter weight 0): the sample's
  * weight is added once, by the walk. */
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, bool SDFSHAPE>
 __global__ void __launch_bounds__(128, MIN_BLOCKS)
 k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -762,7 +772,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         ds = f3(ds.x * dl, ds.y * dl, ds.z * dl);
         const bool refract = M.boundary == MER_BOUNDARY_HDIELECTRIC;
         merc::ConnectResult C;
-        merc::connect_solve(M, P.neePrecision, P.neeTol2, P.neeRRWeight, P.neeMaxIterations, p1, y, ds, true, refract, P.neeStraightFirst != 0,
+        merc::connect_solve<SDFSHAPE>(M, P.neePrecision, P.neeTol2, P.neeRRWeight, P.neeMaxIterations, p1, y, ds, true, refract, P.neeStraightFirst != 0,
                             nrng, C);
         st[0] = 1u;
         const int steps = C.steps;
@@ -1049,7 +1059,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         P.nIn = nLive;
         MER_CUDA(cudaMemsetAsync(S.nOut, 0, sizeof(unsigned), stream));
         const unsigned blocks = (threads + TPB - 1) / TPB;
-        const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, transient = P.frames > 1;
+        /* `transient` selects the kernels compiled with the extras: transient film, direct connections, light tracing */
+        const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, transient = P.frames > 1 || P.nee || P.lightMode;
 #define MER_PASS(MODE_, D_, T_, S_) MER_LAUNCH((k_render_pass<MODE_, D_, T_, S_>), blocks, TPB, 0, stream, P)
         if (m->dev.shapeType == MER_SHAPE_SDF) { /* tricubic only (checked above) */
             if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true, true); else MER_PASS(MER_RIF_TRICUBIC, true, false, true); }
@@ -1083,8 +1094,9 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
                     MER_LAUNCH(k_nee_scatter, (nReq + 255u) / 256u, 256, 0, stream, P, nReq);
                     launches += 3;
                 }
-                if (neeMinBlocks >= 3) MER_LAUNCH(k_nee<3>, (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
-                else MER_LAUNCH(k_nee<2>, (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
+                if (m->dev.shapeType == MER_SHAPE_SDF) MER_LAUNCH((k_nee<2, true>), (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
+                else if (neeMinBlocks >= 3) MER_LAUNCH((k_nee<3, false>), (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
+                else MER_LAUNCH((k_nee<2, false>), (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
                 launches++;
                 MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
             }
