@@ -89,9 +89,9 @@ k_connect(const __grid_constant__ MediumDev M, int precision, float tol2, float 
         rng.init(seed, (unsigned long long) i, 0u);
         ConnectResult R;
         if (M.shapeType == MER_SHAPE_SDF)
-            connect_solve<true>(M, precision, tol2, rrweight, maxIterations, p1, p2, din, isSensor != 0, M.boundary == MER_BOUNDARY_HDIELECTRIC, straightFirst != 0, rng, R);
+            connect_solve<true, true>(M, precision, tol2, rrweight, maxIterations, p1, p2, din, isSensor != 0, M.boundary == MER_BOUNDARY_HDIELECTRIC, straightFirst != 0, rng, R);
         else
-            connect_solve<false>(M, precision, tol2, rrweight, maxIterations, p1, p2, din, isSensor != 0, M.boundary == MER_BOUNDARY_HDIELECTRIC, straightFirst != 0, rng, R);
+            connect_solve<false, true>(M, precision, tol2, rrweight, maxIterations, p1, p2, din, isSensor != 0, M.boundary == MER_BOUNDARY_HDIELECTRIC, straightFirst != 0, rng, R);
         const bool success = R.success;
         const float weight = R.weight, opl = R.opl, dist = R.dist;
         const float3 dir = R.dir, rev = R.rev;

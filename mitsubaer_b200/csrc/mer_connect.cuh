@@ -175,7 +175,7 @@ static __device__ float3 container_normal(const MediumDev &M, float3 p) {
  * extension), 2 degenerate (error = p1 - p2, Jacobian 0), 3 left the object by total internal reflection.  `refract` = the reference's behaviour (Snell to exterior
  * index 1, i.e. an hdielectric container); false = index-matched container: the velocity crosses unchanged. */
 template <bool SDFSHAPE>
-static __device__ int compute_fdf(const MediumDev &M, int precision, float3 vi, float3 p1, float3 p2, bool isSensorSample,
+static __device__ __forceinline__ int compute_fdf(const MediumDev &M, int precision, float3 vi, float3 p1, float3 p2, bool isSensorSample,
                            bool refract, float3 &err, M3 &derr, int &count) {
     M3 A = m3_zero(), B = m3_identity();
     derr = m3_zero();
@@ -281,8 +281,10 @@ struct ExitInfo { /* how a connection left the container (next-event estimation 
     float cosI; /* cosine between the interior direction and the outward normal */
 };
 
-template <bool SDFSHAPE>
-static __device__ bool compute_path_lengths(const MediumDev &M, int precision, float tol2, float3 p1, float3 p2, float3 dirToP2, float3 &revDir,
+/* WANT_OPL = false skips the midpoint-rule optical length (a whole uncached 64-tap lookup per step of the re-trace) for
+ * callers that only need the geometric length, the arrival direction and the boundary terms */
+template <bool SDFSHAPE, bool WANT_OPL>
+static __device__ __forceinline__ bool compute_path_lengths(const MediumDev &M, int precision, float tol2, float3 p1, float3 p2, float3 dirToP2, float3 &revDir,
                                      bool isSensorSample, bool refract, float &opl, float &dist, ExitInfo &ex) {
     dist = 0.0f;
     opl = 0.0f;
@@ -309,9 +311,9 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
                 h = h / 2;
                 er_step_fused<MER_RIF_TRICUBIC, false>(M.rif, S, p, v, n, G, h, dummy);
                 if ((SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p))) {
-                    float nm;
+                    float nm = 0.0f;
                     float3 gm;
-                    rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
+                    if (WANT_OPL) rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
                     dist += h;
                     opl += h * nm;
                     if (M.hasGrid) ex.tau += h * (grid_lookup(M.grid, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z))) * M.densityScale);
@@ -350,9 +352,9 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
                 er_step_fused<MER_RIF_TRICUBIC, false>(M.rif, S, p, v, n, G, h, dummy);
                 signNew = signbit(dot3(p - p2, v));
                 if (signNew == signOld) {
-                    float nm;
+                    float nm = 0.0f;
                     float3 gm;
-                    rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
+                    if (WANT_OPL) rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
                     dist += h;
                     opl += h * nm;
                     if (M.hasGrid) ex.tau += h * (grid_lookup(M.grid, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z))) * M.densityScale);
@@ -361,9 +363,9 @@ static __device__ bool compute_path_lengths(const MediumDev &M, int precision, f
             }
             break;
         } else {
-            float nm;
+            float nm = 0.0f;
             float3 gm;
-            rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
+            if (WANT_OPL) rif_lookup<MER_RIF_TRICUBIC>(M.rif, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z)), nm, gm);
             dist += h;
             opl += h * nm;
             if (M.hasGrid) ex.tau += h * (grid_lookup(M.grid, f3(0.5f * (p.x + oldp.x), 0.5f * (p.y + oldp.y), 0.5f * (p.z + oldp.z))) * M.densityScale);
@@ -398,8 +400,8 @@ struct ConnectResult {
     float xnorm; /* ... and |x|: computefdf renormalises x to n(p1), so J scales like n(p1) / |x| */
 };
 
-template <bool SDFSHAPE>
-static __device__ void connect_solve(const MediumDev &M, int precision, float tol2, float rrweight, int maxIterations, float3 p1, float3 p2,
+template <bool SDFSHAPE, bool WANT_OPL>
+static __device__ __forceinline__ void connect_solve(const MediumDev &M, int precision, float tol2, float rrweight, int maxIterations, float3 p1, float3 p2,
                                      float3 din, bool isSensor, bool refract, bool straightFirst, PathRng &rng, ConnectResult &R) {
     R.success = false;
     R.weight = 1.0f;
@@ -491,7 +493,7 @@ static __device__ void connect_solve(const MediumDev &M, int precision, float to
     R.xnorm = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
     const float xl = 1.0f / R.xnorm;
     R.dir = f3((x[0] * xl) * RIFp, (x[1] * xl) * RIFp, (x[2] * xl) * RIFp);
-    if (converged && compute_path_lengths<SDFSHAPE>(M, precision, tol2, p1, p2, R.dir, R.rev, isSensor, refract, R.opl, R.dist, R.exit)) R.success = true;
+    if (converged && compute_path_lengths<SDFSHAPE, WANT_OPL>(M, precision, tol2, p1, p2, R.dir, R.rev, isSensor, refract, R.opl, R.dist, R.exit)) R.success = true;
 }
 
 /* |d r_perp / d omega| of a solved connection: the area, in the plane perpendicular to the arriving ray, swept per unit

@@ -739,8 +739,8 @@ __global__ void k_nee_scatter(const __grid_constant__ RenderParams P, unsigned n
  * i.e. the random walk's own exit-edge weights with the change of variables launch direction -> sampled point written
  * with the solver's Jacobian in place of 1 / distance^2.  The splat adds radiance only (filter weight 0): the sample's
  * weight is added once, by the walk. */
-template <int MIN_BLOCKS, bool SDFSHAPE>
-__global__ void __launch_bounds__(128, MIN_BLOCKS)
+template <bool WANT_OPL, bool SDFSHAPE>
+__global__ void __launch_bounds__(128, 2)
 k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -753,7 +753,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         const float3 p1 = f3(a.x, a.y, a.z), wi = f3(a.w, b.x, b.y);
         const float thr[3] = {b.z, b.w, __uint_as_float(c.x)};
         const unsigned depth = c.y, pixel = c.z, sample = c.w;
-        const float oplVertex = P.frames > 1 ? P.neeQ3[i] : 0.0f;
+        const float oplVertex = WANT_OPL ? P.neeQ3[i] : 0.0f;
         PathRng nrng;
         nrng.init(P.seed ^ MER_NEE_SALT, (unsigned long long) pixel * (unsigned long long) P.sppTotal + sample, depth * 256u);
         float3 y, Nq = f3(0.f, 0.f, 1.f);
@@ -772,7 +772,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         ds = f3(ds.x * dl, ds.y * dl, ds.z * dl);
         const bool refract = M.boundary == MER_BOUNDARY_HDIELECTRIC;
         merc::ConnectResult C;
-        merc::connect_solve<SDFSHAPE>(M, P.neePrecision, P.neeTol2, P.neeRRWeight, P.neeMaxIterations, p1, y, ds, true, refract, P.neeStraightFirst != 0,
+        merc::connect_solve<SDFSHAPE, WANT_OPL>(M, P.neePrecision, P.neeTol2, P.neeRRWeight, P.neeMaxIterations, p1, y, ds, true, refract, P.neeStraightFirst != 0,
                             nrng, C);
         st[0] = 1u;
         const int steps = C.steps;
@@ -808,7 +808,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                             rad[k] = thr[k] * phase * T * C.weight * bf * g;
                         }
                         /* bdpt_proc.cpp:352-357: the sensor connection's length is left out of a calibrated transient */
-                        const int frame = path_frame(P, oplVertex + (P.calibrated ? 0.0f : C.opl));
+                        const int frame = WANT_OPL ? path_frame(P, oplVertex + (P.calibrated ? 0.0f : C.opl)) : 0;
                         if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, nonfinite);
                     }
                 }
@@ -833,7 +833,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                 float sx, sy;
                 sample_position(P, pixel, sample, sx, sy);
                 /* the connection's optical length: curved part (midpoint rule, :941-1030) + exterior segment */
-                const int frame = path_frame(P, oplVertex + C.opl);
+                const int frame = WANT_OPL ? path_frame(P, oplVertex + C.opl) : 0;
                 if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, nonfinite);
             }
         }
@@ -1047,8 +1047,6 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
 
     unsigned nLive = 0;
     unsigned long long started = 0, passes = 0, launches = 0;
-    int neeMinBlocks = 2;
-    if (const char *e = getenv("MER_NEE_MIN_BLOCKS")) neeMinBlocks = atoi(e); /* tuning knob */
     MER_CUDA(cudaEventRecord(S.ev0, stream));
     while (true) {
         const bool fresh = started < P.totalSamples;
@@ -1094,10 +1092,10 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
                     MER_LAUNCH(k_nee_scatter, (nReq + 255u) / 256u, 256, 0, stream, P, nReq);
                     launches += 3;
                 }
-                if (m->dev.shapeType == MER_SHAPE_SDF) MER_LAUNCH((k_nee<2, true>), (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
-                else if (neeMinBlocks >= 3) MER_LAUNCH((k_nee<3, false>), (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
-                else MER_LAUNCH((k_nee<2, false>), (nReq + TPB - 1) / TPB, TPB, 0, stream, Pn, nReq);
-                launches++;
+                const unsigned nb = (nReq + TPB - 1) / TPB;
+                const bool sdfShape = m->dev.shapeType == MER_SHAPE_SDF, wantOpl = P.frames > 1; /* optical length: transient film only */
+                if (sdfShape) { if (wantOpl) MER_LAUNCH((k_nee<true, true>), nb, TPB, 0, stream, Pn, nReq); else MER_LAUNCH((k_nee<false, true>), nb, TPB, 0, stream, Pn, nReq); }
+                else { if (wantOpl) MER_LAUNCH((k_nee<true, false>), nb, TPB, 0, stream, Pn, nReq); else MER_LAUNCH((k_nee<false, false>), nb, TPB, 0, stream, Pn, nReq); }
                 MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
             }
         }
