@@ -969,7 +969,11 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.minBound = r->min_bound;
     P.binWidth = r->bin_width;
     P.calibrated = r->calibrated_transient ? 1 : 0;
-    if (P.frames > 1) MER_REQUIRE(r->bin_width > 0.0f, "transient film: bin_width must be positive");
+    if (P.frames > 1) {
+        MER_REQUIRE(r->bin_width > 0.0f, "transient film: bin_width must be positive");
+        MER_REQUIRE((double) r->width * r->height * (3.0 * P.frames + 2.0) * sizeof(float) <= 64.0 * (double) (1ull << 30),
+                    "transient film: width * height * (3 * frames + 2) floats exceed 64 GiB");
+    }
     P.nee = (r->direct_connections || r->light_tracing) ? 1 : 0;
     P.lightMode = r->light_tracing ? 1 : 0;
     P.emitterType = r->emitter_type;

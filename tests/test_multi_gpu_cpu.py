@@ -45,10 +45,23 @@ def _worker(rank, world, port, out_dir):
     assert stats["samples"] == 24 * 16 * mdist.local_spp(6, rank, world)
     total = mdist.reduce_stats(stats)
     assert total["samples"] == 24 * 16 * 6
+    # the widened path shards the same way: light paths + transient frames, each rank adding its share of the unit weight
+    scene2 = dict(scene_dict(16, 16, 5, rfilter="box"), fov=30.0, envRadiance=0.0, transient=dict(minBound=2.0, maxBound=18.0, binWidth=2.0))
+    film2 = torch.zeros(16, 16, 3 * 8 + 2)
+
+    def render_light(begin, stride):
+        f, st = orc.render(omed, oracle_render_desc(scene2, sample_begin=begin, sample_stride=stride, light_tracing=True, props=props), nthreads=2)
+        film2.add_(torch.from_numpy(f))
+        return st.as_dict()
+
+    stats2 = mdist.reduce_stats(mdist.render_sharded(render_light, film2, dst=0))
     if rank == 0:
         full, st = orc.render(omed, oracle_render_desc(scene), nthreads=2)
         assert total["ray_steps"] == st.ray_steps
         assert np.allclose(film.numpy(), full, rtol=1e-5, atol=1e-6)
+        full2, st2 = orc.render(omed, oracle_render_desc(scene2, light_tracing=True, props=props), nthreads=2)
+        assert stats2["connections"] == st2.connections and stats2["samples"] == 16 * 16 * 5
+        assert np.allclose(film2.numpy()[..., -1], 1.0) and np.allclose(film2.numpy(), full2, rtol=1e-5, atol=1e-6 * np.abs(full2).max() + 1e-7)
         open(os.path.join(out_dir, "ok"), "w").write("ok")
     dist.barrier()
     dist.destroy_process_group()
