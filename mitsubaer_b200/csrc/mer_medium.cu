@@ -17,7 +17,9 @@
 #include "mer_internal.h"
 
 /* ------------------------------------------------------------------ a8: trace() */
-template <int MODE>
+/* SDFSHAPE: the container is the signed-distance grid (MER_SHAPE_SDF); the test is a full lookup per step here (the batch
+ * steppers are the parity surface, the renderer has the lazy version) */
+template <int MODE, bool SDFSHAPE = false>
 __device__ __forceinline__ bool trace_dev(const MediumDev &M, StencilCache<MODE> &S, float3 &p, float3 &v, float &n, float3 &G, float dist,
                                           float &distSurf, float &opl, int &count) {
     int steps;
@@ -28,7 +30,7 @@ __device__ __forceinline__ bool trace_dev(const MediumDev &M, StencilCache<MODE>
     for (int i = 0; i < steps; i++) {
         er_step_fused<MODE>(M.rif, S, p, v, n, G, h, opl);
         count++;
-        if (!inside_shape(M, p)) {
+        if (!(SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p))) {
             er_step_fused<MODE>(M.rif, S, p, v, n, G, -h, opl); /* step back, :679 */
             count++;
             return false;
@@ -37,7 +39,7 @@ __device__ __forceinline__ bool trace_dev(const MediumDev &M, StencilCache<MODE>
     }
     er_step_fused<MODE>(M.rif, S, p, v, n, G, rem, opl);
     count++;
-    if (!inside_shape(M, p)) {
+    if (!(SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p))) {
         er_step_fused<MODE>(M.rif, S, p, v, n, G, -rem, opl);
         count++;
         return false;
@@ -47,7 +49,7 @@ __device__ __forceinline__ bool trace_dev(const MediumDev &M, StencilCache<MODE>
 }
 
 /* ------------------------------------------------------------------ a9: traceTillBoundary() */
-template <int MODE>
+template <int MODE, bool SDFSHAPE = false>
 __device__ __forceinline__ void trace_till_boundary_dev(const MediumDev &M, StencilCache<MODE> &S, float3 &p, float3 &v, float &n, float3 &G,
                                                         float &distSurf, float &opl, int &count) {
     distSurf = 0.0f;
@@ -55,7 +57,7 @@ __device__ __forceinline__ void trace_till_boundary_dev(const MediumDev &M, Sten
     for (int i = 0; i < 100000; i++) { /* maxsteps 1e5, :746 */
         er_step_fused<MODE>(M.rif, S, p, v, n, G, h, opl);
         count++;
-        if (inside_shape(M, p)) {
+        if ((SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p))) {
             distSurf += h;
         } else {
             er_step_fused<MODE>(M.rif, S, p, v, n, G, -h, opl);
@@ -89,7 +91,7 @@ __device__ __forceinline__ void aggressive_trace_dev(const MediumDev &M, Stencil
  * Per-ray results are identical to trace() / traceTillBoundary() (:671-691, :742-776). */
 enum TraceKind : int { T_FULL = 0, T_REM = 1, T_BACKF = 2, T_BACKR = 3, T_ENTRY = 4, T_IDLE = 5 };
 
-template <int MODE, bool TILL_BOUNDARY>
+template <int MODE, bool TILL_BOUNDARY, bool SDFSHAPE = false>
 __global__ void __launch_bounds__(128, 3)
 k_trace(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P, float *__restrict__ V,
         const float *__restrict__ dist, uint8_t *__restrict__ success, float *__restrict__ distSurfOut,
@@ -122,7 +124,7 @@ k_trace(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P
             /* measured (C4 sweep): speculation pays in the packed mode (+16 %) but costs the compute-bound
              * tricubic stepper 3-14 % */
             er_step_fused<MODE, MODE == MER_RIF_TRILINEAR_PACKED>(M.rif, S, p, v, n, G, hc, opl);
-            const bool inside = inside_shape(M, p);
+            const bool inside = SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p);
             bool done = false, ok = false;
             if (k == T_ENTRY) {
                 opl = 0.0f;
@@ -167,7 +169,7 @@ struct SampleDistanceOut {
     int32_t *nsteps;
 };
 
-template <int MODE>
+template <int MODE, bool SDFSHAPE = false>
 __global__ void __launch_bounds__(128)
 k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float *__restrict__ RO,
                   const float *__restrict__ RD, const float *__restrict__ mintIn, const float *__restrict__ xi,
@@ -200,7 +202,7 @@ k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float
             v = f3(v.x * refStart, v.y * refStart, v.z * refStart);
             if (isfinite(sampledDistance)) {
                 if (!M.aggressive) {
-                    success = trace_dev<MODE>(M, S, p, v, n, G, sampledDistance, distSurf, opl, count);
+                    success = trace_dev<MODE, SDFSHAPE>(M, S, p, v, n, G, sampledDistance, distSurf, opl, count);
                 } else { /* :476-493 */
                     float distLeft = sampledDistance, distTraced = 0.0f;
                     while (distLeft > MER_EPSILON) {
@@ -214,11 +216,11 @@ k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float
                         distLeft = __fsub_rn(distLeft, traceDist);
                         distTraced = __fadd_rn(distTraced, traceDist);
                     }
-                    success = trace_dev<MODE>(M, S, p, v, n, G, distLeft, distSurf, opl, count);
+                    success = trace_dev<MODE, SDFSHAPE>(M, S, p, v, n, G, distLeft, distSurf, opl, count);
                     distSurf = __fadd_rn(distSurf, distTraced);
                 }
             } else {
-                trace_till_boundary_dev<MODE>(M, S, p, v, n, G, distSurf, opl, count);
+                trace_till_boundary_dev<MODE, SDFSHAPE>(M, S, p, v, n, G, distSurf, opl, count);
                 success = false;
             }
             refRatioSq *= n * n; /* refEnd = value at the final p, carried by the fused stepper */
@@ -441,12 +443,15 @@ int mer_medium_resolved(const mer_medium *m, mer_medium_desc *out, float *sampli
 int mer_medium_trace_device(const mer_medium *m, size_t n, float *p_dev, float *v_dev, const float *dist_dev,
                             uint8_t *success_dev, float *dist_surf_dev, float *opl_dev, int32_t *nsteps_dev,
                             void *stream) {
-    if (m && m->dev.shapeType == MER_SHAPE_SDF)
-        return mer::fail(MER_ERR_UNSUPPORTED, "the batch steppers hold box and sphere containers; shape type SDF is carried by mer_render and the connection entry points");
     MER_REQUIRE(m && (n == 0 || (p_dev && v_dev && dist_dev)), "null argument");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(m->device);
-    if (m->rif->mode == MER_RIF_TRICUBIC)
+    if (m->dev.shapeType == MER_SHAPE_SDF) {
+        MER_REQUIRE(m->dev.hasSdf, "shape type SDF needs the sdf volume (mer_medium_set_sdf)");
+        if (m->rif->mode != MER_RIF_TRICUBIC) return mer::fail(MER_ERR_UNSUPPORTED, "shape type SDF is built for the tricubic RIF mode");
+        MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, false, true>), trace_grid(k_trace<MER_RIF_TRICUBIC, false, true>, n), 128, 0, (cudaStream_t) stream, m->dev, n,
+                   p_dev, v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev);
+    } else if (m->rif->mode == MER_RIF_TRICUBIC)
         MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, false>), trace_grid(k_trace<MER_RIF_TRICUBIC, false>, n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev, v_dev,
                    dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev);
     else
@@ -474,15 +479,18 @@ int mer_medium_trace_batch(const mer_medium *m, size_t n, float *p, float *v, co
 
 int mer_medium_trace_till_boundary_batch(const mer_medium *m, size_t n, float *p, float *v, float *dist_surf_out,
                                          float *opl_out, int32_t *nsteps_out) {
-    if (m && m->dev.shapeType == MER_SHAPE_SDF)
-        return mer::fail(MER_ERR_UNSUPPORTED, "the batch steppers hold box and sphere containers; shape type SDF is carried by mer_render and the connection entry points");
     MER_REQUIRE(m && (n == 0 || (p && v)), "null argument");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(m->device);
     DevBuf dp, dv, dds, dopl, dns;
     UP(dp, p, n * 12); UP(dv, v, n * 12);
     UP(dds, (void *) nullptr, n * 4); UP(dopl, (void *) nullptr, n * 4); UP(dns, (void *) nullptr, n * 4);
-    if (m->rif->mode == MER_RIF_TRICUBIC)
+    if (m->dev.shapeType == MER_SHAPE_SDF) {
+        MER_REQUIRE(m->dev.hasSdf, "shape type SDF needs the sdf volume (mer_medium_set_sdf)");
+        if (m->rif->mode != MER_RIF_TRICUBIC) return mer::fail(MER_ERR_UNSUPPORTED, "shape type SDF is built for the tricubic RIF mode");
+        MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, true, true>), trace_grid(k_trace<MER_RIF_TRICUBIC, true, true>, n), 128, 0, 0, m->dev, n, dp.as<float>(),
+                   dv.as<float>(), (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
+    } else if (m->rif->mode == MER_RIF_TRICUBIC)
         MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, true>), trace_grid(k_trace<MER_RIF_TRICUBIC, true>, n), 128, 0, 0, m->dev, n, dp.as<float>(), dv.as<float>(),
                    (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
     else
@@ -496,8 +504,6 @@ int mer_medium_trace_till_boundary_batch(const mer_medium *m, size_t n, float *p
 
 int mer_medium_sample_distance_batch(const mer_medium *m, size_t n, const float *ray_o, const float *ray_d,
                                      const float *ray_mint, const float *xi, mer_medium_sampling_records *rec) {
-    if (m && m->dev.shapeType == MER_SHAPE_SDF)
-        return mer::fail(MER_ERR_UNSUPPORTED, "the batch steppers hold box and sphere containers; shape type SDF is carried by mer_render and the connection entry points");
     MER_REQUIRE(m && rec && (n == 0 || (ray_o && ray_d && xi)), "null argument");
     if (m->grid)
         return mer::fail(MER_ERR_UNSUPPORTED,
@@ -517,7 +523,12 @@ int mer_medium_sample_distance_batch(const mer_medium *m, size_t n, const float 
     o.pdfSuccess = dps.as<float>(); o.pdfFailure = dpf.as<float>(); o.sigmaS = dss.as<float>();
     o.nsteps = dns.as<int32_t>();
     const float *mintDev = ray_mint ? dmint.as<float>() : nullptr;
-    if (m->rif->mode == MER_RIF_TRICUBIC)
+    if (m->dev.shapeType == MER_SHAPE_SDF) {
+        MER_REQUIRE(m->dev.hasSdf, "shape type SDF needs the sdf volume (mer_medium_set_sdf)");
+        if (m->rif->mode != MER_RIF_TRICUBIC) return mer::fail(MER_ERR_UNSUPPORTED, "shape type SDF is built for the tricubic RIF mode");
+        MER_LAUNCH((k_sample_distance<MER_RIF_TRICUBIC, true>), trace_grid(k_sample_distance<MER_RIF_TRICUBIC, true>, n), 128, 0, 0, m->dev, n, dro.as<float>(),
+                   drd.as<float>(), mintDev, dxi.as<float>(), o);
+    } else if (m->rif->mode == MER_RIF_TRICUBIC)
         MER_LAUNCH(k_sample_distance<MER_RIF_TRICUBIC>, trace_grid(k_sample_distance<MER_RIF_TRICUBIC>, n), 128, 0, 0, m->dev, n, dro.as<float>(),
                    drd.as<float>(), mintDev, dxi.as<float>(), o);
     else

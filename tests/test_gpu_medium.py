@@ -524,3 +524,39 @@ def test_curved_direct_connections(oracle32, oracle64):
     # passing within sqrt(2 tol2) of p2 bounds the direction error by ~1.4e-3 / |p2 - p1|
     dir_err = np.abs(out["dir_to_p2"][s] / 1.4 - (seg / np.linalg.norm(seg, axis=1, keepdims=True))[s]).max(axis=1)
     assert (dir_err * np.linalg.norm(seg, axis=1)[s]).max() < 2.5e-3
+
+
+def test_batch_steppers_with_sdf_container(oracle32):
+    """trace / traceTillBoundary / sampleDistance with the container given by a signed-distance grid: like the
+    oracle with the same shape type, and like the analytic sphere the grid was sampled from"""
+    res = 40
+    data, lo, hi = make_field("radial", res)
+    sdf_data = mer.fields.sphere_sdf((res,) * 3, lo, hi, radius=0.8).astype(np.float32)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    sdf = mer.SplineDataSource(data=sdf_data, min=lo, max=hi)
+    props = medium_props(stepsize=5e-3, strategy="single", sigmaS=2.0, sigmaA=0.5, shape=("sdf", BOX_MIN, BOX_MAX))
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("sdf", sdf).configure()
+    ball = mer.HeterogeneousRefractiveMedium(dict(props, shape=("sphere", (0.0, 0.0, 0.0), 0.8))).addChild("rif", rif).configure()
+    d = volume_desc((res,) * 3, lo, hi)
+    omed = oracle32.medium_create(oracle_medium_desc(props), oracle32.rif_create(d, data))
+    oracle32.medium_set_sdf(omed, oracle32.rif_create(d, sdf_data), False)
+    rng = np.random.default_rng(5)
+    n = 4096
+    p0 = rng.normal(size=(n, 3))
+    p0 = (p0 / np.linalg.norm(p0, axis=1, keepdims=True) * rng.uniform(0, 0.75, (n, 1))).astype(np.float32)
+    d0 = rng.normal(size=(n, 3))
+    d0 = (d0 / np.linalg.norm(d0, axis=1, keepdims=True)).astype(np.float32)
+    v0 = d0 * rif.value(p0)[:, None]
+    dist = rng.uniform(0.05, 1.5, n).astype(np.float32)
+    got, ref, ana = med.trace(p0, v0, dist), oracle32.trace(omed, p0, v0, dist), ball.trace(p0, v0, dist)
+    same = (got["success"] == ref["success"]) & (got["nsteps"] == ref["nsteps"])
+    assert same.mean() > 0.995 and 0.2 < got["success"].mean() < 0.9
+    assert np.max(np.abs(got["p"][same] - ref["p"][same])) <= 2e-5
+    like = (got["success"] == ana["success"]) & (np.abs(got["nsteps"] - ana["nsteps"]) <= 1)
+    assert like.mean() > 0.99  # the zero set of the spline is the sphere to ~1e-4
+    tb, tb_ref = med.traceTillBoundary(p0, v0), oracle32.trace_till_boundary(omed, p0, v0)
+    ok = tb["nsteps"] == tb_ref["nsteps"]
+    assert ok.mean() > 0.995 and np.max(np.abs(tb["dist_surf"][ok] - tb_ref["dist_surf"][ok])) <= 1e-4
+    xi = rng.random((n, 2)).astype(np.float32)
+    sd, sd_ref = med.sampleDistance(p0, d0, np.zeros(n, np.float32), xi), oracle32.sample_distance(omed, p0, d0, np.zeros(n, np.float32), xi)
+    assert (sd["success"] == sd_ref["success"]).mean() > 0.995
