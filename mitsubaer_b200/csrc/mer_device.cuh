@@ -269,6 +269,22 @@ __device__ __forceinline__ void stencil_ensure(const RifDev &R, StencilCache<MER
     }
 }
 
+/* sm_100's packed FP32 (fma.rn.f32x2: two FMAs on a 64-bit register pair in ONE issue slot; measured at the scalar FLOP
+ * rate, tools/microbench.cu, so it saves issue slots, not pipe cycles).  The separable contraction is linear, so it can run
+ * on pairs (x-taps {0,1} and {2,3} of a row side by side, which is how the 256-bit stencil loads leave them in registers)
+ * and fold the two halves once at the very end: 7 packed instructions per stencil row instead of 11 scalar ones. */
+/* MEASURED AND REJECTED (default off): k_trace shrinks from 864 to 808 instructions and every parity test passes, but C2
+ * (39.6 vs 40.0-40.7 M samples/s) and the C4 sweep are unchanged: an FFMA2 holds the FMA pipe for two cycles, and the step
+ * body is bound by the pipe plus dependent-issue latency, not by issue slots. */
+#ifndef MER_FFMA2
+#define MER_FFMA2 0
+#endif
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float fold2(f32x2_t a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return lo + hi; }
+
 __device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, StencilCache<MER_RIF_TRICUBIC> &S,
                                                     float &f, float3 &g) {
     const float x = (pv.x - R.xmin[0]) * R.xres[0], y = (pv.y - R.xmin[1]) * R.xres[1],
@@ -279,6 +295,34 @@ __device__ __forceinline__ void rif_tricubic_cached(const RifDev &R, float3 pv, 
     bs_weights(x, fx, wx0, wx1);
     bs_weights(y, fy, wy0, wy1);
     bs_weights(z, fz, wz0, wz1);
+#if MER_FFMA2
+    {
+        const f32x2_t X0a = pk2(wx0[0], wx0[1]), X0b = pk2(wx0[2], wx0[3]), X1a = pk2(wx1[0], wx1[1]), X1b = pk2(wx1[2], wx1[3]);
+        f32x2_t accF = 0ull, accX = 0ull, accY = 0ull, accZ = 0ull; /* (+0, +0) */
+#pragma unroll
+        for (int dz = 0; dz < 4; dz++) {
+            f32x2_t b00 = 0ull, b10 = 0ull, b01 = 0ull;
+#pragma unroll
+            for (int dy = 0; dy < 4; dy++) {
+                const float4 q = S.get(dz * 4 + dy);
+                const f32x2_t qa = pk2(q.x, q.y), qb = pk2(q.z, q.w);
+                const f32x2_t a0 = fma2(qb, X0b, mul2(qa, X0a)), a1 = fma2(qb, X1b, mul2(qa, X1a));
+                const f32x2_t Y0 = pk2(wy0[dy], wy0[dy]), Y1 = pk2(wy1[dy], wy1[dy]);
+                b00 = fma2(a0, Y0, b00);
+                b10 = fma2(a1, Y0, b10);
+                b01 = fma2(a0, Y1, b01);
+            }
+            const f32x2_t Z0 = pk2(wz0[dz], wz0[dz]), Z1 = pk2(wz1[dz], wz1[dz]);
+            accF = fma2(b00, Z0, accF);
+            accX = fma2(b10, Z0, accX);
+            accY = fma2(b01, Z0, accY);
+            accZ = fma2(b00, Z1, accZ);
+        }
+        f = fold2(accF);
+        g = f3(fold2(accX) * R.xres[0], fold2(accY) * R.xres[1], fold2(accZ) * R.xres[2]);
+        return;
+    }
+#endif
     float accF = 0.f, accX = 0.f, accY = 0.f, accZ = 0.f;
 #pragma unroll
     for (int dz = 0; dz < 4; dz++) {
