@@ -146,6 +146,8 @@ public:
     EikonalVolPathIntegrator(const Properties &props) : Integrator(props) {
         m_maxDepth = props.getInteger("maxDepth", -1);
         m_rrDepth = props.getInteger("rrDepth", 5);
+        m_directConnections = props.getBoolean("directConnections", false); /* curved next-event estimation */
+        m_lightTracing = props.getBoolean("lightTracing", false);           /* emitter-side walk + sensor connections */
         if (m_maxDepth == 0 || m_maxDepth < -1)
             Log(EError, "maxDepth must be set to -1 (infinite) or a value greater than zero!");
     }
@@ -164,6 +166,17 @@ public:
         r.fov_deg = static_cast<const PerspectiveCamera *>(sensor)->getXFov();
         r.filter = film->getReconstructionFilter()->getRadius() > 1 ? MER_FILTER_GAUSSIAN : MER_FILTER_BOX;
         r.max_depth = m_maxDepth; r.rr_depth = m_rrDepth;
+        r.direct_connections = m_directConnections ? 1 : 0;
+        r.light_tracing = m_lightTracing ? 1 : 0;
+        /* the fork's transient film (src/librender/film.cpp:56-78): frames, bounds, calibration */
+        if (film->getDecompositionType() == Film::ETransient && film->getFrames() > 1) {
+            r.frames = (int32_t) film->getFrames();
+            r.min_bound = film->getDecompositionMinBound();
+            r.bin_width = film->getDecompositionBinWidth();
+            r.calibrated_transient = film->isCalibratedTransient() ? 1 : 0;
+        }
+        /* emitters: the rectangle area light (quad_*) and the collimated beam (beam_*) are read off scene->getEmitters() the
+         * same way; left out of this stub for brevity */
         if (scene->hasEnvironmentEmitter()) {
             Spectrum L = scene->getEnvironmentEmitter()->evalEnvironment(RayDifferential(Point(0.0f), Vector(0, 0, 1), 0));
             for (int i = 0; i < 3; ++i) r.env_radiance[i] = L[i];
@@ -173,7 +186,8 @@ public:
             if (scene->getMedia()[i]->isheterogeneousrefractive())
                 medium = static_cast<const B200HeterogeneousRefractiveMedium *>(scene->getMedia()[i].get());
         if (!medium) Log(EError, "ervolpath needs a heterogeneousrefractive medium");
-        ref<Bitmap> bitmap = new Bitmap(Bitmap::ESpectrumAlphaWeight, Bitmap::EFloat32, size);
+        ref<Bitmap> bitmap = r.frames > 1 ? new Bitmap(Bitmap::EMultiSpectrumAlphaWeight, Bitmap::EFloat32, size, 3 * r.frames + 2)
+                                          : new Bitmap(Bitmap::ESpectrumAlphaWeight, Bitmap::EFloat32, size);
         mer_render_stats stats;
         MER_CHECK(mer_render(medium->handle(), &r, bitmap->getFloat32Data(), &stats));
         Log(EInfo, "ervolpath: %llu samples, %llu eikonal steps, %.1f ms on the GPU",
@@ -185,6 +199,7 @@ public:
     MTS_DECLARE_CLASS()
 private:
     int m_maxDepth, m_rrDepth;
+    bool m_directConnections, m_lightTracing;
 };
 
 MTS_IMPLEMENT_CLASS(B200SplineDataSource, false, VolumeDataSource)
