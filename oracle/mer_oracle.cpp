@@ -12,6 +12,10 @@
  * so it is pinned only by line-by-line restatement + analytic invariants: PARITY UNPINNED
  * by reference fixtures for those rows, except HG which is pinned statistically by the
  * reference's chi-square test (src/tests/test_chisquare.cpp:508-572).
+ * The "next" rows restated here as well (curved direct connections and their use as next-event
+ * estimation, hdielectric boundary, transient film, light tracing, SDF containers) are UNPINNED too: the reference has
+ * no fixtures for them and its solver is Ceres; they are checked by closed forms (slab reflectance 2R/(1+R), time of
+ * flight through a slab, white furnaces) and by requiring that independent estimators of the same image agree.
  *
  * Every function cites the reference lines it follows (paths relative to the MitsubaER tree).
  * All arithmetic is templated on FLOAT in {float, double}: float is Mitsuba's `Float`,
