@@ -308,13 +308,26 @@ Scene loadScene(const std::string &xmlPath, const std::map<std::string, std::str
         for (auto &c : dec) c = (char) std::tolower((unsigned char) c);
         if (dec != "none" && dec != "transient") logError("The \"decomposition\" parameter must be equal to either \"none\" or \"transient\" on this path");
         const double lo = film->props.getFloat("minBound", 0.0), hi = film->props.getFloat("maxBound", 0.0), bw = film->props.getFloat("binWidth", 1.0);
-        if (film->props.getString("modulation", "none") != "none") logError("continuous-wave modulation (pathlengthsampler.cpp) is not carried by this path");
+        std::string mod = film->props.getString("modulation", "none"); /* PathLengthSampler, src/librender/pathlengthsampler.cpp:6-35 */
+        for (auto &c : mod) c = (char) std::tolower((unsigned char) c);
+        if (mod != "none" && mod != "sine" && mod != "square" && mod != "hamiltonian")
+            logError("modulation \"" + mod + "\": none, sine, square and hamiltonian are carried by this path");
+        if (mod != "none" && dec == "transient") {
+            R.modulation = mod == "sine" ? MER_MODULATION_SINE : mod == "square" ? MER_MODULATION_SQUARE : MER_MODULATION_HAMILTONIAN;
+            R.lambda = (float) film->props.getFloat("lambda", 1.0);
+            R.phase_deg = (float) film->props.getFloat("phase", 0.0);
+            if (!(R.lambda > 0)) logError("modulation: lambda must be positive");
+        } else {
+            film->props.getFloat("lambda", 1.0);
+            film->props.getFloat("phase", 0.0);
+        }
         if (dec == "transient") {
             if (!(bw > 0) || !(hi > lo)) logError("transient film: binWidth must be positive and maxBound > minBound");
             R.frames = (int) std::ceil((hi - lo) / bw);
             R.min_bound = (float) lo;
             R.bin_width = (float) bw;
             R.calibrated_transient = film->props.getBoolean("calibratedTransient", false) ? 1 : 0;
+            if (R.modulation) R.frames = 0; /* a modulated film has one frame, film.cpp:76-78 */
         }
     }
     std::shared_ptr<Generic> rf = film ? film->child("rfilter") : nullptr;

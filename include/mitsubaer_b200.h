@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 7
+#define MER_ABI_VERSION 8
 
 enum mer_status {
     MER_OK = 0,
@@ -334,7 +334,15 @@ typedef struct mer_render_desc {
     int32_t light_tracing;
     int32_t emitter_type;   /* MER_EMITTER_QUAD: the quad above, cosine-weighted, both sides; MER_EMITTER_COLLIMATED */
     float beam_origin[3], beam_direction[3], beam_power[3]; /* <emitter type="collimated">: src/emitters/collimated.cpp:59-110 */
+    /* continuous-wave time-of-flight camera: <film> properties modulation, lambda, phase (degrees) of the fork's
+     * PathLengthSampler (src/librender/pathlengthsampler.cpp:6-35).  With a modulation the film has ONE frame
+     * (film.cpp:76-78) and every contribution is multiplied by correlationFunction(path length) (:66-96, applied at
+     * bdpt_proc.cpp:440-441); frames / min_bound / bin_width are then ignored.  mseq / depthselective codes are not carried. */
+    int32_t modulation;
+    float lambda, phase_deg;
 } mer_render_desc;
+
+enum mer_modulation { MER_MODULATION_NONE = 0, MER_MODULATION_SINE = 1, MER_MODULATION_SQUARE = 2, MER_MODULATION_HAMILTONIAN = 3 };
 
 enum mer_emitter_type { MER_EMITTER_QUAD = 0, MER_EMITTER_COLLIMATED = 1 };
 

@@ -95,6 +95,8 @@ struct RenderParams {
     float filterRadius, filterScale, filterValues[32];
     int frames, channels, calibrated; /* transient film: 3 * frames + 2 channels per pixel (bdpt_wr.cpp:52-56) */
     float minBound, binWidth;
+    int modulation;                   /* continuous-wave ToF: contributions times correlationFunction(path length) */
+    float lambda, phaseShift;         /* phaseShift = phase * lambda / (2 pi), pathlengthsampler.cpp:74 */
     int stepsPerPass, maxWait;
     float *film;
     PathPool in, out;
@@ -234,6 +236,21 @@ __device__ __forceinline__ int path_frame(const RenderParams &P, float len) {
     return (b >= 0.0f && b < (float) P.frames) ? (int) b : -1;
 }
 
+/* PathLengthSampler::correlationFunction, src/librender/pathlengthsampler.cpp:66-96; 1 without a modulation.  An emitter at
+ * infinity (the environment) has no path length: it contributes nothing to a modulated image. */
+__device__ __forceinline__ float path_weight(const RenderParams &P, float len) {
+    if (P.modulation == MER_MODULATION_NONE) return 1.0f;
+    if (!isfinite(len)) return 0.0f;
+    float pl = len + P.phaseShift;
+    if (P.modulation == MER_MODULATION_SINE) return cosf(pl * 6.283185307179586f / P.lambda);
+    if (P.modulation == MER_MODULATION_SQUARE) return 4.0f / P.lambda * (fabsf(fmodf(pl, P.lambda) - P.lambda / 2.0f) - P.lambda / 4.0f);
+    pl = fmodf(pl, P.lambda); /* Hamiltonian code */
+    if (pl < P.lambda / 6.0f) return 6.0f * pl / P.lambda;
+    if (pl < P.lambda / 2.0f) return 1.0f;
+    if (pl < 2.0f * P.lambda / 3.0f) return 1.0f - (pl - P.lambda / 2.0f) * 6.0f / P.lambda;
+    return 0.0f;
+}
+
 __device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha, float wgt, int frame,
                                          unsigned &nonfinite) {
     const float value[5] = {L[0], L[1], L[2], alpha, wgt};
@@ -275,6 +292,13 @@ __device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, co
     if (EXTRAS && P.lightMode) { L.kind = E_NEW; return; } /* a light path that leaves or dies deposits nothing: only its connections do */
     float sx, sy;
     sample_position(P, L.pixel, L.sample, sx, sy);
+    if (EXTRAS && P.modulation) {
+        const float w = path_weight(P, pathLength);
+        const float mod[3] = {rad[0] * w, rad[1] * w, rad[2] * w};
+        film_put(P, sx, sy, mod, alpha, 1.0f, 0, st[ST_NONFINITE]);
+        L.kind = E_NEW;
+        return;
+    }
     film_put(P, sx, sy, rad, alpha, 1.0f, EXTRAS ? path_frame(P, pathLength) : 0, st[ST_NONFINITE]);
     L.kind = E_NEW;
 }
@@ -808,7 +832,13 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                             rad[k] = thr[k] * phase * T * C.weight * bf * g;
                         }
                         /* bdpt_proc.cpp:352-357: the sensor connection's length is left out of a calibrated transient */
-                        const int frame = WANT_OPL ? path_frame(P, oplVertex + (P.calibrated ? 0.0f : C.opl)) : 0;
+                        const float len = oplVertex + (P.calibrated ? 0.0f : C.opl);
+                        if (WANT_OPL && P.modulation) {
+                            const float w = path_weight(P, len);
+#pragma unroll
+                            for (int k = 0; k < 3; k++) rad[k] *= w;
+                        }
+                        const int frame = (WANT_OPL && !P.modulation) ? path_frame(P, len) : 0;
                         if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, nonfinite);
                     }
                 }
@@ -833,7 +863,12 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                 float sx, sy;
                 sample_position(P, pixel, sample, sx, sy);
                 /* the connection's optical length: curved part (midpoint rule, :941-1030) + exterior segment */
-                const int frame = WANT_OPL ? path_frame(P, oplVertex + C.opl) : 0;
+                if (WANT_OPL && P.modulation) {
+                    const float w = path_weight(P, oplVertex + C.opl);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) rad[k] *= w;
+                }
+                const int frame = (WANT_OPL && !P.modulation) ? path_frame(P, oplVertex + C.opl) : 0;
                 if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, nonfinite);
             }
         }
@@ -964,7 +999,12 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.maxWait = 12;
     if (const char *e = getenv("MER_MAX_WAIT")) P.maxWait = atoi(e); /* tuning knob */
     P.film = film_dev;
-    P.frames = r->frames > 1 ? r->frames : 1;
+    MER_REQUIRE(r->modulation >= MER_MODULATION_NONE && r->modulation <= MER_MODULATION_HAMILTONIAN, "unknown modulation");
+    P.modulation = r->modulation;
+    P.lambda = r->lambda;
+    P.phaseShift = (float) ((double) r->phase_deg * M_PI / 180.0) * r->lambda * (float) (0.5 / M_PI);
+    if (P.modulation) MER_REQUIRE(r->lambda > 0.0f, "modulation: lambda must be positive");
+    P.frames = (r->frames > 1 && !P.modulation) ? r->frames : 1; /* one frame under a modulation, film.cpp:76-78 */
     P.channels = 3 * P.frames + 2;
     P.minBound = r->min_bound;
     P.binWidth = r->bin_width;
@@ -1062,7 +1102,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         MER_CUDA(cudaMemsetAsync(S.nOut, 0, sizeof(unsigned), stream));
         const unsigned blocks = (threads + TPB - 1) / TPB;
         /* `transient` selects the kernels compiled with the extras: transient film, direct connections, light tracing */
-        const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, transient = P.frames > 1 || P.nee || P.lightMode;
+        const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, transient = P.frames > 1 || P.modulation || P.nee || P.lightMode;
 #define MER_PASS(MODE_, D_, T_, S_) MER_LAUNCH((k_render_pass<MODE_, D_, T_, S_>), blocks, TPB, 0, stream, P)
         if (m->dev.shapeType == MER_SHAPE_SDF) { /* tricubic only (checked above) */
             if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true, true); else MER_PASS(MER_RIF_TRICUBIC, true, false, true); }
@@ -1097,7 +1137,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
                     launches += 3;
                 }
                 const unsigned nb = (nReq + TPB - 1) / TPB;
-                const bool sdfShape = m->dev.shapeType == MER_SHAPE_SDF, wantOpl = P.frames > 1; /* optical length: transient film only */
+                const bool sdfShape = m->dev.shapeType == MER_SHAPE_SDF, wantOpl = P.frames > 1 || P.modulation; /* optical length: transient / modulated film only */
                 if (sdfShape) { if (wantOpl) MER_LAUNCH((k_nee<true, true>), nb, TPB, 0, stream, Pn, nReq); else MER_LAUNCH((k_nee<false, true>), nb, TPB, 0, stream, Pn, nReq); }
                 else { if (wantOpl) MER_LAUNCH((k_nee<true, false>), nb, TPB, 0, stream, Pn, nReq); else MER_LAUNCH((k_nee<false, false>), nb, TPB, 0, stream, Pn, nReq); }
                 MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
@@ -1140,7 +1180,7 @@ int mer_render(const mer_medium *m, const mer_render_desc *r, float *film_host, 
     MER_REQUIRE(r->width > 0 && r->height > 0, "film size must be positive");
     mer::DeviceGuard guard(m->device);
     float *film = nullptr;
-    const size_t bytes = (size_t) r->width * r->height * (3 * (size_t) (r->frames > 1 ? r->frames : 1) + 2) * sizeof(float);
+    const size_t bytes = (size_t) r->width * r->height * (3 * (size_t) ((r->frames > 1 && !r->modulation) ? r->frames : 1) + 2) * sizeof(float);
     MER_CUDA(cudaMalloc(&film, bytes));
     cudaError_t e = cudaMemset(film, 0, bytes);
     int rc = e == cudaSuccess ? mer_render_device(m, r, film, stats_out, nullptr) : mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));

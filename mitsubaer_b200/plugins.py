@@ -464,6 +464,9 @@ class HeterogeneousRefractiveMedium:
         return out
 
 
+_MODULATIONS = {"none": 0, "sine": 1, "square": 2, "hamiltonian": 3}
+
+
 class EikonalVolPathIntegrator:
     """<integrator type="ervolpath">: props `maxDepth` (-1), `rrDepth` (5) (MonteCarloIntegrator,
     src/librender/integrator.cpp:190-225) + scheduling knobs `poolPaths`, `stepsPerPass`.
@@ -532,12 +535,18 @@ class EikonalVolPathIntegrator:
             r.frames = int(np.ceil((float(tr["maxBound"]) - float(tr["minBound"])) / width))  # film.cpp:73
             r.min_bound, r.bin_width = float(tr["minBound"]), width
             r.calibrated_transient = 1 if tr.get("calibrated", tr.get("calibratedTransient", False)) else 0
+            mod = str(tr.get("modulation", "none")).lower()  # continuous-wave ToF: pathlengthsampler.cpp
+            if mod not in _MODULATIONS:
+                raise _abi.MerError(_abi.MER_ERR_INVALID, 'The "modulation" parameter must be "none", "sine", "square" or "hamiltonian" on this path')
+            r.modulation = _MODULATIONS[mod]
+            r.lambda_ = float(tr.get("lambda", 1.0))
+            r.phase_deg = float(tr.get("phase", 0.0))
         return r
 
     def render(self, scene, medium, sample_begin=0, sample_stride=1):
         """-> (film[H][W][5] = [R,G,B,alpha,weight], stats dict); with scene["transient"]: film[H][W][3*frames+2]"""
         r = self.render_desc(scene, sample_begin, sample_stride, medium)
-        film = np.zeros((r.height, r.width, 3 * max(int(r.frames), 1) + 2), np.float32)
+        film = np.zeros((r.height, r.width, 3 * (max(int(r.frames), 1) if not r.modulation else 1) + 2), np.float32)
         stats = _abi.RenderStats()
         check(lib.mer_render(medium.handle, C.byref(r), _fp(film), C.byref(stats)))
         return film, stats.as_dict()

@@ -1377,13 +1377,41 @@ struct Radiance {
     float *L;
     int frames;
     float minBound, binWidth;
+    int modulation = MER_MODULATION_NONE; /* continuous-wave ToF (pathlengthsampler.cpp): one frame, weighted contributions */
+    float lambda = 1, phaseShift = 0;
+    /* PathLengthSampler::correlationFunction, src/librender/pathlengthsampler.cpp:66-96 */
+    float correlation(float len) const {
+        if (!std::isfinite(len)) return 0.0f; /* the environment has no path length */
+        float pl = len + phaseShift;
+        if (modulation == MER_MODULATION_SINE) return std::cos(pl * 6.283185307179586f / lambda);
+        if (modulation == MER_MODULATION_SQUARE) return 4.0f / lambda * (std::abs(std::fmod(pl, lambda) - lambda / 2.0f) - lambda / 4.0f);
+        pl = std::fmod(pl, lambda);
+        if (pl < lambda / 6.0f) return 6.0f * pl / lambda;
+        if (pl < lambda / 2.0f) return 1.0f;
+        if (pl < 2.0f * lambda / 3.0f) return 1.0f - (pl - lambda / 2.0f) * 6.0f / lambda;
+        return 0.0f;
+    }
     void add(float pathLength, const float rgb[3]) const {
+        if (modulation != MER_MODULATION_NONE) { /* bdpt_proc.cpp:440-441 */
+            const float w = correlation(pathLength);
+            for (int i = 0; i < 3; i++) L[i] += rgb[i] * w;
+            return;
+        }
         if (frames <= 1) { for (int i = 0; i < 3; i++) L[i] += rgb[i]; return; }
         const float b = std::floor((pathLength - minBound) / binWidth);
         if (!(b >= 0.0f && b < (float) frames)) return;
         for (int i = 0; i < 3; i++) L[3 * (int) b + i] += rgb[i];
     }
 };
+
+inline int filmFrames(const mer_render_desc &R) { return (R.frames > 1 && !R.modulation) ? R.frames : 1; } /* film.cpp:73-78 */
+inline Radiance makeRadiance(const mer_render_desc &R, float *L) {
+    Radiance r = {L, filmFrames(R), R.min_bound, R.bin_width};
+    r.modulation = R.modulation;
+    r.lambda = R.lambda;
+    r.phaseShift = (float) ((double) R.phase_deg * M_PI / 180.0) * R.lambda * (float) (0.5 / M_PI);
+    return r;
+}
 
 const uint64_t kNeeSalt = 0x5851F42D4C957F2DULL; /* next-event estimation draws come from their own Philox key */
 
@@ -1508,9 +1536,8 @@ void sensorConnection(const Medium<F> &M, const mer_render_desc &R, const LightC
         bf = 1.0f - fresnelDielectricExt(-C.exit.cosI, cosT, C.exit.nb);
     }
     const float g = LC.lightScale / (spread * zc * zc * zc);
-    const int frames = R.frames > 1 ? R.frames : 1;
     std::vector<float> value(LC.channels, 0.0f);
-    const Radiance acc = {value.data(), frames, R.min_bound, R.bin_width};
+    const Radiance acc = makeRadiance(R, value.data());
     float rad[3];
     for (int c = 0; c < 3; c++) {
         float T = (float) std::exp((double) (M.density ? -C.exit.tau : M.sigmaT[c] * (float) (-C.dist)));
@@ -1527,7 +1554,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
     /* LC != nullptr: the same walk started at the emitter (o, dcam = emitted ray) with importance-mode weights; nothing is
      * returned, the scattering vertices splat their sensor connections */
     const bool light = LC != nullptr;
-    const Radiance L = {Lout, R.frames > 1 ? R.frames : 1, R.min_bound, R.bin_width};
+    const Radiance L = makeRadiance(R, Lout);
     if (!light) for (int i = 0; i < 3 * L.frames; i++) Lout[i] = 0;
     alpha = 0;
     F opl = 0; /* optical path length from the camera (or from the first surface: calibrated_transient) */
@@ -1728,7 +1755,7 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
     Camera cam;
     cam.configure(&R);
     const int bx = (W + B - 1) / B, by = (H + B - 1) / B;
-    const int channels = 3 * (R.frames > 1 ? R.frames : 1) + 2; /* bdpt_wr.cpp:52-56 */
+    const int channels = 3 * filmFrames(R) + 2; /* bdpt_wr.cpp:52-56 */
     const float lightScale = (float) (1.0 / ((double) W * H * (double) R.spp_total * ((2.0 * cam.tanHalf) * (2.0 * cam.tanHalf / cam.aspect)) / ((double) W * H)));
     Stats total;
 #ifdef _OPENMP

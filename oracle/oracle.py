@@ -50,7 +50,8 @@ class RenderDesc(C.Structure):
                 ("pool_paths", C.c_int32), ("steps_per_pass", C.c_int32), ("direct_connections", C.c_int32),
                 ("connection", ConnectionParams), ("frames", C.c_int32), ("min_bound", C.c_float), ("bin_width", C.c_float),
                 ("calibrated_transient", C.c_int32), ("light_tracing", C.c_int32), ("emitter_type", C.c_int32),
-                ("beam_origin", C.c_float * 3), ("beam_direction", C.c_float * 3), ("beam_power", C.c_float * 3)]
+                ("beam_origin", C.c_float * 3), ("beam_direction", C.c_float * 3), ("beam_power", C.c_float * 3),
+                ("modulation", C.c_int32), ("lambda_", C.c_float), ("phase_deg", C.c_float)]
 
 
 class RenderStats(C.Structure):
@@ -382,7 +383,8 @@ class Oracle:
 
     # ---- integrator
     def render(self, medium, rdesc, nthreads=0):
-        film = np.zeros((rdesc.height, rdesc.width, 3 * max(int(rdesc.frames), 1) + 2), dtype=np.float32)
+        frames = max(int(rdesc.frames), 1) if not rdesc.modulation else 1
+        film = np.zeros((rdesc.height, rdesc.width, 3 * frames + 2), dtype=np.float32)
         stats = RenderStats()
         self._fn("orc_render")(medium, C.byref(rdesc), _ptr(film, C.c_float), C.byref(stats), C.c_int(nthreads))
         return film, stats

@@ -139,4 +139,7 @@ def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_s
         r.frames = int(np.ceil((tr["maxBound"] - tr["minBound"]) / tr["binWidth"]))
         r.min_bound, r.bin_width = float(tr["minBound"]), float(tr["binWidth"])
         r.calibrated_transient = 1 if tr.get("calibrated", False) else 0
+        r.modulation = {"none": 0, "sine": 1, "square": 2, "hamiltonian": 3}[tr.get("modulation", "none")]
+        r.lambda_ = float(tr.get("lambda", 1.0))
+        r.phase_deg = float(tr.get("phase", 0.0))
     return r

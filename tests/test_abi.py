@@ -41,7 +41,7 @@ def test_struct_layouts_match_the_header(tmp_path):
                                   "sampling_density", "shape_type", "shape", "hg_g", "density_scale", "albedo", "boundary", "radiance_scaling"],
               "mer_render_desc": ["width", "spp_total", "sample_stride", "seed", "cam_origin", "fov_deg", "filter",
                                   "max_depth", "env_radiance", "has_quad", "quad_radiance", "pool_paths", "steps_per_pass",
-                                  "direct_connections", "connection", "frames", "min_bound", "bin_width", "calibrated_transient", "light_tracing", "emitter_type", "beam_power"],
+                                  "direct_connections", "connection", "frames", "min_bound", "bin_width", "calibrated_transient", "light_tracing", "emitter_type", "beam_power", "modulation", "phase_deg"],
               "mer_render_stats": ["samples", "ray_steps", "passes", "connections", "connection_steps", "kernel_launches", "device_ms"],
               "mer_medium_sampling_records": ["success", "t", "nsteps"],
               "mer_connection_params": ["tol2", "rrweight", "boundary_precision", "max_iterations", "start_mode"],
@@ -72,7 +72,7 @@ def test_struct_layouts_match_the_header(tmp_path):
 
 
 def test_version_and_error_plumbing():
-    assert _abi.lib.mer_abi_version() == 7
+    assert _abi.lib.mer_abi_version() == 8
     assert isinstance(mer.kernel_launch_count(), int)
     with pytest.raises(mer.MerError, match=r"interval \(-1, 1\)"):
         mer.HGPhaseFunction(g=-1.5)

@@ -534,3 +534,27 @@ def test_sdf_container_matches_oracle_and_the_analytic_sphere(oracle32, bsdf, ne
     assert np.mean(np.abs(a - ref) <= 2e-3 * np.maximum(ref, 1.0)) > 0.95 and abs(a.mean() / ref.mean() - 1) < 3e-3
     with pytest.raises(mer.MerError, match="sdf"):
         mer.HeterogeneousRefractiveMedium(medium_props(shape=("sdf", BOX_MIN, BOX_MAX))).addChild("rif", rif).configure()
+
+
+@pytest.mark.parametrize("modulation,mode", [("sine", "camera"), ("square", "camera+nee"), ("hamiltonian", "light")])
+def test_cw_tof_modulation_matches_oracle(oracle32, modulation, mode):
+    """continuous-wave ToF: contributions times PathLengthSampler::correlationFunction(path length), one frame
+    (src/librender/pathlengthsampler.cpp:66-96, film.cpp:76-78) — camera walk, its direct connections, and light tracing"""
+    med, rif, props, data, lo, hi = _nee_medium("linear", 1e-2, "null")
+    omed = oracle32.medium_create(oracle_medium_desc(props, 0.5), oracle32.rif_create(volume_desc((32,) * 3, lo, hi), data))
+    scene = _hidden_quad_scene(32, 32, 8, transient=dict(minBound=0.0, maxBound=50.0, binWidth=1.0, modulation=modulation, **{"lambda": 3.0, "phase": 30.0}))
+    kw = dict(directConnections=mode == "camera+nee", lightTracing=mode == "light")
+    film, st = mer.EikonalVolPathIntegrator(rrDepth=5, poolPaths=1024, stepsPerPass=128, **kw).render(scene, med)
+    ofilm, ost = oracle32.render(omed, oracle_render_desc(scene, direct_connections=kw["directConnections"], light_tracing=kw["lightTracing"], props=props))
+    assert film.shape == ofilm.shape == (32, 32, 5) and st["samples"] == ost.samples
+    a, b = mer.develop(film), oracle32.film_develop(ofilm)
+    assert np.abs(b).max() > 0
+    if modulation != "hamiltonian":  # sine and square codes have both signs, the Hamiltonian code lives in [0, 1]
+        assert b.min() < 0 < b.max()
+    scale = np.abs(b).max()
+    assert np.mean(np.abs(a - b) <= 0.02 * np.abs(b) + 2e-3 * scale) > 0.95
+    assert abs(a.sum() - b.sum()) <= 0.01 * np.abs(b).sum()
+    # and the unmodulated steady-state image of the same samples bounds it: |correlation| <= 1
+    del scene["transient"]
+    steady = mer.develop(mer.EikonalVolPathIntegrator(rrDepth=5, poolPaths=1024, stepsPerPass=128, **kw).render(scene, med)[0])
+    assert np.all(np.abs(a) <= steady * (1 + 1e-4) + 1e-6)

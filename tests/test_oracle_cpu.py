@@ -360,3 +360,27 @@ def test_oracle_light_tracing_agrees_with_camera_tracer(oracle32):
     assert abs(b.mean() / a.mean() - 1) < 0.05, (a.mean(), b.mean())
     ab, bb = a.reshape(8, 8, 8, 8).mean(axis=(1, 3)), b.reshape(8, 8, 8, 8).mean(axis=(1, 3))
     assert np.corrcoef(ab.ravel(), bb.ravel())[0, 1] > 0.98
+
+
+@pytest.mark.parametrize("modulation", ["sine", "square", "hamiltonian"])
+def test_oracle_cw_tof_modulation(oracle32, modulation):
+    """continuous-wave ToF film (PathLengthSampler::correlationFunction, src/librender/pathlengthsampler.cpp:66-96): the
+    clear-slab scene puts all light at optical length 8 (minus up to 0.03 for the walk's short exit), so every pixel
+    is the correlation function at that length"""
+    from common import BOX_MAX, BOX_MIN, medium_props, oracle_medium_desc, oracle_render_desc, scene_dict
+    from mitsubaer_b200 import fields
+    res = 16
+    lo, hi = fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    orif = oracle32.rif_create(volume_desc((res,) * 3, lo, hi), np.full((res,) * 3, 1.5, np.float32))
+    clear = oracle32.medium_create(oracle_medium_desc(medium_props(stepsize=1e-2, sigmaS=0.0, sigmaA=0.0, mediumSamplingWeight=0.0), 0.0), orif)
+    lam, phase = 5.0, 60.0
+    scene = scene_dict(8, 8, 8, rfilter="box", quad=False)
+    scene.update(fov=2.0, envRadiance=0.0, quad=dict(origin=(-50.0, -50.0, 3.0), u=(100.0, 0.0, 0.0), v=(0.0, 100.0, 0.0), radiance=(1.0, 1.0, 1.0)),
+                 transient=dict(minBound=0.0, maxBound=100.0, binWidth=1.0, modulation=modulation, **{"lambda": lam, "phase": phase}))
+    film, _ = oracle32.render(clear, oracle_render_desc(scene))
+    assert film.shape == (8, 8, 5)  # one frame under a modulation (film.cpp:76-78)
+    got = oracle32.film_develop(film)[..., 0].mean()
+    pl = 8.0 - 0.015 + np.deg2rad(phase) * lam / (2 * np.pi)
+    expect = {"sine": np.cos(pl * 2 * np.pi / lam), "square": 4 / lam * (abs(pl % lam - lam / 2) - lam / 4),
+              "hamiltonian": (lambda t: 6 * t / lam if t < lam / 6 else 1.0 if t < lam / 2 else 1 - (t - lam / 2) * 6 / lam if t < 2 * lam / 3 else 0.0)(pl % lam)}[modulation]
+    assert abs(got - expect) < 0.03, (modulation, got, expect)
