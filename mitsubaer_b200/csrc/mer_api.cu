@@ -12,6 +12,36 @@ std::atomic<uint64_t> g_launches{0};
 
 void set_error(const std::string &msg) { t_error = msg; }
 
+cudaError_t pool_malloc(void **p, size_t bytes) {
+    static std::atomic<unsigned> configured{0}; /* bit per device */
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool = nullptr;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 32 && !(configured.load() & (1u << dev))) {
+        unsigned long long keep = ~0ull; /* never hand freed blocks back to the driver on a synchronisation */
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        configured.fetch_or(1u << dev);
+    }
+    e = cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t) 0);
+    if (e == cudaErrorMemoryAllocation) { /* give the cached blocks back and try once more */
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+        e = cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t) 0);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) 0); /* usable from any stream from here on */
+    return e;
+}
+
+void pool_free(void *p) {
+    if (!p) return;
+    cudaDeviceSynchronize(); /* cudaFree's guarantee: nothing still uses the buffer */
+    cudaFreeAsync(p, (cudaStream_t) 0);
+}
+
 int fail(int code, const std::string &msg) {
     t_error = msg;
     return code;

@@ -240,23 +240,23 @@ void fill_rif_dev(mer_rif *r) {
 int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
     const mer_volume_desc &d = r->desc;
     const size_t total = voxels(&d);
-    MER_CUDA(cudaMalloc(&r->d_coeff, total * sizeof(float)));
+    MER_CUDA(mer::pool_malloc((void **) &r->d_coeff, total * sizeof(float)));
     const int N0 = d.res[0], N1 = d.res[1], N2 = d.res[2];
     const unsigned T = 128;
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N2, T), T, 0, s, data_dev, r->d_coeff, N0, N1, N2, (int) PASS_Y);
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N1 * N2, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_X);
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N1, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_Z);
-    MER_CUDA(cudaMalloc(&r->d_coeff8, 2 * total * sizeof(float4)));
+    MER_CUDA(mer::pool_malloc((void **) &r->d_coeff8, 2 * total * sizeof(float4)));
     const unsigned G = (unsigned) std::min<size_t>(mer_blocks(total, 256), 148u * 16u);
     MER_LAUNCH(k_expand_coeff8, G, 256, 0, s, r->d_coeff, r->d_coeff8, N0, N1, total);
     fill_rif_dev(r);
     if (r->mode == MER_RIF_TRILINEAR_PACKED) {
-        MER_CUDA(cudaMalloc(&r->d_packed, total * sizeof(float4)));
+        MER_CUDA(mer::pool_malloc((void **) &r->d_packed, total * sizeof(float4)));
         fill_rif_dev(r);
         MER_LAUNCH(k_build_packed, G, 256, 0, s, r->dev, r->d_packed, total);
         MER_CUDA(cudaStreamSynchronize(s));
         /* the 8x-expanded cubic coefficients are only needed to build the packed grid */
-        cudaFree(r->d_coeff8);
+        mer::pool_free(r->d_coeff8);
         r->d_coeff8 = nullptr;
         fill_rif_dev(r);
     }
@@ -328,7 +328,7 @@ int stream_vol_to_device(int device, const char *path, mer_volume_desc *desc, fl
     float *dev = nullptr, *stage[2] = {nullptr, nullptr};
     cudaStream_t st = nullptr;
     cudaEvent_t done[2] = {nullptr, nullptr};
-    cudaError_t e = cudaMalloc(&dev, total * sizeof(float));
+    cudaError_t e = mer::pool_malloc((void **) &dev, total * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreate(&st);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
         e = cudaMallocHost(&stage[i], slab * sizeof(float));
@@ -349,7 +349,7 @@ int stream_vol_to_device(int device, const char *path, mer_volume_desc *desc, fl
     for (int i = 0; i < 2; i++) { if (stage[i]) cudaFreeHost(stage[i]); if (done[i]) cudaEventDestroy(done[i]); }
     if (st) cudaStreamDestroy(st);
     if (truncated || e != cudaSuccess) {
-        cudaFree(dev);
+        mer::pool_free(dev);
         return truncated ? mer::fail(MER_ERR_INVALID, "volume file truncated") : mer::fail(e == cudaErrorMemoryAllocation ? MER_ERR_OOM : MER_ERR_CUDA, cudaGetErrorString(e));
     }
     *data_dev_out = dev;
@@ -402,11 +402,11 @@ int mer_rif_create(int device, const mer_volume_desc *desc, const float *data, i
     mer::DeviceGuard guard(device);
     float *d_data = nullptr;
     const size_t bytes = voxels(desc) * sizeof(float);
-    MER_CUDA(cudaMalloc(&d_data, bytes));
+    MER_CUDA(mer::pool_malloc((void **) &d_data, bytes));
     cudaError_t e = cudaMemcpy(d_data, data, bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d_data); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { mer::pool_free(d_data); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
     rc = mer_rif_create_device(device, desc, d_data, mode, out);
-    cudaFree(d_data);
+    mer::pool_free(d_data);
     return rc;
 }
 
@@ -422,16 +422,16 @@ int mer_rif_create_from_file(int device, const char *vol_path, const mer_volume_
     apply_override(&d, override_or_null);
     rc = mer_rif_create_device(device, &d, raw, mode, out);
     mer::DeviceGuard guard(device);
-    cudaFree(raw);
+    mer::pool_free(raw);
     return rc;
 }
 
 void mer_rif_destroy(mer_rif *r) {
     if (!r) return;
     mer::DeviceGuard guard(r->device);
-    cudaFree(r->d_coeff);
-    cudaFree(r->d_coeff8);
-    cudaFree(r->d_packed);
+    mer::pool_free(r->d_coeff);
+    mer::pool_free(r->d_coeff8);
+    mer::pool_free(r->d_packed);
     delete r;
 }
 
@@ -520,7 +520,7 @@ int mer_grid_create_device(int device, const mer_volume_desc *desc, const float 
     g->device = device;
     g->desc = *desc;
     const size_t bytes = voxels(desc) * sizeof(float);
-    cudaError_t e = cudaMalloc(&g->d_data, bytes);
+    cudaError_t e = mer::pool_malloc((void **) &g->d_data, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_data, data_dev, bytes, cudaMemcpyDeviceToDevice);
     if (e != cudaSuccess) { mer_grid_destroy(g); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
     for (int r = 0; r < 3; r++) {
@@ -572,11 +572,11 @@ int mer_grid_create(int device, const mer_volume_desc *desc, const float *data, 
     mer::DeviceGuard guard(device);
     float *d_data = nullptr;
     const size_t bytes = voxels(desc) * sizeof(float);
-    MER_CUDA(cudaMalloc(&d_data, bytes));
+    MER_CUDA(mer::pool_malloc((void **) &d_data, bytes));
     cudaError_t e = cudaMemcpy(d_data, data, bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d_data); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { mer::pool_free(d_data); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
     rc = mer_grid_create_device(device, desc, d_data, out);
-    cudaFree(d_data);
+    mer::pool_free(d_data);
     return rc;
 }
 
@@ -592,14 +592,14 @@ int mer_grid_create_from_file(int device, const char *vol_path, const mer_volume
     apply_override(&d, override_or_null);
     rc = mer_grid_create_device(device, &d, raw, out);
     mer::DeviceGuard guard(device);
-    cudaFree(raw);
+    mer::pool_free(raw);
     return rc;
 }
 
 void mer_grid_destroy(mer_grid *g) {
     if (!g) return;
     mer::DeviceGuard guard(g->device);
-    cudaFree(g->d_data);
+    mer::pool_free(g->d_data);
     delete g;
 }
 
