@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Writes the .vol files scenes/eikonal_box.xml refers to (the reference's MATLAB generators, restated in
-mitsubaer_b200/fields.py): BoxRIF_Linear.vol, BoxRIF_Radial.vol, BoxSDRIF_2.vol, BoxDensity.vol."""
+"""Writes the .vol files the scenes/*.xml refer to (the reference's MATLAB generators, restated in
+mitsubaer_b200/fields.py): BoxRIF_Linear.vol, BoxRIF_Radial.vol, BoxSDRIF_2.vol, BoxDensity.vol, and SphereSDF.vol
+(signed distance to a sphere: the `sdf` child volume of a mesh container, MER_SHAPE_SDF)."""
 import argparse
 import os
 import sys
@@ -24,7 +25,8 @@ def main():
     fields.write_vol(os.path.join(a.out, "BoxRIF_Radial.vol"), fields.radial_rif(res, lo, hi), lo, hi)
     fields.write_vol(os.path.join(a.out, "BoxSDRIF_2.vol"), fields.rif_from_sd(fields.sphere_sdf(res, lo, hi, radius=0.8)), lo, hi)
     fields.write_vol(os.path.join(a.out, "BoxDensity.vol"), fields.sine_density(res, lo_box, hi_box), lo_box, hi_box)
-    print("wrote 4 volumes (%d^3) to %s" % (a.res, a.out))
+    fields.write_vol(os.path.join(a.out, "SphereSDF.vol"), fields.sphere_sdf(res, lo, hi, radius=0.8).astype(np.float32), lo, hi)
+    print("wrote 5 volumes (%d^3) to %s" % (a.res, a.out))
 
 
 if __name__ == "__main__":
