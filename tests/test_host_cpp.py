@@ -171,3 +171,20 @@ def test_mesh_container_through_sdf_volume(volumes, tmp_path):
     assert out.returncode == 0, out.stderr
     m = json.loads(out.stdout)["medium"]
     assert m["shape_type"] == 2 and np.allclose(m["shape"], list(lo) + list(hi))
+
+
+def test_cw_tof_film_resolves(volumes, tmp_path):
+    """<film> modulation / lambda / phase (PathLengthSampler, src/librender/pathlengthsampler.cpp:6-35): one frame, the code and
+    its parameters in the descriptor; unknown codes are refused"""
+    d, lo, hi = volumes
+    text = open(BEAM).read().replace('<float name="binWidth" value="$tRes"/>',
+                                     '<float name="binWidth" value="$tRes"/>\n<string name="modulation" value="$mod"/>\n'
+                                     '<float name="lambda" value="3.5"/>\n<float name="phase" value="90"/>')
+    p = tmp_path / "cw.xml"
+    p.write_text(text)
+    out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "-D", "mod=Sine", "--dry-run"])
+    assert out.returncode == 0, out.stderr
+    s = json.loads(out.stdout)
+    assert s["frames"] == 0 and s["light_tracing"] == 1  # a modulated film has one frame (film.cpp:76-78)
+    out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "-D", "mod=mseq", "--dry-run"])
+    assert out.returncode == 1 and "modulation" in out.stderr

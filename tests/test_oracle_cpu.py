@@ -384,3 +384,25 @@ def test_oracle_cw_tof_modulation(oracle32, modulation):
     expect = {"sine": np.cos(pl * 2 * np.pi / lam), "square": 4 / lam * (abs(pl % lam - lam / 2) - lam / 4),
               "hamiltonian": (lambda t: 6 * t / lam if t < lam / 6 else 1.0 if t < lam / 2 else 1 - (t - lam / 2) * 6 / lam if t < 2 * lam / 3 else 0.0)(pl % lam)}[modulation]
     assert abs(got - expect) < 0.03, (modulation, got, expect)
+
+
+def test_oracle_float_vs_double_on_the_widened_path(oracle32, oracle64):
+    """R9 for the "next" rows: the float restatement (Mitsuba's Float, what the GPU is gated against) and the double one
+    (the authors' FLOATDEBUG arithmetic for the eikonal math) walk the same Philox streams; direct connections, the Fresnel
+    boundary and the transient film give the same image up to the few paths that rounding sends different ways"""
+    from common import make_field, medium_props, oracle_medium_desc, oracle_render_desc, scene_dict
+    data, lo, hi = make_field("linear", 24)
+    props = medium_props(stepsize=2e-2, sigmaS=1.5, sigmaA=0.5, bsdf="hdielectric")
+    scene = scene_dict(24, 24, 6, rfilter="box")
+    scene.update(envRadiance=0.0, transient=dict(minBound=4.0, maxBound=36.0, binWidth=1.0))
+    films = {}
+    for name, orc in (("f32", oracle32), ("f64", oracle64)):
+        med = orc.medium_create(oracle_medium_desc(props, 0.5), orc.rif_create(volume_desc((24,) * 3, lo, hi), data))
+        films[name], st = orc.render(med, oracle_render_desc(scene, direct_connections=True, props=props))
+        assert st.connections > 2000 and st.connections_failed < 0.3 * st.connections
+    a, b = films["f32"][..., :-2].reshape(24, 24, 32, 3), films["f64"][..., :-2].reshape(24, 24, 32, 3)
+    assert abs(a.sum() / b.sum() - 1) < 0.02
+    pa, pb = a.sum(axis=(0, 1, 3)), b.sum(axis=(0, 1, 3))  # time profile
+    assert np.allclose(pa, pb, rtol=0.1, atol=0.02 * pb.max())
+    ia, ib = a.sum(axis=(2, 3)), b.sum(axis=(2, 3))
+    assert np.mean(np.abs(ia - ib) <= 0.02 * ib + 1e-3 * ib.max()) > 0.9
