@@ -18,9 +18,9 @@ static void printDesc(const Scene &S) {
     const mer_render_desc &r = S.render;
     const mer_medium_desc &m = S.medium->desc;
     std::printf("{\"integrator\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %d, \"seed\": %llu, \"fov\": %g, \"filter\": %d,\n"
-                " \"max_depth\": %d, \"rr_depth\": %d, \"direct_connections\": %d, \"light_tracing\": %d, \"emitter_type\": %d, \"frames\": %d, \"min_bound\": %g, \"bin_width\": %g, \"cam_origin\": [%g, %g, %g], \"cam_target\": [%g, %g, %g], \"cam_up\": [%g, %g, %g],\n"
+                " \"max_depth\": %d, \"rr_depth\": %d, \"direct_connections\": %d, \"light_tracing\": %d, \"emitter_type\": %d, \"frames\": %d, \"min_bound\": %g, \"bin_width\": %g, \"modulation\": %d, \"lambda\": %g, \"phase\": %g, \"cam_origin\": [%g, %g, %g], \"cam_target\": [%g, %g, %g], \"cam_up\": [%g, %g, %g],\n"
                 " \"env\": [%g, %g, %g], \"has_quad\": %d, \"quad_origin\": [%g, %g, %g], \"quad_u\": [%g, %g, %g], \"quad_v\": [%g, %g, %g], \"quad_radiance\": [%g, %g, %g],\n",
-                S.integratorType.c_str(), r.width, r.height, r.spp_total, (unsigned long long) r.seed, r.fov_deg, r.filter, r.max_depth, r.rr_depth, r.direct_connections, r.light_tracing, r.emitter_type, r.frames, r.min_bound, r.bin_width,
+                S.integratorType.c_str(), r.width, r.height, r.spp_total, (unsigned long long) r.seed, r.fov_deg, r.filter, r.max_depth, r.rr_depth, r.direct_connections, r.light_tracing, r.emitter_type, r.frames, r.min_bound, r.bin_width, r.modulation, r.lambda, r.phase_deg,
                 r.cam_origin[0], r.cam_origin[1], r.cam_origin[2], r.cam_target[0], r.cam_target[1], r.cam_target[2], r.cam_up[0], r.cam_up[1], r.cam_up[2],
                 r.env_radiance[0], r.env_radiance[1], r.env_radiance[2], r.has_quad, r.quad_origin[0], r.quad_origin[1], r.quad_origin[2],
                 r.quad_u[0], r.quad_u[1], r.quad_u[2], r.quad_v[0], r.quad_v[1], r.quad_v[2], r.quad_radiance[0], r.quad_radiance[1], r.quad_radiance[2]);

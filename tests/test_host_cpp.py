@@ -186,5 +186,6 @@ def test_cw_tof_film_resolves(volumes, tmp_path):
     assert out.returncode == 0, out.stderr
     s = json.loads(out.stdout)
     assert s["frames"] == 0 and s["light_tracing"] == 1  # a modulated film has one frame (film.cpp:76-78)
+    assert s["modulation"] == 1 and s["lambda"] == 3.5 and s["phase"] == 90
     out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "-D", "mod=mseq", "--dry-run"])
     assert out.returncode == 1 and "modulation" in out.stderr
