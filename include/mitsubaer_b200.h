@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 8
+#define MER_ABI_VERSION 9
 
 enum mer_status {
     MER_OK = 0,
@@ -385,6 +385,12 @@ int mer_abi_version(void);
 int mer_device_count(void);
 /* total kernels launched by this library in this process (bench.py `gpu_launches`) */
 uint64_t mer_kernel_launch_count(void);
+
+/* Hands the memory this library caches on `device` back to the driver: the private stream-ordered pool that backs the
+ * volume handles, the cached coefficient atlases and the render scratch (path pool).  The reference has no equivalent
+ * (its volumes are mmap()ed files, src/volume/splinevolume.cpp:204-317); a host that shares the GPU calls this after
+ * tearing a scene down.  Live handles are not affected. */
+int mer_trim_memory(int device);
 
 #ifdef __cplusplus
 }

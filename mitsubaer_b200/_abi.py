@@ -137,6 +137,7 @@ SIGNATURES = {
     "mer_abi_version": (C.c_int, []),
     "mer_device_count": (C.c_int, []),
     "mer_kernel_launch_count": (C.c_uint64, []),
+    "mer_trim_memory": (C.c_int, [C.c_int]),
 }
 
 
@@ -153,7 +154,19 @@ def _load():
     return lib
 
 
-lib = _load()
+class _Lib:
+    """The shared library, loaded on first use.  `import mitsubaer_b200` touches it right away (so a missing or
+    stale .so fails at import, loudly) unless MER_B200_DEFER_LOAD=1, which bench.py's CPU-reference arm sets so
+    that the process timing the oracle never maps the CUDA library (it only needs fields.py's generators)."""
+    _handle = None
+
+    def __getattr__(self, name):
+        if _Lib._handle is None:
+            _Lib._handle = _load()
+        return getattr(_Lib._handle, name)
+
+
+lib = _Lib()
 
 
 def check(rc):

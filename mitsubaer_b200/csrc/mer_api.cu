@@ -3,6 +3,9 @@
  * Replaces the Log(EError) -> std::runtime_error convention of src/libcore/logger.cpp:100-147
  * with status codes + mer_last_error() (the Mitsuba-side shim rethrows).
  */
+#include <cstdlib>
+#include <cstring>
+
 #include "mer_internal.h"
 
 namespace mer {
@@ -12,34 +15,62 @@ std::atomic<uint64_t> g_launches{0};
 
 void set_error(const std::string &msg) { t_error = msg; }
 
+/* Grid-sized buffers come from a PRIVATE stream-ordered pool per device (cudaMemPoolCreate): its release threshold is lifted
+ * so that a scene torn down and rebuilt reuses the memory, without touching the device's default pool, which the host
+ * application (PyTorch, Mitsuba) shares.  mer_trim_memory() hands everything cached back to the driver. */
+static std::mutex g_poolLock;
+static cudaMemPool_t g_pools[64] = {nullptr};
+
+static cudaError_t device_pool(int dev, cudaMemPool_t *out) {
+    std::lock_guard<std::mutex> hold(g_poolLock);
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaError_t e = cudaMemPoolCreate(&g_pools[dev], &props);
+        if (e != cudaSuccess) { g_pools[dev] = nullptr; return e; }
+        unsigned long long keep = ~0ull; /* cached blocks stay with THIS pool across synchronisations */
+        if (const char *env = getenv("MER_POOL_KEEP_BYTES")) keep = strtoull(env, nullptr, 10);
+        cudaMemPoolSetAttribute(g_pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    *out = g_pools[dev];
+    return cudaSuccess;
+}
+
 cudaError_t pool_malloc(void **p, size_t bytes) {
-    static std::atomic<unsigned> configured{0}; /* bit per device */
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     cudaMemPool_t pool = nullptr;
-    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    e = device_pool(dev, &pool);
     if (e != cudaSuccess) return e;
-    if (dev < 32 && !(configured.load() & (1u << dev))) {
-        unsigned long long keep = ~0ull; /* never hand freed blocks back to the driver on a synchronisation */
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        configured.fetch_or(1u << dev);
-    }
-    e = cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t) 0);
+    e = cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, (cudaStream_t) 0);
     if (e == cudaErrorMemoryAllocation) { /* give the cached blocks back and try once more */
         cudaGetLastError();
         cudaDeviceSynchronize();
         cudaMemPoolTrimTo(pool, 0);
-        e = cudaMallocAsync(p, bytes ? bytes : 1, (cudaStream_t) 0);
+        e = cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, (cudaStream_t) 0);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) 0); /* usable from any stream from here on */
     return e;
 }
 
+/* the caller has made sure nothing still uses the buffer (pool_quiesce once per handle, not once per buffer) */
 void pool_free(void *p) {
-    if (!p) return;
-    cudaDeviceSynchronize(); /* cudaFree's guarantee: nothing still uses the buffer */
-    cudaFreeAsync(p, (cudaStream_t) 0);
+    if (p) cudaFreeAsync(p, (cudaStream_t) 0);
+}
+void pool_quiesce() { cudaDeviceSynchronize(); }
+
+void pool_trim(int dev) {
+    std::lock_guard<std::mutex> hold(g_poolLock);
+    if (dev >= 0 && dev < 64 && g_pools[dev]) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(g_pools[dev], 0);
+    }
 }
 
 int fail(int code, const std::string &msg) {
@@ -94,5 +125,17 @@ int mer_device_count(void) {
 }
 
 uint64_t mer_kernel_launch_count(void) { return mer::g_launches.load(); }
+
+int mer_trim_memory(int device) {
+    int rc = mer::check_device(device);
+    if (rc) return rc;
+    mer::DeviceGuard guard(device);
+    mer::array_cache_trim(device);
+    mer::pool_trim(device);
+    RenderScratch &S = mer::device_scratch(device);
+    std::lock_guard<std::mutex> hold(S.lock);
+    S.release();
+    return MER_OK;
+}
 
 } /* extern "C" */

@@ -72,16 +72,13 @@ static __device__ void rif_field(const RifDev &R, float3 pw, Field &F) {
     bs_weights2(x, fx, wx0, wx1, wx2);
     bs_weights2(y, fy, wy0, wy1, wy2);
     bs_weights2(z, fz, wz0, wz1, wz2);
-    const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
-    const float4 *base = R.coeff8 + 2 * (size_t) clampi(i0, 0, N0 - 1);
-    const size_t rowA = 2 * (size_t) clampi(j0 - 1, 0, N1 - 1) * (size_t) N0, rowB = 2 * (size_t) clampi(j0 + 1, 0, N1 - 1) * (size_t) N0;
+    const bool interior = rif_cell_interior(R, i0, j0, k0);
     float f = 0, gx = 0, gy = 0, gz = 0, hxx = 0, hyy = 0, hzz = 0, hxy = 0, hyz = 0, hzx = 0;
 #pragma unroll
     for (int dz = 0; dz < 4; dz++) {
-        const size_t slab = 2 * (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
         float4 c[4];
-        ldg256(base + slab + rowA, c[0], c[1]);
-        ldg256(base + slab + rowB, c[2], c[3]);
+        if (interior) rif_slab_tex(R, i0, j0, k0 - 1 + dz, c);
+        else rif_slab_clamped(R, i0, j0, k0 - 1 + dz, c);
         float b00 = 0, b10 = 0, b20 = 0, b01 = 0, b11 = 0, b02 = 0;
 #pragma unroll
         for (int dy = 0; dy < 4; dy++) {

@@ -13,10 +13,10 @@
  *
  * Data layout in HBM:
  *   coeff   float  [z][y][x]   prefiltered B-spline coefficients, the reference's layout
- *   coeff8  2 x float4 [z][y][x] = (c[x-1..x+2] of row y, c[x-1..x+2] of row y+1) (clamped): the x-taps of
- *           TWO stencil rows in one aligned 32-byte sector -> a 4x4x4 stencil is 8 independent
- *           LDG.E.256 that use every byte of the 8 sectors they touch (the scalar layout needs 64
- *           loads from 16-32 sectors; a one-row float4 layout 16 loads from 16 half-used sectors)
+ *   atlas   the same coefficients once more as a 2-D CUDA array (block-linear, texture path): layer z is tile
+ *           (z & tileMask, z >> tileShift).  A 4x4x4 stencil is 16 texture gathers (tld4: one instruction returns
+ *           a 2x2 block of texels at ANY alignment), so the table is 1x the grid and stays L2-resident up to
+ *           ~300^3 (round 1 used an 8x-redundant table of x-tap tuples, coeff8: 512 MiB for 256^3, DRAM-bound)
  *   packed  float4 [z][y][x] = (n, dn/dx, dn/dy, dn/dz) sampled at the grid nodes (fast mode)
  */
 #pragma once
@@ -35,8 +35,12 @@ struct RifDev {
     int hasXform;
     float M[12];
     const float *coeff;
-    const float4 *coeff8; /* two float4 per voxel */
     const float4 *packed;
+    /* Texture storage of the cubic coefficients: a 2-D atlas of the z-layers in a CUDA array (tile (k & tileMask,
+     * k >> tileShift) holds layer k), read with tld4 — one gather returns a 2x2 block of raw coefficients, 16 gathers a
+     * 4x4x4 stencil, at any alignment. */
+    unsigned long long tex;
+    int tileShift, tileMask;
 };
 
 struct GridDev {
@@ -114,13 +118,6 @@ __device__ __forceinline__ void bs_weights(float x, float fx, float w0[4], float
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-/* one 32-byte sector per lane: LDG.E.256 (sm_100+), read-only path */
-__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p));
-}
-
 __device__ __forceinline__ float3 rif_to_volume(const RifDev &R, float3 p) {
     if (!R.hasXform) return p;
     return f3(R.M[0] * p.x + R.M[1] * p.y + R.M[2] * p.z + R.M[3], R.M[4] * p.x + R.M[5] * p.y + R.M[6] * p.z + R.M[7],
@@ -145,6 +142,36 @@ __device__ __forceinline__ bool rif_inside_limits(const RifDev &R, float3 pw) {
  * Tap set = floor(x)-1 .. floor(x)+2 per axis, which is the reference's
  * ceil(x-2)..floor(x+2) range minus its zero-weight end taps.  Indices are clamped into the
  * grid (the reference reads out of bounds there). */
+/* ---- stencil loads.  Interior cells (every tap inside the grid: always the case within insideVolumeLimits, whose margin
+ * is two voxels) read the atlas: per layer four gathers, each the 2x2 block of texels around (u, v); component order
+ * w,z,x,y = (i,j), (i+1,j), (i,j+1), (i+1,j+1) (checked against the coefficient array when the texture is built).
+ * Anything else reads the linear array tap by tap with indices clamped into the grid (the reference reads out of bounds). */
+__device__ __forceinline__ bool rif_cell_interior(const RifDev &R, int i0, int j0, int k0) {
+    return (unsigned) (i0 - 1) <= (unsigned) (R.N[0] - 4) && (unsigned) (j0 - 1) <= (unsigned) (R.N[1] - 4) &&
+           (unsigned) (k0 - 1) <= (unsigned) (R.N[2] - 4);
+}
+/* rows j0-1 .. j0+2 (x taps i0-1 .. i0+2 each) of layer k; (i0, j0) interior, k in the grid */
+__device__ __forceinline__ void rif_slab_tex(const RifDev &R, int i0, int j0, int k, float4 c[4]) {
+    const float u = (float) ((k & R.tileMask) * R.N[0] + i0), v = (float) ((k >> R.tileShift) * R.N[1] + j0);
+    const cudaTextureObject_t t = (cudaTextureObject_t) R.tex;
+    const float4 A = tex2Dgather<float4>(t, u, v, 0), B = tex2Dgather<float4>(t, u + 2.0f, v, 0);
+    const float4 C = tex2Dgather<float4>(t, u, v + 2.0f, 0), D = tex2Dgather<float4>(t, u + 2.0f, v + 2.0f, 0);
+    c[0] = make_float4(A.w, A.z, B.w, B.z);
+    c[1] = make_float4(A.x, A.y, B.x, B.y);
+    c[2] = make_float4(C.w, C.z, D.w, D.z);
+    c[3] = make_float4(C.x, C.y, D.x, D.y);
+}
+__device__ __forceinline__ void rif_slab_clamped(const RifDev &R, int i0, int j0, int k, float4 c[4]) {
+    const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
+    const int xa = clampi(i0 - 1, 0, N0 - 1), xb = clampi(i0, 0, N0 - 1), xc = clampi(i0 + 1, 0, N0 - 1), xd = clampi(i0 + 2, 0, N0 - 1);
+    const float *slab = R.coeff + (size_t) clampi(k, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
+#pragma unroll
+    for (int dy = 0; dy < 4; dy++) {
+        const float *row = slab + (size_t) clampi(j0 - 1 + dy, 0, N1 - 1) * (size_t) N0;
+        c[dy] = make_float4(__ldg(row + xa), __ldg(row + xb), __ldg(row + xc), __ldg(row + xd));
+    }
+}
+
 __device__ __forceinline__ void rif_tricubic(const RifDev &R, float3 pv, float &f, float3 &g) {
     const float x = (pv.x - R.xmin[0]) * R.xres[0], y = (pv.y - R.xmin[1]) * R.xres[1],
                 z = (pv.z - R.xmin[2]) * R.xres[2];
@@ -154,15 +181,13 @@ __device__ __forceinline__ void rif_tricubic(const RifDev &R, float3 pv, float &
     bs_weights(x, fx, wx0, wx1);
     bs_weights(y, fy, wy0, wy1);
     bs_weights(z, fz, wz0, wz1);
-    const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
-    const float4 *base = R.coeff8 + 2 * (size_t) clampi(i0, 0, N0 - 1);
-    const size_t rowA = 2 * (size_t) clampi(j0 - 1, 0, N1 - 1) * (size_t) N0, rowB = 2 * (size_t) clampi(j0 + 1, 0, N1 - 1) * (size_t) N0;
     float4 c[16];
+    if (rif_cell_interior(R, i0, j0, k0)) {
 #pragma unroll
-    for (int dz = 0; dz < 4; dz++) {
-        const size_t slab = 2 * (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
-        ldg256(base + slab + rowA, c[dz * 4 + 0], c[dz * 4 + 1]);
-        ldg256(base + slab + rowB, c[dz * 4 + 2], c[dz * 4 + 3]);
+        for (int dz = 0; dz < 4; dz++) rif_slab_tex(R, i0, j0, k0 - 1 + dz, c + 4 * dz);
+    } else {
+#pragma unroll 1
+        for (int dz = 0; dz < 4; dz++) rif_slab_clamped(R, i0, j0, k0 - 1 + dz, c + 4 * dz);
     }
 
     float accF = 0.f, accX = 0.f, accY = 0.f, accZ = 0.f;
@@ -251,22 +276,39 @@ template <> struct StencilCache<MER_RIF_TRILINEAR_PACKED> : StencilStore<8> {
     __device__ __forceinline__ void invalidate() { bind(); i = j = k = -0x7fffffff; }
 };
 
-__device__ __forceinline__ void stencil_ensure(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
-    if (i0 != S.i || j0 != S.j || k0 != S.k) {
-        const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
-        const float4 *base = R.coeff8 + 2 * (size_t) clampi(i0, 0, N0 - 1);
-        const size_t rowA = 2 * (size_t) clampi(j0 - 1, 0, N1 - 1) * (size_t) N0, rowB = 2 * (size_t) clampi(j0 + 1, 0, N1 - 1) * (size_t) N0;
+/* unconditional (re)load of the block of cell (i0, j0, k0) */
+__device__ __forceinline__ void rif_fetch(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
+    if (rif_cell_interior(R, i0, j0, k0)) {
 #pragma unroll
         for (int dz = 0; dz < 4; dz++) {
-            const size_t slab = 2 * (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
-            float4 a, b;
-            ldg256(base + slab + rowA, a, b);
-            S.set(dz * 4 + 0, a); S.set(dz * 4 + 1, b);
-            ldg256(base + slab + rowB, a, b);
-            S.set(dz * 4 + 2, a); S.set(dz * 4 + 3, b);
+            float4 c[4];
+            rif_slab_tex(R, i0, j0, k0 - 1 + dz, c);
+            S.set(dz * 4 + 0, c[0]); S.set(dz * 4 + 1, c[1]); S.set(dz * 4 + 2, c[2]); S.set(dz * 4 + 3, c[3]);
+        }
+    } else {
+#pragma unroll
+        for (int dz = 0; dz < 4; dz++) {
+            float4 c[4];
+            rif_slab_clamped(R, i0, j0, k0 - 1 + dz, c);
+            S.set(dz * 4 + 0, c[0]); S.set(dz * 4 + 1, c[1]); S.set(dz * 4 + 2, c[2]); S.set(dz * 4 + 3, c[3]);
+        }
+    }
+    S.i = i0; S.j = j0; S.k = k0;
+}
+/* the same for a SPECULATIVE request: interior cells only (anything else is left to the exact request that follows) */
+__device__ __forceinline__ void rif_fetch_interior(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
+    if (rif_cell_interior(R, i0, j0, k0)) {
+#pragma unroll
+        for (int dz = 0; dz < 4; dz++) {
+            float4 c[4];
+            rif_slab_tex(R, i0, j0, k0 - 1 + dz, c);
+            S.set(dz * 4 + 0, c[0]); S.set(dz * 4 + 1, c[1]); S.set(dz * 4 + 2, c[2]); S.set(dz * 4 + 3, c[3]);
         }
         S.i = i0; S.j = j0; S.k = k0;
     }
+}
+__device__ __forceinline__ void stencil_ensure(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
+    if (i0 != S.i || j0 != S.j || k0 != S.k) rif_fetch(R, S, i0, j0, k0);
 }
 
 /* sm_100's packed FP32 (fma.rn.f32x2: two FMAs on a 64-bit register pair in ONE issue slot; measured at the scalar FLOP
@@ -394,49 +436,6 @@ template <int MODE> __device__ __forceinline__ void rif_speculate(const RifDev &
 #endif
 }
 
-/* Software prefetch of the NEXT cell's stencil rows.  A warp stalls for a full L2/HBM round trip whenever
- * one of its lanes changes cell (at h = pitch/4 that is almost every warp-step).  The position one step ahead
- * is predictable to O(h^2) by linear extrapolation, so when it falls into a different cell the 16 rows of that
- * cell are pulled towards L1 one step early; the real (dependent) fetch of the next step then hits on chip. */
-#ifndef MER_PREFETCH
-#define MER_PREFETCH 0 /* measured: CCTL.E.PF1 + the extra index math cost more than the latency they hide (-15 %) */
-#endif
-__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
-
-__device__ __forceinline__ void rif_prefetch_tricubic(const RifDev &R, float3 pvNext, int ci, int cj, int ck) {
-    const int i0 = (int) floorf((pvNext.x - R.xmin[0]) * R.xres[0]), j0 = (int) floorf((pvNext.y - R.xmin[1]) * R.xres[1]),
-              k0 = (int) floorf((pvNext.z - R.xmin[2]) * R.xres[2]);
-    if (i0 != ci || j0 != cj || k0 != ck) {
-        const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
-        const float4 *base = R.coeff8 + 2 * (size_t) clampi(i0, 0, N0 - 1);
-#pragma unroll
-        for (int dz = 0; dz < 4; dz++) {
-            const size_t slab = 2 * (size_t) clampi(k0 - 1 + dz, 0, N2 - 1) * (size_t) N0 * (size_t) N1;
-            prefetch_l1(base + slab + 2 * (size_t) clampi(j0 - 1, 0, N1 - 1) * (size_t) N0);
-            prefetch_l1(base + slab + 2 * (size_t) clampi(j0 + 1, 0, N1 - 1) * (size_t) N0);
-        }
-    }
-}
-__device__ __forceinline__ void rif_prefetch_trilinear(const RifDev &R, float3 pvNext, int ci, int cj, int ck) {
-    const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
-    const int i0 = clampi((int) floorf((pvNext.x - R.xmin[0]) * R.xres[0]), 0, N0 - 2),
-              j0 = clampi((int) floorf((pvNext.y - R.xmin[1]) * R.xres[1]), 0, N1 - 2),
-              k0 = clampi((int) floorf((pvNext.z - R.xmin[2]) * R.xres[2]), 0, N2 - 2);
-    if (i0 != ci || j0 != cj || k0 != ck) {
-        const float4 *b = R.packed + ((size_t) k0 * N1 + j0) * (size_t) N0 + i0;
-        const size_t sy = N0, sz = (size_t) N0 * N1;
-        prefetch_l1(b); prefetch_l1(b + sy); prefetch_l1(b + sz); prefetch_l1(b + sz + sy); /* x and x+1 share a sector pair */
-        prefetch_l1(b + 1); prefetch_l1(b + sy + 1); prefetch_l1(b + sz + 1); prefetch_l1(b + sz + sy + 1);
-    }
-}
-template <int MODE> __device__ __forceinline__ void rif_prefetch(const RifDev &R, float3 pwNext, const StencilCache<MODE> &S) {
-#if MER_PREFETCH
-    const float3 pv = rif_to_volume(R, pwNext);
-    if (MODE == MER_RIF_TRICUBIC) rif_prefetch_tricubic(R, pv, S.i, S.j, S.k);
-    else rif_prefetch_trilinear(R, pv, S.i, S.j, S.k);
-#endif
-}
-
 template <int MODE>
 __device__ __forceinline__ void rif_lookup_cached(const RifDev &R, float3 pw, StencilCache<MODE> &S, float &n, float3 &G);
 template <>
@@ -451,6 +450,93 @@ __device__ __forceinline__ void rif_lookup_cached<MER_RIF_TRILINEAR_PACKED>(cons
                                                                              float &n, float3 &G) {
     rif_trilinear_cached(R, rif_to_volume(R, pw), S, n, G);
     G = rif_rot_t(R, G);
+}
+
+/* ------------------------------------------------------------------ split lookup: cell -> fetch -> contract
+ * The wavefront stepper (mer_render.cu) software-pipelines a step: the drift of step k+1 is applied right after the
+ * second kick of step k, so the EXACT next cell is known a whole loop turn before its contraction and the block is
+ * requested there (one fetch site, no prediction).  That needs the lookup in three pieces.  Same arithmetic as
+ * rif_tricubic_cached / rif_trilinear_cached, operation for operation. */
+struct CellPos {
+    float x, y, z; /* continuous grid coordinates */
+    int i, j, k;   /* cell index = key of the cached block */
+};
+
+/* XFORM = false: the caller knows the volume has no toWorld transform (the kernel variant is chosen on the host), so the
+ * twelve matrix entries are not even loaded */
+template <int MODE, bool XFORM = true> __device__ __forceinline__ CellPos rif_cell(const RifDev &R, float3 pw) {
+    const float3 pv = XFORM ? rif_to_volume(R, pw) : pw;
+    CellPos c;
+    c.x = (pv.x - R.xmin[0]) * R.xres[0];
+    c.y = (pv.y - R.xmin[1]) * R.xres[1];
+    c.z = (pv.z - R.xmin[2]) * R.xres[2];
+    if (MODE == MER_RIF_TRICUBIC) {
+        c.i = (int) floorf(c.x); c.j = (int) floorf(c.y); c.k = (int) floorf(c.z);
+    } else {
+        c.i = clampi((int) floorf(c.x), 0, R.N[0] - 2);
+        c.j = clampi((int) floorf(c.y), 0, R.N[1] - 2);
+        c.k = clampi((int) floorf(c.z), 0, R.N[2] - 2);
+    }
+    return c;
+}
+
+template <int MODE> __device__ __forceinline__ bool stencil_has(const StencilCache<MODE> &S, const CellPos &c) {
+    return c.i == S.i && c.j == S.j && c.k == S.k;
+}
+
+__device__ __forceinline__ void rif_fetch(const RifDev &R, StencilCache<MER_RIF_TRILINEAR_PACKED> &S, int i0, int j0, int k0) {
+    S.i = -0x7fffffff;
+    stencil_ensure(R, S, i0, j0, k0);
+}
+__device__ __forceinline__ void rif_fetch_interior(const RifDev &R, StencilCache<MER_RIF_TRILINEAR_PACKED> &S, int i0, int j0, int k0) {
+    rif_fetch(R, S, i0, j0, k0); /* indices are clamped into the grid by rif_cell */
+}
+
+/* contraction of the cached block at grid coordinates c; gradient in world space.  AFTER_X runs between the x stage
+ * (the last reader of the 64 cached coefficients) and the y/z stages: the stepper requests the block of the predicted
+ * next cell there, into the same registers, with the rest of the step still to overlap the loads. */
+template <bool XFORM = true, typename AfterX>
+__device__ __forceinline__ void rif_contract(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, const CellPos &c, float &f, float3 &G, AfterX afterX) {
+    float wx0[4], wx1[4], wy0[4], wy1[4], wz0[4], wz1[4];
+    bs_weights(c.x, floorf(c.x), wx0, wx1);
+    bs_weights(c.y, floorf(c.y), wy0, wy1);
+    bs_weights(c.z, floorf(c.z), wz0, wz1);
+    float a0[16], a1[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const float4 q = S.get(r);
+        a0[r] = q.x * wx0[0] + q.y * wx0[1] + q.z * wx0[2] + q.w * wx0[3];
+        a1[r] = q.x * wx1[0] + q.y * wx1[1] + q.z * wx1[2] + q.w * wx1[3];
+    }
+    afterX(S);
+    float accF = 0.f, accX = 0.f, accY = 0.f, accZ = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 4; dz++) {
+        float b00 = 0.f, b10 = 0.f, b01 = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 4; dy++) {
+            b00 = fmaf(a0[dz * 4 + dy], wy0[dy], b00);
+            b10 = fmaf(a1[dz * 4 + dy], wy0[dy], b10);
+            b01 = fmaf(a0[dz * 4 + dy], wy1[dy], b01);
+        }
+        accF = fmaf(b00, wz0[dz], accF);
+        accX = fmaf(b10, wz0[dz], accX);
+        accY = fmaf(b01, wz0[dz], accY);
+        accZ = fmaf(b00, wz1[dz], accZ);
+    }
+    f = accF;
+    G = f3(accX * R.xres[0], accY * R.xres[1], accZ * R.xres[2]);
+    if (XFORM) G = rif_rot_t(R, G);
+}
+template <bool XFORM = true, typename AfterX>
+__device__ __forceinline__ void rif_contract(const RifDev &R, StencilCache<MER_RIF_TRILINEAR_PACKED> &S, const CellPos &c, float &f, float3 &G, AfterX afterX) {
+    const float tx = c.x - (float) c.i, ty = c.y - (float) c.j, tz = c.z - (float) c.k;
+    const float4 r0 = lerp4(S.get(0), S.get(1), tx), r1 = lerp4(S.get(2), S.get(3), tx), r2 = lerp4(S.get(4), S.get(5), tx), r3 = lerp4(S.get(6), S.get(7), tx);
+    afterX(S);
+    const float4 r = lerp4(lerp4(r0, r1, ty), lerp4(r2, r3, ty), tz);
+    f = r.x;
+    G = f3(r.y, r.z, r.w);
+    if (XFORM) G = rif_rot_t(R, G);
 }
 
 /* SplineDataSource::valueAndGradient (splinevolume.cpp:352-358) in the handle's mode, world space */

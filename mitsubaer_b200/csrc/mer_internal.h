@@ -19,8 +19,10 @@ struct mer_rif {
     mer_volume_desc desc;
     RifDev dev;
     float *d_coeff;
-    float4 *d_coeff8;
     float4 *d_packed;
+    cudaArray_t texArray = nullptr; /* atlas of the coefficient layers (texture storage) */
+    size_t texW = 0, texH = 0;
+    cudaTextureObject_t tex = 0;
 };
 
 struct mer_grid {
@@ -45,6 +47,7 @@ struct RenderScratch {
     unsigned *nOut = nullptr;
     unsigned long long *counters = nullptr;
     unsigned long long *hostPinned = nullptr;
+    void *paramsDev = nullptr, *paramsHost = nullptr; /* RenderParams of the pass in flight (global copy + pinned staging) */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void release() {
         for (void *&p : pool) { cudaFree(p); p = nullptr; }
@@ -59,6 +62,9 @@ struct RenderScratch {
         cudaFree(counters); counters = nullptr;
         if (hostPinned) cudaFreeHost(hostPinned);
         hostPinned = nullptr;
+        cudaFree(paramsDev); paramsDev = nullptr;
+        if (paramsHost) cudaFreeHost(paramsHost);
+        paramsHost = nullptr;
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         ev0 = ev1 = nullptr;
@@ -81,7 +87,13 @@ void set_error(const std::string &msg);
  * a scene that is torn down and rebuilt (the e2e leg of bench.py, a host that reloads volumes) reuses the memory instead of
  * paying cudaMalloc / cudaFree of half a gigabyte each time (measured: 0.2-0.8 s per rebuild of C2, depending on the box). */
 cudaError_t pool_malloc(void **p, size_t bytes);
-void pool_free(void *p);
+void pool_free(void *p);     /* stream-ordered free; call pool_quiesce() first, once per handle */
+void pool_quiesce();
+void pool_trim(int device);
+/* CUDA arrays of the coefficient atlases are cached the same way (cudaMallocArray / cudaFreeArray are synchronising) */
+cudaError_t array_acquire(int device, size_t W, size_t H, cudaArray_t *out);
+void array_release(int device, cudaArray_t arr, size_t W, size_t H);
+void array_cache_trim(int device);
 int fail(int code, const std::string &msg);
 extern std::atomic<uint64_t> g_launches;
 

@@ -63,7 +63,9 @@ enum {
     FLAG_TB = 1, FLAG_MOVED = 2,
     FLAG_OUTWARD = 4, /* reached the surface from inside */
     FLAG_COVERED = 8, /* the quad's light along the current edge chain is estimated by a direct connection */
-    FLAG_PARKED = 16  /* the request queue is full: wait for the next pass */
+    FLAG_PARKED = 16, /* the request queue is full: wait for the next pass */
+    FLAG_DRIFTED = 32, /* first kick + drift of the step `kind` are already applied (software-pipelined stepper) */
+    FLAG_DMOVED = 64   /* ... and that drift changed p */
 };
 
 enum { ST_SAMPLES = 0, ST_STEPS, ST_SCATTER, ST_NULL, ST_EXIT, ST_NONFINITE, ST_CONN, ST_CONNFAIL, ST_CONNSTEPS, ST_COUNT };
@@ -104,6 +106,7 @@ struct RenderParams {
     unsigned *nOut;
     unsigned long long *sampleCounter;
     unsigned long long *stats;
+    const RenderParams *self; /* a copy of this struct in global memory, for the out-of-line event code */
     /* direct connections */
     int nee, neePrecision, neeMaxIterations, neeStraightFirst;
     float neeTol2, neeRRWeight;
@@ -251,12 +254,13 @@ __device__ __forceinline__ float path_weight(const RenderParams &P, float len) {
     return 0.0f;
 }
 
+#define ST_INC(st, i) atomicAdd(&(st)[i], 1u)
 __device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha, float wgt, int frame,
-                                         unsigned &nonfinite) {
+                                         unsigned *nonfinite) {
     const float value[5] = {L[0], L[1], L[2], alpha, wgt};
 #pragma unroll
     for (int k = 0; k < 5; k++)
-        if (!isfinite(value[k])) { nonfinite++; return; }
+        if (!isfinite(value[k])) { atomicAdd(nonfinite, 1u); return; }
     const float px = sx - 0.5f, py = sy - 0.5f, r = P.filterRadius;
     const int x0 = max((int) ceilf(px - r), 0), y0 = max((int) ceilf(py - r), 0),
               x1 = min((int) floorf(px + r), P.W - 1), y1 = min((int) floorf(py + r), P.H - 1);
@@ -295,11 +299,11 @@ __device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, co
     if (EXTRAS && P.modulation) {
         const float w = path_weight(P, pathLength);
         const float mod[3] = {rad[0] * w, rad[1] * w, rad[2] * w};
-        film_put(P, sx, sy, mod, alpha, 1.0f, 0, st[ST_NONFINITE]);
+        film_put(P, sx, sy, mod, alpha, 1.0f, 0, st + ST_NONFINITE);
         L.kind = E_NEW;
         return;
     }
-    film_put(P, sx, sy, rad, alpha, 1.0f, EXTRAS ? path_frame(P, pathLength) : 0, st[ST_NONFINITE]);
+    film_put(P, sx, sy, rad, alpha, 1.0f, EXTRAS ? path_frame(P, pathLength) : 0, st + ST_NONFINITE);
     L.kind = E_NEW;
 }
 
@@ -376,7 +380,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             /* ---- SamplingIntegrator::renderBlock: next (pixel, sample) */
             unsigned long long g = atomicAdd(P.sampleCounter, 1ULL);
             if (g >= P.totalSamples) { L.kind = K_DEAD; break; }
-            st[ST_SAMPLES]++;
+            ST_INC(st, ST_SAMPLES);
             unsigned pixel, k;
             if (P.totalSamples <= 0xffffffffULL) { /* warp-uniform: 32-bit division in the common case */
                 pixel = (unsigned) g / (unsigned) P.sppLocal;
@@ -536,7 +540,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                         scatter = true;
                         edge[0] = M.albedo[0]; edge[1] = M.albedo[1]; edge[2] = M.albedo[2];
                     } else {
-                        st[ST_NULL]++;
+                        ST_INC(st, ST_NULL);
                         float dist = __fmul_rn(-fastlog_dev(1.0f - L.rng.next()), M.invMaxDensity);
                         int moved = L.flags & FLAG_MOVED;
                         begin_trace(P, L, dist);
@@ -558,14 +562,14 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             if (EXTRAS && P.lightMode) rrs = 1.0f; /* weight[EImportance] carries no refRatioSq, edge.cpp:96-98 */
             const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
             if (scatter) {
-                st[ST_SCATTER]++;
+                ST_INC(st, ST_SCATTER);
                 if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
 #pragma unroll
                 for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
                 if (EXTRAS) L.kind = E_SCATTER; /* the vertex may have to wait for a slot of the request queue */
                 else scatter_and_roulette<DIELECTRIC, false>(P, L, f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv), st);
             } else {
-                st[ST_EXIT]++;
+                ST_INC(st, ST_EXIT);
 #pragma unroll
                 for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
                 if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
@@ -590,20 +594,67 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
     }
 }
 
-template <int MODE, bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE>
-__global__ void __launch_bounds__(128, MER_RENDER_MIN_BLOCKS)
-k_render_pass(const __grid_constant__ RenderParams P) {
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    const MediumDev &M = P.M;
-    Lane L;
-    unsigned st[ST_COUNT];
-#pragma unroll
-    for (int i = 0; i < ST_COUNT; i++) st[i] = 0;
+/* ------------------------------------------------------------------ two paths per lane
+ * A lane owns TWO paths: the active one (hot state in registers) and an alternate one parked in shared memory.  When the
+ * active path reaches an event (end of a free flight every 30-120 steps: scatter, null collision, exit, new sample) the
+ * lane swaps to its alternate path and keeps stepping; the event is handled later, when enough of the warp's 64 paths
+ * are waiting, by a lane-dense event phase.  (Round 1 had one path per lane: a lane that reached an event idled until 12
+ * lanes were waiting — 16-19 % of the step slots — and the event code then ran for 12 of 32 lanes: ncu r01, 20.5 of 32.)
+ * The state is split in two: HOT (what a step reads and writes, 15 words) moves between registers and shared memory on a
+ * swap; COLD (throughput, sample id, RNG position, ... 11 words) stays in shared memory for both paths and is loaded only
+ * for the event code, so it costs no registers in the step loop.  Layout [word][thread]: conflict-free, 18.5 KB per CTA. */
+enum { HOT_WORDS = 14, COLD_WORDS = 11, LANE_SMEM_WORDS = HOT_WORDS + 2 * COLD_WORDS };
 
-    if (tid < P.nIn) {
-        float4 a = P.in.q0[tid], b = P.in.q1[tid], c = P.in.q2[tid], d = P.in.q3[tid];
-        uint4 e = P.in.q4[tid];
+__device__ __forceinline__ bool is_waiting(int kind, int flags) { return kind >= E_BEGIN && kind != K_DEAD && !(flags & FLAG_PARKED); }
+
+/* hot state of the active path <-> alternate slot; the alternate path's kind/flags live in the register altKF */
+/* altKF = kind | flags << 8 of the alternate path, bit 31 = cold slot of the ACTIVE path (one register for both) */
+#define ALT_CUR 0x80000000u
+__device__ __forceinline__ void hot_swap(Lane &L, unsigned &altKF, uint32_t *sm) {
+#define MER_XF(w, f) { const float t_ = __uint_as_float(sm[(w) * MER_STENCIL_BLOCK]); sm[(w) * MER_STENCIL_BLOCK] = __float_as_uint(f); f = t_; }
+    MER_XF(0, L.p.x) MER_XF(1, L.p.y) MER_XF(2, L.p.z)
+    MER_XF(3, L.v.x) MER_XF(4, L.v.y) MER_XF(5, L.v.z)
+    MER_XF(6, L.n) MER_XF(7, L.G.x) MER_XF(8, L.G.y) MER_XF(9, L.G.z)
+    MER_XF(10, L.rem) MER_XF(11, L.distSurf) MER_XF(12, L.opl)
+#undef MER_XF
+    { const int t_ = (int) sm[13 * MER_STENCIL_BLOCK]; sm[13 * MER_STENCIL_BLOCK] = (unsigned) L.stepsLeft; L.stepsLeft = t_; }
+    const unsigned t = altKF;
+    altKF = ((unsigned) L.kind | ((unsigned) L.flags << 8)) | ((t & ALT_CUR) ^ ALT_CUR); /* the other cold slot is the active one now */
+    L.kind = (int) (t & 0xffu);
+    L.flags = (int) ((t >> 8) & 0xffu);
+    L.safe = 0.0f;
+}
+__device__ __forceinline__ void hot_store(const Lane &L, uint32_t *sm) {
+    sm[0 * MER_STENCIL_BLOCK] = __float_as_uint(L.p.x); sm[1 * MER_STENCIL_BLOCK] = __float_as_uint(L.p.y); sm[2 * MER_STENCIL_BLOCK] = __float_as_uint(L.p.z);
+    sm[3 * MER_STENCIL_BLOCK] = __float_as_uint(L.v.x); sm[4 * MER_STENCIL_BLOCK] = __float_as_uint(L.v.y); sm[5 * MER_STENCIL_BLOCK] = __float_as_uint(L.v.z);
+    sm[6 * MER_STENCIL_BLOCK] = __float_as_uint(L.n);
+    sm[7 * MER_STENCIL_BLOCK] = __float_as_uint(L.G.x); sm[8 * MER_STENCIL_BLOCK] = __float_as_uint(L.G.y); sm[9 * MER_STENCIL_BLOCK] = __float_as_uint(L.G.z);
+    sm[10 * MER_STENCIL_BLOCK] = __float_as_uint(L.rem); sm[11 * MER_STENCIL_BLOCK] = __float_as_uint(L.distSurf); sm[12 * MER_STENCIL_BLOCK] = __float_as_uint(L.opl);
+    sm[13 * MER_STENCIL_BLOCK] = (unsigned) L.stepsLeft;
+}
+__device__ __forceinline__ void cold_store(const Lane &L, uint32_t *sm, int slot) {
+    uint32_t *c = sm + (HOT_WORDS + slot * COLD_WORDS) * MER_STENCIL_BLOCK;
+    c[0 * MER_STENCIL_BLOCK] = __float_as_uint(L.thr[0]); c[1 * MER_STENCIL_BLOCK] = __float_as_uint(L.thr[1]); c[2 * MER_STENCIL_BLOCK] = __float_as_uint(L.thr[2]);
+    c[3 * MER_STENCIL_BLOCK] = __float_as_uint(L.refStart); c[4 * MER_STENCIL_BLOCK] = __float_as_uint(L.segDist); c[5 * MER_STENCIL_BLOCK] = __float_as_uint(L.sd);
+    c[6 * MER_STENCIL_BLOCK] = __float_as_uint(L.etaPath);
+    c[7 * MER_STENCIL_BLOCK] = (unsigned) L.depth; c[8 * MER_STENCIL_BLOCK] = L.rng.k; c[9 * MER_STENCIL_BLOCK] = L.pixel; c[10 * MER_STENCIL_BLOCK] = L.sample;
+}
+__device__ __forceinline__ void cold_load(const RenderParams &P, Lane &L, const uint32_t *sm, int slot) {
+    const uint32_t *c = sm + (HOT_WORDS + slot * COLD_WORDS) * MER_STENCIL_BLOCK;
+    L.thr[0] = __uint_as_float(c[0 * MER_STENCIL_BLOCK]); L.thr[1] = __uint_as_float(c[1 * MER_STENCIL_BLOCK]); L.thr[2] = __uint_as_float(c[2 * MER_STENCIL_BLOCK]);
+    L.refStart = __uint_as_float(c[3 * MER_STENCIL_BLOCK]); L.segDist = __uint_as_float(c[4 * MER_STENCIL_BLOCK]); L.sd = __uint_as_float(c[5 * MER_STENCIL_BLOCK]);
+    L.etaPath = __uint_as_float(c[6 * MER_STENCIL_BLOCK]);
+    L.depth = (int) c[7 * MER_STENCIL_BLOCK];
+    L.pixel = c[9 * MER_STENCIL_BLOCK]; L.sample = c[10 * MER_STENCIL_BLOCK];
+    L.rng.init(P.seed, (unsigned long long) L.pixel * (unsigned long long) P.sppTotal + L.sample, c[8 * MER_STENCIL_BLOCK]);
+}
+
+/* persisted path -> Lane (pool index idx), or a lane that asks for a fresh camera sample */
+template <bool DIELECTRIC, bool EXTRAS>
+__device__ __forceinline__ void path_load(const RenderParams &P, unsigned idx, Lane &L) {
+    if (idx < P.nIn) {
+        float4 a = P.in.q0[idx], b = P.in.q1[idx], c = P.in.q2[idx], d = P.in.q3[idx];
+        uint4 e = P.in.q4[idx];
         L.p = f3(a.x, a.y, a.z);
         L.v = f3(a.w, b.x, b.y);
         L.thr[0] = b.z; L.thr[1] = b.w; L.thr[2] = c.x;
@@ -612,12 +663,11 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.kind = (int) (e.x & 0xffu); L.flags = (int) (e.x >> 8) & ~FLAG_PARKED;
         L.pixel = e.z; L.sample = e.w;
         L.rng.init(P.seed, (unsigned long long) e.z * (unsigned long long) P.sppTotal + e.w, e.y);
-        float4 fg = P.in.q5[tid];
+        float4 fg = P.in.q5[idx];
         L.n = fg.x; L.G = f3(fg.y, fg.z, fg.w);
         L.etaPath = 1.0f;
         L.opl = 0.0f;
-        L.safe = 0.0f;
-        if (DIELECTRIC || EXTRAS) { const float4 ex = P.in.q6[tid]; L.etaPath = ex.x; L.opl = ex.y; }
+        if (DIELECTRIC || EXTRAS) { const float4 ex = P.in.q6[idx]; L.etaPath = ex.x; L.opl = ex.y; }
     } else {
         L.p = L.v = L.G = f3(0.f, 0.f, 0.f);
         L.n = 1.0f;
@@ -625,70 +675,17 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         L.refStart = L.segDist = L.distSurf = L.rem = L.sd = 0.0f;
         L.etaPath = 1.0f;
         L.opl = 0.0f;
-        L.safe = 0.0f;
         L.stepsLeft = L.depth = L.flags = 0;
         L.pixel = L.sample = 0;
         L.rng.init(P.seed, 0ULL, 0u);
         L.kind = E_NEW;
     }
+    L.safe = 0.0f;
+}
 
-    StencilCache<MODE> S; /* registers only: refilled by the first step of the pass */
-    S.invalidate();
-    const float h = M.h;
-    int budget = P.stepsPerPass;
-    float oplUnused = 0.0f;
-    /* ONE flat loop, three votes per iteration, and a two-way (warp-uniform) choice between a convergent
-     * step and the event phase.  (A nested step-loop/event-loop formulation left the halves of a warp
-     * that diverged in the event phase running the 600-instruction step body one after the other for
-     * the rest of the pass: ncu r01a/r01b, 19 of 32 lanes active.) */
-    while (true) {
-        /* Explicit reconvergence.  The event phase leaves the warp split into groups (its BSYNC is a plain one
-         * with YIELDs), and from then on every group would run the step body on its own, meeting the others
-         * only inside the collective votes (ncu r01c: 16 of 32 lanes active).  NVVM folds __syncwarp() into the
-         * following vote, so the barrier is spelled in PTX. */
-        asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
-        const bool stepping = L.kind <= K_ENTRY;
-        const bool waiting = L.kind >= E_BEGIN && L.kind != K_DEAD && !(L.flags & FLAG_PARKED);
-        const unsigned ms = __ballot_sync(0xffffffffu, stepping);
-        const unsigned mw = __ballot_sync(0xffffffffu, waiting);
-        if (ms != 0u && budget > 0 && __popc(mw) < P.maxWait) {
-            /* ---------------- convergent stepping phase */
-            budget--;
-            if (stepping) {
-                /* K_ENTRY is a zero-length step: with hc = 0 the kicks and the drift are exact no-ops and
-                 * only the field fetch remains, so the warp has ONE lookup call site */
-                const int kind = L.kind;
-                const float hc = kind == K_FULL ? h : (kind == K_REM ? L.rem : (kind == K_BACKF ? -h : (kind == K_BACKR ? -L.rem : 0.0f)));
-                const float3 pOld = L.p;
-                er_step_fused<MODE>(M.rif, S, L.p, L.v, L.n, L.G, hc, EXTRAS ? L.opl : oplUnused);
-                const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
-                const bool moved = L.p.x != pOld.x || L.p.y != pOld.y || L.p.z != pOld.z;
-                int next;
-                if (kind == K_FULL) {
-                    next = inside ? ((L.stepsLeft == 1) ? ((L.flags & FLAG_TB) ? E_EXIT : K_REM) : K_FULL) : K_BACKF;
-                    if (inside) { L.distSurf += h; L.stepsLeft--; }
-                } else if (kind == K_REM) {
-                    next = inside ? E_REACHED : K_BACKR;
-                    if (inside) L.distSurf += L.rem;
-                } else if (kind == K_ENTRY) {
-                    next = DIELECTRIC ? E_SURFACE : E_BEGIN;
-                } else {
-                    if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= h; /* :761 */
-                    next = E_EXIT;
-                }
-                if (kind <= K_REM && inside && moved) L.flags |= FLAG_MOVED;
-                if (kind != K_ENTRY) st[ST_STEPS]++;
-                L.kind = next;
-            }
-        } else if (mw != 0u) {
-            /* ---------------- event phase: scatter / exit / regenerate for every waiting lane at once */
-            if (waiting) handle_events<DIELECTRIC, EXTRAS, SDFSHAPE>(P, L, st);
-        } else {
-            break; /* budget exhausted (or nobody alive) and nothing waiting */
-        }
-    }
-
-    /* ---------------- compaction: survivors go to the output queue, one atomic per warp */
+/* survivors go to the output queue compacted: warp ballot, popc prefix, one atomic per warp */
+template <bool DIELECTRIC, bool EXTRAS>
+__device__ __forceinline__ void path_store(const RenderParams &P, const Lane &L, unsigned lane) {
     const bool live = L.kind != K_DEAD;
     const unsigned m = __ballot_sync(0xffffffffu, live);
     unsigned base = 0;
@@ -704,14 +701,182 @@ k_render_pass(const __grid_constant__ RenderParams P) {
         P.out.q5[o] = make_float4(L.n, L.G.x, L.G.y, L.G.z);
         if (DIELECTRIC || EXTRAS) P.out.q6[o] = make_float4(L.etaPath, L.opl, 0.f, 0.f);
     }
+}
 
-    /* ---------------- statistics: warp reduce, one atomic per warp and counter */
-#pragma unroll
-    for (int i = 0; i < ST_COUNT; i++) {
-        unsigned v = st[i];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicAdd(P.stats + i, (unsigned long long) v);
+/* K_FULL +h, K_REM +rem, K_BACKF -h, K_BACKR -rem, K_ENTRY 0: selects, no branches (bit 0 = remainder, bit 1 = backwards) */
+__device__ __forceinline__ float step_length(int kind, float h, float rem) {
+    const float mag = (kind & 1) ? rem : h;
+    const float sgn = (kind & 2) ? -mag : mag;
+    return kind == K_ENTRY ? 0.0f : sgn;
+}
+
+/* first half of er_step (:655-657): kick, drift with n at the OLD point, optical length.  Rounded operation by operation
+ * like the reference's float build (see er_step_fused). */
+template <bool EXTRAS>
+__device__ __forceinline__ void lane_drift(Lane &L, float hc) {
+    const float hs = __fmul_rn(0.5f, hc);
+    L.v = f3(__fadd_rn(L.v.x, __fmul_rn(hs, L.G.x)), __fadd_rn(L.v.y, __fmul_rn(hs, L.G.y)), __fadd_rn(L.v.z, __fmul_rn(hs, L.G.z)));
+    const float recip = __frcp_rn(L.n);
+    const float3 pOld = L.p;
+    L.p = f3(__fadd_rn(L.p.x, __fmul_rn(__fmul_rn(hc, L.v.x), recip)), __fadd_rn(L.p.y, __fmul_rn(__fmul_rn(hc, L.v.y), recip)),
+             __fadd_rn(L.p.z, __fmul_rn(__fmul_rn(hc, L.v.z), recip)));
+    if (EXTRAS) L.opl = __fadd_rn(L.opl, __fmul_rn(hc, L.n));
+    const bool moved = L.p.x != pOld.x || L.p.y != pOld.y || L.p.z != pOld.z;
+    L.flags |= FLAG_DRIFTED | (moved ? FLAG_DMOVED : 0);
+}
+
+/* The event code as a real call: out of line it neither shares the step loop's registers nor drags its ~60 kernel
+ * parameters into the loop (inlined, ptxas hoisted their loads to the loop head: 30 LDCU per turn, ncu r02a/b), and the
+ * hot loop shrinks to what the instruction cache holds.  The hot state crosses the call through the stack (cold path). */
+template <bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE>
+__device__ __noinline__ void handle_events_call(const RenderParams *Pg, Lane *Lp, uint32_t *sm, int cur, unsigned *st) {
+    const RenderParams &P = *Pg;
+    Lane L = *Lp;
+    cold_load(P, L, sm, cur);
+    handle_events<DIELECTRIC, EXTRAS, SDFSHAPE>(P, L, st);
+    cold_store(L, sm, cur);
+    *Lp = L;
+}
+
+template <int MODE, bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE, bool XFORM>
+__global__ void __launch_bounds__(MER_STENCIL_BLOCK, MER_RENDER_MIN_BLOCKS)
+k_render_pass(const __grid_constant__ RenderParams P) {
+    __shared__ uint32_t laneSmem[LANE_SMEM_WORDS * MER_STENCIL_BLOCK];
+    __shared__ unsigned st[ST_COUNT];
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nThreads = gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const MediumDev &M = P.M;
+    uint32_t *sm = laneSmem + threadIdx.x;
+    if (threadIdx.x < ST_COUNT) st[threadIdx.x] = 0u;
+    __syncthreads();
+
+    /* path tid is the active one, path tid + nThreads the alternate */
+    Lane L;
+    unsigned altKF;
+    path_load<DIELECTRIC, EXTRAS>(P, tid + nThreads, L);
+    hot_store(L, sm);
+    cold_store(L, sm, 1);
+    altKF = (unsigned) L.kind | ((unsigned) L.flags << 8);
+    path_load<DIELECTRIC, EXTRAS>(P, tid, L);
+    cold_store(L, sm, 0);
+
+    StencilCache<MODE> S; /* registers only: refilled by the first step of the pass */
+    S.invalidate();
+    const float h = M.h;
+    int budget = P.stepsPerPass;
+    unsigned nSteps = 0;
+    /* An outer loop of event phases around an inner loop of convergent steps; both are left by warp-uniform votes
+     * only.  (The inner loop holds no calls and a fixed set of kernel parameters, which lets ptxas keep them in uniform
+     * registers across its turns; in one flat loop it reloaded ~50 of them every turn, 13 % of the issued
+     * instructions: ncu r02a.) */
+    while (true) {
+        int nw;
+        bool lw, aw;
+        while (true) {
+            /* Explicit reconvergence.  The event phase leaves the warp split into groups (its BSYNC is a plain one
+             * with YIELDs), and from then on every group would run the step body on its own, meeting the others
+             * only inside the collective votes (ncu r01c: 16 of 32 lanes active).  NVVM folds __syncwarp() into the
+             * following vote, so the barrier is spelled in PTX. */
+            asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+            /* a lane whose active path cannot step takes its alternate path if that one can */
+            if (L.kind > K_ENTRY && (int) (altKF & 0xffu) <= K_ENTRY) {
+                hot_swap(L, altKF, sm);
+                S.i = -0x7fffffff;
+            }
+            const bool stepping = L.kind <= K_ENTRY;
+            lw = is_waiting(L.kind, L.flags);
+            aw = is_waiting((int) (altKF & 0xffu), (int) ((altKF >> 8) & 0xffu));
+            const unsigned ms = __ballot_sync(0xffffffffu, stepping);
+            nw = __popc(__ballot_sync(0xffffffffu, lw)) + __popc(__ballot_sync(0xffffffffu, aw));
+            if (!(ms != 0u && budget > 0 && nw < P.maxWait)) break;
+            /* ---------------- convergent step, software-pipelined: a step is
+             *   [kick1 + drift]  ->  lookup at the new point  ->  [kick2, containment test, bookkeeping]
+             * and the first bracket of step k+1 runs right behind the second of step k, so the exact next cell is known
+             * at the end of a turn.  Its block is normally in flight by then: between the x stage of the contraction (the
+             * last reader of the cached coefficients) and the y/z stages the block of the PREDICTED next cell (one more
+             * drift with the old field) is requested into the same registers, a whole turn before it is needed.  A lane
+             * that finds its block missing at the top (misprediction, first step after an event or of a pass) has
+             * requested it at the end of the previous turn or does so now, and sits the turn out.
+             * K_ENTRY is a zero-length step: both brackets are exact no-ops and only the lookup remains. */
+            budget--;
+            bool counted = false; /* this turn completed an er_step (the count is kept per warp, in a uniform register) */
+            if (stepping) {
+                const int kind = L.kind;
+                const float hc = step_length(kind, h, L.rem);
+                if (!(L.flags & FLAG_DRIFTED)) lane_drift<EXTRAS>(L, hc);
+                CellPos c = rif_cell<MODE, XFORM>(M.rif, L.p);
+                bool want = true;
+                if (stencil_has(S, c)) {
+                    float rn; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(L.n)); /* prediction only */
+                    const CellPos cp = rif_cell<MODE, XFORM>(M.rif, f3(fmaf(h * L.v.x, rn, L.p.x), fmaf(h * L.v.y, rn, L.p.y), fmaf(h * L.v.z, rn, L.p.z)));
+                    rif_contract<XFORM>(M.rif, S, c, L.n, L.G, [&](StencilCache<MODE> &Sx) {
+                        if (MER_SPECULATE && kind == K_FULL && !stencil_has(Sx, cp)) rif_fetch_interior(M.rif, Sx, cp.i, cp.j, cp.k);
+                    });
+                    const float hs = __fmul_rn(0.5f, hc);
+                    L.v = f3(__fadd_rn(L.v.x, __fmul_rn(hs, L.G.x)), __fadd_rn(L.v.y, __fmul_rn(hs, L.G.y)), __fadd_rn(L.v.z, __fmul_rn(hs, L.G.z)));
+                    const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
+                    const bool moved = (L.flags & FLAG_DMOVED) != 0;
+                    int next;
+                    if (kind == K_FULL) {
+                        next = inside ? ((L.stepsLeft == 1) ? ((L.flags & FLAG_TB) ? E_EXIT : K_REM) : K_FULL) : K_BACKF;
+                        if (inside) { L.distSurf += h; L.stepsLeft--; }
+                    } else if (kind == K_REM) {
+                        next = inside ? E_REACHED : K_BACKR;
+                        if (inside) L.distSurf += L.rem;
+                    } else if (kind == K_ENTRY) {
+                        next = DIELECTRIC ? E_SURFACE : E_BEGIN;
+                    } else {
+                        if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= h; /* :761 */
+                        next = E_EXIT;
+                    }
+                    L.flags &= ~(FLAG_DRIFTED | FLAG_DMOVED);
+                    if (kind <= K_REM && inside && moved) L.flags |= FLAG_MOVED;
+                    counted = kind != K_ENTRY;
+                    L.kind = next;
+                    want = false;
+                    if (next <= K_BACKR) {
+                        lane_drift<EXTRAS>(L, step_length(next, h, L.rem));
+                        c = rif_cell<MODE, XFORM>(M.rif, L.p);
+                        want = !stencil_has(S, c);
+                    }
+                }
+                if (want) rif_fetch(M.rif, S, c.i, c.j, c.k);
+            }
+            nSteps += (unsigned) __popc(__ballot_sync(0xffffffffu, counted));
+        }
+        if (nw == 0) break; /* budget exhausted (or nobody alive) and nothing waiting */
+        /* ---------------- event phase: scatter / exit / regenerate for every waiting path the lane can bring into
+         * registers (an alternate path that waits while the active one does too is handled in the next turn) */
+        if (aw && !lw) {
+            hot_swap(L, altKF, sm);
+            S.i = -0x7fffffff;
+        }
+        if (is_waiting(L.kind, L.flags)) {
+            Lane T = L;
+            const int cur = (int) (altKF >> 31);
+            if (SDFSHAPE || EXTRAS) { /* inlined in these variants */
+                cold_load(P, T, sm, cur);
+                handle_events<DIELECTRIC, EXTRAS, SDFSHAPE>(P, T, st);
+                cold_store(T, sm, cur);
+            } else {
+                handle_events_call<DIELECTRIC, false, false>(P.self, &T, sm, cur, st);
+            }
+            L.p = T.p; L.v = T.v; L.n = T.n; L.G = T.G; L.rem = T.rem; L.distSurf = T.distSurf; L.opl = T.opl; L.safe = T.safe;
+            L.stepsLeft = T.stepsLeft; L.kind = T.kind; L.flags = T.flags;
+        }
     }
+
+    /* ---------------- compaction: both paths of the lane */
+    cold_load(P, L, sm, (int) (altKF >> 31));
+    path_store<DIELECTRIC, EXTRAS>(P, L, lane);
+    hot_swap(L, altKF, sm);
+    cold_load(P, L, sm, (int) (altKF >> 31));
+    path_store<DIELECTRIC, EXTRAS>(P, L, lane);
+
+    /* ---------------- statistics: one atomic per warp (steps) / CTA (events) and counter */
+    if (lane == 0 && nSteps) atomicAdd(P.stats + ST_STEPS, (unsigned long long) nSteps); /* a per-warp count */
+    __syncthreads();
+    if (threadIdx.x < ST_COUNT && st[threadIdx.x]) atomicAdd(P.stats + threadIdx.x, (unsigned long long) st[threadIdx.x]);
 }
 
 /* A warp of k_nee costs what its longest connection costs, and the cost is roughly the number of steps from the vertex to
@@ -769,7 +934,10 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const MediumDev &M = P.M;
-    unsigned st[3] = {0u, 0u, 0u}, nonfinite = 0u; /* connections, failed, steps */
+    unsigned st[3] = {0u, 0u, 0u}; /* connections, failed, steps */
+    __shared__ unsigned nonfinite;
+    if (threadIdx.x == 0) nonfinite = 0u;
+    __syncthreads();
     if (tid < nReq) {
         const unsigned i = P.neePerm ? P.neePerm[tid] : tid;
         const float4 a = P.neeQ0[i], b = P.neeQ1[i];
@@ -839,7 +1007,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                             for (int k = 0; k < 3; k++) rad[k] *= w;
                         }
                         const int frame = (WANT_OPL && !P.modulation) ? path_frame(P, len) : 0;
-                        if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, nonfinite);
+                        if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, &nonfinite);
                     }
                 }
             } else if (ok) {
@@ -869,7 +1037,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                     for (int k = 0; k < 3; k++) rad[k] *= w;
                 }
                 const int frame = (WANT_OPL && !P.modulation) ? path_frame(P, oplVertex + C.opl) : 0;
-                if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, nonfinite);
+                if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, &nonfinite);
             }
         }
         if (!ok) st[1] = 1u;
@@ -882,7 +1050,8 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0 && v) atomicAdd(P.stats + slots[k], v);
     }
-    if (nonfinite) atomicAdd(P.stats + ST_NONFINITE, (unsigned long long) nonfinite);
+    __syncthreads();
+    if (threadIdx.x == 0 && nonfinite) atomicAdd(P.stats + ST_NONFINITE, (unsigned long long) nonfinite);
 }
 
 /* a light-traced film has no camera samples: every pixel gets this GPU's share of a unit weight (and alpha), so that
@@ -996,8 +1165,9 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     }
     P.hasQuad = r->has_quad;
     P.stepsPerPass = r->steps_per_pass > 0 ? r->steps_per_pass : 2048;
-    P.maxWait = 12;
+    P.maxWait = 16; /* of the warp's 64 paths */
     if (const char *e = getenv("MER_MAX_WAIT")) P.maxWait = atoi(e); /* tuning knob */
+    P.maxWait = std::min(std::max(P.maxWait, 1), 64);
     P.film = film_dev;
     MER_REQUIRE(r->modulation >= MER_MODULATION_NONE && r->modulation <= MER_MODULATION_HAMILTONIAN, "unknown modulation");
     P.modulation = r->modulation;
@@ -1037,10 +1207,11 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.neeStraightFirst = r->connection.start_mode != MER_START_RANDOM;
 
     const unsigned TPB = 128;
-    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 4096u;
-    pool = ((pool + TPB - 1) / TPB) * TPB;
-    if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) (((P.totalSamples + TPB - 1) / TPB) * TPB);
-    if (pool == 0) pool = TPB;
+    /* `pool` counts path slots; a thread owns two of them (k_render_pass) */
+    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 2u * 148u * 4096u;
+    pool = ((pool + 2 * TPB - 1) / (2 * TPB)) * (2 * TPB);
+    if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) (((P.totalSamples + 2 * TPB - 1) / (2 * TPB)) * (2 * TPB));
+    if (pool == 0) pool = 2 * TPB;
 
     RenderScratch &S = mer::device_scratch(m->device);
     std::lock_guard<std::mutex> hold(S.lock);
@@ -1052,6 +1223,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         MER_CUDA(cudaMalloc(&S.nOut, sizeof(unsigned)));
         MER_CUDA(cudaMalloc(&S.counters, (1 + ST_COUNT) * sizeof(unsigned long long)));
         MER_CUDA(cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long)));
+        MER_CUDA(cudaMalloc(&S.paramsDev, sizeof(RenderParams)));
+        MER_CUDA(cudaMallocHost(&S.paramsHost, sizeof(RenderParams)));
         MER_CUDA(cudaEventCreate(&S.ev0));
         MER_CUDA(cudaEventCreate(&S.ev1));
     }
@@ -1094,16 +1267,24 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     MER_CUDA(cudaEventRecord(S.ev0, stream));
     while (true) {
         const bool fresh = started < P.totalSamples;
-        const unsigned threads = fresh ? pool : nLive;
-        if (threads == 0) break;
+        const unsigned paths = fresh ? pool : nLive;
+        if (paths == 0) break;
+        const unsigned threads = (paths + 1) / 2;
         P.in = (passes & 1) ? B : A;
         P.out = (passes & 1) ? A : B;
         P.nIn = nLive;
         MER_CUDA(cudaMemsetAsync(S.nOut, 0, sizeof(unsigned), stream));
         const unsigned blocks = (threads + TPB - 1) / TPB;
+        P.self = (const RenderParams *) S.paramsDev; /* the out-of-line event code reads its parameters from global memory */
+        memcpy(S.paramsHost, &P, sizeof(P));
+        MER_CUDA(cudaMemcpyAsync(S.paramsDev, S.paramsHost, sizeof(P), cudaMemcpyHostToDevice, stream));
         /* `transient` selects the kernels compiled with the extras: transient film, direct connections, light tracing */
         const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, transient = P.frames > 1 || P.modulation || P.nee || P.lightMode;
-#define MER_PASS(MODE_, D_, T_, S_) MER_LAUNCH((k_render_pass<MODE_, D_, T_, S_>), blocks, TPB, 0, stream, P)
+#define MER_PASS(MODE_, D_, T_, S_)                                                                                      \
+    do {                                                                                                                 \
+        if (m->dev.rif.hasXform) MER_LAUNCH((k_render_pass<MODE_, D_, T_, S_, true>), blocks, TPB, 0, stream, P);        \
+        else MER_LAUNCH((k_render_pass<MODE_, D_, T_, S_, false>), blocks, TPB, 0, stream, P);                           \
+    } while (0)
         if (m->dev.shapeType == MER_SHAPE_SDF) { /* tricubic only (checked above) */
             if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true, true); else MER_PASS(MER_RIF_TRICUBIC, true, false, true); }
             else { if (transient) MER_PASS(MER_RIF_TRICUBIC, false, true, true); else MER_PASS(MER_RIF_TRICUBIC, false, false, true); }

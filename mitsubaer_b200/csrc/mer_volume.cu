@@ -82,19 +82,6 @@ k_prefilter(const float *in, float *out, int N0, int N1, int N2, int pass) {
     }
 }
 
-/* coeff [z][y][x] -> coeff8 [z][y][x] = { (c[x-1], c[x], c[x+1], c[x+2]) of row y, the same of row y+1 }, clamped */
-__global__ void k_expand_coeff8(const float *__restrict__ coeff, float4 *__restrict__ coeff8, int N0, int N1, size_t total) {
-    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
-        const int x = (int) (i % (size_t) N0), y = (int) ((i / (size_t) N0) % (size_t) N1);
-        const float *row = coeff + (i - x);
-        const float *rowUp = y + 1 < N1 ? row + N0 : row;
-        const int xm = max(x - 1, 0), x1 = min(x + 1, N0 - 1), x2 = min(x + 2, N0 - 1);
-        coeff8[2 * i] = make_float4(row[xm], row[x], row[x1], row[x2]);
-        coeff8[2 * i + 1] = make_float4(rowUp[xm], rowUp[x], rowUp[x1], rowUp[x2]);
-    }
-}
-
-/* fast mode: sample the spline (value + gradient) at every grid node */
 __global__ void k_build_packed(RifDev R, float4 *__restrict__ packed, size_t total) {
     const size_t n0 = R.N[0], n01 = (size_t) R.N[0] * R.N[1];
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -203,6 +190,47 @@ __global__ void k_grid_woodcock(GridDev D, float scale, size_t n, const float *_
 }
 
 /* ===================================================================== host side */
+namespace mer {
+struct CachedArray { int device; size_t W, H; cudaArray_t arr; };
+static std::mutex g_arrLock;
+static std::vector<CachedArray> g_arrCache;
+
+cudaError_t array_acquire(int device, size_t W, size_t H, cudaArray_t *out) {
+    {
+        std::lock_guard<std::mutex> hold(g_arrLock);
+        for (size_t i = 0; i < g_arrCache.size(); i++)
+            if (g_arrCache[i].device == device && g_arrCache[i].W == W && g_arrCache[i].H == H) {
+                *out = g_arrCache[i].arr;
+                g_arrCache.erase(g_arrCache.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float>();
+    cudaError_t e = cudaMallocArray(out, &fmt, W, H, cudaArrayTextureGather);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        array_cache_trim(device);
+        pool_trim(device);
+        e = cudaMallocArray(out, &fmt, W, H, cudaArrayTextureGather);
+    }
+    return e;
+}
+void array_release(int device, cudaArray_t arr, size_t W, size_t H) {
+    if (!arr) return;
+    std::lock_guard<std::mutex> hold(g_arrLock);
+    size_t mine = 0;
+    for (const CachedArray &c : g_arrCache) mine += c.device == device;
+    if (mine >= 2) { cudaFreeArray(arr); return; } /* keep at most two per device (a RIF and an SDF) */
+    g_arrCache.push_back({device, W, H, arr});
+}
+void array_cache_trim(int device) {
+    std::lock_guard<std::mutex> hold(g_arrLock);
+    for (size_t i = 0; i < g_arrCache.size();)
+        if (g_arrCache[i].device == device) { cudaFreeArray(g_arrCache[i].arr); g_arrCache.erase(g_arrCache.begin() + i); }
+        else i++;
+}
+} /* namespace mer */
+
 namespace {
 
 int validate_desc(const mer_volume_desc *d, int minRes) {
@@ -233,8 +261,66 @@ void fill_rif_dev(mer_rif *r) {
     D.hasXform = d.has_transform != 0;
     for (int i = 0; i < 12; i++) D.M[i] = D.hasXform ? d.world_to_volume[i] : ((i == 0 || i == 5 || i == 10) ? 1.f : 0.f);
     D.coeff = r->d_coeff;
-    D.coeff8 = r->d_coeff8;
     D.packed = r->d_packed;
+    D.tex = (unsigned long long) r->tex; /* tileShift / tileMask: rif_build_texture */
+}
+
+/* does tld4 return (w, z, x, y) = (i0,j0), (i1,j0), (i0,j1), (i1,j1) and land on the texels it is asked for? */
+__global__ void k_check_gather(RifDev R, int i, int j, int k, int *bad) {
+    const float ox = (float) ((k & R.tileMask) * R.N[0]), oy = (float) ((k >> R.tileShift) * R.N[1]);
+    const float4 g = tex2Dgather<float4>((cudaTextureObject_t) R.tex, ox + (float) (i + 1), oy + (float) (j + 1), 0);
+    const size_t o = ((size_t) k * R.N[1] + j) * (size_t) R.N[0] + i;
+    const float c00 = R.coeff[o], c10 = R.coeff[o + 1], c01 = R.coeff[o + R.N[0]], c11 = R.coeff[o + R.N[0] + 1];
+    *bad = !(g.w == c00 && g.z == c10 && g.x == c01 && g.y == c11);
+}
+
+/* texture storage of the coefficients: layer k of coeff -> tile (k & mask, k >> shift) of a 2-D CUDA array (block-linear;
+ * cudaArrayTextureGather).  The gather limit of sm_100 is 32768 x 32768 texels: 1024^3 fits exactly (32 x 32 tiles). */
+int rif_build_texture(mer_rif *r, cudaStream_t s) {
+    const mer_volume_desc &d = r->desc;
+    fill_rif_dev(r);
+    int maxW = 0, maxH = 0;
+    MER_CUDA(cudaDeviceGetAttribute(&maxW, cudaDevAttrMaxTexture2DGatherWidth, r->device));
+    MER_CUDA(cudaDeviceGetAttribute(&maxH, cudaDevAttrMaxTexture2DGatherHeight, r->device));
+    /* tiles per atlas row: a power of two (tile origin = shift and mask), as square as the limits allow */
+    int shift = 0;
+    while ((1 << (2 * shift)) < d.res[2]) shift++;
+    while (shift > 0 && (size_t) d.res[0] << shift > (size_t) maxW) shift--;
+    while ((size_t) d.res[1] * (size_t) ((d.res[2] + (1 << shift) - 1) >> shift) > (size_t) maxH && ((size_t) d.res[0] << (shift + 1)) <= (size_t) maxW) shift++;
+    const int TX = 1 << shift, TY = (d.res[2] + TX - 1) / TX;
+    const size_t W = (size_t) d.res[0] * TX, H = (size_t) d.res[1] * TY;
+    if (W > (size_t) maxW || H > (size_t) maxH)
+        return mer::fail(MER_ERR_UNSUPPORTED, "volume exceeds the texture atlas (gather textures are limited to 32768 x 32768 texels: res_x * T <= 32768 and "
+                                              "res_y * ceil(res_z / T) <= 32768 for a power of two T)");
+    r->dev.tileShift = shift;
+    r->dev.tileMask = TX - 1;
+    MER_CUDA(mer::array_acquire(r->device, W, H, &r->texArray));
+    r->texW = W; r->texH = H;
+    for (int k = 0; k < d.res[2]; k++)
+        MER_CUDA(cudaMemcpy2DToArrayAsync(r->texArray, (size_t) (k & (TX - 1)) * d.res[0] * sizeof(float), (size_t) (k >> shift) * d.res[1],
+                                          r->d_coeff + (size_t) k * d.res[0] * d.res[1], (size_t) d.res[0] * sizeof(float),
+                                          (size_t) d.res[0] * sizeof(float), (size_t) d.res[1], cudaMemcpyDeviceToDevice, s));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = r->texArray;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    MER_CUDA(cudaCreateTextureObject(&r->tex, &res, &td, nullptr));
+    r->dev.tex = (unsigned long long) r->tex;
+    int *bad = nullptr, hbad = 1;
+    MER_CUDA(cudaMalloc(&bad, sizeof(int)));
+    MER_LAUNCH(k_check_gather, 1, 1, 0, s, r->dev, d.res[0] / 2, d.res[1] / 3, d.res[2] - 2, bad);
+    cudaError_t e = cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(bad);
+    if (e != cudaSuccess) return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));
+    if (hbad) return mer::fail(MER_ERR_CUDA, "texture gather does not return the expected texels (component order / footprint)");
+    return MER_OK;
 }
 
 int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
@@ -246,19 +332,23 @@ int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N2, T), T, 0, s, data_dev, r->d_coeff, N0, N1, N2, (int) PASS_Y);
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N1 * N2, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_X);
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N1, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_Z);
-    MER_CUDA(mer::pool_malloc((void **) &r->d_coeff8, 2 * total * sizeof(float4)));
     const unsigned G = (unsigned) std::min<size_t>(mer_blocks(total, 256), 148u * 16u);
-    MER_LAUNCH(k_expand_coeff8, G, 256, 0, s, r->d_coeff, r->d_coeff8, N0, N1, total);
     fill_rif_dev(r);
+    {
+        int rc = rif_build_texture(r, s);
+        if (rc) return rc;
+    }
     if (r->mode == MER_RIF_TRILINEAR_PACKED) {
         MER_CUDA(mer::pool_malloc((void **) &r->d_packed, total * sizeof(float4)));
-        fill_rif_dev(r);
+        r->dev.packed = r->d_packed;
         MER_LAUNCH(k_build_packed, G, 256, 0, s, r->dev, r->d_packed, total);
         MER_CUDA(cudaStreamSynchronize(s));
-        /* the 8x-expanded cubic coefficients are only needed to build the packed grid */
-        mer::pool_free(r->d_coeff8);
-        r->d_coeff8 = nullptr;
-        fill_rif_dev(r);
+        /* the cubic atlas was only needed to sample the spline at the nodes */
+        cudaDestroyTextureObject(r->tex);
+        mer::array_release(r->device, r->texArray, r->texW, r->texH);
+        r->tex = 0;
+        r->texArray = nullptr;
+        r->dev.tex = 0;
     }
     MER_CUDA(cudaStreamSynchronize(s));
     return MER_OK;
@@ -429,9 +519,11 @@ int mer_rif_create_from_file(int device, const char *vol_path, const mer_volume_
 void mer_rif_destroy(mer_rif *r) {
     if (!r) return;
     mer::DeviceGuard guard(r->device);
+    mer::pool_quiesce();
     mer::pool_free(r->d_coeff);
-    mer::pool_free(r->d_coeff8);
     mer::pool_free(r->d_packed);
+    if (r->tex) cudaDestroyTextureObject(r->tex);
+    mer::array_release(r->device, r->texArray, r->texW, r->texH);
     delete r;
 }
 
@@ -599,6 +691,7 @@ int mer_grid_create_from_file(int device, const char *vol_path, const mer_volume
 void mer_grid_destroy(mer_grid *g) {
     if (!g) return;
     mer::DeviceGuard guard(g->device);
+    mer::pool_quiesce();
     mer::pool_free(g->d_data);
     delete g;
 }
