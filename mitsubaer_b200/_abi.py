@@ -157,7 +157,7 @@ def _load():
 class _Lib:
     """The shared library, loaded on first use.  `import mitsubaer_b200` touches it right away (so a missing or
     stale .so fails at import, loudly) unless MER_B200_DEFER_LOAD=1, which bench.py's CPU-reference arm sets so
-    that the process timing the oracle never maps the CUDA library (it only needs fields.py's generators)."""
+    that the process timing the CPU baseline never maps the CUDA library (it only needs fields.py's generators)."""
     _handle = None
 
     def __getattr__(self, name):
