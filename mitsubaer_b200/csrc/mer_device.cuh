@@ -270,10 +270,21 @@ template <int MODE> struct StencilCache;
 template <> struct StencilCache<MER_RIF_TRICUBIC> : StencilStore<16> {
     int i, j, k;
     __device__ __forceinline__ void invalidate() { bind(); i = j = k = -0x7fffffff; }
+    /* invalidate AND overwrite: tells the register allocator that the block is dead (used across a call) */
+    __device__ __forceinline__ void clear() {
+        i = j = k = -0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < 16; r++) set(r, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
 };
 template <> struct StencilCache<MER_RIF_TRILINEAR_PACKED> : StencilStore<8> {
     int i, j, k;
     __device__ __forceinline__ void invalidate() { bind(); i = j = k = -0x7fffffff; }
+    __device__ __forceinline__ void clear() {
+        i = j = k = -0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < 8; r++) set(r, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
 };
 
 /* unconditional (re)load of the block of cell (i0, j0, k0) */
@@ -478,6 +489,12 @@ template <int MODE, bool XFORM = true> __device__ __forceinline__ CellPos rif_ce
         c.k = clampi((int) floorf(c.z), 0, R.N[2] - 2);
     }
     return c;
+}
+
+/* can the hot loop fetch this cell's block with its branch-free loads?  Tricubic: every tap inside the grid (texture
+ * gathers); packed trilinear: always (rif_cell clamps the cell into the grid) */
+template <int MODE> __device__ __forceinline__ bool rif_cell_fast(const RifDev &R, const CellPos &c) {
+    return MODE == MER_RIF_TRICUBIC ? rif_cell_interior(R, c.i, c.j, c.k) : true;
 }
 
 template <int MODE> __device__ __forceinline__ bool stencil_has(const StencilCache<MODE> &S, const CellPos &c) {
@@ -697,7 +714,9 @@ static __device__ __noinline__ float3 hg_sample_dev(float g, float3 wi, float u1
         cosTheta = __fdiv_rn(__fsub_rn(__fadd_rn(1.0f, gg), __fmul_rn(sqrTerm, sqrTerm)), __fmul_rn(2.0f, g));
     }
     float sinTheta = __fsqrt_rn(fmaxf(0.0f, __fsub_rn(1.0f, __fmul_rn(cosTheta, cosTheta))));
-    float phi = (float) (2.0 * 3.14159265358979323846 * (double) u2);
+    /* `2*M_PI*sample.y` is a FLOAT product: constants.h:42-44,84-86 re-define M_PI as M_PI_FLT under -DSINGLE_PRECISION
+     * (pinned by src/phase/hg.cpp compiled verbatim, oracle/ref_phase.cpp) */
+    float phi = __fmul_rn(6.2831854820251464844f, u2);
     float sinPhi, cosPhi;
     sincosf(phi, &sinPhi, &cosPhi);
     float3 nrm = f3(-wi.x, -wi.y, -wi.z), s, t;

@@ -38,7 +38,7 @@ struct mer_grid {
 struct RenderScratch {
     std::mutex lock; /* mer_render* calls on one device are serialised */
     size_t poolBytes = 0;
-    void *pool[14] = {nullptr};
+    void *pool[16] = {nullptr};
     void *neeQ[3] = {nullptr, nullptr, nullptr}; /* direct-connection request queue */
     unsigned *neeCount = nullptr, *neePerm = nullptr, *neeHist = nullptr;
     unsigned char *neeKey = nullptr;

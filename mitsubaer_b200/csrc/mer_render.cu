@@ -60,27 +60,29 @@ enum PathKind : int {
 };
 
 enum {
-    FLAG_TB = 1, FLAG_MOVED = 2,
+    FLAG_TB = 1,
     FLAG_OUTWARD = 4, /* reached the surface from inside */
     FLAG_COVERED = 8, /* the quad's light along the current edge chain is estimated by a direct connection */
     FLAG_PARKED = 16, /* the request queue is full: wait for the next pass */
     FLAG_DRIFTED = 32, /* first kick + drift of the step `kind` are already applied (software-pipelined stepper) */
-    FLAG_DMOVED = 64   /* ... and that drift changed p */
+    FLAG_SLOW = 64     /* K_FULL whose 4x4x4 stencil touches the edge of the grid: stepped by the event code (clamped taps) */
 };
 
 enum { ST_SAMPLES = 0, ST_STEPS, ST_SCATTER, ST_NULL, ST_EXIT, ST_NONFINITE, ST_CONN, ST_CONNFAIL, ST_CONNSTEPS, ST_COUNT };
+#define ST_STEPS2 ST_STEPS /* the event code's steps go through the CTA's shared counter */
 
 #define MER_NEE_SALT 0x5851F42D4C957F2DULL /* direct connections draw from their own Philox key */
 
-/* persisted path state: 6 x 16 bytes per path, SoA by quad so loads/stores are LDG/STG.128 */
+/* the path pool: fixed slots, 128 bytes per path, structure of arrays of 16-byte quads (one LDG/STG.128 each) */
 struct PathPool {
-    float4 *q0; /* p.xyz, v.x */
-    float4 *q1; /* v.yz, thr.rg */
-    float4 *q2; /* thr.b, refStart, segDist, distSurf */
-    float4 *q3; /* rem, sd, (int) stepsLeft, (int) depth */
-    uint4 *q4;  /* kind | flags<<8, rng draw index, pixel, sample index */
-    float4 *q5; /* n(p), grad n(p): the field at p carried by the fused stepper */
-    float4 *q6; /* product of the surface BSDFs' relative indices (RR), optical path length, unused x2; hdielectric / transient only */
+    float4 *h0; /* HOT (step kernel): p.xyz, v.x */
+    float4 *h1; /* v.yz, n(p), grad n(p).x : the field at p carried by the fused stepper */
+    float4 *h2; /* grad n(p).yz, distSurf, optical path length */
+    uint2 *h3;  /* (int) stepsLeft, kind | flags << 8 */
+    float4 *c0; /* COLD (event kernel only): throughput rgb, refStart */
+    float4 *c1; /* segDist, sd, product of the surface BSDFs' relative indices (RR), rem */
+    float4 *c2; /* origin of the current edge xyz, (int) depth */
+    uint4 *c3;  /* rng draw index, pixel, sample index, unused */
 };
 
 struct RenderParams {
@@ -99,14 +101,15 @@ struct RenderParams {
     float minBound, binWidth;
     int modulation;                   /* continuous-wave ToF: contributions times correlationFunction(path length) */
     float lambda, phaseShift;         /* phaseShift = phase * lambda / (2 pi), pathlengthsampler.cpp:74 */
-    int stepsPerPass, maxWait;
+    int stepsPerPass;  /* steps of one visit of the step kernel to a path */
+    int refillGate;    /* lanes of a warp that must be idle before the warp pops new slots */
     float *film;
-    PathPool in, out;
-    unsigned nIn;
-    unsigned *nOut;
+    PathPool pool;
+    unsigned nSlots;
+    unsigned *stepHead; /* next slot of the round to hand out (reset per round) */
+    unsigned *live;     /* slots that are not dead after the event kernel (reset per round) */
     unsigned long long *sampleCounter;
     unsigned long long *stats;
-    const RenderParams *self; /* a copy of this struct in global memory, for the out-of-line event code */
     /* direct connections */
     int nee, neePrecision, neeMaxIterations, neeStraightFirst;
     float neeTol2, neeRRWeight;
@@ -128,6 +131,7 @@ struct RenderParams {
 
 struct Lane {
     float3 p, v;
+    float3 o; /* ray.o of the current path edge ("no forward progress" test, heterogeneousrefractive.cpp:517-520) */
     float n;
     float3 G;
     float thr[3];
@@ -310,7 +314,7 @@ __device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, co
 __device__ __forceinline__ void begin_trace(const RenderParams &P, Lane &L, float dist) {
     L.segDist = dist;
     L.distSurf = 0.0f;
-    L.flags &= ~(FLAG_TB | FLAG_MOVED);
+    L.flags &= ~(FLAG_TB | FLAG_DRIFTED | FLAG_SLOW);
     if (isfinite(dist)) {
         trace_split(dist, P.M.h, L.stepsLeft, L.rem);
         L.kind = L.stepsLeft > 0 ? K_FULL : K_REM;
@@ -320,6 +324,30 @@ __device__ __forceinline__ void begin_trace(const RenderParams &P, Lane &L, floa
         L.rem = 0.0f;
         L.kind = K_FULL;
     }
+}
+
+/* K_FULL +h, K_REM +rem, K_BACKF -h, K_BACKR -rem, K_ENTRY 0: selects, no branches (bit 0 = remainder, bit 1 = backwards) */
+__device__ __forceinline__ float step_length(int kind, float h, float rem) {
+    const float mag = (kind & 1) ? rem : h;
+    const float sgn = (kind & 2) ? -mag : mag;
+    return kind == K_ENTRY ? 0.0f : sgn;
+}
+
+/* first half of er_step (:655-657): kick, drift with n at the OLD point, optical length.  Rounded operation by operation
+ * like the reference's float build (see er_step_fused). */
+template <bool EXTRAS, typename T>
+__device__ __forceinline__ void lane_drift(T &L, float hc) {
+    const float hs = __fmul_rn(0.5f, hc);
+    L.v = f3(__fadd_rn(L.v.x, __fmul_rn(hs, L.G.x)), __fadd_rn(L.v.y, __fmul_rn(hs, L.G.y)), __fadd_rn(L.v.z, __fmul_rn(hs, L.G.z)));
+    const float recip = __frcp_rn(L.n);
+    L.p = f3(__fadd_rn(L.p.x, __fmul_rn(__fmul_rn(hc, L.v.x), recip)), __fadd_rn(L.p.y, __fmul_rn(__fmul_rn(hc, L.v.y), recip)),
+             __fadd_rn(L.p.z, __fmul_rn(__fmul_rn(hc, L.v.z), recip)));
+    if (EXTRAS) L.opl = __fadd_rn(L.opl, __fmul_rn(hc, L.n));
+    L.flags |= FLAG_DRIFTED;
+}
+template <typename T> __device__ __forceinline__ void lane_kick(T &L, float hc) { /* second half of er_step (:659-660) */
+    const float hs = __fmul_rn(0.5f, hc);
+    L.v = f3(__fadd_rn(L.v.x, __fmul_rn(hs, L.G.x)), __fadd_rn(L.v.y, __fmul_rn(hs, L.G.y)), __fadd_rn(L.v.z, __fmul_rn(hs, L.G.z)));
 }
 
 /* exponential free-flight pdfs + transmittance at geometric length d (:533-562) */
@@ -370,13 +398,48 @@ __device__ __forceinline__ void scatter_and_roulette(const RenderParams &P, Lane
 
 /* Everything that is not a leapfrog step.  Runs until the lane is steppable again or dead.
  * DIELECTRIC selects the container surface: false = index-matched null surface, true = hdielectric. */
-template <bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE>
+template <int MODE, bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE, bool XFORM>
 __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, unsigned *st) {
     const MediumDev &M = P.M;
     const float zero[3] = {0.f, 0.f, 0.f};
     L.rng.cachedBlock = 0xffffffffu; /* the cached Philox block lives only inside one event phase (registers) */
-    while (L.kind >= E_BEGIN && L.kind != K_DEAD && !(L.flags & FLAG_PARKED)) {
-        if (L.kind == E_NEW) {
+    while ((L.kind != K_FULL || (L.flags & FLAG_SLOW)) && L.kind != K_DEAD && !(L.flags & FLAG_PARKED)) {
+        if (L.kind <= K_ENTRY) {
+            /* ---- one er_step outside the hot loop (:653-661 inside trace() :674-686 / traceTillBoundary() :748-762):
+             * the remainder step, the step back after leaving the shape, the zero-length step that fetches the field
+             * where a ray enters the container, and full steps whose stencil touches the edge of the grid.  A direct
+             * 64-tap lookup (no cached block), same arithmetic as the hot loop's step. */
+            const int kind = L.kind;
+            const float hc = step_length(kind, M.h, L.rem);
+            if (!(L.flags & FLAG_DRIFTED)) lane_drift<EXTRAS>(L, hc);
+            L.flags &= ~(FLAG_DRIFTED | FLAG_SLOW);
+            rif_lookup<MODE>(M.rif, L.p, L.n, L.G);
+            lane_kick(L, hc);
+            const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
+            if (kind != K_ENTRY) ST_INC(st, ST_STEPS2);
+            if (kind == K_FULL) {
+                if (inside) {
+                    L.distSurf += M.h;
+                    L.stepsLeft--;
+                    L.kind = L.stepsLeft > 0 ? K_FULL : ((L.flags & FLAG_TB) ? E_EXIT : K_REM);
+                    if (L.kind == K_FULL) { /* hand it back drifted if the next stencil is interior again */
+                        lane_drift<EXTRAS>(L, M.h);
+                        const CellPos cn = rif_cell<MODE, XFORM>(M.rif, L.p);
+                        if (!rif_cell_fast<MODE>(M.rif, cn)) L.flags |= FLAG_SLOW;
+                    }
+                } else {
+                    L.kind = K_BACKF;
+                }
+            } else if (kind == K_REM) {
+                if (inside) L.distSurf += L.rem;
+                L.kind = inside ? E_REACHED : K_BACKR;
+            } else if (kind == K_ENTRY) {
+                L.kind = DIELECTRIC ? E_SURFACE : E_BEGIN;
+            } else {
+                if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= M.h; /* :761 */
+                L.kind = E_EXIT;
+            }
+        } else if (L.kind == E_NEW) {
             /* ---- SamplingIntegrator::renderBlock: next (pixel, sample) */
             unsigned long long g = atomicAdd(P.sampleCounter, 1ULL);
             if (g >= P.totalSamples) { L.kind = K_DEAD; break; }
@@ -465,6 +528,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
             /* ---- Medium::sampleDistance prologue, heterogeneousrefractive.cpp:402-475; L.v = unit direction */
             if (!rif_inside_limits(M.rif, L.p)) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
             L.refStart = L.n;
+            L.o = L.p;
             L.v = f3(L.v.x * L.n, L.v.y * L.n, L.v.z * L.n);
             float dist;
             if (M.hasGrid) {
@@ -542,13 +606,11 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                     } else {
                         ST_INC(st, ST_NULL);
                         float dist = __fmul_rn(-fastlog_dev(1.0f - L.rng.next()), M.invMaxDensity);
-                        int moved = L.flags & FLAG_MOVED;
                         begin_trace(P, L, dist);
-                        L.flags |= moved;
                         continue;
                     }
                 } else {
-                    if (!(L.flags & FLAG_MOVED)) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; } /* :517-520 */
+                    if (L.p.x == L.o.x && L.p.y == L.o.y && L.p.z == L.o.z) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; } /* :517-520 */
                     scatter = true;
                     edge_weight(M, L.sd, L.segDist, true, edge);
                 }
@@ -594,289 +656,205 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
     }
 }
 
-/* ------------------------------------------------------------------ two paths per lane
- * A lane owns TWO paths: the active one (hot state in registers) and an alternate one parked in shared memory.  When the
- * active path reaches an event (end of a free flight every 30-120 steps: scatter, null collision, exit, new sample) the
- * lane swaps to its alternate path and keeps stepping; the event is handled later, when enough of the warp's 64 paths
- * are waiting, by a lane-dense event phase.  (Round 1 had one path per lane: a lane that reached an event idled until 12
- * lanes were waiting — 16-19 % of the step slots — and the event code then ran for 12 of 32 lanes: ncu r01, 20.5 of 32.)
- * The state is split in two: HOT (what a step reads and writes, 15 words) moves between registers and shared memory on a
- * swap; COLD (throughput, sample id, RNG position, ... 11 words) stays in shared memory for both paths and is loaded only
- * for the event code, so it costs no registers in the step loop.  Layout [word][thread]: conflict-free, 18.5 KB per CTA. */
-enum { HOT_WORDS = 14, COLD_WORDS = 11, LANE_SMEM_WORDS = HOT_WORDS + 2 * COLD_WORDS };
+/* ------------------------------------------------------------------ the two kernels of a round
+ * The path pool is a set of FIXED slots in global memory (128 bytes per path, structure of arrays of 16-byte quads);
+ * a slot renders one camera sample after the other until the frame runs out of samples.  A round is
+ *
+ *   k_event   one thread per slot whose path is at an EVENT: the remainder step and the step back of trace() (:674-686),
+ *             the zero-length entry step, steps whose stencil touches the edge of the grid, free-flight sampling, Woodcock
+ *             test, scattering, exits, film splat, next camera sample.  Runs until the path can take plain full steps.
+ *   k_step    plain full steps only (kind K_FULL: +h, inside the container, interior stencil).  A persistent kernel:
+ *             a lane POPS the next steppable slot from a global counter (one atomic per warp and refill), keeps the
+ *             hot state (14 words) and the 4x4x4 coefficient block (64 words) in registers, steps until the path
+ *             reaches an event or the visit's step budget, writes the hot state back and pops the next slot.
+ *
+ * Why two kernels (ncu r02s/r02u/r02v, profiles/README.md): with the event code inside the step kernel — inlined, or out
+ * of line and lane-dense — its 54 KB of instructions were cycled through the 32 KB instruction cache between every few
+ * turns of a 10 KB step loop (`no_instructions` the top stall reason, 34 %), it ran at 8 of 32 lanes because the kinds of
+ * event diverge, and the step loop had to keep two paths per lane in shared memory to stay busy.  Here the step kernel's
+ * whole code is the loop, lanes are refilled from the pool (no second path, no shared memory), and the event kernel
+ * costs what it costs once per ~60 steps.
+ *
+ * A turn of the step loop: first kick + drift of step k (er_step :655-657) -> the cell of the drifted point is the EXACT
+ * cell of the lookup: if it differs from the cached block the new block is requested (the one fetch site; the lane does
+ * not sit the turn out, the SM's other warps cover the latency) -> contraction -> second kick -> containment test. */
+__device__ __forceinline__ bool is_waiting(unsigned kf) {
+    const int kind = (int) (kf & 0xffu), flags = (int) (kf >> 8);
+    return (kind != K_FULL || (flags & FLAG_SLOW)) && kind != K_DEAD && !(flags & FLAG_PARKED);
+}
+__device__ __forceinline__ bool is_steppable(unsigned kf) { return (kf & 0xffu) == K_FULL && !((kf >> 8) & (FLAG_SLOW | FLAG_PARKED)); }
 
-__device__ __forceinline__ bool is_waiting(int kind, int flags) { return kind >= E_BEGIN && kind != K_DEAD && !(flags & FLAG_PARKED); }
+struct Hot { /* what a full step reads and writes */
+    float3 p, v;
+    float n;
+    float3 G;
+    float distSurf, opl, safe;
+    int stepsLeft, flags;
+};
 
-/* hot state of the active path <-> alternate slot; the alternate path's kind/flags live in the register altKF */
-/* altKF = kind | flags << 8 of the alternate path, bit 31 = cold slot of the ACTIVE path (one register for both) */
-#define ALT_CUR 0x80000000u
-__device__ __forceinline__ void hot_swap(Lane &L, unsigned &altKF, uint32_t *sm) {
-#define MER_XF(w, f) { const float t_ = __uint_as_float(sm[(w) * MER_STENCIL_BLOCK]); sm[(w) * MER_STENCIL_BLOCK] = __float_as_uint(f); f = t_; }
-    MER_XF(0, L.p.x) MER_XF(1, L.p.y) MER_XF(2, L.p.z)
-    MER_XF(3, L.v.x) MER_XF(4, L.v.y) MER_XF(5, L.v.z)
-    MER_XF(6, L.n) MER_XF(7, L.G.x) MER_XF(8, L.G.y) MER_XF(9, L.G.z)
-    MER_XF(10, L.rem) MER_XF(11, L.distSurf) MER_XF(12, L.opl)
-#undef MER_XF
-    { const int t_ = (int) sm[13 * MER_STENCIL_BLOCK]; sm[13 * MER_STENCIL_BLOCK] = (unsigned) L.stepsLeft; L.stepsLeft = t_; }
-    const unsigned t = altKF;
-    altKF = ((unsigned) L.kind | ((unsigned) L.flags << 8)) | ((t & ALT_CUR) ^ ALT_CUR); /* the other cold slot is the active one now */
-    L.kind = (int) (t & 0xffu);
-    L.flags = (int) ((t >> 8) & 0xffu);
+__device__ __forceinline__ void hot_load(const PathPool &Q, unsigned slot, unsigned kf, int stepsLeft, Hot &H) {
+    const float4 a = Q.h0[slot], b = Q.h1[slot], c = Q.h2[slot];
+    H.p = f3(a.x, a.y, a.z);
+    H.v = f3(a.w, b.x, b.y);
+    H.n = b.z;
+    H.G = f3(b.w, c.x, c.y);
+    H.distSurf = c.z;
+    H.opl = c.w;
+    H.stepsLeft = stepsLeft;
+    H.flags = (int) (kf >> 8);
+    H.safe = 0.0f;
+}
+__device__ __forceinline__ void hot_store(const PathPool &Q, unsigned slot, const Hot &H, int kind) {
+    Q.h0[slot] = make_float4(H.p.x, H.p.y, H.p.z, H.v.x);
+    Q.h1[slot] = make_float4(H.v.y, H.v.z, H.n, H.G.x);
+    Q.h2[slot] = make_float4(H.G.y, H.G.z, H.distSurf, H.opl);
+    Q.h3[slot] = make_uint2((unsigned) H.stepsLeft, (unsigned) kind | ((unsigned) H.flags << 8));
+}
+
+/* the complete path <-> pool (event kernel) */
+__device__ __forceinline__ void full_load(const RenderParams &P, unsigned slot, unsigned kf, int stepsLeft, Lane &L) {
+    const PathPool &Q = P.pool;
+    const float4 a = Q.h0[slot], b = Q.h1[slot], c = Q.h2[slot], d = Q.c0[slot], e = Q.c1[slot], f = Q.c2[slot];
+    const uint4 g = Q.c3[slot];
+    L.p = f3(a.x, a.y, a.z);
+    L.v = f3(a.w, b.x, b.y);
+    L.n = b.z;
+    L.G = f3(b.w, c.x, c.y);
+    L.distSurf = c.z;
+    L.opl = c.w;
+    L.stepsLeft = stepsLeft;
+    L.kind = (int) (kf & 0xffu);
+    L.flags = (int) (kf >> 8) & ~FLAG_PARKED;
+    L.thr[0] = d.x; L.thr[1] = d.y; L.thr[2] = d.z; L.refStart = d.w;
+    L.segDist = e.x; L.sd = e.y; L.etaPath = e.z; L.rem = e.w;
+    L.o = f3(f.x, f.y, f.z);
+    L.depth = __float_as_int(f.w);
+    L.pixel = g.y; L.sample = g.z;
+    L.rng.init(P.seed, (unsigned long long) g.y * (unsigned long long) P.sppTotal + g.z, g.x);
     L.safe = 0.0f;
 }
-__device__ __forceinline__ void hot_store(const Lane &L, uint32_t *sm) {
-    sm[0 * MER_STENCIL_BLOCK] = __float_as_uint(L.p.x); sm[1 * MER_STENCIL_BLOCK] = __float_as_uint(L.p.y); sm[2 * MER_STENCIL_BLOCK] = __float_as_uint(L.p.z);
-    sm[3 * MER_STENCIL_BLOCK] = __float_as_uint(L.v.x); sm[4 * MER_STENCIL_BLOCK] = __float_as_uint(L.v.y); sm[5 * MER_STENCIL_BLOCK] = __float_as_uint(L.v.z);
-    sm[6 * MER_STENCIL_BLOCK] = __float_as_uint(L.n);
-    sm[7 * MER_STENCIL_BLOCK] = __float_as_uint(L.G.x); sm[8 * MER_STENCIL_BLOCK] = __float_as_uint(L.G.y); sm[9 * MER_STENCIL_BLOCK] = __float_as_uint(L.G.z);
-    sm[10 * MER_STENCIL_BLOCK] = __float_as_uint(L.rem); sm[11 * MER_STENCIL_BLOCK] = __float_as_uint(L.distSurf); sm[12 * MER_STENCIL_BLOCK] = __float_as_uint(L.opl);
-    sm[13 * MER_STENCIL_BLOCK] = (unsigned) L.stepsLeft;
-}
-__device__ __forceinline__ void cold_store(const Lane &L, uint32_t *sm, int slot) {
-    uint32_t *c = sm + (HOT_WORDS + slot * COLD_WORDS) * MER_STENCIL_BLOCK;
-    c[0 * MER_STENCIL_BLOCK] = __float_as_uint(L.thr[0]); c[1 * MER_STENCIL_BLOCK] = __float_as_uint(L.thr[1]); c[2 * MER_STENCIL_BLOCK] = __float_as_uint(L.thr[2]);
-    c[3 * MER_STENCIL_BLOCK] = __float_as_uint(L.refStart); c[4 * MER_STENCIL_BLOCK] = __float_as_uint(L.segDist); c[5 * MER_STENCIL_BLOCK] = __float_as_uint(L.sd);
-    c[6 * MER_STENCIL_BLOCK] = __float_as_uint(L.etaPath);
-    c[7 * MER_STENCIL_BLOCK] = (unsigned) L.depth; c[8 * MER_STENCIL_BLOCK] = L.rng.k; c[9 * MER_STENCIL_BLOCK] = L.pixel; c[10 * MER_STENCIL_BLOCK] = L.sample;
-}
-__device__ __forceinline__ void cold_load(const RenderParams &P, Lane &L, const uint32_t *sm, int slot) {
-    const uint32_t *c = sm + (HOT_WORDS + slot * COLD_WORDS) * MER_STENCIL_BLOCK;
-    L.thr[0] = __uint_as_float(c[0 * MER_STENCIL_BLOCK]); L.thr[1] = __uint_as_float(c[1 * MER_STENCIL_BLOCK]); L.thr[2] = __uint_as_float(c[2 * MER_STENCIL_BLOCK]);
-    L.refStart = __uint_as_float(c[3 * MER_STENCIL_BLOCK]); L.segDist = __uint_as_float(c[4 * MER_STENCIL_BLOCK]); L.sd = __uint_as_float(c[5 * MER_STENCIL_BLOCK]);
-    L.etaPath = __uint_as_float(c[6 * MER_STENCIL_BLOCK]);
-    L.depth = (int) c[7 * MER_STENCIL_BLOCK];
-    L.pixel = c[9 * MER_STENCIL_BLOCK]; L.sample = c[10 * MER_STENCIL_BLOCK];
-    L.rng.init(P.seed, (unsigned long long) L.pixel * (unsigned long long) P.sppTotal + L.sample, c[8 * MER_STENCIL_BLOCK]);
+__device__ __forceinline__ void full_store(const RenderParams &P, unsigned slot, const Lane &L) {
+    const PathPool &Q = P.pool;
+    Q.h0[slot] = make_float4(L.p.x, L.p.y, L.p.z, L.v.x);
+    Q.h1[slot] = make_float4(L.v.y, L.v.z, L.n, L.G.x);
+    Q.h2[slot] = make_float4(L.G.y, L.G.z, L.distSurf, L.opl);
+    Q.h3[slot] = make_uint2((unsigned) L.stepsLeft, (unsigned) L.kind | ((unsigned) L.flags << 8));
+    Q.c0[slot] = make_float4(L.thr[0], L.thr[1], L.thr[2], L.refStart);
+    Q.c1[slot] = make_float4(L.segDist, L.sd, L.etaPath, L.rem);
+    Q.c2[slot] = make_float4(L.o.x, L.o.y, L.o.z, __int_as_float(L.depth));
+    Q.c3[slot] = make_uint4(L.rng.k, L.pixel, L.sample, 0u);
 }
 
-/* persisted path -> Lane (pool index idx), or a lane that asks for a fresh camera sample */
-template <bool DIELECTRIC, bool EXTRAS>
-__device__ __forceinline__ void path_load(const RenderParams &P, unsigned idx, Lane &L) {
-    if (idx < P.nIn) {
-        float4 a = P.in.q0[idx], b = P.in.q1[idx], c = P.in.q2[idx], d = P.in.q3[idx];
-        uint4 e = P.in.q4[idx];
-        L.p = f3(a.x, a.y, a.z);
-        L.v = f3(a.w, b.x, b.y);
-        L.thr[0] = b.z; L.thr[1] = b.w; L.thr[2] = c.x;
-        L.refStart = c.y; L.segDist = c.z; L.distSurf = c.w;
-        L.rem = d.x; L.sd = d.y; L.stepsLeft = __float_as_int(d.z); L.depth = __float_as_int(d.w);
-        L.kind = (int) (e.x & 0xffu); L.flags = (int) (e.x >> 8) & ~FLAG_PARKED;
-        L.pixel = e.z; L.sample = e.w;
-        L.rng.init(P.seed, (unsigned long long) e.z * (unsigned long long) P.sppTotal + e.w, e.y);
-        float4 fg = P.in.q5[idx];
-        L.n = fg.x; L.G = f3(fg.y, fg.z, fg.w);
-        L.etaPath = 1.0f;
-        L.opl = 0.0f;
-        if (DIELECTRIC || EXTRAS) { const float4 ex = P.in.q6[idx]; L.etaPath = ex.x; L.opl = ex.y; }
-    } else {
-        L.p = L.v = L.G = f3(0.f, 0.f, 0.f);
-        L.n = 1.0f;
-        L.thr[0] = L.thr[1] = L.thr[2] = 0.0f;
-        L.refStart = L.segDist = L.distSurf = L.rem = L.sd = 0.0f;
-        L.etaPath = 1.0f;
-        L.opl = 0.0f;
-        L.stepsLeft = L.depth = L.flags = 0;
-        L.pixel = L.sample = 0;
-        L.rng.init(P.seed, 0ULL, 0u);
-        L.kind = E_NEW;
-    }
-    L.safe = 0.0f;
-}
-
-/* survivors go to the output queue compacted: warp ballot, popc prefix, one atomic per warp */
-template <bool DIELECTRIC, bool EXTRAS>
-__device__ __forceinline__ void path_store(const RenderParams &P, const Lane &L, unsigned lane) {
-    const bool live = L.kind != K_DEAD;
-    const unsigned m = __ballot_sync(0xffffffffu, live);
-    unsigned base = 0;
-    if (lane == 0 && m) base = atomicAdd(P.nOut, (unsigned) __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (live) {
-        const unsigned o = base + __popc(m & ((1u << lane) - 1u));
-        P.out.q0[o] = make_float4(L.p.x, L.p.y, L.p.z, L.v.x);
-        P.out.q1[o] = make_float4(L.v.y, L.v.z, L.thr[0], L.thr[1]);
-        P.out.q2[o] = make_float4(L.thr[2], L.refStart, L.segDist, L.distSurf);
-        P.out.q3[o] = make_float4(L.rem, L.sd, __int_as_float(L.stepsLeft), __int_as_float(L.depth));
-        P.out.q4[o] = make_uint4((unsigned) L.kind | ((unsigned) L.flags << 8), L.rng.k, L.pixel, L.sample);
-        P.out.q5[o] = make_float4(L.n, L.G.x, L.G.y, L.G.z);
-        if (DIELECTRIC || EXTRAS) P.out.q6[o] = make_float4(L.etaPath, L.opl, 0.f, 0.f);
-    }
-}
-
-/* K_FULL +h, K_REM +rem, K_BACKF -h, K_BACKR -rem, K_ENTRY 0: selects, no branches (bit 0 = remainder, bit 1 = backwards) */
-__device__ __forceinline__ float step_length(int kind, float h, float rem) {
-    const float mag = (kind & 1) ? rem : h;
-    const float sgn = (kind & 2) ? -mag : mag;
-    return kind == K_ENTRY ? 0.0f : sgn;
-}
-
-/* first half of er_step (:655-657): kick, drift with n at the OLD point, optical length.  Rounded operation by operation
- * like the reference's float build (see er_step_fused). */
-template <bool EXTRAS>
-__device__ __forceinline__ void lane_drift(Lane &L, float hc) {
-    const float hs = __fmul_rn(0.5f, hc);
-    L.v = f3(__fadd_rn(L.v.x, __fmul_rn(hs, L.G.x)), __fadd_rn(L.v.y, __fmul_rn(hs, L.G.y)), __fadd_rn(L.v.z, __fmul_rn(hs, L.G.z)));
-    const float recip = __frcp_rn(L.n);
-    const float3 pOld = L.p;
-    L.p = f3(__fadd_rn(L.p.x, __fmul_rn(__fmul_rn(hc, L.v.x), recip)), __fadd_rn(L.p.y, __fmul_rn(__fmul_rn(hc, L.v.y), recip)),
-             __fadd_rn(L.p.z, __fmul_rn(__fmul_rn(hc, L.v.z), recip)));
-    if (EXTRAS) L.opl = __fadd_rn(L.opl, __fmul_rn(hc, L.n));
-    const bool moved = L.p.x != pOld.x || L.p.y != pOld.y || L.p.z != pOld.z;
-    L.flags |= FLAG_DRIFTED | (moved ? FLAG_DMOVED : 0);
-}
-
-/* The event code as a real call: out of line it neither shares the step loop's registers nor drags its ~60 kernel
- * parameters into the loop (inlined, ptxas hoisted their loads to the loop head: 30 LDCU per turn, ncu r02a/b), and the
- * hot loop shrinks to what the instruction cache holds.  The hot state crosses the call through the stack (cold path). */
-template <bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE>
-__device__ __noinline__ void handle_events_call(const RenderParams *Pg, Lane *Lp, uint32_t *sm, int cur, unsigned *st) {
-    const RenderParams &P = *Pg;
-    Lane L = *Lp;
-    cold_load(P, L, sm, cur);
-    handle_events<DIELECTRIC, EXTRAS, SDFSHAPE>(P, L, st);
-    cold_store(L, sm, cur);
-    *Lp = L;
+/* every slot starts by asking for a camera sample */
+__global__ void k_pool_init(PathPool Q, unsigned nSlots) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nSlots; i += gridDim.x * blockDim.x)
+        Q.h3[i] = make_uint2(0u, (unsigned) E_NEW);
 }
 
 template <int MODE, bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE, bool XFORM>
-__global__ void __launch_bounds__(MER_STENCIL_BLOCK, MER_RENDER_MIN_BLOCKS)
-k_render_pass(const __grid_constant__ RenderParams P) {
-    __shared__ uint32_t laneSmem[LANE_SMEM_WORDS * MER_STENCIL_BLOCK];
-    __shared__ unsigned st[ST_COUNT];
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nThreads = gridDim.x * blockDim.x;
-    const unsigned lane = threadIdx.x & 31u;
-    const MediumDev &M = P.M;
-    uint32_t *sm = laneSmem + threadIdx.x;
-    if (threadIdx.x < ST_COUNT) st[threadIdx.x] = 0u;
+__global__ void __launch_bounds__(128)
+k_event(const __grid_constant__ RenderParams P) {
+    __shared__ unsigned st[ST_COUNT + 1]; /* + live slots */
+    if (threadIdx.x <= ST_COUNT) st[threadIdx.x] = 0u;
     __syncthreads();
-
-    /* path tid is the active one, path tid + nThreads the alternate */
-    Lane L;
-    unsigned altKF;
-    path_load<DIELECTRIC, EXTRAS>(P, tid + nThreads, L);
-    hot_store(L, sm);
-    cold_store(L, sm, 1);
-    altKF = (unsigned) L.kind | ((unsigned) L.flags << 8);
-    path_load<DIELECTRIC, EXTRAS>(P, tid, L);
-    cold_store(L, sm, 0);
-
-    StencilCache<MODE> S; /* registers only: refilled by the first step of the pass */
-    S.invalidate();
-    const float h = M.h;
-    int budget = P.stepsPerPass;
-    unsigned nSteps = 0;
-    /* An outer loop of event phases around an inner loop of convergent steps; both are left by warp-uniform votes
-     * only.  (The inner loop holds no calls and a fixed set of kernel parameters, which lets ptxas keep them in uniform
-     * registers across its turns; in one flat loop it reloaded ~50 of them every turn, 13 % of the issued
-     * instructions: ncu r02a.) */
-    while (true) {
-        int nw;
-        bool lw, aw;
-        while (true) {
-            /* Explicit reconvergence.  The event phase leaves the warp split into groups (its BSYNC is a plain one
-             * with YIELDs), and from then on every group would run the step body on its own, meeting the others
-             * only inside the collective votes (ncu r01c: 16 of 32 lanes active).  NVVM folds __syncwarp() into the
-             * following vote, so the barrier is spelled in PTX. */
-            asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
-            /* a lane whose active path cannot step takes its alternate path if that one can */
-            if (L.kind > K_ENTRY && (int) (altKF & 0xffu) <= K_ENTRY) {
-                hot_swap(L, altKF, sm);
-                S.i = -0x7fffffff;
-            }
-            const bool stepping = L.kind <= K_ENTRY;
-            lw = is_waiting(L.kind, L.flags);
-            aw = is_waiting((int) (altKF & 0xffu), (int) ((altKF >> 8) & 0xffu));
-            const unsigned ms = __ballot_sync(0xffffffffu, stepping);
-            nw = __popc(__ballot_sync(0xffffffffu, lw)) + __popc(__ballot_sync(0xffffffffu, aw));
-            if (!(ms != 0u && budget > 0 && nw < P.maxWait)) break;
-            /* ---------------- convergent step, software-pipelined: a step is
-             *   [kick1 + drift]  ->  lookup at the new point  ->  [kick2, containment test, bookkeeping]
-             * and the first bracket of step k+1 runs right behind the second of step k, so the exact next cell is known
-             * at the end of a turn.  Its block is normally in flight by then: between the x stage of the contraction (the
-             * last reader of the cached coefficients) and the y/z stages the block of the PREDICTED next cell (one more
-             * drift with the old field) is requested into the same registers, a whole turn before it is needed.  A lane
-             * that finds its block missing at the top (misprediction, first step after an event or of a pass) has
-             * requested it at the end of the previous turn or does so now, and sits the turn out.
-             * K_ENTRY is a zero-length step: both brackets are exact no-ops and only the lookup remains. */
-            budget--;
-            bool counted = false; /* this turn completed an er_step (the count is kept per warp, in a uniform register) */
-            if (stepping) {
-                const int kind = L.kind;
-                const float hc = step_length(kind, h, L.rem);
-                if (!(L.flags & FLAG_DRIFTED)) lane_drift<EXTRAS>(L, hc);
-                CellPos c = rif_cell<MODE, XFORM>(M.rif, L.p);
-                bool want = true;
-                if (stencil_has(S, c)) {
-                    float rn; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(L.n)); /* prediction only */
-                    const CellPos cp = rif_cell<MODE, XFORM>(M.rif, f3(fmaf(h * L.v.x, rn, L.p.x), fmaf(h * L.v.y, rn, L.p.y), fmaf(h * L.v.z, rn, L.p.z)));
-                    rif_contract<XFORM>(M.rif, S, c, L.n, L.G, [&](StencilCache<MODE> &Sx) {
-                        if (MER_SPECULATE && kind == K_FULL && !stencil_has(Sx, cp)) rif_fetch_interior(M.rif, Sx, cp.i, cp.j, cp.k);
-                    });
-                    const float hs = __fmul_rn(0.5f, hc);
-                    L.v = f3(__fadd_rn(L.v.x, __fmul_rn(hs, L.G.x)), __fadd_rn(L.v.y, __fmul_rn(hs, L.G.y)), __fadd_rn(L.v.z, __fmul_rn(hs, L.G.z)));
-                    const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
-                    const bool moved = (L.flags & FLAG_DMOVED) != 0;
-                    int next;
-                    if (kind == K_FULL) {
-                        next = inside ? ((L.stepsLeft == 1) ? ((L.flags & FLAG_TB) ? E_EXIT : K_REM) : K_FULL) : K_BACKF;
-                        if (inside) { L.distSurf += h; L.stepsLeft--; }
-                    } else if (kind == K_REM) {
-                        next = inside ? E_REACHED : K_BACKR;
-                        if (inside) L.distSurf += L.rem;
-                    } else if (kind == K_ENTRY) {
-                        next = DIELECTRIC ? E_SURFACE : E_BEGIN;
-                    } else {
-                        if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= h; /* :761 */
-                        next = E_EXIT;
-                    }
-                    L.flags &= ~(FLAG_DRIFTED | FLAG_DMOVED);
-                    if (kind <= K_REM && inside && moved) L.flags |= FLAG_MOVED;
-                    counted = kind != K_ENTRY;
-                    L.kind = next;
-                    want = false;
-                    if (next <= K_BACKR) {
-                        lane_drift<EXTRAS>(L, step_length(next, h, L.rem));
-                        c = rif_cell<MODE, XFORM>(M.rif, L.p);
-                        want = !stencil_has(S, c);
-                    }
-                }
-                if (want) rif_fetch(M.rif, S, c.i, c.j, c.k);
-            }
-            nSteps += (unsigned) __popc(__ballot_sync(0xffffffffu, counted));
+    for (unsigned slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.nSlots; slot += gridDim.x * blockDim.x) {
+        const uint2 hk = P.pool.h3[slot];
+        unsigned kf = hk.y & ~((unsigned) FLAG_PARKED << 8); /* a parked vertex tries the request queue again */
+        if (is_waiting(kf)) {
+            Lane L;
+            full_load(P, slot, kf, (int) hk.x, L);
+            handle_events<MODE, DIELECTRIC, EXTRAS, SDFSHAPE, XFORM>(P, L, st);
+            full_store(P, slot, L);
+            kf = (unsigned) L.kind;
         }
-        if (nw == 0) break; /* budget exhausted (or nobody alive) and nothing waiting */
-        /* ---------------- event phase: scatter / exit / regenerate for every waiting path the lane can bring into
-         * registers (an alternate path that waits while the active one does too is handled in the next turn) */
-        if (aw && !lw) {
-            hot_swap(L, altKF, sm);
-            S.i = -0x7fffffff;
-        }
-        if (is_waiting(L.kind, L.flags)) {
-            Lane T = L;
-            const int cur = (int) (altKF >> 31);
-            if (SDFSHAPE || EXTRAS) { /* inlined in these variants */
-                cold_load(P, T, sm, cur);
-                handle_events<DIELECTRIC, EXTRAS, SDFSHAPE>(P, T, st);
-                cold_store(T, sm, cur);
-            } else {
-                handle_events_call<DIELECTRIC, false, false>(P.self, &T, sm, cur, st);
-            }
-            L.p = T.p; L.v = T.v; L.n = T.n; L.G = T.G; L.rem = T.rem; L.distSurf = T.distSurf; L.opl = T.opl; L.safe = T.safe;
-            L.stepsLeft = T.stepsLeft; L.kind = T.kind; L.flags = T.flags;
-        }
+        if ((kf & 0xffu) != K_DEAD) atomicAdd(&st[ST_COUNT], 1u);
     }
-
-    /* ---------------- compaction: both paths of the lane */
-    cold_load(P, L, sm, (int) (altKF >> 31));
-    path_store<DIELECTRIC, EXTRAS>(P, L, lane);
-    hot_swap(L, altKF, sm);
-    cold_load(P, L, sm, (int) (altKF >> 31));
-    path_store<DIELECTRIC, EXTRAS>(P, L, lane);
-
-    /* ---------------- statistics: one atomic per warp (steps) / CTA (events) and counter */
-    if (lane == 0 && nSteps) atomicAdd(P.stats + ST_STEPS, (unsigned long long) nSteps); /* a per-warp count */
     __syncthreads();
     if (threadIdx.x < ST_COUNT && st[threadIdx.x]) atomicAdd(P.stats + threadIdx.x, (unsigned long long) st[threadIdx.x]);
+    if (threadIdx.x == ST_COUNT && st[ST_COUNT]) atomicAdd(P.live, st[ST_COUNT]);
+}
+
+template <int MODE, bool EXTRAS, bool SDFSHAPE, bool XFORM>
+__global__ void __launch_bounds__(MER_STENCIL_BLOCK, MER_RENDER_MIN_BLOCKS)
+k_step(const __grid_constant__ RenderParams P) {
+    const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
+    const MediumDev &M = P.M;
+    const PathPool &Q = P.pool;
+    const unsigned NONE = 0xffffffffu;
+    Hot L;
+    L.p = L.v = L.G = f3(0.f, 0.f, 0.f);
+    L.n = 1.0f; L.distSurf = L.opl = L.safe = 0.0f; L.stepsLeft = L.flags = 0;
+    unsigned cur = NONE; /* the slot whose hot state is in registers */
+    int visit = 0;       /* steps left in this visit */
+    StencilCache<MODE> S; /* registers only */
+    S.invalidate();
+    const float h = M.h;
+    bool exhausted = false; /* warp-uniform: the round's slots are all handed out */
+    unsigned nSteps = 0;
+    while (true) {
+        /* Explicit reconvergence (NVVM folds __syncwarp() into the following vote, so the barrier is spelled in PTX; and
+         * no other warp barrier may appear in this kernel, or ptxas drops the converged-warp assumption and every vote
+         * becomes BRA.DIV + WARPSYNC.COLLECTIVE, which synchronises without merging the groups: ncu r02u, 17 of 32 lanes) */
+        asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+        unsigned need = __ballot_sync(0xffffffffu, cur == NONE);
+        if (need == 0xffffffffu && exhausted) break;
+        /* ---- refill: lanes without a path pop the next slots of the round, one atomic per warp and attempt */
+        if (!exhausted && (__popc(need) >= P.refillGate || need == 0xffffffffu)) {
+            while (need != 0u && !exhausted) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(P.stepHead, (unsigned) __popc(need));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned idx = base + (unsigned) __popc(need & ltMask);
+                bool got = false;
+                if (((need >> lane) & 1u) && idx < P.nSlots) {
+                    const uint2 hk = Q.h3[idx];
+                    if (is_steppable(hk.y)) {
+                        hot_load(Q, idx, hk.y, (int) hk.x, L);
+                        cur = idx;
+                        visit = P.stepsPerPass;
+                        got = true;
+                    }
+                }
+                exhausted = base + (unsigned) __popc(need) >= P.nSlots;
+                need &= ~__ballot_sync(0xffffffffu, got);
+            }
+        }
+        /* ---- first half of the step, then the one place where blocks are requested */
+        CellPos c;
+        bool step = false;
+        if (cur != NONE) {
+            if (!(L.flags & FLAG_DRIFTED)) lane_drift<EXTRAS>(L, h);
+            c = rif_cell<MODE, XFORM>(M.rif, L.p);
+            if (rif_cell_fast<MODE>(M.rif, c)) {
+                if (!stencil_has(S, c)) rif_fetch_interior(M.rif, S, c.i, c.j, c.k);
+                step = true;
+            } else { /* the stencil touches the edge of the grid: a step for the event kernel */
+                L.flags |= FLAG_SLOW;
+                hot_store(Q, cur, L, K_FULL);
+                cur = NONE;
+            }
+        }
+        if (step) {
+            /* ---------------- lookup and second half of er_step */
+            rif_contract<XFORM>(M.rif, S, c, L.n, L.G, [](StencilCache<MODE> &) {});
+            lane_kick(L, h);
+            const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, h, L.safe) : inside_shape(M, L.p);
+            nSteps++;
+            L.flags &= ~FLAG_DRIFTED;
+            int next = K_BACKF;
+            if (inside) {
+                L.distSurf += h;
+                L.stepsLeft--;
+                next = L.stepsLeft > 0 ? K_FULL : ((L.flags & FLAG_TB) ? E_EXIT : K_REM);
+            }
+            if (next != K_FULL || --visit <= 0) { /* an event, or the end of the visit: back to the pool */
+                hot_store(Q, cur, L, next);
+                cur = NONE;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) nSteps += __shfl_down_sync(0xffffffffu, nSteps, o);
+    if (lane == 0 && nSteps) atomicAdd(P.stats + ST_STEPS, (unsigned long long) nSteps);
 }
 
 /* A warp of k_nee costs what its longest connection costs, and the cost is roughly the number of steps from the vertex to
@@ -1164,10 +1142,11 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         P.quadO[i] = r->quad_origin[i]; P.quadU[i] = r->quad_u[i]; P.quadV[i] = r->quad_v[i]; P.quadLe[i] = r->quad_radiance[i];
     }
     P.hasQuad = r->has_quad;
-    P.stepsPerPass = r->steps_per_pass > 0 ? r->steps_per_pass : 2048;
-    P.maxWait = 16; /* of the warp's 64 paths */
-    if (const char *e = getenv("MER_MAX_WAIT")) P.maxWait = atoi(e); /* tuning knob */
-    P.maxWait = std::min(std::max(P.maxWait, 1), 64);
+    P.stepsPerPass = r->steps_per_pass > 0 ? r->steps_per_pass : 128;
+    if (const char *e = getenv("MER_VISIT")) P.stepsPerPass = std::max(atoi(e), 1); /* tuning knobs */
+    P.refillGate = 2;
+    if (const char *e = getenv("MER_GATE")) P.refillGate = atoi(e);
+    P.refillGate = std::min(std::max(P.refillGate, 1), 32);
     P.film = film_dev;
     MER_REQUIRE(r->modulation >= MER_MODULATION_NONE && r->modulation <= MER_MODULATION_HAMILTONIAN, "unknown modulation");
     P.modulation = r->modulation;
@@ -1207,26 +1186,28 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.neeStraightFirst = r->connection.start_mode != MER_START_RANDOM;
 
     const unsigned TPB = 128;
-    /* `pool` counts path slots; a thread owns two of them (k_render_pass) */
-    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 2u * 148u * 4096u;
-    pool = ((pool + 2 * TPB - 1) / (2 * TPB)) * (2 * TPB);
-    if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) (((P.totalSamples + 2 * TPB - 1) / (2 * TPB)) * (2 * TPB));
-    if (pool == 0) pool = 2 * TPB;
+    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 8192u;
+    if (const char *e = getenv("MER_POOL")) pool = (unsigned) atol(e); /* tuning knob */
+    if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) P.totalSamples;
+    pool = std::max(((pool + TPB - 1) / TPB) * TPB, TPB);
 
     RenderScratch &S = mer::device_scratch(m->device);
     std::lock_guard<std::mutex> hold(S.lock);
     const size_t qBytes = (size_t) pool * 16;
     if (S.poolBytes < qBytes) {
         S.release();
-        for (int i = 0; i < 14; i++) MER_CUDA(cudaMalloc(&S.pool[i], qBytes));
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaMalloc(&S.pool[i], qBytes);
+        if (e == cudaSuccess) e = cudaMalloc(&S.nOut, 4 * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMalloc(&S.counters, (1 + ST_COUNT) * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaEventCreate(&S.ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&S.ev1);
+        if (e != cudaSuccess) { /* all or nothing: a later call must not find half of the scratch */
+            S.release();
+            return mer::fail(e == cudaErrorMemoryAllocation ? MER_ERR_OOM : MER_ERR_CUDA, cudaGetErrorString(e));
+        }
         S.poolBytes = qBytes;
-        MER_CUDA(cudaMalloc(&S.nOut, sizeof(unsigned)));
-        MER_CUDA(cudaMalloc(&S.counters, (1 + ST_COUNT) * sizeof(unsigned long long)));
-        MER_CUDA(cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long)));
-        MER_CUDA(cudaMalloc(&S.paramsDev, sizeof(RenderParams)));
-        MER_CUDA(cudaMallocHost(&S.paramsHost, sizeof(RenderParams)));
-        MER_CUDA(cudaEventCreate(&S.ev0));
-        MER_CUDA(cudaEventCreate(&S.ev1));
     }
     if (P.nee) {
         const unsigned cap = std::min(pool * 2u, 1u << 21);
@@ -1255,57 +1236,54 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         if (const char *e = getenv("MER_NEE_SORT")) if (atoi(e) == 0) P.neePerm = nullptr; /* tuning knob */
         MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
     }
-    PathPool A = {(float4 *) S.pool[0], (float4 *) S.pool[1], (float4 *) S.pool[2], (float4 *) S.pool[3], (uint4 *) S.pool[4], (float4 *) S.pool[5], (float4 *) S.pool[12]};
-    PathPool B = {(float4 *) S.pool[6], (float4 *) S.pool[7], (float4 *) S.pool[8], (float4 *) S.pool[9], (uint4 *) S.pool[10], (float4 *) S.pool[11], (float4 *) S.pool[13]};
+    P.pool = PathPool{(float4 *) S.pool[0], (float4 *) S.pool[1], (float4 *) S.pool[2], (uint2 *) S.pool[3],
+                      (float4 *) S.pool[4], (float4 *) S.pool[5], (float4 *) S.pool[6], (uint4 *) S.pool[7]};
+    P.nSlots = pool;
+    P.stepHead = S.nOut;
+    P.live = S.nOut + 1;
     MER_CUDA(cudaMemsetAsync(S.counters, 0, (1 + ST_COUNT) * sizeof(unsigned long long), stream));
-    P.nOut = S.nOut;
     P.sampleCounter = S.counters;
     P.stats = S.counters + 1;
 
-    unsigned nLive = 0;
-    unsigned long long started = 0, passes = 0, launches = 0;
+    /* the step kernel is persistent: as many CTAs as fit the GPU at once (fewer for a small pool) */
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    const unsigned eventBlocks = pool / TPB;
+    const unsigned stepBlocks = std::min((unsigned) sms * MER_RENDER_MIN_BLOCKS, eventBlocks);
+    int syncEvery = 8; /* rounds between two looks at the live-slot counter (a host synchronisation) */
+    if (const char *e = getenv("MER_SYNC_EVERY")) syncEvery = std::max(atoi(e), 1);
+
+    unsigned long long rounds = 0, launches = 0;
     MER_CUDA(cudaEventRecord(S.ev0, stream));
+    MER_LAUNCH(k_pool_init, std::min(eventBlocks, 148u * 8u), 256, 0, stream, P.pool, pool);
+    launches++;
+    const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, extras = P.frames > 1 || P.modulation || P.nee || P.lightMode;
+    const bool sdfShape = m->dev.shapeType == MER_SHAPE_SDF, xform = m->dev.rif.hasXform != 0, packed = m->rif->mode != MER_RIF_TRICUBIC;
     while (true) {
-        const bool fresh = started < P.totalSamples;
-        const unsigned paths = fresh ? pool : nLive;
-        if (paths == 0) break;
-        const unsigned threads = (paths + 1) / 2;
-        P.in = (passes & 1) ? B : A;
-        P.out = (passes & 1) ? A : B;
-        P.nIn = nLive;
-        MER_CUDA(cudaMemsetAsync(S.nOut, 0, sizeof(unsigned), stream));
-        const unsigned blocks = (threads + TPB - 1) / TPB;
-        P.self = (const RenderParams *) S.paramsDev; /* the out-of-line event code reads its parameters from global memory */
-        memcpy(S.paramsHost, &P, sizeof(P));
-        MER_CUDA(cudaMemcpyAsync(S.paramsDev, S.paramsHost, sizeof(P), cudaMemcpyHostToDevice, stream));
-        /* `transient` selects the kernels compiled with the extras: transient film, direct connections, light tracing */
-        const bool dielectric = m->desc.boundary == MER_BOUNDARY_HDIELECTRIC, transient = P.frames > 1 || P.modulation || P.nee || P.lightMode;
-#define MER_PASS(MODE_, D_, T_, S_)                                                                                      \
+        MER_CUDA(cudaMemsetAsync(S.nOut, 0, 2 * sizeof(unsigned), stream)); /* stepHead, live */
+        /* ---- events: every slot whose path cannot take a plain full step */
+#define MER_EVENT(MODE_, D_, T_, S_)                                                                                     \
     do {                                                                                                                 \
-        if (m->dev.rif.hasXform) MER_LAUNCH((k_render_pass<MODE_, D_, T_, S_, true>), blocks, TPB, 0, stream, P);        \
-        else MER_LAUNCH((k_render_pass<MODE_, D_, T_, S_, false>), blocks, TPB, 0, stream, P);                           \
+        if (xform) MER_LAUNCH((k_event<MODE_, D_, T_, S_, true>), eventBlocks, TPB, 0, stream, P);                       \
+        else MER_LAUNCH((k_event<MODE_, D_, T_, S_, false>), eventBlocks, TPB, 0, stream, P);                            \
     } while (0)
-        if (m->dev.shapeType == MER_SHAPE_SDF) { /* tricubic only (checked above) */
-            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true, true); else MER_PASS(MER_RIF_TRICUBIC, true, false, true); }
-            else { if (transient) MER_PASS(MER_RIF_TRICUBIC, false, true, true); else MER_PASS(MER_RIF_TRICUBIC, false, false, true); }
-        } else if (m->rif->mode == MER_RIF_TRICUBIC) {
-            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRICUBIC, true, true, false); else MER_PASS(MER_RIF_TRICUBIC, true, false, false); }
-            else { if (transient) MER_PASS(MER_RIF_TRICUBIC, false, true, false); else MER_PASS(MER_RIF_TRICUBIC, false, false, false); }
-        } else {
-            if (dielectric) { if (transient) MER_PASS(MER_RIF_TRILINEAR_PACKED, true, true, false); else MER_PASS(MER_RIF_TRILINEAR_PACKED, true, false, false); }
-            else { if (transient) MER_PASS(MER_RIF_TRILINEAR_PACKED, false, true, false); else MER_PASS(MER_RIF_TRILINEAR_PACKED, false, false, false); }
-        }
-#undef MER_PASS
+#define MER_EVENT2(MODE_, S_)                                                                                            \
+    do {                                                                                                                 \
+        if (dielectric) { if (extras) MER_EVENT(MODE_, true, true, S_); else MER_EVENT(MODE_, true, false, S_); }        \
+        else { if (extras) MER_EVENT(MODE_, false, true, S_); else MER_EVENT(MODE_, false, false, S_); }                 \
+    } while (0)
+        if (sdfShape) MER_EVENT2(MER_RIF_TRICUBIC, true); /* tricubic only (checked above) */
+        else if (!packed) MER_EVENT2(MER_RIF_TRICUBIC, false);
+        else MER_EVENT2(MER_RIF_TRILINEAR_PACKED, false);
+#undef MER_EVENT2
+#undef MER_EVENT
         launches++;
-        passes++;
-        /* the only host<->device traffic of a pass: 12 bytes telling the host how to size the next one */
-        MER_CUDA(cudaMemcpyAsync(S.hostPinned, S.nOut, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-        MER_CUDA(cudaMemcpyAsync(S.hostPinned + 1, S.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-        if (P.nee) MER_CUDA(cudaMemcpyAsync(S.hostPinned + 2, S.neeCount, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
-        MER_CUDA(cudaStreamSynchronize(stream));
-        nLive = *(unsigned *) S.hostPinned;
-        started = S.hostPinned[1];
+        rounds++;
+        const bool look = P.nee || rounds % (unsigned long long) syncEvery == 0 || rounds <= 2;
+        if (look) MER_CUDA(cudaMemcpyAsync(S.hostPinned, P.live, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
         if (P.nee) {
+            MER_CUDA(cudaMemcpyAsync(S.hostPinned + 2, S.neeCount, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+            MER_CUDA(cudaStreamSynchronize(stream));
             const unsigned nReq = std::min(*(unsigned *) (S.hostPinned + 2), P.neeCap);
             if (nReq) {
                 RenderParams Pn = P; /* this launch's view: sorted only when the sort ran */
@@ -1318,14 +1296,31 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
                     launches += 3;
                 }
                 const unsigned nb = (nReq + TPB - 1) / TPB;
-                const bool sdfShape = m->dev.shapeType == MER_SHAPE_SDF, wantOpl = P.frames > 1 || P.modulation; /* optical length: transient / modulated film only */
+                const bool wantOpl = P.frames > 1 || P.modulation; /* optical length: transient / modulated film only */
                 if (sdfShape) { if (wantOpl) MER_LAUNCH((k_nee<true, true>), nb, TPB, 0, stream, Pn, nReq); else MER_LAUNCH((k_nee<false, true>), nb, TPB, 0, stream, Pn, nReq); }
                 else { if (wantOpl) MER_LAUNCH((k_nee<true, false>), nb, TPB, 0, stream, Pn, nReq); else MER_LAUNCH((k_nee<false, false>), nb, TPB, 0, stream, Pn, nReq); }
+                launches++;
                 MER_CUDA(cudaMemsetAsync(S.neeCount, 0, sizeof(unsigned), stream));
             }
+            if (*(unsigned *) S.hostPinned == 0u) break;
         }
-        if (nLive == 0 && started >= P.totalSamples) break;
+        /* ---- steps: every slot whose path can */
+#define MER_STEP(MODE_, T_, S_)                                                                                          \
+    do {                                                                                                                 \
+        if (xform) MER_LAUNCH((k_step<MODE_, T_, S_, true>), stepBlocks, TPB, 0, stream, P);                             \
+        else MER_LAUNCH((k_step<MODE_, T_, S_, false>), stepBlocks, TPB, 0, stream, P);                                  \
+    } while (0)
+        if (sdfShape) { if (extras) MER_STEP(MER_RIF_TRICUBIC, true, true); else MER_STEP(MER_RIF_TRICUBIC, false, true); }
+        else if (!packed) { if (extras) MER_STEP(MER_RIF_TRICUBIC, true, false); else MER_STEP(MER_RIF_TRICUBIC, false, false); }
+        else { if (extras) MER_STEP(MER_RIF_TRILINEAR_PACKED, true, false); else MER_STEP(MER_RIF_TRILINEAR_PACKED, false, false); }
+#undef MER_STEP
+        launches++;
+        if (look && !P.nee) {
+            MER_CUDA(cudaStreamSynchronize(stream));
+            if (*(unsigned *) S.hostPinned == 0u) break;
+        }
     }
+    const unsigned long long passes = rounds;
     if (P.lightMode) {
         const size_t npx = (size_t) r->width * r->height;
         MER_LAUNCH(k_film_unit_weight, (unsigned) std::min<size_t>(mer_blocks(npx, 256), 148u * 8u), 256, 0, stream, npx, P.channels,

@@ -358,9 +358,12 @@ inline void hg_sample(float g, const float wi[3], float u1, float u2, float wo[3
         cosTheta = (1 + g * g - sqrTerm * sqrTerm) / (2 * g);
     }
     float sinTheta = std::sqrt(std::max(0.0f, 1.0f - cosTheta * cosTheta));
-    /* `2*M_PI*sample.y` is a double product (M_PI is a double literal) passed to sincosf */
-    float phi = (float) (2 * M_PI * u2);
-    float sinPhi = sinf(phi), cosPhi = cosf(phi);
+    /* `2*M_PI*sample.y`: constants.h:42-44,84-86 re-define M_PI as the float literal M_PI_FLT under -DSINGLE_PRECISION, so
+     * this is a float product, (2 * M_PI_FLT) * y; math::sincos(float) is ::sincosf (math.h:218-237).  Pinned bit for bit
+     * against src/phase/hg.cpp compiled verbatim (oracle/ref_phase.cpp). */
+    float phi = (2 * 3.14159265358979323846f) * u2;
+    float sinPhi, cosPhi;
+    ::sincosf(phi, &sinPhi, &cosPhi);
     float n[3] = {-wi[0], -wi[1], -wi[2]}, s[3], t[3];
     coordinateSystem(n, s, t);
     float lx = sinTheta * cosPhi, ly = sinTheta * sinPhi, lz = cosTheta;
@@ -2034,6 +2037,12 @@ extern "C" void orc_hg_eval(float g, size_t n, const float *wi, const float *wo,
     for (size_t i = 0; i < n; i++) out[i] = hg_eval(g, wi + 3 * i, wo + 3 * i);
 }
 /* Medium::evalTransmittance, heterogeneousrefractive.cpp:393-400 */
+extern "C" void orc_coordinate_system(size_t n, const float *a, float *b, float *c) {
+    for (size_t i = 0; i < n; i++) coordinateSystem(a + 3 * i, b + 3 * i, c + 3 * i);
+}
+extern "C" void orc_fresnel_dielectric_ext(size_t n, const float *cosThetaI, const float *eta, float *F, float *cosThetaT) {
+    for (size_t i = 0; i < n; i++) F[i] = fresnelDielectricExt(cosThetaI[i], cosThetaT[i], eta[i]);
+}
 extern "C" void orc_eval_transmittance(const float sigmaT[3], size_t n, const float *mint, const float *maxt,
                                        float *out) {
     for (size_t i = 0; i < n; i++) {

@@ -149,6 +149,51 @@ class RefSpline:
             self.h = None
 
 
+class RefPhase:
+    """The reference's HGPhaseFunction (src/phase/hg.cpp), Frame, coordinateSystem and fresnelDielectricExt
+    (src/libcore/util.cpp), compiled verbatim (oracle/ref_phase.cpp -> oracle/_ref/libmer_refphase.so)."""
+
+    def __init__(self):
+        path = os.path.join(REF_DIR, "libmer_refphase.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(REF_DIR, "libmer_refphase.so"))
+
+    def hg_sample(self, g, wi, xi):
+        wi = np.ascontiguousarray(wi, dtype=np.float32).reshape(-1, 3)
+        xi = np.ascontiguousarray(xi, dtype=np.float32).reshape(-1, 2)
+        wo = np.zeros_like(wi)
+        pdf = np.zeros(wi.shape[0], dtype=np.float32)
+        self.lib.ref_hg_sample(C.c_float(g), C.c_size_t(wi.shape[0]), _ptr(wi, C.c_float), _ptr(xi, C.c_float),
+                               _ptr(wo, C.c_float), _ptr(pdf, C.c_float))
+        return wo, pdf
+
+    def hg_eval(self, g, wi, wo):
+        wi = np.ascontiguousarray(wi, dtype=np.float32).reshape(-1, 3)
+        wo = np.ascontiguousarray(wo, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(wi.shape[0], dtype=np.float32)
+        self.lib.ref_hg_eval(C.c_float(g), C.c_size_t(wi.shape[0]), _ptr(wi, C.c_float), _ptr(wo, C.c_float), _ptr(out, C.c_float))
+        return out
+
+    def coordinate_system(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3)
+        b, c = np.zeros_like(a), np.zeros_like(a)
+        self.lib.ref_coordinate_system(C.c_size_t(a.shape[0]), _ptr(a, C.c_float), _ptr(b, C.c_float), _ptr(c, C.c_float))
+        return b, c
+
+    def fresnel_dielectric_ext(self, cos_i, eta):
+        cos_i = np.ascontiguousarray(cos_i, dtype=np.float32).reshape(-1)
+        eta = np.ascontiguousarray(eta, dtype=np.float32).reshape(-1)
+        F, ct = np.zeros_like(cos_i), np.zeros_like(cos_i)
+        self.lib.ref_fresnel_dielectric_ext(C.c_size_t(cos_i.size), _ptr(cos_i, C.c_float), _ptr(eta, C.c_float), _ptr(F, C.c_float),
+                                            _ptr(ct, C.c_float))
+        return F, ct
+
+
 class Oracle:
     """The restated path (oracle/mer_oracle.cpp) in float (`Float`) or double (-DFLOATDEBUG)."""
 
@@ -240,6 +285,20 @@ class Oracle:
         self.lib.orc_hg_eval(C.c_float(g), C.c_size_t(wi.shape[0]), _ptr(wi, C.c_float), _ptr(wo, C.c_float),
                              _ptr(out, C.c_float))
         return out
+
+    def coordinate_system(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3)
+        b, c = np.zeros_like(a), np.zeros_like(a)
+        self.lib.orc_coordinate_system(C.c_size_t(a.shape[0]), _ptr(a, C.c_float), _ptr(b, C.c_float), _ptr(c, C.c_float))
+        return b, c
+
+    def fresnel_dielectric_ext(self, cos_i, eta):
+        cos_i = np.ascontiguousarray(cos_i, dtype=np.float32).reshape(-1)
+        eta = np.ascontiguousarray(eta, dtype=np.float32).reshape(-1)
+        F, ct = np.zeros_like(cos_i), np.zeros_like(cos_i)
+        self.lib.orc_fresnel_dielectric_ext(C.c_size_t(cos_i.size), _ptr(cos_i, C.c_float), _ptr(eta, C.c_float), _ptr(F, C.c_float),
+                                            _ptr(ct, C.c_float))
+        return F, ct
 
     # ---- medium
     def medium_create(self, desc, rif, density=None):

@@ -1,0 +1,83 @@
+/*
+ * oracle/ref_phase.cpp — TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Compiles, VERBATIM and from where they lie under /root/reference (nothing is copied into this repo):
+ *     src/phase/hg.cpp                              HGPhaseFunction::sample / eval            
+ *     include/mitsuba/core/frame.h                  Frame(n), Frame::toWorld                  (a17)
+ *     include/mitsuba/core/{vector,point,normal,math,constants}.h    dot / cross / safe_sqrt / sincos / Epsilon ...
+ *     src/libcore/util.cpp  coordinateSystem()      (a17)   } the two function bodies are cut out of util.cpp by
+ *     src/libcore/util.cpp  fresnelDielectricExt()  (f-3)   } oracle/Makefile into oracle/_ref/util_extract.inc
+ * behind a C ABI, with the reference's release flags (-DSINGLE_PRECISION -DSPECTRUM_SAMPLES=3).  Built into
+ * oracle/_ref/libmer_refphase.so; tests/test_oracle_cpu.py checks the restated HG / coordinateSystem / Fresnel of
+ * oracle/mer_oracle.cpp against it bit for bit, and tests/golden/phase_ref.npz holds vectors generated from it.
+ */
+#include <mitsuba/mitsuba.h>
+#include <mitsuba/core/frame.h>
+#include <mitsuba/render/phase.h>
+#include <mitsuba/render/sampler.h>
+
+namespace mitsuba {
+#include "util_extract.inc" /* generated: coordinateSystem, fresnelDielectricExt from src/libcore/util.cpp */
+}
+
+#include <phase/hg.cpp> /* -I/root/reference/src */
+
+namespace {
+struct FixedSampler : public mitsuba::Sampler {
+    mitsuba::Float u1, u2;
+    mitsuba::Float next1D() { return u1; }
+    mitsuba::Point2 next2D() { return mitsuba::Point2(u1, u2); }
+};
+}
+
+extern "C" {
+
+/* HGPhaseFunction::sample for n (wi, xi) pairs; pdf = eval of the sampled direction (hg.cpp:100-105) */
+void ref_hg_sample(float g, size_t n, const float *wi, const float *xi, float *wo, float *pdf) {
+    mitsuba::Properties props;
+    props.floats["g"] = g;
+    mitsuba::HGPhaseFunction hg(props);
+    hg.configure();
+    FixedSampler s;
+    for (size_t i = 0; i < n; i++) {
+        mitsuba::PhaseFunctionSamplingRecord rec;
+        rec.wi = mitsuba::Vector(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        s.u1 = xi[2 * i];
+        s.u2 = xi[2 * i + 1];
+        mitsuba::Float p;
+        hg.sample(rec, p, &s);
+        wo[3 * i] = rec.wo.x; wo[3 * i + 1] = rec.wo.y; wo[3 * i + 2] = rec.wo.z;
+        pdf[i] = p;
+    }
+}
+
+void ref_hg_eval(float g, size_t n, const float *wi, const float *wo, float *out) {
+    mitsuba::Properties props;
+    props.floats["g"] = g;
+    mitsuba::HGPhaseFunction hg(props);
+    for (size_t i = 0; i < n; i++) {
+        mitsuba::PhaseFunctionSamplingRecord rec;
+        rec.wi = mitsuba::Vector(wi[3 * i], wi[3 * i + 1], wi[3 * i + 2]);
+        rec.wo = mitsuba::Vector(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]);
+        out[i] = hg.eval(rec);
+    }
+}
+
+void ref_coordinate_system(size_t n, const float *a, float *b, float *c) {
+    for (size_t i = 0; i < n; i++) {
+        mitsuba::Vector bb, cc;
+        mitsuba::coordinateSystem(mitsuba::Vector(a[3 * i], a[3 * i + 1], a[3 * i + 2]), bb, cc);
+        b[3 * i] = bb.x; b[3 * i + 1] = bb.y; b[3 * i + 2] = bb.z;
+        c[3 * i] = cc.x; c[3 * i + 1] = cc.y; c[3 * i + 2] = cc.z;
+    }
+}
+
+void ref_fresnel_dielectric_ext(size_t n, const float *cosThetaI, const float *eta, float *F, float *cosThetaT) {
+    for (size_t i = 0; i < n; i++) {
+        mitsuba::Float ct;
+        F[i] = mitsuba::fresnelDielectricExt(cosThetaI[i], ct, eta[i]);
+        cosThetaT[i] = ct;
+    }
+}
+
+} /* extern "C" */

@@ -6,6 +6,12 @@ where /root/reference exists):
       oracle/_ref/libmer_refspline_{f,d}.so): prefiltered coefficients of a seeded random
       20x30x23 grid (the shape of mfiles/Test.m) and value / gradient / Hessian at seeded points.
 
+  phase_ref.npz
+      src/phase/hg.cpp (HGPhaseFunction::sample / eval), include/mitsuba/core/frame.h and, from src/libcore/util.cpp,
+      coordinateSystem() and fresnelDielectricExt(), compiled verbatim (oracle/ref_phase.cpp ->
+      oracle/_ref/libmer_refphase.so): sampled directions, pdfs, frames and Fresnel terms at seeded inputs,
+      g in {0.9, -0.3} (data/tests/test_phase.xml:12-21), 0.5, 0 and 1e-5 (the isotropic branch).
+
 Usage:  make -C oracle ref && python tests/golden/make_golden.py
 """
 import os
@@ -15,7 +21,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle.oracle import RefSpline  # noqa: E402
+from oracle.oracle import RefPhase, RefSpline  # noqa: E402
 
 
 def main():
@@ -40,5 +46,32 @@ def main():
         print("wrote spline_ref_%s.npz" % tag)
 
 
+def phase():
+    rng = np.random.default_rng(20201202)
+    n = 4096
+    wi = rng.normal(size=(n, 3))
+    wi = (wi / np.linalg.norm(wi, axis=1, keepdims=True)).astype(np.float32)
+    wi[:3] = np.eye(3, dtype=np.float32)  # axis-aligned frames (the |a.x| > |a.y| branch point)
+    wo_in = rng.normal(size=(n, 3))
+    wo_in = (wo_in / np.linalg.norm(wo_in, axis=1, keepdims=True)).astype(np.float32)
+    xi = rng.random((n, 2)).astype(np.float32)
+    xi[:4] = [[0, 0], [0.99999994, 0.99999994], [0.5, 0], [0, 0.5]]
+    ref = RefPhase()
+    out = dict(wi=wi, xi=xi, wo_in=wo_in, g=np.array([0.9, -0.3, 0.5, 0.0, 1e-5], np.float32))
+    for k, g in enumerate(out["g"]):
+        wo, pdf = ref.hg_sample(float(g), wi, xi)
+        out["wo_%d" % k], out["pdf_%d" % k] = wo, pdf
+        out["eval_%d" % k] = ref.hg_eval(float(g), wi, wo_in)
+    out["frame_s"], out["frame_t"] = ref.coordinate_system(wi)
+    cos_i = (rng.random(n) * 2 - 1).astype(np.float32)
+    eta = (1 + rng.random(n)).astype(np.float32)
+    cos_i[:4], eta[:4] = [1.0, -1.0, 0.0, 0.3], [1.5, 1.5, 1.5, 1.0]
+    out["cos_i"], out["eta"] = cos_i, eta
+    out["fresnel"], out["cos_t"] = ref.fresnel_dielectric_ext(cos_i, eta)
+    np.savez_compressed(os.path.join(HERE, "phase_ref.npz"), **out)
+    print("wrote phase_ref.npz")
+
+
 if __name__ == "__main__":
     main()
+    phase()

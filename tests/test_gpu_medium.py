@@ -263,6 +263,20 @@ def test_hg_exact_formula(oracle32, g):
     assert np.max(np.abs(np.linalg.norm(wo, axis=1) - 1)) < 1e-5
 
 
+def test_hg_matches_reference_golden():
+    """the CUDA sampler against vectors from the reference's own src/phase/hg.cpp + frame.h + util.cpp compiled verbatim
+    (tests/golden/phase_ref.npz, made by tests/golden/make_golden.py): parity gate (iii) without the oracle in between"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "phase_ref.npz"))
+    for k, gg in enumerate(g["g"]):
+        phase = mer.HGPhaseFunction(g=float(gg))
+        wo, pdf = phase.sample(g["wi"], g["xi"])
+        assert np.max(np.abs(wo - g["wo_%d" % k])) <= 2e-6
+        ev = phase.eval(g["wi"], g["wo_in"])
+        assert np.max(np.abs(ev - g["eval_%d" % k]) / g["eval_%d" % k]) <= 1e-6
+        assert np.mean(np.all(wo == g["wo_%d" % k], axis=1)) > 0.5  # mostly bit-identical; the rest is sincosf's last ulp
+
+
 @pytest.mark.parametrize("g", [0.9, -0.3])
 def test_hg_chi_square(g):
     """the reference's own test for this row: src/tests/test_chisquare.cpp:508-572 with

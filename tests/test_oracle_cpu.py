@@ -7,7 +7,7 @@ import pytest
 
 from common import (BOX_MAX, BOX_MIN, make_field, medium_props, oracle_medium_desc, oracle_render_desc,
                     random_directions, random_points_in_box, scene_dict)
-from oracle.oracle import Oracle, RefSpline, volume_desc
+from oracle.oracle import Oracle, RefPhase, RefSpline, volume_desc
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -46,6 +46,42 @@ def test_oracle_spline_bit_exact_vs_verbatim_reference(dtype):
     fo, go, Ho = orc.rif_eval_hessian(h, p)
     assert np.array_equal(fr, fo) and np.array_equal(gr, go) and np.array_equal(Hr, Ho)
     orc.rif_destroy(h)
+
+
+def test_oracle_phase_bit_exact_vs_reference_golden():
+    """a15-a17 + fresnelDielectricExt: the restatement against vectors generated from src/phase/hg.cpp, frame.h and
+    util.cpp compiled verbatim (tests/golden/make_golden.py)"""
+    g = np.load(os.path.join(GOLDEN, "phase_ref.npz"))
+    orc = Oracle(np.float32)
+    for k, gg in enumerate(g["g"]):
+        wo, pdf = orc.hg_sample(float(gg), g["wi"], g["xi"])
+        assert np.array_equal(wo, g["wo_%d" % k]) and np.array_equal(pdf, g["pdf_%d" % k])
+        assert np.array_equal(orc.hg_eval(float(gg), g["wi"], g["wo_in"]), g["eval_%d" % k])
+    s, t = orc.coordinate_system(g["wi"])
+    assert np.array_equal(s, g["frame_s"]) and np.array_equal(t, g["frame_t"])
+    F, ct = orc.fresnel_dielectric_ext(g["cos_i"], g["eta"])
+    assert np.array_equal(F, g["fresnel"]) and np.array_equal(ct, g["cos_t"])
+
+
+@pytest.mark.skipif(not RefPhase.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_phase_bit_exact_vs_verbatim_reference():
+    rng = np.random.default_rng(11)
+    n = 200000
+    wi = rng.normal(size=(n, 3))
+    wi = (wi / np.linalg.norm(wi, axis=1, keepdims=True)).astype(np.float32)
+    wo = rng.normal(size=(n, 3))
+    wo = (wo / np.linalg.norm(wo, axis=1, keepdims=True)).astype(np.float32)
+    xi = rng.random((n, 2)).astype(np.float32)
+    ref, orc = RefPhase(), Oracle(np.float32)
+    for gg in (0.9, -0.3, 0.99, 0.0, 5e-5):
+        a, pa = orc.hg_sample(gg, wi, xi)
+        b, pb = ref.hg_sample(gg, wi, xi)
+        assert np.array_equal(a, b) and np.array_equal(pa, pb)
+        assert np.array_equal(orc.hg_eval(gg, wi, wo), ref.hg_eval(gg, wi, wo))
+    assert all(np.array_equal(x, y) for x, y in zip(orc.coordinate_system(wi), ref.coordinate_system(wi)))
+    cos_i = (rng.random(n) * 2 - 1).astype(np.float32)
+    eta = (1 + rng.random(n)).astype(np.float32)
+    assert all(np.array_equal(x, y) for x, y in zip(orc.fresnel_dielectric_ext(cos_i, eta), ref.fresnel_dielectric_ext(cos_i, eta)))
 
 
 def test_spline_interpolates_data_at_nodes(oracle64):
