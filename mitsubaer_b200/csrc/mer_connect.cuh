@@ -77,7 +77,7 @@ static __device__ void rif_field(const RifDev &R, float3 pw, Field &F) {
 #pragma unroll
     for (int dz = 0; dz < 4; dz++) {
         float4 c[4];
-        if (interior) rif_slab_tex(R, i0, j0, k0 - 1 + dz, c);
+        if (interior) rif_slab_interior<-1>(R, i0, j0, k0 - 1 + dz, c);
         else rif_slab_clamped(R, i0, j0, k0 - 1 + dz, c);
         float b00 = 0, b10 = 0, b20 = 0, b01 = 0, b11 = 0, b02 = 0;
 #pragma unroll

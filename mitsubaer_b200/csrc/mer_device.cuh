@@ -41,6 +41,9 @@ struct RifDev {
      * 4x4x4 stencil, at any alignment. */
     unsigned long long tex;
     int tileShift, tileMask;
+    /* Alternative storage for the load/store path: 2 x float4 per voxel = (c[x-1..x+2] of row y, c[x-1..x+2] of row y+1),
+     * one aligned 32-byte sector.  A 4x4x4 stencil is 8 LDG.E.256.  null: the atlas is used. */
+    const float4 *coeff8;
 };
 
 struct GridDev {
@@ -161,6 +164,24 @@ __device__ __forceinline__ void rif_slab_tex(const RifDev &R, int i0, int j0, in
     c[2] = make_float4(C.w, C.z, D.w, D.z);
     c[3] = make_float4(C.x, C.y, D.x, D.y);
 }
+/* one 32-byte sector per lane: LDG.E.256 (sm_100+), read-only path */
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+/* the same four rows from the coeff8 table: two sectors */
+__device__ __forceinline__ void rif_slab_lsu(const RifDev &R, int i0, int j0, int k, float4 c[4]) {
+    const float4 *base = R.coeff8 + 2 * (((size_t) k * (size_t) R.N[1] + (size_t) (j0 - 1)) * (size_t) R.N[0] + (size_t) i0);
+    ldg256(base, c[0], c[1]);
+    ldg256(base + 4 * (size_t) R.N[0], c[2], c[3]);
+}
+/* LAYOUT: 0 atlas (texture gathers), 1 coeff8 (256-bit loads), -1 whichever the volume has (warp-uniform branch) */
+template <int LAYOUT>
+__device__ __forceinline__ void rif_slab_interior(const RifDev &R, int i0, int j0, int k, float4 c[4]) {
+    if (LAYOUT == 1 || (LAYOUT < 0 && R.coeff8)) rif_slab_lsu(R, i0, j0, k, c);
+    else rif_slab_tex(R, i0, j0, k, c);
+}
 __device__ __forceinline__ void rif_slab_clamped(const RifDev &R, int i0, int j0, int k, float4 c[4]) {
     const int N0 = R.N[0], N1 = R.N[1], N2 = R.N[2];
     const int xa = clampi(i0 - 1, 0, N0 - 1), xb = clampi(i0, 0, N0 - 1), xc = clampi(i0 + 1, 0, N0 - 1), xd = clampi(i0 + 2, 0, N0 - 1);
@@ -183,8 +204,13 @@ __device__ __forceinline__ void rif_tricubic(const RifDev &R, float3 pv, float &
     bs_weights(z, fz, wz0, wz1);
     float4 c[16];
     if (rif_cell_interior(R, i0, j0, k0)) {
+        if (R.coeff8) {
 #pragma unroll
-        for (int dz = 0; dz < 4; dz++) rif_slab_tex(R, i0, j0, k0 - 1 + dz, c + 4 * dz);
+            for (int dz = 0; dz < 4; dz++) rif_slab_lsu(R, i0, j0, k0 - 1 + dz, c + 4 * dz);
+        } else {
+#pragma unroll
+            for (int dz = 0; dz < 4; dz++) rif_slab_tex(R, i0, j0, k0 - 1 + dz, c + 4 * dz);
+        }
     } else {
 #pragma unroll 1
         for (int dz = 0; dz < 4; dz++) rif_slab_clamped(R, i0, j0, k0 - 1 + dz, c + 4 * dz);
@@ -287,32 +313,27 @@ template <> struct StencilCache<MER_RIF_TRILINEAR_PACKED> : StencilStore<8> {
     }
 };
 
-/* unconditional (re)load of the block of cell (i0, j0, k0) */
+/* load of the block of an INTERIOR cell (every tap inside the grid) */
+template <int LAYOUT = -1>
+__device__ __forceinline__ void rif_fetch_interior(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
+#pragma unroll
+    for (int dz = 0; dz < 4; dz++) {
+        float4 c[4];
+        rif_slab_interior<LAYOUT>(R, i0, j0, k0 - 1 + dz, c);
+        S.set(dz * 4 + 0, c[0]); S.set(dz * 4 + 1, c[1]); S.set(dz * 4 + 2, c[2]); S.set(dz * 4 + 3, c[3]);
+    }
+    S.i = i0; S.j = j0; S.k = k0;
+}
+/* unconditional (re)load of the block of cell (i0, j0, k0), whatever the cell */
 __device__ __forceinline__ void rif_fetch(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
     if (rif_cell_interior(R, i0, j0, k0)) {
-#pragma unroll
-        for (int dz = 0; dz < 4; dz++) {
-            float4 c[4];
-            rif_slab_tex(R, i0, j0, k0 - 1 + dz, c);
-            S.set(dz * 4 + 0, c[0]); S.set(dz * 4 + 1, c[1]); S.set(dz * 4 + 2, c[2]); S.set(dz * 4 + 3, c[3]);
-        }
+        if (R.coeff8) rif_fetch_interior<1>(R, S, i0, j0, k0);
+        else rif_fetch_interior<0>(R, S, i0, j0, k0);
     } else {
 #pragma unroll
         for (int dz = 0; dz < 4; dz++) {
             float4 c[4];
             rif_slab_clamped(R, i0, j0, k0 - 1 + dz, c);
-            S.set(dz * 4 + 0, c[0]); S.set(dz * 4 + 1, c[1]); S.set(dz * 4 + 2, c[2]); S.set(dz * 4 + 3, c[3]);
-        }
-    }
-    S.i = i0; S.j = j0; S.k = k0;
-}
-/* the same for a SPECULATIVE request: interior cells only (anything else is left to the exact request that follows) */
-__device__ __forceinline__ void rif_fetch_interior(const RifDev &R, StencilCache<MER_RIF_TRICUBIC> &S, int i0, int j0, int k0) {
-    if (rif_cell_interior(R, i0, j0, k0)) {
-#pragma unroll
-        for (int dz = 0; dz < 4; dz++) {
-            float4 c[4];
-            rif_slab_tex(R, i0, j0, k0 - 1 + dz, c);
             S.set(dz * 4 + 0, c[0]); S.set(dz * 4 + 1, c[1]); S.set(dz * 4 + 2, c[2]); S.set(dz * 4 + 3, c[3]);
         }
         S.i = i0; S.j = j0; S.k = k0;
@@ -505,6 +526,7 @@ __device__ __forceinline__ void rif_fetch(const RifDev &R, StencilCache<MER_RIF_
     S.i = -0x7fffffff;
     stencil_ensure(R, S, i0, j0, k0);
 }
+template <int LAYOUT = -1>
 __device__ __forceinline__ void rif_fetch_interior(const RifDev &R, StencilCache<MER_RIF_TRILINEAR_PACKED> &S, int i0, int j0, int k0) {
     rif_fetch(R, S, i0, j0, k0); /* indices are clamped into the grid by rif_cell */
 }

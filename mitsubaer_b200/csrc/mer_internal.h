@@ -20,6 +20,7 @@ struct mer_rif {
     RifDev dev;
     float *d_coeff;
     float4 *d_packed;
+    float4 *d_coeff8 = nullptr;     /* sector table for the load/store path (layout "coeff8") */
     cudaArray_t texArray = nullptr; /* atlas of the coefficient layers (texture storage) */
     size_t texW = 0, texH = 0;
     cudaTextureObject_t tex = 0;

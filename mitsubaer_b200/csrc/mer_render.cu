@@ -41,6 +41,9 @@
 #ifndef MER_RENDER_MIN_BLOCKS
 #define MER_RENDER_MIN_BLOCKS 3 /* 170 registers/thread: the 64-register stencil cache fits without spills */
 #endif
+#ifndef MER_EVENT_MIN_BLOCKS
+#define MER_EVENT_MIN_BLOCKS 4 /* the event kernel is latency-bound: 128 registers, 16 warps per SM */
+#endif
 
 namespace {
 
@@ -56,7 +59,8 @@ enum PathKind : int {
     E_NEW = 8,   /* needs a new camera sample */
     E_SURFACE = 9, /* at the container surface with the field known: dielectric interaction (hdielectric boundary) */
     E_SCATTER = 10, /* real collision accepted, throughput updated: direct connection request, phase sampling, roulette */
-    K_DEAD = 11
+    K_DEAD = 11,
+    E_FINISH = 12   /* the sample is finished, its splat is pending (inside one call of the event code only) */
 };
 
 enum {
@@ -258,13 +262,15 @@ __device__ __forceinline__ float path_weight(const RenderParams &P, float len) {
     return 0.0f;
 }
 
-#define ST_INC(st, i) atomicAdd(&(st)[i], 1u)
-__device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha, float wgt, int frame,
-                                         unsigned *nonfinite) {
+/* per-thread event counters (registers; reduced per warp at the end of the event kernel) */
+struct EvStats { unsigned v[ST_COUNT]; };
+#define ST_INC(st, i) ((st).v[i]++)
+/* returns true when the sample is dropped because a value is not finite (imageblock.h:147-152) */
+__device__ __noinline__ bool film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha, float wgt, int frame) {
     const float value[5] = {L[0], L[1], L[2], alpha, wgt};
 #pragma unroll
     for (int k = 0; k < 5; k++)
-        if (!isfinite(value[k])) { atomicAdd(nonfinite, 1u); return; }
+        if (!isfinite(value[k])) return true;
     const float px = sx - 0.5f, py = sy - 0.5f, r = P.filterRadius;
     const int x0 = max((int) ceilf(px - r), 0), y0 = max((int) ceilf(py - r), 0),
               x1 = min((int) floorf(px + r), P.W - 1), y1 = min((int) floorf(py + r), P.H - 1);
@@ -281,6 +287,7 @@ __device__ __noinline__ void film_put(const RenderParams &P, float sx, float sy,
             atomicAdd(dest + P.channels - 1, w * value[4]);
         }
     }
+    return false;
 }
 
 /* the sample's film position is draw 0/1 of its Philox stream: recomputed, not stored */
@@ -296,19 +303,20 @@ __device__ __forceinline__ void sample_position(const RenderParams &P, unsigned 
 /* EXTRAS = any of: transient film, direct connections, light tracing.  The plain camera walk is compiled without them. */
 template <bool EXTRAS>
 __device__ __forceinline__ void finish_sample(const RenderParams &P, Lane &L, const float rad[3], float alpha,
-                                              unsigned *st, float pathLength = INFINITY) {
-    if (EXTRAS && P.lightMode) { L.kind = E_NEW; return; } /* a light path that leaves or dies deposits nothing: only its connections do */
+                                              EvStats &st, float pathLength = INFINITY) {
+    L.kind = E_NEW;
+    if (EXTRAS && P.lightMode) return; /* a light path that leaves or dies deposits nothing: only its connections do */
     float sx, sy;
     sample_position(P, L.pixel, L.sample, sx, sy);
+    float out[3] = {rad[0], rad[1], rad[2]};
+    int frame = 0;
     if (EXTRAS && P.modulation) {
         const float w = path_weight(P, pathLength);
-        const float mod[3] = {rad[0] * w, rad[1] * w, rad[2] * w};
-        film_put(P, sx, sy, mod, alpha, 1.0f, 0, st + ST_NONFINITE);
-        L.kind = E_NEW;
-        return;
+        out[0] *= w; out[1] *= w; out[2] *= w;
+    } else if (EXTRAS) {
+        frame = path_frame(P, pathLength);
     }
-    film_put(P, sx, sy, rad, alpha, 1.0f, EXTRAS ? path_frame(P, pathLength) : 0, st + ST_NONFINITE);
-    L.kind = E_NEW;
+    if (film_put(P, sx, sy, out, alpha, 1.0f, frame)) ST_INC(st, ST_NONFINITE);
 }
 
 __device__ __forceinline__ void begin_trace(const RenderParams &P, Lane &L, float dist) {
@@ -379,154 +387,213 @@ __device__ __noinline__ void edge_weight(const MediumDev &M, float sd, float d, 
         edge[c] = success ? __fdiv_rn(__fmul_rn(M.sigmaS[c], T[c]), ps) : __fdiv_rn(T[c], pf);
 }
 
-/* phase sampling (wi = normalize(-mRec.d)) and the Russian roulette of volpath.cpp:326-336 at a scattering vertex */
-template <bool DIELECTRIC, bool EXTRAS>
-__device__ __forceinline__ void scatter_and_roulette(const RenderParams &P, Lane &L, float3 wi, unsigned *st) {
-    const float zero[3] = {0.f, 0.f, 0.f};
-    float u1 = L.rng.next(), u2 = L.rng.next();
-    L.v = hg_sample_dev(P.M.g, wi, u1, u2);
-    if (L.depth++ >= P.rrDepth) {
-        float q = fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2]));
-        if (DIELECTRIC) q *= L.etaPath * L.etaPath;
-        q = fminf(q, 0.95f);
-        if (L.rng.next() >= q) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); return; }
-#pragma unroll
-        for (int c = 0; c < 3; c++) L.thr[c] /= q;
-    }
-    L.kind = E_BEGIN; /* field at p is still valid */
-}
-
-/* Everything that is not a leapfrog step.  Runs until the lane is steppable again or dead.
+/* Everything that is not a plain full step, ONE PASS over the kinds of event in the order a path runs through them:
+ *     A  one er_step with a direct lookup (remainder step, step back, entry, edge-of-grid steps)
+ *     R  end of a path edge: Woodcock test / edge weights; null collision -> next flight; exit -> radiance or surface
+ *     C  scattering vertex: direct-connection request, phase sampling, Russian roulette
+ *     S  dielectric container surface
+ *     B  start of a path edge: free-flight distance
+ *     F  film splat of a finished sample
+ *     N  next camera sample (or emitter sample in light-tracing mode)
+ * A collision runs A R [C] B in one call, an exit A R F N; what is left (the entry step of the new sample, a step back
+ * after a remainder step that left the shape) waits for the next round's call.  One pass instead of a loop over "the
+ * lane's current kind": every block is executed at most once per call by all the lanes that need it (the loop ran the
+ * blocks in whatever order the lanes' kinds came up, 10 of 32 lanes: ncu r02z), and there is one splat site.
  * DIELECTRIC selects the container surface: false = index-matched null surface, true = hdielectric. */
 template <int MODE, bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE, bool XFORM>
-__device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, unsigned *st) {
+__device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, EvStats &st) {
     const MediumDev &M = P.M;
-    const float zero[3] = {0.f, 0.f, 0.f};
-    L.rng.cachedBlock = 0xffffffffu; /* the cached Philox block lives only inside one event phase (registers) */
-    while ((L.kind != K_FULL || (L.flags & FLAG_SLOW)) && L.kind != K_DEAD && !(L.flags & FLAG_PARKED)) {
-        if (L.kind <= K_ENTRY) {
-            /* ---- one er_step outside the hot loop (:653-661 inside trace() :674-686 / traceTillBoundary() :748-762):
-             * the remainder step, the step back after leaving the shape, the zero-length step that fetches the field
-             * where a ray enters the container, and full steps whose stencil touches the edge of the grid.  A direct
-             * 64-tap lookup (no cached block), same arithmetic as the hot loop's step. */
-            const int kind = L.kind;
-            const float hc = step_length(kind, M.h, L.rem);
-            if (!(L.flags & FLAG_DRIFTED)) lane_drift<EXTRAS>(L, hc);
-            L.flags &= ~(FLAG_DRIFTED | FLAG_SLOW);
-            rif_lookup<MODE>(M.rif, L.p, L.n, L.G);
-            lane_kick(L, hc);
-            const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
-            if (kind != K_ENTRY) ST_INC(st, ST_STEPS2);
-            if (kind == K_FULL) {
-                if (inside) {
-                    L.distSurf += M.h;
-                    L.stepsLeft--;
-                    L.kind = L.stepsLeft > 0 ? K_FULL : ((L.flags & FLAG_TB) ? E_EXIT : K_REM);
-                    if (L.kind == K_FULL) { /* hand it back drifted if the next stencil is interior again */
-                        lane_drift<EXTRAS>(L, M.h);
-                        const CellPos cn = rif_cell<MODE, XFORM>(M.rif, L.p);
-                        if (!rif_cell_fast<MODE>(M.rif, cn)) L.flags |= FLAG_SLOW;
-                    }
+    L.rng.cachedBlock = 0xffffffffu; /* the cached Philox block lives only inside one call (registers) */
+    float frad[3] = {0.f, 0.f, 0.f}, falpha = 1.0f, flen = INFINITY; /* the finished sample's splat (kind E_FINISH) */
+#define MER_FINISH(r0_, r1_, r2_, a_, len_) do { frad[0] = (r0_); frad[1] = (r1_); frad[2] = (r2_); falpha = (a_); flen = (len_); L.kind = E_FINISH; } while (0)
+
+    /* ---- A: one er_step outside the step kernel (:653-661 inside trace() :674-686 / traceTillBoundary() :748-762): the
+     * remainder step, the step back after leaving the shape, the zero-length step that fetches the field where a ray
+     * enters the container, and full steps whose stencil touches the edge of the grid.  A direct 64-tap lookup (no
+     * cached block), same arithmetic as the step kernel's. */
+    if (L.kind <= K_ENTRY && (L.kind != K_FULL || (L.flags & FLAG_SLOW))) {
+        const int kind = L.kind;
+        const float hc = step_length(kind, M.h, L.rem);
+        if (!(L.flags & FLAG_DRIFTED)) lane_drift<EXTRAS>(L, hc);
+        L.flags &= ~(FLAG_DRIFTED | FLAG_SLOW);
+        rif_lookup<MODE>(M.rif, L.p, L.n, L.G);
+        lane_kick(L, hc);
+        const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
+        if (kind != K_ENTRY) ST_INC(st, ST_STEPS);
+        if (kind == K_FULL) {
+            if (inside) {
+                L.distSurf += M.h;
+                L.stepsLeft--;
+                L.kind = L.stepsLeft > 0 ? K_FULL : ((L.flags & FLAG_TB) ? E_EXIT : K_REM);
+                if (L.kind == K_FULL) { /* hand it back drifted if the next stencil is interior again */
+                    lane_drift<EXTRAS>(L, M.h);
+                    const CellPos cn = rif_cell<MODE, XFORM>(M.rif, L.p);
+                    if (!rif_cell_fast<MODE>(M.rif, cn)) L.flags |= FLAG_SLOW;
+                }
+            } else {
+                L.kind = K_BACKF;
+            }
+        } else if (kind == K_REM) {
+            if (inside) L.distSurf += L.rem;
+            L.kind = inside ? E_REACHED : K_BACKR;
+        } else if (kind == K_ENTRY) {
+            L.kind = DIELECTRIC ? E_SURFACE : E_BEGIN;
+        } else {
+            if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= M.h; /* :761 */
+            L.kind = E_EXIT;
+        }
+    }
+
+    /* ---- R: end of a path edge */
+    if (L.kind == E_REACHED || L.kind == E_EXIT) {
+        bool scatter = false, again = false;
+        float edge[3] = {1.0f, 1.0f, 1.0f};
+        if (L.kind == E_REACHED) {
+            if (M.hasGrid) {
+                /* Woodcock acceptance, heterogeneous.cpp:631-644 */
+                float densityAtT = __fmul_rn(grid_lookup(M.grid, L.p), M.densityScale);
+                if (__fmul_rn(densityAtT, M.invMaxDensity) > L.rng.next()) {
+                    scatter = true;
+                    edge[0] = M.albedo[0]; edge[1] = M.albedo[1]; edge[2] = M.albedo[2];
                 } else {
-                    L.kind = K_BACKF;
+                    ST_INC(st, ST_NULL);
+                    begin_trace(P, L, __fmul_rn(-fastlog_dev(1.0f - L.rng.next()), M.invMaxDensity));
+                    again = true;
                 }
-            } else if (kind == K_REM) {
-                if (inside) L.distSurf += L.rem;
-                L.kind = inside ? E_REACHED : K_BACKR;
-            } else if (kind == K_ENTRY) {
-                L.kind = DIELECTRIC ? E_SURFACE : E_BEGIN;
+            } else if (L.p.x == L.o.x && L.p.y == L.o.y && L.p.z == L.o.z) { /* no forward progress, :517-520 */
+                MER_FINISH(0.f, 0.f, 0.f, 1.0f, INFINITY);
+                again = true;
             } else {
-                if (kind == K_BACKF && (L.flags & FLAG_TB)) L.distSurf -= M.h; /* :761 */
-                L.kind = E_EXIT;
+                scatter = true;
+                edge_weight(M, L.sd, L.segDist, true, edge);
             }
-        } else if (L.kind == E_NEW) {
-            /* ---- SamplingIntegrator::renderBlock: next (pixel, sample) */
-            unsigned long long g = atomicAdd(P.sampleCounter, 1ULL);
-            if (g >= P.totalSamples) { L.kind = K_DEAD; break; }
-            ST_INC(st, ST_SAMPLES);
-            unsigned pixel, k;
-            if (P.totalSamples <= 0xffffffffULL) { /* warp-uniform: 32-bit division in the common case */
-                pixel = (unsigned) g / (unsigned) P.sppLocal;
-                k = (unsigned) g - pixel * (unsigned) P.sppLocal;
-            } else {
-                pixel = (unsigned) (g / (unsigned long long) P.sppLocal);
-                k = (unsigned) (g - (unsigned long long) pixel * (unsigned long long) P.sppLocal);
-            }
-            L.pixel = pixel;
-            L.sample = (unsigned) P.sampleBegin + k * (unsigned) P.sampleStride;
-            L.rng.init(P.seed, (unsigned long long) pixel * (unsigned long long) P.sppTotal + L.sample, 0u);
-            if (EXTRAS && P.lightMode) {
-                /* ---- emitter-side walk: sample the emitter (its stream is keyed like a camera sample's) */
-                float3 o, d;
-                if (P.emitterType == MER_EMITTER_COLLIMATED) { /* collimated.cpp:59-110: delta position and direction, weight = power */
-                    o = f3(P.beamO[0], P.beamO[1], P.beamO[2]);
-                    d = f3(P.beamD[0], P.beamD[1], P.beamD[2]);
-                    L.thr[0] = P.beamPower[0]; L.thr[1] = P.beamPower[1]; L.thr[2] = P.beamPower[2];
-                } else { /* two-sided diffuse quad: uniform position, cosine-weighted direction => weight Le * pi * Area * 2 */
-                    const float u1 = L.rng.next(), u2 = L.rng.next(), u3 = L.rng.next(), u4 = L.rng.next(), u5 = L.rng.next();
-                    const float3 qu = f3(P.quadU[0], P.quadU[1], P.quadU[2]), qv = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
-                    float3 Nq = f3(qu.y * qv.z - qu.z * qv.y, qu.z * qv.x - qu.x * qv.z, qu.x * qv.y - qu.y * qv.x);
-                    const float area = sqrtf(dot3(Nq, Nq)), side = u3 < 0.5f ? 1.0f : -1.0f;
-                    Nq = f3(Nq.x / area * side, Nq.y / area * side, Nq.z / area * side);
-                    float3 sa, ta;
-                    coordinate_system(Nq, sa, ta);
-                    const float rr = sqrtf(u4), lz = sqrtf(fmaxf(0.0f, 1.0f - u4));
-                    float sp, cp;
-                    sincosf(6.283185307179586f * u5, &sp, &cp);
-                    const float lx = rr * cp, ly = rr * sp;
-                    o = f3(P.quadO[0] + u1 * qu.x + u2 * qv.x, P.quadO[1] + u1 * qu.y + u2 * qv.y, P.quadO[2] + u1 * qu.z + u2 * qv.z);
-                    d = f3(sa.x * lx + ta.x * ly + Nq.x * lz, sa.y * lx + ta.y * ly + Nq.y * lz, sa.z * lx + ta.z * ly + Nq.z * lz);
-                    const float wgt = 6.283185307179586f * area;
-                    L.thr[0] = P.quadLe[0] * wgt; L.thr[1] = P.quadLe[1] * wgt; L.thr[2] = P.quadLe[2] * wgt;
+        } else if (!M.hasGrid) {
+            edge_weight(M, L.sd, L.distSurf, false, edge);
+        }
+        if (!again) {
+            float rrs = (float) (1.0 / (double) (L.refStart * L.refStart)); /* :469 */
+            rrs *= L.n * L.n;                                                /* :501, refEnd = n(p) */
+            if (M.physicalScaling) rrs = 1.0f / rrs;
+            if (EXTRAS && P.lightMode) rrs = 1.0f; /* weight[EImportance] carries no refRatioSq, edge.cpp:96-98 */
+            if (scatter) {
+                ST_INC(st, ST_SCATTER);
+                if (P.maxDepth != -1 && L.depth >= P.maxDepth) {
+                    MER_FINISH(0.f, 0.f, 0.f, 1.0f, INFINITY);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
+                    L.kind = E_SCATTER;
                 }
-                float tBox;
-                if (!intersect_shape<SDFSHAPE>(M, o, d, tBox)) continue; /* misses the medium: next path */
-                L.depth = 1;
-                if (P.maxDepth != -1 && L.depth >= P.maxDepth) continue;
-                if (!DIELECTRIC) L.depth = 2;
-                L.etaPath = 1.0f;
-                L.opl = tBox; /* emitterPathlength counts every edge from the emitter, bdpt_proc.cpp:160-165 */
-                L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
-                L.v = d;
-                L.flags = 0;
-                L.safe = 0.0f;
-                L.n = 1.0f;
-                L.G = f3(0.f, 0.f, 0.f);
-                L.kind = K_ENTRY;
-                continue;
+            } else {
+                ST_INC(st, ST_EXIT);
+#pragma unroll
+                for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
+                if (P.maxDepth != -1 && L.depth >= P.maxDepth) {
+                    MER_FINISH(0.f, 0.f, 0.f, 1.0f, INFINITY);
+                } else {
+                    const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
+                    const float3 d = f3(L.v.x * vinv, L.v.y * vinv, L.v.z * vinv);
+                    if (DIELECTRIC) { /* move to the surface point and fetch the field there, then E_SURFACE */
+                        const float te = SDFSHAPE ? exit_distance_sdf(M, L.p, d) : exit_distance(M, L.p, d);
+                        L.p = f3(L.p.x + te * d.x, L.p.y + te * d.y, L.p.z + te * d.z);
+                        L.safe = 0.0f;
+                        L.v = d;
+                        L.flags |= FLAG_OUTWARD;
+                        L.kind = K_ENTRY;
+                    } else {
+                        L.depth++;
+                        float tq;
+                        const bool hitsQuad = intersect_quad(P, L.p, d, tq);
+                        const bool dark = hitsQuad && EXTRAS && (L.flags & FLAG_COVERED);
+                        const float *Le = hitsQuad ? P.quadLe : P.env;
+                        const float k = dark ? 0.0f : 1.0f;
+                        MER_FINISH(k * L.thr[0] * Le[0], k * L.thr[1] * Le[1], k * L.thr[2] * Le[2], 1.0f, hitsQuad ? L.opl + tq : INFINITY);
+                    }
+                }
             }
-            const unsigned py = pixel / (unsigned) P.W;
-            int x = (int) (pixel - py * (unsigned) P.W), y = (int) py;
-            float sx = (float) x + L.rng.next(), sy = (float) y + L.rng.next();
-            /* PerspectiveCamera::sampleRay, closed form of m_sampleToCamera */
-            float cx = (1.0f - 2.0f * (sx * P.invW)) * P.tanHalf, cy = (1.0f - 2.0f * (sy * P.invH)) * P.tanHalf / P.aspect;
-            float inv = 1.0f / sqrtf(cx * cx + cy * cy + 1.0f);
-            cx *= inv; cy *= inv;
-            float cz = inv;
-            float3 d = f3(P.camLeft[0] * cx + P.camUp[0] * cy + P.camDir[0] * cz,
-                          P.camLeft[1] * cx + P.camUp[1] * cy + P.camDir[1] * cz,
-                          P.camLeft[2] * cx + P.camUp[2] * cy + P.camDir[2] * cz);
-            float3 o = f3(P.camO[0], P.camO[1], P.camO[2]);
-            float tBox, tQuad;
-            bool hitBox = intersect_shape<SDFSHAPE>(M, o, d, tBox), hitQuad = intersect_quad(P, o, d, tQuad);
-            if (hitQuad && (!hitBox || tQuad < tBox)) { finish_sample<EXTRAS>(P, L, P.quadLe, 1.0f, st, (EXTRAS && P.calibrated) ? 0.0f : tQuad); continue; }
-            if (!hitBox) { finish_sample<EXTRAS>(P, L, P.env, 0.0f, st); continue; }
-            L.depth = 1;
-            if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
-            if (!DIELECTRIC) L.depth = 2; /* index-matched container surface, volpath.cpp:287-296 */
-            L.etaPath = 1.0f;
-            L.opl = (EXTRAS && P.calibrated) ? 0.0f : tBox; /* bdpt_proc.cpp:163-171 */
-            L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
-            L.v = d;
-            L.thr[0] = L.thr[1] = L.thr[2] = 1.0f;
-            L.flags = 0;
-            L.safe = 0.0f;
-            L.n = 1.0f;
-            L.G = f3(0.f, 0.f, 0.f);
-            L.kind = K_ENTRY;
-        } else if (L.kind == E_BEGIN) {
-            /* ---- Medium::sampleDistance prologue, heterogeneousrefractive.cpp:402-475; L.v = unit direction */
-            if (!rif_inside_limits(M.rif, L.p)) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
+        }
+    }
+
+    /* ---- C: scattering vertex; L.v = arrival velocity, throughput already carries the edge */
+    if (L.kind == E_SCATTER) {
+        const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
+        const float3 wi = f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv);
+        bool parked = false;
+        if (EXTRAS && P.nee) {
+            if (P.maxDepth == -1 || L.depth + 1 < P.maxDepth) {
+                const unsigned slot = atomicAdd(P.neeCount, 1u);
+                if (slot >= P.neeCap) { /* the host clamps the count; retried next round */
+                    L.flags |= FLAG_PARKED;
+                    parked = true;
+                } else {
+                    P.neeQ0[slot] = make_float4(L.p.x, L.p.y, L.p.z, wi.x);
+                    P.neeQ1[slot] = make_float4(wi.y, wi.z, L.thr[0], L.thr[1]);
+                    P.neeQ2[slot] = make_uint4(__float_as_uint(L.thr[2]), (unsigned) L.depth, L.pixel, L.sample);
+                    P.neeQ3[slot] = L.opl;
+                }
+            }
+            if (!parked) L.flags |= FLAG_COVERED;
+        }
+        if (!parked) { /* phase sampling (wi = normalize(-mRec.d)) and the Russian roulette of volpath.cpp:326-336 */
+            const float u1 = L.rng.next(), u2 = L.rng.next();
+            L.v = hg_sample_dev(M.g, wi, u1, u2);
+            L.kind = E_BEGIN; /* field at p is still valid */
+            if (L.depth++ >= P.rrDepth) {
+                float q = fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2]));
+                if (DIELECTRIC) q *= L.etaPath * L.etaPath;
+                q = fminf(q, 0.95f);
+                if (L.rng.next() >= q) {
+                    MER_FINISH(0.f, 0.f, 0.f, 1.0f, INFINITY);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) L.thr[c] /= q;
+                }
+            }
+        }
+    }
+
+    /* ---- S: container surface with a dielectric BSDF; L.v = unit direction of travel, L.n = RIF at the hit point */
+    if (DIELECTRIC && L.kind == E_SURFACE) {
+        /* MER_SHAPE_SDF: normalised gradient of the signed distance; box / sphere: analytic */
+        const float3 N = SDFSHAPE ? merc::container_normal(M, L.p) : shape_normal(M, L.p);
+        const float u = L.rng.next();
+        L.rng.next(); /* the BSDF sample is a Point2 */
+        float3 dOut;
+        float w, es;
+        const bool transmitted = hdielectric_sample(L.v, N, L.n, u, !(EXTRAS && P.lightMode), dOut, w, es);
+#pragma unroll
+        for (int c = 0; c < 3; c++) L.thr[c] *= w;
+        L.etaPath *= es;
+        L.v = dOut;
+        const bool inside = (L.flags & FLAG_OUTWARD) ? !transmitted : transmitted;
+        L.flags &= ~FLAG_OUTWARD;
+        if (!inside) { /* rayIntersectAndLookForEmitter with a delta BSDF: MIS weight 1, volpath.cpp:300-320 */
+            float tq;
+            const bool hitsQuad = intersect_quad(P, L.p, dOut, tq);
+            const bool dark = hitsQuad && EXTRAS && (L.flags & FLAG_COVERED);
+            const float *Le = hitsQuad ? P.quadLe : P.env;
+            const float k = dark ? 0.0f : 1.0f;
+            MER_FINISH(k * L.thr[0] * Le[0], k * L.thr[1] * Le[1], k * L.thr[2] * Le[2], 1.0f, hitsQuad ? L.opl + tq : INFINITY);
+        } else {
+            L.flags &= ~FLAG_COVERED; /* an internal reflection starts a chain no direct connection accounts for */
+            L.kind = E_BEGIN;
+            if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
+                const float q = fminf(fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2])) * L.etaPath * L.etaPath, 0.95f);
+                if (L.rng.next() >= q) {
+                    MER_FINISH(0.f, 0.f, 0.f, 1.0f, INFINITY);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) L.thr[c] /= q;
+                }
+            }
+        }
+    }
+
+    /* ---- B: Medium::sampleDistance prologue, heterogeneousrefractive.cpp:402-475; L.v = unit direction */
+    if (L.kind == E_BEGIN) {
+        if (!rif_inside_limits(M.rif, L.p)) {
+            MER_FINISH(0.f, 0.f, 0.f, 1.0f, INFINITY);
+        } else {
             L.refStart = L.n;
             L.o = L.p;
             L.v = f3(L.v.x * L.n, L.v.y * L.n, L.v.z * L.n);
@@ -545,114 +612,90 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, un
                 }
             }
             begin_trace(P, L, dist);
-        } else if (DIELECTRIC && L.kind == E_SURFACE) {
-            /* ---- container surface with a dielectric BSDF; L.v = unit direction of travel, L.n = RIF at the hit point */
-            /* MER_SHAPE_SDF: normalised gradient of the signed distance; box / sphere: analytic */
-            const float3 N = SDFSHAPE ? merc::container_normal(M, L.p) : shape_normal(M, L.p);
-            const float u = L.rng.next();
-            L.rng.next(); /* the BSDF sample is a Point2 */
-            float3 dOut;
-            float w, es;
-            const bool transmitted = hdielectric_sample(L.v, N, L.n, u, !(EXTRAS && P.lightMode), dOut, w, es);
-#pragma unroll
-            for (int c = 0; c < 3; c++) L.thr[c] *= w;
-            L.etaPath *= es;
-            L.v = dOut;
-            const bool inside = (L.flags & FLAG_OUTWARD) ? !transmitted : transmitted;
-            L.flags &= ~FLAG_OUTWARD;
-            if (!inside) { /* rayIntersectAndLookForEmitter with a delta BSDF: MIS weight 1, volpath.cpp:300-320 */
-                float tq;
-                const bool hitsQuad = intersect_quad(P, L.p, dOut, tq);
-                const float *Le = hitsQuad ? ((EXTRAS && (L.flags & FLAG_COVERED)) ? zero : P.quadLe) : P.env;
-                float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
-                finish_sample<EXTRAS>(P, L, rad, 1.0f, st, hitsQuad ? L.opl + tq : INFINITY);
-                continue;
-            }
-            L.flags &= ~FLAG_COVERED; /* an internal reflection starts a chain no direct connection accounts for */
-            if (L.depth++ >= P.rrDepth) { /* volpath.cpp:326-336 */
-                float q = fminf(fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2])) * L.etaPath * L.etaPath, 0.95f);
-                if (L.rng.next() >= q) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
-#pragma unroll
-                for (int c = 0; c < 3; c++) L.thr[c] /= q;
-            }
-            L.kind = E_BEGIN;
-        } else if (L.kind == E_SCATTER) {
-            /* ---- scattering vertex: L.v = arrival velocity, throughput already carries the edge */
-            const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
-            const float3 wi = f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv);
-            if (EXTRAS && P.nee) {
-                if (P.maxDepth == -1 || L.depth + 1 < P.maxDepth) {
-                    const unsigned slot = atomicAdd(P.neeCount, 1u);
-                    if (slot >= P.neeCap) { L.flags |= FLAG_PARKED; break; } /* the host clamps the count; retried next pass */
-                    P.neeQ0[slot] = make_float4(L.p.x, L.p.y, L.p.z, wi.x);
-                    P.neeQ1[slot] = make_float4(wi.y, wi.z, L.thr[0], L.thr[1]);
-                    P.neeQ2[slot] = make_uint4(__float_as_uint(L.thr[2]), (unsigned) L.depth, L.pixel, L.sample);
-                    if (EXTRAS) P.neeQ3[slot] = L.opl;
-                }
-                L.flags |= FLAG_COVERED;
-            }
-            scatter_and_roulette<DIELECTRIC, EXTRAS>(P, L, wi, st);
-        } else {
-            /* ---- end of a path edge */
-            bool scatter = false;
-            float edge[3];
-            if (L.kind == E_REACHED) {
-                if (M.hasGrid) {
-                    /* Woodcock acceptance, heterogeneous.cpp:631-644 */
-                    float densityAtT = __fmul_rn(grid_lookup(M.grid, L.p), M.densityScale);
-                    if (__fmul_rn(densityAtT, M.invMaxDensity) > L.rng.next()) {
-                        scatter = true;
-                        edge[0] = M.albedo[0]; edge[1] = M.albedo[1]; edge[2] = M.albedo[2];
-                    } else {
-                        ST_INC(st, ST_NULL);
-                        float dist = __fmul_rn(-fastlog_dev(1.0f - L.rng.next()), M.invMaxDensity);
-                        begin_trace(P, L, dist);
-                        continue;
-                    }
-                } else {
-                    if (L.p.x == L.o.x && L.p.y == L.o.y && L.p.z == L.o.z) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; } /* :517-520 */
-                    scatter = true;
-                    edge_weight(M, L.sd, L.segDist, true, edge);
-                }
-            } else { /* E_EXIT */
-                if (M.hasGrid) edge[0] = edge[1] = edge[2] = 1.0f;
-                else edge_weight(M, L.sd, L.distSurf, false, edge);
-            }
-            float rrs = (float) (1.0 / (double) (L.refStart * L.refStart)); /* :469 */
-            rrs *= L.n * L.n;                                                /* :501, refEnd = n(p) */
-            if (M.physicalScaling) rrs = 1.0f / rrs;
-            if (EXTRAS && P.lightMode) rrs = 1.0f; /* weight[EImportance] carries no refRatioSq, edge.cpp:96-98 */
-            const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
-            if (scatter) {
-                ST_INC(st, ST_SCATTER);
-                if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
-#pragma unroll
-                for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
-                if (EXTRAS) L.kind = E_SCATTER; /* the vertex may have to wait for a slot of the request queue */
-                else scatter_and_roulette<DIELECTRIC, false>(P, L, f3(-L.v.x * vinv, -L.v.y * vinv, -L.v.z * vinv), st);
-            } else {
-                ST_INC(st, ST_EXIT);
-#pragma unroll
-                for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
-                if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
-                float3 d = f3(L.v.x * vinv, L.v.y * vinv, L.v.z * vinv);
-                if (DIELECTRIC) { /* move to the surface point and fetch the field there, then E_SURFACE */
-                    const float te = SDFSHAPE ? exit_distance_sdf(M, L.p, d) : exit_distance(M, L.p, d);
-                    L.p = f3(L.p.x + te * d.x, L.p.y + te * d.y, L.p.z + te * d.z);
-                    L.safe = 0.0f;
-                    L.v = d;
-                    L.flags |= FLAG_OUTWARD;
-                    L.kind = K_ENTRY;
-                    continue;
-                }
-                L.depth++;
-                float tq;
-                const bool hitsQuad = intersect_quad(P, L.p, d, tq);
-                const float *Le = hitsQuad ? ((EXTRAS && (L.flags & FLAG_COVERED)) ? zero : P.quadLe) : P.env;
-                float rad[3] = {L.thr[0] * Le[0], L.thr[1] * Le[1], L.thr[2] * Le[2]};
-                finish_sample<EXTRAS>(P, L, rad, 1.0f, st, hitsQuad ? L.opl + tq : INFINITY);
-            }
         }
+    }
+
+    /* ---- F: the one splat site */
+    if (L.kind == E_FINISH) finish_sample<EXTRAS>(P, L, frad, falpha, st, flen);
+#undef MER_FINISH
+
+    /* ---- N: SamplingIntegrator::renderBlock: next (pixel, sample); a few samples that never reach the medium are
+     * finished on the spot */
+    for (int attempt = 0; attempt < 4 && L.kind == E_NEW; attempt++) {
+        unsigned long long g = atomicAdd(P.sampleCounter, 1ULL);
+        if (g >= P.totalSamples) { L.kind = K_DEAD; break; }
+        ST_INC(st, ST_SAMPLES);
+        unsigned pixel, k;
+        if (P.totalSamples <= 0xffffffffULL) { /* warp-uniform: 32-bit division in the common case */
+            pixel = (unsigned) g / (unsigned) P.sppLocal;
+            k = (unsigned) g - pixel * (unsigned) P.sppLocal;
+        } else {
+            pixel = (unsigned) (g / (unsigned long long) P.sppLocal);
+            k = (unsigned) (g - (unsigned long long) pixel * (unsigned long long) P.sppLocal);
+        }
+        L.pixel = pixel;
+        L.sample = (unsigned) P.sampleBegin + k * (unsigned) P.sampleStride;
+        L.rng.init(P.seed, (unsigned long long) pixel * (unsigned long long) P.sppTotal + L.sample, 0u);
+        float3 o, d;
+        float tBox;
+        if (EXTRAS && P.lightMode) {
+            /* ---- emitter-side walk: sample the emitter (its stream is keyed like a camera sample's) */
+            if (P.emitterType == MER_EMITTER_COLLIMATED) { /* collimated.cpp:59-110: delta position and direction, weight = power */
+                o = f3(P.beamO[0], P.beamO[1], P.beamO[2]);
+                d = f3(P.beamD[0], P.beamD[1], P.beamD[2]);
+                L.thr[0] = P.beamPower[0]; L.thr[1] = P.beamPower[1]; L.thr[2] = P.beamPower[2];
+            } else { /* two-sided diffuse quad: uniform position, cosine-weighted direction => weight Le * pi * Area * 2 */
+                const float u1 = L.rng.next(), u2 = L.rng.next(), u3 = L.rng.next(), u4 = L.rng.next(), u5 = L.rng.next();
+                const float3 qu = f3(P.quadU[0], P.quadU[1], P.quadU[2]), qv = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
+                float3 Nq = f3(qu.y * qv.z - qu.z * qv.y, qu.z * qv.x - qu.x * qv.z, qu.x * qv.y - qu.y * qv.x);
+                const float area = sqrtf(dot3(Nq, Nq)), side = u3 < 0.5f ? 1.0f : -1.0f;
+                Nq = f3(Nq.x / area * side, Nq.y / area * side, Nq.z / area * side);
+                float3 sa, ta;
+                coordinate_system(Nq, sa, ta);
+                const float rr = sqrtf(u4), lz = sqrtf(fmaxf(0.0f, 1.0f - u4));
+                float sp, cp;
+                sincosf(6.283185307179586f * u5, &sp, &cp);
+                const float lx = rr * cp, ly = rr * sp;
+                o = f3(P.quadO[0] + u1 * qu.x + u2 * qv.x, P.quadO[1] + u1 * qu.y + u2 * qv.y, P.quadO[2] + u1 * qu.z + u2 * qv.z);
+                d = f3(sa.x * lx + ta.x * ly + Nq.x * lz, sa.y * lx + ta.y * ly + Nq.y * lz, sa.z * lx + ta.z * ly + Nq.z * lz);
+                const float wgt = 6.283185307179586f * area;
+                L.thr[0] = P.quadLe[0] * wgt; L.thr[1] = P.quadLe[1] * wgt; L.thr[2] = P.quadLe[2] * wgt;
+            }
+            if (!intersect_shape<SDFSHAPE>(M, o, d, tBox)) continue; /* misses the medium: next path */
+            L.depth = 1;
+            if (P.maxDepth != -1 && L.depth >= P.maxDepth) continue;
+            L.opl = tBox; /* emitterPathlength counts every edge from the emitter, bdpt_proc.cpp:160-165 */
+        } else {
+            const unsigned py = pixel / (unsigned) P.W;
+            const int x = (int) (pixel - py * (unsigned) P.W), y = (int) py;
+            const float sx = (float) x + L.rng.next(), sy = (float) y + L.rng.next();
+            /* PerspectiveCamera::sampleRay, closed form of m_sampleToCamera */
+            float cx = (1.0f - 2.0f * (sx * P.invW)) * P.tanHalf, cy = (1.0f - 2.0f * (sy * P.invH)) * P.tanHalf / P.aspect;
+            const float inv = 1.0f / sqrtf(cx * cx + cy * cy + 1.0f);
+            cx *= inv; cy *= inv;
+            const float cz = inv;
+            d = f3(P.camLeft[0] * cx + P.camUp[0] * cy + P.camDir[0] * cz, P.camLeft[1] * cx + P.camUp[1] * cy + P.camDir[1] * cz,
+                   P.camLeft[2] * cx + P.camUp[2] * cy + P.camDir[2] * cz);
+            o = f3(P.camO[0], P.camO[1], P.camO[2]);
+            float tQuad;
+            const bool hitBox = intersect_shape<SDFSHAPE>(M, o, d, tBox), hitQuad = intersect_quad(P, o, d, tQuad);
+            const float zero[3] = {0.f, 0.f, 0.f};
+            if (hitQuad && (!hitBox || tQuad < tBox)) { finish_sample<EXTRAS>(P, L, P.quadLe, 1.0f, st, (EXTRAS && P.calibrated) ? 0.0f : tQuad); continue; }
+            if (!hitBox) { finish_sample<EXTRAS>(P, L, P.env, 0.0f, st); continue; }
+            L.depth = 1;
+            if (P.maxDepth != -1 && L.depth >= P.maxDepth) { finish_sample<EXTRAS>(P, L, zero, 1.0f, st); continue; }
+            L.opl = (EXTRAS && P.calibrated) ? 0.0f : tBox; /* bdpt_proc.cpp:163-171 */
+            L.thr[0] = L.thr[1] = L.thr[2] = 1.0f;
+        }
+        if (!DIELECTRIC) L.depth = 2; /* index-matched container surface, volpath.cpp:287-296 */
+        L.etaPath = 1.0f;
+        L.p = f3(o.x + tBox * d.x, o.y + tBox * d.y, o.z + tBox * d.z);
+        L.v = d;
+        L.flags = 0;
+        L.safe = 0.0f;
+        L.n = 1.0f;
+        L.G = f3(0.f, 0.f, 0.f);
+        L.kind = K_ENTRY;
     }
 }
 
@@ -752,11 +795,12 @@ __global__ void k_pool_init(PathPool Q, unsigned nSlots) {
 }
 
 template <int MODE, bool DIELECTRIC, bool EXTRAS, bool SDFSHAPE, bool XFORM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MER_EVENT_MIN_BLOCKS)
 k_event(const __grid_constant__ RenderParams P) {
-    __shared__ unsigned st[ST_COUNT + 1]; /* + live slots */
-    if (threadIdx.x <= ST_COUNT) st[threadIdx.x] = 0u;
-    __syncthreads();
+    EvStats st;
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; i++) st.v[i] = 0u;
+    unsigned live = 0;
     for (unsigned slot = blockIdx.x * blockDim.x + threadIdx.x; slot < P.nSlots; slot += gridDim.x * blockDim.x) {
         const uint2 hk = P.pool.h3[slot];
         unsigned kf = hk.y & ~((unsigned) FLAG_PARKED << 8); /* a parked vertex tries the request queue again */
@@ -767,14 +811,20 @@ k_event(const __grid_constant__ RenderParams P) {
             full_store(P, slot, L);
             kf = (unsigned) L.kind;
         }
-        if ((kf & 0xffu) != K_DEAD) atomicAdd(&st[ST_COUNT], 1u);
+        if ((kf & 0xffu) != K_DEAD) live++;
     }
-    __syncthreads();
-    if (threadIdx.x < ST_COUNT && st[threadIdx.x]) atomicAdd(P.stats + threadIdx.x, (unsigned long long) st[threadIdx.x]);
-    if (threadIdx.x == ST_COUNT && st[ST_COUNT]) atomicAdd(P.live, st[ST_COUNT]);
+    /* one atomic per warp and counter that moved */
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; i++) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, st.v[i]);
+        if (lane == 0 && v) atomicAdd(P.stats + i, (unsigned long long) v);
+    }
+    live = __reduce_add_sync(0xffffffffu, live);
+    if (lane == 0 && live) atomicAdd(P.live, live);
 }
 
-template <int MODE, bool EXTRAS, bool SDFSHAPE, bool XFORM>
+template <int MODE, int LAYOUT, bool EXTRAS, bool SDFSHAPE, bool XFORM>
 __global__ void __launch_bounds__(MER_STENCIL_BLOCK, MER_RENDER_MIN_BLOCKS)
 k_step(const __grid_constant__ RenderParams P) {
     const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
@@ -826,7 +876,7 @@ k_step(const __grid_constant__ RenderParams P) {
             if (!(L.flags & FLAG_DRIFTED)) lane_drift<EXTRAS>(L, h);
             c = rif_cell<MODE, XFORM>(M.rif, L.p);
             if (rif_cell_fast<MODE>(M.rif, c)) {
-                if (!stencil_has(S, c)) rif_fetch_interior(M.rif, S, c.i, c.j, c.k);
+                if (!stencil_has(S, c)) rif_fetch_interior<LAYOUT>(M.rif, S, c.i, c.j, c.k);
                 step = true;
             } else { /* the stencil touches the edge of the grid: a step for the event kernel */
                 L.flags |= FLAG_SLOW;
@@ -985,7 +1035,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                             for (int k = 0; k < 3; k++) rad[k] *= w;
                         }
                         const int frame = (WANT_OPL && !P.modulation) ? path_frame(P, len) : 0;
-                        if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, &nonfinite);
+                        if (frame >= 0 && film_put(P, sx, sy, rad, 0.0f, 0.0f, frame)) atomicAdd(&nonfinite, 1u);
                     }
                 }
             } else if (ok) {
@@ -1015,7 +1065,7 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                     for (int k = 0; k < 3; k++) rad[k] *= w;
                 }
                 const int frame = (WANT_OPL && !P.modulation) ? path_frame(P, oplVertex + C.opl) : 0;
-                if (frame >= 0) film_put(P, sx, sy, rad, 0.0f, 0.0f, frame, &nonfinite);
+                if (frame >= 0 && film_put(P, sx, sy, rad, 0.0f, 0.0f, frame)) atomicAdd(&nonfinite, 1u);
             }
         }
         if (!ok) st[1] = 1u;
@@ -1305,14 +1355,20 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
             if (*(unsigned *) S.hostPinned == 0u) break;
         }
         /* ---- steps: every slot whose path can */
-#define MER_STEP(MODE_, T_, S_)                                                                                          \
+#define MER_STEP(MODE_, L_, T_, S_)                                                                                      \
     do {                                                                                                                 \
-        if (xform) MER_LAUNCH((k_step<MODE_, T_, S_, true>), stepBlocks, TPB, 0, stream, P);                             \
-        else MER_LAUNCH((k_step<MODE_, T_, S_, false>), stepBlocks, TPB, 0, stream, P);                                  \
+        if (xform) MER_LAUNCH((k_step<MODE_, L_, T_, S_, true>), stepBlocks, TPB, 0, stream, P);                         \
+        else MER_LAUNCH((k_step<MODE_, L_, T_, S_, false>), stepBlocks, TPB, 0, stream, P);                              \
     } while (0)
-        if (sdfShape) { if (extras) MER_STEP(MER_RIF_TRICUBIC, true, true); else MER_STEP(MER_RIF_TRICUBIC, false, true); }
-        else if (!packed) { if (extras) MER_STEP(MER_RIF_TRICUBIC, true, false); else MER_STEP(MER_RIF_TRICUBIC, false, false); }
-        else { if (extras) MER_STEP(MER_RIF_TRILINEAR_PACKED, true, false); else MER_STEP(MER_RIF_TRILINEAR_PACKED, false, false); }
+#define MER_STEP2(L_)                                                                                                    \
+    do {                                                                                                                 \
+        if (sdfShape) { if (extras) MER_STEP(MER_RIF_TRICUBIC, L_, true, true); else MER_STEP(MER_RIF_TRICUBIC, L_, false, true); }    \
+        else { if (extras) MER_STEP(MER_RIF_TRICUBIC, L_, true, false); else MER_STEP(MER_RIF_TRICUBIC, L_, false, false); }           \
+    } while (0)
+        if (packed) { if (extras) MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, true, false); else MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, false, false); }
+        else if (m->dev.rif.coeff8) MER_STEP2(1);
+        else MER_STEP2(0);
+#undef MER_STEP2
 #undef MER_STEP
         launches++;
         if (look && !P.nee) {

@@ -9,6 +9,7 @@
  *   .vol v3 format                              src/volume/splinevolume.cpp:39-75, mfiles/writeGridToVol.m
  */
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -82,6 +83,20 @@ k_prefilter(const float *in, float *out, int N0, int N1, int N2, int pass) {
     }
 }
 
+/* coeff [z][y][x] -> coeff8 [z][y][x] = { (c[x-1], c[x], c[x+1], c[x+2]) of row y, the same of row y+1 }, indices clamped
+ * (only interior cells are ever read through this table: rif_cell_interior) */
+__global__ void k_expand_coeff8(const float *__restrict__ coeff, float4 *__restrict__ coeff8, int N0, int N1, size_t total) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const int x = (int) (i % (size_t) N0), y = (int) ((i / (size_t) N0) % (size_t) N1);
+        const float *row = coeff + (i - x);
+        const float *rowUp = y + 1 < N1 ? row + N0 : row;
+        const int xm = max(x - 1, 0), x1 = min(x + 1, N0 - 1), x2 = min(x + 2, N0 - 1);
+        coeff8[2 * i] = make_float4(row[xm], row[x], row[x1], row[x2]);
+        coeff8[2 * i + 1] = make_float4(rowUp[xm], rowUp[x], rowUp[x1], rowUp[x2]);
+    }
+}
+
+/* fast mode: sample the spline (value + gradient) at every grid node */
 __global__ void k_build_packed(RifDev R, float4 *__restrict__ packed, size_t total) {
     const size_t n0 = R.N[0], n01 = (size_t) R.N[0] * R.N[1];
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -263,6 +278,7 @@ void fill_rif_dev(mer_rif *r) {
     D.coeff = r->d_coeff;
     D.packed = r->d_packed;
     D.tex = (unsigned long long) r->tex; /* tileShift / tileMask: rif_build_texture */
+    D.coeff8 = r->d_coeff8;
 }
 
 /* does tld4 return (w, z, x, y) = (i0,j0), (i1,j0), (i0,j1), (i1,j1) and land on the texels it is asked for? */
@@ -334,7 +350,28 @@ int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N1, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_Z);
     const unsigned G = (unsigned) std::min<size_t>(mer_blocks(total, 256), 148u * 16u);
     fill_rif_dev(r);
+    /* Storage of the cubic coefficients for the 4x4x4 gathers: "coeff8" = an 8x table of 32-byte sectors read
+     * with 8 LDG.E.256 per stencil (10.6 cycles of the SM's L1 per lane and stencil, measured), "atlas" = a 1x texture
+     * atlas read with 16 tld4 (20 cycles: the texture unit returns one lane's four texels per 1.27 cycles).  coeff8 when
+     * it fits the budget (MER_COEFF8_MAX_GIB, default 40 GiB per volume), else the atlas; MER_RIF_LAYOUT overrides. */
+    bool useCoeff8 = r->mode == MER_RIF_TRICUBIC;
     {
+        double maxGiB = 40.0;
+        if (const char *e = getenv("MER_COEFF8_MAX_GIB")) maxGiB = atof(e);
+        if ((double) total * 32.0 > maxGiB * (double) (1ull << 30)) useCoeff8 = false;
+        if (const char *e = getenv("MER_RIF_LAYOUT")) {
+            if (!strcmp(e, "atlas")) useCoeff8 = false;
+            else if (!strcmp(e, "coeff8")) useCoeff8 = r->mode == MER_RIF_TRICUBIC;
+        }
+    }
+    if (useCoeff8) {
+        cudaError_t e = mer::pool_malloc((void **) &r->d_coeff8, 2 * total * sizeof(float4));
+        if (e != cudaSuccess) { cudaGetLastError(); r->d_coeff8 = nullptr; useCoeff8 = false; } /* no room: the atlas */
+    }
+    if (useCoeff8) {
+        MER_LAUNCH(k_expand_coeff8, G, 256, 0, s, r->d_coeff, r->d_coeff8, N0, N1, total);
+        r->dev.coeff8 = r->d_coeff8;
+    } else {
         int rc = rif_build_texture(r, s);
         if (rc) return rc;
     }
@@ -522,6 +559,7 @@ void mer_rif_destroy(mer_rif *r) {
     mer::pool_quiesce();
     mer::pool_free(r->d_coeff);
     mer::pool_free(r->d_packed);
+    mer::pool_free(r->d_coeff8);
     if (r->tex) cudaDestroyTextureObject(r->tex);
     mer::array_release(r->device, r->texArray, r->texW, r->texH);
     delete r;
