@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmitsubaer_b200.so")
+LIB_PATH = os.environ.get("MER_LIB") or os.path.join(_HERE, "libmitsubaer_b200.so")  # MER_LIB: a development build to compare
 
 MER_OK, MER_ERR_INVALID, MER_ERR_CUDA, MER_ERR_UNSUPPORTED, MER_ERR_OOM = 0, 1, 2, 3, 4
 RIF_TRICUBIC, RIF_TRILINEAR_PACKED = 0, 1

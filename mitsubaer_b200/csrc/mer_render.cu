@@ -39,7 +39,7 @@
 #include "mer_connect.cuh"
 
 #ifndef MER_RENDER_MIN_BLOCKS
-#define MER_RENDER_MIN_BLOCKS 3 /* 170 registers/thread: the 64-register stencil cache fits without spills */
+#define MER_RENDER_MIN_BLOCKS 4 /* 127 registers, no spills: 16 warps per SM cover the gather latency better than 12 at 168 (C2: 49.6 -> 53.9 M samples/s) */
 #endif
 #ifndef MER_EVENT_MIN_BLOCKS
 #define MER_EVENT_MIN_BLOCKS 4 /* the event kernel is latency-bound: 128 registers, 16 warps per SM */
@@ -1194,7 +1194,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.hasQuad = r->has_quad;
     P.stepsPerPass = r->steps_per_pass > 0 ? r->steps_per_pass : 128;
     if (const char *e = getenv("MER_VISIT")) P.stepsPerPass = std::max(atoi(e), 1); /* tuning knobs */
-    P.refillGate = 2;
+    P.refillGate = 4;
     if (const char *e = getenv("MER_GATE")) P.refillGate = atoi(e);
     P.refillGate = std::min(std::max(P.refillGate, 1), 32);
     P.film = film_dev;
@@ -1236,7 +1236,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     P.neeStraightFirst = r->connection.start_mode != MER_START_RANDOM;
 
     const unsigned TPB = 128;
-    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 8192u;
+    unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 16384u; /* 2.4 M slots, 310 MB: a round's tail is amortised over more visits */
     if (const char *e = getenv("MER_POOL")) pool = (unsigned) atol(e); /* tuning knob */
     if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) P.totalSamples;
     pool = std::max(((pool + TPB - 1) / TPB) * TPB, TPB);

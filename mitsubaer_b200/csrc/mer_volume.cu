@@ -350,20 +350,13 @@ int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N1, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_Z);
     const unsigned G = (unsigned) std::min<size_t>(mer_blocks(total, 256), 148u * 16u);
     fill_rif_dev(r);
-    /* Storage of the cubic coefficients for the 4x4x4 gathers: "coeff8" = an 8x table of 32-byte sectors read
-     * with 8 LDG.E.256 per stencil (10.6 cycles of the SM's L1 per lane and stencil, measured), "atlas" = a 1x texture
-     * atlas read with 16 tld4 (20 cycles: the texture unit returns one lane's four texels per 1.27 cycles).  coeff8 when
-     * it fits the budget (MER_COEFF8_MAX_GIB, default 40 GiB per volume), else the atlas; MER_RIF_LAYOUT overrides. */
-    bool useCoeff8 = r->mode == MER_RIF_TRICUBIC;
-    {
-        double maxGiB = 40.0;
-        if (const char *e = getenv("MER_COEFF8_MAX_GIB")) maxGiB = atof(e);
-        if ((double) total * 32.0 > maxGiB * (double) (1ull << 30)) useCoeff8 = false;
-        if (const char *e = getenv("MER_RIF_LAYOUT")) {
-            if (!strcmp(e, "atlas")) useCoeff8 = false;
-            else if (!strcmp(e, "coeff8")) useCoeff8 = r->mode == MER_RIF_TRICUBIC;
-        }
-    }
+    /* Storage of the cubic coefficients for the 4x4x4 gathers.  "atlas" (default) = a 1x texture atlas read
+     * with 16 tld4: 20 cycles of the SM's texture unit per lane and stencil (it returns one lane's four texels per 1.27
+     * cycles), L2-resident up to ~300^3.  "coeff8" (MER_RIF_LAYOUT=coeff8) = an 8x table of 32-byte sectors read with 8
+     * LDG.E.256: 10.6 cycles of the L1 per lane and stencil, but 512 MiB at 256^3 — every stencil comes from DRAM, and
+     * with 16 warps per SM that latency is not covered (C2: 41 vs 50 M samples/s; profiles/README.md). */
+    bool useCoeff8 = false;
+    if (const char *e = getenv("MER_RIF_LAYOUT")) useCoeff8 = !strcmp(e, "coeff8") && r->mode == MER_RIF_TRICUBIC;
     if (useCoeff8) {
         cudaError_t e = mer::pool_malloc((void **) &r->d_coeff8, 2 * total * sizeof(float4));
         if (e != cudaSuccess) { cudaGetLastError(); r->d_coeff8 = nullptr; useCoeff8 = false; } /* no room: the atlas */
