@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MER_ABI_VERSION 9
+#define MER_ABI_VERSION 10
 
 enum mer_status {
     MER_OK = 0,
@@ -199,6 +199,11 @@ int mer_medium_trace_batch(const mer_medium *medium, size_t n, float *p, float *
 int mer_medium_trace_device(const mer_medium *medium, size_t n, float *p_dev, float *v_dev,
                             const float *dist_dev, uint8_t *success_dev, float *dist_surf_dev,
                             float *opl_dev, int32_t *nsteps_dev, void *stream);
+/* the same, and *block_fetches_dev (device memory, may be NULL) is INCREMENTED by the number of 4x4x4 coefficient blocks
+ * (8 nodes in the packed mode) the stepper gathered from the grid: the algorithmic memory traffic of the C4 sweep */
+int mer_medium_trace_counted_device(const mer_medium *medium, size_t n, float *p_dev, float *v_dev,
+                                    const float *dist_dev, uint8_t *success_dev, float *dist_surf_dev,
+                                    float *opl_dev, int32_t *nsteps_dev, uint64_t *block_fetches_dev, void *stream);
 /* traceTillBoundary() (:742-776) */
 int mer_medium_trace_till_boundary_batch(const mer_medium *medium, size_t n, float *p, float *v,
                                          float *dist_surf_out, float *opl_out, int32_t *nsteps_out);
@@ -359,6 +364,12 @@ typedef struct mer_render_stats {
     uint64_t connection_steps;     /* Hessian-carrying leapfrog steps spent in the solver */
     uint64_t kernel_launches;
     float device_ms;         /* CUDA-event time of the render kernels */
+    float step_kernel_ms;    /* of which: the step kernel (the dominant kernel), summed over its launches */
+    uint64_t step_launches;  /* launches of the step kernel */
+    float tail_ms;           /* of device_ms: the drain tail, from the first look at the pool that found fewer than half of
+                                the path slots alive (the frame has run out of new samples) to the end */
+    uint64_t block_fetches;  /* 4x4x4 coefficient blocks (256 bytes; 8 packed-trilinear nodes = 128 bytes) gathered from the grid:
+                                the algorithmic memory traffic of the stepper (one per cell change, not per step) */
 } mer_render_stats;
 
 /* Integrator::render (include/mitsuba/render/integrator.h:61-96) for the eikonal volumetric

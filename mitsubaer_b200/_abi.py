@@ -81,7 +81,8 @@ class RenderStats(C.Structure):
                 ("null_collisions", C.c_uint64), ("boundary_exits", C.c_uint64),
                 ("nonfinite_dropped", C.c_uint64), ("passes", C.c_uint64), ("connections", C.c_uint64),
                 ("connections_failed", C.c_uint64), ("connection_steps", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("device_ms", C.c_float)]
+                ("device_ms", C.c_float), ("step_kernel_ms", C.c_float), ("step_launches", C.c_uint64), ("tail_ms", C.c_float),
+                ("block_fetches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -121,6 +122,7 @@ SIGNATURES = {
     "mer_medium_resolved": (C.c_int, [_vp, C.POINTER(MediumDesc), _fp]),
     "mer_medium_trace_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp, _u8p, _fp, _fp, _i32p]),
     "mer_medium_trace_device": (C.c_int, [_vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mer_medium_trace_counted_device": (C.c_int, [_vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mer_medium_trace_till_boundary_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp, _fp, _i32p]),
     "mer_medium_sample_distance_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp, _fp, C.POINTER(SamplingRecords)]),
     "mer_medium_eval_transmittance_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp]),

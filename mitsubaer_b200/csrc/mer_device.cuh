@@ -737,7 +737,7 @@ static __device__ __noinline__ float3 hg_sample_dev(float g, float3 wi, float u1
     }
     float sinTheta = __fsqrt_rn(fmaxf(0.0f, __fsub_rn(1.0f, __fmul_rn(cosTheta, cosTheta))));
     /* `2*M_PI*sample.y` is a FLOAT product: constants.h:42-44,84-86 re-define M_PI as M_PI_FLT under -DSINGLE_PRECISION
-     * (pinned by src/phase/hg.cpp compiled verbatim, oracle/ref_phase.cpp) */
+     * (checked against src/phase/hg.cpp compiled verbatim: tests/golden/phase_ref.npz) */
     float phi = __fmul_rn(6.2831854820251464844f, u2);
     float sinPhi, cosPhi;
     sincosf(phi, &sinPhi, &cosPhi);

@@ -49,8 +49,11 @@ struct RenderScratch {
     unsigned long long *counters = nullptr;
     unsigned long long *hostPinned = nullptr;
     void *paramsDev = nullptr, *paramsHost = nullptr; /* RenderParams of the pass in flight (global copy + pinned staging) */
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evTail = nullptr;
+    enum { RING = 32 };
+    cudaEvent_t ring[2 * RING] = {nullptr}; /* event pairs around the step kernel's launches (mer_render_stats.step_kernel_ms) */
     void release() {
+        for (cudaEvent_t &e : ring) { if (e) cudaEventDestroy(e); e = nullptr; }
         for (void *&p : pool) { cudaFree(p); p = nullptr; }
         for (void *&p : neeQ) { cudaFree(p); p = nullptr; }
         cudaFree(neeCount); neeCount = nullptr;
@@ -68,6 +71,8 @@ struct RenderScratch {
         paramsHost = nullptr;
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (evTail) cudaEventDestroy(evTail);
+        evTail = nullptr;
         ev0 = ev1 = nullptr;
         poolBytes = 0;
     }

@@ -95,11 +95,12 @@ template <int MODE, bool TILL_BOUNDARY, bool SDFSHAPE = false>
 __global__ void __launch_bounds__(128, 3)
 k_trace(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P, float *__restrict__ V,
         const float *__restrict__ dist, uint8_t *__restrict__ success, float *__restrict__ distSurfOut,
-        float *__restrict__ oplOut, int32_t *__restrict__ nstepsOut) {
+        float *__restrict__ oplOut, int32_t *__restrict__ nstepsOut, unsigned long long *__restrict__ fetchesOut) {
     const size_t stride = (size_t) gridDim.x * blockDim.x;
     size_t next = (size_t) blockIdx.x * blockDim.x + threadIdx.x, cur = 0;
     StencilCache<MODE> S;
     S.invalidate();
+    unsigned nFetch = 0; /* coefficient blocks gathered (cell changes incl. speculative requests): the algorithmic traffic */
     float3 p = f3(0.f, 0.f, 0.f), v = p, G = p;
     float n = 1.0f, ds = 0.0f, opl = 0.0f, rem = 0.0f;
     int kind = T_IDLE, stepsLeft = 0, count = 0;
@@ -123,7 +124,9 @@ k_trace(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P
             const float hc = k == T_FULL ? h : (k == T_REM ? rem : (k == T_BACKF ? -h : (k == T_BACKR ? -rem : 0.0f)));
             /* measured (C4 sweep): speculation pays in the packed mode (+16 %) but costs the compute-bound
              * tricubic stepper 3-14 % */
+            const int si = S.i, sj = S.j, sk = S.k;
             er_step_fused<MODE, MODE == MER_RIF_TRILINEAR_PACKED>(M.rif, S, p, v, n, G, hc, opl);
+            nFetch += (S.i != si || S.j != sj || S.k != sk) ? 1u : 0u;
             const bool inside = SDFSHAPE ? inside_shape_any(M, p) : inside_shape(M, p);
             bool done = false, ok = false;
             if (k == T_ENTRY) {
@@ -159,6 +162,10 @@ k_trace(const __grid_constant__ MediumDev M, size_t nRays, float *__restrict__ P
                 kind = T_IDLE;
             }
         }
+    }
+    if (fetchesOut) {
+        nFetch = __reduce_add_sync(0xffffffffu, nFetch);
+        if ((threadIdx.x & 31u) == 0u && nFetch) atomicAdd(fetchesOut, (unsigned long long) nFetch);
     }
 }
 
@@ -443,6 +450,12 @@ int mer_medium_resolved(const mer_medium *m, mer_medium_desc *out, float *sampli
 int mer_medium_trace_device(const mer_medium *m, size_t n, float *p_dev, float *v_dev, const float *dist_dev,
                             uint8_t *success_dev, float *dist_surf_dev, float *opl_dev, int32_t *nsteps_dev,
                             void *stream) {
+    return mer_medium_trace_counted_device(m, n, p_dev, v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev, nullptr, stream);
+}
+
+int mer_medium_trace_counted_device(const mer_medium *m, size_t n, float *p_dev, float *v_dev, const float *dist_dev,
+                                    uint8_t *success_dev, float *dist_surf_dev, float *opl_dev, int32_t *nsteps_dev,
+                                    uint64_t *block_fetches_dev, void *stream) {
     MER_REQUIRE(m && (n == 0 || (p_dev && v_dev && dist_dev)), "null argument");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(m->device);
@@ -450,13 +463,13 @@ int mer_medium_trace_device(const mer_medium *m, size_t n, float *p_dev, float *
         MER_REQUIRE(m->dev.hasSdf, "shape type SDF needs the sdf volume (mer_medium_set_sdf)");
         if (m->rif->mode != MER_RIF_TRICUBIC) return mer::fail(MER_ERR_UNSUPPORTED, "shape type SDF is built for the tricubic RIF mode");
         MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, false, true>), trace_grid(k_trace<MER_RIF_TRICUBIC, false, true>, n), 128, 0, (cudaStream_t) stream, m->dev, n,
-                   p_dev, v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev);
+                   p_dev, v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev, (unsigned long long *) block_fetches_dev);
     } else if (m->rif->mode == MER_RIF_TRICUBIC)
         MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, false>), trace_grid(k_trace<MER_RIF_TRICUBIC, false>, n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev, v_dev,
-                   dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev);
+                   dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev, (unsigned long long *) block_fetches_dev);
     else
         MER_LAUNCH((k_trace<MER_RIF_TRILINEAR_PACKED, false>), trace_grid(k_trace<MER_RIF_TRILINEAR_PACKED, false>, n), 128, 0, (cudaStream_t) stream, m->dev, n, p_dev,
-                   v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev);
+                   v_dev, dist_dev, success_dev, dist_surf_dev, opl_dev, nsteps_dev, (unsigned long long *) block_fetches_dev);
     return MER_OK;
 }
 
@@ -489,13 +502,13 @@ int mer_medium_trace_till_boundary_batch(const mer_medium *m, size_t n, float *p
         MER_REQUIRE(m->dev.hasSdf, "shape type SDF needs the sdf volume (mer_medium_set_sdf)");
         if (m->rif->mode != MER_RIF_TRICUBIC) return mer::fail(MER_ERR_UNSUPPORTED, "shape type SDF is built for the tricubic RIF mode");
         MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, true, true>), trace_grid(k_trace<MER_RIF_TRICUBIC, true, true>, n), 128, 0, 0, m->dev, n, dp.as<float>(),
-                   dv.as<float>(), (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
+                   dv.as<float>(), (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>(), (unsigned long long *) nullptr);
     } else if (m->rif->mode == MER_RIF_TRICUBIC)
         MER_LAUNCH((k_trace<MER_RIF_TRICUBIC, true>), trace_grid(k_trace<MER_RIF_TRICUBIC, true>, n), 128, 0, 0, m->dev, n, dp.as<float>(), dv.as<float>(),
-                   (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
+                   (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>(), (unsigned long long *) nullptr);
     else
         MER_LAUNCH((k_trace<MER_RIF_TRILINEAR_PACKED, true>), trace_grid(k_trace<MER_RIF_TRILINEAR_PACKED, true>, n), 128, 0, 0, m->dev, n, dp.as<float>(), dv.as<float>(),
-                   (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>());
+                   (const float *) nullptr, (uint8_t *) nullptr, dds.as<float>(), dopl.as<float>(), dns.as<int32_t>(), (unsigned long long *) nullptr);
     MER_CUDA(cudaDeviceSynchronize());
     DOWN(p, dp, n * 12); DOWN(v, dv, n * 12); DOWN(dist_surf_out, dds, n * 4); DOWN(opl_out, dopl, n * 4);
     DOWN(nsteps_out, dns, n * 4);

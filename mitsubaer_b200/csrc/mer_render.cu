@@ -72,8 +72,7 @@ enum {
     FLAG_SLOW = 64     /* K_FULL whose 4x4x4 stencil touches the edge of the grid: stepped by the event code (clamped taps) */
 };
 
-enum { ST_SAMPLES = 0, ST_STEPS, ST_SCATTER, ST_NULL, ST_EXIT, ST_NONFINITE, ST_CONN, ST_CONNFAIL, ST_CONNSTEPS, ST_COUNT };
-#define ST_STEPS2 ST_STEPS /* the event code's steps go through the CTA's shared counter */
+enum { ST_SAMPLES = 0, ST_STEPS, ST_SCATTER, ST_NULL, ST_EXIT, ST_NONFINITE, ST_CONN, ST_CONNFAIL, ST_CONNSTEPS, ST_FETCH, ST_COUNT };
 
 #define MER_NEE_SALT 0x5851F42D4C957F2DULL /* direct connections draw from their own Philox key */
 
@@ -420,6 +419,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, Ev
         lane_kick(L, hc);
         const bool inside = SDFSHAPE ? inside_shape_lazy(M, L.p, fabsf(hc), L.safe) : inside_shape(M, L.p);
         if (kind != K_ENTRY) ST_INC(st, ST_STEPS);
+        ST_INC(st, ST_FETCH);
         if (kind == K_FULL) {
             if (inside) {
                 L.distSurf += M.h;
@@ -840,7 +840,7 @@ k_step(const __grid_constant__ RenderParams P) {
     S.invalidate();
     const float h = M.h;
     bool exhausted = false; /* warp-uniform: the round's slots are all handed out */
-    unsigned nSteps = 0;
+    unsigned nSteps = 0, nFetch = 0;
     while (true) {
         /* Explicit reconvergence (NVVM folds __syncwarp() into the following vote, so the barrier is spelled in PTX; and
          * no other warp barrier may appear in this kernel, or ptxas drops the converged-warp assumption and every vote
@@ -876,7 +876,10 @@ k_step(const __grid_constant__ RenderParams P) {
             if (!(L.flags & FLAG_DRIFTED)) lane_drift<EXTRAS>(L, h);
             c = rif_cell<MODE, XFORM>(M.rif, L.p);
             if (rif_cell_fast<MODE>(M.rif, c)) {
-                if (!stencil_has(S, c)) rif_fetch_interior<LAYOUT>(M.rif, S, c.i, c.j, c.k);
+                if (!stencil_has(S, c)) {
+                    rif_fetch_interior<LAYOUT>(M.rif, S, c.i, c.j, c.k);
+                    nFetch++;
+                }
                 step = true;
             } else { /* the stencil touches the edge of the grid: a step for the event kernel */
                 L.flags |= FLAG_SLOW;
@@ -903,8 +906,10 @@ k_step(const __grid_constant__ RenderParams P) {
             }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) nSteps += __shfl_down_sync(0xffffffffu, nSteps, o);
+    nSteps = __reduce_add_sync(0xffffffffu, nSteps);
+    nFetch = __reduce_add_sync(0xffffffffu, nFetch);
     if (lane == 0 && nSteps) atomicAdd(P.stats + ST_STEPS, (unsigned long long) nSteps);
+    if (lane == 0 && nFetch) atomicAdd(P.stats + ST_FETCH, (unsigned long long) nFetch);
 }
 
 /* A warp of k_nee costs what its longest connection costs, and the cost is roughly the number of steps from the vertex to
@@ -1253,6 +1258,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         if (e == cudaSuccess) e = cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaEventCreate(&S.ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&S.ev1);
+        if (e == cudaSuccess) e = cudaEventCreate(&S.evTail);
+        for (int i = 0; i < 2 * RenderScratch::RING && e == cudaSuccess; i++) e = cudaEventCreate(&S.ring[i]);
         if (e != cudaSuccess) { /* all or nothing: a later call must not find half of the scratch */
             S.release();
             return mer::fail(e == cudaErrorMemoryAllocation ? MER_ERR_OOM : MER_ERR_CUDA, cudaGetErrorString(e));
@@ -1303,7 +1310,17 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     int syncEvery = 8; /* rounds between two looks at the live-slot counter (a host synchronisation) */
     if (const char *e = getenv("MER_SYNC_EVERY")) syncEvery = std::max(atoi(e), 1);
 
-    unsigned long long rounds = 0, launches = 0;
+    unsigned long long rounds = 0, launches = 0, stepLaunches = 0;
+    double stepMs = 0.0;
+    bool tailMarked = false;
+    int ringUsed = 0; /* event pairs around the step kernel's launches since the last synchronisation */
+    auto drain_ring = [&]() {
+        for (int i = 0; i < ringUsed; i++) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, S.ring[2 * i], S.ring[2 * i + 1]) == cudaSuccess) stepMs += ms;
+        }
+        ringUsed = 0;
+    };
     MER_CUDA(cudaEventRecord(S.ev0, stream));
     MER_LAUNCH(k_pool_init, std::min(eventBlocks, 148u * 8u), 256, 0, stream, P.pool, pool);
     launches++;
@@ -1355,6 +1372,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
             if (*(unsigned *) S.hostPinned == 0u) break;
         }
         /* ---- steps: every slot whose path can */
+        if (ringUsed == RenderScratch::RING) { MER_CUDA(cudaStreamSynchronize(stream)); drain_ring(); }
+        MER_CUDA(cudaEventRecord(S.ring[2 * ringUsed], stream));
 #define MER_STEP(MODE_, L_, T_, S_)                                                                                      \
     do {                                                                                                                 \
         if (xform) MER_LAUNCH((k_step<MODE_, L_, T_, S_, true>), stepBlocks, TPB, 0, stream, P);                         \
@@ -1370,10 +1389,18 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         else MER_STEP2(0);
 #undef MER_STEP2
 #undef MER_STEP
+        MER_CUDA(cudaEventRecord(S.ring[2 * ringUsed + 1], stream));
+        ringUsed++;
         launches++;
+        stepLaunches++;
         if (look && !P.nee) {
             MER_CUDA(cudaStreamSynchronize(stream));
+            drain_ring();
             if (*(unsigned *) S.hostPinned == 0u) break;
+            if (!tailMarked && *(unsigned *) S.hostPinned < pool / 2u) {
+                MER_CUDA(cudaEventRecord(S.evTail, stream));
+                tailMarked = true;
+            }
         }
     }
     const unsigned long long passes = rounds;
@@ -1400,6 +1427,11 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         stats_out->connection_steps = hs[1 + ST_CONNSTEPS];
         stats_out->passes = passes;
         stats_out->kernel_launches = launches;
+        drain_ring();
+        stats_out->step_kernel_ms = (float) stepMs;
+        stats_out->step_launches = stepLaunches;
+        if (tailMarked) cudaEventElapsedTime(&stats_out->tail_ms, S.evTail, S.ev1);
+        stats_out->block_fetches = hs[1 + ST_FETCH];
         float ms = 0;
         cudaEventElapsedTime(&ms, S.ev0, S.ev1);
         stats_out->device_ms = ms;

@@ -60,7 +60,8 @@ class RenderStats(C.Structure):
                 ("null_collisions", C.c_uint64), ("boundary_exits", C.c_uint64),
                 ("nonfinite_dropped", C.c_uint64), ("passes", C.c_uint64), ("connections", C.c_uint64),
                 ("connections_failed", C.c_uint64), ("connection_steps", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("device_ms", C.c_float)]
+                ("device_ms", C.c_float), ("step_kernel_ms", C.c_float), ("step_launches", C.c_uint64), ("tail_ms", C.c_float),
+                ("block_fetches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -72,7 +72,7 @@ def test_struct_layouts_match_the_header(tmp_path):
 
 
 def test_version_and_error_plumbing():
-    assert _abi.lib.mer_abi_version() == 9
+    assert _abi.lib.mer_abi_version() == 10
     assert isinstance(mer.kernel_launch_count(), int)
     with pytest.raises(mer.MerError, match=r"interval \(-1, 1\)"):
         mer.HGPhaseFunction(g=-1.5)

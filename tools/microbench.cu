@@ -68,6 +68,42 @@ __global__ void __launch_bounds__(256) k_read(const uint4 *__restrict__ buf, siz
     if (acc == 0x12345678u) *sink = acc;
 }
 
+/* (4) incoherent 4x4x4-stencil-style gathers, every lane at its own random cell: 16 tld4 from a 2-D array (the atlas layout
+ * of the stepper) and 8 ld.global.nc.v8.f32 sectors from a linear table (the coeff8 layout).  Window 64 MiB (L2-resident). */
+__global__ void __launch_bounds__(128) k_tld4(cudaTextureObject_t tex, int dim, int iters, float *sink) {
+    unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (int it = 0; it < iters; it++) {
+        s = s * 1664525u + 1013904223u;
+        const float u = (float) ((s >> 8) % (unsigned) (dim - 8) + 2), v = (float) ((s >> 3) % (unsigned) (dim - 40) + 2);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float vk = v + 8.0f * (float) k;
+            const float4 a = tex2Dgather<float4>(tex, u, vk, 0), b = tex2Dgather<float4>(tex, u + 2.f, vk, 0);
+            const float4 c = tex2Dgather<float4>(tex, u, vk + 2.f, 0), d = tex2Dgather<float4>(tex, u + 2.f, vk + 2.f, 0);
+            acc += a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w + c.x + c.y + c.z + c.w + d.x + d.y + d.z + d.w;
+        }
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+__global__ void __launch_bounds__(128) k_ldg256(const float4 *__restrict__ tab, size_t nsec, int iters, float *sink) {
+    unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (int it = 0; it < iters; it++) {
+        s = s * 1664525u + 1013904223u;
+        const size_t base = (size_t) (s % (unsigned) (nsec - 8 * 4096));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float4 a, b;
+            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                         : "l"(tab + 2 * (base + (size_t) k * 4096)));
+            acc += a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+        }
+    }
+    if (acc == 123.456f) *sink = acc;
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; CK(cudaEventElapsedTime(&ms, a, b)); return ms; }
 
 int main() {
@@ -126,7 +162,47 @@ int main() {
     };
     const double l2_16 = read_bw((size_t) 16 << 20, 400), l2_32 = read_bw((size_t) 32 << 20, 200), l2_64 = read_bw((size_t) 64 << 20, 100);
     const double hbm = read_bw((size_t) 8 << 30, 2);
-    printf("{\"device\": \"%s\", \"sms\": %d, \"sm_clock_mhz_max\": %d, \"fp32_fma_tflops\": %.2f, \"fp32_fma_f32x2_tflops\": %.2f, "
+    /* (4) gathers: GB/s of coefficients returned to registers */
+    double tld4_gbs = 0, ldg256_gbs = 0;
+    {
+        const int dim = 4096, it4 = 2048, g = sms * 16;
+        cudaArray_t arr;
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
+        CK(cudaMallocArray(&arr, &cd, dim, dim, cudaArrayTextureGather));
+        float *tmp;
+        CK(cudaMalloc(&tmp, (size_t) dim * dim * 4));
+        CK(cudaMemset(tmp, 0, (size_t) dim * dim * 4));
+        CK(cudaMemcpy2DToArray(arr, 0, 0, tmp, (size_t) dim * 4, (size_t) dim * 4, dim, cudaMemcpyDeviceToDevice));
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        cudaTextureObject_t tex;
+        CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        k_tld4<<<g, 128>>>(tex, dim, 64, out);
+        for (int r = 0; r < 5; r++) {
+            CK(cudaEventRecord(e0));
+            k_tld4<<<g, 128>>>(tex, dim, it4, out);
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            const double gbs = 256.0 * it4 * (double) g * 128 / (time_ms(e0, e1) * 1e-3) / 1e9;
+            if (gbs > tld4_gbs) tld4_gbs = gbs;
+        }
+        const size_t nsec = ((size_t) 64 << 20) / 32;
+        k_ldg256<<<g, 128>>>((const float4 *) tmp, nsec, 64, out);
+        for (int r = 0; r < 5; r++) {
+            CK(cudaEventRecord(e0));
+            k_ldg256<<<g, 128>>>((const float4 *) tmp, nsec, it4, out);
+            CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+            const double gbs = 256.0 * it4 * (double) g * 128 / (time_ms(e0, e1) * 1e-3) / 1e9;
+            if (gbs > ldg256_gbs) ldg256_gbs = gbs;
+        }
+        CK(cudaDestroyTextureObject(tex)); CK(cudaFreeArray(arr)); CK(cudaFree(tmp));
+    }
+    printf("{\"gather_tld4_gbs\": %.1f, \"gather_ldg256_gbs\": %.1f, ", tld4_gbs, ldg256_gbs);
+    printf("\"device\": \"%s\", \"sms\": %d, \"sm_clock_mhz_max\": %d, \"fp32_fma_tflops\": %.2f, \"fp32_fma_f32x2_tflops\": %.2f, "
            "\"l2_read_gbs\": {\"16MiB\": %.1f, \"32MiB\": %.1f, \"64MiB\": %.1f}, \"hbm_read_gbs_8GiB\": %.1f, "
            "\"note\": \"best of 5 launches each, CUDA events; FMA: 16 independent chains/thread, 8 CTAs x 256 threads per SM; reads: ld.global.cg 128-bit, every CTA sweeps the whole window\"}\n",
            prop.name, sms, prop.clockRate / 1000, best_fma, best_fma2, l2_16, l2_32, l2_64, hbm);
