@@ -33,6 +33,8 @@ namespace merhost {
 /* --dry-run: parse, instantiate and resolve everything but create no device handles (lets the XML layer be
  * tested on a machine without a GPU; the library itself has no CPU path) */
 inline bool &dryRun() { static bool v = false; return v; }
+/* the GPU a volume without a `device` property is created on: `mer_render --gpus N` loads the scene once per GPU */
+inline int &defaultDevice() { static int v = 0; return v; }
 
 [[noreturn]] inline void logError(const std::string &msg) { throw std::runtime_error(msg); } /* Log(EError, ...) */
 inline void merCheck(int rc) { if (rc != MER_OK) logError(std::string("mitsubaer_b200: ") + mer_last_error()); }
@@ -185,7 +187,7 @@ struct SplineDataSource : Object { /* <volume type="splinevolume"> */
         std::string fetch = props.getString("fetch", "tricubic");
         int mode = fetch == "tricubic" ? MER_RIF_TRICUBIC : fetch == "trilinear_packed" ? MER_RIF_TRILINEAR_PACKED : -1;
         if (mode < 0) logError("splinevolume: unknown fetch mode \"" + fetch + "\"");
-        const int device = (int) props.getInteger("device", 0);
+        const int device = (int) props.getInteger("device", defaultDevice());
         const std::string file = props.getString("filename");
         if (dryRun()) { int32_t enc, ch; merCheck(mer_vol_read_header(file.c_str(), &desc, &enc, &ch)); return; }
         merCheck(mer_rif_create_from_file(device, file.c_str(), &ov, mode, &handle));
@@ -201,7 +203,7 @@ struct GridDataSource : Object { /* <volume type="gridvolume"> */
         mer_volume_desc ov;
         fillVolumeDesc(ov, props);
         props.getBoolean("sendData", false);
-        const int device = (int) props.getInteger("device", 0);
+        const int device = (int) props.getInteger("device", defaultDevice());
         const std::string file = props.getString("filename");
         if (dryRun()) { mer_volume_desc d; int32_t enc, ch; merCheck(mer_vol_read_header(file.c_str(), &d, &enc, &ch)); return; }
         merCheck(mer_grid_create_from_file(device, file.c_str(), &ov, &handle));
@@ -293,6 +295,7 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         if (props.has("material")) logError("material presets are not carried by this path; give sigmaS/sigmaA or sigmaT/albedo");
         Spectrum3 albedo = props.getSpectrum("albedo", 0.0f);
         if (props.has("sigmaT")) { /* medium/materials.h:112-120 */
+            if (!props.has("albedo")) logError("Medium: sigmaT needs albedo (materials.h:112-120)");
             Spectrum3 st = props.getSpectrum("sigmaT", 0.0f);
             for (int i = 0; i < 3; i++) { desc.sigma_s[i] = (float) (st.c[i] * scale * albedo.c[i]); desc.sigma_a[i] = (float) (st.c[i] * scale * (1 - albedo.c[i])); }
         } else {
@@ -311,7 +314,8 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         const std::string scaling = props.getString("radianceScaling", "reference");
         if (scaling != "reference" && scaling != "physical") logError("radianceScaling must be \"reference\" or \"physical\"");
         desc.radiance_scaling = scaling == "physical" ? MER_SCALING_PHYSICAL : MER_SCALING_REFERENCE;
-        props.getBoolean("monochromatic", false);
+        if (props.getBoolean("monochromatic", false)) /* librender/medium.cpp: collapses sigmaA / sigmaS to their average */
+            logError("monochromatic=true is not carried by this path (give the same value for the three channels)");
         /* solver parameters of the direct connections (heterogeneousrefractive.cpp:208-219), used when the integrator asks for them */
         connection.tol2 = (float) props.getFloat("tol2", 1e-6);
         connection.rrweight = (float) props.getFloat("rrweight", 1e-2);
@@ -320,7 +324,12 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         connection.start_mode = MER_START_DEFAULT;
         /* accepted for XML compatibility: Ceres-specific tolerances have no counterpart in the Levenberg-Marquardt solver */
         for (const char *n : {"ceresfunctiontolerance", "ceresgradienttolerance", "ceresparametertolerance"}) props.getFloat(n, 0);
-        for (const char *n : {"cerescheckgradients", "makesensordirectconnections", "aggressivetracing"}) props.getBoolean(n, false);
+        props.getBoolean("cerescheckgradients", false);
+        /* these two change what the reference computes (:230, :476-493; edge.cpp:535-567): refuse rather than render differently */
+        if (props.getBoolean("aggressivetracing", false))
+            logError("aggressivetracing=true: the renderer steps without it (it is available in mer_medium_sample_distance_batch only)");
+        if (props.getBoolean("makesensordirectconnections", false))
+            logError("makesensordirectconnections=true belongs to the reference's bidirectional integrator; use the integrator's lightTracing here");
         if (!rif) logError("No RIF specified!");
     }
     void attach(const Shape &shape) {

@@ -1,5 +1,5 @@
 /*
- * host/mer_render_main.cpp — `mer_render scene.xml [-D name=value]... [-o out.pfm] [--film out.bin] [--dry-run]`
+ * host/mer_render_main.cpp — `mer_render scene.xml [-D name=value]... [-o out.pfm] [--film out.bin] [--gpus N] [--dry-run]`
  *
  * The stand-in for `mitsuba scene.xml -D k=v` (src/mitsuba/mitsuba.cpp:154-400) on this path: loads a Mitsuba
  * scene XML through host/scene_xml.cpp, renders it with libmitsubaer_b200.so (mer_render) and writes the developed
@@ -36,6 +36,7 @@ static void printDesc(const Scene &S) {
 
 int main(int argc, char **argv) {
     std::string scenePath, out = "out.pfm", filmOut;
+    int gpus = 1; /* --gpus N: the scene is loaded once per GPU and mer_render_multi drives them all (0 = every GPU of the box) */
     std::map<std::string, std::string> params;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -46,8 +47,9 @@ int main(int argc, char **argv) {
             params[a.substr(2, eq - 2)] = a.substr(eq + 1);
         } else if (a == "-o" && i + 1 < argc) out = argv[++i];
         else if (a == "--film" && i + 1 < argc) filmOut = argv[++i];
+        else if (a == "--gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
         else if (a == "--dry-run") dryRun() = true;
-        else if (a[0] == '-') { std::fprintf(stderr, "usage: mer_render scene.xml [-D name=value]... [-o out.pfm] [--film out.bin] [--dry-run]\n"); return 2; }
+        else if (a[0] == '-') { std::fprintf(stderr, "usage: mer_render scene.xml [-D name=value]... [-o out.pfm] [--film out.bin] [--gpus N] [--dry-run]\n"); return 2; }
         else scenePath = a;
     }
     if (scenePath.empty()) { std::fprintf(stderr, "mer_render: no scene file given\n"); return 2; }
@@ -59,7 +61,21 @@ int main(int argc, char **argv) {
         const size_t npx = (size_t) r.width * r.height;
         std::vector<float> film(npx * (3 * (size_t) frames + 2)), rgb(npx * 3 * (size_t) frames);
         mer_render_stats st;
-        merCheck(mer_render(S.medium->handle, &r, film.data(), &st));
+        if (gpus == 0) gpus = mer_device_count();
+        if (gpus <= 1) {
+            merCheck(mer_render(S.medium->handle, &r, film.data(), &st));
+        } else { /* the reference's `mitsuba -p N` worker threads (mitsuba.cpp:278-283) become one replica of the scene per GPU */
+            if (gpus > mer_device_count()) logError("--gpus " + std::to_string(gpus) + ": the box has " + std::to_string(mer_device_count()) + " usable GPU(s)");
+            std::vector<Scene> replicas;
+            std::vector<const mer_medium *> media{S.medium->handle};
+            for (int g = 1; g < gpus; g++) {
+                defaultDevice() = g;
+                replicas.push_back(loadScene(scenePath, params));
+                media.push_back(replicas.back().medium->handle);
+            }
+            defaultDevice() = 0;
+            merCheck(mer_render_multi(media.data(), gpus, &r, film.data(), &st));
+        }
         merCheck(mer_film_develop_frames(0, r.width, r.height, frames, film.data(), rgb.data()));
         if (frames == 1) {
             writePFM(out, r.width, r.height, rgb.data());

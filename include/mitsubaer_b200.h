@@ -383,6 +383,15 @@ int mer_render(const mer_medium *medium, const mer_render_desc *desc, float *fil
 /* film_dev is ACCUMULATED into (zero it first); asynchronous except for the pass-count readbacks */
 int mer_render_device(const mer_medium *medium, const mer_render_desc *desc, float *film_dev,
                       mer_render_stats *stats_out, void *stream);
+/* The same render on ALL the GPUs of the box in one call: the replacement of the scheduler behind Integrator::render
+ * (src/librender/integrator.cpp:95-127: BlockedRenderProcess + sched->schedule/wait; src/librender/renderproc.cpp:142-148:
+ * worker results added into the film).  media[g] is the scene's medium created on GPU g (grids replicated per GPU);
+ * GPU g renders the sample indices s = begin + (g + k * ngpus) * stride of every pixel, one host thread per GPU, and the
+ * per-GPU films are added on media[0]'s GPU with one ncclReduce over NVLink (libnccl.so.2, loaded at run time; peer copies
+ * + an add kernel when it is missing or when two handles share a device), then copied to film_host.
+ * stats: counters summed over the GPUs, times = the slowest GPU's. */
+int mer_render_multi(const mer_medium *const *media, int32_t ngpus, const mer_render_desc *desc, float *film_host,
+                     mer_render_stats *stats_out);
 /* HDRFilm::develop (src/films/hdrfilm.cpp:527-540): rgb = sum(w*RGB)/sum(w); host buffers */
 int mer_film_develop(int device, int32_t width, int32_t height, const float *film, float *rgb_out);
 /* the same for a transient film of `frames` frames: film [H][W][3*frames+2] -> rgb_out [H][W][frames][3] */

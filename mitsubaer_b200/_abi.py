@@ -137,6 +137,7 @@ SIGNATURES = {
     "mer_film_develop_frames": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, _fp, _fp]),
     "mer_last_error": (C.c_char_p, []),
     "mer_abi_version": (C.c_int, []),
+    "mer_render_multi": (C.c_int, [_vp, C.c_int32, _vp, _vp, _vp]),
     "mer_device_count": (C.c_int, []),
     "mer_kernel_launch_count": (C.c_uint64, []),
     "mer_trim_memory": (C.c_int, [C.c_int]),

@@ -301,6 +301,12 @@ class HeterogeneousRefractiveMedium:
             raise _abi.MerError(_abi.MER_ERR_INVALID, "No RIF specified!")
         d = _abi.MediumDesc()
         scale = float(p.get("scale", 1.0))
+        if "sigmaT" in p and "albedo" not in p:
+            raise _abi.MerError(_abi.MER_ERR_INVALID, "Medium: sigmaT needs albedo (src/medium/materials.h:112-120)")
+        for name, why in (("monochromatic", "give the same value for the three channels"),
+                          ("makesensordirectconnections", "use the integrator's lightTracing")):
+            if bool(p.get(name, False)):  # these change what the reference computes: refuse rather than render differently
+                raise _abi.MerError(_abi.MER_ERR_UNSUPPORTED, "%s=true is not carried by this path (%s)" % (name, why))
         if "sigmaT" in p and "albedo" in p:
             st, al = _spectrum(p["sigmaT"]) * scale, _spectrum(p["albedo"])
             ss, sa = st * al, st * (1 - al)
@@ -549,6 +555,16 @@ class EikonalVolPathIntegrator:
         film = np.zeros((r.height, r.width, 3 * (max(int(r.frames), 1) if not r.modulation else 1) + 2), np.float32)
         stats = _abi.RenderStats()
         check(lib.mer_render(medium.handle, C.byref(r), _fp(film), C.byref(stats)))
+        return film, stats.as_dict()
+
+    def render_multi(self, scene, media, sample_begin=0, sample_stride=1):
+        """the same frame on several GPUs in one call (mer_render_multi): media = the scene's medium created on each GPU
+        (grids replicated); sample indices are interleaved over the GPUs and the films reduced onto the first one"""
+        r = self.render_desc(scene, sample_begin, sample_stride, media[0])
+        film = np.zeros((r.height, r.width, 3 * (max(int(r.frames), 1) if not r.modulation else 1) + 2), np.float32)
+        stats = _abi.RenderStats()
+        handles = (C.c_void_p * len(media))(*[m.handle for m in media])
+        check(lib.mer_render_multi(handles, len(media), C.byref(r), _fp(film), C.byref(stats)))
         return film, stats.as_dict()
 
     def render_device(self, scene, medium, film_ptr, stream=None, sample_begin=0, sample_stride=1):

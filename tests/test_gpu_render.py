@@ -128,6 +128,42 @@ def test_sample_sharding_adds_up(oracle32):
     assert st2["ray_steps"] == st["ray_steps"] and np.allclose(other, full, rtol=1e-5, atol=1e-5)
 
 
+def test_render_multi_two_shards_on_one_device(oracle32):
+    """mer_render_multi (the scheduler behind Integrator::render, integrator.cpp:95-127 / renderproc.cpp:142-148): two
+    shards of the sample indices rendered by two host threads and reduced — here both on the one GPU a test box has,
+    which takes the peer-copy + add path of the reduce — give the single-call film"""
+    med, omed, keep = setup(oracle32, "radial", 32, medium_props(stepsize=2e-2))
+    scene = scene_dict(32, 24, 8, rfilter="gaussian")
+    integ = mer.EikonalVolPathIntegrator(stepsPerPass=128, poolPaths=1024)
+    full, st = integ.render(scene, med)
+    both, st2 = integ.render_multi(scene, [med, med])
+    assert st2["samples"] == st["samples"] and st2["ray_steps"] == st["ray_steps"]
+    assert np.allclose(both, full, rtol=1e-5, atol=1e-5)
+    one, st1 = integ.render_multi(scene, [med])
+    assert st1["ray_steps"] == st["ray_steps"] and np.allclose(one, full, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.skipif(mer.device_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("nccl", ["1", "0"])
+def test_render_multi_two_gpus(oracle32, nccl, monkeypatch):
+    """one call drives two GPUs (grids replicated, sample indices interleaved, ncclReduce of the film — or, with
+    MER_NCCL=0, peer copies) and the film matches the one-GPU film to 1e-5"""
+    monkeypatch.setenv("MER_NCCL", nccl)
+    props = medium_props(stepsize=2e-2)
+    data, lo, hi = make_field("radial", 32)
+    media, keep = [], []
+    for dev in (0, 1):
+        rif = mer.SplineDataSource(data=data, min=lo, max=hi, device=dev)
+        media.append(mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9)).configure())
+        keep.append(rif)
+    scene = scene_dict(40, 32, 16, rfilter="gaussian")
+    integ = mer.EikonalVolPathIntegrator(stepsPerPass=128, poolPaths=2048)
+    full, st = integ.render(scene, media[0])
+    both, st2 = integ.render_multi(scene, media)
+    assert st2["samples"] == st["samples"] and st2["ray_steps"] == st["ray_steps"]
+    assert np.allclose(both, full, rtol=1e-5, atol=1e-5)
+
+
 def test_packed_mode_renders_close_to_tricubic(oracle32):
     props = medium_props(stepsize=1e-2)
     med_c, _, k1 = setup(oracle32, "radial", 64, props, mode="tricubic")
