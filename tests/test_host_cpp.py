@@ -189,3 +189,14 @@ def test_cw_tof_film_resolves(volumes, tmp_path):
     assert s["modulation"] == 1 and s["lambda"] == 3.5 and s["phase"] == 90
     out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "-D", "mod=mseq", "--dry-run"])
     assert out.returncode == 1 and "modulation" in out.stderr
+
+@pytest.mark.parametrize("tag", ["SPLINEVOLUME", "GRIDVOLUME", "HG", "HETEROGENEOUSREFRACTIVE", "ERVOLPATH"])
+def test_mitsuba_binding_compiles_against_the_header_stub(tag):
+    """integration/mitsuba_plugins.cpp (the file a MitsubaER maintainer builds once per plugin tag) is syntax-checked
+    against integration/mitsuba_stub — declarations of exactly the Mitsuba members it uses — and against the real
+    include/mitsubaer_b200.h: a change of the C ABI that the binding does not follow fails here"""
+    import subprocess
+    r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-Wno-unused-function", "-DMER_PLUGIN_" + tag,
+                        "-I" + os.path.join(ROOT, "integration", "mitsuba_stub"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "integration", "mitsuba_plugins.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0 and "warning" not in r.stderr, r.stderr[-2000:]
