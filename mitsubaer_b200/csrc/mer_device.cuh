@@ -73,6 +73,9 @@ struct MediumDev {
     float g;
     float densityScale, invMaxDensity;
     float albedo[3];
+    /* strategy "maximum": MaxExpDist (src/medium/maxexp.h:29-58) built on the host by mer_medium_create — sigma_t sorted
+     * in decreasing order, the discrete cdf of the pieces, where each piece starts, its lower integration bound */
+    float mxSigma[3], mxCdf[4], mxStart[3], mxLower[3], mxNorm, mxInvNorm;
 };
 
 /* ------------------------------------------------------------------ small vector helpers */
@@ -753,6 +756,31 @@ static __device__ __noinline__ float3 hg_sample_dev(float g, float3 wi, float u1
 /* fastlog / fastexp: double precision rounded to float on Linux x86-64, math.h:185-199 */
 static __device__ __noinline__ float fastlog_dev(float x) { return (float) log((double) x); }
 static __device__ __noinline__ float fastexp_dev(float x) { return (float) exp((double) x); }
+
+/* ------------------------------------------------------------------ MaxExpDist, src/medium/maxexp.h:60-102
+ * (std::lower_bound over three / four entries written out; every operation rounded like the reference's float build) */
+__device__ __forceinline__ int maxexp_piece_of_t(const MediumDev &M, float t) { /* lower_bound(intervalStart, t) - 1, >= 0 */
+    const int lb = (M.mxStart[0] >= t) ? 0 : ((M.mxStart[1] >= t) ? 1 : ((M.mxStart[2] >= t) ? 2 : 3));
+    return max(0, lb - 1);
+}
+static __device__ __noinline__ float maxexp_sample(const MediumDev &M, float u, float &pdf) {
+    const int lb = (M.mxCdf[0] >= u) ? 0 : ((M.mxCdf[1] >= u) ? 1 : ((M.mxCdf[2] >= u) ? 2 : ((M.mxCdf[3] >= u) ? 3 : 4)));
+    const int index = min(max(0, lb - 1), 2);
+    const float s = M.mxSigma[index];
+    const float a = fastexp_dev(__fmul_rn(-M.mxStart[index], s));
+    const float t = __fdiv_rn(-fastlog_dev(__fsub_rn(a, __fmul_rn(M.mxNorm, __fsub_rn(u, M.mxCdf[index])))), s);
+    pdf = __fmul_rn(__fmul_rn(s, fastexp_dev(__fmul_rn(-s, t))), M.mxInvNorm);
+    return t;
+}
+static __device__ __noinline__ float maxexp_pdf(const MediumDev &M, float t) {
+    const float s = M.mxSigma[maxexp_piece_of_t(M, t)];
+    return __fmul_rn(__fmul_rn(s, fastexp_dev(__fmul_rn(-s, t))), M.mxInvNorm);
+}
+static __device__ __noinline__ float maxexp_cdf(const MediumDev &M, float t) {
+    const int index = maxexp_piece_of_t(M, t);
+    const float upper = -fastexp_dev(__fmul_rn(-M.mxSigma[index], t));
+    return __fadd_rn(M.mxCdf[index], __fmul_rn(__fsub_rn(upper, M.mxLower[index]), M.mxInvNorm));
+}
 
 /* ------------------------------------------------------------------ Philox4x32-10
  * key = seed, counter = (sample id lo, hi, block, 0); float = (u >> 8) * 2^-24.  The k-th

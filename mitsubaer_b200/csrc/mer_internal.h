@@ -119,6 +119,19 @@ struct DeviceGuard {
 int check_device(int device); /* MER_OK or MER_ERR_CUDA (no usable sm_100-class GPU) */
 RenderScratch &device_scratch(int device);
 
+/* RAII device buffer of the *_batch (host pointer) entry points: from the private stream-ordered pool, so that an entry
+ * point that is called once per ray (the scalar virtuals of the Mitsuba binding) does not pay cudaMalloc / cudaFree, and
+ * an early return on an error cannot leak the buffers allocated before it */
+struct DevBuf {
+    void *ptr = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { pool_free(ptr); }
+    cudaError_t alloc(size_t bytes) { return pool_malloc(&ptr, bytes ? bytes : 1); }
+    template <typename T> T *as() { return (T *) ptr; }
+};
+
 } /* namespace mer */
 
 #define MER_CUDA(expr)                                                                                  \

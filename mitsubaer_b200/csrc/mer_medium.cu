@@ -9,7 +9,9 @@
  *   Medium base                     src/librender/medium.cpp:27-37
  *   HGPhaseFunction                 src/phase/hg.cpp:76-110
  */
+#include <algorithm>
 #include <cmath>
+#include <functional>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -183,11 +185,15 @@ k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float
                   SampleDistanceOut out) {
     for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < nRays; i += (size_t) gridDim.x * blockDim.x) {
         const float mint = mintIn ? mintIn[i] : 0.0f;
-        float rnd = xi[2 * i], sampledDistance, sd = M.samplingDensity;
+        float rnd = xi[2 * i], sampledDistance, sd = M.samplingDensity, pdfSampled = 0.0f;
         if (rnd < M.weight) {
             rnd = __fdiv_rn(rnd, M.weight);
-            if (M.strategy == MER_STRATEGY_BALANCE) sd = M.sigmaT[min((int) (xi[2 * i + 1] * 3.0f), 2)];
-            sampledDistance = __fdiv_rn(-fastlog_dev(1.0f - rnd), sd);
+            if (M.strategy == MER_STRATEGY_MAXIMUM) { /* :445 */
+                sampledDistance = maxexp_sample(M, 1.0f - rnd, pdfSampled);
+            } else {
+                if (M.strategy == MER_STRATEGY_BALANCE) sd = M.sigmaT[min((int) (xi[2 * i + 1] * 3.0f), 2)];
+                sampledDistance = __fdiv_rn(-fastlog_dev(1.0f - rnd), sd);
+            }
         } else {
             sampledDistance = INFINITY;
         }
@@ -239,7 +245,10 @@ k_sample_distance(const __grid_constant__ MediumDev M, size_t nRays, const float
                 t = sampledDistance + mint;
             }
             float pdfFailure = 0.0f, pdfSuccess = 0.0f;
-            if (M.strategy == MER_STRATEGY_BALANCE) {
+            if (M.strategy == MER_STRATEGY_MAXIMUM) { /* :534-536: pdfSuccess is what MaxExpDist::sample returned */
+                pdfFailure = __fsub_rn(1.0f, maxexp_cdf(M, sampledDistance));
+                pdfSuccess = pdfSampled;
+            } else if (M.strategy == MER_STRATEGY_BALANCE) {
                 for (int c = 0; c < 3; c++) {
                     float tmp = fastexp_dev(__fmul_rn(-M.sigmaT[c], sampledDistance));
                     pdfFailure = __fadd_rn(pdfFailure, tmp);
@@ -303,13 +312,7 @@ __global__ void k_hg_eval(float g, size_t n, const float *__restrict__ wi, const
 /* ===================================================================== host side */
 namespace {
 
-/* tiny RAII device buffer for the *_batch (host pointer) entry points */
-struct DevBuf {
-    void *ptr = nullptr;
-    ~DevBuf() { cudaFree(ptr); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&ptr, bytes ? bytes : 1); }
-    template <typename T> T *as() { return (T *) ptr; }
-};
+using mer::DevBuf; /* RAII device buffer for the *_batch (host pointer) entry points */
 
 /* persistent-style sizing: every CTA the kernel can keep resident (occupancy query: 3 per SM for the
  * 168-register tricubic stepper, 6 for the packed one), times two so that the tail of one wave overlaps
@@ -351,9 +354,7 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
     MER_REQUIRE(desc->shape_type == MER_SHAPE_BOX || desc->shape_type == MER_SHAPE_SPHERE || desc->shape_type == MER_SHAPE_SDF, "unknown shape type");
     MER_REQUIRE(desc->boundary == MER_BOUNDARY_INDEX_MATCHED || desc->boundary == MER_BOUNDARY_HDIELECTRIC, "unknown boundary type");
     MER_REQUIRE(desc->radiance_scaling == MER_SCALING_REFERENCE || desc->radiance_scaling == MER_SCALING_PHYSICAL, "unknown radiance scaling");
-    if (desc->strategy == MER_STRATEGY_MAXIMUM)
-        return mer::fail(MER_ERR_UNSUPPORTED, "strategy 'maximum' (MaxExpDist) is not carried by this path");
-    MER_REQUIRE(desc->strategy >= MER_STRATEGY_BALANCE && desc->strategy <= MER_STRATEGY_MANUAL,
+    MER_REQUIRE(desc->strategy >= MER_STRATEGY_BALANCE && desc->strategy <= MER_STRATEGY_MAXIMUM,
                 "Specified an unknown sampling strategy"); /* :296 */
     if (density) MER_REQUIRE(desc->density_scale > 0.0f, "density_scale must be positive when a density grid is attached");
 
@@ -399,6 +400,22 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
         m->desc.channel = channel;
     } else if (desc->strategy == MER_STRATEGY_MANUAL) {
         D.samplingDensity = desc->sampling_density;
+    } else if (desc->strategy == MER_STRATEGY_MAXIMUM) { /* :287-291 + MaxExpDist::MaxExpDist, src/medium/maxexp.h:29-58, in Float */
+        float sg[3] = {D.sigmaT[0], D.sigmaT[1], D.sigmaT[2]};
+        std::sort(sg, sg + 3, std::greater<float>());
+        float cdf[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 3; i++) {
+            if (i > 0 && sg[i] == sg[i - 1]) { delete m; return mer::fail(MER_ERR_INVALID, "Internal error: sigmaT must vary across channels"); }
+            const float lower = i == 0 ? -1.0f : -std::pow(sg[i] / sg[i - 1], -sg[i] / (sg[i] - sg[i - 1]));
+            const float upper = i == 2 ? 0.0f : -std::pow(sg[i + 1] / sg[i], -sg[i] / (sg[i + 1] - sg[i]));
+            cdf[i + 1] = cdf[i] + (upper - lower);
+            D.mxSigma[i] = sg[i];
+            D.mxLower[i] = lower;
+            D.mxStart[i] = i == 0 ? 0.0f : (float) std::log((double) (sg[i] / sg[i - 1])) / (sg[i] - sg[i - 1]);
+        }
+        D.mxNorm = cdf[3];
+        D.mxInvNorm = 1.0f / D.mxNorm;
+        for (int i = 0; i < 4; i++) D.mxCdf[i] = cdf[i] * D.mxInvNorm;
     }
     D.shapeType = desc->shape_type;
     for (int i = 0; i < 6; i++) D.shape[i] = desc->shape[i];

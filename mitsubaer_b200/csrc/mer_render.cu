@@ -360,7 +360,10 @@ template <typename T> __device__ __forceinline__ void lane_kick(T &L, float hc) 
 /* exponential free-flight pdfs + transmittance at geometric length d (:533-562) */
 __device__ __noinline__ void edge_weight(const MediumDev &M, float sd, float d, bool success, float edge[3]) {
     float pdfFailure = 0.0f, pdfSuccess = 0.0f;
-    if (M.strategy == MER_STRATEGY_BALANCE) {
+    if (M.strategy == MER_STRATEGY_MAXIMUM) { /* :534-536; the density MaxExpDist::sample reported for d is MaxExpDist::pdf(d) */
+        pdfFailure = __fsub_rn(1.0f, maxexp_cdf(M, d));
+        pdfSuccess = success ? maxexp_pdf(M, d) : 0.0f;
+    } else if (M.strategy == MER_STRATEGY_BALANCE) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             float tmp = fastexp_dev(__fmul_rn(-M.sigmaT[c], d));
@@ -605,8 +608,13 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, Ev
                 L.sd = M.samplingDensity;
                 if (rnd < M.weight) {
                     rnd = __fdiv_rn(rnd, M.weight);
-                    if (M.strategy == MER_STRATEGY_BALANCE) L.sd = M.sigmaT[min((int) (L.rng.next() * 3.0f), 2)];
-                    dist = __fdiv_rn(-fastlog_dev(1.0f - rnd), L.sd);
+                    if (M.strategy == MER_STRATEGY_MAXIMUM) {
+                        float pdfUnused;
+                        dist = maxexp_sample(M, 1.0f - rnd, pdfUnused);
+                    } else {
+                        if (M.strategy == MER_STRATEGY_BALANCE) L.sd = M.sigmaT[min((int) (L.rng.next() * 3.0f), 2)];
+                        dist = __fdiv_rn(-fastlog_dev(1.0f - rnd), L.sd);
+                    }
                 } else {
                     dist = INFINITY;
                 }

@@ -384,6 +384,9 @@ int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
     return MER_OK;
 }
 
+/* .vol payloads this path reads: EFloat32 and EUInt8 (value / 255), one channel (gridvolume.cpp:251-262, 369-376) */
+static bool vol_encoding_supported(int32_t enc, int32_t ch) { return ch == 1 && (enc == 1 || enc == 3); }
+
 int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *data, int32_t *encoding,
                   int32_t *channels) {
     FILE *f = fopen(path, "rb");
@@ -406,28 +409,45 @@ int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *d
     memcpy(bb, hdr + 24, 24);
     if (encoding) *encoding = enc;
     if (channels) *channels = ch;
+    /* the header is untrusted input: sizes are checked before anything is multiplied or allocated */
+    for (int i = 0; i < 3; i++)
+        if (res[i] < 1 || res[i] > 65536) { fclose(f); return mer::fail(MER_ERR_INVALID, "Encountered an invalid volume data file (resolution out of range)"); }
+    if (ch < 1 || ch > 4) { fclose(f); return mer::fail(MER_ERR_INVALID, "Encountered an invalid volume data file (channel count)"); }
+    {
+        const size_t bytesPer = enc == 1 ? 4 : (enc == 2 ? 2 : (enc == 3 ? 1 : (enc == 4 ? 2 : 0)));
+        fseek(f, 0, SEEK_END);
+        const long long fileBytes = (long long) ftell(f);
+        fseek(f, 48, SEEK_SET);
+        const unsigned long long need = 48ull + (unsigned long long) res[0] * (unsigned long long) res[1] * (unsigned long long) res[2] *
+                                                  (unsigned long long) ch * (unsigned long long) bytesPer;
+        if (bytesPer == 0) { fclose(f); return mer::fail(MER_ERR_INVALID, "Encountered a volume data file of unknown type"); } /* gridvolume.cpp:262 */
+        if ((unsigned long long) fileBytes < need) { fclose(f); return mer::fail(MER_ERR_INVALID, "volume file truncated"); }
+    }
     if (desc) {
         memset(desc, 0, sizeof(*desc));
         for (int i = 0; i < 3; i++) { desc->res[i] = res[i]; desc->bbox_min[i] = bb[i]; desc->bbox_max[i] = bb[3 + i]; }
         desc->world_to_volume[0] = desc->world_to_volume[5] = desc->world_to_volume[10] = 1.f;
     }
     if (data) {
-        if (enc != 1 || ch != 1) {
+        if (!vol_encoding_supported(enc, ch)) {
             fclose(f);
-            return mer::fail(MER_ERR_UNSUPPORTED, "only single-channel float32 .vol files are supported on this path");
+            return mer::fail(MER_ERR_UNSUPPORTED, "single-channel float32 and uint8 .vol files are supported on this path (no float16, no 3-channel albedo / direction grids)");
         }
         size_t total = (size_t) res[0] * res[1] * res[2];
         data->resize(total);
-        if (fread(data->data(), sizeof(float), total, f) != total) {
-            fclose(f);
-            return mer::fail(MER_ERR_INVALID, "volume file truncated");
+        if (enc == 1) {
+            if (fread(data->data(), sizeof(float), total, f) != total) { fclose(f); return mer::fail(MER_ERR_INVALID, "volume file truncated"); }
+        } else { /* EUInt8: m_densityMap[i] = i / 255 (gridvolume.cpp:369-376) */
+            std::vector<unsigned char> bytes(total);
+            if (fread(bytes.data(), 1, total, f) != total) { fclose(f); return mer::fail(MER_ERR_INVALID, "volume file truncated"); }
+            for (size_t i = 0; i < total; i++) (*data)[i] = (float) bytes[i] / 255.0f;
         }
     }
     fclose(f);
     return MER_OK;
 }
 
-/* Streams the payload of a single-channel float32 .vol file into a fresh device array: 64 MiB slabs through two pinned
+/* Streams the payload of a single-channel float32 (or uint8) .vol file into a fresh device float array: 64 MiB slabs through two pinned
  * staging buffers, the disk read of one overlapping the H2D copy of the other.  Peak host memory is 128 MiB whatever the
  * grid (a 1024^3 RIF is 4 GiB on disk); the reference reads the file through a memory map and prefilters on the CPU
  * (splinevolume.cpp:204-317), here the prefilter runs on the device array. */
@@ -436,7 +456,8 @@ int stream_vol_to_device(int device, const char *path, mer_volume_desc *desc, fl
     int32_t enc = 0, ch = 0;
     int rc = read_vol_file(path, desc, nullptr, &enc, &ch);
     if (rc) return rc;
-    if (enc != 1 || ch != 1) return mer::fail(MER_ERR_UNSUPPORTED, "only single-channel float32 .vol files are supported on this path");
+    if (!vol_encoding_supported(enc, ch))
+        return mer::fail(MER_ERR_UNSUPPORTED, "single-channel float32 and uint8 .vol files are supported on this path (no float16, no 3-channel albedo / direction grids)");
     rc = mer::check_device(device);
     if (rc) return rc;
     mer::DeviceGuard guard(device);
@@ -455,12 +476,19 @@ int stream_vol_to_device(int device, const char *path, mer_volume_desc *desc, fl
         if (e == cudaSuccess) e = cudaEventCreate(&done[i]);
     }
     bool truncated = false;
+    std::vector<unsigned char> bytes;
     for (size_t off = 0, k = 0; e == cudaSuccess && off < total; off += slab, k++) {
         const int b = (int) (k & 1);
         const size_t n = std::min(slab, total - off);
         if (k >= 2) e = cudaEventSynchronize(done[b]); /* the copy that last used this buffer */
         if (e != cudaSuccess) break;
-        if (fread(stage[b], sizeof(float), n, f) != n) { truncated = true; break; }
+        if (enc == 1) {
+            if (fread(stage[b], sizeof(float), n, f) != n) { truncated = true; break; }
+        } else { /* EUInt8 -> float on the way through the staging buffer */
+            bytes.resize(n);
+            if (fread(bytes.data(), 1, n, f) != n) { truncated = true; break; }
+            for (size_t i = 0; i < n; i++) stage[b][i] = (float) bytes[i] / 255.0f;
+        }
         e = cudaMemcpyAsync(dev + off, stage[b], n * sizeof(float), cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaEventRecord(done[b], st);
     }
@@ -593,23 +621,16 @@ int mer_rif_eval_batch(const mer_rif *r, int what, size_t n, const float *p, flo
     MER_REQUIRE(r && (n == 0 || p), "null argument");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(r->device);
-    float *dp = nullptr, *df = nullptr, *dg = nullptr;
-    MER_CUDA(cudaMalloc(&dp, n * 3 * sizeof(float)));
-    MER_CUDA(cudaMalloc(&df, n * sizeof(float)));
-    MER_CUDA(cudaMalloc(&dg, n * 3 * sizeof(float)));
-    int rc = MER_OK;
-    cudaError_t e = cudaMemcpy(dp, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        rc = mer_rif_eval_device(r, what, n, dp, df, dg, nullptr);
-        if (rc == MER_OK) e = cudaDeviceSynchronize();
-        if (rc == MER_OK && e == cudaSuccess && what != MER_EVAL_GRADIENT && value_out)
-            e = cudaMemcpy(value_out, df, n * sizeof(float), cudaMemcpyDeviceToHost);
-        if (rc == MER_OK && e == cudaSuccess && what != MER_EVAL_VALUE && grad_out)
-            e = cudaMemcpy(grad_out, dg, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
-    }
-    cudaFree(dp); cudaFree(df); cudaFree(dg);
+    mer::DevBuf dp, df, dg;
+    MER_CUDA(dp.alloc(n * 3 * sizeof(float)));
+    MER_CUDA(df.alloc(n * sizeof(float)));
+    MER_CUDA(dg.alloc(n * 3 * sizeof(float)));
+    MER_CUDA(cudaMemcpy(dp.ptr, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    int rc = mer_rif_eval_device(r, what, n, dp.as<float>(), df.as<float>(), dg.as<float>(), nullptr);
     if (rc) return rc;
-    if (e != cudaSuccess) return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e));
+    MER_CUDA(cudaDeviceSynchronize());
+    if (what != MER_EVAL_GRADIENT && value_out) MER_CUDA(cudaMemcpy(value_out, df.ptr, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (what != MER_EVAL_VALUE && grad_out) MER_CUDA(cudaMemcpy(grad_out, dg.ptr, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
     return MER_OK;
 }
 
@@ -617,14 +638,12 @@ int mer_rif_inside_limits_batch(const mer_rif *r, size_t n, const float *p, uint
     MER_REQUIRE(r && (n == 0 || (p && inside_out)), "null argument");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(r->device);
-    float *dp = nullptr;
-    uint8_t *dout = nullptr;
-    MER_CUDA(cudaMalloc(&dp, n * 3 * sizeof(float)));
-    MER_CUDA(cudaMalloc(&dout, n));
-    MER_CUDA(cudaMemcpy(dp, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
-    MER_LAUNCH(k_rif_inside, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, r->dev, n, dp, dout);
-    MER_CUDA(cudaMemcpy(inside_out, dout, n, cudaMemcpyDeviceToHost));
-    cudaFree(dp); cudaFree(dout);
+    mer::DevBuf dp, dout;
+    MER_CUDA(dp.alloc(n * 3 * sizeof(float)));
+    MER_CUDA(dout.alloc(n));
+    MER_CUDA(cudaMemcpy(dp.ptr, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    MER_LAUNCH(k_rif_inside, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, r->dev, n, dp.as<float>(), dout.as<uint8_t>());
+    MER_CUDA(cudaMemcpy(inside_out, dout.ptr, n, cudaMemcpyDeviceToHost));
     return MER_OK;
 }
 
@@ -731,13 +750,12 @@ int mer_grid_lookup_batch(const mer_grid *g, size_t n, const float *p, float *va
     MER_REQUIRE(g && (n == 0 || (p && value_out)), "null argument");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(g->device);
-    float *dp = nullptr, *dout = nullptr;
-    MER_CUDA(cudaMalloc(&dp, n * 3 * sizeof(float)));
-    MER_CUDA(cudaMalloc(&dout, n * sizeof(float)));
-    MER_CUDA(cudaMemcpy(dp, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
-    MER_LAUNCH(k_grid_lookup, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, g->dev, n, dp, dout);
-    MER_CUDA(cudaMemcpy(value_out, dout, n * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaFree(dp); cudaFree(dout);
+    mer::DevBuf dp, dout;
+    MER_CUDA(dp.alloc(n * 3 * sizeof(float)));
+    MER_CUDA(dout.alloc(n * sizeof(float)));
+    MER_CUDA(cudaMemcpy(dp.ptr, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    MER_LAUNCH(k_grid_lookup, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, g->dev, n, dp.as<float>(), dout.as<float>());
+    MER_CUDA(cudaMemcpy(value_out, dout.ptr, n * sizeof(float), cudaMemcpyDeviceToHost));
     return MER_OK;
 }
 
@@ -747,19 +765,17 @@ static int grid_woodcock(const mer_grid *g, float scale, size_t n, const float *
     MER_REQUIRE(scale > 0.0f, "scale must be positive");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(g->device);
-    float *dro = nullptr, *drd = nullptr, *dmi = nullptr, *dma = nullptr, *dt = nullptr, *dd = nullptr, *dtr = nullptr;
-    uint8_t *dok = nullptr;
-    MER_CUDA(cudaMalloc(&dro, n * 12)); MER_CUDA(cudaMalloc(&drd, n * 12)); MER_CUDA(cudaMalloc(&dmi, n * 4)); MER_CUDA(cudaMalloc(&dma, n * 4));
-    MER_CUDA(cudaMalloc(&dt, n * 4)); MER_CUDA(cudaMalloc(&dd, n * 4)); MER_CUDA(cudaMalloc(&dtr, n * 4)); MER_CUDA(cudaMalloc(&dok, n));
-    MER_CUDA(cudaMemcpy(dro, ro, n * 12, cudaMemcpyHostToDevice)); MER_CUDA(cudaMemcpy(drd, rd, n * 12, cudaMemcpyHostToDevice));
-    MER_CUDA(cudaMemcpy(dmi, mint, n * 4, cudaMemcpyHostToDevice)); MER_CUDA(cudaMemcpy(dma, maxt, n * 4, cudaMemcpyHostToDevice));
-    MER_LAUNCH(k_grid_woodcock, (unsigned) std::min<size_t>(mer_blocks(n, 128), 148u * 16u), 128, 0, 0, g->dev, scale, n, dro, drd, dmi, dma,
-               (unsigned long long) seed, evalT, dok, dt, dd, dtr);
-    if (ok) MER_CUDA(cudaMemcpy(ok, dok, n, cudaMemcpyDeviceToHost));
-    if (t) MER_CUDA(cudaMemcpy(t, dt, n * 4, cudaMemcpyDeviceToHost));
-    if (dens) MER_CUDA(cudaMemcpy(dens, dd, n * 4, cudaMemcpyDeviceToHost));
-    if (tr) MER_CUDA(cudaMemcpy(tr, dtr, n * 4, cudaMemcpyDeviceToHost));
-    cudaFree(dro); cudaFree(drd); cudaFree(dmi); cudaFree(dma); cudaFree(dt); cudaFree(dd); cudaFree(dtr); cudaFree(dok);
+    mer::DevBuf dro, drd, dmi, dma, dt, dd, dtr, dok;
+    MER_CUDA(dro.alloc(n * 12)); MER_CUDA(drd.alloc(n * 12)); MER_CUDA(dmi.alloc(n * 4)); MER_CUDA(dma.alloc(n * 4));
+    MER_CUDA(dt.alloc(n * 4)); MER_CUDA(dd.alloc(n * 4)); MER_CUDA(dtr.alloc(n * 4)); MER_CUDA(dok.alloc(n));
+    MER_CUDA(cudaMemcpy(dro.ptr, ro, n * 12, cudaMemcpyHostToDevice)); MER_CUDA(cudaMemcpy(drd.ptr, rd, n * 12, cudaMemcpyHostToDevice));
+    MER_CUDA(cudaMemcpy(dmi.ptr, mint, n * 4, cudaMemcpyHostToDevice)); MER_CUDA(cudaMemcpy(dma.ptr, maxt, n * 4, cudaMemcpyHostToDevice));
+    MER_LAUNCH(k_grid_woodcock, (unsigned) std::min<size_t>(mer_blocks(n, 128), 148u * 16u), 128, 0, 0, g->dev, scale, n, dro.as<float>(), drd.as<float>(),
+               dmi.as<float>(), dma.as<float>(), (unsigned long long) seed, evalT, dok.as<uint8_t>(), dt.as<float>(), dd.as<float>(), dtr.as<float>());
+    if (ok) MER_CUDA(cudaMemcpy(ok, dok.ptr, n, cudaMemcpyDeviceToHost));
+    if (t) MER_CUDA(cudaMemcpy(t, dt.ptr, n * 4, cudaMemcpyDeviceToHost));
+    if (dens) MER_CUDA(cudaMemcpy(dens, dd.ptr, n * 4, cudaMemcpyDeviceToHost));
+    if (tr) MER_CUDA(cudaMemcpy(tr, dtr.ptr, n * 4, cudaMemcpyDeviceToHost));
     return MER_OK;
 }
 

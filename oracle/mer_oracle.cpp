@@ -23,6 +23,7 @@
  * include/mitsuba/core/fwd.h:174-184).  Exported with suffixes _f / _d.
  */
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -423,7 +424,54 @@ inline float exitDistance(const mer_medium_desc &m, const float o[3], const floa
     return std::max(t1, 0.0f);
 }
 
+/* MaxExpDist — src/medium/maxexp.h:27-102 (strategy "maximum"), in `Float` like the reference; pinned bit for bit
+ * against the header compiled verbatim (oracle/ref_phase.cpp) */
+struct MaxExpDist {
+    std::vector<float> m_sigmaT, m_cdf, m_intervalStart;
+    float m_normalization = 1, m_invNormalization = 1;
+    bool valid = false;
+    void build(const float sigmaT[3]) {
+        m_sigmaT.assign(sigmaT, sigmaT + 3);
+        m_cdf.assign(4, 0.0f);
+        m_intervalStart.assign(3, 0.0f);
+        std::sort(m_sigmaT.begin(), m_sigmaT.end(), std::greater<float>());
+        valid = true;
+        for (size_t i = 0; i < 3; ++i) {
+            if (i > 0 && m_sigmaT[i] == m_sigmaT[i - 1]) { valid = false; return; } /* "sigmaT must vary across channels" */
+            float lower = (i == 0) ? -1 : -std::pow((m_sigmaT[i] / m_sigmaT[i - 1]), -m_sigmaT[i] / (m_sigmaT[i] - m_sigmaT[i - 1]));
+            float upper = (i == 2) ? 0 : -std::pow((m_sigmaT[i + 1] / m_sigmaT[i]), -m_sigmaT[i] / (m_sigmaT[i + 1] - m_sigmaT[i]));
+            m_cdf[i + 1] = m_cdf[i] + (upper - lower);
+            m_intervalStart[i] = (i == 0) ? 0 : (float) std::log((double) (m_sigmaT[i] / m_sigmaT[i - 1])) / (m_sigmaT[i] - m_sigmaT[i - 1]);
+        }
+        m_normalization = m_cdf[3];
+        m_invNormalization = 1 / m_normalization;
+        for (size_t i = 0; i < 4; ++i) m_cdf[i] *= m_invNormalization;
+    }
+    static float fexp(float x) { return (float) std::exp((double) x); }
+    static float flog(float x) { return (float) std::log((double) x); }
+    float sample(float u, float &pdf) const {
+        const float *lowerBound = std::lower_bound(&m_cdf[0], &m_cdf[0] + 4, u);
+        int index = std::max(0, (int) (lowerBound - &m_cdf[0]) - 1);
+        index = std::min(index, 2);
+        float t = -flog(fexp(-m_intervalStart[index] * m_sigmaT[index]) - m_normalization * (u - m_cdf[index])) / m_sigmaT[index];
+        pdf = m_sigmaT[index] * fexp(-m_sigmaT[index] * t) * m_invNormalization;
+        return t;
+    }
+    int piece(float t) const {
+        const float *lowerBound = std::lower_bound(&m_intervalStart[0], &m_intervalStart[0] + 3, t);
+        return std::max(0, (int) (lowerBound - &m_intervalStart[0]) - 1);
+    }
+    float pdf(float t) const { int index = piece(t); return m_sigmaT[index] * fexp(-m_sigmaT[index] * t) * m_invNormalization; }
+    float cdf(float t) const {
+        int index = piece(t);
+        float lower = (index == 0) ? -1 : -std::pow((m_sigmaT[index] / m_sigmaT[index - 1]), -m_sigmaT[index] / (m_sigmaT[index] - m_sigmaT[index - 1]));
+        float upper = -fexp(-m_sigmaT[index] * t);
+        return m_cdf[index] + (upper - lower) * m_invNormalization;
+    }
+};
+
 template <typename F> struct Medium {
+    MaxExpDist maxExp;
     const SplineVolume<F> *rif;
     const SplineVolume<F> *sdf = nullptr; /* <volume name="sdf">, used by aggressive tracing (a10) */
     bool aggressive = false;              /* `aggressivetracing` */
@@ -461,6 +509,8 @@ template <typename F> struct Medium {
             samplingDensity = sigmaT[channel];
         } else if (d.strategy == MER_STRATEGY_MANUAL) {
             samplingDensity = d.sampling_density;
+        } else if (d.strategy == MER_STRATEGY_MAXIMUM) { /* :287-291 */
+            maxExp.build(sigmaT);
         }
         invMaxDensity = den ? 1.0f / (d.density_scale * 1.0f) : 0.f; /* heterogeneous.cpp:239-242 */
     }
@@ -754,13 +804,18 @@ template <typename F> struct Medium {
         F rnd = (F) u1, sampledDistance;
         F sd = (F) samplingDensity;
         rec.nsteps = 0;
+        float pdfSampled = 0;
         if (rnd < weight) {
             rnd /= weight;
-            if (d.strategy == MER_STRATEGY_BALANCE) {
-                int channel = std::min((int) (u2 * 3), 2);
-                sd = sigmaT[channel];
+            if (d.strategy == MER_STRATEGY_MAXIMUM) { /* :445 */
+                sampledDistance = (F) maxExp.sample((float) (1 - rnd), pdfSampled);
+            } else {
+                if (d.strategy == MER_STRATEGY_BALANCE) {
+                    int channel = std::min((int) (u2 * 3), 2);
+                    sd = sigmaT[channel];
+                }
+                sampledDistance = (F) (-std::log((double) (1 - rnd))) / sd; /* fastlog: math.h:193-199 */
             }
-            sampledDistance = (F) (-std::log((double) (1 - rnd))) / sd; /* fastlog: math.h:193-199 */
         } else {
             sampledDistance = std::numeric_limits<F>::infinity();
         }
@@ -814,7 +869,10 @@ template <typename F> struct Medium {
         rec.refRatioSq = refRatioSq;
         /* pdfs :533-555, fastexp = exp in double rounded to FLOAT */
         F pdfFailure = 0, pdfSuccess = 0;
-        if (d.strategy == MER_STRATEGY_BALANCE) {
+        if (d.strategy == MER_STRATEGY_MAXIMUM) { /* :534-536 */
+            pdfFailure = 1 - maxExp.cdf((float) sampledDistance);
+            pdfSuccess = pdfSampled;
+        } else if (d.strategy == MER_STRATEGY_BALANCE) {
             for (int i = 0; i < 3; i++) {
                 F tmp = (F) std::exp((double) (-sigmaT[i] * sampledDistance));
                 pdfFailure += tmp;
@@ -1647,10 +1705,15 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         float edge[3]; /* T / pdf (and sigma_s on success) */
         if (!M.density) {
             F rnd = (F) rng.next(), sampledDistance, sd = (F) M.samplingDensity;
+            float pdfSampled = 0;
             if (rnd < M.weight) {
                 rnd /= M.weight;
-                if (M.d.strategy == MER_STRATEGY_BALANCE) sd = M.sigmaT[std::min((int) (rng.next() * 3), 2)];
-                sampledDistance = (F) (-std::log((double) (1 - rnd))) / sd;
+                if (M.d.strategy == MER_STRATEGY_MAXIMUM) {
+                    sampledDistance = (F) M.maxExp.sample((float) (1 - rnd), pdfSampled);
+                } else {
+                    if (M.d.strategy == MER_STRATEGY_BALANCE) sd = M.sigmaT[std::min((int) (rng.next() * 3), 2)];
+                    sampledDistance = (F) (-std::log((double) (1 - rnd))) / sd;
+                }
             } else {
                 sampledDistance = std::numeric_limits<F>::infinity();
             }
@@ -1665,7 +1728,10 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             if (success && p[0] == p0[0] && p[1] == p0[1] && p[2] == p0[2]) return; /* no forward progress */
             if (!success) sampledDistance = distSurf;
             F pdfFailure = 0, pdfSuccess = 0;
-            if (M.d.strategy == MER_STRATEGY_BALANCE) {
+            if (M.d.strategy == MER_STRATEGY_MAXIMUM) {
+                pdfFailure = 1 - M.maxExp.cdf((float) sampledDistance);
+                pdfSuccess = pdfSampled;
+            } else if (M.d.strategy == MER_STRATEGY_BALANCE) {
                 for (int i = 0; i < 3; i++) {
                     F tmp = (F) std::exp((double) (-M.sigmaT[i] * sampledDistance));
                     pdfFailure += tmp;
@@ -2042,6 +2108,18 @@ extern "C" void orc_coordinate_system(size_t n, const float *a, float *b, float 
 }
 extern "C" void orc_fresnel_dielectric_ext(size_t n, const float *cosThetaI, const float *eta, float *F, float *cosThetaT) {
     for (size_t i = 0; i < n; i++) F[i] = fresnelDielectricExt(cosThetaI[i], cosThetaT[i], eta[i]);
+}
+/* MaxExpDist over a batch: what = 0 sample(u) -> (t, pdf), 1 pdf(t), 2 cdf(t) */
+extern "C" int orc_maxexp(const float sigmaT[3], int what, size_t n, const float *in, float *out0, float *out1) {
+    MaxExpDist mx;
+    mx.build(sigmaT);
+    if (!mx.valid) return 1;
+    for (size_t i = 0; i < n; i++) {
+        if (what == 0) out0[i] = mx.sample(in[i], out1[i]);
+        else if (what == 1) out0[i] = mx.pdf(in[i]);
+        else out0[i] = mx.cdf(in[i]);
+    }
+    return 0;
 }
 extern "C" void orc_eval_transmittance(const float sigmaT[3], size_t n, const float *mint, const float *maxt,
                                        float *out) {

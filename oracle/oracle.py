@@ -150,6 +150,15 @@ class RefSpline:
             self.h = None
 
 
+def _maxexp(fn, sigma_t, what, x):
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    st = (C.c_float * 3)(*[float(v) for v in sigma_t])
+    a, b = np.zeros_like(x), np.zeros_like(x)
+    if fn(st, C.c_int(what), C.c_size_t(x.size), _ptr(x, C.c_float), _ptr(a, C.c_float), _ptr(b, C.c_float)) != 0:
+        raise ValueError("sigmaT must vary across channels")
+    return (a, b) if what == 0 else a
+
+
 class RefPhase:
     """The reference's HGPhaseFunction (src/phase/hg.cpp), Frame, coordinateSystem and fresnelDielectricExt
     (src/libcore/util.cpp), compiled verbatim (oracle/ref_phase.cpp -> oracle/_ref/libmer_refphase.so)."""
@@ -185,6 +194,10 @@ class RefPhase:
         b, c = np.zeros_like(a), np.zeros_like(a)
         self.lib.ref_coordinate_system(C.c_size_t(a.shape[0]), _ptr(a, C.c_float), _ptr(b, C.c_float), _ptr(c, C.c_float))
         return b, c
+
+    def maxexp(self, sigma_t, what, x):
+        """MaxExpDist (src/medium/maxexp.h): what = 0 sample(u) -> (t, pdf); 1 pdf(t); 2 cdf(t)"""
+        return _maxexp(self.lib.ref_maxexp, sigma_t, what, x)
 
     def fresnel_dielectric_ext(self, cos_i, eta):
         cos_i = np.ascontiguousarray(cos_i, dtype=np.float32).reshape(-1)
@@ -286,6 +299,9 @@ class Oracle:
         self.lib.orc_hg_eval(C.c_float(g), C.c_size_t(wi.shape[0]), _ptr(wi, C.c_float), _ptr(wo, C.c_float),
                              _ptr(out, C.c_float))
         return out
+
+    def maxexp(self, sigma_t, what, x):
+        return _maxexp(self.lib.orc_maxexp, sigma_t, what, x)
 
     def coordinate_system(self, a):
         a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3)

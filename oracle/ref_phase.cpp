@@ -5,6 +5,7 @@
  *     src/phase/hg.cpp                              HGPhaseFunction::sample / eval            
  *     include/mitsuba/core/frame.h                  Frame(n), Frame::toWorld                  (a17)
  *     include/mitsuba/core/{vector,point,normal,math,constants}.h    dot / cross / safe_sqrt / sincos / Epsilon ...
+ *     src/medium/maxexp.h                           MaxExpDist (strategy "maximum")            (a12)
  *     src/libcore/util.cpp  coordinateSystem()      (a17)   } the two function bodies are cut out of util.cpp by
  *     src/libcore/util.cpp  fresnelDielectricExt()  (f-3)   } oracle/Makefile into oracle/_ref/util_extract.inc
  * behind a C ABI, with the reference's release flags (-DSINGLE_PRECISION -DSPECTRUM_SAMPLES=3).  Built into
@@ -21,6 +22,7 @@ namespace mitsuba {
 }
 
 #include <phase/hg.cpp> /* -I/root/reference/src */
+#include <medium/maxexp.h> /* MaxExpDist, the "maximum" free-flight strategy (heterogeneousrefractive.cpp:287-291, 437-445, 534-536) */
 
 namespace {
 struct FixedSampler : public mitsuba::Sampler {
@@ -78,6 +80,20 @@ void ref_fresnel_dielectric_ext(size_t n, const float *cosThetaI, const float *e
         F[i] = mitsuba::fresnelDielectricExt(cosThetaI[i], ct, eta[i]);
         cosThetaT[i] = ct;
     }
+}
+
+/* MaxExpDist over a batch: what = 0 sample(u) -> (t, pdf), 1 pdf(t), 2 cdf(t) */
+int ref_maxexp(const float sigmaT[3], int what, size_t n, const float *in, float *out0, float *out1) {
+    std::vector<mitsuba::Float> st(sigmaT, sigmaT + 3);
+    try {
+        mitsuba::MaxExpDist mx(st);
+        for (size_t i = 0; i < n; i++) {
+            if (what == 0) out0[i] = mx.sample(in[i], out1[i]);
+            else if (what == 1) out0[i] = mx.pdf(in[i]);
+            else out0[i] = mx.cdf(in[i]);
+        }
+    } catch (const std::exception &) { return 1; }
+    return 0;
 }
 
 } /* extern "C" */

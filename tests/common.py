@@ -68,7 +68,7 @@ def oracle_medium_desc(props, g=0.9, has_density=False):
     d.sigma_s[:] = [float(x) for x in ss]
     d.stepsize = float(props.get("stepsize", 1e-3))
     d.medium_sampling_weight = float(props.get("mediumSamplingWeight", -1))
-    d.strategy = {"balance": 0, "single": 1, "manual": 2}[props.get("strategy", "balance")]
+    d.strategy = {"balance": 0, "single": 1, "manual": 2, "maximum": 3}[props.get("strategy", "balance")]
     d.channel = int(props.get("channel", -1))
     d.sampling_density = float(props.get("samplingDensity", 0.0))
     shape = props["shape"]

@@ -68,6 +68,14 @@ def phase():
     cos_i[:4], eta[:4] = [1.0, -1.0, 0.0, 0.3], [1.5, 1.5, 1.5, 1.0]
     out["cos_i"], out["eta"] = cos_i, eta
     out["fresnel"], out["cos_t"] = ref.fresnel_dielectric_ext(cos_i, eta)
+    # MaxExpDist (src/medium/maxexp.h), the "maximum" free-flight strategy
+    out["maxexp_sigma_t"] = np.array([[2.5, 3.25, 0.5], [4.0, 3.5, 3.0]], np.float32)
+    out["maxexp_u"] = rng.random(n).astype(np.float32)
+    out["maxexp_t"] = (rng.random(n) * 6).astype(np.float32)
+    for k, st in enumerate(out["maxexp_sigma_t"]):
+        out["maxexp_sample_t_%d" % k], out["maxexp_sample_pdf_%d" % k] = ref.maxexp(st, 0, out["maxexp_u"])
+        out["maxexp_pdf_%d" % k] = ref.maxexp(st, 1, out["maxexp_t"])
+        out["maxexp_cdf_%d" % k] = ref.maxexp(st, 2, out["maxexp_t"])
     np.savez_compressed(os.path.join(HERE, "phase_ref.npz"), **out)
     print("wrote phase_ref.npz")
 

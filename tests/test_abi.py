@@ -90,6 +90,24 @@ def test_vol_io_is_host_only(tmp_path):
     assert np.array_equal(back, data) and tuple(lo) == (-1, -2, 0.5) and tuple(hi) == (1, 1, 2)
     with pytest.raises(mer.MerError, match="cannot open"):
         mer.fields.read_vol(tmp_path / "missing.vol")
+    # EUInt8 payloads (gridvolume.cpp:251-262, 369-376: value / 255), one channel
+    import struct
+    u8 = rng.integers(0, 256, (5, 6, 7), dtype=np.uint8)
+    hdr = b"VOL\x03" + struct.pack("<iiiii", 3, 7, 6, 5, 1) + struct.pack("<6f", 0, 0, 0, 1, 1, 1)
+    (tmp_path / "u8.vol").write_bytes(hdr + u8.tobytes())
+    back, lo, hi = mer.fields.read_vol(tmp_path / "u8.vol")
+    assert back.shape == (5, 6, 7) and np.array_equal(back, u8.astype(np.float32) / np.float32(255.0))
+    # untrusted headers: sizes are validated before anything is multiplied or allocated
+    for res in ((-1, 6, 5), (7, 0, 5), (1 << 20, 6, 5)):
+        (tmp_path / "bad.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", 1, *res, 1) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + b"\0" * 64)
+        with pytest.raises(mer.MerError, match="resolution out of range"):
+            mer.fields.read_vol(tmp_path / "bad.vol")
+    (tmp_path / "short.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", 1, 7, 6, 5, 1) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + b"\0" * 100)
+    with pytest.raises(mer.MerError, match="truncated"):
+        mer.fields.read_vol(tmp_path / "short.vol")
+    (tmp_path / "rgb.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", 1, 2, 2, 2, 3) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + b"\0" * 96)
+    with pytest.raises(mer.MerError, match="single-channel"):
+        mer.fields.read_vol(tmp_path / "rgb.vol")
 
 
 @pytest.mark.skipif(mer.device_count() > 0, reason="a GPU is present")

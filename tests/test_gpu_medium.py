@@ -208,7 +208,7 @@ def test_analytic_invariants():
     assert np.all(out["opl"][ok] >= 1.0 * out["dist_surf"][ok]) and np.all(out["opl"][ok] <= 2.0 * out["dist_surf"][ok])
 
 
-@pytest.mark.parametrize("strategy", ["balance", "single", "manual"])
+@pytest.mark.parametrize("strategy", ["balance", "single", "manual", "maximum"])
 def test_sample_distance_records(oracle32, strategy):
     props = medium_props(stepsize=4e-3, strategy=strategy, sigmaS=(2.0, 3.0, 4.0), sigmaA=(0.5, 0.25, 0.1),
                          samplingDensity=2.5)
@@ -325,7 +325,7 @@ def test_error_behaviour():
         mer.HeterogeneousRefractiveMedium(medium_props(strategy="bogus"))
     with pytest.raises(mer.MerError, match=r"interval \(-1, 1\)"):
         mer.HGPhaseFunction(g=1.0)
-    with pytest.raises(mer.MerError):
+    with pytest.raises(mer.MerError, match="must vary across channels"):  # MaxExpDist, src/medium/maxexp.h:38-39
         mer.HeterogeneousRefractiveMedium(medium_props(strategy="maximum")).addChild("rif", rif).configure()
     with pytest.raises(mer.MerError):
         mer.SplineDataSource(data=np.ones((2, 2, 2), np.float32), min=(0, 0, 0), max=(1, 1, 1))

@@ -50,7 +50,7 @@ def image_gates(film_gpu, film_cpu, spp):
 
 
 @pytest.mark.parametrize("kind,strategy,filt", [("linear", "single", "gaussian"), ("radial", "balance", "box"),
-                                                ("sd", "single", "box")])
+                                                ("sd", "single", "box"), ("radial", "maximum", "box")])
 def test_homogeneous_image_matches_oracle(oracle32, kind, strategy, filt):
     props = medium_props(stepsize=1e-2, strategy=strategy, sigmaS=(3.6, 3.0, 2.4), sigmaA=(0.4, 0.5, 0.6))
     med, omed, keep = setup(oracle32, kind, 40, props)

@@ -173,6 +173,19 @@ def test_vol_roundtrip_and_file_loading(tmp_path, oracle32):
         mer.SplineDataSource(filename=str(bad))
 
 
+def test_uint8_density_file(tmp_path):
+    """EUInt8 .vol payloads (gridvolume.cpp:251-262, 369-376): streamed to the device as value / 255"""
+    import struct
+    rng = np.random.default_rng(8)
+    u8 = rng.integers(0, 256, (24, 20, 28), dtype=np.uint8)
+    hdr = b"VOL\x03" + struct.pack("<iiiii", 3, 28, 20, 24, 1) + struct.pack("<6f", -1, -1, -1, 1, 1, 1)
+    (tmp_path / "u8.vol").write_bytes(hdr + u8.tobytes())
+    g = mer.GridDataSource(filename=str(tmp_path / "u8.vol"))
+    ref = mer.GridDataSource(data=u8.astype(np.float32) / np.float32(255.0), min=BOX_MIN, max=BOX_MAX)
+    pts = rng.uniform(-0.95, 0.95, (5000, 3)).astype(np.float32)
+    assert np.array_equal(g.lookupFloat(pts), ref.lookupFloat(pts))
+
+
 def test_streamed_loading_of_a_multi_slab_file(tmp_path):
     """.vol files are streamed to the device in 64 MiB slabs through two pinned buffers (a 1024^3 RIF is 4 GiB
     on disk); a 288^3 file spans two slabs, a truncated one is refused, density grids go the same way"""

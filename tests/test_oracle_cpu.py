@@ -61,6 +61,11 @@ def test_oracle_phase_bit_exact_vs_reference_golden():
     assert np.array_equal(s, g["frame_s"]) and np.array_equal(t, g["frame_t"])
     F, ct = orc.fresnel_dielectric_ext(g["cos_i"], g["eta"])
     assert np.array_equal(F, g["fresnel"]) and np.array_equal(ct, g["cos_t"])
+    for k, st in enumerate(g["maxexp_sigma_t"]):  # MaxExpDist, src/medium/maxexp.h
+        t, pdf = orc.maxexp(st, 0, g["maxexp_u"])
+        assert np.array_equal(t, g["maxexp_sample_t_%d" % k]) and np.array_equal(pdf, g["maxexp_sample_pdf_%d" % k])
+        assert np.array_equal(orc.maxexp(st, 1, g["maxexp_t"]), g["maxexp_pdf_%d" % k])
+        assert np.array_equal(orc.maxexp(st, 2, g["maxexp_t"]), g["maxexp_cdf_%d" % k])
 
 
 @pytest.mark.skipif(not RefPhase.available(), reason="oracle/_ref not built (needs /root/reference)")
