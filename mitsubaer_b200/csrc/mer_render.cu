@@ -265,6 +265,11 @@ __device__ __forceinline__ float path_weight(const RenderParams &P, float len) {
 struct EvStats { unsigned v[ST_COUNT]; };
 #define ST_INC(st, i) ((st).v[i]++)
 /* returns true when the sample is dropped because a value is not finite (imageblock.h:147-152) */
+/* film accumulation: red.global.add.f32, no return value and no generic-address dispatch (a plain atomicAdd on the film
+ * pointer compiled to ATOM.E.ADD.F32 plus a shared-memory CAS-spin fallback: the compiler cannot see that it is global) */
+__device__ __forceinline__ void film_red(float *p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 __device__ __noinline__ bool film_put(const RenderParams &P, float sx, float sy, const float L[3], float alpha, float wgt, int frame) {
     const float value[5] = {L[0], L[1], L[2], alpha, wgt};
 #pragma unroll
@@ -280,10 +285,10 @@ __device__ __noinline__ bool film_put(const RenderParams &P, float sx, float sy,
             float *dest = P.film + ((size_t) y * P.W + x) * (size_t) P.channels;
             if (frame >= 0) {
 #pragma unroll
-                for (int k = 0; k < 3; k++) atomicAdd(dest + 3 * frame + k, w * value[k]);
+                for (int k = 0; k < 3; k++) film_red(dest + 3 * frame + k, w * value[k]);
             }
-            atomicAdd(dest + P.channels - 2, w * value[3]);
-            atomicAdd(dest + P.channels - 1, w * value[4]);
+            film_red(dest + P.channels - 2, w * value[3]);
+            film_red(dest + P.channels - 1, w * value[4]);
         }
     }
     return false;
