@@ -5,13 +5,17 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the
  * checker / baseline.  The product (libmitsubaer_b200.so) never links, loads or calls it.
  *
- * Parity pinning: the spline part (rows a1-a4 of SURVEY.md §8a) is checked bit-for-bit
- * against the reference's own basisspline.h compiled verbatim (oracle/_ref, ref_spline.cpp)
- * and against the golden vectors generated from it (tests/golden/spline_ref_*.npz).
- * Everything else (a5-a24) has NO golden vectors or tests in the reference,
- * so it is pinned only by line-by-line restatement + analytic invariants: PARITY UNPINNED
- * by reference fixtures for those rows, except HG which is pinned statistically by the
- * reference's chi-square test (src/tests/test_chisquare.cpp:508-572).
+ * Parity pinning (what is checked bit for bit against the REFERENCE'S OWN CODE compiled here, oracle/_ref):
+ *   a1-a4 + Hessian   include/mitsuba/core/basisspline.h                      (ref_spline.cpp, float and double)
+ *   a15-a17           src/phase/hg.cpp, include/mitsuba/core/{frame,vector,math,constants}.h,
+ *                     coordinateSystem() of src/libcore/util.cpp              (ref_phase.cpp)
+ *   hdielectric       fresnelDielectricExt() of src/libcore/util.cpp          (ref_phase.cpp)
+ *   strategy maximum  src/medium/maxexp.h (MaxExpDist)                        (ref_phase.cpp)
+ * and against golden vectors generated from those builds (tests/golden/*.npz, make_golden.py).
+ * The rest (a5-a14: er_step / trace / traceTillBoundary / sampleDistance, a18-a24: density grid, Woodcock, bounce loop,
+ * film) needs Mitsuba's framework to compile and has NO golden vectors or tests in the reference: it is
+ * pinned only by line-by-line restatement + analytic invariants: PARITY UNPINNED by reference fixtures for those rows;
+ * HG is in addition pinned statistically by the reference's chi-square test (src/tests/test_chisquare.cpp:508-572).
  * The "next" rows restated here as well (curved direct connections and their use as next-event
  * estimation, hdielectric boundary, transient film, light tracing, SDF containers) are UNPINNED too: the reference has
  * no fixtures for them and its solver is Ceres; they are checked by closed forms (slab reflectance 2R/(1+R), time of
