@@ -11,7 +11,7 @@
  *                     coordinateSystem() of src/libcore/util.cpp              (ref_phase.cpp)
  *   hdielectric       fresnelDielectricExt() of src/libcore/util.cpp          (ref_phase.cpp)
  *   strategy maximum  src/medium/maxexp.h (MaxExpDist)                        (ref_phase.cpp)
- * and against golden vectors generated from those builds (tests/golden/*.npz, make_golden.py).
+ * and against golden vectors generated from those builds (the .npz files under tests/golden, make_golden.py).
  * The rest (a5-a14: er_step / trace / traceTillBoundary / sampleDistance, a18-a24: density grid, Woodcock, bounce loop,
  * film) needs Mitsuba's framework to compile and has NO golden vectors or tests in the reference: it is
  * pinned only by line-by-line restatement + analytic invariants: PARITY UNPINNED by reference fixtures for those rows;
