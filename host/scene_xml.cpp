@@ -284,6 +284,8 @@ Scene loadScene(const std::string &xmlPath, const std::map<std::string, std::str
     R.pool_paths = (int) integrator->props.getInteger("poolPaths", 0);
     R.steps_per_pass = (int) integrator->props.getInteger("stepsPerPass", 0);
     R.direct_connections = integrator->props.getBoolean("directConnections", false) ? 1 : 0;
+    /* multiple importance sampling between the connection and phase sampling, as volpath does it (volpath.cpp:120-147, 430-433) */
+    if (integrator->props.getBoolean("misConnections", false)) R.direct_connections = 2;
     R.light_tracing = integrator->props.getBoolean("lightTracing", false) ? 1 : 0; /* emitter-side walk + t = 1 sensor connections */
     const std::string connectionStart = integrator->props.getString("connectionStart", "straight");
     if (connectionStart != "straight" && connectionStart != "random") logError("connectionStart must be \"straight\" or \"random\"");

@@ -318,7 +318,11 @@ typedef struct mer_render_desc {
      * 1 = every scattering vertex in the medium is connected to a uniformly sampled point of the quad by solving the
      * shooting problem of makeDirectConnections (heterogeneousrefractive.cpp:1087-1163), and paths that reach the quad
      * after a scattering event no longer count it.  Requires a quad and the tricubic RIF mode; through a density grid the
-     * connection's transmittance is exp(-optical depth), midpoint rule on the re-trace's steps. */
+     * connection's transmittance is exp(-optical depth), midpoint rule on the re-trace's steps.
+     * 2 = the same with multiple importance sampling as volpath does it (src/integrators/path/volpath.cpp:120-147,
+     * 164-173, miWeight :430-433): the connection is weighted by p_nee^2 / (p_nee^2 + p_phase^2), and a phase-sampled
+     * path that reaches the quad counts it with p_phase^2 / (p_phase^2 + p_nee^2), p_nee being the solid-angle density
+     * of the curved connection (from the solver's Jacobian, solved for the point that was hit). */
     int32_t direct_connections;
     mer_connection_params connection; /* solver parameters for direct_connections = 1 (zeros => tol2 1e-6, rrweight 1e-2, 3, 20) */
     /* transient film: <film> properties decomposition="transient", minBound, maxBound, binWidth (src/librender/film.cpp

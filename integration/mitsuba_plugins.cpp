@@ -325,6 +325,7 @@ public:
         m_maxDepth = props.getInteger("maxDepth", -1);
         m_rrDepth = props.getInteger("rrDepth", 5);
         m_directConnections = props.getBoolean("directConnections", false); /* curved next-event estimation */
+        m_misConnections = props.getBoolean("misConnections", false);       /* ... with volpath's power heuristic (volpath.cpp:120-147) */
         m_lightTracing = props.getBoolean("lightTracing", false);           /* emitter-side walk + sensor connections */
         m_gpus = props.getInteger("gpus", 1);                               /* 0: every GPU of the box */
         if (m_maxDepth == 0 || m_maxDepth < -1)
@@ -332,12 +333,12 @@ public:
     }
     EikonalVolPathIntegrator(Stream *stream, InstanceManager *manager) : Integrator(stream, manager) {
         m_maxDepth = stream->readInt(); m_rrDepth = stream->readInt();
-        m_directConnections = stream->readBool(); m_lightTracing = stream->readBool(); m_gpus = stream->readInt();
+        m_directConnections = stream->readBool(); m_misConnections = stream->readBool(); m_lightTracing = stream->readBool(); m_gpus = stream->readInt();
     }
     void serialize(Stream *stream, InstanceManager *manager) const {
         Integrator::serialize(stream, manager);
         stream->writeInt(m_maxDepth); stream->writeInt(m_rrDepth);
-        stream->writeBool(m_directConnections); stream->writeBool(m_lightTracing); stream->writeInt(m_gpus);
+        stream->writeBool(m_directConnections); stream->writeBool(m_misConnections); stream->writeBool(m_lightTracing); stream->writeInt(m_gpus);
     }
     bool render(Scene *scene, RenderQueue *, const RenderJob *, int, int, int) {
         const Sensor *sensor = scene->getSensor();
@@ -354,7 +355,7 @@ public:
         r.fov_deg = static_cast<const PerspectiveCamera *>(sensor)->getXFov();
         r.filter = film->getReconstructionFilter()->getRadius() > 1 ? MER_FILTER_GAUSSIAN : MER_FILTER_BOX;
         r.max_depth = m_maxDepth; r.rr_depth = m_rrDepth;
-        r.direct_connections = m_directConnections ? 1 : 0;
+        r.direct_connections = m_misConnections ? 2 : (m_directConnections ? 1 : 0);
         r.light_tracing = m_lightTracing ? 1 : 0;
         /* the fork's transient film (src/librender/film.cpp:56-78): frames, bounds, calibration */
         if (film->getDecompositionType() == Film::ETransient && film->getFrames() > 1) {
@@ -423,7 +424,7 @@ public:
     MTS_DECLARE_CLASS()
 private:
     int m_maxDepth, m_rrDepth, m_gpus;
-    bool m_directConnections, m_lightTracing;
+    bool m_directConnections, m_misConnections, m_lightTracing;
 };
 
 MTS_IMPLEMENT_CLASS_S(B200SplineDataSource, false, VolumeDataSource)

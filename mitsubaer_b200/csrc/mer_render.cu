@@ -115,12 +115,14 @@ struct RenderParams {
     unsigned long long *stats;
     /* direct connections */
     int nee, neePrecision, neeMaxIterations, neeStraightFirst;
+    int neeMis; /* power heuristic between phase sampling and the curved connection (volpath.cpp:120-147, 164-173, 430-433) */
     float neeTol2, neeRRWeight;
     unsigned neeCap;
     unsigned *neeCount;
     float4 *neeQ0, *neeQ1; /* (p1.xyz, wi.x), (wi.yz, thr.rg) */
     uint4 *neeQ2;          /* thr.b, depth, pixel, sample */
     float *neeQ3;          /* optical path length at the vertex (transient film) */
+    float *neeQ4;          /* HIT requests (neeMis): the pdf the walk sampled the emitted direction with */
     /* light tracing */
     int lightMode, emitterType;
     float beamO[3], beamD[3], beamPower[3];
@@ -131,6 +133,7 @@ struct RenderParams {
 };
 
 #define NEE_BINS 64
+#define NEE_HIT 0x80000000u /* request flag in the depth word: a phase-sampled path that HIT the quad asks for its MIS weight */
 
 struct Lane {
     float3 p, v;
@@ -140,6 +143,7 @@ struct Lane {
     float thr[3];
     float refStart, segDist, distSurf, rem, sd, etaPath, opl;
     float safe; /* MER_SHAPE_SDF: distance the ray may still move before the containment test needs a lookup (not persisted) */
+    float phasePdf; /* pdf of the direction sampled at the last scattering vertex (MIS of emitter hits) */
     int stepsLeft, depth, kind, flags;
     PathRng rng;
     unsigned pixel, sample; /* sample id = pixel * sppTotal + sample */
@@ -394,6 +398,22 @@ __device__ __noinline__ void edge_weight(const MediumDev &M, float sd, float d, 
         edge[c] = success ? __fdiv_rn(__fmul_rn(M.sigmaS[c], T[c]), ps) : __fdiv_rn(T[c], pf);
 }
 
+/* MIS (desc.direct_connections = 2): a phase-sampled path that reaches the quad after a vertex whose direct connection
+ * was requested does not count the quad with weight 0 (round 1) but asks k_nee for its power-heuristic weight: the
+ * connection vertex -> hit point is solved like any other, its Jacobian gives the solid-angle density p_nee the
+ * next-event estimator would have had for that point, and the hit is splatted with p_phase^2 / (p_phase^2 + p_nee^2)
+ * (volpath.cpp:164-173, miWeight :430-433).  false: the request queue is full (the caller parks the path). */
+__device__ __forceinline__ bool nee_hit_request(const RenderParams &P, const Lane &L, float3 vertex, float3 y, const float rad[3], float length) {
+    const unsigned slot = atomicAdd(P.neeCount, 1u);
+    if (slot >= P.neeCap) return false;
+    P.neeQ0[slot] = make_float4(vertex.x, vertex.y, vertex.z, y.x);
+    P.neeQ1[slot] = make_float4(y.y, y.z, rad[0], rad[1]);
+    P.neeQ2[slot] = make_uint4(__float_as_uint(rad[2]), (unsigned) L.depth | NEE_HIT, L.pixel, L.sample);
+    P.neeQ3[slot] = length;
+    P.neeQ4[slot] = L.phasePdf;
+    return true;
+}
+
 /* Everything that is not a plain full step, ONE PASS over the kinds of event in the order a path runs through them:
  *     A  one er_step with a direct lookup (remainder step, step back, entry, edge-of-grid steps)
  *     R  end of a path edge: Woodcock test / edge weights; null collision -> next flight; exit -> radiance or surface
@@ -493,15 +513,26 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, Ev
                     L.kind = E_SCATTER;
                 }
             } else {
-                ST_INC(st, ST_EXIT);
-#pragma unroll
-                for (int c = 0; c < 3; c++) L.thr[c] *= edge[c] * rrs;
-                if (P.maxDepth != -1 && L.depth >= P.maxDepth) {
-                    MER_FINISH(0.f, 0.f, 0.f, 1.0f, INFINITY);
+                const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
+                const float3 d = f3(L.v.x * vinv, L.v.y * vinv, L.v.z * vinv);
+                const float thrNew[3] = {L.thr[0] * (edge[0] * rrs), L.thr[1] * (edge[1] * rrs), L.thr[2] * (edge[2] * rrs)};
+                const bool deep = P.maxDepth != -1 && L.depth >= P.maxDepth;
+                float tq = 0.0f;
+                const bool hitsQuad = !DIELECTRIC && !deep && intersect_quad(P, L.p, d, tq);
+                const bool dark = hitsQuad && EXTRAS && (L.flags & FLAG_COVERED);
+                bool parked = false;
+                if (EXTRAS && dark && P.neeMis) { /* the hit's share under the power heuristic comes from k_nee */
+                    const float rad[3] = {thrNew[0] * P.quadLe[0], thrNew[1] * P.quadLe[1], thrNew[2] * P.quadLe[2]};
+                    parked = !nee_hit_request(P, L, L.o, f3(L.p.x + tq * d.x, L.p.y + tq * d.y, L.p.z + tq * d.z), rad, L.opl + tq);
+                }
+                if (parked) { /* nothing has been committed: the exit is taken again next round */
+                    L.flags |= FLAG_PARKED;
                 } else {
-                    const float vinv = 1.0f / sqrtf(dot3(L.v, L.v));
-                    const float3 d = f3(L.v.x * vinv, L.v.y * vinv, L.v.z * vinv);
-                    if (DIELECTRIC) { /* move to the surface point and fetch the field there, then E_SURFACE */
+                    ST_INC(st, ST_EXIT);
+                    L.thr[0] = thrNew[0]; L.thr[1] = thrNew[1]; L.thr[2] = thrNew[2];
+                    if (deep) {
+                        MER_FINISH(0.f, 0.f, 0.f, 1.0f, INFINITY);
+                    } else if (DIELECTRIC) { /* move to the surface point and fetch the field there, then E_SURFACE */
                         const float te = SDFSHAPE ? exit_distance_sdf(M, L.p, d) : exit_distance(M, L.p, d);
                         L.p = f3(L.p.x + te * d.x, L.p.y + te * d.y, L.p.z + te * d.z);
                         L.safe = 0.0f;
@@ -510,9 +541,6 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, Ev
                         L.kind = K_ENTRY;
                     } else {
                         L.depth++;
-                        float tq;
-                        const bool hitsQuad = intersect_quad(P, L.p, d, tq);
-                        const bool dark = hitsQuad && EXTRAS && (L.flags & FLAG_COVERED);
                         const float *Le = hitsQuad ? P.quadLe : P.env;
                         const float k = dark ? 0.0f : 1.0f;
                         MER_FINISH(k * L.thr[0] * Le[0], k * L.thr[1] * Le[1], k * L.thr[2] * Le[2], 1.0f, hitsQuad ? L.opl + tq : INFINITY);
@@ -545,6 +573,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, Ev
         if (!parked) { /* phase sampling (wi = normalize(-mRec.d)) and the Russian roulette of volpath.cpp:326-336 */
             const float u1 = L.rng.next(), u2 = L.rng.next();
             L.v = hg_sample_dev(M.g, wi, u1, u2);
+            if (EXTRAS && P.neeMis) L.phasePdf = hg_eval_dev(M.g, wi, L.v); /* HGPhaseFunction::sample's pdf (hg.cpp:100-105) */
             L.kind = E_BEGIN; /* field at p is still valid */
             if (L.depth++ >= P.rrDepth) {
                 float q = fmaxf(L.thr[0], fmaxf(L.thr[1], L.thr[2]));
@@ -564,21 +593,31 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, Ev
     if (DIELECTRIC && L.kind == E_SURFACE) {
         /* MER_SHAPE_SDF: normalised gradient of the signed distance; box / sphere: analytic */
         const float3 N = SDFSHAPE ? merc::container_normal(M, L.p) : shape_normal(M, L.p);
+        const unsigned rngBefore = L.rng.k;
         const float u = L.rng.next();
         L.rng.next(); /* the BSDF sample is a Point2 */
         float3 dOut;
         float w, es;
         const bool transmitted = hdielectric_sample(L.v, N, L.n, u, !(EXTRAS && P.lightMode), dOut, w, es);
+        const bool inside = (L.flags & FLAG_OUTWARD) ? !transmitted : transmitted;
+        float tq = 0.0f;
+        const bool hitsQuad = !inside && intersect_quad(P, L.p, dOut, tq);
+        const bool dark = hitsQuad && EXTRAS && (L.flags & FLAG_COVERED);
+        bool parked = false;
+        if (EXTRAS && dark && P.neeMis) { /* the refracted exit of a covered chain reached the quad: MIS weight from k_nee */
+            const float rad[3] = {L.thr[0] * w * P.quadLe[0], L.thr[1] * w * P.quadLe[1], L.thr[2] * w * P.quadLe[2]};
+            parked = !nee_hit_request(P, L, L.o, f3(L.p.x + tq * dOut.x, L.p.y + tq * dOut.y, L.p.z + tq * dOut.z), rad, L.opl + tq);
+        }
+        if (parked) { /* nothing committed, the draws are given back: the surface event is taken again next round */
+            L.rng.k = rngBefore;
+            L.flags |= FLAG_PARKED;
+        } else {
 #pragma unroll
         for (int c = 0; c < 3; c++) L.thr[c] *= w;
         L.etaPath *= es;
         L.v = dOut;
-        const bool inside = (L.flags & FLAG_OUTWARD) ? !transmitted : transmitted;
         L.flags &= ~FLAG_OUTWARD;
         if (!inside) { /* rayIntersectAndLookForEmitter with a delta BSDF: MIS weight 1, volpath.cpp:300-320 */
-            float tq;
-            const bool hitsQuad = intersect_quad(P, L.p, dOut, tq);
-            const bool dark = hitsQuad && EXTRAS && (L.flags & FLAG_COVERED);
             const float *Le = hitsQuad ? P.quadLe : P.env;
             const float k = dark ? 0.0f : 1.0f;
             MER_FINISH(k * L.thr[0] * Le[0], k * L.thr[1] * Le[1], k * L.thr[2] * Le[2], 1.0f, hitsQuad ? L.opl + tq : INFINITY);
@@ -594,6 +633,7 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, Ev
                     for (int c = 0; c < 3; c++) L.thr[c] /= q;
                 }
             }
+        }
         }
     }
 
@@ -786,6 +826,7 @@ __device__ __forceinline__ void full_load(const RenderParams &P, unsigned slot, 
     L.o = f3(f.x, f.y, f.z);
     L.depth = __float_as_int(f.w);
     L.pixel = g.y; L.sample = g.z;
+    L.phasePdf = __uint_as_float(g.w);
     L.rng.init(P.seed, (unsigned long long) g.y * (unsigned long long) P.sppTotal + g.z, g.x);
     L.safe = 0.0f;
 }
@@ -798,7 +839,7 @@ __device__ __forceinline__ void full_store(const RenderParams &P, unsigned slot,
     Q.c0[slot] = make_float4(L.thr[0], L.thr[1], L.thr[2], L.refStart);
     Q.c1[slot] = make_float4(L.segDist, L.sd, L.etaPath, L.rem);
     Q.c2[slot] = make_float4(L.o.x, L.o.y, L.o.z, __int_as_float(L.depth));
-    Q.c3[slot] = make_uint4(L.rng.k, L.pixel, L.sample, 0u);
+    Q.c3[slot] = make_uint4(L.rng.k, L.pixel, L.sample, __float_as_uint(L.phasePdf));
 }
 
 /* every slot starts by asking for a camera sample */
@@ -990,14 +1031,20 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         const uint4 c = P.neeQ2[i];
         const float3 p1 = f3(a.x, a.y, a.z), wi = f3(a.w, b.x, b.y);
         const float thr[3] = {b.z, b.w, __uint_as_float(c.x)};
-        const unsigned depth = c.y, pixel = c.z, sample = c.w;
-        const float oplVertex = WANT_OPL ? P.neeQ3[i] : 0.0f;
+        const bool isHit = (c.y & NEE_HIT) != 0u; /* MIS weight of a phase-sampled path that hit the quad */
+        const unsigned depth = c.y & ~NEE_HIT, pixel = c.z, sample = c.w;
+        const float oplVertex = (WANT_OPL || isHit) ? P.neeQ3[i] : 0.0f;
         PathRng nrng;
-        nrng.init(P.seed ^ MER_NEE_SALT, (unsigned long long) pixel * (unsigned long long) P.sppTotal + sample, depth * 256u);
+        nrng.init(P.seed ^ MER_NEE_SALT, (unsigned long long) pixel * (unsigned long long) P.sppTotal + sample, depth * 256u + (isHit ? 128u : 0u));
         float3 y, Nq = f3(0.f, 0.f, 1.f);
         float area = 1.0f;
         if (P.lightMode) { /* t = 1: the target is the pinhole */
             y = f3(P.camO[0], P.camO[1], P.camO[2]);
+        } else if (isHit) { /* the target is the point the walk hit (stored in the wi slots) */
+            const float3 qu = f3(P.quadU[0], P.quadU[1], P.quadU[2]), qv = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
+            Nq = f3(qu.y * qv.z - qu.z * qv.y, qu.z * qv.x - qu.x * qv.z, qu.x * qv.y - qu.y * qv.x);
+            area = sqrtf(dot3(Nq, Nq));
+            y = wi;
         } else {
             const float u = nrng.next(), w = nrng.next();
             const float3 qu = f3(P.quadU[0], P.quadU[1], P.quadU[2]), qv = f3(P.quadV[0], P.quadV[1], P.quadV[2]);
@@ -1015,9 +1062,9 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
         st[0] = 1u;
         const int steps = C.steps;
         bool ok = C.success && C.exit.exited && !C.exit.tir;
-        if (ok) {
-            const float spread = merc::connection_spread(C.J, C.xnorm); /* the Jacobian of the solver's last accepted evaluation */
-            ok = spread > 0.0f;
+        if (ok || isHit) {
+            const float spread = ok ? merc::connection_spread(C.J, C.xnorm) : 0.0f; /* the Jacobian of the solver's last accepted evaluation */
+            ok = ok && spread > 0.0f;
             if (ok && P.lightMode) {
                 /* C.rev is the direction in which the camera sees the vertex: pixel by the inverse of sampleRay's mapping,
                  * importance of the perspective sensor 1 / (A cos^3 theta) (src/sensors/perspective.cpp importance()),
@@ -1056,6 +1103,26 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                         if (frame >= 0 && film_put(P, sx, sy, rad, 0.0f, 0.0f, frame)) atomicAdd(&nonfinite, 1u);
                     }
                 }
+            } else if (isHit) {
+                /* the hit is already weighted by the walk; what is missing is the density p_nee (solid angle at the vertex)
+                 * with which the next-event estimator samples this very point: spread / (Area cos theta_y) */
+                float w = 1.0f;
+                if (ok) {
+                    const float cosY = fabsf(dot3(C.rev, Nq)) / area;
+                    const float pNee = spread / fmaxf(cosY * area, 1e-20f), pPhase = P.neeQ4[i];
+                    w = (pPhase * pPhase) / fmaxf(pPhase * pPhase + pNee * pNee, 1e-30f);
+                }
+                ok = true; /* an unsolvable connection means next-event estimation could not have found the point: weight 1 */
+                float rad[3] = {thr[0] * w, thr[1] * w, thr[2] * w};
+                float sx, sy;
+                sample_position(P, pixel, sample, sx, sy);
+                if (WANT_OPL && P.modulation) {
+                    const float wm = path_weight(P, oplVertex);
+#pragma unroll
+                    for (int k = 0; k < 3; k++) rad[k] *= wm;
+                }
+                const int frame = (WANT_OPL && !P.modulation) ? path_frame(P, oplVertex) : 0;
+                if (frame >= 0 && film_put(P, sx, sy, rad, 0.0f, 0.0f, frame)) atomicAdd(&nonfinite, 1u);
             } else if (ok) {
                 const float cosY = fabsf(dot3(C.rev, Nq)) / area;
                 const float inv1 = 1.0f / C.n1;
@@ -1067,7 +1134,11 @@ k_nee(const __grid_constant__ RenderParams P, unsigned nReq) {
                     const float Fr = fresnel_dielectric_ext(-C.exit.cosI, cosT, C.exit.nb);
                     scale *= (1.0f - Fr) * (C.exit.nb * C.exit.nb);
                 }
-                const float geom = cosY * area / spread;
+                float geom = cosY * area / spread;
+                if (P.neeMis) { /* miWeight(pdf_emitter, pdf_phase), volpath.cpp:137-141: both densities per solid angle at the vertex */
+                    const float pNee = 1.0f / fmaxf(geom, 1e-30f);
+                    geom *= (pNee * pNee) / fmaxf(pNee * pNee + phase * phase, 1e-30f);
+                }
                 float rad[3];
 #pragma unroll
                 for (int k = 0; k < 3; k++) { /* homogeneous: exp(-sigma_t dist); density grid: exp(-optical depth along the curve) */
@@ -1232,6 +1303,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
                     "transient film: width * height * (3 * frames + 2) floats exceed 64 GiB");
     }
     P.nee = (r->direct_connections || r->light_tracing) ? 1 : 0;
+    P.neeMis = (r->direct_connections == 2 && !r->light_tracing) ? 1 : 0;
     P.lightMode = r->light_tracing ? 1 : 0;
     P.emitterType = r->emitter_type;
     {
@@ -1292,7 +1364,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
             if (!S.neeHist) MER_CUDA(cudaMalloc(&S.neeHist, NEE_BINS * sizeof(unsigned)));
             cudaFree(S.neeOpl);
             S.neeOpl = nullptr;
-            MER_CUDA(cudaMalloc(&S.neeOpl, (size_t) cap * sizeof(float)));
+            MER_CUDA(cudaMalloc(&S.neeOpl, 2 * (size_t) cap * sizeof(float))); /* optical lengths, then the HIT requests' phase pdfs */
             if (!S.neeCount) MER_CUDA(cudaMalloc(&S.neeCount, sizeof(unsigned)));
             S.neeCap = cap;
         }
@@ -1300,6 +1372,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         P.neeCount = S.neeCount;
         P.neeQ0 = (float4 *) S.neeQ[0]; P.neeQ1 = (float4 *) S.neeQ[1]; P.neeQ2 = (uint4 *) S.neeQ[2];
         P.neeQ3 = S.neeOpl;
+        P.neeQ4 = S.neeOpl + cap;
         P.neeKey = S.neeKey;
         P.neeHist = S.neeHist;
         P.neePerm = m->dev.hasSdf ? nullptr : S.neePerm; /* the length estimate needs an analytic container */
@@ -1319,7 +1392,9 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
     const unsigned eventBlocks = pool / TPB;
-    const unsigned stepBlocks = std::min((unsigned) sms * MER_RENDER_MIN_BLOCKS, eventBlocks);
+    unsigned stepPerSm = MER_RENDER_MIN_BLOCKS;
+    if (const char *e = getenv("MER_STEP_CTAS")) stepPerSm = (unsigned) std::min(std::max(atoi(e), 1), MER_RENDER_MIN_BLOCKS); /* tuning knob */
+    const unsigned stepBlocks = std::min((unsigned) sms * stepPerSm, eventBlocks);
     int syncEvery = 8; /* rounds between two looks at the live-slot counter (a host synchronisation) */
     if (const char *e = getenv("MER_SYNC_EVERY")) syncEvery = std::max(atoi(e), 1);
 

@@ -486,7 +486,8 @@ class EikonalVolPathIntegrator:
         self.rrDepth = int(props.get("rrDepth", 5))
         self.poolPaths = int(props.get("poolPaths", 0))
         self.stepsPerPass = int(props.get("stepsPerPass", 0))
-        self.directConnections = bool(props.get("directConnections", False))
+        dc = props.get("directConnections", False)  # False | True | "mis" (power heuristic with phase sampling, volpath.cpp:120-147)
+        self.directConnections = 2 if str(dc).lower() == "mis" else (1 if (dc is True or str(dc).lower() == "true" or dc == 1) else 0)
         self.lightTracing = bool(props.get("lightTracing", False))  # emitter-side walk + t = 1 sensor connections
         self.connectionStart = str(props.get("connectionStart", "straight"))
         if self.connectionStart not in ("straight", "random"):
@@ -517,7 +518,7 @@ class EikonalVolPathIntegrator:
             r.quad_v[:] = [float(x) for x in quad["v"]]
             r.quad_radiance[:] = [float(x) for x in _spectrum(quad["radiance"])]
         r.pool_paths, r.steps_per_pass = self.poolPaths, self.stepsPerPass
-        r.direct_connections = 1 if self.directConnections else 0
+        r.direct_connections = int(self.directConnections)
         mp = getattr(medium, "props", None) or {}
         r.connection.tol2 = float(mp.get("tol2", 1e-6))
         r.connection.rrweight = float(mp.get("rrweight", 1e-2))

@@ -295,6 +295,32 @@ def test_direct_connections_agree_with_random_walk(kind, bsdf, shape):
     assert mean[True][1] < mean[False][1]  # and it is the lower-variance estimator
 
 
+@pytest.mark.parametrize("kind,bsdf,shape", [("linear", "null", ("box", BOX_MIN, BOX_MAX)), ("sd", "hdielectric", ("box", BOX_MIN, BOX_MAX))])
+def test_mis_connections_agree_with_both_estimators(kind, bsdf, shape):
+    """direct_connections = 2: volpath's power heuristic (volpath.cpp:120-147, 164-173, 430-433) between the curved
+    connection and phase sampling.  A weighted combination of two unbiased estimators of the quad's light, so its
+    expectation is theirs: against the un-MIS'd connections (same 0.75 sigma_t h exit-length quirk on the hit part only
+    where hits count) and against the plain walk; and the hit requests really ran (more requests than scattering
+    vertices ask for)."""
+    h, sigma_t = 2.5e-3, 2.0
+    med = _nee_medium(kind, h, bsdf, shape=shape)[0]
+    mean, conn = {}, {}
+    for mode in (False, True, "mis"):
+        vals = []
+        for seed in range(1, 9):
+            scene = scene_dict(128, 128, 16, rfilter="box", seed=seed)
+            scene["envRadiance"] = 0.0
+            film, st = mer.EikonalVolPathIntegrator(rrDepth=5, directConnections=mode).render(scene, med)
+            vals.append(float(mer.develop(film)[..., 0].mean()))
+        mean[mode] = (np.mean(vals), np.std(vals, ddof=1) / np.sqrt(len(vals)))
+        conn[mode] = st["connections"]
+    assert conn["mis"] > conn[True] > 1e5  # the emitter hits of covered chains asked for their weight
+    lo_, hi_ = sorted([mean[False][0], mean[True][0]])
+    slack = 4 * max(mean[False][1], mean[True][1], mean["mis"][1]) + 4e-3 * hi_
+    assert lo_ - slack <= mean["mis"][0] <= hi_ + slack, (kind, bsdf, mean)
+    assert mean["mis"][1] < mean[False][1]  # far less noisy than finding the quad by hitting it
+
+
 def test_direct_connections_queue_and_validation(oracle32):
     med, rif, props, data, lo, hi = _nee_medium("linear", 1e-2, "null")
     scene = scene_dict(32, 32, 8, rfilter="box")
