@@ -403,7 +403,8 @@ def c5_strong(mer, dist, dev, local, rank, world, spp_total=C5_STRONG_SPP, steps
            "scaling": "strong", "n_gpus": world, "spp_total": spp_total, "ms_per_frame": ms, "samples_per_sec": samples / (ms * 1e-3),
            "ray_steps_per_sec": ray_steps / (ms * 1e-3), "setup_s_generate_prefilter": setup_s,
            "rank0": {"device_ms": s0["device_ms"], "step_kernel_ms": s0["step_kernel_ms"], "tail_ms": s0["tail_ms"],
-                     "tail_share": s0["tail_ms"] / max(s0["device_ms"], 1e-9), "rounds": s0["passes"]},
+                     "tail_share": s0["tail_ms"] / max(s0["device_ms"], 1e-9), "rounds": s0["passes"],
+                     "step_lanes_per_sm": int(s0["step_lanes_per_sm"])},
            "roofline": {k: rl[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "block_fetches_per_ray_step")},
            "frac_hbm": rl["ceilings"]["hbm"]["frac"], "frac_tex": rl["ceilings"]["tex"]["frac"]}
     del med, rif, grid, film
@@ -580,6 +581,7 @@ def run_gpu(args, w, wname):
                               r0["scatter_events"] + r0["null_collisions"], r0["step_kernel_ms"], r0["step_launches"], grid_bytes, traffic)
     roofline["step_kernel_share_of_device_time"] = r0["step_kernel_ms"] / max(r0["device_ms"], 1e-9)
     roofline["drain_tail_share"] = r0["tail_ms"] / max(r0["device_ms"], 1e-9)
+    roofline["step_lanes_per_sm"] = int(stats[-1]["step_lanes_per_sm"])  # 512, or 192 when the table exceeds the L2 and the in-run comparison chose it
 
     # ---- CPU baseline (oracle port) on this box's host cores, bounded sample, rank 0 / N=1 only
     cpu = None

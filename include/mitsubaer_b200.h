@@ -374,6 +374,9 @@ typedef struct mer_render_stats {
                                 the path slots alive (the frame has run out of new samples) to the end */
     uint64_t block_fetches;  /* 4x4x4 coefficient blocks (256 bytes; 8 packed-trilinear nodes = 128 bytes) gathered from the grid:
                                 the algorithmic memory traffic of the stepper (one per cell change, not per step) */
+    uint32_t step_lanes_per_sm; /* resident threads per SM the step kernel ran with for most of the frame: 512, or 192 when the
+                                   coefficient table exceeds the L2 and the in-run comparison of the two found 192 faster */
+    uint32_t reserved0;
 } mer_render_stats;
 
 /* Integrator::render (include/mitsuba/render/integrator.h:61-96) for the eikonal volumetric

@@ -16,6 +16,7 @@
 
 #include <cstring>
 #include <string>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -38,8 +39,14 @@ struct Nccl {
     const char *(*GetErrorString)(int) = nullptr;
     bool ok = false;
     Nccl() {
-        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        /* The NCCL the process already has (PyTorch's, the host application's) is the one to use: a second libnccl.so.2
+         * cannot be loaded next to it (same SONAME), and loading the system's first would hand an older library to a
+         * torch imported LATER (its libtorch_cuda.so then fails on ncclDevCommCreate).  Only a process without NCCL loads
+         * one here: MER_NCCL_LIB if set, else the loader's libnccl.so.2 — with RTLD_LOCAL. */
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) if (const char *e = getenv("MER_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
         if (!h) return;
         CommInitAll = (decltype(CommInitAll)) dlsym(h, "ncclCommInitAll");
         CommDestroy = (decltype(CommDestroy)) dlsym(h, "ncclCommDestroy");
@@ -101,10 +108,14 @@ extern "C" int mer_render_multi(const mer_medium *const *media, int32_t ngpus, c
 
     /* ---- film reduce onto GPU 0 */
     if (rc == MER_OK && ngpus > 1) {
-        static Nccl nccl;
         bool reduced = false;
         const char *env = getenv("MER_NCCL"); /* MER_NCCL=0 forces the peer-copy path */
-        if (nccl.ok && distinct && !(env && !strcmp(env, "0"))) {
+        const bool wantNccl = distinct && !(env && !strcmp(env, "0"));
+        static Nccl *ncclLib = nullptr; /* loaded on the first reduce that can use it, never for shards of one device */
+        static std::once_flag ncclOnce;
+        if (wantNccl) std::call_once(ncclOnce, [] { ncclLib = new Nccl(); });
+        if (wantNccl && ncclLib && ncclLib->ok) {
+            Nccl &nccl = *ncclLib;
             std::vector<Nccl::comm_t> comms((size_t) ngpus, nullptr);
             std::vector<int> devs((size_t) ngpus);
             for (int g = 0; g < ngpus; g++) devs[(size_t) g] = media[g]->device;
@@ -159,6 +170,7 @@ extern "C" int mer_render_multi(const mer_medium *const *media, int32_t ngpus, c
             stats_out->device_ms = std::max(stats_out->device_ms, s.device_ms);         /* the GPUs run side by side */
             stats_out->step_kernel_ms = std::max(stats_out->step_kernel_ms, s.step_kernel_ms);
             stats_out->tail_ms = std::max(stats_out->tail_ms, s.tail_ms);
+            if (g == 0) stats_out->step_lanes_per_sm = s.step_lanes_per_sm;
         }
     }
     for (int g = 0; g < ngpus; g++) {

@@ -878,8 +878,13 @@ k_event(const __grid_constant__ RenderParams P) {
     if (lane == 0 && live) atomicAdd(P.live, live);
 }
 
-template <int MODE, int LAYOUT, bool EXTRAS, bool SDFSHAPE, bool XFORM>
-__global__ void __launch_bounds__(MER_STENCIL_BLOCK, MER_RENDER_MIN_BLOCKS)
+/* SPEC (the narrow configuration, tables far larger than the L2): the lane also gathers the block of the cell the NEXT step
+ * is predicted to land in (p + h v / n with the half-kicked velocity: off by h^2 |grad n| / n, ~1e-3 of a cell) into a
+ * second set of 64 registers, a whole turn before it is needed, so that two DRAM round trips per lane are in flight
+ * instead of one.  The prediction only decides WHICH registers a block is read from: blocks are keyed by their cell, a
+ * wrong guess costs the ordinary gather, and the arithmetic of the step is untouched.  One warp per CTA, <= 255 registers. */
+template <int MODE, int LAYOUT, bool EXTRAS, bool SDFSHAPE, bool XFORM, bool SPEC = false>
+__global__ void __launch_bounds__(SPEC ? 32 : MER_STENCIL_BLOCK, SPEC ? 6 : MER_RENDER_MIN_BLOCKS)
 k_step(const __grid_constant__ RenderParams P) {
     const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
     const MediumDev &M = P.M;
@@ -892,6 +897,8 @@ k_step(const __grid_constant__ RenderParams P) {
     int visit = 0;       /* steps left in this visit */
     StencilCache<MODE> S; /* registers only */
     S.invalidate();
+    StencilCache<MODE> N; /* SPEC: the prefetched block */
+    if (SPEC) N.invalidate();
     const float h = M.h;
     bool exhausted = false; /* warp-uniform: the round's slots are all handed out */
     unsigned nSteps = 0, nFetch = 0;
@@ -931,8 +938,14 @@ k_step(const __grid_constant__ RenderParams P) {
             c = rif_cell<MODE, XFORM>(M.rif, L.p);
             if (rif_cell_fast<MODE>(M.rif, c)) {
                 if (!stencil_has(S, c)) {
-                    rif_fetch_interior<LAYOUT>(M.rif, S, c.i, c.j, c.k);
+                    if (SPEC && stencil_has(N, c)) S = N; /* requested a turn ago */
+                    else rif_fetch_interior<LAYOUT>(M.rif, S, c.i, c.j, c.k);
                     nFetch++;
+                }
+                if (SPEC) { /* the block the next step will most likely need */
+                    const float r = __fdividef(h, L.n);
+                    const CellPos cn = rif_cell<MODE, XFORM>(M.rif, f3(fmaf(r, L.v.x, L.p.x), fmaf(r, L.v.y, L.p.y), fmaf(r, L.v.z, L.p.z)));
+                    if (!stencil_has(S, cn) && !stencil_has(N, cn) && rif_cell_fast<MODE>(M.rif, cn)) rif_fetch_interior<LAYOUT>(M.rif, N, cn.i, cn.j, cn.k);
                 }
                 step = true;
             } else { /* the stencil touches the edge of the grid: a step for the event kernel */
@@ -1340,7 +1353,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaMalloc(&S.pool[i], qBytes);
         if (e == cudaSuccess) e = cudaMalloc(&S.nOut, 4 * sizeof(unsigned));
         if (e == cudaSuccess) e = cudaMalloc(&S.counters, (1 + ST_COUNT) * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaMallocHost(&S.hostPinned, 4 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMallocHost(&S.hostPinned, (4 + RenderScratch::RING) * sizeof(unsigned long long)); /* + the step counter after every step launch */
         if (e == cudaSuccess) e = cudaEventCreate(&S.ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&S.ev1);
         if (e == cudaSuccess) e = cudaEventCreate(&S.evTail);
@@ -1392,9 +1405,45 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
     const unsigned eventBlocks = pool / TPB;
-    unsigned stepPerSm = MER_RENDER_MIN_BLOCKS;
-    if (const char *e = getenv("MER_STEP_CTAS")) stepPerSm = (unsigned) std::min(std::max(atoi(e), 1), MER_RENDER_MIN_BLOCKS); /* tuning knob */
-    const unsigned stepBlocks = std::min((unsigned) sms * stepPerSm, eventBlocks);
+    /* Lanes per SM of the step kernel.  WIDE (4 x 128) is what an L2-resident table wants: the texture unit's return path is
+     * the limit and every lane helps to cover the gather latency.  A table far larger than the L2 (C5: 4 GiB) behaves the
+     * other way round once the paths of a warp have scattered apart: a path re-gathers its whole 4x4x4 block on every cell
+     * change and three quarters of it are the previous block, which only the L1 can serve; a block occupies ~9.6 128-byte
+     * lines (8 x 4 texels of one layer of the atlas each), so beyond ~200 lanes per SM the L1 thrashes and every gather goes
+     * to DRAM.  Measured on C5, lanes per SM -> G ray steps/s: 32: 2.7, 64: 5.2, 96: 7.3, 128: 9.3, 160: 10.5, 192: 10.0,
+     * 224: 7.6, 256: 6.6, 384: 5.6, 512: 5.4 (profiles/README.md, r06).  NARROW = 5 x 32.  Which of the two a scene wants
+     * is MEASURED, not guessed, and measured again as the frame goes on (the first rounds of a frame are coherent camera
+     * rays, which like WIDE whatever the table): when the table does not fit the L2, four rounds of every 32 alternate
+     * between the two (same mix of paths), and the faster one (ray steps per ms of the step kernel) renders the other 28. */
+    struct StepCfg { unsigned ctas, tpb; bool spec; };
+    /* the prefetching variant exists for the tricubic atlas without an SDF container (the C5 class of scenes) */
+    const bool specOk = m->rif->mode == MER_RIF_TRICUBIC && !m->dev.rif.coeff8 && m->dev.shapeType != MER_SHAPE_SDF;
+    const StepCfg stepCfgs[2] = {{(unsigned) MER_RENDER_MIN_BLOCKS, TPB, false}, {5u, 32u, specOk}};
+    StepCfg stepFixed = stepCfgs[0];
+    bool stepEnv = false;
+    if (const char *e = getenv("MER_STEP_CTAS")) { stepFixed.ctas = (unsigned) std::min(std::max(atoi(e), 1), 16); stepEnv = true; } /* tuning knobs */
+    if (const char *e = getenv("MER_STEP_TPB")) { stepFixed.tpb = (unsigned) std::min(std::max(atoi(e) / 32 * 32, 32), (int) TPB); stepEnv = true; }
+    if (const char *e = getenv("MER_STEP_SPEC")) { stepFixed.spec = atoi(e) != 0 && specOk; stepEnv = true; if (stepFixed.spec) stepFixed.tpb = 32u; }
+    if (stepFixed.ctas * stepFixed.tpb > (unsigned) MER_RENDER_MIN_BLOCKS * TPB) stepFixed.ctas = (unsigned) MER_RENDER_MIN_BLOCKS * TPB / stepFixed.tpb;
+    int l2Bytes = 0;
+    cudaDeviceGetAttribute(&l2Bytes, cudaDevAttrL2CacheSize, m->device);
+    const size_t tableBytes = (size_t) m->dev.rif.N[0] * m->dev.rif.N[1] * m->dev.rif.N[2] * (m->rif->mode == MER_RIF_TRICUBIC ? (m->dev.rif.coeff8 ? 32u : 4u) : 16u);
+    bool tuning = !stepEnv && !P.nee && tableBytes > (size_t) std::max(l2Bytes, 1);
+    if (const char *e = getenv("MER_STEP_TUNE")) tuning = atoi(e) != 0 && !P.nee && !stepEnv;
+    /* probes: four rounds (wide, narrow, wide, narrow) starting at probeAt; decided at the next look at the pool; the gap to
+     * the next probe doubles (32 -> 512 rounds) every time the comparison confirms the current choice */
+    unsigned long long probeAt = 9, probeGap = 32;
+    auto probe_of = [&](unsigned long long round) -> int { /* -1: not a probe round, else the candidate it runs */
+        if (!tuning || round < probeAt || round >= probeAt + 4) return -1;
+        return (int) ((round - probeAt) & 1ull);
+    };
+    bool maxL1 = true;
+    if (const char *e = getenv("MER_STEP_MAXL1")) maxL1 = atoi(e) != 0; /* tuning knob */
+    int stepChoice = 0; /* index into stepCfgs */
+    double tuneSteps[2] = {0.0, 0.0}, tuneMs[2] = {0.0, 0.0};
+    unsigned long long roundsWith[2] = {0, 0};
+    unsigned long long stepsSeen = 0; /* the device's step counter at the end of the previous step launch */
+    int ringCfg[RenderScratch::RING];
     int syncEvery = 8; /* rounds between two looks at the live-slot counter (a host synchronisation) */
     if (const char *e = getenv("MER_SYNC_EVERY")) syncEvery = std::max(atoi(e), 1);
 
@@ -1406,6 +1455,12 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         for (int i = 0; i < ringUsed; i++) {
             float ms = 0.0f;
             if (cudaEventElapsedTime(&ms, S.ring[2 * i], S.ring[2 * i + 1]) == cudaSuccess) stepMs += ms;
+            const unsigned long long seen = S.hostPinned[4 + i];
+            if (ringCfg[i] >= 0) { /* a round of the tuning window */
+                tuneSteps[ringCfg[i]] += (double) (seen - stepsSeen);
+                tuneMs[ringCfg[i]] += ms;
+            }
+            stepsSeen = seen;
         }
         ringUsed = 0;
     };
@@ -1461,29 +1516,54 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         }
         /* ---- steps: every slot whose path can */
         if (ringUsed == RenderScratch::RING) { MER_CUDA(cudaStreamSynchronize(stream)); drain_ring(); }
+        const int probe = probe_of(rounds);
+        const StepCfg cfg = stepEnv ? stepFixed : stepCfgs[probe >= 0 ? probe : stepChoice];
+        ringCfg[ringUsed] = probe;
+        roundsWith[probe >= 0 ? probe : stepChoice]++;
+        const unsigned stepBlocks = std::min((unsigned) sms * cfg.ctas, (pool + cfg.tpb - 1) / cfg.tpb), stepTpb = cfg.tpb;
         MER_CUDA(cudaEventRecord(S.ring[2 * ringUsed], stream));
+#define MER_STEP_K(K_)                                                                                                   \
+    do { /* no shared memory in the step kernel: the whole 256 KB of the SM's array as L1 (what the narrow configuration lives on) */ \
+        if (maxL1) cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);  \
+        MER_LAUNCH(K_, stepBlocks, stepTpb, 0, stream, P);                                                               \
+    } while (0)
 #define MER_STEP(MODE_, L_, T_, S_)                                                                                      \
     do {                                                                                                                 \
-        if (xform) MER_LAUNCH((k_step<MODE_, L_, T_, S_, true>), stepBlocks, TPB, 0, stream, P);                         \
-        else MER_LAUNCH((k_step<MODE_, L_, T_, S_, false>), stepBlocks, TPB, 0, stream, P);                              \
+        if (xform) MER_STEP_K((k_step<MODE_, L_, T_, S_, true>)); else MER_STEP_K((k_step<MODE_, L_, T_, S_, false>));    \
     } while (0)
 #define MER_STEP2(L_)                                                                                                    \
     do {                                                                                                                 \
         if (sdfShape) { if (extras) MER_STEP(MER_RIF_TRICUBIC, L_, true, true); else MER_STEP(MER_RIF_TRICUBIC, L_, false, true); }    \
         else { if (extras) MER_STEP(MER_RIF_TRICUBIC, L_, true, false); else MER_STEP(MER_RIF_TRICUBIC, L_, false, false); }           \
     } while (0)
-        if (packed) { if (extras) MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, true, false); else MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, false, false); }
+        if (cfg.spec) { /* tricubic, atlas, analytic container: checked where the candidates are set up */
+            if (extras) { if (xform) MER_STEP_K((k_step<MER_RIF_TRICUBIC, 0, true, false, true, true>)); else MER_STEP_K((k_step<MER_RIF_TRICUBIC, 0, true, false, false, true>)); }
+            else { if (xform) MER_STEP_K((k_step<MER_RIF_TRICUBIC, 0, false, false, true, true>)); else MER_STEP_K((k_step<MER_RIF_TRICUBIC, 0, false, false, false, true>)); }
+        }
+        else if (packed) { if (extras) MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, true, false); else MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, false, false); }
         else if (m->dev.rif.coeff8) MER_STEP2(1);
         else MER_STEP2(0);
+#undef MER_STEP_K
 #undef MER_STEP2
 #undef MER_STEP
         MER_CUDA(cudaEventRecord(S.ring[2 * ringUsed + 1], stream));
+        MER_CUDA(cudaMemcpyAsync(S.hostPinned + 4 + ringUsed, P.stats + ST_STEPS, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         ringUsed++;
         launches++;
         stepLaunches++;
         if (look && !P.nee) {
             MER_CUDA(cudaStreamSynchronize(stream));
             drain_ring();
+            if (tuning && tuneMs[0] > 0.0 && tuneMs[1] > 0.0 && rounds >= probeAt + 3) {
+                /* both candidates have rendered two rounds of the same mix of paths; 3 % of hysteresis */
+                const double wide = tuneSteps[0] / tuneMs[0], narrow = tuneSteps[1] / tuneMs[1];
+                const int before = stepChoice;
+                if (narrow > 1.03 * wide) stepChoice = 1;
+                else if (wide > 1.03 * narrow) stepChoice = 0;
+                probeGap = stepChoice == before ? std::min(probeGap * 2ull, 512ull) : 32ull;
+                probeAt = rounds + probeGap;
+                tuneSteps[0] = tuneSteps[1] = tuneMs[0] = tuneMs[1] = 0.0;
+            }
             if (*(unsigned *) S.hostPinned == 0u) break;
             if (!tailMarked && *(unsigned *) S.hostPinned < pool / 2u) {
                 MER_CUDA(cudaEventRecord(S.evTail, stream));
@@ -1520,6 +1600,8 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         stats_out->step_launches = stepLaunches;
         if (tailMarked) cudaEventElapsedTime(&stats_out->tail_ms, S.evTail, S.ev1);
         stats_out->block_fetches = hs[1 + ST_FETCH];
+        const int most = roundsWith[1] > roundsWith[0] ? 1 : 0; /* the configuration most rounds ran with */
+        stats_out->step_lanes_per_sm = stepEnv ? stepFixed.ctas * stepFixed.tpb : stepCfgs[most].ctas * stepCfgs[most].tpb;
         float ms = 0;
         cudaEventElapsedTime(&ms, S.ev0, S.ev1);
         stats_out->device_ms = ms;

@@ -1533,13 +1533,62 @@ void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, cons
         float cosT, Fr = fresnelDielectricExt(-C.exit.cosI, cosT, C.exit.nb);
         scale *= (1.0f - Fr) * (C.exit.nb * C.exit.nb);
     }
-    const float geom = cosY * area / spread;
+    float geom = cosY * area / spread;
+    if (R.direct_connections == 2) { /* miWeight(pdf_emitter, pdf_phase), volpath.cpp:137-141, 430-433: both per solid angle at p1 */
+        const float pNee = 1.0f / std::max(geom, 1e-30f);
+        geom *= (pNee * pNee) / std::max(pNee * pNee + phase * phase, 1e-30f);
+    }
     float rad[3];
     for (int c = 0; c < 3; c++) {
         float T = (float) std::exp((double) (M.density ? -C.exit.tau : M.sigmaT[c] * (float) (-C.dist)));
         rad[c] = thr[c] * phase * T * (float) C.weight * scale * R.quad_radiance[c] * geom;
     }
     L.add(pathLength + (float) C.opticalDist, rad); /* the connection's optical length: curved part + exterior segment */
+}
+
+/* direct_connections = 2: the power-heuristic weight of a PHASE-sampled path that reached the quad at y after the
+ * scattering vertex p1 (volpath.cpp:164-173, miWeight :430-433).  p_nee, the solid-angle density at p1 with which the
+ * next-event estimator samples y, comes from the same shooting problem solved for y: |d r_perp / d omega| / (Area cos). */
+template <typename F>
+float hitWeight(const Medium<F> &M, const mer_render_desc &R, const F *p1, const float yq[3], float phasePdf, int depth,
+                uint64_t sampleId, Stats &st) {
+    PhiloxStream nrng;
+    nrng.init(R.seed ^ kNeeSalt, sampleId);
+    nrng.ctr[2] = (uint32_t) depth * 64u + 32u; /* second half of the vertex's 256 draws */
+    const float *qu = R.quad_u, *qv = R.quad_v;
+    float Nq[3] = {qu[1] * qv[2] - qu[2] * qv[1], qu[2] * qv[0] - qu[0] * qv[2], qu[0] * qv[1] - qu[1] * qv[0]};
+    const float area = std::sqrt(Nq[0] * Nq[0] + Nq[1] * Nq[1] + Nq[2] * Nq[2]);
+    F y[3], dseed[3];
+    float dl = 0;
+    for (int i = 0; i < 3; i++) {
+        y[i] = (F) yq[i];
+        dseed[i] = (F) (yq[i] - (float) p1[i]);
+        dl += (float) dseed[i] * (float) dseed[i];
+    }
+    dl = 1.0f / std::sqrt(dl);
+    for (int i = 0; i < 3; i++) dseed[i] = (F) ((float) dseed[i] * dl);
+    const bool refract = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
+    const float rrweight = R.connection.rrweight > 0 ? R.connection.rrweight : 1e-2f;
+    const int maxIt = R.connection.max_iterations > 0 ? R.connection.max_iterations : 20;
+    ConnectionResult<F> C;
+    long steps = 0;
+    connect<F>(M, p1, y, dseed, true, rrweight, maxIt, nrng, C, refract, &steps, R.connection.start_mode != MER_START_RANDOM);
+    st.connections++;
+    st.connSteps += steps;
+    if (!C.success || !C.exit.exited || C.exit.tir) return 1.0f; /* next-event estimation cannot produce this point */
+    const F *m = C.J;
+    const F cof[9] = {m[4] * m[8] - m[5] * m[7], m[5] * m[6] - m[3] * m[8], m[3] * m[7] - m[4] * m[6],
+                      m[2] * m[7] - m[1] * m[8], m[0] * m[8] - m[2] * m[6], m[1] * m[6] - m[0] * m[7],
+                      m[1] * m[5] - m[2] * m[4], m[2] * m[3] - m[0] * m[5], m[0] * m[4] - m[1] * m[3]};
+    F ss = 0;
+    for (int i = 0; i < 9; i++) ss += cof[i] * cof[i];
+    const float spread = (float) (C.xnorm * C.xnorm) * (float) std::sqrt(ss);
+    if (!(spread > 0)) return 1.0f;
+    float cosY = 0;
+    for (int i = 0; i < 3; i++) cosY += (float) C.revDirToP1[i] * (Nq[i] / area);
+    cosY = std::abs(cosY);
+    const float pNee = spread / std::max(cosY * area, 1e-20f);
+    return (phasePdf * phasePdf) / std::max(phasePdf * phasePdf + pNee * pNee, 1e-30f);
 }
 
 /* light tracing: where the t = 1 connections of an emitter-side walk are splatted */
@@ -1629,6 +1678,9 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
     const bool dielectric = M.d.boundary == MER_BOUNDARY_HDIELECTRIC;
     const bool nee = R.direct_connections != 0 && R.has_quad;
     bool covered = false; /* the quad's light along the current edge chain was already estimated by a direct connection */
+    const bool mis = nee && R.direct_connections == 2;
+    F vertex[3] = {0, 0, 0}; /* mis: the last scattering vertex and the density its outgoing direction was sampled with */
+    float phasePdf = 0.0f;
     float tBox, tQuad;
     bool hitBox = M.enterShape(o, dcam, tBox);
     bool hitQuad = !light && intersectQuad(R, o, dcam, tQuad);
@@ -1649,13 +1701,18 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
     for (int i = 0; i < 3; i++) { p[i] = (F) (o[i] + tBox * dcam[i]); dir[i] = (F) dcam[i]; }
 
     /* straight escape from point q in direction e: emitters are gathered by hitting them */
-    auto escape = [&](const float q[3], const float e[3]) {
+    auto escape = [&](const float q[3], const float e[3], int vertexDepth) {
         if (light) return; /* a light path that leaves deposits nothing */
         float tq;
         const bool hitsQuad = intersectQuad(R, q, e, tq);
-        if (hitsQuad && covered) return;
+        float k = 1.0f;
+        if (hitsQuad && covered) {
+            if (!mis) return;
+            const float yq[3] = {q[0] + tq * e[0], q[1] + tq * e[1], q[2] + tq * e[2]};
+            k = hitWeight<F>(M, R, vertex, yq, phasePdf, vertexDepth, sampleId, st);
+        }
         const float *Le = hitsQuad ? R.quad_radiance : R.env_radiance;
-        const float rad[3] = {thr[0] * Le[0], thr[1] * Le[1], thr[2] * Le[2]};
+        const float rad[3] = {thr[0] * Le[0] * k, thr[1] * Le[1] * k, thr[2] * Le[2] * k};
         L.add(hitsQuad ? (float) opl + tq : std::numeric_limits<float>::infinity(), rad);
     };
     /* Russian roulette of volpath.cpp:326-336 (eta = product of the BSDFs' relative indices) */
@@ -1672,7 +1729,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         float pf[3] = {(float) p[0], (float) p[1], (float) p[2]}, df[3] = {(float) dir[0], (float) dir[1], (float) dir[2]};
         if (!dielectric) { /* null BSDF: depth++ and `continue` without RR (volpath.cpp:287-296) */
             depth++;
-            if (!fromOutside) escape(pf, df);
+            if (!fromOutside) escape(pf, df, depth - 1);
             return fromOutside;
         }
         float N[3], dOut[3], w, es;
@@ -1692,7 +1749,7 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
         for (int i = 0; i < 3; i++) dir[i] = (F) dOut[i];
         bool inside = fromOutside ? transmitted : !transmitted;
         if (inside) covered = false; /* an internal reflection starts a chain no direct connection accounts for */
-        if (!inside) { escape(pf, dOut); return false; } /* rayIntersectAndLookForEmitter with a delta BSDF: weight 1 */
+        if (!inside) { escape(pf, dOut, depth); return false; } /* rayIntersectAndLookForEmitter with a delta BSDF: weight 1 */
         return roulette();
     };
 
@@ -1796,6 +1853,10 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             }
             float u1 = rng.next(), u2 = rng.next();
             hg_sample(M.d.hg_g, wi, u1, u2, wo);
+            if (mis) { /* HGPhaseFunction::sample returns the value = the pdf (hg.cpp:100-105) */
+                phasePdf = hg_eval(M.d.hg_g, wi, wo);
+                for (int i = 0; i < 3; i++) vertex[i] = p[i];
+            }
             for (int i = 0; i < 3; i++) dir[i] = (F) wo[i];
             if (!roulette()) return;
         } else {

@@ -61,7 +61,7 @@ class RenderStats(C.Structure):
                 ("nonfinite_dropped", C.c_uint64), ("passes", C.c_uint64), ("connections", C.c_uint64),
                 ("connections_failed", C.c_uint64), ("connection_steps", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_float), ("step_kernel_ms", C.c_float), ("step_launches", C.c_uint64), ("tail_ms", C.c_float),
-                ("block_fetches", C.c_uint64)]
+                ("block_fetches", C.c_uint64), ("step_lanes_per_sm", C.c_uint32), ("reserved0", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -119,7 +119,7 @@ def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_s
         r.quad_u[:] = q["u"]
         r.quad_v[:] = q["v"]
         r.quad_radiance[:] = q["radiance"]
-    r.direct_connections = 1 if direct_connections else 0
+    r.direct_connections = 2 if direct_connections == "mis" else (1 if direct_connections else 0)
     r.light_tracing = 1 if light_tracing else 0
     props = props or {}
     r.connection.tol2 = float(props.get("tol2", 1e-6))

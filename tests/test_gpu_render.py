@@ -128,6 +128,23 @@ def test_sample_sharding_adds_up(oracle32):
     assert st2["ray_steps"] == st["ray_steps"] and np.allclose(other, full, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("env", [{"MER_STEP_SPEC": "1", "MER_STEP_CTAS": "5"}, {"MER_STEP_CTAS": "2", "MER_STEP_TPB": "96"}, {"MER_STEP_TUNE": "1"}])
+def test_step_kernel_configurations_render_the_same_paths(oracle32, env, monkeypatch):
+    """the step kernel's lanes per SM and its prefetching variant (the narrow configuration the in-run tuner picks for tables
+    far larger than the L2) are scheduling only: same paths, same step and block counts, same film"""
+    med, omed, keep = setup(oracle32, "radial", 32, medium_props(stepsize=2e-2))
+    scene = scene_dict(48, 40, 16, rfilter="gaussian")
+    integ = mer.EikonalVolPathIntegrator(stepsPerPass=16, poolPaths=4096)  # short visits: many rounds, so the tuner probes
+    full, st = integ.render(scene, med)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    other, st2 = integ.render(scene, med)
+    assert st["step_lanes_per_sm"] == 512 and (st2["step_lanes_per_sm"] == (160 if "MER_STEP_SPEC" in env else 192) or "MER_STEP_TUNE" in env)
+    for k in ("samples", "ray_steps", "block_fetches", "scatter_events", "boundary_exits"):
+        assert st2[k] == st[k], k
+    assert np.allclose(other, full, rtol=1e-5, atol=1e-5)
+
+
 def test_render_multi_two_shards_on_one_device(oracle32):
     """mer_render_multi (the scheduler behind Integrator::render, integrator.cpp:95-127 / renderproc.cpp:142-148): two
     shards of the sample indices rendered by two host threads and reduced — here both on the one GPU a test box has,
@@ -148,6 +165,8 @@ def test_render_multi_two_shards_on_one_device(oracle32):
 def test_render_multi_two_gpus(oracle32, nccl, monkeypatch):
     """one call drives two GPUs (grids replicated, sample indices interleaved, ncclReduce of the film — or, with
     MER_NCCL=0, peer copies) and the film matches the one-GPU film to 1e-5"""
+    import torch  # noqa: F401  the library reduces with the NCCL the process already has; without this import it would load the
+    # system's (older) libnccl.so.2, and a torch imported by a LATER test would be handed that one (same SONAME)
     monkeypatch.setenv("MER_NCCL", nccl)
     props = medium_props(stepsize=2e-2)
     data, lo, hi = make_field("radial", 32)
@@ -293,6 +312,28 @@ def test_direct_connections_agree_with_random_walk(kind, bsdf, shape):
     sigma = np.hypot(mean[True][1], mean[False][1]) / mean[False][0]
     assert abs(ratio) < 4 * sigma + 4e-3, (kind, bsdf, ratio, sigma, mean)
     assert mean[True][1] < mean[False][1]  # and it is the lower-variance estimator
+
+
+@pytest.mark.parametrize("kind,bsdf", [("linear", "null"), ("radial", "hdielectric")])
+def test_mis_connections_match_oracle(oracle32, kind, bsdf):
+    """direct_connections = 2 against the oracle's restatement of volpath's power heuristic (volpath.cpp:120-147, 164-173,
+    430-433) on shared Philox streams: the walk, the connections AND the weight requests of the emitter hits (solved for
+    the hit point, second half of the vertex's NEE stream) agree one by one"""
+    med, rif, props, data, lo, hi = _nee_medium(kind, 1e-2, bsdf)
+    omed = oracle32.medium_create(oracle_medium_desc(props, 0.5), oracle32.rif_create(volume_desc((32,) * 3, lo, hi), data))
+    scene = scene_dict(32, 32, 8, rfilter="box")
+    scene["envRadiance"] = 0.25
+    film, st = mer.EikonalVolPathIntegrator(rrDepth=5, directConnections="mis", poolPaths=512, stepsPerPass=64).render(scene, med)
+    ofilm, ost = oracle32.render(omed, oracle_render_desc(scene, direct_connections="mis", props=props))
+    _, ost1 = oracle32.render(omed, oracle_render_desc(scene, direct_connections=True, props=props))
+    assert ost.connections > ost1.connections + 20  # the hit requests are there
+    assert abs(st["connections"] - ost.connections) <= 0.005 * ost.connections
+    assert abs(st["connections_failed"] - ost.connections_failed) <= 0.02 * ost.connections + 3
+    assert abs(st["connection_steps"] - ost.connection_steps) <= 0.01 * ost.connection_steps
+    assert st["nonfinite_dropped"] == 0
+    a, b = mer.develop(film), oracle32.film_develop(ofilm)
+    assert np.mean(np.abs(a - b) <= 2e-3 * np.maximum(b, 1.0)) > 0.97
+    assert abs(a.mean() - b.mean()) <= 2e-3 * b.mean()
 
 
 @pytest.mark.parametrize("kind,bsdf,shape", [("linear", "null", ("box", BOX_MIN, BOX_MAX)), ("sd", "hdielectric", ("box", BOX_MIN, BOX_MAX))])

@@ -319,13 +319,18 @@ def test_oracle_direct_connections_agree_with_random_walk(oracle32):
     med = oracle32.medium_create(oracle_medium_desc(props, 0.5), orif)
     scene = scene_dict(64, 64, 12, rfilter="box", quad=True)
     scene["envRadiance"] = 0.0
-    means = {}
-    for nee in (False, True):
+    means, conn = {}, {}
+    for nee in (False, "mis", True):
         film, st = oracle32.render(med, oracle_render_desc(scene, direct_connections=nee, props=props))
         means[nee] = oracle32.film_develop(film)[..., 0].mean()
+        conn[nee] = st.connections
     assert st.connections > 30000 and st.connections_failed < 0.01 * st.connections
     assert st.connection_steps / st.connections < 4 * (2.5 / 1e-2)  # ~2-3 residual evaluations of ~200 steps each
     assert abs(means[True] / means[False] - 1 + 0.75 * 2.0 * 1e-2) < 0.05, means  # walk noise ~1.5 % at 49k samples
+    # volpath's power heuristic between the two (volpath.cpp:120-147, 164-173, 430-433): same expectation, and the emitter
+    # hits of connected chains asked for their weight (one more solve each)
+    assert conn["mis"] > conn[True]
+    assert min(means[True], means[False]) * 0.97 < means["mis"] < max(means[True], means[False]) * 1.03, means
 
 
 def test_oracle_transient_film(oracle32):
