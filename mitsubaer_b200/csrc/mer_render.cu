@@ -878,13 +878,8 @@ k_event(const __grid_constant__ RenderParams P) {
     if (lane == 0 && live) atomicAdd(P.live, live);
 }
 
-/* SPEC (the narrow configuration, tables far larger than the L2): the lane also gathers the block of the cell the NEXT step
- * is predicted to land in (p + h v / n with the half-kicked velocity: off by h^2 |grad n| / n, ~1e-3 of a cell) into a
- * second set of 64 registers, a whole turn before it is needed, so that two DRAM round trips per lane are in flight
- * instead of one.  The prediction only decides WHICH registers a block is read from: blocks are keyed by their cell, a
- * wrong guess costs the ordinary gather, and the arithmetic of the step is untouched.  One warp per CTA, <= 255 registers. */
-template <int MODE, int LAYOUT, bool EXTRAS, bool SDFSHAPE, bool XFORM, bool SPEC = false>
-__global__ void __launch_bounds__(SPEC ? 32 : MER_STENCIL_BLOCK, SPEC ? 6 : MER_RENDER_MIN_BLOCKS)
+template <int MODE, int LAYOUT, bool EXTRAS, bool SDFSHAPE, bool XFORM>
+__global__ void __launch_bounds__(MER_STENCIL_BLOCK, MER_RENDER_MIN_BLOCKS)
 k_step(const __grid_constant__ RenderParams P) {
     const unsigned lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
     const MediumDev &M = P.M;
@@ -897,8 +892,6 @@ k_step(const __grid_constant__ RenderParams P) {
     int visit = 0;       /* steps left in this visit */
     StencilCache<MODE> S; /* registers only */
     S.invalidate();
-    StencilCache<MODE> N; /* SPEC: the prefetched block */
-    if (SPEC) N.invalidate();
     const float h = M.h;
     bool exhausted = false; /* warp-uniform: the round's slots are all handed out */
     unsigned nSteps = 0, nFetch = 0;
@@ -938,14 +931,8 @@ k_step(const __grid_constant__ RenderParams P) {
             c = rif_cell<MODE, XFORM>(M.rif, L.p);
             if (rif_cell_fast<MODE>(M.rif, c)) {
                 if (!stencil_has(S, c)) {
-                    if (SPEC && stencil_has(N, c)) S = N; /* requested a turn ago */
-                    else rif_fetch_interior<LAYOUT>(M.rif, S, c.i, c.j, c.k);
+                    rif_fetch_interior<LAYOUT>(M.rif, S, c.i, c.j, c.k);
                     nFetch++;
-                }
-                if (SPEC) { /* the block the next step will most likely need */
-                    const float r = __fdividef(h, L.n);
-                    const CellPos cn = rif_cell<MODE, XFORM>(M.rif, f3(fmaf(r, L.v.x, L.p.x), fmaf(r, L.v.y, L.p.y), fmaf(r, L.v.z, L.p.z)));
-                    if (!stencil_has(S, cn) && !stencil_has(N, cn) && rif_cell_fast<MODE>(M.rif, cn)) rif_fetch_interior<LAYOUT>(M.rif, N, cn.i, cn.j, cn.k);
                 }
                 step = true;
             } else { /* the stencil touches the edge of the grid: a step for the event kernel */
@@ -1409,21 +1396,22 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
      * the limit and every lane helps to cover the gather latency.  A table far larger than the L2 (C5: 4 GiB) behaves the
      * other way round once the paths of a warp have scattered apart: a path re-gathers its whole 4x4x4 block on every cell
      * change and three quarters of it are the previous block, which only the L1 can serve; a block occupies ~9.6 128-byte
-     * lines (8 x 4 texels of one layer of the atlas each), so beyond ~200 lanes per SM the L1 thrashes and every gather goes
-     * to DRAM.  Measured on C5, lanes per SM -> G ray steps/s: 32: 2.7, 64: 5.2, 96: 7.3, 128: 9.3, 160: 10.5, 192: 10.0,
-     * 224: 7.6, 256: 6.6, 384: 5.6, 512: 5.4 (profiles/README.md, r06).  NARROW = 5 x 32.  Which of the two a scene wants
-     * is MEASURED, not guessed, and measured again as the frame goes on (the first rounds of a frame are coherent camera
-     * rays, which like WIDE whatever the table): when the table does not fit the L2, four rounds of every 32 alternate
-     * between the two (same mix of paths), and the faster one (ray steps per ms of the step kernel) renders the other 28. */
-    struct StepCfg { unsigned ctas, tpb; bool spec; };
-    /* the prefetching variant exists for the tricubic atlas without an SDF container (the C5 class of scenes) */
-    const bool specOk = m->rif->mode == MER_RIF_TRICUBIC && !m->dev.rif.coeff8 && m->dev.shapeType != MER_SHAPE_SDF;
-    const StepCfg stepCfgs[2] = {{(unsigned) MER_RENDER_MIN_BLOCKS, TPB, false}, {5u, 32u, specOk}};
+     * lines (8 x 4 texels of one layer of the atlas each), so beyond ~200 lanes per SM the L1 thrashes, every gather goes to
+     * L2 / DRAM and the texture unit's miss queue backs up (tex_throttle 74 % of the stall samples).  Measured on C5, lanes per
+     * SM -> G ray steps/s: 32: 2.7, 64: 5.2, 96: 7.3, 128: 9.3, 160: 10.5-10.8, 192: 10.0, 224: 7.6, 256: 6.6, 384: 5.6,
+     * 512: 5.4 (profiles/r02_c5_lanes_sweep.json).  NARROW = 5 x 32; at 10.8 G steps/s the gathers return 2.7 TB/s, 0.76 of
+     * what the same texture path delivers from the L2-resident C2 table: the narrow configuration is texture-bound again.
+     * Which of the two a scene wants is MEASURED, not guessed, and measured again as the frame goes on (the first rounds
+     * of a frame are coherent camera rays, which like WIDE whatever the table): when the table does not fit the L2, four
+     * probe rounds (wide, narrow, wide, narrow: the same mix of paths) are compared by ray steps per ms of the step kernel
+     * and the faster one renders on; the gap to the next probe doubles (32 -> 512 rounds) while the comparison keeps
+     * confirming the choice.  C3 (512^3, h = pitch / 2) stays WIDE: 61.3 vs 40.4 M samples/s. */
+    struct StepCfg { unsigned ctas, tpb; };
+    const StepCfg stepCfgs[2] = {{(unsigned) MER_RENDER_MIN_BLOCKS, TPB}, {5u, 32u}};
     StepCfg stepFixed = stepCfgs[0];
     bool stepEnv = false;
     if (const char *e = getenv("MER_STEP_CTAS")) { stepFixed.ctas = (unsigned) std::min(std::max(atoi(e), 1), 16); stepEnv = true; } /* tuning knobs */
     if (const char *e = getenv("MER_STEP_TPB")) { stepFixed.tpb = (unsigned) std::min(std::max(atoi(e) / 32 * 32, 32), (int) TPB); stepEnv = true; }
-    if (const char *e = getenv("MER_STEP_SPEC")) { stepFixed.spec = atoi(e) != 0 && specOk; stepEnv = true; if (stepFixed.spec) stepFixed.tpb = 32u; }
     if (stepFixed.ctas * stepFixed.tpb > (unsigned) MER_RENDER_MIN_BLOCKS * TPB) stepFixed.ctas = (unsigned) MER_RENDER_MIN_BLOCKS * TPB / stepFixed.tpb;
     int l2Bytes = 0;
     cudaDeviceGetAttribute(&l2Bytes, cudaDevAttrL2CacheSize, m->device);
@@ -1536,11 +1524,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         if (sdfShape) { if (extras) MER_STEP(MER_RIF_TRICUBIC, L_, true, true); else MER_STEP(MER_RIF_TRICUBIC, L_, false, true); }    \
         else { if (extras) MER_STEP(MER_RIF_TRICUBIC, L_, true, false); else MER_STEP(MER_RIF_TRICUBIC, L_, false, false); }           \
     } while (0)
-        if (cfg.spec) { /* tricubic, atlas, analytic container: checked where the candidates are set up */
-            if (extras) { if (xform) MER_STEP_K((k_step<MER_RIF_TRICUBIC, 0, true, false, true, true>)); else MER_STEP_K((k_step<MER_RIF_TRICUBIC, 0, true, false, false, true>)); }
-            else { if (xform) MER_STEP_K((k_step<MER_RIF_TRICUBIC, 0, false, false, true, true>)); else MER_STEP_K((k_step<MER_RIF_TRICUBIC, 0, false, false, false, true>)); }
-        }
-        else if (packed) { if (extras) MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, true, false); else MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, false, false); }
+        if (packed) { if (extras) MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, true, false); else MER_STEP(MER_RIF_TRILINEAR_PACKED, 0, false, false); }
         else if (m->dev.rif.coeff8) MER_STEP2(1);
         else MER_STEP2(0);
 #undef MER_STEP_K

@@ -128,10 +128,10 @@ def test_sample_sharding_adds_up(oracle32):
     assert st2["ray_steps"] == st["ray_steps"] and np.allclose(other, full, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("env", [{"MER_STEP_SPEC": "1", "MER_STEP_CTAS": "5"}, {"MER_STEP_CTAS": "2", "MER_STEP_TPB": "96"}, {"MER_STEP_TUNE": "1"}])
+@pytest.mark.parametrize("env", [{"MER_STEP_CTAS": "5", "MER_STEP_TPB": "32"}, {"MER_STEP_CTAS": "2", "MER_STEP_TPB": "96"}, {"MER_STEP_TUNE": "1"}])
 def test_step_kernel_configurations_render_the_same_paths(oracle32, env, monkeypatch):
-    """the step kernel's lanes per SM and its prefetching variant (the narrow configuration the in-run tuner picks for tables
-    far larger than the L2) are scheduling only: same paths, same step and block counts, same film"""
+    """the step kernel's lanes per SM (the narrow configuration the in-run tuner picks for tables far larger than the L2) are
+    scheduling only: same paths, same step and block counts, same film"""
     med, omed, keep = setup(oracle32, "radial", 32, medium_props(stepsize=2e-2))
     scene = scene_dict(48, 40, 16, rfilter="gaussian")
     integ = mer.EikonalVolPathIntegrator(stepsPerPass=16, poolPaths=4096)  # short visits: many rounds, so the tuner probes
@@ -139,7 +139,7 @@ def test_step_kernel_configurations_render_the_same_paths(oracle32, env, monkeyp
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     other, st2 = integ.render(scene, med)
-    assert st["step_lanes_per_sm"] == 512 and (st2["step_lanes_per_sm"] == (160 if "MER_STEP_SPEC" in env else 192) or "MER_STEP_TUNE" in env)
+    assert st["step_lanes_per_sm"] == 512 and (st2["step_lanes_per_sm"] == int(env.get("MER_STEP_CTAS", 0)) * int(env.get("MER_STEP_TPB", 0)) or "MER_STEP_TUNE" in env)
     for k in ("samples", "ray_steps", "block_fetches", "scatter_events", "boundary_exits"):
         assert st2[k] == st[k], k
     assert np.allclose(other, full, rtol=1e-5, atol=1e-5)
