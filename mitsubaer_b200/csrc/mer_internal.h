@@ -50,6 +50,10 @@ struct RenderScratch {
     unsigned long long *hostPinned = nullptr;
     void *paramsDev = nullptr, *paramsHost = nullptr; /* RenderParams of the pass in flight (global copy + pinned staging) */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evTail = nullptr;
+    /* the step kernel's configuration the last frame on this device settled on, and the table it was measured on: the next
+     * frame of the same scene starts from it instead of measuring from scratch */
+    int stepChoice = 0;
+    size_t stepChoiceTable = 0;
     enum { RING = 32 };
     cudaEvent_t ring[2 * RING] = {nullptr}; /* event pairs around the step kernel's launches (mer_render_stats.step_kernel_ms) */
     void release() {

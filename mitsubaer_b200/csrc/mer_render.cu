@@ -1420,14 +1420,14 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     if (const char *e = getenv("MER_STEP_TUNE")) tuning = atoi(e) != 0 && !P.nee && !stepEnv;
     /* probes: four rounds (wide, narrow, wide, narrow) starting at probeAt; decided at the next look at the pool; the gap to
      * the next probe doubles (32 -> 512 rounds) every time the comparison confirms the current choice */
-    unsigned long long probeAt = 9, probeGap = 32;
+    unsigned long long probeAt = 5, probeGap = 32;
     auto probe_of = [&](unsigned long long round) -> int { /* -1: not a probe round, else the candidate it runs */
         if (!tuning || round < probeAt || round >= probeAt + 4) return -1;
         return (int) ((round - probeAt) & 1ull);
     };
     bool maxL1 = true;
     if (const char *e = getenv("MER_STEP_MAXL1")) maxL1 = atoi(e) != 0; /* tuning knob */
-    int stepChoice = 0; /* index into stepCfgs */
+    int stepChoice = (tuning && S.stepChoiceTable == tableBytes) ? S.stepChoice : 0; /* index into stepCfgs */
     double tuneSteps[2] = {0.0, 0.0}, tuneMs[2] = {0.0, 0.0};
     unsigned long long roundsWith[2] = {0, 0};
     unsigned long long stepsSeen = 0; /* the device's step counter at the end of the previous step launch */
@@ -1564,6 +1564,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     }
     MER_CUDA(cudaEventRecord(S.ev1, stream));
     MER_CUDA(cudaEventSynchronize(S.ev1));
+    if (tuning) { S.stepChoice = stepChoice; S.stepChoiceTable = tableBytes; }
     if (stats_out) {
         unsigned long long hs[1 + ST_COUNT];
         MER_CUDA(cudaMemcpy(hs, S.counters, sizeof(hs), cudaMemcpyDeviceToHost));
