@@ -208,6 +208,139 @@ class RefPhase:
         return F, ct
 
 
+class RefTrace:
+    """The reference's stepper — er_step, trace, aggressive_trace, traceTillBoundary, insideShape (= hackForSphere: a
+    hard-coded sphere) of src/medium/heterogeneousrefractive.cpp and SplineDataSource's lookup wrappers of
+    src/volume/splinevolume.cpp — compiled verbatim (oracle/ref_trace.cpp -> oracle/_ref/libmer_reftrace.so), FLOAT = float."""
+
+    def __init__(self, data, bmin, bmax, stepsize):
+        path = os.path.join(REF_DIR, "libmer_reftrace.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.ref_medium_create.restype = C.c_void_p
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        N = (C.c_int * 3)(data.shape[2], data.shape[1], data.shape[0])  # arrays are [z][y][x]
+        lo = (C.c_float * 3)(*[float(v) for v in bmin])
+        hi = (C.c_float * 3)(*[float(v) for v in bmax])
+        self.h = C.c_void_p(self.lib.ref_medium_create(_ptr(data, C.c_float), N, lo, hi, C.c_float(stepsize)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_medium_free(self.h)
+            self.h = None
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(REF_DIR, "libmer_reftrace.so"))
+
+    def container(self):
+        """(centre, radius) of the sphere the compiled insideShape() tests against"""
+        cr = (C.c_float * 4)()
+        self.lib.ref_medium_container(cr)
+        return np.array(cr[:3], np.float32), float(np.float32(cr[3]))
+
+    @staticmethod
+    def _pv(p, v):
+        return (np.array(p, dtype=np.float32, order="C", copy=True).reshape(-1, 3),
+                np.array(v, dtype=np.float32, order="C", copy=True).reshape(-1, 3))
+
+    def value_gradient(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        f, g = np.zeros(p.shape[0], np.float32), np.zeros_like(p)
+        self.lib.ref_rif_value_gradient(self.h, C.c_size_t(p.shape[0]), _ptr(p, C.c_float), _ptr(f, C.c_float), _ptr(g, C.c_float))
+        return f, g
+
+    def inside_limits(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(p.shape[0], np.int32)
+        self.lib.ref_rif_inside_limits(self.h, C.c_size_t(p.shape[0]), _ptr(p, C.c_float), _ptr(out, C.c_int))
+        return out.astype(bool)
+
+    def inside_shape(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(p.shape[0], np.int32)
+        self.lib.ref_inside_shape(self.h, C.c_size_t(p.shape[0]), _ptr(p, C.c_float), _ptr(out, C.c_int))
+        return out.astype(bool)
+
+    def er_step(self, p, v, stepsize, opl=None):
+        p, v = self._pv(p, v)
+        n = p.shape[0]
+        h = np.ascontiguousarray(np.broadcast_to(np.asarray(stepsize, np.float32), (n,)), dtype=np.float32)
+        o = np.zeros(n, np.float32) if opl is None else np.array(opl, dtype=np.float32, copy=True)
+        self.lib.ref_er_step(self.h, C.c_size_t(n), _ptr(p, C.c_float), _ptr(v, C.c_float), _ptr(h, C.c_float), _ptr(o, C.c_float))
+        return p, v, o
+
+    def trace(self, p, v, dist):
+        """-> p, v, distSurf, opticalDistance, success  (trace(), heterogeneousrefractive.cpp:671-691)"""
+        p, v = self._pv(p, v)
+        n = p.shape[0]
+        d = np.ascontiguousarray(dist, dtype=np.float32).reshape(-1)
+        ds, o, ok = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        self.lib.ref_trace(self.h, C.c_size_t(n), _ptr(p, C.c_float), _ptr(v, C.c_float), _ptr(d, C.c_float), _ptr(ds, C.c_float),
+                           _ptr(o, C.c_float), _ptr(ok, C.c_int))
+        return p, v, ds, o, ok.astype(bool)
+
+    def trace_till_boundary(self, p, v):
+        """-> p, v, distSurf, opticalDistance  (traceTillBoundary(), :742-776)"""
+        p, v = self._pv(p, v)
+        n = p.shape[0]
+        ds, o = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self.lib.ref_trace_till_boundary(self.h, C.c_size_t(n), _ptr(p, C.c_float), _ptr(v, C.c_float), _ptr(ds, C.c_float), _ptr(o, C.c_float))
+        return p, v, ds, o
+
+    def configure(self, sigma_a, sigma_s, strategy, sampling_density, medium_sampling_weight, sdf=None, sdf_min=None, sdf_max=None,
+                  aggressive=False):
+        """the members the constructor resolves from the properties (heterogeneousrefractive.cpp:201-300), handed over resolved;
+        strategy: "balance" | "single" | "manual" | "maximum"; sdf: optional signed-distance grid [z][y][x] (the `sdf` child)"""
+        sa = (C.c_float * 3)(*[float(x) for x in np.broadcast_to(np.asarray(sigma_a, np.float32), (3,))])
+        ss = (C.c_float * 3)(*[float(x) for x in np.broadcast_to(np.asarray(sigma_s, np.float32), (3,))])
+        st = {"balance": 0, "single": 1, "manual": 2, "maximum": 3}[strategy]
+        if sdf is not None:
+            sdf = np.ascontiguousarray(sdf, dtype=np.float32)
+            N = (C.c_int * 3)(sdf.shape[2], sdf.shape[1], sdf.shape[0])
+            lo = (C.c_float * 3)(*[float(v) for v in sdf_min])
+            hi = (C.c_float * 3)(*[float(v) for v in sdf_max])
+            self.lib.ref_medium_configure(self.h, sa, ss, C.c_int(st), C.c_float(sampling_density), C.c_float(medium_sampling_weight),
+                                          _ptr(sdf, C.c_float), N, lo, hi, C.c_int(1 if aggressive else 0))
+        else:
+            self.lib.ref_medium_configure(self.h, sa, ss, C.c_int(st), C.c_float(sampling_density), C.c_float(medium_sampling_weight),
+                                          None, None, None, None, C.c_int(0))
+        return self
+
+    def sample_distance(self, ro, rd, mint, xi):
+        """Medium::sampleDistance (heterogeneousrefractive.cpp:402-568) over a batch; xi[n][2] replays sampler->next1D()"""
+        ro = np.ascontiguousarray(ro, dtype=np.float32).reshape(-1, 3)
+        rd = np.ascontiguousarray(rd, dtype=np.float32).reshape(-1, 3)
+        n = ro.shape[0]
+        mint = np.ascontiguousarray(np.broadcast_to(np.asarray(mint, dtype=np.float32), (n,)))
+        xi = np.ascontiguousarray(xi, dtype=np.float32).reshape(-1, 2)
+        r = dict(success=np.zeros(n, np.int32), t=np.zeros(n, np.float32), p=np.zeros((n, 3), np.float32), d=np.zeros((n, 3), np.float32),
+                 optical_length=np.zeros(n, np.float32), ref_ratio_sq=np.zeros(n, np.float32), transmittance=np.zeros((n, 3), np.float32),
+                 pdf_success=np.zeros(n, np.float32), pdf_failure=np.zeros(n, np.float32))
+        self.lib.ref_sample_distance(self.h, C.c_size_t(n), _ptr(ro, C.c_float), _ptr(rd, C.c_float), _ptr(mint, C.c_float), _ptr(xi, C.c_float),
+                                     _ptr(r["success"], C.c_int), _ptr(r["t"], C.c_float), _ptr(r["p"], C.c_float), _ptr(r["d"], C.c_float),
+                                     _ptr(r["optical_length"], C.c_float), _ptr(r["ref_ratio_sq"], C.c_float), _ptr(r["transmittance"], C.c_float),
+                                     _ptr(r["pdf_success"], C.c_float), _ptr(r["pdf_failure"], C.c_float))
+        r["success"] = r["success"].astype(bool)
+        return r
+
+    def eval_transmittance(self, mint, maxt):
+        mint = np.ascontiguousarray(mint, dtype=np.float32).reshape(-1)
+        maxt = np.ascontiguousarray(maxt, dtype=np.float32).reshape(-1)
+        out = np.zeros((mint.size, 3), np.float32)
+        self.lib.ref_eval_transmittance(self.h, C.c_size_t(mint.size), _ptr(mint, C.c_float), _ptr(maxt, C.c_float), _ptr(out, C.c_float))
+        return out
+
+    def aggressive_trace(self, p, v, dist):
+        p, v = self._pv(p, v)
+        n = p.shape[0]
+        d = np.ascontiguousarray(dist, dtype=np.float32).reshape(-1)
+        o = np.zeros(n, np.float32)
+        self.lib.ref_aggressive_trace(self.h, C.c_size_t(n), _ptr(p, C.c_float), _ptr(v, C.c_float), _ptr(d, C.c_float), _ptr(o, C.c_float))
+        return p, v, o
+
+
 class Oracle:
     """The restated path (oracle/mer_oracle.cpp) in float (`Float`) or double (-DFLOATDEBUG)."""
 

@@ -1,0 +1,285 @@
+/*
+ * oracle/ref_trace.cpp — TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * Compiles, VERBATIM and from where they lie under /root/reference (nothing is copied into this repo), the stepper of the
+ * hot path:
+ *     src/medium/heterogeneousrefractive.cpp   er_step (both overloads, :653-669), trace (:671-691), aggressive_trace
+ *                                              (:697-704), insideShape / hackForSphere / hackForBox (:707-726),
+ *                                              traceTillBoundary (:742-776), sampleDistance with its aggressive-tracing
+ *                                              loop (:402-568), evalTransmittance (:393-400), enum ESamplingStrategy
+ *     src/medium/maxexp.h                      MaxExpDist (strategy "maximum"), as it is
+ *     src/volume/splinevolume.cpp              SplineDataSource::insideVolumeLimits / value / gradient / valueAndGradient
+ *                                              (:319-360)
+ *     src/libcore/aabb.cpp                     AABB::getCorner (:23-27)
+ * The member-function bodies are cut out of the two .cpp files by oracle/Makefile (awk, by signature) into
+ * oracle/_ref/hetref_extract.inc and oracle/_ref/splinevolume_extract.inc and included into two structs that declare
+ * exactly the data members those bodies use.  Underneath them the reference's own headers are compiled as they are:
+ * include/mitsuba/core/{basisspline,transform,matrix,ray,aabb,vector,point,normal,math,constants,fwd,platform}.h
+ * (oracle/shim_phase stands in for mitsuba.h / stream.h, oracle/shim_trace for the one Boost header matrix.h asks for).
+ * Release flags of the reference: -DSINGLE_PRECISION -DSPECTRUM_SAMPLES=3, so FLOAT = Float = float.
+ *
+ * NOTE the reference's insideShape() is hackForSphere(): a hard-coded sphere, centre (-0.22827, 1.2, 0.152505), radius 0.3,
+ * strict inequality (:707-718).  The parity tests put their medium in exactly that sphere.
+ *
+ * Built into oracle/_ref/libmer_reftrace.so; tests/test_oracle_cpu.py checks the restated er_step / trace /
+ * traceTillBoundary of oracle/mer_oracle.cpp against it bit for bit, tests/golden/trace_ref.npz holds vectors generated
+ * from it (tests/golden/make_trace_golden.py), and tests/test_gpu_medium.py compares the CUDA stepper with it.
+ */
+#include <mitsuba/mitsuba.h>
+namespace mitsuba { using std::endl; }
+#include <mitsuba/core/basisspline.h>
+namespace mitsuba { extern bool solveQuadratic(Float a, Float b, Float c, Float &x0, Float &x1); } /* util.h; bsphere.h mentions it */
+#include <mitsuba/core/aabb.h>
+#include <mitsuba/core/spectrum.h>   /* reference */
+#include <mitsuba/render/sampler.h>  /* oracle/shim_phase: next1D / next2D */
+#include <medium/maxexp.h>           /* reference (src/medium/maxexp.h): MaxExpDist */
+
+namespace mitsuba {
+#include "aabb_extract.inc" /* generated: AABB::getCorner from src/libcore/aabb.cpp */
+
+/* SplineDataSource (src/volume/splinevolume.cpp) reduced to the data members its lookup wrappers use */
+struct RefSplineDataSource {
+    basisspline::Spline<3> m_spline;
+    Transform m_worldToVolume;                 /* toWorld = identity: Transform() */
+    Matrix3x3F m_worldToVolume_Rot, m_worldToVolume_RotT;
+    AABB m_interpolatableLimits;
+    Float m_maxSDFError;
+#include "splinevolume_extract.inc" /* generated: insideVolumeLimits, maxSDFError, value, gradient, valueAndGradient */
+};
+
+/* MediumSamplingRecord (include/mitsuba/render/medium.h:36-108): the data members sampleDistance() writes */
+struct RefHeterogeneousRefractiveMedium;
+struct MediumSamplingRecord {
+    Float t, opticalLength;
+    Point p;
+    Vector d;
+    Float time;
+    Spectrum transmittance, sigmaA, sigmaS;
+    Float pdfSuccess, pdfSuccessRev, pdfFailure;
+    const RefHeterogeneousRefractiveMedium *medium;
+    Float refRatioSq;
+};
+
+/* HeterogeneousRefractiveMedium (src/medium/heterogeneousrefractive.cpp) reduced to what its stepper uses */
+struct RefHeterogeneousRefractiveMedium {
+    RefSplineDataSource *m_rif, *m_SDF;
+    FLOAT m_erstepsize;
+    int m_precision;
+    bool m_aggressiveTracing;
+    Spectrum m_sigmaA, m_sigmaS, m_sigmaT;
+    Float m_samplingDensity, m_mediumSamplingWeight;
+    MaxExpDist *m_maxExpDist;
+#include "hetref_extract.inc" /* generated: enum ESamplingStrategy, evalTransmittance, sampleDistance, er_step x2, trace,
+                                 aggressive_trace, insideShape, hackForSphere, hackForBox, traceTillBoundary */
+    ESamplingStrategy m_strategy;
+};
+
+}
+
+using namespace mitsuba;
+
+extern "C" {
+
+static RefSplineDataSource *make_source(const float *data, const int *N, const float *bmin, const float *bmax);
+
+void *ref_medium_create(const float *data, const int *N, const float *bmin, const float *bmax, float stepsize) {
+    RefSplineDataSource *rif = make_source(data, N, bmin, bmax);
+    RefHeterogeneousRefractiveMedium *m = new RefHeterogeneousRefractiveMedium();
+    m->m_rif = rif;
+    m->m_SDF = rif; /* only its insideVolumeLimits() is asked until ref_medium_configure() gives it a signed distance */
+    m->m_erstepsize = stepsize;
+    m->m_precision = 6;
+    m->m_aggressiveTracing = false;
+    m->m_maxExpDist = NULL;
+    m->m_strategy = RefHeterogeneousRefractiveMedium::ESingle;
+    m->m_samplingDensity = 1;
+    m->m_mediumSamplingWeight = 0.5f;
+    return m;
+}
+
+static RefSplineDataSource *make_source(const float *data, const int *N, const float *bmin, const float *bmax) {
+    RefSplineDataSource *rif = new RefSplineDataSource();
+    FLOAT xmin[3], xmax[3];
+    int n[3];
+    for (int i = 0; i < 3; i++) { xmin[i] = (FLOAT) bmin[i]; xmax[i] = (FLOAT) bmax[i]; n[i] = N[i]; }
+    rif->m_spline.initialize(xmin, xmax, n);
+    /* splinevolume.cpp:280-281 */
+    rif->m_interpolatableLimits = AABB(Point(xmin[0], xmin[1], xmin[2]) + Point( 2.0*rif->m_spline.getStride(0)+Epsilon,  2.0*rif->m_spline.getStride(1)+Epsilon,  2.0*rif->m_spline.getStride(2)+Epsilon),
+                                       Point(xmax[0], xmax[1], xmax[2]) + Point(-2.0*rif->m_spline.getStride(0)-Epsilon, -2.0*rif->m_spline.getStride(1)-Epsilon, -2.0*rif->m_spline.getStride(2)-Epsilon));
+    size_t total = (size_t) N[0] * N[1] * N[2];
+    FLOAT *tmp = new FLOAT[total];
+    for (size_t i = 0; i < total; i++) tmp[i] = (FLOAT) data[i]; /* splinevolume.cpp:284-287 */
+    rif->m_spline.build(tmp);
+    delete[] tmp;
+    /* splinevolume.cpp:282 */
+    rif->m_maxSDFError = std::sqrt( rif->m_spline.getStride(0)*rif->m_spline.getStride(0) + rif->m_spline.getStride(1)*rif->m_spline.getStride(1) + rif->m_spline.getStride(2)*rif->m_spline.getStride(2));
+    rif->m_worldToVolume_Rot.setIdentity();  /* :90-92 with an identity toWorld */
+    rif->m_worldToVolume_RotT.setIdentity();
+    return rif;
+}
+
+/* what the constructor resolves from the properties (heterogeneousrefractive.cpp:201-300), handed over resolved:
+ * strategy 0 balance / 1 single / 2 manual / 3 maximum; sdf may be NULL (then no aggressive tracing) */
+void ref_medium_configure(void *h, const float *sigmaA, const float *sigmaS, int strategy, float samplingDensity, float mediumSamplingWeight,
+                          const float *sdf, const int *N, const float *bmin, const float *bmax, int aggressive) {
+    RefHeterogeneousRefractiveMedium *m = (RefHeterogeneousRefractiveMedium *) h;
+    for (int i = 0; i < 3; i++) { m->m_sigmaA[i] = sigmaA[i]; m->m_sigmaS[i] = sigmaS[i]; }
+    m->m_sigmaT = m->m_sigmaA + m->m_sigmaS; /* :222 */
+    m->m_strategy = (RefHeterogeneousRefractiveMedium::ESamplingStrategy) strategy;
+    m->m_samplingDensity = samplingDensity;
+    m->m_mediumSamplingWeight = mediumSamplingWeight;
+    if (m->m_maxExpDist) { delete m->m_maxExpDist; m->m_maxExpDist = NULL; }
+    if (strategy == 3) { /* :282-286 */
+        std::vector<Float> coeffs(SPECTRUM_SAMPLES);
+        for (int i = 0; i < SPECTRUM_SAMPLES; i++) coeffs[i] = m->m_sigmaT[i];
+        m->m_maxExpDist = new MaxExpDist(coeffs);
+    }
+    if (m->m_SDF != m->m_rif) delete m->m_SDF;
+    m->m_SDF = sdf ? make_source(sdf, N, bmin, bmax) : m->m_rif;
+    m->m_aggressiveTracing = sdf && aggressive;
+}
+
+void ref_medium_free(void *h) {
+    RefHeterogeneousRefractiveMedium *m = (RefHeterogeneousRefractiveMedium *) h;
+    if (m->m_SDF != m->m_rif) delete m->m_SDF;
+    delete m->m_rif;
+    delete m->m_maxExpDist;
+    delete m;
+}
+
+namespace {
+struct ReplaySampler : public mitsuba::Sampler { /* next1D() replays the given numbers in order */
+    const float *xi;
+    int k;
+    mitsuba::Float next1D() { return xi[k++]; }
+    mitsuba::Point2 next2D() { mitsuba::Float a = xi[k++], b = xi[k++]; return mitsuba::Point2(a, b); }
+};
+}
+
+/* sampleDistance (:402-568) over n rays; xi[n][2] are the numbers sampler->next1D() returns, in order */
+void ref_sample_distance(void *h, size_t n, const float *ro, const float *rd, const float *mint, const float *xi, int *success, float *t,
+                         float *p, float *d, float *opticalLength, float *refRatioSq, float *transmittance, float *pdfSuccess,
+                         float *pdfFailure) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < (long) n; i++) {
+        Ray ray(Point(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), Vector(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]), 0.0f);
+        ray.mint = mint[i];
+        MediumSamplingRecord mRec;
+        mRec.t = mRec.opticalLength = mRec.refRatioSq = 0;
+        mRec.pdfSuccess = mRec.pdfSuccessRev = mRec.pdfFailure = 0;
+        ReplaySampler s;
+        s.xi = xi + 2 * i;
+        s.k = 0;
+        success[i] = m->sampleDistance(ray, mRec, &s) ? 1 : 0;
+        t[i] = mRec.t;
+        p[3 * i] = mRec.p.x; p[3 * i + 1] = mRec.p.y; p[3 * i + 2] = mRec.p.z;
+        d[3 * i] = mRec.d.x; d[3 * i + 1] = mRec.d.y; d[3 * i + 2] = mRec.d.z;
+        opticalLength[i] = mRec.opticalLength;
+        refRatioSq[i] = mRec.refRatioSq;
+        for (int c = 0; c < 3; c++) transmittance[3 * i + c] = mRec.transmittance[c];
+        pdfSuccess[i] = mRec.pdfSuccess;
+        pdfFailure[i] = mRec.pdfFailure;
+    }
+}
+
+/* evalTransmittance (:393-400) */
+void ref_eval_transmittance(void *h, size_t n, const float *mint, const float *maxt, float *out) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+    for (size_t i = 0; i < n; i++) {
+        Ray ray(Point(0.0f), Vector(0.0f, 0.0f, 1.0f), 0.0f);
+        ray.mint = mint[i];
+        ray.maxt = maxt[i];
+        Spectrum T = m->evalTransmittance(ray, NULL);
+        for (int c = 0; c < 3; c++) out[3 * i + c] = T[c];
+    }
+}
+
+int ref_medium_sizeof_float(void) { return (int) sizeof(FLOAT); }
+
+/* the hard-coded container: centre and radius as the compiled code has them */
+void ref_medium_container(float *centre_radius) {
+    centre_radius[0] = -0.22827f; centre_radius[1] = 1.2f; centre_radius[2] = 0.152505f; centre_radius[3] = 0.3f;
+}
+
+/* SplineDataSource wrappers over n points */
+void ref_rif_value_gradient(void *h, size_t n, const float *p, float *f, float *g) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+    for (size_t i = 0; i < n; i++) {
+        FLOAT fv;
+        VectorF G;
+        m->m_rif->valueAndGradient(PointF(p[3 * i], p[3 * i + 1], p[3 * i + 2]), fv, G);
+        f[i] = fv;
+        g[3 * i] = G.x; g[3 * i + 1] = G.y; g[3 * i + 2] = G.z;
+    }
+}
+void ref_rif_inside_limits(void *h, size_t n, const float *p, int *out) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+    for (size_t i = 0; i < n; i++) out[i] = m->m_rif->insideVolumeLimits(PointF(p[3 * i], p[3 * i + 1], p[3 * i + 2])) ? 1 : 0;
+}
+void ref_inside_shape(void *h, size_t n, const float *p, int *out) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+    for (size_t i = 0; i < n; i++) out[i] = m->insideShape(PointF(p[3 * i], p[3 * i + 1], p[3 * i + 2])) ? 1 : 0;
+}
+
+/* one er_step with the given step size (in place; opl accumulated) */
+void ref_er_step(void *h, size_t n, float *p, float *v, const float *stepsize, float *opl) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+    for (size_t i = 0; i < n; i++) {
+        PointF P(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        VectorF V(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        FLOAT o = opl[i];
+        m->er_step(P, V, stepsize[i], o);
+        p[3 * i] = P.x; p[3 * i + 1] = P.y; p[3 * i + 2] = P.z;
+        v[3 * i] = V.x; v[3 * i + 1] = V.y; v[3 * i + 2] = V.z;
+        opl[i] = o;
+    }
+}
+
+/* trace (:671-691), in place */
+void ref_trace(void *h, size_t n, float *p, float *v, const float *dist, float *dist_surf, float *opl, int *success) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < (long) n; i++) {
+        PointF P(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        VectorF V(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        FLOAT ds = 0, o = opl[i];
+        success[i] = m->trace(P, V, dist[i], ds, o) ? 1 : 0;
+        p[3 * i] = P.x; p[3 * i + 1] = P.y; p[3 * i + 2] = P.z;
+        v[3 * i] = V.x; v[3 * i + 1] = V.y; v[3 * i + 2] = V.z;
+        dist_surf[i] = ds;
+        opl[i] = o;
+    }
+}
+
+/* traceTillBoundary (:742-776), in place */
+void ref_trace_till_boundary(void *h, size_t n, float *p, float *v, float *dist_surf, float *opl) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long i = 0; i < (long) n; i++) {
+        PointF P(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        VectorF V(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        FLOAT ds = 0, o = opl[i];
+        m->traceTillBoundary(P, V, ds, o);
+        p[3 * i] = P.x; p[3 * i + 1] = P.y; p[3 * i + 2] = P.z;
+        v[3 * i] = V.x; v[3 * i + 1] = V.y; v[3 * i + 2] = V.z;
+        dist_surf[i] = ds;
+        opl[i] = o;
+    }
+}
+
+/* aggressive_trace (:697-704), in place */
+void ref_aggressive_trace(void *h, size_t n, float *p, float *v, const float *dist, float *opl) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+    for (size_t i = 0; i < n; i++) {
+        PointF P(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        VectorF V(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        FLOAT o = opl[i];
+        m->aggressive_trace(P, V, dist[i], o);
+        p[3 * i] = P.x; p[3 * i + 1] = P.y; p[3 * i + 2] = P.z;
+        v[3 * i] = V.x; v[3 * i + 1] = V.y; v[3 * i + 2] = V.z;
+        opl[i] = o;
+    }
+}
+
+} /* extern "C" */

@@ -1,5 +1,6 @@
 /* oracle shim — include/mitsuba/core/stream.h reduced to what vector.h / point.h / frame.h mention. TEST INFRASTRUCTURE ONLY. */
 #pragma once
+#include <cstddef>
 namespace mitsuba {
 class Stream {
 public:
@@ -7,6 +8,8 @@ public:
     template <typename T> void writeElement(T) {}
     float readFloat() { return 0.0f; }
     void writeFloat(float) {}
+    template <typename T> void readArray(T *, size_t) {}        /* matrix.h (ref_trace.cpp) */
+    template <typename T> void writeArray(const T *, size_t) {}
 };
 class InstanceManager {};
 }

@@ -143,3 +143,34 @@ def oracle_render_desc(scene, max_depth=-1, rr_depth=5, sample_begin=0, sample_s
         r.lambda_ = float(tr.get("lambda", 1.0))
         r.phase_deg = float(tr.get("phase", 0.0))
     return r
+
+
+# ---- the reference's own container: insideShape() is hackForSphere(), a hard-coded sphere (heterogeneousrefractive.cpp:707-718)
+REF_SPHERE_CENTRE = np.array([-0.22827, 1.2, 0.152505], np.float32)
+REF_SPHERE_RADIUS = 0.3
+
+
+def ref_sphere_scene(kind, res=40, n_rays=4000, seed=7):
+    """A field on a grid around the reference's hard-coded sphere and rays that start inside it:
+    -> (data[z][y][x], bbox_min, bbox_max, p0, unit directions, distances).  The caller scales the directions by n(p0)."""
+    c = REF_SPHERE_CENTRE.astype(np.float64)
+    lo, hi = fields.padded_bbox(c - 0.32, c + 0.32, (res,) * 3)
+    if kind == "linear":
+        data = fields.linear_rif((res,) * 3, lo, hi)
+    elif kind == "radial":
+        data = fields.radial_rif((res,) * 3, lo, hi)
+    elif kind == "sd":
+        data = fields.rif_from_sd(fields.sphere_sdf((res,) * 3, lo, hi, centre=tuple(c), radius=0.28))
+    else:
+        x = np.linspace(lo[0], hi[0], res)[None, None, :]
+        y = np.linspace(lo[1], hi[1], res)[None, :, None]
+        z = np.linspace(lo[2], hi[2], res)[:, None, None]
+        data = (1.4 + 0.1 * np.sin(9.0 * x + 0.3) * np.cos(7.0 * y) + 0.05 * np.sin(11.0 * z + 5.0 * x * y)).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n_rays, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    q = rng.normal(size=(n_rays, 3))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    p0 = (c + q * (0.95 * REF_SPHERE_RADIUS * rng.random((n_rays, 1)) ** (1 / 3))).astype(np.float32)
+    dist = (0.7 * rng.random(n_rays)).astype(np.float32)  # up to ~1.2 diameters: about half of the rays leave the sphere
+    return data, lo.astype(np.float32), hi.astype(np.float32), p0, d.astype(np.float32), dist

@@ -12,6 +12,12 @@ where /root/reference exists):
       oracle/_ref/libmer_refphase.so): sampled directions, pdfs, frames and Fresnel terms at seeded inputs,
       g in {0.9, -0.3} (data/tests/test_phase.xml:12-21), 0.5, 0 and 1e-5 (the isotropic branch).
 
+  trace_ref.npz
+      src/medium/heterogeneousrefractive.cpp (er_step, trace, traceTillBoundary, insideShape = hackForSphere) and the
+      SplineDataSource wrappers of src/volume/splinevolume.cpp, compiled verbatim (oracle/ref_trace.cpp ->
+      oracle/_ref/libmer_reftrace.so): end states of seeded rays in the reference's hard-coded sphere for four fields
+      (the scenes of tests/common.py:ref_sphere_scene; the inputs are regenerated from the seeds, only outputs are stored).
+
 Usage:  make -C oracle ref && python tests/golden/make_golden.py
 """
 import os
@@ -21,7 +27,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle.oracle import RefPhase, RefSpline  # noqa: E402
+from oracle.oracle import RefPhase, RefSpline, RefTrace  # noqa: E402
 
 
 def main():
@@ -80,6 +86,43 @@ def phase():
     print("wrote phase_ref.npz")
 
 
+TRACE_CASES = (("linear", 2e-3), ("radial", 5e-3), ("sd", 1e-3), ("smooth", 3.3e-3))
+
+
+def trace():
+    sys.path.insert(0, os.path.dirname(HERE))
+    from common import ref_sphere_scene
+    out = {}
+    for kind, h in TRACE_CASES:
+        data, lo, hi, p0, d0, dist = ref_sphere_scene(kind, n_rays=1024)
+        ref = RefTrace(data, lo, hi, h)
+        n0, g0 = ref.value_gradient(p0)
+        v0 = (d0 * n0[:, None]).astype(np.float32)
+        p, v, ds, opl, ok = ref.trace(p0, v0, dist)
+        tp, tv, tds, topl = ref.trace_till_boundary(p0, v0)
+        out.update({kind + "_h": np.float32(h), kind + "_n0": n0, kind + "_g0": g0, kind + "_p": p, kind + "_v": v, kind + "_dist_surf": ds,
+                    kind + "_opl": opl, kind + "_success": ok, kind + "_tb_p": tp, kind + "_tb_v": tv, kind + "_tb_dist_surf": tds,
+                    kind + "_tb_opl": topl, kind + "_data_sum": np.float64(data.astype(np.float64).sum()), kind + "_p0_sum": np.float64(p0.astype(np.float64).sum())})
+    # Medium::sampleDistance (:402-568) and evalTransmittance (:393-400); the media are resolved by the restated oracle (weight,
+    # sampling density), which test_oracle_cpu.py pins bit for bit against this very library
+    from test_oracle_cpu import SAMPLE_DISTANCE_CASES, _sample_distance_scene
+    from common import oracle_medium_desc
+    from oracle.oracle import Oracle, volume_desc
+    orc = Oracle(np.float32)
+    for strategy, aggressive in SAMPLE_DISTANCE_CASES:
+        props, data, lo, hi, sdf, ro, rd, mint, xi = _sample_distance_scene(orc, strategy, aggressive, n_rays=1024)
+        omed = orc.medium_create(oracle_medium_desc(props), orc.rif_create(volume_desc(data.shape[::-1], lo, hi), data))
+        w, sd = orc.medium_resolved(omed)
+        ref = RefTrace(data, lo, hi, props["stepsize"]).configure(props["sigmaA"], props["sigmaS"], strategy, sd, w, sdf, lo, hi, aggressive)
+        r = ref.sample_distance(ro, rd, mint, xi)
+        tag = "sd_%s_%d_" % (strategy, int(aggressive))
+        out.update({tag + k: v for k, v in r.items()})
+        out[tag + "weight"], out[tag + "density"] = np.float32(w), np.float32(sd)
+    np.savez_compressed(os.path.join(HERE, "trace_ref.npz"), **out)
+    print("wrote trace_ref.npz")
+
+
 if __name__ == "__main__":
     main()
     phase()
+    trace()

@@ -88,6 +88,54 @@ def test_trace_parity(oracle32, oracle64, kind, h):
     assert got["nsteps"].max() <= 1003
 
 
+@pytest.mark.parametrize("kind", ["linear", "radial", "sd", "smooth"])
+def test_trace_against_the_reference_compiled_verbatim(kind):
+    """SURVEY a5-a9, a11 against the REFERENCE ITSELF, not the restatement: the CUDA stepper in the reference's own
+    container (insideShape = hackForSphere, heterogeneousrefractive.cpp:707-718) against what er_step / trace /
+    traceTillBoundary of heterogeneousrefractive.cpp, compiled verbatim (oracle/ref_trace.cpp), return: the committed
+    golden vectors (tests/golden/trace_ref.npz) and, where oracle/_ref/libmer_reftrace.so travelled, 20000 more rays."""
+    import os
+    from common import REF_SPHERE_CENTRE, REF_SPHERE_RADIUS, ref_sphere_scene
+    from oracle.oracle import RefTrace
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    h = float(G[kind + "_h"])
+    props = medium_props(stepsize=h, shape=("sphere", tuple(float(x) for x in REF_SPHERE_CENTRE), REF_SPHERE_RADIUS))
+
+    def gpu(data, lo, hi):
+        rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+        med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9)).configure()
+        return rif, med
+
+    def check(got, ref, tag, n):
+        """ref: dict of float32 arrays of the reference; the gates of test_trace_parity (gate ii)"""
+        same = np.ones(n, bool) if "success" not in ref else (got["success"] == ref["success"])
+        assert np.mean(same) > 0.998, tag
+        scales = dict(p=1.0, v=2.0, dist_surf=max(float(np.abs(ref["dist_surf"]).max()), 1e-3), opl=max(float(np.abs(ref["opl"]).max()), 1e-3))
+        for key, scale in scales.items():
+            e = np.abs(np.asarray(got[key], np.float64) - ref[key]).reshape(n, -1).max(axis=1) / scale
+            bulk = np.mean(e[same] <= 1e-5)
+            print("vs verbatim reference [%s %s %s]: max %.2e, within 1e-5: %.3f %%" % (kind, tag, key, e[same].max(), 100 * bulk))
+            assert bulk >= 0.998 and np.quantile(e[same], 0.9995) <= 1e-4, (tag, key)
+
+    data, lo, hi, p0, d0, dist = ref_sphere_scene(kind, n_rays=1024)
+    rif, med = gpu(data, lo, hi)
+    n0 = rif.value(p0)
+    assert np.max(np.abs(n0 - G[kind + "_n0"])) <= 1e-5 * 2.0
+    v0 = (d0 * G[kind + "_n0"][:, None]).astype(np.float32)
+    check(med.trace(p0, v0, dist), {k: G[kind + "_" + k] for k in ("p", "v", "dist_surf", "opl", "success")}, "golden trace", 1024)
+    check(med.traceTillBoundary(p0, v0), {k: G[kind + "_tb_" + k] for k in ("p", "v", "dist_surf", "opl")}, "golden traceTillBoundary", 1024)
+    if RefTrace.available():
+        n = 20000
+        data, lo, hi, p0, d0, dist = ref_sphere_scene(kind, n_rays=n, seed=11)
+        ref = RefTrace(data, lo, hi, h)
+        rn0, _ = ref.value_gradient(p0)
+        v0 = (d0 * rn0[:, None]).astype(np.float32)
+        rp, rv, rds, ropl, rok = ref.trace(p0, v0, dist)
+        check(med.trace(p0, v0, dist), dict(p=rp, v=rv, dist_surf=rds, opl=ropl, success=rok), "library trace", n)
+        tp, tv, tds, topl = ref.trace_till_boundary(p0, v0)
+        check(med.traceTillBoundary(p0, v0), dict(p=tp, v=tv, dist_surf=tds, opl=topl), "library traceTillBoundary", n)
+
+
 def test_long_trajectory_drift_report(oracle32, oracle64):
     """drift against the FLOAT=double reference up to 1e5 steps (h = 2.5e-6 * extent).  Single precision cannot hold 1e-5 over 1e5 steps against double (position round-off
     alone random-walks to ~1e-5); the assertion is that the GPU drifts no more than the reference's own float
@@ -234,6 +282,34 @@ def test_sample_distance_records(oracle32, strategy):
     assert outside.sum() > 0
     assert not got["success"][outside].any() and np.all(got["transmittance"][outside] == 0)
     assert np.all(got["pdf_success"][outside] == 1) and np.all(got["pdf_failure"][outside] == 1)
+
+
+@pytest.mark.parametrize("strategy,aggressive", [("single", False), ("balance", False), ("manual", False), ("maximum", False), ("single", True)])
+def test_sample_distance_against_the_reference_compiled_verbatim(oracle32, strategy, aggressive):
+    """SURVEY a10, a12-a14 against the REFERENCE ITSELF: the CUDA sampleDistance (through the C ABI) against what
+    Medium::sampleDistance of heterogeneousrefractive.cpp, compiled verbatim (oracle/ref_trace.cpp), returned for the same
+    rays and random numbers (tests/golden/trace_ref.npz); the gates of test_sample_distance_records"""
+    import os
+    from test_oracle_cpu import _sample_distance_scene
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    tag = "sd_%s_%d_" % (strategy, int(aggressive))
+    props, data, lo, hi, sdf, ro, rd, mint, xi = _sample_distance_scene(oracle32, strategy, aggressive, n_rays=1024)
+    if aggressive:
+        props["aggressivetracing"] = True
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9))
+    if sdf is not None:
+        med.addChild("sdf", mer.SplineDataSource(data=sdf, min=lo, max=hi))
+    med.configure()
+    assert np.float32(med.mediumSamplingWeight) == G[tag + "weight"] and np.float32(med.samplingDensity) == G[tag + "density"]
+    got = med.sampleDistance(ro, rd, mint, xi)
+    same = got["success"] == G[tag + "success"]
+    assert np.mean(same) > 0.997
+    for key, scale in (("t", 4.0), ("p", 1.0), ("d", 2.0), ("optical_length", 8.0), ("ref_ratio_sq", 2.0),
+                       ("transmittance", 1.0), ("pdf_success", 20.0), ("pdf_failure", 1.0)):
+        e = np.abs(np.asarray(got[key], np.float64) - G[tag + key]).reshape(1024, -1).max(axis=1) / scale
+        print("sampleDistance vs verbatim reference [%s %s]: max %.2e" % (tag, key, e[same].max()))
+        assert np.mean(e[same] <= 1e-5) >= 0.998 and e[same].max() <= 1e-4, key
 
 
 def test_eval_transmittance(oracle32):

@@ -7,7 +7,7 @@ import pytest
 
 from common import (BOX_MAX, BOX_MIN, make_field, medium_props, oracle_medium_desc, oracle_render_desc,
                     random_directions, random_points_in_box, scene_dict)
-from oracle.oracle import Oracle, RefPhase, RefSpline, volume_desc
+from oracle.oracle import Oracle, RefPhase, RefSpline, RefTrace, volume_desc
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -87,6 +87,126 @@ def test_oracle_phase_bit_exact_vs_verbatim_reference():
     cos_i = (rng.random(n) * 2 - 1).astype(np.float32)
     eta = (1 + rng.random(n)).astype(np.float32)
     assert all(np.array_equal(x, y) for x, y in zip(orc.fresnel_dielectric_ext(cos_i, eta), ref.fresnel_dielectric_ext(cos_i, eta)))
+
+
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+@pytest.mark.parametrize("kind,h", [("linear", 2e-3), ("radial", 5e-3), ("sd", 1e-3), ("smooth", 3.3e-3)])
+def test_oracle_stepper_bit_exact_vs_verbatim_reference(oracle32, kind, h):
+    """SURVEY a5-a9, a11 PINNED: er_step, trace, traceTillBoundary and insideShape of heterogeneousrefractive.cpp and the
+    SplineDataSource wrappers of splinevolume.cpp, compiled verbatim (oracle/ref_trace.cpp), against the restatement -
+    bit for bit, in the reference's own container (hackForSphere: a hard-coded sphere, strict inequality)."""
+    from common import REF_SPHERE_CENTRE, REF_SPHERE_RADIUS, ref_sphere_scene
+    data, lo, hi, p0, d0, dist = ref_sphere_scene(kind)
+    ref = RefTrace(data, lo, hi, h)
+    c, r = ref.container()
+    assert np.array_equal(c, REF_SPHERE_CENTRE) and r == np.float32(REF_SPHERE_RADIUS)
+    props = medium_props(stepsize=h, shape=("sphere", tuple(float(x) for x in c), float(r)))
+    orif = oracle32.rif_create(volume_desc(data.shape[::-1], lo, hi), data)
+    omed = oracle32.medium_create(oracle_medium_desc(props), orif)
+    # the lookup wrappers and the containment test
+    n0, g0 = ref.value_gradient(p0)
+    f1, g1 = oracle32.rif_eval(orif, p0, what=2) if hasattr(oracle32, "rif_eval") else (None, None)
+    if f1 is not None:
+        assert np.array_equal(np.asarray(f1, np.float32), n0) and np.array_equal(np.asarray(g1, np.float32), g0)
+    v0 = (d0 * n0[:, None]).astype(np.float32)
+    # trace()
+    rp, rv, rds, ropl, rok = ref.trace(p0, v0, dist)
+    got = oracle32.trace(omed, p0, v0, dist)
+    assert 0.2 < rok.mean() < 0.8  # both outcomes are exercised
+    assert np.array_equal(got["success"], rok)
+    for name, a, b in (("p", got["p"], rp), ("v", got["v"], rv), ("dist_surf", got["dist_surf"], rds), ("opl", got["opl"], ropl)):
+        assert np.array_equal(np.asarray(a, np.float32), b), (name, np.abs(np.asarray(a, np.float64) - b).max())
+    # traceTillBoundary()
+    tp, tv, tds, topl = ref.trace_till_boundary(p0, v0)
+    gotb = oracle32.trace_till_boundary(omed, p0, v0)
+    for name, a, b in (("p", gotb["p"], tp), ("v", gotb["v"], tv), ("dist_surf", gotb["dist_surf"], tds), ("opl", gotb["opl"], topl)):
+        assert np.array_equal(np.asarray(a, np.float32), b), (name, np.abs(np.asarray(a, np.float64) - b).max())
+    assert ref.inside_shape(tp).mean() > 0.99  # stepped back inside (the leapfrog step is not exactly reversible in float)
+
+
+@pytest.mark.parametrize("kind", ["linear", "radial", "sd", "smooth"])
+def test_oracle_stepper_bit_exact_vs_reference_golden(oracle32, kind):
+    """the same pin without /root/reference: tests/golden/trace_ref.npz holds what the reference's own er_step / trace /
+    traceTillBoundary (compiled verbatim, tests/golden/make_golden.py) returned for these seeded rays"""
+    from common import REF_SPHERE_CENTRE, REF_SPHERE_RADIUS, ref_sphere_scene
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    data, lo, hi, p0, d0, dist = ref_sphere_scene(kind, n_rays=1024)
+    assert float(data.astype(np.float64).sum()) == float(G[kind + "_data_sum"]) and float(p0.astype(np.float64).sum()) == float(G[kind + "_p0_sum"])
+    props = medium_props(stepsize=float(G[kind + "_h"]), shape=("sphere", tuple(float(x) for x in REF_SPHERE_CENTRE), REF_SPHERE_RADIUS))
+    orif = oracle32.rif_create(volume_desc(data.shape[::-1], lo, hi), data)
+    omed = oracle32.medium_create(oracle_medium_desc(props), orif)
+    f, g = oracle32.rif_eval(orif, p0, what=2)
+    assert np.array_equal(np.asarray(f, np.float32), G[kind + "_n0"]) and np.array_equal(np.asarray(g, np.float32), G[kind + "_g0"])
+    v0 = (d0 * G[kind + "_n0"][:, None]).astype(np.float32)
+    got = oracle32.trace(omed, p0, v0, dist)
+    assert np.array_equal(got["success"], G[kind + "_success"])
+    for name in ("p", "v", "dist_surf", "opl"):
+        assert np.array_equal(np.asarray(got[name], np.float32), G[kind + "_" + name]), name
+    gotb = oracle32.trace_till_boundary(omed, p0, v0)
+    for name in ("p", "v", "dist_surf", "opl"):
+        assert np.array_equal(np.asarray(gotb[name], np.float32), G[kind + "_tb_" + name]), name
+
+
+SAMPLE_DISTANCE_CASES = [("single", False), ("balance", False), ("manual", False), ("maximum", False), ("single", True)]
+
+
+def _sample_distance_scene(oracle, strategy, aggressive, n_rays=3000):
+    """medium + rays for Medium::sampleDistance in the reference's hard-coded sphere; -> (props, data, lo, hi, sdf, ro, rd, mint, xi)"""
+    from common import REF_SPHERE_CENTRE, REF_SPHERE_RADIUS, ref_sphere_scene
+    from mitsubaer_b200 import fields
+    data, lo, hi, p0, d0, dist = ref_sphere_scene("radial", n_rays=n_rays, seed=5)
+    props = medium_props(stepsize=2e-3, sigmaS=(9.0, 12.0, 1.6), sigmaA=(1.0, 1.0, 0.4), strategy=strategy,
+                         shape=("sphere", tuple(float(x) for x in REF_SPHERE_CENTRE), REF_SPHERE_RADIUS))
+    if strategy == "manual":
+        props["samplingDensity"] = 11.0
+    sdf = fields.sphere_sdf(data.shape[::-1], lo, hi, centre=tuple(float(x) for x in REF_SPHERE_CENTRE), radius=REF_SPHERE_RADIUS).astype(np.float32) if aggressive else None
+    rng = np.random.default_rng(17)
+    xi = rng.random((n_rays, 2)).astype(np.float32)
+    mint = (0.01 * rng.random(n_rays)).astype(np.float32)
+    return props, data, lo, hi, sdf, p0, d0, mint, xi
+
+
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+@pytest.mark.parametrize("strategy,aggressive", SAMPLE_DISTANCE_CASES)
+def test_oracle_sample_distance_bit_exact_vs_verbatim_reference(oracle32, strategy, aggressive):
+    """SURVEY a10, a12-a14 PINNED: Medium::sampleDistance of heterogeneousrefractive.cpp (:402-568: free-flight strategies,
+    the aggressive-tracing loop over the signed distance, pdfs, transmittance, refRatioSq) and evalTransmittance
+    (:393-400), compiled verbatim with src/medium/maxexp.h, against the restatement - bit for bit"""
+    props, data, lo, hi, sdf, ro, rd, mint, xi = _sample_distance_scene(oracle32, strategy, aggressive)
+    orif = oracle32.rif_create(volume_desc(data.shape[::-1], lo, hi), data)
+    omed = oracle32.medium_create(oracle_medium_desc(props), orif)
+    if sdf is not None:
+        oracle32.medium_set_sdf(omed, oracle32.rif_create(volume_desc(data.shape[::-1], lo, hi), sdf), aggressive=True)
+    w, sd = oracle32.medium_resolved(omed)
+    ref = RefTrace(data, lo, hi, props["stepsize"]).configure(props["sigmaA"], props["sigmaS"], strategy, sd, w, sdf, lo, hi, aggressive)
+    a, b = oracle32.sample_distance(omed, ro, rd, mint, xi), ref.sample_distance(ro, rd, mint, xi)
+    assert 0.15 < b["success"].mean() < 0.85
+    assert np.array_equal(a["success"], b["success"])
+    for key in ("t", "p", "d", "optical_length", "ref_ratio_sq", "transmittance", "pdf_success", "pdf_failure"):
+        x, y = np.asarray(a[key], np.float32), b[key]
+        assert np.array_equal(x, y), (key, np.abs(x.astype(np.float64) - y).max(), np.mean(x != y))
+    rng = np.random.default_rng(3)
+    t0, t1 = rng.random(500).astype(np.float32), (1 + 3 * rng.random(500)).astype(np.float32)
+    sigma_t = np.asarray(props["sigmaS"], np.float32) + np.asarray(props["sigmaA"], np.float32)
+    assert np.array_equal(oracle32.eval_transmittance(sigma_t, t0, t1), ref.eval_transmittance(t0, t1))
+
+
+@pytest.mark.parametrize("strategy,aggressive", SAMPLE_DISTANCE_CASES)
+def test_oracle_sample_distance_bit_exact_vs_reference_golden(oracle32, strategy, aggressive):
+    """the same pin without /root/reference: the reference's own sampleDistance outputs in tests/golden/trace_ref.npz"""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    tag = "sd_%s_%d_" % (strategy, int(aggressive))
+    props, data, lo, hi, sdf, ro, rd, mint, xi = _sample_distance_scene(oracle32, strategy, aggressive, n_rays=1024)
+    orif = oracle32.rif_create(volume_desc(data.shape[::-1], lo, hi), data)
+    omed = oracle32.medium_create(oracle_medium_desc(props), orif)
+    if sdf is not None:
+        oracle32.medium_set_sdf(omed, oracle32.rif_create(volume_desc(data.shape[::-1], lo, hi), sdf), aggressive=True)
+    w, sd = oracle32.medium_resolved(omed)
+    assert np.float32(w) == G[tag + "weight"] and np.float32(sd) == G[tag + "density"]
+    a = oracle32.sample_distance(omed, ro, rd, mint, xi)
+    assert np.array_equal(a["success"], G[tag + "success"])
+    for key in ("t", "p", "d", "optical_length", "ref_ratio_sq", "transmittance", "pdf_success", "pdf_failure"):
+        assert np.array_equal(np.asarray(a[key], np.float32), G[tag + key]), key
 
 
 def test_spline_interpolates_data_at_nodes(oracle64):
