@@ -7,19 +7,30 @@
  *
  * Parity pinning (what is checked bit for bit against the REFERENCE'S OWN CODE compiled here, oracle/_ref):
  *   a1-a4 + Hessian   include/mitsuba/core/basisspline.h                      (ref_spline.cpp, float and double)
+ *   a5 (lookups)      SplineDataSource::insideVolumeLimits / value / gradient / valueAndGradient of
+ *                     src/volume/splinevolume.cpp                             (ref_trace.cpp)
+ *   a7-a11            er_step, trace, aggressive_trace, traceTillBoundary, insideShape (= hackForSphere, the hard-coded
+ *                     sphere) of src/medium/heterogeneousrefractive.cpp       (ref_trace.cpp)
+ *   a10, a12-a14      Medium::sampleDistance (all four strategies + the aggressive-tracing loop over the signed distance)
+ *                     and evalTransmittance of src/medium/heterogeneousrefractive.cpp, with src/medium/maxexp.h
+ *                                                                             (ref_trace.cpp)
  *   a15-a17           src/phase/hg.cpp, include/mitsuba/core/{frame,vector,math,constants}.h,
  *                     coordinateSystem() of src/libcore/util.cpp              (ref_phase.cpp)
  *   hdielectric       fresnelDielectricExt() of src/libcore/util.cpp          (ref_phase.cpp)
  *   strategy maximum  src/medium/maxexp.h (MaxExpDist)                        (ref_phase.cpp)
- * and against golden vectors generated from those builds (the .npz files under tests/golden, make_golden.py).
- * The rest (a5-a14: er_step / trace / traceTillBoundary / sampleDistance, a18-a24: density grid, Woodcock, bounce loop,
- * film) needs Mitsuba's framework to compile and has NO golden vectors or tests in the reference: it is
- * pinned only by line-by-line restatement + analytic invariants: PARITY UNPINNED by reference fixtures for those rows;
- * HG is in addition pinned statistically by the reference's chi-square test (src/tests/test_chisquare.cpp:508-572).
+ * and against golden vectors generated from those builds (the .npz files under tests/golden, make_golden.py).  The member
+ * functions are cut out of the reference's .cpp files by oracle/Makefile at build time and compiled inside structs that
+ * declare only the data members they use, on top of the reference's own core headers; nothing is copied into this repo.
+ * NOT pinned that way: the constructor's resolution of the medium properties (heterogeneousrefractive.cpp:201-300), the
+ * .vol loader (a6), a18-a24 (density grid, Woodcock tracking, the bounce loop of volpath.cpp, ImageBlock / film): they
+ * need Mitsuba's framework (Scene, Properties, Boost) to compile and the reference has NO golden vectors or tests for
+ * them: line-by-line restatement + analytic invariants, PARITY UNPINNED by reference fixtures for those
+ * rows; HG is in addition pinned statistically by the reference's chi-square test (src/tests/test_chisquare.cpp:508-572).
  * The "next" rows restated here as well (curved direct connections and their use as next-event
- * estimation, hdielectric boundary, transient film, light tracing, SDF containers) are UNPINNED too: the reference has
- * no fixtures for them and its solver is Ceres; they are checked by closed forms (slab reflectance 2R/(1+R), time of
- * flight through a slab, white furnaces) and by requiring that independent estimators of the same image agree.
+ * estimation, with or without volpath's MIS, hdielectric boundary, transient film, light tracing, SDF containers) are
+ * UNPINNED too: the reference has no fixtures for them and its solver is Ceres; they are checked by closed forms (slab
+ * reflectance 2R/(1+R), time of flight through a slab, white furnaces) and by requiring that independent estimators of
+ * the same image agree.
  *
  * Every function cites the reference lines it follows (paths relative to the MitsubaER tree).
  * All arithmetic is templated on FLOAT in {float, double}: float is Mitsuba's `Float`,
@@ -615,23 +626,30 @@ template <typename F> struct Medium {
 
     /* er_derivativestep, :798-814: leapfrog on (p, v, A = dp/dv0, B = dv/dv0) */
     void er_derivativestep(F *p, F *v, F *A, F *B, F stepsize, long &count) const {
-        const F half = (F) 0.5;
-        F n, G[3], H[9], T[9];
+        /* evaluated as the reference's operators do it (matrix.h, vector.h): `VHALF * stepsize * H*dpdv0` is
+         * ((VHALF * stepsize) * H) * dpdv0, the scalar goes into the matrix BEFORE the product; pinned bit for bit by
+         * oracle/ref_trace.cpp (tests/test_oracle_cpu.py::test_oracle_connection_bit_exact_vs_verbatim_reference) */
+        const F half = (F) 0.5, hs = half * stepsize;
+        F n, G[3], H[9], T[9], Hs[9];
         rif->valueGradientAndHessian(p, &n, G, H);
-        for (int i = 0; i < 3; i++) v[i] += half * stepsize * G[i];
-        mmul(H, A, T);
-        for (int i = 0; i < 9; i++) B[i] += half * stepsize * T[i];
+        for (int i = 0; i < 3; i++) v[i] += hs * G[i];
+        for (int i = 0; i < 9; i++) Hs[i] = H[i] * hs;
+        mmul(Hs, A, T);
+        for (int i = 0; i < 9; i++) B[i] += T[i];
         F recip = (F) 1 / n;
         for (int i = 0; i < 3; i++) p[i] += (stepsize * v[i]) * recip;
         rif->valueGradientAndHessian(p, &n, G, H);
         F invn = 1 / n;
         F VG[9], T2[9];
+        const F c = -invn * invn;
         outer(v, G, VG);
+        for (int i = 0; i < 9; i++) VG[i] = VG[i] * c; /* -invn*invn*Matrix3x3F(v, G) */
         mmul(VG, A, T2);
-        for (int i = 0; i < 9; i++) A[i] += stepsize * (-invn * invn * T2[i] + invn * B[i]);
-        for (int i = 0; i < 3; i++) v[i] += half * stepsize * G[i];
-        mmul(H, A, T);
-        for (int i = 0; i < 9; i++) B[i] += half * stepsize * T[i];
+        for (int i = 0; i < 9; i++) A[i] += (T2[i] + B[i] * invn) * stepsize;
+        for (int i = 0; i < 3; i++) v[i] += hs * G[i];
+        for (int i = 0; i < 9; i++) Hs[i] = H[i] * hs;
+        mmul(Hs, A, T);
+        for (int i = 0; i < 9; i++) B[i] += T[i];
         count++;
     }
 
@@ -663,9 +681,10 @@ template <typename F> struct Medium {
         sq = std::sqrt(sq);
         int sg = (F(0) < dotp) - (dotp < F(0));
         F w[3], NW[9];
-        for (int i = 0; i < 3; i++) w[i] = (r * v[i] + dotp * N[i]) / sq;
+        const F rsq = (F) 1 / sq; /* Vector / Float multiplies by the reciprocal */
+        for (int i = 0; i < 3; i++) w[i] = (r * v[i] + dotp * N[i]) * rsq;
         outer(N, w, NW);
-        for (int i = 0; i < 9; i++) L[i] = ((i % 4 == 0) ? (F) 1 : (F) 0) - NN[i] + sg * NW[i];
+        for (int i = 0; i < 9; i++) L[i] = ((i % 4 == 0) ? (F) 1 : (F) 0) - NN[i] + (F) sg * NW[i];
         mmul(L, S, B);
         for (int i = 0; i < 3; i++) v[i] = v[i] - dotp * N[i] + sg * sq * N[i];
     }
@@ -750,8 +769,8 @@ template <typename F> struct Medium {
                 for (int i = 0; i < 3; i++) dpdtb[i] = v[i] * rn;
                 containerNormal(p, N);
                 preMult(A, N, dtb);
-                F den = dot(N, dpdtb);
-                for (int i = 0; i < 3; i++) dtb[i] = -dtb[i] / den;
+                F rden = (F) 1 / dot(N, dpdtb); /* Vector / Float multiplies by the reciprocal (vector.h) */
+                for (int i = 0; i < 3; i++) dtb[i] = (-dtb[i]) * rden;
                 if (refract) {
                     F dotp = dot(v, N), rr = (F) 1 / nb;
                     rr = rr * rr - 1;
@@ -782,12 +801,12 @@ template <typename F> struct Medium {
             rif->valueAndGradient(p, &r, dvdt);
             F rr = (F) 1 / r;
             for (int i = 0; i < 3; i++) dpdt[i] = v[i] * rr;
-            F den = dot(v, dpdt) + dot(d, dvdt);
-            for (int i = 0; i < 3; i++) dts[i] = -(a[i] + b[i]) / den;
+            F rden = (F) 1 / (dot(v, dpdt) + dot(d, dvdt));
+            for (int i = 0; i < 3; i++) dts[i] = (-(a[i] + b[i])) * rden;
         } else {
             for (int i = 0; i < 3; i++) dpdt[i] = v[i];
-            F den = dot(v, dpdt);
-            for (int i = 0; i < 3; i++) dts[i] = -(a[i] + b[i]) / den;
+            F rden = (F) 1 / dot(v, dpdt);
+            for (int i = 0; i < 3; i++) dts[i] = (-(a[i] + b[i])) * rden;
         }
         F O[9];
         outer(dpdt, dts, O);

@@ -332,6 +332,43 @@ class RefTrace:
         self.lib.ref_eval_transmittance(self.h, C.c_size_t(mint.size), _ptr(mint, C.c_float), _ptr(maxt, C.c_float), _ptr(out, C.c_float))
         return out
 
+    def set_connection(self, precision, tol):
+        """`boundaryprecision` and `tol` of the medium (the shooting problem's bisection depth and acceptance)"""
+        self.lib.ref_medium_set_connection(self.h, C.c_int(int(precision)), C.c_float(tol))
+        return self
+
+    def derivative_trace(self, p, v, nsteps):
+        """er_derivativestep (:798-814) nsteps times from dpdv0 = 0, dvdv0 = I"""
+        p, v = self._pv(p, v)
+        n = p.shape[0]
+        A = np.zeros((n, 3, 3), np.float32)
+        B = np.ascontiguousarray(np.broadcast_to(np.eye(3, dtype=np.float32), (n, 3, 3)))
+        self.lib.ref_derivative_trace(self.h, C.c_size_t(n), _ptr(p, C.c_float), _ptr(v, C.c_float), _ptr(A, C.c_float), _ptr(B, C.c_float),
+                                      C.c_int(int(nsteps)))
+        return dict(p=p, v=v, dpdv0=A, dvdv0=B)
+
+    def connection_residual(self, p1, p2, v0, is_sensor=False):
+        """computefdfBDPT (:816-939) as DirectConnectionCostFunction::Evaluate calls it -> error [n,3], derror [n,3,3] (derror.m)"""
+        p1 = np.ascontiguousarray(p1, dtype=np.float32).reshape(-1, 3)
+        p2 = np.ascontiguousarray(p2, dtype=np.float32).reshape(-1, 3)
+        v0 = np.ascontiguousarray(v0, dtype=np.float32).reshape(-1, 3)
+        n = p1.shape[0]
+        err, J = np.zeros((n, 3), np.float32), np.zeros((n, 3, 3), np.float32)
+        self.lib.ref_connection_residual(self.h, C.c_size_t(n), _ptr(p1, C.c_float), _ptr(p2, C.c_float), _ptr(v0, C.c_float),
+                                         C.c_int(1 if is_sensor else 0), _ptr(err, C.c_float), _ptr(J, C.c_float))
+        return dict(error=err, derror=J)
+
+    def path_lengths(self, p1, p2, dir_to_p2, is_sensor=False):
+        """computePathLengthsTillClosestP2 (:941-1030) -> success, revDirToP1, opticalDistToP2, distToP2"""
+        p1 = np.ascontiguousarray(p1, dtype=np.float32).reshape(-1, 3)
+        p2 = np.ascontiguousarray(p2, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dir_to_p2, dtype=np.float32).reshape(-1, 3)
+        n = p1.shape[0]
+        rev, od, dist, ok = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        self.lib.ref_path_lengths(self.h, C.c_size_t(n), _ptr(p1, C.c_float), _ptr(p2, C.c_float), _ptr(d, C.c_float), C.c_int(1 if is_sensor else 0),
+                                  _ptr(rev, C.c_float), _ptr(od, C.c_float), _ptr(dist, C.c_float), _ptr(ok, C.c_int))
+        return dict(success=ok.astype(bool), rev_dir=rev, optical_dist=od, dist=dist)
+
     def aggressive_trace(self, p, v, dist):
         p, v = self._pv(p, v)
         n = p.shape[0]

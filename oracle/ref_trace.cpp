@@ -8,11 +8,14 @@
  *                                              traceTillBoundary (:742-776), sampleDistance with its aggressive-tracing
  *                                              loop (:402-568), evalTransmittance (:393-400), enum ESamplingStrategy
  *     src/medium/maxexp.h                      MaxExpDist (strategy "maximum"), as it is
- *     src/volume/splinevolume.cpp              SplineDataSource::insideVolumeLimits / value / gradient / valueAndGradient
- *                                              (:319-360)
- *     src/libcore/aabb.cpp                     AABB::getCorner (:23-27)
+ *                                              er_derivativestep (:798-814), computefdfBDPT (:816-939),
+ *                                              computePathLengthsTillClosestP2 (:941-1030), boundaryVelocity (:1036-1051), boundaryVelocityDerivative
+ *                                              (:1057-1074), sgn (:163-165)   [the shooting problem's residual, its Jacobian
+ *                                              and the connection's lengths: everything of a25 except the Ceres solver]
+ *     src/volume/splinevolume.cpp              SplineDataSource's lookups (:319-377), in ref_volume.cpp
+ *     src/libcore/aabb.cpp                     AABB::getCorner (:23-27), in ref_volume.cpp
  * The member-function bodies are cut out of the two .cpp files by oracle/Makefile (awk, by signature) into
- * oracle/_ref/hetref_extract.inc and oracle/_ref/splinevolume_extract.inc and included into two structs that declare
+ * oracle/_ref/hetref_extract.inc and oracle/_ref/splinevolume_extract.inc and included into two structs (two translation units) that declare
  * exactly the data members those bodies use.  Underneath them the reference's own headers are compiled as they are:
  * include/mitsuba/core/{basisspline,transform,matrix,ray,aabb,vector,point,normal,math,constants,fwd,platform}.h
  * (oracle/shim_phase stands in for mitsuba.h / stream.h, oracle/shim_trace for the one Boost header matrix.h asks for).
@@ -25,27 +28,15 @@
  * traceTillBoundary of oracle/mer_oracle.cpp against it bit for bit, tests/golden/trace_ref.npz holds vectors generated
  * from it (tests/golden/make_trace_golden.py), and tests/test_gpu_medium.py compares the CUDA stepper with it.
  */
-#include <mitsuba/mitsuba.h>
+#include "ref_volume.h"
 namespace mitsuba { using std::endl; }
-#include <mitsuba/core/basisspline.h>
-namespace mitsuba { extern bool solveQuadratic(Float a, Float b, Float c, Float &x0, Float &x1); } /* util.h; bsphere.h mentions it */
-#include <mitsuba/core/aabb.h>
+#include <mitsuba/core/ray.h>        /* reference */
 #include <mitsuba/core/spectrum.h>   /* reference */
 #include <mitsuba/render/sampler.h>  /* oracle/shim_phase: next1D / next2D */
 #include <medium/maxexp.h>           /* reference (src/medium/maxexp.h): MaxExpDist */
 
 namespace mitsuba {
-#include "aabb_extract.inc" /* generated: AABB::getCorner from src/libcore/aabb.cpp */
-
-/* SplineDataSource (src/volume/splinevolume.cpp) reduced to the data members its lookup wrappers use */
-struct RefSplineDataSource {
-    basisspline::Spline<3> m_spline;
-    Transform m_worldToVolume;                 /* toWorld = identity: Transform() */
-    Matrix3x3F m_worldToVolume_Rot, m_worldToVolume_RotT;
-    AABB m_interpolatableLimits;
-    Float m_maxSDFError;
-#include "splinevolume_extract.inc" /* generated: insideVolumeLimits, maxSDFError, value, gradient, valueAndGradient */
-};
+#include "sgn_extract.inc" /* generated: template <typename T> FLOAT sgn(T) of heterogeneousrefractive.cpp:163-165 */
 
 /* MediumSamplingRecord (include/mitsuba/render/medium.h:36-108): the data members sampleDistance() writes */
 struct RefHeterogeneousRefractiveMedium;
@@ -62,15 +53,16 @@ struct MediumSamplingRecord {
 
 /* HeterogeneousRefractiveMedium (src/medium/heterogeneousrefractive.cpp) reduced to what its stepper uses */
 struct RefHeterogeneousRefractiveMedium {
-    RefSplineDataSource *m_rif, *m_SDF;
-    FLOAT m_erstepsize;
+    RefVolume *m_rif, *m_SDF;
+    FLOAT m_erstepsize, m_tol;
     int m_precision;
     bool m_aggressiveTracing;
     Spectrum m_sigmaA, m_sigmaS, m_sigmaT;
     Float m_samplingDensity, m_mediumSamplingWeight;
     MaxExpDist *m_maxExpDist;
 #include "hetref_extract.inc" /* generated: enum ESamplingStrategy, evalTransmittance, sampleDistance, er_step x2, trace,
-                                 aggressive_trace, insideShape, hackForSphere, hackForBox, traceTillBoundary */
+                                 aggressive_trace, insideShape, hackForSphere, hackForBox, traceTillBoundary, er_derivativestep,
+                                 computefdfBDPT, computePathLengthsTillClosestP2, boundaryVelocity, boundaryVelocityDerivative */
     ESamplingStrategy m_strategy;
 };
 
@@ -80,42 +72,20 @@ using namespace mitsuba;
 
 extern "C" {
 
-static RefSplineDataSource *make_source(const float *data, const int *N, const float *bmin, const float *bmax);
-
 void *ref_medium_create(const float *data, const int *N, const float *bmin, const float *bmax, float stepsize) {
-    RefSplineDataSource *rif = make_source(data, N, bmin, bmax);
+    RefVolume *rif = ref_make_volume(data, N, bmin, bmax);
     RefHeterogeneousRefractiveMedium *m = new RefHeterogeneousRefractiveMedium();
     m->m_rif = rif;
     m->m_SDF = rif; /* only its insideVolumeLimits() is asked until ref_medium_configure() gives it a signed distance */
     m->m_erstepsize = stepsize;
     m->m_precision = 6;
+    m->m_tol = 1e-6f;
     m->m_aggressiveTracing = false;
     m->m_maxExpDist = NULL;
     m->m_strategy = RefHeterogeneousRefractiveMedium::ESingle;
     m->m_samplingDensity = 1;
     m->m_mediumSamplingWeight = 0.5f;
     return m;
-}
-
-static RefSplineDataSource *make_source(const float *data, const int *N, const float *bmin, const float *bmax) {
-    RefSplineDataSource *rif = new RefSplineDataSource();
-    FLOAT xmin[3], xmax[3];
-    int n[3];
-    for (int i = 0; i < 3; i++) { xmin[i] = (FLOAT) bmin[i]; xmax[i] = (FLOAT) bmax[i]; n[i] = N[i]; }
-    rif->m_spline.initialize(xmin, xmax, n);
-    /* splinevolume.cpp:280-281 */
-    rif->m_interpolatableLimits = AABB(Point(xmin[0], xmin[1], xmin[2]) + Point( 2.0*rif->m_spline.getStride(0)+Epsilon,  2.0*rif->m_spline.getStride(1)+Epsilon,  2.0*rif->m_spline.getStride(2)+Epsilon),
-                                       Point(xmax[0], xmax[1], xmax[2]) + Point(-2.0*rif->m_spline.getStride(0)-Epsilon, -2.0*rif->m_spline.getStride(1)-Epsilon, -2.0*rif->m_spline.getStride(2)-Epsilon));
-    size_t total = (size_t) N[0] * N[1] * N[2];
-    FLOAT *tmp = new FLOAT[total];
-    for (size_t i = 0; i < total; i++) tmp[i] = (FLOAT) data[i]; /* splinevolume.cpp:284-287 */
-    rif->m_spline.build(tmp);
-    delete[] tmp;
-    /* splinevolume.cpp:282 */
-    rif->m_maxSDFError = std::sqrt( rif->m_spline.getStride(0)*rif->m_spline.getStride(0) + rif->m_spline.getStride(1)*rif->m_spline.getStride(1) + rif->m_spline.getStride(2)*rif->m_spline.getStride(2));
-    rif->m_worldToVolume_Rot.setIdentity();  /* :90-92 with an identity toWorld */
-    rif->m_worldToVolume_RotT.setIdentity();
-    return rif;
 }
 
 /* what the constructor resolves from the properties (heterogeneousrefractive.cpp:201-300), handed over resolved:
@@ -135,7 +105,7 @@ void ref_medium_configure(void *h, const float *sigmaA, const float *sigmaS, int
         m->m_maxExpDist = new MaxExpDist(coeffs);
     }
     if (m->m_SDF != m->m_rif) delete m->m_SDF;
-    m->m_SDF = sdf ? make_source(sdf, N, bmin, bmax) : m->m_rif;
+    m->m_SDF = sdf ? ref_make_volume(sdf, N, bmin, bmax) : m->m_rif;
     m->m_aggressiveTracing = sdf && aggressive;
 }
 
@@ -265,6 +235,65 @@ void ref_trace_till_boundary(void *h, size_t n, float *p, float *v, float *dist_
         v[3 * i] = V.x; v[3 * i + 1] = V.y; v[3 * i + 2] = V.z;
         dist_surf[i] = ds;
         opl[i] = o;
+    }
+}
+
+/* the medium's connection parameters: boundaryprecision and tol (heterogeneousrefractive.cpp:242-250) */
+void ref_medium_set_connection(void *h, int precision, float tol) {
+    RefHeterogeneousRefractiveMedium *m = (RefHeterogeneousRefractiveMedium *) h;
+    m->m_precision = precision;
+    m->m_tol = tol;
+}
+
+/* er_derivativestep (:798-814) nsteps times, in place; dpdv0 / dvdv0 row-major 3x3 */
+void ref_derivative_trace(void *h, size_t n, float *p, float *v, float *dpdv0, float *dvdv0, int nsteps) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+    for (size_t i = 0; i < n; i++) {
+        PointF P(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        VectorF V(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        Matrix3x3F A, B;
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { A.m[r][c] = dpdv0[9 * i + 3 * r + c]; B.m[r][c] = dvdv0[9 * i + 3 * r + c]; }
+        for (int k = 0; k < nsteps; k++) m->er_derivativestep(P, V, A, B, m->m_erstepsize);
+        p[3 * i] = P.x; p[3 * i + 1] = P.y; p[3 * i + 2] = P.z;
+        v[3 * i] = V.x; v[3 * i + 1] = V.y; v[3 * i + 2] = V.z;
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { dpdv0[9 * i + 3 * r + c] = A.m[r][c]; dvdv0[9 * i + 3 * r + c] = B.m[r][c]; }
+    }
+}
+
+/* computefdfBDPT (:816-939) exactly as DirectConnectionCostFunction::Evaluate (:1247-1280) calls it: dpdv0 = 0, dvdv0 = I
+ * (makeDirectConnections :1088-1091); err[3], derr row-major 3x3 (= derror.m) */
+void ref_connection_residual(void *h, size_t n, const float *p1, const float *p2, const float *v0, int isSensor, float *err, float *derr) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long i = 0; i < (long) n; i++) {
+        Matrix3x3F dpdv0((FLOAT)0);
+        Matrix3x3F dvdv0((FLOAT)1, 0, 0,
+                        0, 1, 0,
+                        0, 0, 1);
+        VectorF error(0.0);
+        Matrix3x3F derror(0.0);
+        bool isSensorSample = isSensor != 0;
+        m->computefdfBDPT(VectorF(v0[3 * i], v0[3 * i + 1], v0[3 * i + 2]), PointF(p1[3 * i], p1[3 * i + 1], p1[3 * i + 2]),
+                          PointF(p2[3 * i], p2[3 * i + 1], p2[3 * i + 2]), isSensorSample, dpdv0, dvdv0, error, derror);
+        err[3 * i] = error.x; err[3 * i + 1] = error.y; err[3 * i + 2] = error.z;
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) derr[9 * i + 3 * r + c] = derror.m[r][c];
+    }
+}
+
+/* computePathLengthsTillClosestP2 (:941-1051) */
+void ref_path_lengths(void *h, size_t n, const float *p1, const float *p2, const float *dirToP2, int isSensor, float *revDir, float *opticalDist,
+                      float *dist, int *ok) {
+    const RefHeterogeneousRefractiveMedium *m = (const RefHeterogeneousRefractiveMedium *) h;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long i = 0; i < (long) n; i++) {
+        VectorF rev(0.0);
+        FLOAT od = 0, d = 0;
+        bool isSensorSample = isSensor != 0;
+        ok[i] = m->computePathLengthsTillClosestP2(PointF(p1[3 * i], p1[3 * i + 1], p1[3 * i + 2]), PointF(p2[3 * i], p2[3 * i + 1], p2[3 * i + 2]),
+                                                   VectorF(dirToP2[3 * i], dirToP2[3 * i + 1], dirToP2[3 * i + 2]), rev, isSensorSample, od, d) ? 1 : 0;
+        revDir[3 * i] = rev.x; revDir[3 * i + 1] = rev.y; revDir[3 * i + 2] = rev.z;
+        opticalDist[i] = od;
+        dist[i] = d;
     }
 }
 

@@ -118,6 +118,19 @@ def trace():
         tag = "sd_%s_%d_" % (strategy, int(aggressive))
         out.update({tag + k: v for k, v in r.items()})
         out[tag + "weight"], out[tag + "density"] = np.float32(w), np.float32(sd)
+    # a25 minus the solver: er_derivativestep, computefdfBDPT (residual + Jacobian)
+    from test_oracle_cpu import CONNECTION_KINDS, _connection_scene
+    for kind in CONNECTION_KINDS:
+        props, data, lo, hi, sdf, p1, d0, p2, w = _connection_scene(kind, n=512)
+        ref = RefTrace(data, lo, hi, props["stepsize"]).configure((0.4,) * 3, (3.6,) * 3, "single", 4.0, 0.9, sdf, lo, hi, False).set_connection(3, 1e-6)
+        n0, _ = ref.value_gradient(p1)
+        v0 = (d0 * n0[:, None]).astype(np.float32)
+        dt = ref.derivative_trace(p1, v0, 40)
+        out["conn_%s_n0" % kind] = n0
+        out.update({"conn_%s_dt_%s" % (kind, k): v for k, v in dt.items()})
+        for sensor in (0, 1):
+            B = ref.connection_residual(p1, p2, w, is_sensor=bool(sensor))
+            out["conn_%s_error_%d" % (kind, sensor)], out["conn_%s_derror_%d" % (kind, sensor)] = B["error"], B["derror"]
     np.savez_compressed(os.path.join(HERE, "trace_ref.npz"), **out)
     print("wrote trace_ref.npz")
 

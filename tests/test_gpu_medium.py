@@ -554,6 +554,32 @@ def test_derivative_step_and_connection_residual(oracle32, oracle64):
     assert np.median(np.abs(J - Ja).max(axis=(1, 2))) < 0.02 * np.median(np.abs(Ja).max(axis=(1, 2))) + 2e-3
 
 
+@pytest.mark.parametrize("kind", ["linear", "radial", "sd", "smooth"])
+def test_connection_residual_against_the_reference_compiled_verbatim(kind):
+    """SURVEY a25 minus the solver against the REFERENCE ITSELF: the CUDA er_derivativestep and computefdfBDPT (residual and
+    Jacobian, through the C ABI) against what heterogeneousrefractive.cpp's own functions, compiled verbatim
+    (oracle/ref_trace.cpp), returned (tests/golden/trace_ref.npz); gates of test_derivative_step_and_connection_residual"""
+    import os
+    from test_oracle_cpu import _connection_scene
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    props, data, lo, hi, sdf, p1, d0, p2, w = _connection_scene(kind, n=512)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    med = mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("sdf", mer.SplineDataSource(data=sdf, min=lo, max=hi)).configure()
+    v0 = (d0 * G["conn_%s_n0" % kind][:, None]).astype(np.float32)
+    got = med.derivativeTrace(p1, v0, np.full(512, 40, np.int32))
+    assert np.abs(got["p"] - G["conn_%s_dt_p" % kind]).max() <= 1e-5 and np.abs(got["v"] - G["conn_%s_dt_v" % kind]).max() <= 2e-5
+    assert np.abs(got["dpdv0"] - G["conn_%s_dt_dpdv0" % kind]).max() <= 2e-5 and np.abs(got["dvdv0"] - G["conn_%s_dt_dvdv0" % kind]).max() <= 5e-5
+    for sensor in (0, 1):
+        res = med.connectionResidual(p1, p2, w, bool(sensor))
+        e, J = G["conn_%s_error_%d" % (kind, sensor)], G["conn_%s_derror_%d" % (kind, sensor)]
+        # a shooting problem whose exit / closest-approach decision sits on a rounding tie ends a step apart: excluded and counted
+        close = np.abs(res["error"] - e).max(axis=1) <= 5e-5
+        print("computefdfBDPT vs verbatim reference [%s sensor=%d]: same branch %.3f, error max %.2e, Jacobian max %.2e" %
+              (kind, sensor, close.mean(), np.abs(res["error"] - e)[close].max(), np.abs(res["derror"] - J)[close].max()))
+        assert close.mean() > 0.985
+        assert np.abs(res["derror"] - J)[close].max() <= 2e-3 * max(1.0, np.abs(J).max())
+
+
 def test_curved_direct_connections(oracle32, oracle64):
     """makeDirectConnections / eval (:571-640, 1087-1163) with the Levenberg-Marquardt minimiser.
     Parity is UNPINNED at the solver (the reference calls Ceres): validated by (1) ground truth — p2 is the end

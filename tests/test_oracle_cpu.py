@@ -209,6 +209,80 @@ def test_oracle_sample_distance_bit_exact_vs_reference_golden(oracle32, strategy
         assert np.array_equal(np.asarray(a[key], np.float32), G[tag + key]), key
 
 
+def _connection_scene(kind, n=2000):
+    """medium (hdielectric boundary: Snell at the exit, as the reference always does) with an sdf child in the reference's
+    hard-coded sphere, and shooting problems p1 -> p2 with launch velocities near the straight line"""
+    from common import REF_SPHERE_CENTRE, REF_SPHERE_RADIUS, ref_sphere_scene
+    from mitsubaer_b200 import fields
+    data, lo, hi, p1, d0, dist = ref_sphere_scene(kind, n_rays=n, seed=3)
+    c, r = REF_SPHERE_CENTRE, REF_SPHERE_RADIUS
+    sdf = fields.sphere_sdf(data.shape[::-1], lo, hi, centre=tuple(float(x) for x in c), radius=r).astype(np.float32)
+    props = medium_props(stepsize=2e-3, shape=("sphere", tuple(float(x) for x in c), r), bsdf="hdielectric")
+    rng = np.random.default_rng(1)
+    q = rng.normal(size=(n, 3))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    p2 = (c + q * (r * (0.3 + 1.2 * rng.random((n, 1))))).astype(np.float32)  # inside and outside the container
+    w = p2 - p1
+    w /= np.linalg.norm(w, axis=1, keepdims=True)
+    w = (w + 0.05 * rng.normal(size=w.shape)).astype(np.float32)
+    w = (w / np.linalg.norm(w, axis=1, keepdims=True) * 1.7).astype(np.float32)  # |v0| != n: the renormalisation chain rule
+    return props, data, lo, hi, sdf, p1, d0, p2, w
+
+
+CONNECTION_KINDS = ["linear", "radial", "sd", "smooth"]
+
+
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+@pytest.mark.parametrize("kind", CONNECTION_KINDS)
+def test_oracle_connection_bit_exact_vs_verbatim_reference(oracle32, kind):
+    """SURVEY a25 minus the solver, PINNED: er_derivativestep (:798-814), computefdfBDPT (:816-939: the shooting problem's
+    residual AND its Jacobian, closest approach by bisection, Snell exit through boundaryVelocityDerivative :1057-1074) and
+    computePathLengthsTillClosestP2 (:941-1030) with boundaryVelocity (:1036-1051), compiled verbatim, against the
+    restatement - bit for bit.  (What stays unpinned is Ceres' BFGS itself.)"""
+    props, data, lo, hi, sdf, p1, d0, p2, w = _connection_scene(kind)
+    d = volume_desc(data.shape[::-1], lo, hi)
+    omed = oracle32.medium_create(oracle_medium_desc(props), oracle32.rif_create(d, data))
+    oracle32.medium_set_sdf(omed, oracle32.rif_create(d, sdf), aggressive=False)
+    ref = RefTrace(data, lo, hi, props["stepsize"]).configure((0.4,) * 3, (3.6,) * 3, "single", 4.0, 0.9, sdf, lo, hi, False).set_connection(3, 1e-6)
+    n0, _ = ref.value_gradient(p1)
+    v0 = (d0 * n0[:, None]).astype(np.float32)
+    a, b = oracle32.derivative_trace(omed, p1, v0, 40), ref.derivative_trace(p1, v0, 40)
+    for key in ("p", "v", "dpdv0", "dvdv0"):
+        assert np.array_equal(np.asarray(a[key], np.float32), b[key]), key
+    for sensor in (False, True):
+        A, B = oracle32.connection_residual(omed, p1, p2, w, is_sensor=sensor), ref.connection_residual(p1, p2, w, is_sensor=sensor)
+        assert set(np.unique(A["status"])) >= {0, 1}  # closest approach inside the medium, and exits through the boundary
+        assert np.array_equal(np.asarray(A["error"], np.float32), B["error"])
+        assert np.array_equal(np.asarray(A["derror"], np.float32), B["derror"])
+    # the connection's lengths along a solved direction: the restated solver's result fed to the reference's re-trace
+    sel = slice(0, 300)
+    r = oracle32.connect(omed, p1[sel], p2[sel], (p2[sel] - p1[sel]) / np.linalg.norm(p2[sel] - p1[sel], axis=1, keepdims=True), tol2=1e-6, precision=3, seed=5, start_mode=2)
+    ok = r["success"].astype(bool)
+    assert ok.mean() > 0.5
+    L = ref.path_lengths(p1[sel][ok], p2[sel][ok], np.asarray(r["dir_to_p2"], np.float32)[ok])
+    assert L["success"].all()
+    assert np.array_equal(L["rev_dir"], np.asarray(r["rev_dir"], np.float32)[ok])
+    assert np.array_equal(L["optical_dist"], np.asarray(r["optical_dist"], np.float32)[ok]) and np.array_equal(L["dist"], np.asarray(r["dist"], np.float32)[ok])
+
+
+@pytest.mark.parametrize("kind", CONNECTION_KINDS)
+def test_oracle_connection_bit_exact_vs_reference_golden(oracle32, kind):
+    """the same pin without /root/reference (tests/golden/trace_ref.npz, key prefix conn_)"""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    props, data, lo, hi, sdf, p1, d0, p2, w = _connection_scene(kind, n=512)
+    d = volume_desc(data.shape[::-1], lo, hi)
+    omed = oracle32.medium_create(oracle_medium_desc(props), oracle32.rif_create(d, data))
+    oracle32.medium_set_sdf(omed, oracle32.rif_create(d, sdf), aggressive=False)
+    v0 = (d0 * G["conn_%s_n0" % kind][:, None]).astype(np.float32)
+    a = oracle32.derivative_trace(omed, p1, v0, 40)
+    for key in ("p", "v", "dpdv0", "dvdv0"):
+        assert np.array_equal(np.asarray(a[key], np.float32), G["conn_%s_dt_%s" % (kind, key)]), key
+    for sensor in (0, 1):
+        A = oracle32.connection_residual(omed, p1, p2, w, is_sensor=bool(sensor))
+        assert np.array_equal(np.asarray(A["error"], np.float32), G["conn_%s_error_%d" % (kind, sensor)])
+        assert np.array_equal(np.asarray(A["derror"], np.float32), G["conn_%s_derror_%d" % (kind, sensor)])
+
+
 def test_spline_interpolates_data_at_nodes(oracle64):
     """the prefilter makes the cubic B-spline INTERPOLATE the samples (that is what build3d is for)"""
     res = (16, 14, 12)
