@@ -378,6 +378,35 @@ class RefTrace:
         return p, v, o
 
 
+class RefGrid:
+    """The reference's GridDataSource::lookupFloat (src/volume/gridvolume.cpp:337-388) with the Transform functions its
+    configure() uses, compiled verbatim (oracle/ref_volume.cpp -> oracle/_ref/libmer_reftrace.so); float32 or uint8 payloads."""
+
+    def __init__(self, data, bmin, bmax):
+        path = os.path.join(REF_DIR, "libmer_reftrace.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.ref_grid_create.restype = C.c_void_p
+        data = np.ascontiguousarray(data)
+        assert data.dtype in (np.float32, np.uint8)
+        N = (C.c_int * 3)(data.shape[2], data.shape[1], data.shape[0])
+        lo = (C.c_float * 3)(*[float(v) for v in bmin])
+        hi = (C.c_float * 3)(*[float(v) for v in bmax])
+        self.h = C.c_void_p(self.lib.ref_grid_create(data.ctypes.data_as(C.c_void_p), N, lo, hi, C.c_int(1 if data.dtype == np.float32 else 3)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_grid_free(self.h)
+            self.h = None
+
+    def lookup(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros(p.shape[0], np.float32)
+        self.lib.ref_grid_lookup(self.h, C.c_size_t(p.shape[0]), _ptr(p, C.c_float), _ptr(out, C.c_float))
+        return out
+
+
 class Oracle:
     """The restated path (oracle/mer_oracle.cpp) in float (`Float`) or double (-DFLOATDEBUG)."""
 

@@ -27,7 +27,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle.oracle import RefPhase, RefSpline, RefTrace  # noqa: E402
+from oracle.oracle import RefGrid, RefPhase, RefSpline, RefTrace  # noqa: E402
 
 
 def main():
@@ -131,6 +131,10 @@ def trace():
         for sensor in (0, 1):
             B = ref.connection_residual(p1, p2, w, is_sensor=bool(sensor))
             out["conn_%s_error_%d" % (kind, sensor)], out["conn_%s_derror_%d" % (kind, sensor)] = B["error"], B["derror"]
+    # a18: GridDataSource::lookupFloat
+    from test_oracle_cpu import _grid_scene
+    res, data, lo, hi, p = _grid_scene()
+    out["grid_lookup"] = RefGrid(data, lo, hi).lookup(p)
     np.savez_compressed(os.path.join(HERE, "trace_ref.npz"), **out)
     print("wrote trace_ref.npz")
 

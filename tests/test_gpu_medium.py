@@ -312,6 +312,17 @@ def test_sample_distance_against_the_reference_compiled_verbatim(oracle32, strat
         assert np.mean(e[same] <= 1e-5) >= 0.998 and e[same].max() <= 1e-4, key
 
 
+def test_grid_lookup_against_the_reference_compiled_verbatim():
+    """SURVEY a18 against the REFERENCE ITSELF: GridDataSource::lookupFloat (gridvolume.cpp:337-388) compiled verbatim
+    (oracle/ref_volume.cpp) -> tests/golden/trace_ref.npz; the CUDA lookup is bit-identical"""
+    import os
+    from test_oracle_cpu import _grid_scene
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    res, data, lo, hi, p = _grid_scene()
+    grid = mer.GridDataSource(data=data, min=lo, max=hi)
+    assert np.array_equal(grid.lookupFloat(p), G["grid_lookup"])
+
+
 def test_eval_transmittance(oracle32):
     props = medium_props(sigmaS=(2.0, 3.0, 0.0), sigmaA=(0.5, 0.25, 0.0))
     rif, med, orif, omed = build("linear", 24, oracle32, props)

@@ -7,7 +7,7 @@ import pytest
 
 from common import (BOX_MAX, BOX_MIN, make_field, medium_props, oracle_medium_desc, oracle_render_desc,
                     random_directions, random_points_in_box, scene_dict)
-from oracle.oracle import Oracle, RefPhase, RefSpline, RefTrace, volume_desc
+from oracle.oracle import Oracle, RefGrid, RefPhase, RefSpline, RefTrace, volume_desc
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -281,6 +281,35 @@ def test_oracle_connection_bit_exact_vs_reference_golden(oracle32, kind):
         A = oracle32.connection_residual(omed, p1, p2, w, is_sensor=bool(sensor))
         assert np.array_equal(np.asarray(A["error"], np.float32), G["conn_%s_error_%d" % (kind, sensor)])
         assert np.array_equal(np.asarray(A["derror"], np.float32), G["conn_%s_derror_%d" % (kind, sensor)])
+
+
+def _grid_scene():
+    rng = np.random.default_rng(31)
+    res = (23, 17, 29)
+    data = rng.random((res[2], res[1], res[0])).astype(np.float32)
+    lo, hi = np.array([-1.0, -0.5, 0.25], np.float32), np.array([1.5, 0.75, 2.0], np.float32)
+    p = (lo - 0.1 + rng.random((6000, 3)) * (hi - lo + 0.2)).astype(np.float32)  # some outside: lookupFloat returns 0 there
+    p[:8] = [[lo[0], lo[1], lo[2]], [hi[0], hi[1], hi[2]], [lo[0], hi[1], lo[2]], [hi[0], lo[1], hi[2]], [0, 0, 1], [1.5, 0, 1], [0, 0.75, 1], [0, 0, 2]]
+    return res, data, lo, hi, p
+
+
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+def test_oracle_grid_lookup_bit_exact_vs_verbatim_reference(oracle32):
+    """SURVEY a18 PINNED: GridDataSource::lookupFloat (gridvolume.cpp:337-388) with Transform::scale / translate / operator*
+    (transform.cpp) compiled verbatim against the restated density lookup - bit for bit, faces and corners of the box included"""
+    res, data, lo, hi, p = _grid_scene()
+    ref = RefGrid(data, lo, hi).lookup(p)
+    g = oracle32.grid_create(volume_desc(res, lo, hi), data)
+    got = oracle32.grid_lookup(g, p)
+    assert (ref == 0).sum() > 100 and (ref > 0).sum() > 3000
+    assert np.array_equal(got, ref), (np.abs(got - ref).max(), np.mean(got != ref))
+
+
+def test_oracle_grid_lookup_bit_exact_vs_reference_golden(oracle32):
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    res, data, lo, hi, p = _grid_scene()
+    g = oracle32.grid_create(volume_desc(res, lo, hi), data)
+    assert np.array_equal(oracle32.grid_lookup(g, p), G["grid_lookup"])
 
 
 def test_spline_interpolates_data_at_nodes(oracle64):
