@@ -14,6 +14,11 @@
  *   a10, a12-a14      Medium::sampleDistance (all four strategies + the aggressive-tracing loop over the signed distance)
  *                     and evalTransmittance of src/medium/heterogeneousrefractive.cpp, with src/medium/maxexp.h
  *                                                                             (ref_trace.cpp)
+ *   a18               GridDataSource::lookupFloat of src/volume/gridvolume.cpp with Transform::scale / translate / operator*
+ *                     of src/libcore/transform.cpp                            (ref_volume.cpp)
+ *   a25 - solver      er_derivativestep, computefdfBDPT (residual + Jacobian), computePathLengthsTillClosestP2,
+ *                     boundaryVelocity, boundaryVelocityDerivative of src/medium/heterogeneousrefractive.cpp
+ *                                                                             (ref_trace.cpp)
  *   a15-a17           src/phase/hg.cpp, include/mitsuba/core/{frame,vector,math,constants}.h,
  *                     coordinateSystem() of src/libcore/util.cpp              (ref_phase.cpp)
  *   hdielectric       fresnelDielectricExt() of src/libcore/util.cpp          (ref_phase.cpp)
@@ -22,7 +27,7 @@
  * functions are cut out of the reference's .cpp files by oracle/Makefile at build time and compiled inside structs that
  * declare only the data members they use, on top of the reference's own core headers; nothing is copied into this repo.
  * NOT pinned that way: the constructor's resolution of the medium properties (heterogeneousrefractive.cpp:201-300), the
- * .vol loader (a6), a18-a24 (density grid, Woodcock tracking, the bounce loop of volpath.cpp, ImageBlock / film): they
+ * .vol loader (a6), a19-a24 (straight-ray Woodcock tracking, the bounce loop of volpath.cpp, ImageBlock / film), Ceres' BFGS: they
  * need Mitsuba's framework (Scene, Properties, Boost) to compile and the reference has NO golden vectors or tests for
  * them: line-by-line restatement + analytic invariants, PARITY UNPINNED by reference fixtures for those
  * rows; HG is in addition pinned statistically by the reference's chi-square test (src/tests/test_chisquare.cpp:508-572).
