@@ -16,6 +16,8 @@
  *                                                                             (ref_trace.cpp)
  *   a18               GridDataSource::lookupFloat of src/volume/gridvolume.cpp with Transform::scale / translate / operator*
  *                     of src/libcore/transform.cpp                            (ref_volume.cpp)
+ *   a23               ReconstructionFilter::configure / evalDiscretized, GaussianFilter::eval, BoxFilter::eval, ImageBlock::put
+ *                                                                             (ref_film.cpp)
  *   a25 - solver      er_derivativestep, computefdfBDPT (residual + Jacobian), computePathLengthsTillClosestP2,
  *                     boundaryVelocity, boundaryVelocityDerivative of src/medium/heterogeneousrefractive.cpp
  *                                                                             (ref_trace.cpp)
@@ -27,7 +29,7 @@
  * functions are cut out of the reference's .cpp files by oracle/Makefile at build time and compiled inside structs that
  * declare only the data members they use, on top of the reference's own core headers; nothing is copied into this repo.
  * NOT pinned that way: the constructor's resolution of the medium properties (heterogeneousrefractive.cpp:201-300), the
- * .vol loader (a6), a19-a24 (straight-ray Woodcock tracking, the bounce loop of volpath.cpp, ImageBlock / film), Ceres' BFGS: they
+ * .vol loader (a6), a19-a22, a24 (straight-ray Woodcock tracking, the bounce loop of volpath.cpp, camera, develop), Ceres' BFGS: they
  * need Mitsuba's framework (Scene, Properties, Boost) to compile and the reference has NO golden vectors or tests for
  * them: line-by-line restatement + analytic invariants, PARITY UNPINNED by reference fixtures for those
  * rows; HG is in addition pinned statistically by the reference's chi-square test (src/tests/test_chisquare.cpp:508-572).
@@ -2229,6 +2231,12 @@ extern "C" void orc_filter_table(int type, float *values32, float *radius, float
     memcpy(values32, f.values, sizeof(f.values));
     *radius = f.radius;
     *scaleFactor = f.scaleFactor;
+}
+/* ImageBlock::put over n samples into a zeroed W x H film, in order (imageblock.h:144-206) */
+extern "C" void orc_film_put(int type, int W, int H, int channels, size_t n, const float *pos, const float *values, float *film, int *ok) {
+    Filter f;
+    f.configure(type);
+    for (size_t i = 0; i < n; i++) ok[i] = film_put(film, W, H, f, pos[2 * i], pos[2 * i + 1], values + (size_t) channels * i, channels) ? 1 : 0;
 }
 extern "C" void orc_camera_ray(const mer_render_desc *r, size_t n, const float *samplePos, float *d) {
     Camera c;

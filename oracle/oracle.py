@@ -407,6 +407,32 @@ class RefGrid:
         return out
 
 
+class RefFilm:
+    """The reference's reconstruction-filter table (rfilter.cpp / rfilter.h, gaussian.cpp, box.cpp) and ImageBlock::put
+    (imageblock.h), compiled verbatim (oracle/ref_film.cpp -> oracle/_ref/libmer_reftrace.so)."""
+
+    def __init__(self):
+        path = os.path.join(REF_DIR, "libmer_reftrace.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+
+    def filter_table(self, ftype):
+        vals = np.zeros(32, np.float32)
+        r, s, b = C.c_float(), C.c_float(), C.c_int()
+        self.lib.ref_filter_table(C.c_int(ftype), _ptr(vals, C.c_float), C.byref(r), C.byref(s), C.byref(b))
+        return vals, r.value, s.value, b.value
+
+    def film_put(self, ftype, W, H, pos, values):
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 2)
+        values = np.ascontiguousarray(values, dtype=np.float32).reshape(pos.shape[0], -1)
+        film = np.zeros((H, W, values.shape[1]), np.float32)
+        ok = np.zeros(pos.shape[0], np.int32)
+        self.lib.ref_film_put(C.c_int(ftype), C.c_int(W), C.c_int(H), C.c_int(values.shape[1]), C.c_size_t(pos.shape[0]), _ptr(pos, C.c_float),
+                              _ptr(values, C.c_float), _ptr(film, C.c_float), _ptr(ok, C.c_int))
+        return film, ok.astype(bool)
+
+
 class Oracle:
     """The restated path (oracle/mer_oracle.cpp) in float (`Float`) or double (-DFLOATDEBUG)."""
 
@@ -674,6 +700,16 @@ class Oracle:
         r, s = C.c_float(), C.c_float()
         self.lib.orc_filter_table(C.c_int(ftype), _ptr(vals, C.c_float), C.byref(r), C.byref(s))
         return vals, r.value, s.value
+
+    def film_put(self, ftype, W, H, pos, values):
+        """ImageBlock::put of n samples (pos [n][2], values [n][channels]) into a zeroed film, in order -> film [H][W][channels], ok [n]"""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 2)
+        values = np.ascontiguousarray(values, dtype=np.float32).reshape(pos.shape[0], -1)
+        film = np.zeros((H, W, values.shape[1]), np.float32)
+        ok = np.zeros(pos.shape[0], np.int32)
+        self.lib.orc_film_put(C.c_int(ftype), C.c_int(W), C.c_int(H), C.c_int(values.shape[1]), C.c_size_t(pos.shape[0]), _ptr(pos, C.c_float),
+                              _ptr(values, C.c_float), _ptr(film, C.c_float), _ptr(ok, C.c_int))
+        return film, ok.astype(bool)
 
     def camera_ray(self, rdesc, sample_pos):
         sp = np.ascontiguousarray(sample_pos, dtype=np.float32).reshape(-1, 2)

@@ -1,0 +1,118 @@
+/*
+ * oracle/ref_film.cpp - TEST INFRASTRUCTURE ONLY (never linked into the product).  Part of oracle/_ref/libmer_reftrace.so.
+ *
+ * SURVEY a23, compiled VERBATIM from where it lies under /root/reference (nothing is copied into this repo):
+ *     src/libcore/rfilter.cpp              ReconstructionFilter::configure (:37-55: the discretised, normalised filter table)
+ *     include/mitsuba/core/rfilter.h       MTS_FILTER_RESOLUTION (:28), evalDiscretized (:75-77)
+ *     src/rfilters/gaussian.cpp            GaussianFilter::eval (:52-57)
+ *     src/rfilters/box.cpp                 BoxFilter::eval (:46-48)
+ *     include/mitsuba/render/imageblock.h  ImageBlock::put(const Point2 &, const Float *) (:144-206) and the Spectrum overload
+ *                                          (:124-131)
+ * The bodies are cut out of those files by oracle/Makefile (awk, by signature) into oracle/_ref/film_*_extract.inc and
+ * included into structs that declare exactly the data members they use.
+ */
+#include <mitsuba/mitsuba.h>
+#include <mitsuba/core/spectrum.h> /* reference */
+#include "film_resolution_extract.inc" /* generated: #define MTS_FILTER_RESOLUTION 31 */
+
+namespace mitsuba {
+
+struct ReconstructionFilter { /* include/mitsuba/core/rfilter.h reduced to what configure() / evalDiscretized() / put() use */
+    Float m_radius, m_scaleFactor;
+    Float m_values[MTS_FILTER_RESOLUTION + 1];
+    int m_borderSize;
+    virtual ~ReconstructionFilter() {}
+    virtual Float eval(Float x) const = 0;
+    inline Float getRadius() const { return m_radius; }
+    inline int getBorderSize() const { return m_borderSize; }
+#include "film_discretized_extract.inc" /* generated: evalDiscretized */
+    void configure();
+};
+#include "film_configure_extract.inc" /* generated: void ReconstructionFilter::configure() */
+
+struct GaussianFilter : public ReconstructionFilter {
+    Float m_stddev;
+#include "film_gaussian_extract.inc" /* generated: eval */
+};
+struct BoxFilter : public ReconstructionFilter {
+#include "film_box_extract.inc" /* generated: eval */
+};
+
+struct RefBitmap { /* the three accessors put() calls */
+    int channels;
+    Vector2i size;
+    std::vector<Float> data;
+    int getChannelCount() const { return channels; }
+    const Vector2i &getSize() const { return size; }
+    Float *getFloatData() { return data.data(); }
+};
+
+struct RefImageBlock { /* include/mitsuba/render/imageblock.h reduced to the data members put() uses */
+    RefBitmap *m_bitmap;
+    const ReconstructionFilter *m_filter;
+    Point2i m_offset;
+    int m_borderSize;
+    Float *m_weightsX, *m_weightsY;
+    bool m_warn;
+#include "film_put_extract.inc" /* generated: both put() overloads */
+};
+
+}
+
+using namespace mitsuba;
+
+static ReconstructionFilter *make_filter(int type) {
+    ReconstructionFilter *f;
+    if (type == 1) {
+        GaussianFilter *g = new GaussianFilter();
+        g->m_stddev = 0.5f;            /* gaussian.cpp:35 default */
+        g->m_radius = 4 * g->m_stddev; /* :38 */
+        f = g;
+    } else {
+        f = new BoxFilter();
+        f->m_radius = 0.5f + 1e-5f; /* box.cpp:38 default */
+    }
+    f->configure();
+    return f;
+}
+
+extern "C" {
+
+/* type: 0 box, 1 gaussian -> the 32 table values, radius, scale factor, border size */
+void ref_filter_table(int type, float *values32, float *radius, float *scaleFactor, int *borderSize) {
+    ReconstructionFilter *f = make_filter(type);
+    for (int i = 0; i <= MTS_FILTER_RESOLUTION; i++) values32[i] = f->m_values[i];
+    *radius = f->m_radius;
+    *scaleFactor = f->m_scaleFactor;
+    *borderSize = f->m_borderSize;
+    delete f;
+}
+
+/* n samples (pos [n][2] in fractional pixel coordinates, values [n][channels]) put into ONE block that covers the whole W x H
+ * film (offset 0, border = the filter's), in order; out: the block without its border, [H][W][channels]; ok[i] = put()'s result */
+void ref_film_put(int type, int W, int H, int channels, size_t n, const float *pos, const float *values, float *out, int *ok) {
+    ReconstructionFilter *f = make_filter(type);
+    RefBitmap bmp;
+    const int b = f->getBorderSize();
+    bmp.channels = channels;
+    bmp.size = Vector2i(W + 2 * b, H + 2 * b); /* imageblock.cpp: ImageBlock::ImageBlock allocates size + 2 * border */
+    bmp.data.assign((size_t) bmp.size.x * bmp.size.y * channels, 0.0f);
+    RefImageBlock blk;
+    blk.m_bitmap = &bmp;
+    blk.m_filter = f;
+    blk.m_offset = Point2i(0, 0);
+    blk.m_borderSize = b;
+    const int wsize = (int) std::ceil(2 * f->getRadius()) + 1;
+    std::vector<Float> wx(wsize), wy(wsize);
+    blk.m_weightsX = wx.data();
+    blk.m_weightsY = wy.data();
+    blk.m_warn = true;
+    for (size_t i = 0; i < n; i++) ok[i] = blk.put(Point2(pos[2 * i], pos[2 * i + 1]), values + (size_t) channels * i) ? 1 : 0;
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++)
+            for (int k = 0; k < channels; k++)
+                out[((size_t) y * W + x) * channels + k] = bmp.data[((size_t) (y + b) * bmp.size.x + (x + b)) * channels + k];
+    delete f;
+}
+
+}

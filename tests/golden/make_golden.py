@@ -27,7 +27,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from oracle.oracle import RefGrid, RefPhase, RefSpline, RefTrace  # noqa: E402
+from oracle.oracle import RefFilm, RefGrid, RefPhase, RefSpline, RefTrace  # noqa: E402
 
 
 def main():
@@ -135,6 +135,14 @@ def trace():
     from test_oracle_cpu import _grid_scene
     res, data, lo, hi, p = _grid_scene()
     out["grid_lookup"] = RefGrid(data, lo, hi).lookup(p)
+    # a23: filter tables and ImageBlock::put
+    from test_oracle_cpu import _film_scene
+    W, H, pos, values = _film_scene()
+    rf = RefFilm()
+    for ftype in (0, 1):
+        v, r, s_, b = rf.filter_table(ftype)
+        out["film_table_%d" % ftype], out["film_radius_%d" % ftype] = v, np.float32(r)
+        out["film_put_%d" % ftype] = rf.film_put(ftype, W, H, pos, values)[0]
     np.savez_compressed(os.path.join(HERE, "trace_ref.npz"), **out)
     print("wrote trace_ref.npz")
 

@@ -7,7 +7,7 @@ import pytest
 
 from common import (BOX_MAX, BOX_MIN, make_field, medium_props, oracle_medium_desc, oracle_render_desc,
                     random_directions, random_points_in_box, scene_dict)
-from oracle.oracle import Oracle, RefGrid, RefPhase, RefSpline, RefTrace, volume_desc
+from oracle.oracle import Oracle, RefFilm, RefGrid, RefPhase, RefSpline, RefTrace, volume_desc
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -310,6 +310,43 @@ def test_oracle_grid_lookup_bit_exact_vs_reference_golden(oracle32):
     res, data, lo, hi, p = _grid_scene()
     g = oracle32.grid_create(volume_desc(res, lo, hi), data)
     assert np.array_equal(oracle32.grid_lookup(g, p), G["grid_lookup"])
+
+
+def _film_scene():
+    rng = np.random.default_rng(41)
+    W, H, n = 37, 29, 20000
+    pos = (rng.random((n, 2)) * [W, H]).astype(np.float32)
+    pos[:6] = [[0, 0], [W, H], [0.5, 0.5], [W - 1e-3, 1e-3], [12.0, 7.0], [12.5, 7.5]]  # corners, pixel centres and edges
+    values = rng.random((n, 5)).astype(np.float32)
+    values[:, 4] = 1.0
+    values[100, 1], values[200, 3] = np.nan, np.inf  # rejected like imageblock.h:147-152
+    return W, H, pos, values
+
+
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+@pytest.mark.parametrize("ftype", [0, 1])
+def test_oracle_filter_and_film_put_bit_exact_vs_verbatim_reference(oracle32, ftype):
+    """SURVEY a23 PINNED: ReconstructionFilter::configure (rfilter.cpp:37-55), evalDiscretized (rfilter.h), the box and
+    gaussian kernels and ImageBlock::put (imageblock.h:124-206) compiled verbatim against the restatement - bit for bit"""
+    ref = RefFilm()
+    v, r, s, b = ref.filter_table(ftype)
+    ov, orr, os_ = oracle32.filter_table(ftype)
+    assert np.array_equal(ov, v) and orr == r and os_ == s and b == int(np.ceil(r - 0.5))
+    W, H, pos, values = _film_scene()
+    film, ok = ref.film_put(ftype, W, H, pos, values)
+    ofilm, ook = oracle32.film_put(ftype, W, H, pos, values)
+    assert (~ok).sum() == 2 and np.array_equal(ook, ok)
+    assert np.array_equal(ofilm, film), np.abs(ofilm - film).max()
+
+
+@pytest.mark.parametrize("ftype", [0, 1])
+def test_oracle_filter_and_film_put_bit_exact_vs_reference_golden(oracle32, ftype):
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    ov, orr, os_ = oracle32.filter_table(ftype)
+    assert np.array_equal(ov, G["film_table_%d" % ftype]) and np.float32(orr) == G["film_radius_%d" % ftype]
+    W, H, pos, values = _film_scene()
+    ofilm, ook = oracle32.film_put(ftype, W, H, pos, values)
+    assert np.array_equal(ofilm, G["film_put_%d" % ftype])
 
 
 def test_spline_interpolates_data_at_nodes(oracle64):
