@@ -16,6 +16,8 @@
  *                                                                             (ref_trace.cpp)
  *   a18               GridDataSource::lookupFloat of src/volume/gridvolume.cpp with Transform::scale / translate / operator*
  *                     of src/libcore/transform.cpp                            (ref_volume.cpp)
+ *   a19               HeterogeneousMedium::sampleDistance / evalTransmittance (Woodcock) of src/medium/heterogeneous.cpp
+ *                                                                             (ref_volume.cpp)
  *   a23               ReconstructionFilter::configure / evalDiscretized, GaussianFilter::eval, BoxFilter::eval, ImageBlock::put
  *                                                                             (ref_film.cpp)
  *   a25 - solver      er_derivativestep, computefdfBDPT (residual + Jacobian), computePathLengthsTillClosestP2,
@@ -29,7 +31,7 @@
  * functions are cut out of the reference's .cpp files by oracle/Makefile at build time and compiled inside structs that
  * declare only the data members they use, on top of the reference's own core headers; nothing is copied into this repo.
  * NOT pinned that way: the constructor's resolution of the medium properties (heterogeneousrefractive.cpp:201-300), the
- * .vol loader (a6), a19-a22, a24 (straight-ray Woodcock tracking, the bounce loop of volpath.cpp, camera, develop), Ceres' BFGS: they
+ * .vol loader (a6), a20-a22, a24 (the bounce loop of volpath.cpp with libbidir's curved-walk semantics, camera, develop), Ceres' BFGS: they
  * need Mitsuba's framework (Scene, Properties, Boost) to compile and the reference has NO golden vectors or tests for
  * them: line-by-line restatement + analytic invariants, PARITY UNPINNED by reference fixtures for those
  * rows; HG is in addition pinned statistically by the reference's chi-square test (src/tests/test_chisquare.cpp:508-572).

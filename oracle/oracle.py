@@ -407,6 +407,49 @@ class RefGrid:
         return out
 
 
+class RefHeterogeneousMedium:
+    """The reference's straight-ray HeterogeneousMedium::sampleDistance / evalTransmittance (src/medium/heterogeneous.cpp:546-672)
+    over a RefGrid, compiled verbatim; method "woodcock" | "simpson"; xi[n][k]: what sampler->next1D() returns, in order."""
+
+    def __init__(self, grid, bmin, bmax, scale, max_density, method="woodcock", step_size=0.0, albedo=(0.9, 0.9, 0.9)):
+        self.grid, self.lib = grid, grid.lib
+        self.lib.ref_hetmedium_create.restype = C.c_void_p
+        lo = (C.c_float * 3)(*[float(v) for v in bmin])
+        hi = (C.c_float * 3)(*[float(v) for v in bmax])
+        al = (C.c_float * 3)(*[float(v) for v in albedo])
+        self.h = C.c_void_p(self.lib.ref_hetmedium_create(grid.h, lo, hi, C.c_float(scale), C.c_float(max_density),
+                                                          C.c_int(1 if method == "woodcock" else 0), C.c_float(step_size), al))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_hetmedium_free(self.h)
+            self.h = None
+
+    def _rays(self, ro, rd, mint, maxt, xi):
+        ro = np.ascontiguousarray(ro, dtype=np.float32).reshape(-1, 3)
+        rd = np.ascontiguousarray(rd, dtype=np.float32).reshape(-1, 3)
+        n = ro.shape[0]
+        mint = np.ascontiguousarray(np.broadcast_to(np.asarray(mint, np.float32), (n,)))
+        maxt = np.ascontiguousarray(np.broadcast_to(np.asarray(maxt, np.float32), (n,)))
+        xi = np.ascontiguousarray(xi, dtype=np.float32).reshape(n, -1)
+        return ro, rd, mint, maxt, xi, n
+
+    def sample_distance(self, ro, rd, mint, maxt, xi):
+        ro, rd, mint, maxt, xi, n = self._rays(ro, rd, mint, maxt, xi)
+        ok, t = np.zeros(n, np.int32), np.zeros(n, np.float32)
+        ss, T = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        self.lib.ref_hetmedium_sample_distance(self.h, C.c_size_t(n), _ptr(ro, C.c_float), _ptr(rd, C.c_float), _ptr(mint, C.c_float), _ptr(maxt, C.c_float),
+                                               _ptr(xi, C.c_float), C.c_size_t(xi.shape[1]), _ptr(ok, C.c_int), _ptr(t, C.c_float), _ptr(ss, C.c_float), _ptr(T, C.c_float))
+        return ok.astype(bool), t, ss, T
+
+    def eval_transmittance(self, ro, rd, mint, maxt, xi):
+        ro, rd, mint, maxt, xi, n = self._rays(ro, rd, mint, maxt, xi)
+        out = np.zeros(n, np.float32)
+        self.lib.ref_hetmedium_eval_transmittance(self.h, C.c_size_t(n), _ptr(ro, C.c_float), _ptr(rd, C.c_float), _ptr(mint, C.c_float), _ptr(maxt, C.c_float),
+                                                  _ptr(xi, C.c_float), C.c_size_t(xi.shape[1]), _ptr(out, C.c_float))
+        return out
+
+
 class RefFilm:
     """The reference's reconstruction-filter table (rfilter.cpp / rfilter.h, gaussian.cpp, box.cpp) and ImageBlock::put
     (imageblock.h), compiled verbatim (oracle/ref_film.cpp -> oracle/_ref/libmer_reftrace.so)."""

@@ -29,7 +29,7 @@
  * from it (tests/golden/make_trace_golden.py), and tests/test_gpu_medium.py compares the CUDA stepper with it.
  */
 #include "ref_volume.h"
-namespace mitsuba { using std::endl; }
+#include "ref_records.h"
 #include <mitsuba/core/ray.h>        /* reference */
 #include <mitsuba/core/spectrum.h>   /* reference */
 #include <mitsuba/render/sampler.h>  /* oracle/shim_phase: next1D / next2D */
@@ -37,19 +37,6 @@ namespace mitsuba { using std::endl; }
 
 namespace mitsuba {
 #include "sgn_extract.inc" /* generated: template <typename T> FLOAT sgn(T) of heterogeneousrefractive.cpp:163-165 */
-
-/* MediumSamplingRecord (include/mitsuba/render/medium.h:36-108): the data members sampleDistance() writes */
-struct RefHeterogeneousRefractiveMedium;
-struct MediumSamplingRecord {
-    Float t, opticalLength;
-    Point p;
-    Vector d;
-    Float time;
-    Spectrum transmittance, sigmaA, sigmaS;
-    Float pdfSuccess, pdfSuccessRev, pdfFailure;
-    const RefHeterogeneousRefractiveMedium *medium;
-    Float refRatioSq;
-};
 
 /* HeterogeneousRefractiveMedium (src/medium/heterogeneousrefractive.cpp) reduced to what its stepper uses */
 struct RefHeterogeneousRefractiveMedium {

@@ -7,10 +7,14 @@
  * of the reference's own basisspline.h / transform.h / matrix.h / aabb.h; AABB::getCorner comes from src/libcore/aabb.cpp
  * the same way.  GridDataSource::lookupFloat (src/volume/gridvolume.cpp:337-388) likewise, with enum EVolumeType
  * (:101-106) and the three Transform functions its configure() uses (src/libcore/transform.cpp:28-65: operator*, translate,
- * scale).  Nothing is copied into this repo.
+ * scale).  And the straight-ray medium over such a grid: HeterogeneousMedium::sampleDistance / evalTransmittance
+ * (src/medium/heterogeneous.cpp:546-672, Woodcock tracking and Simpson quadrature) with integrateDensity, invertDensityIntegral,
+ * lookupDensity and enum EIntegrationMethod.  Nothing is copied into this repo.
  */
 #include "ref_volume.h"
-namespace mitsuba { using std::endl; }
+#include "ref_records.h"
+#include <mitsuba/core/ray.h>       /* reference */
+#include <mitsuba/render/sampler.h> /* oracle/shim_phase */
 #include <mitsuba/core/basisspline.h>
 namespace mitsuba { extern bool solveQuadratic(Float a, Float b, Float c, Float &x0, Float &x1); } /* util.h; bsphere.h mentions it */
 #include <mitsuba/core/aabb.h>
@@ -37,6 +41,29 @@ struct RefGridDataSource {
     EVolumeType m_volumeType;
     uint8_t *m_data;
     Float m_densityMap[256];
+};
+
+/* what HeterogeneousMedium asks of its albedo / orientation children and of its phase function */
+struct RefConstantSpectrumVolume {
+    Spectrum value;
+    Spectrum lookupSpectrum(const Point &) const { return value; }
+    Vector lookupVector(const Point &) const { return Vector(0.0f); }
+};
+struct RefPhaseSigmaDir { Float sigmaDir(Float) const { return 1.0f; } };
+
+/* HeterogeneousMedium (src/medium/heterogeneous.cpp) reduced to the data members its distance sampling uses */
+struct RefHeterogeneousMedium {
+#include "heterogeneous_extract.inc" /* generated: enum EIntegrationMethod, integrateDensity, invertDensityIntegral, evalTransmittance,
+                                        sampleDistance, lookupDensity */
+    EIntegrationMethod m_method;
+    RefGridDataSource *m_density;
+    RefConstantSpectrumVolume *m_albedo, *m_orientation;
+    RefPhaseSigmaDir *m_phaseFunction;
+    Float m_scale;
+    bool m_anisotropicMedium;
+    Float m_stepSize;
+    AABB m_densityAABB;
+    Float m_maxDensity, m_invMaxDensity;
 };
 
 RefVolume *ref_make_volume(const float *data, const int *N, const float *bmin, const float *bmax) {
@@ -86,6 +113,66 @@ void ref_grid_free(void *h) {
     RefGridDataSource *g = (RefGridDataSource *) h;
     delete[] g->m_data;
     delete g;
+}
+/* HeterogeneousMedium over the grid: method 0 Simpson quadrature, 1 Woodcock tracking; configure() :221-262 resolved by the
+ * caller: max_density = scale * (maximum of the grid), step_size for the quadrature */
+namespace {
+struct ReplaySampler : public mitsuba::Sampler {
+    const float *xi;
+    size_t k, n;
+    mitsuba::Float next1D() { return k < n ? xi[k++] : 0.5f; }
+    mitsuba::Point2 next2D() { mitsuba::Float a = next1D(), b = next1D(); return mitsuba::Point2(a, b); }
+};
+}
+void *ref_hetmedium_create(void *grid, const float *bmin, const float *bmax, float scale, float maxDensity, int method, float stepSize, const float *albedo) {
+    RefHeterogeneousMedium *m = new RefHeterogeneousMedium();
+    m->m_density = (RefGridDataSource *) grid;
+    m->m_albedo = new RefConstantSpectrumVolume();
+    for (int c = 0; c < 3; c++) m->m_albedo->value[c] = albedo[c];
+    m->m_orientation = NULL;
+    m->m_phaseFunction = NULL;
+    m->m_anisotropicMedium = false;
+    m->m_scale = scale;
+    m->m_method = (RefHeterogeneousMedium::EIntegrationMethod) method;
+    m->m_stepSize = stepSize;
+    m->m_densityAABB = AABB(Point(bmin[0], bmin[1], bmin[2]), Point(bmax[0], bmax[1], bmax[2]));
+    m->m_maxDensity = maxDensity;          /* :243: m_scale * m_density->getMaximumFloatValue() */
+    m->m_invMaxDensity = 1.0f / maxDensity; /* :244 */
+    return m;
+}
+void ref_hetmedium_free(void *h) {
+    RefHeterogeneousMedium *m = (RefHeterogeneousMedium *) h;
+    delete m->m_albedo;
+    delete m;
+}
+/* sampleDistance over n rays; xi: nxi numbers per ray that sampler->next1D() returns in order */
+void ref_hetmedium_sample_distance(void *h, size_t n, const float *ro, const float *rd, const float *mint, const float *maxt, const float *xi, size_t nxi,
+                                   int *success, float *t, float *sigmaS, float *transmittance) {
+    const RefHeterogeneousMedium *m = (const RefHeterogeneousMedium *) h;
+    for (size_t i = 0; i < n; i++) {
+        Ray ray(Point(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), Vector(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]), 0.0f);
+        ray.mint = mint[i];
+        ray.maxt = maxt[i];
+        MediumSamplingRecord mRec;
+        mRec.t = 0;
+        ReplaySampler s;
+        s.xi = xi + nxi * i; s.k = 0; s.n = nxi;
+        success[i] = m->sampleDistance(ray, mRec, &s) ? 1 : 0;
+        t[i] = mRec.t;
+        for (int c = 0; c < 3; c++) { sigmaS[3 * i + c] = success[i] ? mRec.sigmaS[c] : 0.0f; transmittance[3 * i + c] = mRec.transmittance[c]; }
+    }
+}
+void ref_hetmedium_eval_transmittance(void *h, size_t n, const float *ro, const float *rd, const float *mint, const float *maxt, const float *xi, size_t nxi,
+                                      float *out) {
+    const RefHeterogeneousMedium *m = (const RefHeterogeneousMedium *) h;
+    for (size_t i = 0; i < n; i++) {
+        Ray ray(Point(ro[3 * i], ro[3 * i + 1], ro[3 * i + 2]), Vector(rd[3 * i], rd[3 * i + 1], rd[3 * i + 2]), 0.0f);
+        ray.mint = mint[i];
+        ray.maxt = maxt[i];
+        ReplaySampler s;
+        s.xi = xi + nxi * i; s.k = 0; s.n = nxi;
+        out[i] = m->evalTransmittance(ray, &s)[0];
+    }
 }
 void ref_grid_lookup(void *h, size_t n, const float *p, float *out) {
     const RefGridDataSource *g = (const RefGridDataSource *) h;

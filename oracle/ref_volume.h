@@ -6,6 +6,7 @@
  */
 #pragma once
 #include <mitsuba/mitsuba.h>
+namespace mitsuba { using std::endl; } /* mitsuba.h brings it in; ray.h writes a bare `endl` */
 #include <mitsuba/core/matrix.h> /* reference */
 
 namespace mitsuba {

@@ -7,7 +7,7 @@ import pytest
 
 from common import (BOX_MAX, BOX_MIN, make_field, medium_props, oracle_medium_desc, oracle_render_desc,
                     random_directions, random_points_in_box, scene_dict)
-from oracle.oracle import Oracle, RefFilm, RefGrid, RefPhase, RefSpline, RefTrace, volume_desc
+from oracle.oracle import Oracle, RefFilm, RefGrid, RefHeterogeneousMedium, RefPhase, RefSpline, RefTrace, volume_desc
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -347,6 +347,39 @@ def test_oracle_filter_and_film_put_bit_exact_vs_reference_golden(oracle32, ftyp
     W, H, pos, values = _film_scene()
     ofilm, ook = oracle32.film_put(ftype, W, H, pos, values)
     assert np.array_equal(ofilm, G["film_put_%d" % ftype])
+
+
+def _woodcock_scene(n=3000):
+    from mitsubaer_b200 import fields
+    res = (24, 20, 28)
+    dens = fields.sine_density(res, BOX_MIN, BOX_MAX)
+    o = (random_points_in_box(n, 131) * 1.6).astype(np.float32)  # some origins outside the box
+    dd = random_directions(n, 132)
+    dd[:50, 0] = 0.0  # rays parallel to a slab
+    mint = np.zeros(n, np.float32)
+    maxt = (np.random.default_rng(133).random(n) * 3 + 0.1).astype(np.float32)
+    return res, dens, o, dd, mint, maxt
+
+
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+@pytest.mark.parametrize("scale", [4.0, 20.0])
+def test_oracle_straight_woodcock_bit_exact_vs_verbatim_reference(oracle32, scale):
+    """SURVEY a19 PINNED: HeterogeneousMedium::sampleDistance / evalTransmittance (heterogeneous.cpp:546-672, Woodcock tracking)
+    with lookupDensity and AABB::rayIntersect, compiled verbatim over the verbatim GridDataSource, fed the oracle's own Philox
+    draws through a replaying sampler - success, t, sigma_s and the 2-sample transmittance estimate bit for bit"""
+    res, dens, o, dd, mint, maxt = _woodcock_scene()
+    n, K = o.shape[0], 512
+    d = volume_desc(res, BOX_MIN, BOX_MAX)
+    ogrid = oracle32.grid_create(d, dens)
+    ref = RefHeterogeneousMedium(RefGrid(dens, BOX_MIN, BOX_MAX), BOX_MIN, BOX_MAX, scale, scale * 1.0, "woodcock")
+    xi = np.stack([oracle32.philox(77, i, K) for i in range(n)])
+    rok, rt, rden = oracle32.grid_sample_distance(ogrid, d, scale, o, dd, mint, maxt, 77)
+    ok, t, ss, T = ref.sample_distance(o, dd, mint, maxt, xi)
+    assert ok.sum() > n // 10 and (~ok).sum() > n // 10
+    assert np.array_equal(ok, rok) and np.array_equal(t[ok], rt[ok])
+    assert np.array_equal(ss[ok][:, 0], (np.float32(0.9) * rden[ok]).astype(np.float32))  # sigmaS = albedo * densityAtT (:641)
+    xi = np.stack([oracle32.philox(78, i, K) for i in range(n)])
+    assert np.array_equal(ref.eval_transmittance(o, dd, mint, maxt, xi), oracle32.grid_eval_transmittance(ogrid, d, scale, o, dd, mint, maxt, 78))
 
 
 def test_spline_interpolates_data_at_nodes(oracle64):
