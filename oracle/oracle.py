@@ -466,6 +466,16 @@ class RefFilm:
         self.lib.ref_filter_table(C.c_int(ftype), _ptr(vals, C.c_float), C.byref(r), C.byref(s), C.byref(b))
         return vals, r.value, s.value, b.value
 
+    def camera_rays(self, origin, target, up, fov, W, H, sample_pos):
+        """PerspectiveCameraImpl::sampleRay (perspective.cpp:247-269) behind Transform::lookAt / perspective and the reference's
+        own 4x4 inversion -> ray origins and directions for pixel samples [n][2] (fractional pixel coordinates)"""
+        sp = np.ascontiguousarray(sample_pos, dtype=np.float32).reshape(-1, 2)
+        o, d = np.zeros((sp.shape[0], 3), np.float32), np.zeros((sp.shape[0], 3), np.float32)
+        f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+        self.lib.ref_camera_rays(f3(origin), f3(target), f3(up), C.c_float(fov), C.c_int(W), C.c_int(H), C.c_size_t(sp.shape[0]), _ptr(sp, C.c_float),
+                                 _ptr(o, C.c_float), _ptr(d, C.c_float))
+        return o, d
+
     def film_put(self, ftype, W, H, pos, values):
         pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 2)
         values = np.ascontiguousarray(values, dtype=np.float32).reshape(pos.shape[0], -1)

@@ -8,11 +8,18 @@
  *     src/rfilters/box.cpp                 BoxFilter::eval (:46-48)
  *     include/mitsuba/render/imageblock.h  ImageBlock::put(const Point2 &, const Float *) (:144-206) and the Spectrum overload
  *                                          (:124-131)
+ * and SURVEY a22 (the pinhole sensor):
+ *     src/sensors/perspective.cpp          PerspectiveCameraImpl::configure, the lines that build m_cameraToSample and invert
+ *                                          it (:128-156), and sampleRay (:247-269)
+ *     src/libcore/transform.cpp            Transform::perspective (:99-123), Transform::lookAt (:191-214) [operator*, translate,
+ *                                          scale come with ref_volume.cpp]; include/mitsuba/core/matrix.inl's 4x4 inversion as it is
  * The bodies are cut out of those files by oracle/Makefile (awk, by signature) into oracle/_ref/film_*_extract.inc and
- * included into structs that declare exactly the data members they use.
+ * oracle/_ref/camera_*_extract.inc and included into structs that declare exactly the data members they use.
  */
 #include <mitsuba/mitsuba.h>
+namespace mitsuba { using std::endl; }
 #include <mitsuba/core/spectrum.h> /* reference */
+#include <mitsuba/core/transform.h> /* reference (with matrix.h / matrix.inl / ray.h) */
 #include "film_resolution_extract.inc" /* generated: #define MTS_FILTER_RESOLUTION 31 */
 
 namespace mitsuba {
@@ -55,6 +62,34 @@ struct RefImageBlock { /* include/mitsuba/render/imageblock.h reduced to the dat
     Float *m_weightsX, *m_weightsY;
     bool m_warn;
 #include "film_put_extract.inc" /* generated: both put() overloads */
+};
+
+#include "camera_util_extract.inc"      /* generated: degToRad (include/mitsuba/core/util.h:293) */
+#include "camera_transform_extract.inc" /* generated: Transform::perspective, Transform::lookAt */
+
+/* PerspectiveCameraImpl (src/sensors/perspective.cpp) reduced to what configure()'s projection lines and sampleRay() use */
+struct RefFilmSize {
+    Vector2i size;
+    Point2i offset;
+    const Vector2i &getSize() const { return size; }
+    const Vector2i &getCropSize() const { return size; }
+    const Point2i &getCropOffset() const { return offset; }
+};
+struct RefAnimatedTransform {
+    Transform t;
+    const Transform &eval(Float) const { return t; }
+};
+struct RefPerspectiveCamera {
+    RefFilmSize *m_film;
+    RefAnimatedTransform *m_worldTransform;
+    Transform m_cameraToSample, m_sampleToCamera;
+    Float m_aspect, m_xfov, m_nearClip, m_farClip;
+    Vector2 m_invResolution;
+    Float sampleTime(Float) const { return 0.0f; }
+    void configureProjection() {
+#include "camera_configure_extract.inc" /* generated: perspective.cpp:128-156 */
+    }
+#include "camera_sampleray_extract.inc" /* generated: sampleRay */
 };
 
 }
@@ -113,6 +148,33 @@ void ref_film_put(int type, int W, int H, int channels, size_t n, const float *p
             for (int k = 0; k < channels; k++)
                 out[((size_t) y * W + x) * channels + k] = bmp.data[((size_t) (y + b) * bmp.size.x + (x + b)) * channels + k];
     delete f;
+}
+
+
+/* PerspectiveCamera::sampleRay for n pixel samples: <lookat origin target up>, fov along x (sensor.cpp:244-262, fovAxis "x"),
+ * near / far clip 1e-2 / 1e4 (sensor.cpp defaults), uncropped W x H film */
+void ref_camera_rays(const float *origin, const float *target, const float *up, float fov, int W, int H, size_t n, const float *samplePos,
+                     float *o, float *d) {
+    RefFilmSize film;
+    film.size = Vector2i(W, H);
+    film.offset = Point2i(0, 0);
+    RefAnimatedTransform world;
+    world.t = Transform::lookAt(Point(origin[0], origin[1], origin[2]), Point(target[0], target[1], target[2]), Vector(up[0], up[1], up[2]));
+    RefPerspectiveCamera cam;
+    cam.m_film = &film;
+    cam.m_worldTransform = &world;
+    cam.m_aspect = film.size.x / (Float) film.size.y;                      /* sensor.cpp ProjectiveCamera::configure */
+    cam.m_xfov = fov;
+    cam.m_nearClip = 1e-2f;
+    cam.m_farClip = 1e4f;
+    cam.m_invResolution = Vector2(1.0f / film.size.x, 1.0f / film.size.y);  /* sensor.cpp Sensor::configure */
+    cam.configureProjection();
+    for (size_t i = 0; i < n; i++) {
+        Ray ray;
+        cam.sampleRay(ray, Point2(samplePos[2 * i], samplePos[2 * i + 1]), Point2(0.5f, 0.5f), 0.5f);
+        o[3 * i] = ray.o.x; o[3 * i + 1] = ray.o.y; o[3 * i + 2] = ray.o.z;
+        d[3 * i] = ray.d.x; d[3 * i + 1] = ray.d.y; d[3 * i + 2] = ray.d.z;
+    }
 }
 
 }

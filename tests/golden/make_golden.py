@@ -143,6 +143,10 @@ def trace():
         v, r, s_, b = rf.filter_table(ftype)
         out["film_table_%d" % ftype], out["film_radius_%d" % ftype] = v, np.float32(r)
         out["film_put_%d" % ftype] = rf.film_put(ftype, W, H, pos, values)[0]
+    # a22: the pinhole sensor's rays
+    from test_oracle_cpu import CAMERAS, _camera_samples
+    for k, cam in enumerate(CAMERAS):
+        out["camera_d_%d" % k] = rf.camera_rays(cam["origin"], cam["target"], cam["up"], cam["fov"], cam["width"], cam["height"], _camera_samples(cam))[1]
     np.savez_compressed(os.path.join(HERE, "trace_ref.npz"), **out)
     print("wrote trace_ref.npz")
 

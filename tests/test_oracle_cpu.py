@@ -382,6 +382,43 @@ def test_oracle_straight_woodcock_bit_exact_vs_verbatim_reference(oracle32, scal
     assert np.array_equal(ref.eval_transmittance(o, dd, mint, maxt, xi), oracle32.grid_eval_transmittance(ogrid, d, scale, o, dd, mint, maxt, 78))
 
 
+CAMERAS = [dict(origin=(0.0, 0.0, -4.0), target=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fov=40.0, width=96, height=64),
+           dict(origin=(2.5, 1.25, -3.0), target=(0.1, -0.2, 0.3), up=(0.1, 1.0, 0.2), fov=28.0, width=50, height=80)]
+
+
+def _camera_samples(cam):
+    rng = np.random.default_rng(9)
+    sp = (rng.random((5000, 2)) * [cam["width"], cam["height"]]).astype(np.float32)
+    sp[:4] = [[0, 0], [cam["width"], cam["height"]], [cam["width"] / 2, cam["height"] / 2], [0.5, cam["height"] - 0.5]]
+    return sp
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_oracle_camera_against_reference_golden(oracle32, k):
+    cam = CAMERAS[k]
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "trace_ref.npz"))
+    scene = scene_dict(cam["width"], cam["height"], 4)
+    scene.update(origin=cam["origin"], target=cam["target"], up=cam["up"], fov=cam["fov"])
+    assert np.abs(oracle32.camera_ray(oracle_render_desc(scene), _camera_samples(cam)) - G["camera_d_%d" % k]).max() <= 4e-7
+
+
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+@pytest.mark.parametrize("cam", CAMERAS)
+def test_oracle_camera_against_verbatim_reference(oracle32, cam):
+    """SURVEY a22 (pinhole sensor): PerspectiveCameraImpl's m_cameraToSample composition with the reference's own 4x4
+    inversion, sampleRay (perspective.cpp:128-156, 247-269), Transform::lookAt / perspective, compiled verbatim.  The oracle
+    and the kernels evaluate a CLOSED FORM of m_sampleToCamera, so this pin is to rounding (<= 4e-7 on unit directions),
+    not bit for bit."""
+    scene = scene_dict(cam["width"], cam["height"], 4)
+    scene.update(origin=cam["origin"], target=cam["target"], up=cam["up"], fov=cam["fov"])
+    sp = _camera_samples(cam)
+    o, d = RefFilm().camera_rays(cam["origin"], cam["target"], cam["up"], cam["fov"], cam["width"], cam["height"], sp)
+    got = oracle32.camera_ray(oracle_render_desc(scene), sp)
+    assert np.abs(o - np.asarray(cam["origin"], np.float32)).max() <= 1e-6
+    assert np.abs(np.linalg.norm(d, axis=1) - 1).max() <= 1e-6
+    assert np.abs(got - d).max() <= 4e-7, np.abs(got - d).max()
+
+
 def test_spline_interpolates_data_at_nodes(oracle64):
     """the prefilter makes the cubic B-spline INTERPOLATE the samples (that is what build3d is for)"""
     res = (16, 14, 12)
