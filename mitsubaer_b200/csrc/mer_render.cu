@@ -1420,7 +1420,11 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     if (const char *e = getenv("MER_STEP_TUNE")) tuning = atoi(e) != 0 && !P.nee && !stepEnv;
     /* probes: four rounds (wide, narrow, wide, narrow) starting at probeAt; decided at the next look at the pool; the gap to
      * the next probe doubles (32 -> 512 rounds) every time the comparison confirms the current choice */
-    unsigned long long probeAt = 5, probeGap = 32;
+    /* the first rounds of a frame are coherent camera rays, which like WIDE whatever the table (a comparison made there flips
+     * the choice for the next 40 rounds: measured on a 16-spp C5 frame, 0.83 instead of 0.9+ of the 64-spp rate), so the first
+     * probe waits for the mix of paths to settle - and longer when the previous frame of the same table left its choice */
+    const bool hinted = tuning && S.stepChoiceTable == tableBytes;
+    unsigned long long probeAt = hinted ? 49 : 17, probeGap = 32;
     auto probe_of = [&](unsigned long long round) -> int { /* -1: not a probe round, else the candidate it runs */
         if (!tuning || round < probeAt || round >= probeAt + 4) return -1;
         return (int) ((round - probeAt) & 1ull);
