@@ -13,8 +13,8 @@
  *                                          it (:128-156), and sampleRay (:247-269)
  *     src/libcore/transform.cpp            Transform::perspective (:99-123), Transform::lookAt (:191-214) [operator*, translate,
  *                                          scale come with ref_volume.cpp]; include/mitsuba/core/matrix.inl's 4x4 inversion as it is
- * The bodies are cut out of those files by oracle/Makefile (awk, by signature) into oracle/_ref/film_*_extract.inc and
- * oracle/_ref/camera_*_extract.inc and included into structs that declare exactly the data members they use.
+ * The bodies are cut out of those files by oracle/Makefile (awk, by signature) into film_*_extract.inc and camera_*_extract.inc in a
+ * temporary directory (deleted after the build) and included into structs that declare exactly the data members they use.
  */
 #include <mitsuba/mitsuba.h>
 namespace mitsuba { using std::endl; }

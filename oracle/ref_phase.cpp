@@ -7,7 +7,7 @@
  *     include/mitsuba/core/{vector,point,normal,math,constants}.h    dot / cross / safe_sqrt / sincos / Epsilon ...
  *     src/medium/maxexp.h                           MaxExpDist (strategy "maximum")            (a12)
  *     src/libcore/util.cpp  coordinateSystem()      (a17)   } the two function bodies are cut out of util.cpp by
- *     src/libcore/util.cpp  fresnelDielectricExt()  (f-3)   } oracle/Makefile into oracle/_ref/util_extract.inc
+ *     src/libcore/util.cpp  fresnelDielectricExt()  (f-3)   } oracle/Makefile into util_extract.inc (temporary dir)
  * behind a C ABI, with the reference's release flags (-DSINGLE_PRECISION -DSPECTRUM_SAMPLES=3).  Built into
  * oracle/_ref/libmer_refphase.so; tests/test_oracle_cpu.py checks the restated HG / coordinateSystem / Fresnel of
  * oracle/mer_oracle.cpp against it bit for bit, and tests/golden/phase_ref.npz holds vectors generated from it.

@@ -15,7 +15,7 @@
  *     src/volume/splinevolume.cpp              SplineDataSource's lookups (:319-377), in ref_volume.cpp
  *     src/libcore/aabb.cpp                     AABB::getCorner (:23-27), in ref_volume.cpp
  * The member-function bodies are cut out of the two .cpp files by oracle/Makefile (awk, by signature) into
- * oracle/_ref/hetref_extract.inc and oracle/_ref/splinevolume_extract.inc and included into two structs (two translation units) that declare
+ * hetref_extract.inc and splinevolume_extract.inc (a temporary directory, deleted after the build) and included into two structs (two translation units) that declare
  * exactly the data members those bodies use.  Underneath them the reference's own headers are compiled as they are:
  * include/mitsuba/core/{basisspline,transform,matrix,ray,aabb,vector,point,normal,math,constants,fwd,platform}.h
  * (oracle/shim_phase stands in for mitsuba.h / stream.h, oracle/shim_trace for the one Boost header matrix.h asks for).

@@ -3,7 +3,7 @@
  *
  * SplineDataSource's lookups (src/volume/splinevolume.cpp:319-377: insideVolumeLimits, maxSDFError, value, gradient, hessian,
  * valueAndGradient, gradientAndHessian, valueGradientAndHessian), cut out of the .cpp by oracle/Makefile into
- * oracle/_ref/splinevolume_extract.inc and compiled VERBATIM inside a struct that declares the data members they use, on top
+ * splinevolume_extract.inc (a temporary directory, deleted after the build) and compiled VERBATIM inside a struct that declares the data members they use, on top
  * of the reference's own basisspline.h / transform.h / matrix.h / aabb.h; AABB::getCorner comes from src/libcore/aabb.cpp
  * the same way.  GridDataSource::lookupFloat (src/volume/gridvolume.cpp:337-388) likewise, with enum EVolumeType
  * (:101-106) and the three Transform functions its configure() uses (src/libcore/transform.cpp:28-65: operator*, translate,
