@@ -9,6 +9,8 @@
  *   a1-a4 + Hessian   include/mitsuba/core/basisspline.h                      (ref_spline.cpp, float and double)
  *   a5 (lookups)      SplineDataSource::insideVolumeLimits / value / gradient / valueAndGradient of
  *                     src/volume/splinevolume.cpp                             (ref_trace.cpp)
+ *   a6                SplineDataSource::loadFromFile of src/volume/splinevolume.cpp reads the .vol files this repo writes
+ *                                                                             (ref_volume.cpp)
  *   a7-a11            er_step, trace, aggressive_trace, traceTillBoundary, insideShape (= hackForSphere, the hard-coded
  *                     sphere) of src/medium/heterogeneousrefractive.cpp       (ref_trace.cpp)
  *   a10, a12-a14      Medium::sampleDistance (all four strategies + the aggressive-tracing loop over the signed distance)
@@ -31,7 +33,7 @@
  * functions are cut out of the reference's .cpp files by oracle/Makefile at build time and compiled inside structs that
  * declare only the data members they use, on top of the reference's own core headers; nothing is copied into this repo.
  * NOT pinned that way: the constructor's resolution of the medium properties (heterogeneousrefractive.cpp:201-300), the
- * .vol loader (a6), a20-a22, a24 (the bounce loop of volpath.cpp with libbidir's curved-walk semantics, camera, develop), Ceres' BFGS: they
+ * a20-a21, a24 (the bounce loop of volpath.cpp with libbidir's curved-walk semantics, develop), Ceres' BFGS: they
  * need Mitsuba's framework (Scene, Properties, Boost) to compile and the reference has NO golden vectors or tests for
  * them: line-by-line restatement + analytic invariants, PARITY UNPINNED by reference fixtures for those
  * rows; HG is in addition pinned statistically by the reference's chi-square test (src/tests/test_chisquare.cpp:508-572).

@@ -213,12 +213,18 @@ class RefTrace:
     hard-coded sphere) of src/medium/heterogeneousrefractive.cpp and SplineDataSource's lookup wrappers of
     src/volume/splinevolume.cpp — compiled verbatim (oracle/ref_trace.cpp -> oracle/_ref/libmer_reftrace.so), FLOAT = float."""
 
-    def __init__(self, data, bmin, bmax, stepsize):
+    def __init__(self, data, bmin=None, bmax=None, stepsize=1e-3):
+        """data: a float grid [z][y][x] with its bounding box, or the path of a .vol file, which is then read by the reference's
+        own SplineDataSource::loadFromFile (splinevolume.cpp:204-317)"""
         path = os.path.join(REF_DIR, "libmer_reftrace.so")
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.lib = C.CDLL(path)
         self.lib.ref_medium_create.restype = C.c_void_p
+        self.lib.ref_medium_create_from_file.restype = C.c_void_p
+        if isinstance(data, (str, os.PathLike)):
+            self.h = C.c_void_p(self.lib.ref_medium_create_from_file(os.fspath(data).encode(), C.c_float(stepsize)))
+            return
         data = np.ascontiguousarray(data, dtype=np.float32)
         N = (C.c_int * 3)(data.shape[2], data.shape[1], data.shape[0])  # arrays are [z][y][x]
         lo = (C.c_float * 3)(*[float(v) for v in bmin])

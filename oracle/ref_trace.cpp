@@ -96,6 +96,23 @@ void ref_medium_configure(void *h, const float *sigmaA, const float *sigmaS, int
     m->m_aggressiveTracing = sdf && aggressive;
 }
 
+/* the medium over a .vol file read by the reference's loader */
+void *ref_medium_create_from_file(const char *path, float stepsize) {
+    RefVolume *rif = ref_load_volume(path);
+    RefHeterogeneousRefractiveMedium *m = new RefHeterogeneousRefractiveMedium();
+    m->m_rif = rif;
+    m->m_SDF = rif;
+    m->m_erstepsize = stepsize;
+    m->m_precision = 6;
+    m->m_tol = 1e-6f;
+    m->m_aggressiveTracing = false;
+    m->m_maxExpDist = NULL;
+    m->m_strategy = RefHeterogeneousRefractiveMedium::ESingle;
+    m->m_samplingDensity = 1;
+    m->m_mediumSamplingWeight = 0.5f;
+    return m;
+}
+
 void ref_medium_free(void *h) {
     RefHeterogeneousRefractiveMedium *m = (RefHeterogeneousRefractiveMedium *) h;
     if (m->m_SDF != m->m_rif) delete m->m_SDF;

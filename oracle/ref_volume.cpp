@@ -5,7 +5,9 @@
  * valueAndGradient, gradientAndHessian, valueGradientAndHessian), cut out of the .cpp by oracle/Makefile into
  * splinevolume_extract.inc (a temporary directory, deleted after the build) and compiled VERBATIM inside a struct that declares the data members they use, on top
  * of the reference's own basisspline.h / transform.h / matrix.h / aabb.h; AABB::getCorner comes from src/libcore/aabb.cpp
- * the same way.  GridDataSource::lookupFloat (src/volume/gridvolume.cpp:337-388) likewise, with enum EVolumeType
+ * the same way, and SplineDataSource::loadFromFile (:204-317, SURVEY a6: the .vol v3 header, the float -> FLOAT copy, the
+ * prefilter) with enum EVolumeType, behind stand-ins for the framework plumbing it names (fs::path, the file resolver, the memory
+ * map, MemoryStream).  GridDataSource::lookupFloat (src/volume/gridvolume.cpp:337-388) likewise, with enum EVolumeType
  * (:101-106) and the three Transform functions its configure() uses (src/libcore/transform.cpp:28-65: operator*, translate,
  * scale).  And the straight-ray medium over such a grid: HeterogeneousMedium::sampleDistance / evalTransmittance
  * (src/medium/heterogeneous.cpp:546-672, Woodcock tracking and Simpson quadrature) with integrateDensity, invertDensityIntegral,
@@ -22,7 +24,62 @@ namespace mitsuba { extern bool solveQuadratic(Float a, Float b, Float c, Float 
 namespace mitsuba {
 #include "aabb_extract.inc" /* generated: AABB::getCorner from src/libcore/aabb.cpp */
 
+/* ---- what loadFromFile() names of the framework, reduced to what it does with it (TEST INFRASTRUCTURE) */
+namespace fs {
+struct path {
+    std::string s;
+    path() {}
+    path(const std::string &x) : s(x) {}
+    path(const char *x) : s(x) {}
+    path filename() const { size_t k = s.find_last_of('/'); return path(k == std::string::npos ? s : s.substr(k + 1)); }
+    const std::string &string() const { return s; }
+};
+}
+template <typename T> struct ref {
+    T *p;
+    ref(T *q = NULL) : p(q) {}
+    T *operator->() const { return p; }
+    T *get() const { return p; }
+};
+struct FileResolver { fs::path resolve(const fs::path &p) const { return p; } };
+struct Thread {
+    static Thread *getThread() { static Thread t; return &t; }
+    FileResolver *getFileResolver() { static FileResolver r; return &r; }
+};
+struct MemoryMappedFile { /* the whole file in memory */
+    std::vector<char> buf;
+    explicit MemoryMappedFile(const fs::path &p) {
+        FILE *f = fopen(p.string().c_str(), "rb");
+        if (!f) throw std::runtime_error("cannot open " + p.string());
+        fseek(f, 0, SEEK_END);
+        buf.resize((size_t) ftell(f));
+        fseek(f, 0, SEEK_SET);
+        if (fread(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); throw std::runtime_error("short read"); }
+        fclose(f);
+    }
+    void *getData() { return buf.data(); }
+    size_t getSize() const { return buf.size(); }
+};
+struct MemoryStream { /* little-endian reads from a memory block (this host is little-endian) */
+    const char *d;
+    size_t n, pos;
+    MemoryStream(void *data, size_t size) : d((const char *) data), n(size), pos(0) {}
+    void setByteOrder(Stream::EByteOrder) {}
+    void read(void *dst, size_t k) { if (pos + k > n) throw std::runtime_error("read past the end"); memcpy(dst, d + pos, k); pos += k; }
+    int readInt() { int32_t v; read(&v, 4); return v; }
+    float readSingle() { float v; read(&v, 4); return v; }
+};
+inline std::string memString(size_t) { return std::string(); }
+
 struct RefSplineDataSource : public RefVolume {
+#include "splinevolume_loader_extract.inc" /* generated: enum EVolumeType, loadFromFile */
+    fs::path m_filename;
+    ref<MemoryMappedFile> m_mmap;
+    Vector3i m_res;
+    int m_channels;
+    EVolumeType m_volumeType;
+    AABB m_dataAABB; /* default-constructed = invalid: the bounding box comes from the file */
+    uint8_t *m_data;
     basisspline::Spline<3> m_spline;
     Transform m_worldToVolume;                 /* toWorld = identity: Transform() */
     Matrix3x3F m_worldToVolume_Rot, m_worldToVolume_RotT;
@@ -83,6 +140,15 @@ RefVolume *ref_make_volume(const float *data, const int *N, const float *bmin, c
     delete[] tmp;
     rif->m_worldToVolume_Rot.setIdentity();  /* :90-92 with an identity toWorld */
     rif->m_worldToVolume_RotT.setIdentity();
+    return rif;
+}
+
+/* SplineDataSource from a .vol file through the reference's own loadFromFile() */
+RefVolume *ref_load_volume(const char *path) {
+    RefSplineDataSource *rif = new RefSplineDataSource();
+    rif->m_worldToVolume_Rot.setIdentity();
+    rif->m_worldToVolume_RotT.setIdentity();
+    rif->loadFromFile(fs::path(path));
     return rif;
 }
 

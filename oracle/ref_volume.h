@@ -23,4 +23,6 @@ struct RefVolume {
 };
 /* SplineDataSource over a float grid [z][y][x] with an identity toWorld (ref_volume.cpp) */
 RefVolume *ref_make_volume(const float *data, const int *N, const float *bmin, const float *bmax);
+/* the same from a .vol file, through SplineDataSource::loadFromFile (ref_volume.cpp) */
+RefVolume *ref_load_volume(const char *path);
 }

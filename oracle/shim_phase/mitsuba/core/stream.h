@@ -4,6 +4,7 @@
 namespace mitsuba {
 class Stream {
 public:
+    enum EByteOrder { EBigEndian = 0, ELittleEndian = 1 }; /* stream.h: loadFromFile() of splinevolume.cpp names it */
     template <typename T> T readElement() { return T(); }
     template <typename T> void writeElement(T) {}
     float readFloat() { return 0.0f; }

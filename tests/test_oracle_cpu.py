@@ -419,6 +419,34 @@ def test_oracle_camera_against_verbatim_reference(oracle32, cam):
     assert np.abs(got - d).max() <= 4e-7, np.abs(got - d).max()
 
 
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+def test_vol_file_is_what_the_reference_loader_reads(oracle32, tmp_path):
+    """a .vol v3 file written by this repo's writer (mer_vol_write, the format of mfiles/writeGridToVol.m) is read by
+    the reference's OWN loader - SplineDataSource::loadFromFile (splinevolume.cpp:204-317: header, bounding box, payload offset,
+    float -> FLOAT copy, prefilter), compiled verbatim - and gives, bit for bit, the spline built from the array in memory"""
+    from mitsubaer_b200 import fields
+    rng = np.random.default_rng(51)
+    res = (19, 23, 17)
+    data = (1.0 + rng.random((res[2], res[1], res[0]))).astype(np.float32)
+    lo, hi = np.array([-1.25, 0.5, -0.75], np.float32), np.array([0.5, 2.0, 1.0], np.float32)
+    path = tmp_path / "rif.vol"
+    fields.write_vol(path, data, lo, hi)
+    raw = path.read_bytes()
+    assert raw[:4] == b"VOL\x03" and len(raw) == 48 + data.size * 4
+    pitch = (hi - lo) / (np.array(res, np.float32) - 1)
+    p = (lo + 2.1 * pitch + rng.random((4000, 3)) * (hi - lo - 4.2 * pitch)).astype(np.float32)
+    from_file, from_array = RefTrace(path), RefTrace(data, lo, hi, 1e-3)
+    f1, g1 = from_file.value_gradient(p)
+    f2, g2 = from_array.value_gradient(p)
+    assert np.array_equal(f1, f2) and np.array_equal(g1, g2)
+    assert np.array_equal(from_file.inside_limits(p), from_array.inside_limits(p))
+    orif = oracle32.rif_create(volume_desc(res, lo, hi), data)
+    f3, g3 = oracle32.rif_eval(orif, p, what=2)
+    assert np.array_equal(np.asarray(f3, np.float32), f1) and np.array_equal(np.asarray(g3, np.float32), g1)
+    d2, lo2, hi2 = fields.read_vol(path)  # and this repo's reader returns what was written
+    assert np.array_equal(d2, data) and np.array_equal(lo2, lo) and np.array_equal(hi2, hi)
+
+
 def test_spline_interpolates_data_at_nodes(oracle64):
     """the prefilter makes the cubic B-spline INTERPOLATE the samples (that is what build3d is for)"""
     res = (16, 14, 12)
