@@ -32,7 +32,7 @@
  * and against golden vectors generated from those builds (the .npz files under tests/golden, make_golden.py).  The member
  * functions are cut out of the reference's .cpp files by oracle/Makefile at build time and compiled inside structs that
  * declare only the data members they use, on top of the reference's own core headers; nothing is copied into this repo.
- * NOT pinned that way: the constructor's resolution of the medium properties (heterogeneousrefractive.cpp:201-300), the
+ * NOT pinned that way (the constructor's resolution of mediumSamplingWeight / strategy, :238-293, IS: ref_trace.cpp): the
  * a20-a21, a24 (the bounce loop of volpath.cpp with libbidir's curved-walk semantics, develop), Ceres' BFGS: they
  * need Mitsuba's framework (Scene, Properties, Boost) to compile and the reference has NO golden vectors or tests for
  * them: line-by-line restatement + analytic invariants, PARITY UNPINNED by reference fixtures for those

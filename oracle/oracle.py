@@ -314,6 +314,16 @@ class RefTrace:
                                           None, None, None, None, C.c_int(0))
         return self
 
+    def resolve(self, sigma_a, sigma_s, strategy, medium_sampling_weight=-1.0, sampling_density=0.0, channel=-1):
+        """the constructor's resolution of the free-flight sampling (heterogeneousrefractive.cpp:238-293), compiled verbatim
+        -> (mediumSamplingWeight, samplingDensity, strategy index)"""
+        sa = (C.c_float * 3)(*[float(x) for x in np.broadcast_to(np.asarray(sigma_a, np.float32), (3,))])
+        ss = (C.c_float * 3)(*[float(x) for x in np.broadcast_to(np.asarray(sigma_s, np.float32), (3,))])
+        w, d, st = C.c_float(), C.c_float(), C.c_int()
+        self.lib.ref_medium_resolve(self.h, sa, ss, strategy.encode(), C.c_float(medium_sampling_weight), C.c_float(sampling_density), C.c_int(channel),
+                                    C.byref(w), C.byref(d), C.byref(st))
+        return w.value, d.value, st.value
+
     def sample_distance(self, ro, rd, mint, xi):
         """Medium::sampleDistance (heterogeneousrefractive.cpp:402-568) over a batch; xi[n][2] replays sampler->next1D()"""
         ro = np.ascontiguousarray(ro, dtype=np.float32).reshape(-1, 3)

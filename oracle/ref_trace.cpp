@@ -34,6 +34,7 @@
 #include <mitsuba/core/spectrum.h>   /* reference */
 #include <mitsuba/render/sampler.h>  /* oracle/shim_phase: next1D / next2D */
 #include <medium/maxexp.h>           /* reference (src/medium/maxexp.h): MaxExpDist */
+#include <mitsuba/core/properties.h> /* oracle/shim_phase */
 
 namespace mitsuba {
 #include "sgn_extract.inc" /* generated: template <typename T> FLOAT sgn(T) of heterogeneousrefractive.cpp:163-165 */
@@ -51,6 +52,10 @@ struct RefHeterogeneousRefractiveMedium {
                                  aggressive_trace, insideShape, hackForSphere, hackForBox, traceTillBoundary, er_derivativestep,
                                  computefdfBDPT, computePathLengthsTillClosestP2, boundaryVelocity, boundaryVelocityDerivative */
     ESamplingStrategy m_strategy;
+    /* the part of the constructor (:238-293) that resolves mediumSamplingWeight, the sampling strategy and its density */
+    void resolve(const Properties &props, const std::string &strategy) {
+#include "hetref_ctor_extract.inc" /* generated */
+    }
 };
 
 }
@@ -94,6 +99,25 @@ void ref_medium_configure(void *h, const float *sigmaA, const float *sigmaS, int
     if (m->m_SDF != m->m_rif) delete m->m_SDF;
     m->m_SDF = sdf ? ref_make_volume(sdf, N, bmin, bmax) : m->m_rif;
     m->m_aggressiveTracing = sdf && aggressive;
+}
+
+/* the constructor's resolution of the free-flight sampling (:238-293) from sigmaA / sigmaS and the properties
+ * mediumSamplingWeight (-1 = automatic), strategy, samplingDensity (manual), channel (-1 = automatic) */
+void ref_medium_resolve(void *h, const float *sigmaA, const float *sigmaS, const char *strategy, float mediumSamplingWeight, float samplingDensity,
+                        int channel, float *weightOut, float *densityOut, int *strategyOut) {
+    RefHeterogeneousRefractiveMedium *m = (RefHeterogeneousRefractiveMedium *) h;
+    for (int i = 0; i < 3; i++) { m->m_sigmaA[i] = sigmaA[i]; m->m_sigmaS[i] = sigmaS[i]; }
+    m->m_sigmaT = m->m_sigmaA + m->m_sigmaS; /* Medium::Medium, src/librender/medium.cpp:36 */
+    m->m_samplingDensity = 0.0f;             /* initialiser list, :202 */
+    if (m->m_maxExpDist) { delete m->m_maxExpDist; m->m_maxExpDist = NULL; }
+    Properties props;
+    if (mediumSamplingWeight != -1) props.floats["mediumSamplingWeight"] = mediumSamplingWeight;
+    if (samplingDensity > 0) props.floats["samplingDensity"] = samplingDensity;
+    if (channel >= 0) props.floats["channel"] = (float) channel;
+    m->resolve(props, strategy);
+    *weightOut = m->m_mediumSamplingWeight;
+    *densityOut = m->m_samplingDensity;
+    *strategyOut = (int) m->m_strategy;
 }
 
 /* the medium over a .vol file read by the reference's loader */

@@ -447,6 +447,34 @@ def test_vol_file_is_what_the_reference_loader_reads(oracle32, tmp_path):
     assert np.array_equal(d2, data) and np.array_equal(lo2, lo) and np.array_equal(hi2, hi)
 
 
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+def test_oracle_medium_property_resolution_vs_verbatim_reference(oracle32):
+    """the constructor of HeterogeneousRefractiveMedium (:238-293: automatic mediumSamplingWeight = max albedo, at least 0.5;
+    strategy single = the channel with the smallest sigma_t; manual; balance; maximum), compiled verbatim, against the
+    restated resolution (what plugins.HeterogeneousRefractiveMedium.configure and mer_medium_create do too)"""
+    data, lo, hi = make_field("linear", 16)
+    ref = RefTrace(data, lo, hi, 1e-2)
+    orif = oracle32.rif_create(volume_desc((16,) * 3, lo, hi), data)
+    cases = [dict(sigmaS=(3.6, 3.6, 3.6), sigmaA=(0.4, 0.4, 0.4), strategy="single"),
+             dict(sigmaS=(2.0, 3.0, 4.0), sigmaA=(0.5, 0.25, 0.1), strategy="single"),
+             dict(sigmaS=(0.1, 0.2, 0.05), sigmaA=(1.0, 1.0, 1.0), strategy="balance"),        # albedo < 0.5 -> weight 0.5
+             dict(sigmaS=(0.0, 0.0, 0.0), sigmaA=(1.0, 2.0, 3.0), strategy="single"),          # no scattering -> weight 0
+             dict(sigmaS=(2.0, 0.0, 1.0), sigmaA=(0.5, 0.0, 3.0), strategy="balance"),         # a channel with sigma_t = 0
+             dict(sigmaS=(2.0, 3.0, 4.0), sigmaA=(0.5, 0.25, 0.1), strategy="manual", samplingDensity=2.5),
+             dict(sigmaS=(2.0, 3.0, 0.4), sigmaA=(0.5, 0.25, 0.1), strategy="maximum"),
+             dict(sigmaS=(2.0, 3.0, 4.0), sigmaA=(0.5, 0.25, 0.1), strategy="single", mediumSamplingWeight=0.8)]
+    for c in cases:
+        props = medium_props(stepsize=1e-2, **c)
+        omed = oracle32.medium_create(oracle_medium_desc(props), orif)
+        w, sd = oracle32.medium_resolved(omed)
+        rw, rsd, rst = ref.resolve(c["sigmaA"], c["sigmaS"], c["strategy"], c.get("mediumSamplingWeight", -1.0), c.get("samplingDensity", 0.0))
+        assert np.float32(w) == np.float32(rw), (c, w, rw)
+        if c["strategy"] in ("single", "manual"):
+            assert np.float32(sd) == np.float32(rsd), (c, sd, rsd)
+        assert rst == {"balance": 0, "single": 1, "manual": 2, "maximum": 3}[c["strategy"]]
+        oracle32.medium_destroy(omed)
+
+
 def test_spline_interpolates_data_at_nodes(oracle64):
     """the prefilter makes the cubic B-spline INTERPOLATE the samples (that is what build3d is for)"""
     res = (16, 14, 12)
