@@ -1327,13 +1327,28 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
 
     const unsigned TPB = 128;
     unsigned pool = r->pool_paths > 0 ? (unsigned) r->pool_paths : 148u * 16384u; /* 2.4 M slots, 310 MB: a round's tail is amortised over more visits */
+    int l2Bytes = 0;
+    cudaDeviceGetAttribute(&l2Bytes, cudaDevAttrL2CacheSize, m->device);
+    const size_t tableBytes = (size_t) m->dev.rif.N[0] * m->dev.rif.N[1] * m->dev.rif.N[2] * (m->rif->mode == MER_RIF_TRICUBIC ? (m->dev.rif.coeff8 ? 32u : 4u) : 16u);
+    if (r->pool_paths <= 0 && tableBytes > (size_t) std::max(l2Bytes, 1)) {
+        /* A table larger than the L2: the samples in flight are consecutive pixels (pixel-major sample ids), i.e. a slab of the
+         * volume about pool / (samples of this call) of the table thick.  With few samples per pixel on this GPU (an N-GPU
+         * frame gives a rank 1/N of them) the default pool spreads over N times more image rows and the slab outgrows the
+         * L2, and the frame's ramp and drain rounds, whose number does not shrink with the work, weigh N times more.
+         * Keep the slab at about a third of the L2.  Measured on one rank's share of the 64-spp C5 frame (tools/c5_rank_probe.py):
+         * 16 spp 9.4 -> 10.5 G ray steps/s with 0.6 M slots, 8 spp 8.2 -> 10.0 G with 0.3 M (64 spp, 2.4 M slots: 10.9 G). */
+        const double fit = (double) l2Bytes / 3.0 * (double) P.totalSamples / (double) tableBytes;
+        pool = (unsigned) std::min((double) pool, std::max(fit, 148.0 * 2048.0));
+    }
     if (const char *e = getenv("MER_POOL")) pool = (unsigned) atol(e); /* tuning knob */
     if ((unsigned long long) pool > P.totalSamples) pool = (unsigned) P.totalSamples;
     pool = std::max(((pool + TPB - 1) / TPB) * TPB, TPB);
 
     RenderScratch &S = mer::device_scratch(m->device);
     std::lock_guard<std::mutex> hold(S.lock);
-    const size_t qBytes = (size_t) pool * 16;
+    /* the scratch is sized for the default pool at least: frames of one scene choose pools of different sizes (above), and
+     * re-allocating between two of them costs more than the smaller frame (cudaFree synchronises: 0.6-1.5 s measured) */
+    const size_t qBytes = (size_t) std::max(pool, r->pool_paths > 0 ? 0u : 148u * 16384u) * 16;
     if (S.poolBytes < qBytes) {
         S.release();
         cudaError_t e = cudaSuccess;
@@ -1413,9 +1428,6 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
     if (const char *e = getenv("MER_STEP_CTAS")) { stepFixed.ctas = (unsigned) std::min(std::max(atoi(e), 1), 16); stepEnv = true; } /* tuning knobs */
     if (const char *e = getenv("MER_STEP_TPB")) { stepFixed.tpb = (unsigned) std::min(std::max(atoi(e) / 32 * 32, 32), (int) TPB); stepEnv = true; }
     if (stepFixed.ctas * stepFixed.tpb > (unsigned) MER_RENDER_MIN_BLOCKS * TPB) stepFixed.ctas = (unsigned) MER_RENDER_MIN_BLOCKS * TPB / stepFixed.tpb;
-    int l2Bytes = 0;
-    cudaDeviceGetAttribute(&l2Bytes, cudaDevAttrL2CacheSize, m->device);
-    const size_t tableBytes = (size_t) m->dev.rif.N[0] * m->dev.rif.N[1] * m->dev.rif.N[2] * (m->rif->mode == MER_RIF_TRICUBIC ? (m->dev.rif.coeff8 ? 32u : 4u) : 16u);
     bool tuning = !stepEnv && !P.nee && tableBytes > (size_t) std::max(l2Bytes, 1);
     if (const char *e = getenv("MER_STEP_TUNE")) tuning = atoi(e) != 0 && !P.nee && !stepEnv;
     /* probes: four rounds (wide, narrow, wide, narrow) starting at probeAt; decided at the next look at the pool; the gap to
