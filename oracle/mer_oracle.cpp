@@ -27,7 +27,8 @@
  *                                                                             (ref_trace.cpp)
  *   a15-a17           src/phase/hg.cpp, include/mitsuba/core/{frame,vector,math,constants}.h,
  *                     coordinateSystem() of src/libcore/util.cpp              (ref_phase.cpp)
- *   hdielectric       fresnelDielectricExt() of src/libcore/util.cpp          (ref_phase.cpp)
+ *   hdielectric       fresnelDielectricExt() of src/libcore/util.cpp; HSmoothDielectric::sample / reflect / refract /
+ *                     getEtaInvEta of src/bsdfs/hdielectric.cpp (direction to rounding)   (ref_phase.cpp)
  *   strategy maximum  src/medium/maxexp.h (MaxExpDist)                        (ref_phase.cpp)
  * and against golden vectors generated from those builds (the .npz files under tests/golden, make_golden.py).  The member
  * functions are cut out of the reference's .cpp files by oracle/Makefile at build time and compiled inside structs that
@@ -2241,6 +2242,12 @@ extern "C" void orc_film_put(int type, int W, int H, int channels, size_t n, con
     Filter f;
     f.configure(type);
     for (size_t i = 0; i < n; i++) ok[i] = film_put(film, W, H, f, pos[2 * i], pos[2 * i + 1], values + (size_t) channels * i, channels) ? 1 : 0;
+}
+/* HSmoothDielectric::sample in world space (hdielectric.cpp:244-300) over n rays */
+extern "C" void orc_hdielectric_sample(size_t n, const float *d, const float *N, const float *eta, const float *u, int mode, float *dOut,
+                                       float *weight, float *etaScale, int *transmitted) {
+    for (size_t i = 0; i < n; i++)
+        transmitted[i] = hdielectricSample(d + 3 * i, N + 3 * i, eta[i], u[i], dOut + 3 * i, weight[i], etaScale[i], mode == 0) ? 1 : 0;
 }
 extern "C" void orc_camera_ray(const mer_render_desc *r, size_t n, const float *samplePos, float *d) {
     Camera c;

@@ -195,6 +195,19 @@ class RefPhase:
         self.lib.ref_coordinate_system(C.c_size_t(a.shape[0]), _ptr(a, C.c_float), _ptr(b, C.c_float), _ptr(c, C.c_float))
         return b, c
 
+    def hdielectric_sample(self, d, N, eta, u, importance=False):
+        """HSmoothDielectric::sample (hdielectric.cpp:244-300) for rays along d at a surface with normal N and interior index eta
+        -> (direction out, weight, relative index of the event, transmitted?)"""
+        d = np.ascontiguousarray(d, dtype=np.float32).reshape(-1, 3)
+        N = np.ascontiguousarray(N, dtype=np.float32).reshape(-1, 3)
+        n = d.shape[0]
+        eta = np.ascontiguousarray(np.broadcast_to(np.asarray(eta, np.float32), (n,)))
+        u = np.ascontiguousarray(u, dtype=np.float32).reshape(-1)
+        out, w, es, tr = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        self.lib.ref_hdielectric_sample(C.c_size_t(n), _ptr(d, C.c_float), _ptr(N, C.c_float), _ptr(eta, C.c_float), _ptr(u, C.c_float), C.c_int(1 if importance else 0),
+                    _ptr(out, C.c_float), _ptr(w, C.c_float), _ptr(es, C.c_float), _ptr(tr, C.c_int))
+        return out, w, es, tr.astype(bool)
+
     def maxexp(self, sigma_t, what, x):
         """MaxExpDist (src/medium/maxexp.h): what = 0 sample(u) -> (t, pdf); 1 pdf(t); 2 cdf(t)"""
         return _maxexp(self.lib.ref_maxexp, sigma_t, what, x)
@@ -779,6 +792,19 @@ class Oracle:
         self.lib.orc_film_put(C.c_int(ftype), C.c_int(W), C.c_int(H), C.c_int(values.shape[1]), C.c_size_t(pos.shape[0]), _ptr(pos, C.c_float),
                               _ptr(values, C.c_float), _ptr(film, C.c_float), _ptr(ok, C.c_int))
         return film, ok.astype(bool)
+
+    def hdielectric_sample(self, d, N, eta, u, importance=False):
+        """HSmoothDielectric::sample (hdielectric.cpp:244-300) for rays along d at a surface with normal N and interior index eta
+        -> (direction out, weight, relative index of the event, transmitted?)"""
+        d = np.ascontiguousarray(d, dtype=np.float32).reshape(-1, 3)
+        N = np.ascontiguousarray(N, dtype=np.float32).reshape(-1, 3)
+        n = d.shape[0]
+        eta = np.ascontiguousarray(np.broadcast_to(np.asarray(eta, np.float32), (n,)))
+        u = np.ascontiguousarray(u, dtype=np.float32).reshape(-1)
+        out, w, es, tr = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32)
+        self.lib.orc_hdielectric_sample(C.c_size_t(n), _ptr(d, C.c_float), _ptr(N, C.c_float), _ptr(eta, C.c_float), _ptr(u, C.c_float), C.c_int(1 if importance else 0),
+                    _ptr(out, C.c_float), _ptr(w, C.c_float), _ptr(es, C.c_float), _ptr(tr, C.c_int))
+        return out, w, es, tr.astype(bool)
 
     def camera_ray(self, rdesc, sample_pos):
         sp = np.ascontiguousarray(sample_pos, dtype=np.float32).reshape(-1, 2)

@@ -7,6 +7,8 @@
  *     include/mitsuba/core/{vector,point,normal,math,constants}.h    dot / cross / safe_sqrt / sincos / Epsilon ...
  *     src/medium/maxexp.h                           MaxExpDist (strategy "maximum")            (a12)
  *     src/libcore/util.cpp  coordinateSystem()      (a17)   } the two function bodies are cut out of util.cpp by
+ *     src/bsdfs/hdielectric.cpp                     HSmoothDielectric::sample(bRec, p, sample) (:244-300), reflect (:86-88),
+ *                                                   refract (:119-125), getEtaInvEta (:113-117)      (SURVEY f-3)
  *     src/libcore/util.cpp  fresnelDielectricExt()  (f-3)   } oracle/Makefile into util_extract.inc (temporary dir)
  * behind a C ABI, with the reference's release flags (-DSINGLE_PRECISION -DSPECTRUM_SAMPLES=3).  Built into
  * oracle/_ref/libmer_refphase.so; tests/test_oracle_cpu.py checks the restated HG / coordinateSystem / Fresnel of
@@ -23,6 +25,32 @@ namespace mitsuba {
 
 #include <phase/hg.cpp> /* -I/root/reference/src */
 #include <medium/maxexp.h> /* MaxExpDist, the "maximum" free-flight strategy (heterogeneousrefractive.cpp:287-291, 437-445, 534-536) */
+
+#include <mitsuba/core/spectrum.h> /* reference */
+namespace mitsuba {
+/* what HSmoothDielectric::sample names of the framework, reduced (the enumerators' values: include/mitsuba/render/bsdf.h:240-242,
+ * include/mitsuba/render/common.h:38-40) */
+enum { EDeltaReflection = 0x00020, EDeltaTransmission = 0x00040 };
+enum ETransportMode { ERadiance = 0, EImportance = 1 };
+struct Intersection {};
+struct BSDFSamplingRecord {
+    Intersection its;
+    Vector wi, wo;
+    Float eta;
+    ETransportMode mode;
+    unsigned int typeMask;
+    int component, sampledComponent;
+    unsigned int sampledType;
+};
+struct RefUnitTexture { Spectrum eval(const Intersection &) const { return Spectrum(1.0f); } };
+struct RefInteriorMedium { Float rif; Float getRIF(const Point &) const { return rif; } };
+struct RefShapeWithMedium { RefInteriorMedium medium; const RefInteriorMedium *getInteriorMedium() const { return &medium; } };
+struct RefHSmoothDielectric {
+    RefShapeWithMedium *m_shape;
+    RefUnitTexture *m_specularReflectance, *m_specularTransmittance;
+#include "hdielectric_extract.inc" /* generated: reflect, getEtaInvEta, refract, sample(bRec, p, sample) */
+};
+}
 
 namespace {
 struct FixedSampler : public mitsuba::Sampler {
@@ -79,6 +107,33 @@ void ref_fresnel_dielectric_ext(size_t n, const float *cosThetaI, const float *e
         mitsuba::Float ct;
         F[i] = mitsuba::fresnelDielectricExt(cosThetaI[i], ct, eta[i]);
         cosThetaT[i] = ct;
+    }
+}
+
+/* HSmoothDielectric::sample for n rays arriving along d (world space, unit) at a surface with unit normal N and interior index eta;
+ * u = sample.x; mode 0 radiance / 1 importance.  World <-> local through Frame(N) as Intersection::toLocal / toWorld do
+ * (wi = toLocal(-d)).  Out: the sampled direction in world space, the returned weight (first channel), bRec.eta, transmitted? */
+void ref_hdielectric_sample(size_t n, const float *d, const float *N, const float *eta, const float *u, int mode, float *dOut, float *weight,
+                            float *etaScale, int *transmitted) {
+    mitsuba::RefShapeWithMedium shape;
+    mitsuba::RefUnitTexture one;
+    mitsuba::RefHSmoothDielectric bsdf;
+    bsdf.m_shape = &shape;
+    bsdf.m_specularReflectance = bsdf.m_specularTransmittance = &one;
+    for (size_t i = 0; i < n; i++) {
+        shape.medium.rif = eta[i];
+        mitsuba::Frame frame(mitsuba::Vector(N[3 * i], N[3 * i + 1], N[3 * i + 2]));
+        mitsuba::BSDFSamplingRecord bRec;
+        bRec.wi = frame.toLocal(mitsuba::Vector(-d[3 * i], -d[3 * i + 1], -d[3 * i + 2]));
+        bRec.mode = mode ? mitsuba::EImportance : mitsuba::ERadiance;
+        bRec.typeMask = 0xffffffffu; /* BSDF::EAll */
+        bRec.component = -1;
+        mitsuba::Spectrum w = bsdf.sample(bRec, mitsuba::Point(0.0f), mitsuba::Point2(u[i], 0.5f));
+        mitsuba::Vector wo = frame.toWorld(bRec.wo);
+        dOut[3 * i] = wo.x; dOut[3 * i + 1] = wo.y; dOut[3 * i + 2] = wo.z;
+        weight[i] = w[0];
+        etaScale[i] = bRec.eta;
+        transmitted[i] = bRec.sampledType == (unsigned) mitsuba::EDeltaTransmission ? 1 : 0;
     }
 }
 

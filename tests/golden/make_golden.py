@@ -82,6 +82,15 @@ def phase():
         out["maxexp_sample_t_%d" % k], out["maxexp_sample_pdf_%d" % k] = ref.maxexp(st, 0, out["maxexp_u"])
         out["maxexp_pdf_%d" % k] = ref.maxexp(st, 1, out["maxexp_t"])
         out["maxexp_cdf_%d" % k] = ref.maxexp(st, 2, out["maxexp_t"])
+    # f-3: HSmoothDielectric::sample (src/bsdfs/hdielectric.cpp:244-300), radiance and importance mode
+    dd = rng.normal(size=(n, 3))
+    dd = (dd / np.linalg.norm(dd, axis=1, keepdims=True)).astype(np.float32)
+    nn = rng.normal(size=(n, 3))
+    nn = (nn / np.linalg.norm(nn, axis=1, keepdims=True)).astype(np.float32)
+    out["hd_d"], out["hd_n"], out["hd_eta"], out["hd_u"] = dd, nn, (1.05 + 0.6 * rng.random(n)).astype(np.float32), rng.random(n).astype(np.float32)
+    for mode in (0, 1):
+        o, w, es, tr = ref.hdielectric_sample(dd, nn, out["hd_eta"], out["hd_u"], bool(mode))
+        out["hd_out_%d" % mode], out["hd_weight_%d" % mode], out["hd_etascale_%d" % mode], out["hd_transmitted_%d" % mode] = o, w, es, tr
     np.savez_compressed(os.path.join(HERE, "phase_ref.npz"), **out)
     print("wrote phase_ref.npz")
 

@@ -475,6 +475,38 @@ def test_oracle_medium_property_resolution_vs_verbatim_reference(oracle32):
         oracle32.medium_destroy(omed)
 
 
+@pytest.mark.skipif(not RefPhase.available(), reason="oracle/_ref/libmer_refphase.so not built (needs /root/reference)")
+@pytest.mark.parametrize("importance", [False, True])
+def test_oracle_hdielectric_sample_vs_verbatim_reference(oracle32, importance):
+    """SURVEY f-3 PINNED: HSmoothDielectric::sample with reflect / refract / getEtaInvEta (src/bsdfs/hdielectric.cpp:86-125,
+    244-300), compiled verbatim and driven through Frame::toLocal / toWorld like Intersection does, against the restated
+    world-space form: the same event (reflection or refraction, total internal reflection included), weight and relative
+    index exactly, the direction to rounding (the reference goes through a local frame, the restatement does not)"""
+    rng = np.random.default_rng(61)
+    n = 20000
+    d = random_directions(n, 62)
+    N = random_directions(n, 63)
+    eta = (1.05 + 0.6 * rng.random(n)).astype(np.float32)
+    u = rng.random(n).astype(np.float32)
+    ro, rw, res, rtr = RefPhase().hdielectric_sample(d, N, eta, u, importance)
+    go, gw, ges, gtr = oracle32.hdielectric_sample(d, N, eta, u, importance)
+    assert 0.05 < rtr.mean() < 0.95 and np.array_equal(gtr, rtr)
+    assert np.array_equal(gw, rw) and np.array_equal(ges, res)
+    assert np.abs(go - ro).max() <= 1e-6
+    # total internal reflection from inside: always reflected
+    inside = np.einsum("ij,ij->i", d, N) > 0
+    tir = inside & (1 - np.einsum("ij,ij->i", d, N) ** 2 > 1 / eta.astype(np.float64) ** 2 + 1e-6)
+    assert tir.sum() > 100 and not rtr[tir].any()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_oracle_hdielectric_sample_vs_reference_golden(oracle32, mode):
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "phase_ref.npz"))
+    go, gw, ges, gtr = oracle32.hdielectric_sample(G["hd_d"], G["hd_n"], G["hd_eta"], G["hd_u"], bool(mode))
+    assert np.array_equal(gtr, G["hd_transmitted_%d" % mode]) and np.array_equal(gw, G["hd_weight_%d" % mode])
+    assert np.array_equal(ges, G["hd_etascale_%d" % mode]) and np.abs(go - G["hd_out_%d" % mode]).max() <= 1e-6
+
+
 def test_spline_interpolates_data_at_nodes(oracle64):
     """the prefilter makes the cubic B-spline INTERPOLATE the samples (that is what build3d is for)"""
     res = (16, 14, 12)
