@@ -1441,8 +1441,6 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         if (!tuning || round < probeAt || round >= probeAt + 4) return -1;
         return (int) ((round - probeAt) & 1ull);
     };
-    bool maxL1 = true;
-    if (const char *e = getenv("MER_STEP_MAXL1")) maxL1 = atoi(e) != 0; /* tuning knob */
     int stepChoice = (tuning && S.stepChoiceTable == tableBytes) ? S.stepChoice : 0; /* index into stepCfgs */
     double tuneSteps[2] = {0.0, 0.0}, tuneMs[2] = {0.0, 0.0};
     unsigned long long roundsWith[2] = {0, 0};
@@ -1526,11 +1524,7 @@ int mer_render_device(const mer_medium *m, const mer_render_desc *r, float *film
         roundsWith[probe >= 0 ? probe : stepChoice]++;
         const unsigned stepBlocks = std::min((unsigned) sms * cfg.ctas, (pool + cfg.tpb - 1) / cfg.tpb), stepTpb = cfg.tpb;
         MER_CUDA(cudaEventRecord(S.ring[2 * ringUsed], stream));
-#define MER_STEP_K(K_)                                                                                                   \
-    do { /* no shared memory in the step kernel: the whole 256 KB of the SM's array as L1 (what the narrow configuration lives on) */ \
-        if (maxL1) cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);  \
-        MER_LAUNCH(K_, stepBlocks, stepTpb, 0, stream, P);                                                               \
-    } while (0)
+#define MER_STEP_K(K_) MER_LAUNCH(K_, stepBlocks, stepTpb, 0, stream, P) /* no shared memory: the SM's whole array is L1 (an explicit carve-out request changed nothing) */
 #define MER_STEP(MODE_, L_, T_, S_)                                                                                      \
     do {                                                                                                                 \
         if (xform) MER_STEP_K((k_step<MODE_, L_, T_, S_, true>)); else MER_STEP_K((k_step<MODE_, L_, T_, S_, false>));    \
