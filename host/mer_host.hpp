@@ -276,7 +276,7 @@ struct Shape : Object { /* the medium's container: <shape type="cube"|"sphere"> 
 
 struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousrefractive"> */
     std::shared_ptr<SplineDataSource> rif, sdf;
-    std::shared_ptr<GridDataSource> density;
+    std::shared_ptr<GridDataSource> density, albedo; /* heterogeneous.cpp:262-271 */
     std::shared_ptr<HGPhaseFunction> phase;
     mer_medium_desc desc;
     mer_connection_params connection;
@@ -286,6 +286,7 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         if (auto p = std::dynamic_pointer_cast<HGPhaseFunction>(child)) { if (phase) logError("Medium: phase function already set"); phase = p; }
         else if (name == "rif" && std::dynamic_pointer_cast<SplineDataSource>(child)) rif = std::dynamic_pointer_cast<SplineDataSource>(child);
         else if (name == "density" && std::dynamic_pointer_cast<GridDataSource>(child)) density = std::dynamic_pointer_cast<GridDataSource>(child);
+        else if (name == "albedo" && std::dynamic_pointer_cast<GridDataSource>(child)) albedo = std::dynamic_pointer_cast<GridDataSource>(child);
         else if (name == "sdf" && std::dynamic_pointer_cast<SplineDataSource>(child)) sdf = std::dynamic_pointer_cast<SplineDataSource>(child); /* :376-380 */
         else logError("Medium: Invalid child node! (\"" + std::string(child->className()) + "\")");
     }
@@ -344,6 +345,7 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         if (dryRun()) return;
         merCheck(mer_medium_create(&desc, rif->handle, density ? density->handle : nullptr, &handle));
         if (sdf) merCheck(mer_medium_set_sdf(handle, sdf->handle, 0));
+        if (albedo) merCheck(mer_medium_set_albedo_grid(handle, albedo->handle));
     }
     ~HeterogeneousRefractiveMedium() override { mer_medium_destroy(handle); }
 };

@@ -91,8 +91,15 @@ int mer_grid_create_device(int device, const mer_volume_desc *desc, const float 
 int mer_grid_create_from_file(int device, const char *vol_path, const mer_volume_desc *override_or_null,
                               mer_grid **out);
 void mer_grid_destroy(mer_grid *grid);
-/* GridDataSource::lookupFloat (gridvolume.cpp:337-363) */
+/* GridDataSource::lookupFloat (gridvolume.cpp:337-363); single-channel grids only (supportsFloatLookups, :578) */
 int mer_grid_lookup_batch(const mer_grid *grid, size_t n, const float *p, float *value_out);
+/* three-channel grids, the `albedo` child of a medium (heterogeneous.cpp:262-268): rgb[(z*yres + y)*xres + x][3],
+ * the float3 payload of gridvolume.cpp:293-329.  mer_grid_create_from_file makes one from a 3-channel float32 or
+ * uint8 .vol file (gridvolume.cpp:251-262); mer_grid_channels tells which kind a handle is (:578-579). */
+int mer_grid_create_spectrum(int device, const mer_volume_desc *desc, const float *rgb, mer_grid **out);
+int mer_grid_channels(const mer_grid *grid);
+/* GridDataSource::lookupSpectrum (gridvolume.cpp:386-463), rgb_out[3*n] */
+int mer_grid_lookup_spectrum_batch(const mer_grid *grid, size_t n, const float *p, float *rgb_out);
 
 /* HeterogeneousMedium on STRAIGHT rays, Woodcock tracking (src/medium/heterogeneous.cpp:239-242 majorant =
  * scale * 1, :613-658 sampleDistance, :546-587 evalTransmittance with 2 samples; AABB clipping
@@ -109,6 +116,8 @@ int mer_grid_eval_transmittance_batch(const mer_grid *grid, float scale, size_t 
 int mer_vol_read_header(const char *path, mer_volume_desc *out, int32_t *encoding, int32_t *channels);
 int mer_vol_read_data(const char *path, float *data_out, size_t n_floats);
 int mer_vol_write(const char *path, const mer_volume_desc *desc, const float *data);
+/* the same with three interleaved channels per voxel (an albedo grid; header field `channels` = 3, gridvolume.cpp:240-262) */
+int mer_vol_write_spectrum(const char *path, const mer_volume_desc *desc, const float *rgb);
 
 /* ------------------------------------------------------------ phase function */
 
@@ -188,6 +197,10 @@ void mer_medium_destroy(mer_medium *medium);
  * keeps using tested tracing only (containment there is the analytic box / sphere predicate, R5) and
  * returns MER_ERR_UNSUPPORTED for an aggressive medium. */
 int mer_medium_set_sdf(mer_medium *medium, const mer_rif *sdf, int aggressive);
+/* addChild("albedo") (heterogeneous.cpp:262-268): a spatially varying single-scattering albedo for a medium with a
+ * density grid; scattering events weigh the path by lookupSpectrum(p) (:646-649) instead of the constant
+ * mer_medium_desc.albedo.  NULL detaches.  The medium keeps a reference; destroy the grid after the medium. */
+int mer_medium_set_albedo_grid(mer_medium *medium, const mer_grid *albedo_or_null);
 /* resolved parameters (after the -1 defaults are applied) */
 int mer_medium_resolved(const mer_medium *medium, mer_medium_desc *out, float *sampling_density_out);
 

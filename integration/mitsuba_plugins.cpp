@@ -131,9 +131,12 @@ public:
     B200GridDataSource(Stream *stream, InstanceManager *manager) : VolumeDataSource(stream, manager), m_handle(NULL) { m_src.read(stream); load(); }
     virtual ~B200GridDataSource() { mer_grid_destroy(m_handle); }
     void serialize(Stream *stream, InstanceManager *manager) const { VolumeDataSource::serialize(stream, manager); m_src.write(stream); }
-    bool supportsFloatLookups() const { return true; }
+    bool supportsFloatLookups() const { return mer_grid_channels(m_handle) == 1; }    /* gridvolume.cpp:578 */
+    bool supportsSpectrumLookups() const { return mer_grid_channels(m_handle) == 3; } /* gridvolume.cpp:579 */
     Float lookupFloat(const Point &p) const { float q[3] = {p.x, p.y, p.z}, v; /* gridvolume.cpp:337-363 */
         MER_CHECK(mer_grid_lookup_batch(m_handle, 1, q, &v)); return v; }
+    Spectrum lookupSpectrum(const Point &p) const { float q[3] = {p.x, p.y, p.z}, v[3]; /* gridvolume.cpp:386-463 */
+        MER_CHECK(mer_grid_lookup_spectrum_batch(m_handle, 1, q, v)); Spectrum s; s.fromLinearRGB(v[0], v[1], v[2]); return s; }
     Float getStepSize() const { return m_stepSize; }            /* gridvolume.cpp:581 */
     Float getMaximumFloatValue() const { return 1.0f; }
     mer_grid *handle() const { return m_handle; }
@@ -208,6 +211,7 @@ public:
         m_rif = static_cast<B200SplineDataSource *>(manager->getInstance(stream));
         if (stream->readBool()) m_sdf = static_cast<B200SplineDataSource *>(manager->getInstance(stream));
         if (stream->readBool()) m_density = static_cast<B200GridDataSource *>(manager->getInstance(stream));
+        if (stream->readBool()) m_albedoVolume = static_cast<B200GridDataSource *>(manager->getInstance(stream));
         m_stepSize = stream->readFloat(); m_mediumSamplingWeight = stream->readFloat(); m_strategy = stream->readString();
         m_channel = stream->readInt(); m_samplingDensity = stream->readFloat(); m_scale = stream->readFloat();
         for (int i = 0; i < 3; ++i) m_albedo[i] = stream->readFloat();
@@ -223,6 +227,7 @@ public:
         manager->serialize(stream, m_rif.get());
         stream->writeBool(m_sdf.get() != NULL); if (m_sdf.get()) manager->serialize(stream, m_sdf.get());
         stream->writeBool(m_density.get() != NULL); if (m_density.get()) manager->serialize(stream, m_density.get());
+        stream->writeBool(m_albedoVolume.get() != NULL); if (m_albedoVolume.get()) manager->serialize(stream, m_albedoVolume.get());
         stream->writeFloat(m_stepSize); stream->writeFloat(m_mediumSamplingWeight); stream->writeString(m_strategy);
         stream->writeInt(m_channel); stream->writeFloat(m_samplingDensity); stream->writeFloat(m_scale);
         for (int i = 0; i < 3; ++i) stream->writeFloat(m_albedo[i]);
@@ -236,6 +241,10 @@ public:
             if (name == "rif") m_rif = static_cast<B200SplineDataSource *>(child);
             else if (name == "sdf") m_sdf = static_cast<B200SplineDataSource *>(child);
             else if (name == "density") m_density = static_cast<B200GridDataSource *>(child); /* heterogeneous.cpp:262-281 */
+            else if (name == "albedo") { /* heterogeneous.cpp:266-268 */
+                m_albedoVolume = static_cast<B200GridDataSource *>(child);
+                if (!m_albedoVolume->supportsSpectrumLookups()) Log(EError, "Medium: the albedo volume must have three channels");
+            }
             else Log(EError, "Medium: Invalid child node! (\"%s\")", name.c_str());
         } else {
             Medium::addChild(name, child); /* the phase function */
@@ -267,6 +276,7 @@ public:
         if (m_handle) mer_medium_destroy(m_handle);
         MER_CHECK(mer_medium_create(&d, m_rif->handle(), m_density.get() ? m_density->handle() : NULL, &m_handle));
         if (m_sdf.get() || m_aggressive) MER_CHECK(mer_medium_set_sdf(m_handle, m_sdf.get() ? m_sdf->handle() : NULL, m_aggressive ? 1 : 0));
+        if (m_albedoVolume.get()) MER_CHECK(mer_medium_set_albedo_grid(m_handle, m_albedoVolume->handle()));
     }
 
     /* Medium::sampleDistance (include/mitsuba/render/medium.h:130-131): a one-ray batch that replays the sampler draws the
@@ -294,7 +304,7 @@ public:
     mer_medium *handle() const { return m_handle; }
     const mer_connection_params &connection() const { return m_connection; }
     /* one more replica of this medium (same files, same properties) on another GPU, for mer_render_multi */
-    mer_medium *replicate(int device, mer_rif **rifOut, mer_grid **gridOut) const {
+    mer_medium *replicate(int device, mer_rif **rifOut, mer_grid **gridOut, mer_grid **albedoOut) const {
         mer_volume_desc rd; int mode; mer_medium_desc md; float sd;
         MER_CHECK(mer_rif_desc(m_rif->handle(), &rd, &mode));
         MER_CHECK(mer_medium_resolved(m_handle, &md, &sd));
@@ -304,13 +314,18 @@ public:
         if (m_density.get()) MER_CHECK(mer_grid_create_from_file(device, gridFile().c_str(), NULL, gridOut));
         mer_medium *m = NULL;
         MER_CHECK(mer_medium_create(&md, *rifOut, *gridOut, &m));
+        *albedoOut = NULL;
+        if (m_albedoVolume.get()) {
+            MER_CHECK(mer_grid_create_from_file(device, m_albedoVolume->getProperties().getString("filename").c_str(), NULL, albedoOut));
+            MER_CHECK(mer_medium_set_albedo_grid(m, *albedoOut));
+        }
         return m;
     }
     MTS_DECLARE_CLASS()
 private:
     std::string rifFile() const { return m_rif->getProperties().getString("filename"); }
     std::string gridFile() const { return m_density->getProperties().getString("filename"); }
-    ref<B200SplineDataSource> m_rif, m_sdf; ref<B200GridDataSource> m_density; mer_medium *m_handle;
+    ref<B200SplineDataSource> m_rif, m_sdf; ref<B200GridDataSource> m_density, m_albedoVolume; mer_medium *m_handle;
     Float m_stepSize, m_mediumSamplingWeight, m_samplingDensity, m_scale; std::string m_strategy; int m_channel; Spectrum m_albedo;
     bool m_aggressive; mer_connection_params m_connection;
 };
@@ -406,13 +421,14 @@ public:
             std::vector<const mer_medium *> media(1, medium->handle());
             std::vector<mer_medium *> owned; std::vector<mer_rif *> rifs; std::vector<mer_grid *> grids;
             for (int g = 1; g < gpus; ++g) {
-                mer_rif *rf; mer_grid *gr;
-                owned.push_back(medium->replicate(g, &rf, &gr));
-                rifs.push_back(rf); grids.push_back(gr);
+                mer_rif *rf; mer_grid *gr, *al;
+                owned.push_back(medium->replicate(g, &rf, &gr, &al));
+                rifs.push_back(rf); grids.push_back(gr); grids.push_back(al);
                 media.push_back(owned.back());
             }
             int rc = mer_render_multi(&media[0], gpus, &r, bitmap->getFloat32Data(), &stats);
-            for (size_t i = 0; i < owned.size(); ++i) { mer_medium_destroy(owned[i]); mer_rif_destroy(rifs[i]); mer_grid_destroy(grids[i]); }
+            for (size_t i = 0; i < owned.size(); ++i) { mer_medium_destroy(owned[i]); mer_rif_destroy(rifs[i]); }
+            for (size_t i = 0; i < grids.size(); ++i) mer_grid_destroy(grids[i]);
             MER_CHECK(rc);
         }
         Log(EInfo, "ervolpath: %llu samples, %llu eikonal steps, %.1f ms on %d GPU(s)",

@@ -47,7 +47,8 @@ typedef TVec3<FLOAT> VectorF; typedef TVec3<FLOAT> PointF;
 struct Point2 { Float x, y; Point2() : x(0), y(0) {} Point2(Float a, Float b) : x(a), y(b) {} };
 struct Vector2i { int x, y; };
 struct Spectrum { Float s[3]; Spectrum() { s[0] = s[1] = s[2] = 0; } explicit Spectrum(Float v) { s[0] = s[1] = s[2] = v; }
-    Float &operator[](int i) { return s[i]; } const Float &operator[](int i) const { return s[i]; } };
+    Float &operator[](int i) { return s[i]; } const Float &operator[](int i) const { return s[i]; }
+    void fromLinearRGB(Float r, Float g, Float b) { s[0] = r; s[1] = g; s[2] = b; } /* spectrum.h:793-797 (RGB build) */ };
 struct Matrix4x4 { Float m[4][4]; Float operator()(int r, int c) const { return m[r][c]; } bool isIdentity() const; };
 struct Transform { const Matrix4x4 &getMatrix() const; const Matrix4x4 &getInverseMatrix() const; Point operator()(const Point &p) const; };
 struct AABB { Point min, max; AABB() {} AABB(const Point &a, const Point &b) : min(a), max(b) {} };
@@ -87,6 +88,7 @@ class PhaseFunction : public ConfigurableObject { public: PhaseFunction(const Pr
 class VolumeDataSource : public ConfigurableObject { public: /* volume.h:31-107 + the fork's value / gradient / insideVolumeLimits */
     VolumeDataSource(const Properties &p) : ConfigurableObject(p) {} VolumeDataSource(Stream *s, InstanceManager *m) : ConfigurableObject(s, m) {}
     inline const AABB &getAABB() const { return m_aabb; } virtual bool supportsFloatLookups() const; virtual Float lookupFloat(const Point &) const;
+    virtual bool supportsSpectrumLookups() const; virtual Spectrum lookupSpectrum(const Point &) const; /* volume.h */
     virtual Float getStepSize() const = 0; virtual Float getMaximumFloatValue() const = 0; MTS_DECLARE_CLASS() protected: AABB m_aabb; };
 class BSDF : public ConfigurableObject { public: BSDF(const Properties &p) : ConfigurableObject(p) {} MTS_DECLARE_CLASS() };
 class Emitter; class TriMesh;

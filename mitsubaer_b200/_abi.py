@@ -109,16 +109,21 @@ SIGNATURES = {
     "mer_grid_create_from_file": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(VolumeDesc), C.POINTER(_vp)]),
     "mer_grid_destroy": (None, [_vp]),
     "mer_grid_lookup_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp]),
+    "mer_grid_create_spectrum": (C.c_int, [C.c_int, C.POINTER(VolumeDesc), _fp, C.POINTER(_vp)]),
+    "mer_grid_channels": (C.c_int, [_vp]),
+    "mer_grid_lookup_spectrum_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp]),
     "mer_grid_sample_distance_batch": (C.c_int, [_vp, C.c_float, C.c_size_t, _fp, _fp, _fp, _fp, C.c_uint64, _u8p, _fp, _fp]),
     "mer_grid_eval_transmittance_batch": (C.c_int, [_vp, C.c_float, C.c_size_t, _fp, _fp, _fp, _fp, C.c_uint64, _fp]),
     "mer_vol_read_header": (C.c_int, [C.c_char_p, C.POINTER(VolumeDesc), _i32p, _i32p]),
     "mer_vol_read_data": (C.c_int, [C.c_char_p, _fp, C.c_size_t]),
     "mer_vol_write": (C.c_int, [C.c_char_p, C.POINTER(VolumeDesc), _fp]),
+    "mer_vol_write_spectrum": (C.c_int, [C.c_char_p, C.POINTER(VolumeDesc), _fp]),
     "mer_hg_sample_batch": (C.c_int, [C.c_int, C.c_float, C.c_size_t, _fp, _fp, _fp, _fp]),
     "mer_hg_eval_batch": (C.c_int, [C.c_int, C.c_float, C.c_size_t, _fp, _fp, _fp]),
     "mer_medium_create": (C.c_int, [C.POINTER(MediumDesc), _vp, _vp, C.POINTER(_vp)]),
     "mer_medium_destroy": (None, [_vp]),
     "mer_medium_set_sdf": (C.c_int, [_vp, _vp, C.c_int]),
+    "mer_medium_set_albedo_grid": (C.c_int, [_vp, _vp]),
     "mer_medium_resolved": (C.c_int, [_vp, C.POINTER(MediumDesc), _fp]),
     "mer_medium_trace_batch": (C.c_int, [_vp, C.c_size_t, _fp, _fp, _fp, _u8p, _fp, _fp, _i32p]),
     "mer_medium_trace_device": (C.c_int, [_vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -51,6 +51,7 @@ struct GridDev {
     float G[12]; /* world -> grid, row-major 3x4 (gridvolume.cpp:190-195) */
     float aabbLo[3], aabbHi[3]; /* world AABB of the data box (gridvolume.cpp:199-201) */
     const float *data;
+    int channels; /* 1: density (lookupFloat); 3: interleaved RGB albedo (lookupSpectrum, gridvolume.cpp:386-463) */
 };
 
 struct MediumDev {
@@ -60,6 +61,8 @@ struct MediumDev {
     float maxSdfError;
     GridDev grid;
     int hasGrid;
+    GridDev albedoGrid; /* <volume name="albedo"> (heterogeneous.cpp:262-268, looked up at :600 / :646) */
+    int hasAlbedoGrid;
     float sigmaA[3], sigmaS[3], sigmaT[3];
     float h;
     float weight;          /* m_mediumSamplingWeight */
@@ -613,6 +616,33 @@ __device__ __forceinline__ float grid_lookup(const GridDev &D, float3 pw) {
                 a2 = __fadd_rn(__fmul_rn(d100, gx), __fmul_rn(d101, fx)), a3 = __fadd_rn(__fmul_rn(d110, gx), __fmul_rn(d111, fx));
     const float b0 = __fadd_rn(__fmul_rn(a0, gy), __fmul_rn(a1, fy)), b1 = __fadd_rn(__fmul_rn(a2, gy), __fmul_rn(a3, fy));
     return __fadd_rn(__fmul_rn(b0, gz), __fmul_rn(b1, fz));
+}
+
+/* GridDataSource::lookupSpectrum, 3-channel grids (gridvolume.cpp:386-463): the float3 operators of the reference
+ * act per channel, so each channel repeats lookupFloat's expression on the interleaved data */
+__device__ __forceinline__ void grid_lookup3(const GridDev &D, float3 pw, float out[3]) {
+    const float px = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(D.G[0], pw.x), __fmul_rn(D.G[1], pw.y)), __fmul_rn(D.G[2], pw.z)), D.G[3]);
+    const float py = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(D.G[4], pw.x), __fmul_rn(D.G[5], pw.y)), __fmul_rn(D.G[6], pw.z)), D.G[7]);
+    const float pz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(D.G[8], pw.x), __fmul_rn(D.G[9], pw.y)), __fmul_rn(D.G[10], pw.z)), D.G[11]);
+    const int x1 = (int) floorf(px), y1 = (int) floorf(py), z1 = (int) floorf(pz);
+    const int x2 = x1 + 1, y2 = y1 + 1, z2 = z1 + 1;
+    out[0] = out[1] = out[2] = 0.0f;
+    if (x1 < 0 || y1 < 0 || z1 < 0 || x2 >= D.N[0] || y2 >= D.N[1] || z2 >= D.N[2]) return;
+    const float fx = px - (float) x1, fy = py - (float) y1, fz = pz - (float) z1;
+    const float gx = 1.0f - fx, gy = 1.0f - fy, gz = 1.0f - fz;
+    const size_t rx = D.N[0], ry = D.N[1];
+    const float *r00 = D.data + 3 * (((size_t) z1 * ry + y1) * rx + x1), *r01 = D.data + 3 * (((size_t) z1 * ry + y2) * rx + x1),
+                *r10 = D.data + 3 * (((size_t) z2 * ry + y1) * rx + x1), *r11 = D.data + 3 * (((size_t) z2 * ry + y2) * rx + x1);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        /* x2 = x1 + 1 is the next texel of the row: 3 floats further */
+        const float a0 = __fadd_rn(__fmul_rn(__ldg(r00 + c), gx), __fmul_rn(__ldg(r00 + 3 + c), fx)),
+                    a1 = __fadd_rn(__fmul_rn(__ldg(r01 + c), gx), __fmul_rn(__ldg(r01 + 3 + c), fx)),
+                    a2 = __fadd_rn(__fmul_rn(__ldg(r10 + c), gx), __fmul_rn(__ldg(r10 + 3 + c), fx)),
+                    a3 = __fadd_rn(__fmul_rn(__ldg(r11 + c), gx), __fmul_rn(__ldg(r11 + 3 + c), fx));
+        const float b0 = __fadd_rn(__fmul_rn(a0, gy), __fmul_rn(a1, fy)), b1 = __fadd_rn(__fmul_rn(a2, gy), __fmul_rn(a3, fy));
+        out[c] = __fadd_rn(__fmul_rn(b0, gz), __fmul_rn(b1, fz));
+    }
 }
 
 /* ------------------------------------------------------------------ a11: containment */

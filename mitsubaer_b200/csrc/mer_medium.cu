@@ -358,6 +358,7 @@ int mer_medium_create(const mer_medium_desc *desc, const mer_rif *rif, const mer
                 "Specified an unknown sampling strategy"); /* :296 */
     if (density) MER_REQUIRE(desc->density_scale > 0.0f, "density_scale must be positive when a density grid is attached");
 
+    if (density) MER_REQUIRE(density->dev.channels == 1, "the density volume must have one channel (heterogeneous.cpp:269-271)");
     mer_medium *m = new mer_medium();
     memset(m, 0, sizeof(*m));
     m->device = rif->device;
@@ -454,6 +455,17 @@ int mer_medium_set_sdf(mer_medium *m, const mer_rif *sdf, int aggressive) {
     /* maxSDFError, splinevolume.cpp:282: sqrt(sum stride^2), stride = FLOAT(1/xres) */
     float s0 = (float) (1.0 / (double) sdf->dev.xres[0]), s1 = (float) (1.0 / (double) sdf->dev.xres[1]), s2 = (float) (1.0 / (double) sdf->dev.xres[2]);
     m->dev.maxSdfError = std::sqrt(s0 * s0 + s1 * s1 + s2 * s2);
+    return MER_OK;
+}
+
+int mer_medium_set_albedo_grid(mer_medium *m, const mer_grid *albedo) {
+    MER_REQUIRE(m, "null handle");
+    if (!albedo) { m->dev.hasAlbedoGrid = 0; return MER_OK; }
+    MER_REQUIRE(m->dev.hasGrid, "an albedo volume goes with a density volume (heterogeneous.cpp:229-236)");
+    MER_REQUIRE(albedo->device == m->device, "medium and albedo volume live on different devices");
+    MER_REQUIRE(albedo->dev.channels == 3, "the albedo volume must support spectrum lookups (heterogeneous.cpp:266-268)");
+    m->dev.albedoGrid = albedo->dev;
+    m->dev.hasAlbedoGrid = 1;
     return MER_OK;
 }
 

@@ -482,7 +482,10 @@ __device__ __forceinline__ void handle_events(const RenderParams &P, Lane &L, Ev
                 float densityAtT = __fmul_rn(grid_lookup(M.grid, L.p), M.densityScale);
                 if (__fmul_rn(densityAtT, M.invMaxDensity) > L.rng.next()) {
                     scatter = true;
-                    edge[0] = M.albedo[0]; edge[1] = M.albedo[1]; edge[2] = M.albedo[2];
+                    /* sigmaS = albedo * densityAtT * scale over a transmittance of 1 / densityAtT: the edge weighs by the
+                     * albedo, a constant or the `albedo` volume at the event (heterogeneous.cpp:646-649) */
+                    if (M.hasAlbedoGrid) grid_lookup3(M.albedoGrid, L.p, edge);
+                    else { edge[0] = M.albedo[0]; edge[1] = M.albedo[1]; edge[2] = M.albedo[2]; }
                 } else {
                     ST_INC(st, ST_NULL);
                     begin_trace(P, L, __fmul_rn(-fastlog_dev(1.0f - L.rng.next()), M.invMaxDensity));

@@ -134,6 +134,14 @@ __global__ void k_grid_lookup(GridDev D, size_t n, const float *__restrict__ p, 
         out[i] = grid_lookup(D, f3(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
 }
 
+__global__ void k_grid_lookup3(GridDev D, size_t n, const float *__restrict__ p, float *__restrict__ out) {
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        float rgb[3];
+        grid_lookup3(D, f3(p[3 * i], p[3 * i + 1], p[3 * i + 2]), rgb);
+        out[3 * i] = rgb[0]; out[3 * i + 1] = rgb[1]; out[3 * i + 2] = rgb[2];
+    }
+}
+
 /* ------------------------------------------------------------------ a19: straight-ray Woodcock tracking
  * heterogeneous.cpp:613-658 / :546-587; every operation individually rounded like the reference's float code. */
 __device__ __forceinline__ bool aabb_ray_intersect(const GridDev &D, float3 o, float3 d, float &nearT, float &farT) {
@@ -384,8 +392,10 @@ int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
     return MER_OK;
 }
 
-/* .vol payloads this path reads: EFloat32 and EUInt8 (value / 255), one channel (gridvolume.cpp:251-262, 369-376) */
-static bool vol_encoding_supported(int32_t enc, int32_t ch) { return ch == 1 && (enc == 1 || enc == 3); }
+/* .vol payloads this path reads: EFloat32 and EUInt8 (value / 255), one channel (densities, RIFs, SDFs) or three
+ * interleaved channels (albedo grids) (gridvolume.cpp:251-262, 369-376, 401-460) */
+static bool vol_encoding_supported(int32_t enc, int32_t ch) { return (ch == 1 || ch == 3) && (enc == 1 || enc == 3); }
+static const char *kVolUnsupported = "float32 and uint8 .vol files with one channel or three (albedo) are supported on this path (no float16, no quantized-direction grids)";
 
 int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *data, int32_t *encoding,
                   int32_t *channels) {
@@ -431,9 +441,9 @@ int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *d
     if (data) {
         if (!vol_encoding_supported(enc, ch)) {
             fclose(f);
-            return mer::fail(MER_ERR_UNSUPPORTED, "single-channel float32 and uint8 .vol files are supported on this path (no float16, no 3-channel albedo / direction grids)");
+            return mer::fail(MER_ERR_UNSUPPORTED, kVolUnsupported);
         }
-        size_t total = (size_t) res[0] * res[1] * res[2];
+        size_t total = (size_t) res[0] * res[1] * res[2] * (size_t) ch;
         data->resize(total);
         if (enc == 1) {
             if (fread(data->data(), sizeof(float), total, f) != total) { fclose(f); return mer::fail(MER_ERR_INVALID, "volume file truncated"); }
@@ -451,17 +461,19 @@ int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *d
  * staging buffers, the disk read of one overlapping the H2D copy of the other.  Peak host memory is 128 MiB whatever the
  * grid (a 1024^3 RIF is 4 GiB on disk); the reference reads the file through a memory map and prefilters on the CPU
  * (splinevolume.cpp:204-317), here the prefilter runs on the device array. */
-int stream_vol_to_device(int device, const char *path, mer_volume_desc *desc, float **data_dev_out) {
+int stream_vol_to_device(int device, const char *path, mer_volume_desc *desc, float **data_dev_out, int *channels_out = nullptr) {
     *data_dev_out = nullptr;
     int32_t enc = 0, ch = 0;
     int rc = read_vol_file(path, desc, nullptr, &enc, &ch);
     if (rc) return rc;
-    if (!vol_encoding_supported(enc, ch))
-        return mer::fail(MER_ERR_UNSUPPORTED, "single-channel float32 and uint8 .vol files are supported on this path (no float16, no 3-channel albedo / direction grids)");
+    if (!vol_encoding_supported(enc, ch)) return mer::fail(MER_ERR_UNSUPPORTED, kVolUnsupported);
+    /* a caller that does not ask for the channel count takes scalar fields only (RIF, SDF) */
+    if (!channels_out && ch != 1) return mer::fail(MER_ERR_INVALID, "this volume must have one channel (supportsFloatLookups)");
+    if (channels_out) *channels_out = ch;
     rc = mer::check_device(device);
     if (rc) return rc;
     mer::DeviceGuard guard(device);
-    const size_t total = (size_t) desc->res[0] * desc->res[1] * desc->res[2];
+    const size_t total = (size_t) desc->res[0] * desc->res[1] * desc->res[2] * (size_t) ch;
     FILE *f = fopen(path, "rb");
     if (!f) return mer::fail(MER_ERR_INVALID, std::string("cannot open volume file: ") + path);
     fseek(f, 48, SEEK_SET);
@@ -648,11 +660,12 @@ int mer_rif_inside_limits_batch(const mer_rif *r, size_t n, const float *p, uint
 }
 
 /* ------------------------------------------------------------------ density grid */
-int mer_grid_create_device(int device, const mer_volume_desc *desc, const float *data_dev, mer_grid **out) {
+static int grid_create_device(int device, const mer_volume_desc *desc, const float *data_dev, int channels, mer_grid **out) {
     if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
     *out = nullptr;
     int rc = validate_desc(desc, 2);
     if (rc) return rc;
+    MER_REQUIRE(channels == 1 || channels == 3, "a grid volume has one channel (density) or three (albedo)");
     MER_REQUIRE(data_dev != nullptr, "No density specified!");
     rc = mer::check_device(device);
     if (rc) return rc;
@@ -661,7 +674,8 @@ int mer_grid_create_device(int device, const mer_volume_desc *desc, const float 
     memset(g, 0, sizeof(*g));
     g->device = device;
     g->desc = *desc;
-    const size_t bytes = voxels(desc) * sizeof(float);
+    g->dev.channels = channels;
+    const size_t bytes = voxels(desc) * (size_t) channels * sizeof(float);
     cudaError_t e = mer::pool_malloc((void **) &g->d_data, bytes);
     if (e == cudaSuccess) e = cudaMemcpy(g->d_data, data_dev, bytes, cudaMemcpyDeviceToDevice);
     if (e != cudaSuccess) { mer_grid_destroy(g); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
@@ -703,7 +717,11 @@ int mer_grid_create_device(int device, const mer_volume_desc *desc, const float 
     return MER_OK;
 }
 
-int mer_grid_create(int device, const mer_volume_desc *desc, const float *data, mer_grid **out) {
+int mer_grid_create_device(int device, const mer_volume_desc *desc, const float *data_dev, mer_grid **out) {
+    return grid_create_device(device, desc, data_dev, 1, out);
+}
+
+static int grid_create_host(int device, const mer_volume_desc *desc, const float *data, int channels, mer_grid **out) {
     if (!out) return mer::fail(MER_ERR_INVALID, "null output handle");
     *out = nullptr;
     int rc = validate_desc(desc, 2);
@@ -713,14 +731,24 @@ int mer_grid_create(int device, const mer_volume_desc *desc, const float *data, 
     if (rc) return rc;
     mer::DeviceGuard guard(device);
     float *d_data = nullptr;
-    const size_t bytes = voxels(desc) * sizeof(float);
+    const size_t bytes = voxels(desc) * (size_t) channels * sizeof(float);
     MER_CUDA(mer::pool_malloc((void **) &d_data, bytes));
     cudaError_t e = cudaMemcpy(d_data, data, bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { mer::pool_free(d_data); return mer::fail(MER_ERR_CUDA, cudaGetErrorString(e)); }
-    rc = mer_grid_create_device(device, desc, d_data, out);
+    rc = grid_create_device(device, desc, d_data, channels, out);
     mer::pool_free(d_data);
     return rc;
 }
+
+int mer_grid_create(int device, const mer_volume_desc *desc, const float *data, mer_grid **out) {
+    return grid_create_host(device, desc, data, 1, out);
+}
+
+int mer_grid_create_spectrum(int device, const mer_volume_desc *desc, const float *rgb, mer_grid **out) {
+    return grid_create_host(device, desc, rgb, 3, out);
+}
+
+int mer_grid_channels(const mer_grid *g) { return g ? g->dev.channels : 0; }
 
 int mer_grid_create_from_file(int device, const char *vol_path, const mer_volume_desc *override_or_null,
                               mer_grid **out) {
@@ -729,10 +757,11 @@ int mer_grid_create_from_file(int device, const char *vol_path, const mer_volume
     MER_REQUIRE(vol_path, "null path");
     mer_volume_desc d;
     float *raw = nullptr;
-    int rc = stream_vol_to_device(device, vol_path, &d, &raw);
+    int channels = 1;
+    int rc = stream_vol_to_device(device, vol_path, &d, &raw, &channels);
     if (rc) return rc;
     apply_override(&d, override_or_null);
-    rc = mer_grid_create_device(device, &d, raw, out);
+    rc = grid_create_device(device, &d, raw, channels, out);
     mer::DeviceGuard guard(device);
     mer::pool_free(raw);
     return rc;
@@ -746,8 +775,23 @@ void mer_grid_destroy(mer_grid *g) {
     delete g;
 }
 
+int mer_grid_lookup_spectrum_batch(const mer_grid *g, size_t n, const float *p, float *rgb_out) {
+    MER_REQUIRE(g && (n == 0 || (p && rgb_out)), "null argument");
+    MER_REQUIRE(g->dev.channels == 3, "lookupSpectrum needs a 3-channel grid (supportsSpectrumLookups, gridvolume.cpp:579)");
+    if (n == 0) return MER_OK;
+    mer::DeviceGuard guard(g->device);
+    mer::DevBuf dp, dout;
+    MER_CUDA(dp.alloc(n * 3 * sizeof(float)));
+    MER_CUDA(dout.alloc(n * 3 * sizeof(float)));
+    MER_CUDA(cudaMemcpy(dp.ptr, p, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    MER_LAUNCH(k_grid_lookup3, (unsigned) std::min<size_t>(mer_blocks(n, 256), 148u * 8u), 256, 0, 0, g->dev, n, dp.as<float>(), dout.as<float>());
+    MER_CUDA(cudaMemcpy(rgb_out, dout.ptr, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return MER_OK;
+}
+
 int mer_grid_lookup_batch(const mer_grid *g, size_t n, const float *p, float *value_out) {
     MER_REQUIRE(g && (n == 0 || (p && value_out)), "null argument");
+    MER_REQUIRE(g->dev.channels == 1, "lookupFloat needs a single-channel grid (supportsFloatLookups, gridvolume.cpp:578)");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(g->device);
     mer::DevBuf dp, dout;
@@ -762,6 +806,7 @@ int mer_grid_lookup_batch(const mer_grid *g, size_t n, const float *p, float *va
 static int grid_woodcock(const mer_grid *g, float scale, size_t n, const float *ro, const float *rd, const float *mint,
                          const float *maxt, uint64_t seed, int evalT, uint8_t *ok, float *t, float *dens, float *tr) {
     MER_REQUIRE(g && (n == 0 || (ro && rd && mint && maxt)), "null argument");
+    MER_REQUIRE(g->dev.channels == 1, "the density volume must have one channel (heterogeneous.cpp:269-271)");
     MER_REQUIRE(scale > 0.0f, "scale must be positive");
     if (n == 0) return MER_OK;
     mer::DeviceGuard guard(g->device);
@@ -807,23 +852,26 @@ int mer_vol_read_data(const char *path, float *data_out, size_t n_floats) {
     return MER_OK;
 }
 
-int mer_vol_write(const char *path, const mer_volume_desc *desc, const float *data) {
+static int vol_write(const char *path, const mer_volume_desc *desc, const float *data, int32_t ch) {
     MER_REQUIRE(path && desc && data, "null argument");
     FILE *f = fopen(path, "wb");
     if (!f) return mer::fail(MER_ERR_INVALID, std::string("cannot create volume file: ") + path);
     unsigned char hdr[48];
     hdr[0] = 'V'; hdr[1] = 'O'; hdr[2] = 'L'; hdr[3] = 3;
-    int32_t enc = 1, ch = 1;
+    int32_t enc = 1;
     memcpy(hdr + 4, &enc, 4);
     memcpy(hdr + 8, desc->res, 12);
     memcpy(hdr + 20, &ch, 4);
     memcpy(hdr + 24, desc->bbox_min, 12);
     memcpy(hdr + 36, desc->bbox_max, 12);
-    size_t total = voxels(desc);
+    size_t total = voxels(desc) * (size_t) ch;
     bool ok = fwrite(hdr, 1, 48, f) == 48 && fwrite(data, sizeof(float), total, f) == total;
     fclose(f);
     if (!ok) return mer::fail(MER_ERR_INVALID, "short write to volume file");
     return MER_OK;
 }
+
+int mer_vol_write(const char *path, const mer_volume_desc *desc, const float *data) { return vol_write(path, desc, data, 1); }
+int mer_vol_write_spectrum(const char *path, const mer_volume_desc *desc, const float *rgb) { return vol_write(path, desc, rgb, 3); }
 
 } /* extern "C" */

@@ -72,20 +72,21 @@ def padded_bbox(box_min, box_max, res, pad_voxels=3):
 
 # ---------------------------------------------------------------- .vol v3 I/O through the C ABI
 def write_vol(path, data, bbox_min, bbox_max):
-    """data[z][y][x] float32 -> Mitsuba .vol v3 (mfiles/writeGridToVol.m)"""
+    """data[z][y][x] (or data[z][y][x][3], an albedo grid) float32 -> Mitsuba .vol v3 (mfiles/writeGridToVol.m)"""
     data = np.ascontiguousarray(data, dtype=np.float32)
     d = _abi.VolumeDesc()
     d.res[:] = [data.shape[2], data.shape[1], data.shape[0]]
     d.bbox_min[:] = [float(x) for x in bbox_min]
     d.bbox_max[:] = [float(x) for x in bbox_max]
-    check(lib.mer_vol_write(str(path).encode(), C.byref(d), data.ctypes.data_as(C.POINTER(C.c_float))))
+    write = lib.mer_vol_write_spectrum if data.ndim == 4 and data.shape[3] == 3 else lib.mer_vol_write
+    check(write(str(path).encode(), C.byref(d), data.ctypes.data_as(C.POINTER(C.c_float))))
 
 
 def read_vol(path):
-    """-> (data[z][y][x], bbox_min, bbox_max)  (mfiles/readVolToGrid.m, splinevolume.cpp:204-273)"""
+    """-> (data[z][y][x] or data[z][y][x][3], bbox_min, bbox_max)  (mfiles/readVolToGrid.m, splinevolume.cpp:204-273)"""
     d = _abi.VolumeDesc()
     enc, ch = C.c_int32(), C.c_int32()
     check(lib.mer_vol_read_header(str(path).encode(), C.byref(d), C.byref(enc), C.byref(ch)))
-    data = np.zeros((d.res[2], d.res[1], d.res[0]), np.float32)
+    data = np.zeros((d.res[2], d.res[1], d.res[0]) + ((ch.value,) if ch.value > 1 else ()), np.float32)
     check(lib.mer_vol_read_data(str(path).encode(), data.ctypes.data_as(C.POINTER(C.c_float)), data.size))
     return data, np.array(d.bbox_min[:], np.float32), np.array(d.bbox_max[:], np.float32)

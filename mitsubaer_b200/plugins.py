@@ -156,7 +156,9 @@ class SplineDataSource(_Volume):
 
 
 class GridDataSource(_Volume):
-    """props: `filename` | (`data`, `res`, `min`, `max`), `toWorld`, `device`."""
+    """props: `filename` | (`data`, `res`, `min`, `max`), `toWorld`, `device`.  `data` of shape [z, y, x] makes a
+    density grid, [z, y, x, 3] (or `channels` = 3) an albedo grid (gridvolume.cpp:251-262, 578-579); a file says
+    which it is in its header."""
 
     def __init__(self, props=None, **kw):
         props = dict(props or {}, **kw)
@@ -180,13 +182,17 @@ class GridDataSource(_Volume):
             check(lib.mer_grid_create_device(self.device, C.byref(self.desc), C.c_void_p(int(props["data_ptr"])),
                                              C.byref(h)))
         else:
+            shape = np.shape(props["data"])
+            channels = int(props.get("channels", 3 if len(shape) == 4 and shape[3] == 3 else 1))
             data = _f32(props["data"]).reshape(-1)
-            res = props.get("res") or tuple(reversed(np.shape(props["data"])))
+            res = props.get("res") or tuple(reversed(shape[:3]))
             self.desc = make_volume_desc(res, props["min"], props["max"], props.get("toWorld"))
-            if data.size != self.desc.res[0] * self.desc.res[1] * self.desc.res[2]:
+            if channels not in (1, 3) or data.size != self.desc.res[0] * self.desc.res[1] * self.desc.res[2] * channels:
                 raise _abi.MerError(_abi.MER_ERR_INVALID, "data size does not match res")
-            check(lib.mer_grid_create(self.device, C.byref(self.desc), _fp(data), C.byref(h)))
+            create = lib.mer_grid_create if channels == 1 else lib.mer_grid_create_spectrum
+            check(create(self.device, C.byref(self.desc), _fp(data), C.byref(h)))
         self.handle = h
+        self.channels = int(lib.mer_grid_channels(h))
 
     def __del__(self):
         if getattr(self, "handle", None):
@@ -199,8 +205,17 @@ class GridDataSource(_Volume):
         check(lib.mer_grid_lookup_batch(self.handle, p.shape[0], _fp(p), _fp(out)))
         return out
 
+    def lookupSpectrum(self, p):
+        p = _f32(p, (-1, 3))
+        out = np.zeros((p.shape[0], 3), np.float32)
+        check(lib.mer_grid_lookup_spectrum_batch(self.handle, p.shape[0], _fp(p), _fp(out)))
+        return out
+
     def supportsFloatLookups(self):
-        return True
+        return self.channels == 1
+
+    def supportsSpectrumLookups(self):
+        return self.channels == 3
 
     # ---- HeterogeneousMedium (straight rays, Woodcock tracking) on this density grid: heterogeneous.cpp:546-658
     def _rays(self, ray_o, ray_d, mint, maxt):
@@ -289,6 +304,8 @@ class HeterogeneousRefractiveMedium:
             self.rif = child
         elif isinstance(child, GridDataSource) and name == "density":
             self.density = child
+        elif isinstance(child, GridDataSource) and name == "albedo":  # heterogeneous.cpp:266-268
+            self.albedo_grid = child
         elif isinstance(child, SplineDataSource) and name == "sdf":
             self.sdf = child
         else:
@@ -353,6 +370,8 @@ class HeterogeneousRefractiveMedium:
         check(lib.mer_medium_create(C.byref(d), self.rif.handle, self.density.handle if self.density else None,
                                     C.byref(h)))
         self.handle = h
+        if getattr(self, "albedo_grid", None) is not None:
+            check(lib.mer_medium_set_albedo_grid(self.handle, self.albedo_grid.handle))
         aggressive = bool(p.get("aggressivetracing", False))
         if self.sdf is not None or aggressive:
             check(lib.mer_medium_set_sdf(self.handle, self.sdf.handle if self.sdf is not None else None, 1 if aggressive else 0))
@@ -367,6 +386,12 @@ class HeterogeneousRefractiveMedium:
         if getattr(self, "handle", None):
             lib.mer_medium_destroy(self.handle)
             self.handle = None
+
+    def setAlbedoVolume(self, grid):
+        """attach / replace / detach (None) the `albedo` child of a configured medium (heterogeneous.cpp:262-268)"""
+        check(lib.mer_medium_set_albedo_grid(self.handle, grid.handle if grid is not None else None))
+        self.albedo_grid = grid
+        return self
 
     def isheterogeneousrefractive(self):
         return True

@@ -317,8 +317,10 @@ struct GridVolume {
     int res[3];
     float G[12]; /* m_worldToGrid = scale((res-1)/extent) * translate(-min) * worldToVolume, :190-195 */
     std::vector<float> data;
-    void create(const mer_volume_desc *d, const float *src) {
-        size_t total = 1;
+    int channels = 1; /* m_channels: 1 = density, 3 = interleaved RGB albedo (gridvolume.cpp:578-579) */
+    void create(const mer_volume_desc *d, const float *src, int nchannels = 1) {
+        channels = nchannels;
+        size_t total = (size_t) nchannels;
         for (int r = 0; r < 3; r++) {
             res[r] = d->res[r];
             total *= (size_t) res[r];
@@ -349,6 +351,30 @@ struct GridVolume {
                     d110 = fd[(z2 * ry + y2) * rx + x1], d111 = fd[(z2 * ry + y2) * rx + x2];
         return ((d000 * _fx + d001 * fx) * _fy + (d010 * _fx + d011 * fx) * fy) * _fz +
                ((d100 * _fx + d101 * fx) * _fy + (d110 * _fx + d111 * fx) * fy) * fz;
+    }
+    /* GridDataSource::lookupSpectrum, EFloat32 (gridvolume.cpp:386-421): the float3 operators (:293-329) act per
+     * channel, toSpectrum is fromLinearRGB = the identity for RGB spectra */
+    void lookupSpectrum(const float *pw, float out[3]) const {
+        float p[3];
+        for (int r = 0; r < 3; r++)
+            p[r] = G[4 * r] * pw[0] + G[4 * r + 1] * pw[1] + G[4 * r + 2] * pw[2] + G[4 * r + 3];
+        const int x1 = (int) std::floor(p[0]), y1 = (int) std::floor(p[1]), z1 = (int) std::floor(p[2]),
+                  x2 = x1 + 1, y2 = y1 + 1, z2 = z1 + 1;
+        out[0] = out[1] = out[2] = 0;
+        if (x1 < 0 || y1 < 0 || z1 < 0 || x2 >= res[0] || y2 >= res[1] || z2 >= res[2])
+            return;
+        const float fx = p[0] - x1, fy = p[1] - y1, fz = p[2] - z1, _fx = 1.0f - fx, _fy = 1.0f - fy,
+                    _fz = 1.0f - fz;
+        const float *fd = data.data();
+        const size_t rx = res[0], ry = res[1];
+        for (int c = 0; c < 3; c++) {
+            const float d000 = fd[3 * ((z1 * ry + y1) * rx + x1) + c], d001 = fd[3 * ((z1 * ry + y1) * rx + x2) + c],
+                        d010 = fd[3 * ((z1 * ry + y2) * rx + x1) + c], d011 = fd[3 * ((z1 * ry + y2) * rx + x2) + c],
+                        d100 = fd[3 * ((z2 * ry + y1) * rx + x1) + c], d101 = fd[3 * ((z2 * ry + y1) * rx + x2) + c],
+                        d110 = fd[3 * ((z2 * ry + y2) * rx + x1) + c], d111 = fd[3 * ((z2 * ry + y2) * rx + x2) + c];
+            out[c] = ((d000 * _fx + d001 * fx) * _fy + (d010 * _fx + d011 * fx) * fy) * _fz +
+                     ((d100 * _fx + d101 * fx) * _fy + (d110 * _fx + d111 * fx) * fy) * fz;
+        }
     }
 };
 
@@ -503,6 +529,7 @@ template <typename F> struct Medium {
     const SplineVolume<F> *sdf = nullptr; /* <volume name="sdf">, used by aggressive tracing (a10) */
     bool aggressive = false;              /* `aggressivetracing` */
     const GridVolume *density; /* optional (new composition, R2) */
+    const GridVolume *albedoGrid = nullptr; /* optional `albedo` child (heterogeneous.cpp:262-268) */
     mer_medium_desc d;
     float sigmaT[3];
     float samplingDensity;
@@ -1861,6 +1888,10 @@ void Li(const Medium<F> &M, const mer_render_desc &R, const float o[3], const fl
             }
             for (int i = 0; i < 3; i++)
                 edge[i] = success ? M.d.albedo[i] : 1.0f; /* sigmaS * (1/density) / 1, :640-644 */
+            if (success && M.albedoGrid) { /* m_albedo->lookupSpectrum(p), heterogeneous.cpp:646-647 */
+                float pf32[3] = {(float) p[0], (float) p[1], (float) p[2]};
+                M.albedoGrid->lookupSpectrum(pf32, edge);
+            }
         }
         F refEnd = M.rif->value(p);
         F rrs = (F) (1.0 / (refStart * refStart)); /* heterogeneousrefractive.cpp:469, :501 */
@@ -2045,6 +2076,9 @@ void render(const Medium<F> &M, const mer_render_desc &R, float *film, mer_rende
         ((Medium<F> *) h)->sdf = (const SplineVolume<F> *) sdf;                                                    \
         ((Medium<F> *) h)->aggressive = aggressive != 0;                                                          \
     }                                  \
+    extern "C" void orc_medium_set_albedo_grid##SUF(void *h, void *grid) {                                        \
+        ((Medium<F> *) h)->albedoGrid = (const GridVolume *) grid;                                                \
+    }                                                                                                             \
     extern "C" void orc_medium_resolved##SUF(void *h, float *weight, float *samplingDensity) {                    \
         *weight = ((Medium<F> *) h)->weight;                                                                      \
         *samplingDensity = ((Medium<F> *) h)->samplingDensity;                                                    \
@@ -2156,6 +2190,15 @@ extern "C" void *orc_grid_create(const mer_volume_desc *d, const float *data) {
     GridVolume *g = new GridVolume();
     g->create(d, data);
     return g;
+}
+extern "C" void *orc_grid_create_spectrum(const mer_volume_desc *d, const float *rgb) {
+    GridVolume *g = new GridVolume();
+    g->create(d, rgb, 3);
+    return g;
+}
+extern "C" void orc_grid_lookup_spectrum(void *h, size_t n, const float *p, float *out) {
+    const GridVolume *g = (const GridVolume *) h;
+    for (size_t i = 0; i < n; i++) g->lookupSpectrum(p + 3 * i, out + 3 * i);
 }
 extern "C" void orc_grid_destroy(void *h) { delete (GridVolume *) h; }
 extern "C" void orc_grid_lookup(void *h, size_t n, const float *p, float *out) {

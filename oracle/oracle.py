@@ -416,13 +416,16 @@ class RefGrid:
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.lib = C.CDLL(path)
-        self.lib.ref_grid_create.restype = C.c_void_p
+        self.lib.ref_grid_create_channels.restype = C.c_void_p
         data = np.ascontiguousarray(data)
         assert data.dtype in (np.float32, np.uint8)
+        self.channels = 3 if data.ndim == 4 else 1  # [z, y, x] density or [z, y, x, 3] albedo (lookupSpectrum, gridvolume.cpp:386-463)
+        assert data.ndim == 3 or data.shape[3] == 3
         N = (C.c_int * 3)(data.shape[2], data.shape[1], data.shape[0])
         lo = (C.c_float * 3)(*[float(v) for v in bmin])
         hi = (C.c_float * 3)(*[float(v) for v in bmax])
-        self.h = C.c_void_p(self.lib.ref_grid_create(data.ctypes.data_as(C.c_void_p), N, lo, hi, C.c_int(1 if data.dtype == np.float32 else 3)))
+        self.h = C.c_void_p(self.lib.ref_grid_create_channels(data.ctypes.data_as(C.c_void_p), N, lo, hi, C.c_int(1 if data.dtype == np.float32 else 3),
+                                                              C.c_int(self.channels)))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -433,6 +436,13 @@ class RefGrid:
         p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
         out = np.zeros(p.shape[0], np.float32)
         self.lib.ref_grid_lookup(self.h, C.c_size_t(p.shape[0]), _ptr(p, C.c_float), _ptr(out, C.c_float))
+        return out
+
+    def lookup_spectrum(self, p):
+        assert self.channels == 3
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((p.shape[0], 3), np.float32)
+        self.lib.ref_grid_lookup_spectrum(self.h, C.c_size_t(p.shape[0]), _ptr(p, C.c_float), _ptr(out, C.c_float))
         return out
 
 
@@ -529,6 +539,7 @@ class Oracle:
         for name in ("orc_rif_create", "orc_medium_create"):
             getattr(self.lib, name + self.suf).restype = C.c_void_p
         self.lib.orc_grid_create.restype = C.c_void_p
+        self.lib.orc_grid_create_spectrum.restype = C.c_void_p
 
     def _fn(self, name):
         return getattr(self.lib, name + self.suf)
@@ -578,6 +589,17 @@ class Oracle:
     def grid_create(self, desc, data):
         data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
         return C.c_void_p(self.lib.orc_grid_create(C.byref(desc), _ptr(data, C.c_float)))
+
+    def grid_create_spectrum(self, desc, rgb):
+        """3-channel grid, rgb[z, y, x, 3] (gridvolume.cpp:293-329, 401-421)"""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1)
+        return C.c_void_p(self.lib.orc_grid_create_spectrum(C.byref(desc), _ptr(rgb, C.c_float)))
+
+    def grid_lookup_spectrum(self, h, p):
+        p = np.ascontiguousarray(p, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((p.shape[0], 3), dtype=np.float32)
+        self.lib.orc_grid_lookup_spectrum(h, C.c_size_t(p.shape[0]), _ptr(p, C.c_float), _ptr(out, C.c_float))
+        return out
 
     def grid_destroy(self, h):
         self.lib.orc_grid_destroy(h)
@@ -677,6 +699,9 @@ class Oracle:
                                        _ptr(r["evaluations"], C.c_int32), C.c_int(start_mode))
         r["success"] = r["success"].astype(bool)
         return r
+
+    def medium_set_albedo_grid(self, h, grid):
+        self._fn("orc_medium_set_albedo_grid")(h, grid)
 
     def medium_set_sdf(self, h, sdf, aggressive=True):
         self._fn("orc_medium_set_sdf")(h, sdf, C.c_int(1 if aggressive else 0))

@@ -92,7 +92,7 @@ struct RefSplineDataSource : public RefVolume {
 
 /* GridDataSource (src/volume/gridvolume.cpp) reduced to the data members lookupFloat() uses */
 struct RefGridDataSource {
-#include "gridvolume_extract.inc" /* generated: enum EVolumeType, lookupFloat */
+#include "gridvolume_extract.inc" /* generated: enum EVolumeType, struct float3, lookupFloat, lookupSpectrum */
     Transform m_worldToGrid;
     Vector3i m_res;
     EVolumeType m_volumeType;
@@ -154,12 +154,12 @@ RefVolume *ref_load_volume(const char *path) {
 
 /* ---- C entry points of the density grid */
 extern "C" {
-/* type: 1 = float32 payload, 3 = uint8 payload (EVolumeType); data [z][y][x] */
-void *ref_grid_create(const void *data, const int *N, const float *bmin, const float *bmax, int type) {
+/* type: 1 = float32 payload, 3 = uint8 payload (EVolumeType); data [z][y][x][channels] */
+void *ref_grid_create_channels(const void *data, const int *N, const float *bmin, const float *bmax, int type, int channels) {
     RefGridDataSource *g = new RefGridDataSource();
     g->m_res = Vector3i(N[0], N[1], N[2]);
     g->m_volumeType = (RefGridDataSource::EVolumeType) type;
-    const size_t total = (size_t) N[0] * N[1] * N[2], bytes = total * (type == 1 ? sizeof(float) : 1);
+    const size_t total = (size_t) N[0] * N[1] * N[2] * channels, bytes = total * (type == 1 ? sizeof(float) : 1);
     g->m_data = new uint8_t[bytes];
     memcpy(g->m_data, data, bytes);
     /* configure(), gridvolume.cpp:188-195, with an identity toWorld */
@@ -174,6 +174,16 @@ void *ref_grid_create(const void *data, const int *N, const float *bmin, const f
     for (int i=0; i<255; i++) g->m_densityMap[i] = i/255.0f; /* :210 */
     g->m_densityMap[255] = 1.0f;                             /* :214 */
     return g;
+}
+void *ref_grid_create(const void *data, const int *N, const float *bmin, const float *bmax, int type) {
+    return ref_grid_create_channels(data, N, bmin, bmax, type, 1);
+}
+void ref_grid_lookup_spectrum(void *h, size_t n, const float *p, float *out) {
+    const RefGridDataSource *g = (const RefGridDataSource *) h;
+    for (size_t i = 0; i < n; i++) {
+        Spectrum s = g->lookupSpectrum(Point(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
+        out[3 * i] = s[0]; out[3 * i + 1] = s[1]; out[3 * i + 2] = s[2];
+    }
 }
 void ref_grid_free(void *h) {
     RefGridDataSource *g = (RefGridDataSource *) h;

@@ -160,7 +160,21 @@ def trace():
     print("wrote trace_ref.npz")
 
 
+def grid_spectrum():
+    """GridDataSource::lookupSpectrum (gridvolume.cpp:386-463, float3 :293-329) compiled verbatim, float32 and uint8 payloads"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_oracle_cpu import _grid_spectrum_scene
+    res, rgb, u8, lo, hi, p = _grid_spectrum_scene()
+    np.savez_compressed(os.path.join(HERE, "grid_spectrum_ref.npz"), f32=RefGrid(rgb, lo, hi).lookup_spectrum(p),
+                        u8=RefGrid(u8, lo, hi).lookup_spectrum(p))
+    print("wrote grid_spectrum_ref.npz")
+
+
 if __name__ == "__main__":
+    if "--grid-spectrum-only" in sys.argv:  # the other files are not rewritten
+        grid_spectrum()
+        sys.exit(0)
     main()
     phase()
     trace()
+    grid_spectrum()

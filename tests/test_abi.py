@@ -105,9 +105,21 @@ def test_vol_io_is_host_only(tmp_path):
     (tmp_path / "short.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", 1, 7, 6, 5, 1) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + b"\0" * 100)
     with pytest.raises(mer.MerError, match="truncated"):
         mer.fields.read_vol(tmp_path / "short.vol")
-    (tmp_path / "rgb.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", 1, 2, 2, 2, 3) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + b"\0" * 96)
-    with pytest.raises(mer.MerError, match="single-channel"):
-        mer.fields.read_vol(tmp_path / "rgb.vol")
+    # three interleaved channels: an albedo grid (gridvolume.cpp:251-262, 401-460); float32 and uint8
+    rgb = rng.random((4, 3, 5, 3)).astype(np.float32)
+    mer.fields.write_vol(tmp_path / "rgb.vol", rgb, (0, 0, 0), (1, 1, 1))
+    assert open(tmp_path / "rgb.vol", "rb").read()[:24] == b"VOL\x03" + struct.pack("<iiiii", 1, 5, 3, 4, 3)
+    back, lo, hi = mer.fields.read_vol(tmp_path / "rgb.vol")
+    assert back.shape == (4, 3, 5, 3) and np.array_equal(back, rgb)
+    u8 = rng.integers(0, 256, (4, 3, 5, 3), dtype=np.uint8)
+    (tmp_path / "rgb8.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", 3, 5, 3, 4, 3) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + u8.tobytes())
+    back, lo, hi = mer.fields.read_vol(tmp_path / "rgb8.vol")
+    assert np.array_equal(back, u8.astype(np.float32) / np.float32(255.0))
+    # float16 payloads and two-channel files are refused, not misread
+    for enc, ch in ((2, 1), (1, 2)):
+        (tmp_path / "f16.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", enc, 2, 2, 2, ch) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + b"\0" * 96)
+        with pytest.raises(mer.MerError, match="are supported on this path"):
+            mer.fields.read_vol(tmp_path / "f16.vol")
 
 
 @pytest.mark.skipif(mer.device_count() > 0, reason="a GPU is present")

@@ -323,6 +323,35 @@ def test_grid_lookup_against_the_reference_compiled_verbatim():
     assert np.array_equal(grid.lookupFloat(p), G["grid_lookup"])
 
 
+def test_grid_spectrum_lookup_against_the_reference_compiled_verbatim(oracle32, tmp_path):
+    """GridDataSource::lookupSpectrum (gridvolume.cpp:386-463) compiled verbatim (oracle/ref_volume.cpp) ->
+    tests/golden/grid_spectrum_ref.npz; the CUDA lookup is bit-identical for float32 and uint8 payloads, from arrays and files;
+    a lookup of the wrong kind is refused (supportsFloatLookups / supportsSpectrumLookups, :578-579)"""
+    import os
+    import struct
+    from test_oracle_cpu import _grid_spectrum_scene
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "grid_spectrum_ref.npz"))
+    res, rgb, u8, lo, hi, p = _grid_spectrum_scene()
+    grid = mer.GridDataSource(data=rgb, min=lo, max=hi)
+    got = grid.lookupSpectrum(p)
+    assert np.array_equal(got, G["f32"])
+    assert np.array_equal(got, oracle32.grid_lookup_spectrum(oracle32.grid_create_spectrum(volume_desc(res, lo, hi), rgb), p))
+    mer.fields.write_vol(tmp_path / "rgb.vol", rgb, lo, hi)
+    assert np.array_equal(mer.GridDataSource(filename=str(tmp_path / "rgb.vol")).lookupSpectrum(p), G["f32"])
+    hdr = b"VOL\x03" + struct.pack("<iiiii", 3, res[0], res[1], res[2], 3) + struct.pack("<6f", *lo, *hi)
+    (tmp_path / "rgb8.vol").write_bytes(hdr + u8.tobytes())
+    g8 = mer.GridDataSource(filename=str(tmp_path / "rgb8.vol"))
+    assert g8.channels == 3 and np.array_equal(g8.lookupSpectrum(p), G["u8"])
+    with pytest.raises(mer.MerError, match="single-channel"):
+        grid.lookupFloat(p)
+    with pytest.raises(mer.MerError, match="3-channel"):
+        mer.GridDataSource(data=rgb[..., 0], min=lo, max=hi).lookupSpectrum(p)
+    with pytest.raises(mer.MerError, match="one channel"):
+        grid.sampleDistance(p[:4], p[:4], 0.0, 1.0, 1.0, 1)
+    with pytest.raises(mer.MerError, match="one channel"):
+        mer.SplineDataSource(filename=str(tmp_path / "rgb.vol"))
+
+
 def test_eval_transmittance(oracle32):
     props = medium_props(sigmaS=(2.0, 3.0, 0.0), sigmaA=(0.5, 0.25, 0.0))
     rif, med, orif, omed = build("linear", 24, oracle32, props)

@@ -83,6 +83,69 @@ def test_woodcock_density_image_matches_oracle(oracle32):
         assert abs(stats[k] - ok) <= 0.005 * ok + 5, (k, stats[k], ok)
 
 
+def _albedo_field(res):
+    """a smooth RGB albedo in [0.2, 1] with different structure per channel, [z, y, x, 3]"""
+    x, y, z = [np.linspace(-1, 1, n, dtype=np.float32) for n in res]
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    return np.stack([0.6 + 0.4 * np.sin(3 * X), 0.6 + 0.4 * np.cos(2 * Y + 1), 0.6 + 0.4 * np.sin(2 * Z + X)], axis=-1).astype(np.float32)
+
+
+def test_albedo_grid_image_matches_oracle(oracle32, tmp_path):
+    """<volume name="albedo"> (heterogeneous.cpp:262-268): scattering events of the Woodcock walk weigh the path by
+    lookupSpectrum(p) (:646-649).  The image and the event counts follow the oracle on shared streams; a constant albedo
+    grid renders the constant-albedo image; a 3-channel .vol file gives the same medium as the array"""
+    props = medium_props(stepsize=1e-2, albedo=(0.9, 0.8, 0.7), densityScale=8.0)
+    med, omed, keep = setup(oracle32, "radial", 40, props, density=True)
+    scene = scene_dict(40, 40, 8, rfilter="box")
+    integ = mer.EikonalVolPathIntegrator(stepsPerPass=300, poolPaths=2048)
+    film_const, stats_const = integ.render(scene, med)
+
+    ares = (24, 20, 28)
+    rgb = _albedo_field(ares)
+    agrid = mer.GridDataSource(data=rgb, min=BOX_MIN, max=BOX_MAX)
+    assert agrid.supportsSpectrumLookups() and not agrid.supportsFloatLookups()
+    med2, omed2, keep2 = setup(oracle32, "radial", 40, props, density=True)
+    med2.setAlbedoVolume(agrid)
+    oracle32.medium_set_albedo_grid(omed2, oracle32.grid_create_spectrum(volume_desc(ares, BOX_MIN, BOX_MAX), rgb))
+    film, stats = integ.render(scene, med2)
+    ofilm, ostats = oracle32.render(omed2, oracle_render_desc(scene))
+    relmse, frac_tight = image_gates(film, ofilm, 8)
+    assert frac_tight > 0.97 and relmse < 1e-3, (relmse, frac_tight)
+    for k, ok in (("ray_steps", ostats.ray_steps), ("scatter_events", ostats.scatter_events), ("null_collisions", ostats.null_collisions)):
+        assert abs(stats[k] - ok) <= 0.005 * ok + 5, (k, stats[k], ok)
+    assert np.abs(film[..., :3] - film_const[..., :3]).max() > 1e-3  # the albedo grid does change the image
+
+    # through addChild("albedo") + configure(), from a 3-channel .vol file
+    mer.fields.write_vol(tmp_path / "albedo.vol", rgb, BOX_MIN, BOX_MAX)
+    fgrid = mer.GridDataSource(filename=str(tmp_path / "albedo.vol"))
+    assert fgrid.channels == 3
+    data, lo, hi = make_field("radial", 40)
+    rif = mer.SplineDataSource(data=data, min=lo, max=hi)
+    dens = mer.GridDataSource(data=mer.fields.sine_density((32, 32, 32), BOX_MIN, BOX_MAX), min=BOX_MIN, max=BOX_MAX)
+    med3 = (mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9))
+            .addChild("density", dens).addChild("albedo", fgrid).configure())
+    film3, _ = integ.render(scene, med3)
+    assert np.array_equal(film3, film)
+
+    # a constant grid is the constant albedo: lerps of equal values are exact up to (1 - f) + f rounding, so compare closely
+    cgrid = mer.GridDataSource(data=np.broadcast_to(np.array((0.9, 0.8, 0.7), np.float32), ares[::-1] + (3,)).copy(), min=BOX_MIN, max=BOX_MAX)
+    med2.setAlbedoVolume(cgrid)
+    film_c, _ = integ.render(scene, med2)
+    assert np.allclose(film_c, film_const, rtol=2e-5, atol=1e-6)
+    med2.setAlbedoVolume(None)  # detached: the constant again, exactly
+    film_d, _ = integ.render(scene, med2)
+    assert np.array_equal(film_d, film_const)
+
+    # validation: an albedo volume needs spectrum lookups and a density volume (heterogeneous.cpp:229-236, 266-268)
+    with pytest.raises(mer.MerError, match="spectrum lookups"):
+        med2.setAlbedoVolume(keep2[1])
+    plain, _, _ = setup(oracle32, "radial", 40, medium_props(stepsize=1e-2))
+    with pytest.raises(mer.MerError, match="density volume"):
+        plain.setAlbedoVolume(agrid)
+    with pytest.raises(mer.MerError, match="one channel"):
+        mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("density", agrid).configure()
+
+
 def test_max_depth_and_rr(oracle32):
     props = medium_props(stepsize=2e-2, sigmaS=6.0, sigmaA=0.0)
     med, omed, keep = setup(oracle32, "radial", 32, props, g=0.0)

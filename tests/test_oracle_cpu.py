@@ -312,6 +312,39 @@ def test_oracle_grid_lookup_bit_exact_vs_reference_golden(oracle32):
     assert np.array_equal(oracle32.grid_lookup(g, p), G["grid_lookup"])
 
 
+def _grid_spectrum_scene():
+    rng = np.random.default_rng(37)
+    res = (19, 13, 21)
+    rgb = rng.random((res[2], res[1], res[0], 3)).astype(np.float32)
+    u8 = rng.integers(0, 256, (res[2], res[1], res[0], 3), dtype=np.uint8)
+    lo, hi = np.array([-1.0, -0.5, 0.25], np.float32), np.array([1.5, 0.75, 2.0], np.float32)
+    p = (lo - 0.1 + rng.random((6000, 3)) * (hi - lo + 0.2)).astype(np.float32)  # some outside: lookupSpectrum returns 0 there
+    p[:8] = [[lo[0], lo[1], lo[2]], [hi[0], hi[1], hi[2]], [lo[0], hi[1], lo[2]], [hi[0], lo[1], hi[2]], [0, 0, 1], [1.5, 0, 1], [0, 0.75, 1], [0, 0, 2]]
+    return res, rgb, u8, lo, hi, p
+
+
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+def test_oracle_grid_spectrum_lookup_bit_exact_vs_verbatim_reference(oracle32):
+    """GridDataSource::lookupSpectrum (gridvolume.cpp:386-463) with its float3 helper (:293-329) compiled verbatim against the
+    restated 3-channel lookup - bit for bit, float32 and uint8 payloads (the latter through m_densityMap = i / 255)"""
+    res, rgb, u8, lo, hi, p = _grid_spectrum_scene()
+    for payload, as_float in ((rgb, rgb), (u8, u8.astype(np.float32) / np.float32(255.0))):
+        ref = RefGrid(payload, lo, hi).lookup_spectrum(p)
+        g = oracle32.grid_create_spectrum(volume_desc(res, lo, hi), as_float)
+        got = oracle32.grid_lookup_spectrum(g, p)
+        assert (ref.sum(axis=1) == 0).sum() > 100 and (ref.min(axis=1) > 0).sum() > 3000
+        assert np.array_equal(got, ref), (np.abs(got - ref).max(), np.mean(got != ref))
+
+
+def test_oracle_grid_spectrum_lookup_bit_exact_vs_reference_golden(oracle32):
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "grid_spectrum_ref.npz"))
+    res, rgb, u8, lo, hi, p = _grid_spectrum_scene()
+    g = oracle32.grid_create_spectrum(volume_desc(res, lo, hi), rgb)
+    assert np.array_equal(oracle32.grid_lookup_spectrum(g, p), G["f32"])
+    g = oracle32.grid_create_spectrum(volume_desc(res, lo, hi), u8.astype(np.float32) / np.float32(255.0))
+    assert np.array_equal(oracle32.grid_lookup_spectrum(g, p), G["u8"])
+
+
 def _film_scene():
     rng = np.random.default_rng(41)
     W, H, n = 37, 29, 20000
@@ -648,6 +681,35 @@ def test_render_white_furnace_and_sharding(oracle32):
     parts = [oracle32.render(omed, oracle_render_desc(scene, rr_depth=1000, sample_begin=r, sample_stride=3)) for r in range(3)]
     assert sum(p[1].samples for p in parts) == st.samples and sum(p[1].ray_steps for p in parts) == st.ray_steps
     assert np.allclose(sum(p[0] for p in parts), film, rtol=1e-5, atol=1e-6)
+
+
+def test_render_with_an_albedo_volume(oracle32):
+    """the `albedo` child (heterogeneous.cpp:262-268, :646-649) in the oracle's Woodcock walk: a constant RGB grid is the
+    constant albedo (to the rounding of the trilinear weights), a per-channel grid scales each channel's single-scattered part
+    and leaves the path geometry (events, steps) alone"""
+    res = 16
+    from mitsubaer_b200 import fields
+    lo, hi = fields.padded_bbox(BOX_MIN, BOX_MAX, (res,) * 3)
+    orif = oracle32.rif_create(volume_desc((res,) * 3, lo, hi), fields.radial_rif((res,) * 3, lo, hi))
+    dens = oracle32.grid_create(volume_desc((12,) * 3, BOX_MIN, BOX_MAX), fields.sine_density((12,) * 3, BOX_MIN, BOX_MAX))
+    props = medium_props(stepsize=5e-2, albedo=(0.9, 0.6, 0.3), densityScale=4.0)
+    scene = scene_dict(12, 12, 4, rfilter="box")
+    omed = oracle32.medium_create(oracle_medium_desc(props, 0.5, has_density=True), orif, dens)
+    film0, st0 = oracle32.render(omed, oracle_render_desc(scene))
+    const = np.broadcast_to(np.array((0.9, 0.6, 0.3), np.float32), (9, 8, 7, 3)).copy()
+    oracle32.medium_set_albedo_grid(omed, oracle32.grid_create_spectrum(volume_desc((7, 8, 9), BOX_MIN, BOX_MAX), const))
+    film1, st1 = oracle32.render(omed, oracle_render_desc(scene))
+    assert st1.ray_steps == st0.ray_steps and st1.scatter_events == st0.scatter_events and st0.scatter_events > 100
+    assert np.allclose(film1, film0, rtol=2e-5, atol=1e-6)
+    red = const.copy()
+    red[..., 1:] = 0.0  # no green or blue scattering at all: those channels keep only unscattered light
+    oracle32.medium_set_albedo_grid(omed, oracle32.grid_create_spectrum(volume_desc((7, 8, 9), BOX_MIN, BOX_MAX), red))
+    film2, st2 = oracle32.render(omed, oracle_render_desc(scene))
+    assert st2.ray_steps == st0.ray_steps
+    assert np.allclose(film2[..., 0], film0[..., 0], rtol=2e-5, atol=1e-6)
+    assert film2[..., 1].sum() < film0[..., 1].sum() and np.all(film2[..., 1] <= film0[..., 1] + 1e-6)
+    oracle32.medium_set_albedo_grid(omed, None)
+    assert np.array_equal(oracle32.render(omed, oracle_render_desc(scene))[0], film0)
 
 
 def test_hessian_and_derivative_step_consistency(oracle64):
