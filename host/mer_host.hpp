@@ -198,6 +198,7 @@ struct SplineDataSource : Object { /* <volume type="splinevolume"> */
 
 struct GridDataSource : Object { /* <volume type="gridvolume"> */
     mer_grid *handle = nullptr;
+    int channels = 1; /* the file header's channel count: 1 = density, 3 = albedo (gridvolume.cpp:251-262, 578-579) */
     const char *className() const override { return "GridDataSource"; }
     void configure() override {
         mer_volume_desc ov;
@@ -205,7 +206,8 @@ struct GridDataSource : Object { /* <volume type="gridvolume"> */
         props.getBoolean("sendData", false);
         const int device = (int) props.getInteger("device", defaultDevice());
         const std::string file = props.getString("filename");
-        if (dryRun()) { mer_volume_desc d; int32_t enc, ch; merCheck(mer_vol_read_header(file.c_str(), &d, &enc, &ch)); return; }
+        { mer_volume_desc d; int32_t enc, ch; merCheck(mer_vol_read_header(file.c_str(), &d, &enc, &ch)); channels = ch; }
+        if (dryRun()) return;
         merCheck(mer_grid_create_from_file(device, file.c_str(), &ov, &handle));
     }
     ~GridDataSource() override { mer_grid_destroy(handle); }
@@ -286,7 +288,10 @@ struct HeterogeneousRefractiveMedium : Object { /* <medium type="heterogeneousre
         if (auto p = std::dynamic_pointer_cast<HGPhaseFunction>(child)) { if (phase) logError("Medium: phase function already set"); phase = p; }
         else if (name == "rif" && std::dynamic_pointer_cast<SplineDataSource>(child)) rif = std::dynamic_pointer_cast<SplineDataSource>(child);
         else if (name == "density" && std::dynamic_pointer_cast<GridDataSource>(child)) density = std::dynamic_pointer_cast<GridDataSource>(child);
-        else if (name == "albedo" && std::dynamic_pointer_cast<GridDataSource>(child)) albedo = std::dynamic_pointer_cast<GridDataSource>(child);
+        else if (name == "albedo" && std::dynamic_pointer_cast<GridDataSource>(child)) {
+            albedo = std::dynamic_pointer_cast<GridDataSource>(child);
+            if (albedo->channels != 3) logError("Medium: the albedo volume must support spectrum lookups (3 channels, heterogeneous.cpp:266-268)");
+        }
         else if (name == "sdf" && std::dynamic_pointer_cast<SplineDataSource>(child)) sdf = std::dynamic_pointer_cast<SplineDataSource>(child); /* :376-380 */
         else logError("Medium: Invalid child node! (\"" + std::string(child->className()) + "\")");
     }

@@ -25,11 +25,11 @@ static void printDesc(const Scene &S) {
                 r.env_radiance[0], r.env_radiance[1], r.env_radiance[2], r.has_quad, r.quad_origin[0], r.quad_origin[1], r.quad_origin[2],
                 r.quad_u[0], r.quad_u[1], r.quad_u[2], r.quad_v[0], r.quad_v[1], r.quad_v[2], r.quad_radiance[0], r.quad_radiance[1], r.quad_radiance[2]);
     std::printf(" \"medium\": {\"sigma_s\": [%g, %g, %g], \"sigma_a\": [%g, %g, %g], \"albedo\": [%g, %g, %g], \"stepsize\": %g, \"weight\": %g, \"strategy\": %d,\n"
-                "  \"channel\": %d, \"density_scale\": %g, \"hg_g\": %g, \"shape_type\": %d, \"shape\": [%g, %g, %g, %g, %g, %g], \"boundary\": %d, \"has_density\": %d,\n"
+                "  \"channel\": %d, \"density_scale\": %g, \"hg_g\": %g, \"shape_type\": %d, \"shape\": [%g, %g, %g, %g, %g, %g], \"boundary\": %d, \"has_density\": %d, \"has_albedo_volume\": %d,\n"
                 "  \"rif_res\": [%d, %d, %d], \"rif_bbox\": [%g, %g, %g, %g, %g, %g]}}\n",
                 m.sigma_s[0], m.sigma_s[1], m.sigma_s[2], m.sigma_a[0], m.sigma_a[1], m.sigma_a[2], m.albedo[0], m.albedo[1], m.albedo[2], m.stepsize,
                 m.medium_sampling_weight, m.strategy, m.channel, m.density_scale, m.hg_g, m.shape_type, m.shape[0], m.shape[1], m.shape[2], m.shape[3],
-                m.shape[4], m.shape[5], m.boundary, S.medium->density ? 1 : 0, S.medium->rif->desc.res[0], S.medium->rif->desc.res[1], S.medium->rif->desc.res[2],
+                m.shape[4], m.shape[5], m.boundary, S.medium->density ? 1 : 0, S.medium->albedo ? 1 : 0, S.medium->rif->desc.res[0], S.medium->rif->desc.res[1], S.medium->rif->desc.res[2],
                 S.medium->rif->desc.bbox_min[0], S.medium->rif->desc.bbox_min[1], S.medium->rif->desc.bbox_min[2], S.medium->rif->desc.bbox_max[0],
                 S.medium->rif->desc.bbox_max[1], S.medium->rif->desc.bbox_max[2]);
 }

@@ -125,16 +125,16 @@ def test_albedo_grid_image_matches_oracle(oracle32, tmp_path):
     med3 = (mer.HeterogeneousRefractiveMedium(props).addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9))
             .addChild("density", dens).addChild("albedo", fgrid).configure())
     film3, _ = integ.render(scene, med3)
-    assert np.array_equal(film3, film)
+    assert np.allclose(film3, film, rtol=2e-5, atol=2e-5)  # the same paths; splats are atomic adds in a free order
 
     # a constant grid is the constant albedo: lerps of equal values are exact up to (1 - f) + f rounding, so compare closely
     cgrid = mer.GridDataSource(data=np.broadcast_to(np.array((0.9, 0.8, 0.7), np.float32), ares[::-1] + (3,)).copy(), min=BOX_MIN, max=BOX_MAX)
     med2.setAlbedoVolume(cgrid)
     film_c, _ = integ.render(scene, med2)
-    assert np.allclose(film_c, film_const, rtol=2e-5, atol=1e-6)
-    med2.setAlbedoVolume(None)  # detached: the constant again, exactly
-    film_d, _ = integ.render(scene, med2)
-    assert np.array_equal(film_d, film_const)
+    assert np.allclose(film_c, film_const, rtol=5e-5, atol=2e-5)
+    med2.setAlbedoVolume(None)  # detached: the constant again
+    film_d, stats_d = integ.render(scene, med2)
+    assert np.allclose(film_d, film_const, rtol=2e-5, atol=2e-5) and stats_d["ray_steps"] == stats_const["ray_steps"]
 
     # validation: an albedo volume needs spectrum lookups and a density volume (heterogeneous.cpp:229-236, 266-268)
     with pytest.raises(mer.MerError, match="spectrum lookups"):

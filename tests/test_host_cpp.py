@@ -100,6 +100,56 @@ def test_density_child_and_sphere_container(volumes, tmp_path):
     assert np.allclose(m["sigma_s"], 3.6 * 8)  # `scale` multiplies sigmaS / sigmaA (medium/materials.h)
 
 
+def _albedo_scene(volumes, tmp_path):
+    d, lo, hi = volumes
+    x = np.linspace(-1, 1, 20, dtype=np.float32)
+    Z, Y, X = np.meshgrid(x, x, x, indexing="ij")
+    rgb = np.stack([0.6 + 0.4 * np.sin(3 * X), 0.6 + 0.4 * np.cos(2 * Y), 0.6 + 0.4 * np.sin(2 * Z)], axis=-1).astype(np.float32)
+    mer.fields.write_vol(tmp_path / "albedo.vol", rgb, BOX_MIN, BOX_MAX)
+    text = open(SCENE).read()
+    text = text.replace('<volume name="rif" type="splinevolume">', '<volume name="density" type="gridvolume"><string name="filename" value="%s"/></volume>\n'
+                        '<volume name="albedo" type="gridvolume"><string name="filename" value="%s"/></volume>\n'
+                        '<float name="scale" value="8"/><spectrum name="albedo" value="0.9, 0.8, 0.7"/>\n<volume name="rif" type="splinevolume">'
+                        % (d / "den.vol", tmp_path / "albedo.vol"))
+    p = tmp_path / "albedo.xml"
+    p.write_text(text)
+    return p, rgb
+
+
+def test_albedo_volume_child(volumes, tmp_path):
+    """<volume name="albedo" type="gridvolume"> (heterogeneous.cpp:262-268): a 3-channel .vol; a density file in its place is refused"""
+    d, lo, hi = volumes
+    p, rgb = _albedo_scene(volumes, tmp_path)
+    out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "--dry-run"])
+    assert out.returncode == 0, out.stderr
+    m = json.loads(out.stdout)["medium"]
+    assert m["has_density"] == 1 and m["has_albedo_volume"] == 1
+    bad = tmp_path / "bad.xml"
+    bad.write_text(p.read_text().replace(str(tmp_path / "albedo.vol"), str(d / "den.vol")))
+    out = run([str(bad), "-D", "rif=%s" % (d / "rif.vol"), "--dry-run"])
+    assert out.returncode == 1 and "spectrum lookups" in out.stderr
+
+
+@pytest.mark.gpu
+def test_cli_render_with_albedo_volume_matches_python_mirror(volumes, tmp_path):
+    d, lo, hi = volumes
+    p, rgb = _albedo_scene(volumes, tmp_path)
+    film_path = tmp_path / "film.bin"
+    out = run([str(p), "-D", "rif=%s" % (d / "rif.vol"), "-D", "spp=8", "-D", "width=48", "-D", "height=40", "-D", "stepsize=0.01", "--film", str(film_path)])
+    assert out.returncode == 0, out.stderr
+    stats = json.loads(out.stdout)
+    film = np.fromfile(film_path, np.float32).reshape(40, 48, 5)
+    rif = mer.SplineDataSource(filename=str(d / "rif.vol"))
+    med = mer.HeterogeneousRefractiveMedium(sigmaS=3.6, sigmaA=0.4, scale=8.0, albedo=(0.9, 0.8, 0.7), stepsize=0.01, strategy="single", shape=("box", BOX_MIN, BOX_MAX))
+    med.addChild("rif", rif).addChild("", mer.HGPhaseFunction(g=0.9)).addChild("density", mer.GridDataSource(filename=str(d / "den.vol")))
+    med.addChild("albedo", mer.GridDataSource(data=rgb, min=BOX_MIN, max=BOX_MAX)).configure()
+    scene = dict(width=48, height=40, sampleCount=8, seed=20201201, origin=(0, 0, -4), target=(0, 0, -3), up=(0, 1, 0), fov=40.0,
+                 rfilter="gaussian", envRadiance=1.0, quad=dict(origin=(-0.5, 1.5, -0.5), u=(1, 0, 0), v=(0, 0, 1), radiance=(8, 6, 4)))
+    ref, st = mer.EikonalVolPathIntegrator(maxDepth=64, rrDepth=5).render(scene, med)
+    assert stats["samples"] == st["samples"] == 48 * 40 * 8 and stats["ray_steps"] == st["ray_steps"] and st["null_collisions"] > 0
+    assert np.allclose(film, ref, rtol=1e-5, atol=1e-5)  # same paths; only the order of the float atomics differs
+
+
 @pytest.mark.gpu
 def test_cli_render_matches_python_mirror(volumes, tmp_path):
     d, lo, hi = volumes
