@@ -54,6 +54,7 @@ k_prefilter(const float *in, float *out, int N0, int N1, int N2, int pass) {
     const int CUT = 64;
     float cp = 0.0f;
     double zp = 1.0;
+#pragma unroll 8
     for (int i = 0; i < len && i < CUT; i++) {
         cp = (float) ((double) cp + (double) src[(size_t) i * stride] * zp);
         zp *= z1d;
@@ -65,21 +66,136 @@ k_prefilter(const float *in, float *out, int N0, int N1, int N2, int pass) {
     }
     cp = (float) ((double) cp / (1.0 - pow(z1d, (double) (2 * len - 2))));
 
+    /* The recursions are a dependent chain per line, so a thread that loads one element at a time keeps one 4-byte load in
+     * flight: 2048 threads per SM x 4 bytes is a quarter of what the HBM latency asks for (measured: 1.55 TB/s at 1024^3).
+     * Elements are therefore loaded PF at a time ahead of the chain (same operations in the same order: bit-identical). */
+    constexpr int PF = 8;
     /* causal recursion, storing c+ in place */
     dst[0] = cp;
     float cpPrev2 = cp;
-    for (int i = 1; i < len; i++) {
-        cpPrev2 = cp;
-        cp = __fadd_rn(src[(size_t) i * stride], __fmul_rn(z1, cp));
-        dst[(size_t) i * stride] = cp;
+    for (int i0 = 1; i0 < len; i0 += PF) {
+        float v[PF];
+#pragma unroll
+        for (int k = 0; k < PF; k++)
+            if (i0 + k < len) v[k] = src[(size_t) (i0 + k) * stride];
+#pragma unroll
+        for (int k = 0; k < PF; k++)
+            if (i0 + k < len) {
+                cpPrev2 = cp;
+                cp = __fadd_rn(v[k], __fmul_rn(z1, cp));
+                dst[(size_t) (i0 + k) * stride] = cp;
+            }
     }
     /* anti-causal recursion */
     const float gain = __fdiv_rn(z1, __fsub_rn(__fmul_rn(z1, z1), 1.0f));
     float cn = __fmul_rn(gain, __fadd_rn(cp, __fmul_rn(z1, cpPrev2)));
     dst[(size_t) (len - 1) * stride] = __fmul_rn(6.0f, cn);
-    for (int i = len - 2; i >= 0; i--) {
-        cn = __fmul_rn(z1, __fsub_rn(cn, dst[(size_t) i * stride]));
-        dst[(size_t) i * stride] = __fmul_rn(6.0f, cn);
+    for (int i0 = len - 2; i0 >= 0; i0 -= PF) {
+        float v[PF];
+#pragma unroll
+        for (int k = 0; k < PF; k++)
+            if (i0 - k >= 0) v[k] = dst[(size_t) (i0 - k) * stride];
+#pragma unroll
+        for (int k = 0; k < PF; k++)
+            if (i0 - k >= 0) {
+                cn = __fmul_rn(z1, __fsub_rn(cn, v[k]));
+                dst[(size_t) (i0 - k) * stride] = __fmul_rn(6.0f, cn);
+            }
+    }
+}
+
+/* The x pass, tiled: a thread still owns one line and runs build1d's recursions in the same order (bit-identical to
+ * k_prefilter's PASS_X), but the line's elements travel through a shared-memory tile of 32 x-values by PFX_LINES lines, so
+ * every global load and store is a warp reading 128 consecutive bytes of ONE line instead of 32 threads touching 32
+ * different lines (k_prefilter's x pass ran at half the rate of its y and z passes: profiles/r02_launch_summary.txt).
+ * Lines of a block are consecutive in memory (line l starts at l * N0).  Forward sweep over the tiles: c+ in place;
+ * backward sweep: c- from c+, scaled by 6. */
+enum { PFX_LINES = 128, PFX_TILE = 32 }; /* PFX_LINES / 32 = 4 warps, each moving every 4th line of a tile */
+
+__global__ void __launch_bounds__(PFX_LINES)
+k_prefilter_x(float *data, int N0, size_t nLines) {
+    __shared__ float tile[PFX_LINES][PFX_TILE + 1];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const size_t line0 = (size_t) blockIdx.x * PFX_LINES;
+    const int linesHere = (int) min((size_t) PFX_LINES, nLines - line0);
+    float *blockBase = data + line0 * (size_t) N0;
+    const int len = N0;
+    const int nTiles = (len + PFX_TILE - 1) / PFX_TILE;
+    const bool mine = t < linesHere;
+
+    auto loadTile = [&](int c) {
+        const int x = c * PFX_TILE + lane;
+#pragma unroll 8
+        for (int r = warp; r < PFX_LINES; r += PFX_LINES / 32)
+            if (r < linesHere && x < len) tile[r][lane] = blockBase[(size_t) r * len + x];
+        __syncthreads();
+    };
+    auto storeTile = [&](int c) {
+        __syncthreads();
+        const int x = c * PFX_TILE + lane;
+#pragma unroll 8
+        for (int r = warp; r < PFX_LINES; r += PFX_LINES / 32)
+            if (r < linesHere && x < len) blockBase[(size_t) r * len + x] = tile[r][lane];
+        __syncthreads();
+    };
+
+    const float z1 = (float) (-2.0 + sqrt(3.0));
+    const double z1d = (double) z1;
+    const int CUT = 64;
+    /* initial causal coefficient: the first CUT elements (two tiles), then build1d's mirrored tail for lines shorter than CUT */
+    float cp = 0.0f;
+    double zp = 1.0;
+    for (int c = 0; c < nTiles && c * PFX_TILE < CUT; c++) {
+        loadTile(c);
+        if (mine)
+            for (int j = 0; j < PFX_TILE; j++) {
+                const int i = c * PFX_TILE + j;
+                if (i >= len || i >= CUT) break;
+                cp = (float) ((double) cp + (double) tile[t][j] * zp);
+                zp *= z1d;
+            }
+        __syncthreads();
+    }
+    if (mine) {
+        const float *src = blockBase + (size_t) t * len;
+        for (int i = len - 2; i > 0; i--) {
+            int e = 2 * len - 2 - i;
+            if (e >= CUT) break;
+            cp = (float) ((double) cp + (double) src[i] * pow(z1d, (double) e));
+        }
+        cp = (float) ((double) cp / (1.0 - pow(z1d, (double) (2 * len - 2))));
+    }
+
+    /* causal recursion */
+    float cpPrev2 = cp;
+    for (int c = 0; c < nTiles; c++) {
+        loadTile(c);
+        if (mine)
+            for (int j = 0; j < PFX_TILE; j++) {
+                const int i = c * PFX_TILE + j;
+                if (i >= len) break;
+                if (i > 0) {
+                    cpPrev2 = cp;
+                    cp = __fadd_rn(tile[t][j], __fmul_rn(z1, cp));
+                }
+                tile[t][j] = cp;
+            }
+        storeTile(c);
+    }
+    /* anti-causal recursion */
+    const float gain = __fdiv_rn(z1, __fsub_rn(__fmul_rn(z1, z1), 1.0f));
+    float cn = 0.0f;
+    for (int c = nTiles - 1; c >= 0; c--) {
+        loadTile(c);
+        if (mine)
+            for (int j = PFX_TILE - 1; j >= 0; j--) {
+                const int i = c * PFX_TILE + j;
+                if (i >= len) continue;
+                if (i == len - 1) cn = __fmul_rn(gain, __fadd_rn(cp, __fmul_rn(z1, cpPrev2)));
+                else cn = __fmul_rn(z1, __fsub_rn(cn, tile[t][j]));
+                tile[t][j] = __fmul_rn(6.0f, cn);
+            }
+        storeTile(c);
     }
 }
 
@@ -354,7 +470,10 @@ int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
     const int N0 = d.res[0], N1 = d.res[1], N2 = d.res[2];
     const unsigned T = 128;
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N2, T), T, 0, s, data_dev, r->d_coeff, N0, N1, N2, (int) PASS_Y);
-    MER_LAUNCH(k_prefilter, mer_blocks((size_t) N1 * N2, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_X);
+    if (getenv("MER_PREFILTER_X_UNTILED")) /* the one-thread-per-line x pass, kept for comparison (bit-identical) */
+        MER_LAUNCH(k_prefilter, mer_blocks((size_t) N1 * N2, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_X);
+    else
+        MER_LAUNCH(k_prefilter_x, mer_blocks((size_t) N1 * N2, PFX_LINES), PFX_LINES, 0, s, r->d_coeff, N0, (size_t) N1 * N2);
     MER_LAUNCH(k_prefilter, mer_blocks((size_t) N0 * N1, T), T, 0, s, r->d_coeff, r->d_coeff, N0, N1, N2, (int) PASS_Z);
     const unsigned G = (unsigned) std::min<size_t>(mer_blocks(total, 256), 148u * 16u);
     fill_rif_dev(r);
