@@ -110,7 +110,7 @@ k_prefilter(const float *in, float *out, int N0, int N1, int N2, int pass) {
  * different lines (k_prefilter's x pass ran at half the rate of its y and z passes: profiles/r02_launch_summary.txt).
  * Lines of a block are consecutive in memory (line l starts at l * N0).  Forward sweep over the tiles: c+ in place;
  * backward sweep: c- from c+, scaled by 6. */
-enum { PFX_LINES = 128, PFX_TILE = 32 }; /* PFX_LINES / 32 = 4 warps, each moving every 4th line of a tile */
+enum { PFX_LINES = 128, PFX_TILE = 32 }; /* 4 warps, each moving every 4th line of a tile */
 
 __global__ void __launch_bounds__(PFX_LINES)
 k_prefilter_x(float *data, int N0, size_t nLines) {
@@ -136,6 +136,23 @@ k_prefilter_x(float *data, int N0, size_t nLines) {
 #pragma unroll 8
         for (int r = warp; r < PFX_LINES; r += PFX_LINES / 32)
             if (r < linesHere && x < len) blockBase[(size_t) r * len + x] = tile[r][lane];
+        __syncthreads();
+    };
+
+    /* the next tile waits in registers while the block runs the recursion on the current one: the loads of a block overlap its
+     * own arithmetic (a thread reads back exactly the addresses it stored in the other sweep, so program order is enough) */
+    float nxt[PFX_LINES / 4];
+    auto fetch = [&](int c) {
+        const int x = c * PFX_TILE + lane;
+#pragma unroll
+        for (int k = 0; k < PFX_LINES / 4; k++) {
+            const int r = warp + 4 * k;
+            nxt[k] = (r < linesHere && x < len) ? blockBase[(size_t) r * len + x] : 0.0f;
+        }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int k = 0; k < PFX_LINES / 4; k++) tile[warp + 4 * k][lane] = nxt[k];
         __syncthreads();
     };
 
@@ -168,9 +185,12 @@ k_prefilter_x(float *data, int N0, size_t nLines) {
 
     /* causal recursion */
     float cpPrev2 = cp;
+    fetch(0);
     for (int c = 0; c < nTiles; c++) {
-        loadTile(c);
+        commit();
+        if (c + 1 < nTiles) fetch(c + 1);
         if (mine)
+#pragma unroll 4
             for (int j = 0; j < PFX_TILE; j++) {
                 const int i = c * PFX_TILE + j;
                 if (i >= len) break;
@@ -185,9 +205,12 @@ k_prefilter_x(float *data, int N0, size_t nLines) {
     /* anti-causal recursion */
     const float gain = __fdiv_rn(z1, __fsub_rn(__fmul_rn(z1, z1), 1.0f));
     float cn = 0.0f;
+    fetch(nTiles - 1);
     for (int c = nTiles - 1; c >= 0; c--) {
-        loadTile(c);
+        commit();
+        if (c > 0) fetch(c - 1);
         if (mine)
+#pragma unroll 4
             for (int j = PFX_TILE - 1; j >= 0; j--) {
                 const int i = c * PFX_TILE + j;
                 if (i >= len) continue;
