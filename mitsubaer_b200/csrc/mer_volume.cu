@@ -537,7 +537,14 @@ int rif_build(mer_rif *r, const float *data_dev, cudaStream_t s) {
 /* .vol payloads this path reads: EFloat32 and EUInt8 (value / 255), one channel (densities, RIFs, SDFs) or three
  * interleaved channels (albedo grids) (gridvolume.cpp:251-262, 369-376, 401-460) */
 static bool vol_encoding_supported(int32_t enc, int32_t ch) { return (ch == 1 || ch == 3) && (enc == 1 || enc == 3); }
-static const char *kVolUnsupported = "float32 and uint8 .vol files with one channel or three (albedo) are supported on this path (no float16, no quantized-direction grids)";
+/* the reference's own messages where it refuses a payload too (gridvolume.cpp:243-268) */
+static int vol_unsupported(int32_t enc, int32_t ch) {
+    char msg[160];
+    if (enc == 2) return mer::fail(MER_ERR_UNSUPPORTED, "Error: float16 volumes are not yet supported!");
+    if (enc == 4) return mer::fail(MER_ERR_UNSUPPORTED, "quantized-direction volumes feed the micro-flake phase functions, which are not on this path");
+    snprintf(msg, sizeof(msg), "Encountered an unsupported %s volume data file (%i channels, only 1 and 3 are supported)", enc == 1 ? "float32" : "uint8", (int) ch);
+    return mer::fail(MER_ERR_UNSUPPORTED, msg);
+}
 
 int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *data, int32_t *encoding,
                   int32_t *channels) {
@@ -583,7 +590,7 @@ int read_vol_file(const char *path, mer_volume_desc *desc, std::vector<float> *d
     if (data) {
         if (!vol_encoding_supported(enc, ch)) {
             fclose(f);
-            return mer::fail(MER_ERR_UNSUPPORTED, kVolUnsupported);
+            return vol_unsupported(enc, ch);
         }
         size_t total = (size_t) res[0] * res[1] * res[2] * (size_t) ch;
         data->resize(total);
@@ -608,7 +615,7 @@ int stream_vol_to_device(int device, const char *path, mer_volume_desc *desc, fl
     int32_t enc = 0, ch = 0;
     int rc = read_vol_file(path, desc, nullptr, &enc, &ch);
     if (rc) return rc;
-    if (!vol_encoding_supported(enc, ch)) return mer::fail(MER_ERR_UNSUPPORTED, kVolUnsupported);
+    if (!vol_encoding_supported(enc, ch)) return vol_unsupported(enc, ch);
     /* a caller that does not ask for the channel count takes scalar fields only (RIF, SDF) */
     if (!channels_out && ch != 1) return mer::fail(MER_ERR_INVALID, "this volume must have one channel (supportsFloatLookups)");
     if (channels_out) *channels_out = ch;

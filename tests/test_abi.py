@@ -115,10 +115,11 @@ def test_vol_io_is_host_only(tmp_path):
     (tmp_path / "rgb8.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", 3, 5, 3, 4, 3) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + u8.tobytes())
     back, lo, hi = mer.fields.read_vol(tmp_path / "rgb8.vol")
     assert np.array_equal(back, u8.astype(np.float32) / np.float32(255.0))
-    # float16 payloads and two-channel files are refused, not misread
-    for enc, ch in ((2, 1), (1, 2)):
+    # float16 payloads and two-channel files are refused with the reference's own messages (gridvolume.cpp:243-258), not misread
+    for enc, ch, msg in ((2, 1, "float16 volumes are not yet supported"), (1, 2, r"unsupported float32 volume data file \(2 channels, only 1 and 3"),
+                         (3, 2, "unsupported uint8 volume data file"), (4, 3, "quantized-direction")):
         (tmp_path / "f16.vol").write_bytes(b"VOL\x03" + struct.pack("<iiiii", enc, 2, 2, 2, ch) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + b"\0" * 96)
-        with pytest.raises(mer.MerError, match="are supported on this path"):
+        with pytest.raises(mer.MerError, match=msg):
             mer.fields.read_vol(tmp_path / "f16.vol")
 
 
