@@ -397,6 +397,13 @@ inline void coordinateSystem(const float a[3], float b[3], float c[3]) {
     b[2] = c[0] * a[1] - c[1] * a[0];
 }
 
+/* VolumetricPathTracer::miWeight, the power heuristic (volpath.cpp:430-433).  The floor only acts where both densities
+ * underflow (the reference divides 0 by 0 there). */
+inline float miWeight(float pdfA, float pdfB) {
+    pdfA *= pdfA; pdfB *= pdfB;
+    return pdfA / std::max(pdfA + pdfB, 1e-30f);
+}
+
 inline float hg_eval(float g, const float wi[3], const float wo[3]) {
     const float INV_FOURPI = 0.07957747154594766788f;
     float temp = 1.0f + g * g + 2.0f * g * (wi[0] * wo[0] + wi[1] * wo[1] + wi[2] * wo[2]);
@@ -1592,10 +1599,8 @@ void directLight(const Medium<F> &M, const mer_render_desc &R, const F *p1, cons
         scale *= (1.0f - Fr) * (C.exit.nb * C.exit.nb);
     }
     float geom = cosY * area / spread;
-    if (R.direct_connections == 2) { /* miWeight(pdf_emitter, pdf_phase), volpath.cpp:137-141, 430-433: both per solid angle at p1 */
-        const float pNee = 1.0f / std::max(geom, 1e-30f);
-        geom *= (pNee * pNee) / std::max(pNee * pNee + phase * phase, 1e-30f);
-    }
+    if (R.direct_connections == 2) /* miWeight(pdf_emitter, pdf_phase), volpath.cpp:137-141, 430-433: both per solid angle at p1 */
+        geom *= miWeight(1.0f / std::max(geom, 1e-30f), phase);
     float rad[3];
     for (int c = 0; c < 3; c++) {
         float T = (float) std::exp((double) (M.density ? -C.exit.tau : M.sigmaT[c] * (float) (-C.dist)));
@@ -1646,7 +1651,7 @@ float hitWeight(const Medium<F> &M, const mer_render_desc &R, const F *p1, const
     for (int i = 0; i < 3; i++) cosY += (float) C.revDirToP1[i] * (Nq[i] / area);
     cosY = std::abs(cosY);
     const float pNee = spread / std::max(cosY * area, 1e-20f);
-    return (phasePdf * phasePdf) / std::max(phasePdf * phasePdf + pNee * pNee, 1e-30f);
+    return miWeight(phasePdf, pNee);
 }
 
 /* light tracing: where the t = 1 connections of an emitter-side walk are splatted */
@@ -2186,6 +2191,9 @@ ORC_API(double, _d)
 ORC_CONNECT(float, _f)
 ORC_CONNECT(double, _d)
 
+extern "C" void orc_mi_weight(size_t n, const float *pdfA, const float *pdfB, float *out) {
+    for (size_t i = 0; i < n; i++) out[i] = miWeight(pdfA[i], pdfB[i]);
+}
 extern "C" void *orc_grid_create(const mer_volume_desc *d, const float *data) {
     GridVolume *g = new GridVolume();
     g->create(d, data);

@@ -505,6 +505,14 @@ class RefFilm:
         self.lib.ref_filter_table(C.c_int(ftype), _ptr(vals, C.c_float), C.byref(r), C.byref(s), C.byref(b))
         return vals, r.value, s.value, b.value
 
+    def mi_weight(self, pdf_a, pdf_b):
+        """VolumetricPathTracer::miWeight (volpath.cpp:430-433) compiled verbatim"""
+        a = np.ascontiguousarray(pdf_a, dtype=np.float32).reshape(-1)
+        b = np.ascontiguousarray(pdf_b, dtype=np.float32).reshape(-1)
+        out = np.zeros(a.shape[0], np.float32)
+        self.lib.ref_mi_weight(C.c_size_t(a.shape[0]), _ptr(a, C.c_float), _ptr(b, C.c_float), _ptr(out, C.c_float))
+        return out
+
     def camera_rays(self, origin, target, up, fov, W, H, sample_pos):
         """PerspectiveCameraImpl::sampleRay (perspective.cpp:247-269) behind Transform::lookAt / perspective and the reference's
         own 4x4 inversion -> ray origins and directions for pixel samples [n][2] (fractional pixel coordinates)"""
@@ -589,6 +597,14 @@ class Oracle:
     def grid_create(self, desc, data):
         data = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
         return C.c_void_p(self.lib.orc_grid_create(C.byref(desc), _ptr(data, C.c_float)))
+
+    def mi_weight(self, pdf_a, pdf_b):
+        """the restated power heuristic the MIS connections use (volpath.cpp:430-433)"""
+        a = np.ascontiguousarray(pdf_a, dtype=np.float32).reshape(-1)
+        b = np.ascontiguousarray(pdf_b, dtype=np.float32).reshape(-1)
+        out = np.zeros(a.shape[0], np.float32)
+        self.lib.orc_mi_weight(C.c_size_t(a.shape[0]), _ptr(a, C.c_float), _ptr(b, C.c_float), _ptr(out, C.c_float))
+        return out
 
     def grid_create_spectrum(self, desc, rgb):
         """3-channel grid, rgb[z, y, x, 3] (gridvolume.cpp:293-329, 401-421)"""

@@ -64,6 +64,11 @@ struct RefImageBlock { /* include/mitsuba/render/imageblock.h reduced to the dat
 #include "film_put_extract.inc" /* generated: both put() overloads */
 };
 
+/* VolumetricPathTracer (src/integrators/path/volpath.cpp) reduced to its MIS weight */
+struct RefVolPath {
+#include "volpath_miweight_extract.inc" /* generated: miWeight (volpath.cpp:430-433), the power heuristic of :137-141 and :164-173 */
+};
+
 #include "camera_util_extract.inc"      /* generated: degToRad (include/mitsuba/core/util.h:293) */
 #include "camera_transform_extract.inc" /* generated: Transform::perspective, Transform::lookAt */
 
@@ -112,6 +117,12 @@ static ReconstructionFilter *make_filter(int type) {
 }
 
 extern "C" {
+
+/* volpath's miWeight(pdfA, pdfB) for n pairs */
+void ref_mi_weight(size_t n, const float *pdfA, const float *pdfB, float *out) {
+    RefVolPath v;
+    for (size_t i = 0; i < n; i++) out[i] = v.miWeight(pdfA[i], pdfB[i]);
+}
 
 /* type: 0 box, 1 gaussian -> the 32 table values, radius, scale factor, border size */
 void ref_filter_table(int type, float *values32, float *radius, float *scaleFactor, int *borderSize) {

@@ -345,6 +345,19 @@ def test_oracle_grid_spectrum_lookup_bit_exact_vs_reference_golden(oracle32):
     assert np.array_equal(oracle32.grid_lookup_spectrum(g, p), G["u8"])
 
 
+@pytest.mark.skipif(not RefTrace.available(), reason="oracle/_ref/libmer_reftrace.so not built (needs /root/reference)")
+def test_oracle_mi_weight_bit_exact_vs_verbatim_reference(oracle32):
+    """SURVEY a21's only arithmetic of its own: VolumetricPathTracer::miWeight (volpath.cpp:430-433) compiled verbatim against the
+    power heuristic the restated MIS connections use - bit for bit over 12 decades of densities"""
+    rng = np.random.default_rng(43)
+    a = (10.0 ** rng.uniform(-6, 6, 100000)).astype(np.float32)
+    b = (10.0 ** rng.uniform(-6, 6, 100000)).astype(np.float32)
+    b[:100] = 0.0  # a delta on the other side: weight 1
+    ref = RefFilm().mi_weight(a, b)
+    got = oracle32.mi_weight(a, b)
+    assert np.all(ref[:100] == 1.0) and np.array_equal(got, ref)
+
+
 def _film_scene():
     rng = np.random.default_rng(41)
     W, H, n = 37, 29, 20000
